@@ -1,0 +1,256 @@
+#!/usr/bin/env python3
+"""Benchmark of the accelerated SaGePhy hot path (see BASELINE.json / DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference ...                       (CPU reference arm: the reference algorithm on host cores)
+
+One "step" = one pass of the whole path (sample -> label/prune -> emit, outputs resident in HBM) over one batch of
+synthetic replicates of BASELINE config C2: HostTreeGen, T=1, birth 5, death 0.05, 100-leaf window, leaf sampling 0.8.
+Replicates are sharded by index range across ranks (no data-path collective); the only collective is the NCCL
+all-reduce(sum) of the summary histograms.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "C2: HostTreeGen -min 100 -max 100 -p 0.8 -a 10000 1.0 5.0 0.05, Philox throughput mode, 4 output files/replicate"
+C2_ARGS = ["-s", "20260101", "-min", "100", "-max", "100", "-p", "0.8", "-a", "10000", "1.0", "5.0", "0.05", "bench"]
+METRIC, UNIT = "accepted trees/sec", "trees/s"
+
+# Algorithmic instruction mix of one vertex expansion of the sampler (DESIGN.md "K1 roofline"): warp-level instructions
+# on the FP64 pipe and on the INT/other pipes needed by Philox4x32-10 + two 53-bit uniforms + fdlibm log + divide + compare.
+ALG_FP64_INST_PER_VERTEX = 62.0
+ALG_INT_INST_PER_VERTEX = 118.0
+
+
+def clocks_sampler(stop, rows, gpu_index):
+    q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    while not stop.is_set():
+        try:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(gpu_index)],
+                                 capture_output=True, text=True, timeout=5).stdout.strip()
+            if out:
+                rows.append([x.strip() for x in out.split(",")])
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def summarise_clocks(rows):
+    if not rows:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+    sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+    mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+    reasons = set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for r in rows:
+        for k, nm in enumerate(names):
+            if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                reasons.add(nm)
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(rows)}
+
+
+def cpu_reference(n_trees, procs):
+    """Times the reference algorithm (CPU oracle, C++ port of the Java code path) on `procs` host processes."""
+    from concurrent.futures import ProcessPoolExecutor
+    per = max(1, n_trees // procs)
+    t0 = time.perf_counter()
+    with ProcessPoolExecutor(procs) as ex:
+        res = list(ex.map(_cpu_worker, [(i * per, per) for i in range(procs)]))
+    wall = time.perf_counter() - t0
+    ok = sum(r[0] for r in res)
+    return ok / wall, ok, wall, sum(r[1] for r in res)
+
+
+def _cpu_worker(job):
+    first, n = job
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_util import oracle_batch
+    sec, st = oracle_batch("HostTreeGen", C2_ARGS, first, n)
+    return int((st[:, 1] == 0).sum()), float(st[:, 7].sum())
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, cores)
+    per_step = max(procs * 4, 64)
+    for _ in range(args.warmup):
+        cpu_reference(max(procs, per_step // 8), procs)
+    t0 = time.perf_counter(); ok = 0
+    for _ in range(args.steps):
+        v, k, wall, verts = cpu_reference(per_step, procs)
+        ok += k
+    wall = time.perf_counter() - t0
+    value = ok / wall
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "replicates_per_step": per_step, "note": "reference-algorithm CPU restatement (C++ oracle, MT19937 stream, one process per host core); the Java jar cannot run here (no JVM)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": f"{per_step} replicates per step x {args.steps} steps of the same workload"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native")
+    ap.add_argument("--replicates", type=int, default=1_000_000, help="replicates per GPU per step")
+    ap.add_argument("--e2e-replicates", type=int, default=131072)
+    ap.add_argument("--cpu-sample", type=int, default=600, help="replicates timed on one host core for cpu_baseline")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import sagephy_b200 as sg
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = sg.Context(local)
+    n = args.replicates
+    W = max(args.warmup, 3); K = args.steps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i, n_rep, keep=True):
+        # global replicate ids: step-major, then rank-major index ranges
+        off = (i * world + rank) * n_rep
+        return ctx.run("HostTreeGen", C2_ARGS, n=n_rep, rng=sg.RNG_PHILOX, offset=off, keep_on_device=keep)
+
+    def merge(summary):
+        v = torch.from_numpy(summary.as_vector()).cuda()
+        if world > 1:
+            dist.all_reduce(v)          # NCCL: the only collective on the path (summary histograms)
+        return sg.Summary.from_vector(v.cpu().numpy())
+
+    # roofline denominators measured live (FP64 / INT issue rates)
+    peaks = ctx.issue_peaks()
+    for i in range(W):
+        b = step(1000 + i, n); merge(b.summary()); b.free()
+
+    stop = threading.Event(); rows = []
+    th = threading.Thread(target=clocks_sampler, args=(stop, rows, local), daemon=True); th.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    t0 = time.perf_counter()
+    tim = {"find_ms": 0.0, "build_ms": 0.0, "label_ms": 0.0, "emit_size_ms": 0.0, "emit_write_ms": 0.0, "total_ms": 0.0}
+    launches = 0; total = None; node_bytes = 0
+    for i in range(K):
+        b = step(i, n)
+        t = b.timings()
+        for k in tim:
+            tim[k] += t[k]
+        launches += int(t["kernel_launches"])
+        s = merge(b.summary())
+        total = s if total is None else sg.Summary.from_vector(total.as_vector() + s.as_vector())
+        b.free()
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    stop.set(); th.join(timeout=2)
+    # max over ranks of the timed region
+    tt = torch.tensor([wall, tim["total_ms"], tim["find_ms"], tim["emit_write_ms"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    wall_max, dev_ms, find_ms, emitw_ms = [float(x) for x in tt.cpu()]
+    trees = int(total.n_ok)
+    value = trees / wall_max
+
+    # end-to-end through the public API with host buffers: argv in, every output file's bytes + offsets out to pinned memory
+    ne = args.e2e_replicates
+    b = step(2000, ne); sizes = [b.stream_bytes(s) for s in range(8)]; b.free()
+    pinned = [torch.empty(int(sz * 1.05) + 4096, dtype=torch.uint8, pin_memory=True) if sz else None for sz in sizes]
+    offs = [torch.empty(ne + 1, dtype=torch.int64, pin_memory=True) for _ in range(8)]
+    e_steps = max(1, min(K, 3))
+    barrier(); t0 = time.perf_counter(); e_ok = 0; d2h = 0
+    for i in range(e_steps):
+        b = step(3000 + i, ne)
+        for s in range(8):
+            if pinned[s] is not None and b.stream_bytes(s):
+                d2h += b.copy_stream_into(s, pinned[s].data_ptr(), pinned[s].numel())
+                b.copy_offsets_into(s, offs[s].data_ptr()); d2h += 8 * (ne + 1)
+        st = b.rep_status; d2h += st.nbytes * 2
+        e_ok += int((st == 0).sum())
+        b.free()
+    barrier(); e_wall = time.perf_counter() - t0
+    ee = torch.tensor([e_wall], dtype=torch.float64, device="cuda"); eo = torch.tensor([e_ok, d2h], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ee, op=dist.ReduceOp.MAX); dist.all_reduce(eo)
+    e2e_value = float(eo[0]) / float(ee[0])
+    h2d_per_step = 4096          # argv-derived tables (host-tree tables, constant strings, Java math tables are resident per context)
+
+    if rank == 0:
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak, hbm_src = 6650.0, "fallback"
+        if os.path.exists(peaks_file):
+            try:
+                hbm_peak = float(json.load(open(peaks_file))["hbm_gbs"]); hbm_src = "measured"
+            except Exception:
+                pass
+        verts = float(total.vertices_sampled)
+        gverts = verts / (find_ms * 1e-3) * 1e-9 / world * world     # chip aggregate over ranks / max time
+        # issue-slot roofline of the sampler: time per vertex-warp is bounded below by each pipe's issue rate
+        r_fp64 = peaks["dfma_ginst_per_s"]; r_int = peaks["imad_ginst_per_s"]
+        t_vertex_warp = max(ALG_FP64_INST_PER_VERTEX / r_fp64, ALG_INT_INST_PER_VERTEX / r_int)     # ns per warp of 32 vertices
+        peak_gverts = 32.0 / t_vertex_warp * world
+        out_bytes = float(np.sum(total.out_bytes))
+        emit_alg_bytes = out_bytes + float(total.event_counts.sum()) * (80 + 16)      # node records + order arrays read once, text written once
+        emit_gbs = emit_alg_bytes / (emitw_ms * 1e-3) * 1e-9
+        cpu_n = args.cpu_sample
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle_util import oracle_batch
+        sec, st = oracle_batch("HostTreeGen", C2_ARGS, 0, cpu_n)
+        cpu_val = float((st[:, 1] == 0).sum()) / sec
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * wall_max / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "replicates_per_gpu_per_step": n, "timing": "wall clock between barrier+cuda synchronize, max over ranks; "
+                       "device CUDA-event time in device_ms_per_step", "l2": "inputs are generated on the fly; outputs (>=20 GB/step) exceed L2",
+                       "rng": "philox4x32-10"},
+            "device_ms_per_step": dev_ms / K,
+            "phase_ms_per_step": {k: v / K for k, v in tim.items()},
+            "gpu_launches": launches,
+            "attempts_per_tree": float(total.attempts_total) / max(trees, 1), "vertices_per_tree": verts / max(trees, 1),
+            "out_bytes_per_tree": out_bytes / max(trees, 1), "n_failed": int(total.n_failed),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": int(float(eo[1]) / e_steps / world),
+                    "replicates_per_gpu_per_step": ne, "steps": e_steps},
+            "roofline": {"bound": "issue", "kernel": "k_bd_find", "achieved": gverts, "peak": peak_gverts, "unit": "Gvertex/s", "frac": gverts / peak_gverts,
+                         "traffic": None, "alg_inst_per_vertex": {"fp64": ALG_FP64_INST_PER_VERTEX, "int": ALG_INT_INST_PER_VERTEX},
+                         "measured_issue_peaks_ginst_per_s": peaks, "share_of_step": find_ms / dev_ms},
+            "roofline_emit": {"bound": "hbm", "kernel": "k_emit<write>", "achieved": emit_gbs, "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
+                              "frac": emit_gbs / hbm_peak, "traffic": None, "share_of_step": emitw_ms / dev_ms},
+            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"{cpu_n} replicates of the same workload (MT19937 stream), single thread, C++ restatement of the Java path"},
+            "clocks": summarise_clocks(rows),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

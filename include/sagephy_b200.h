@@ -1,0 +1,131 @@
+/*
+ * sagephy_b200 — C ABI of the B200-native batched phylogeny simulator.
+ *
+ * This is the drop-in boundary for SaGePhy's data-parallel hot path. The reference (Java, no FFI of its own) exposes the
+ * path through two in-JVM seams and the process-level CLI; each entry point below names the seam it replaces
+ * (paths relative to src/main/java/uc/sgp/sagephy/ of the reference):
+ *
+ *   sgp_app_run          <- the CLI contract  `java -jar sagephy.jar <App> [options] <positionals>`:
+ *                           apps/SaGePhyStarter.java:75-103 (first token = app), apps/SaGePhy/HostTreeGen.java:25-116,
+ *                           GuestTreeGen.java:21-107, DomainTreeGen.java:21-107, BranchRelaxer.java:48-141.
+ *                           Same options, defaults (from the code) and positional counts, plus a replicate count.
+ *   sgp_treegen_run      <- UnprunedGuestTreeCreator (apps/SaGePhy/UnprunedGuestTreeCreator.java:17-59) driven by
+ *                           GuestTreeMachina.sampleGuestTree (apps/SaGePhy/GuestTreeMachina.java:69-115), followed by
+ *                           PruningHelper / GuestVertex.setMeta / NewickTreeWriter / getInfo / getSigma / getLeafMap.
+ *   sgp_relax_run        <- RateModel.getRates (apps/SaGePhy/RateModel.java:13-29) + BranchRelaxer.main's retry loop
+ *                           and rescaling (apps/SaGePhy/BranchRelaxer.java:94-101,148-197).
+ *
+ * All pointers are plain host pointers; no CUDA or torch types cross the boundary. Calls block until the outputs are
+ * resident (in HBM for the *_device accessors, in pinned host memory for the host accessors). There is no CPU fallback:
+ * every entry point fails with SGP_ERR_NO_DEVICE if no CUDA device is usable.
+ */
+#ifndef SAGEPHY_B200_H
+#define SAGEPHY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sgp_context sgp_context;
+typedef struct sgp_batch sgp_batch;
+
+typedef enum {
+    SGP_OK = 0,
+    SGP_ERR_NO_DEVICE = 1,      /* no usable CUDA device / CUDA runtime failure */
+    SGP_ERR_INVALID_ARGUMENT = 2,
+    SGP_ERR_PARSE = 3,          /* malformed Newick / number */
+    SGP_ERR_UNSUPPORTED = 4,    /* e.g. -hybrid host graphs (out of scope) */
+    SGP_ERR_INTERNAL = 5,
+    SGP_USAGE = 6               /* wrong positional count or -h: usage text is in the batch's stdout */
+} sgp_status;
+
+/* per-replicate status (GuestTreeMachina retry budget: apps/SaGePhy/MaxAttemptsException.java:8-20) */
+typedef enum { SGP_REP_OK = 0, SGP_REP_MAX_ATTEMPTS = 1, SGP_REP_NODE_OVERFLOW = 2, SGP_REP_STACK_OVERFLOW = 3, SGP_REP_MODEL_ERROR = 4 } sgp_rep_status;
+
+typedef enum { SGP_RNG_PHILOX = 0, SGP_RNG_MT_REPLAY = 1 } sgp_rng_mode;
+
+/* output streams of a tree-generator batch (file suffixes of the reference in the comments) */
+typedef enum {
+    SGP_STREAM_UNPRUNED_TREE = 0,     /* .unpruned.tree        */
+    SGP_STREAM_PRUNED_TREE = 1,       /* .pruned.tree          */
+    SGP_STREAM_UNPRUNED_INFO = 2,     /* .unpruned.info        */
+    SGP_STREAM_PRUNED_INFO = 3,       /* .pruned.info          */
+    SGP_STREAM_UNPRUNED_G2H = 4,      /* .unpruned.guest2host  */
+    SGP_STREAM_PRUNED_G2H = 5,        /* .pruned.guest2host    */
+    SGP_STREAM_UNPRUNED_LEAFMAP = 6,  /* .unpruned.leafmap     */
+    SGP_STREAM_PRUNED_LEAFMAP = 7,    /* .pruned.leafmap       */
+    SGP_STREAM_COUNT = 8
+} sgp_stream;
+
+/* Batch extension of the reference CLI (everything else in argv is the reference's own grammar). */
+typedef struct {
+    int64_t n_replicates;       /* number of independent replicates (reference: 1 per JVM launch) */
+    int64_t replicate_offset;   /* global index of this call's first replicate (multi-GPU sharding by index range) */
+    int32_t rng_mode;           /* sgp_rng_mode; MT replay: replicate i == reference run with -s (seed + i) */
+    uint32_t stream_mask;       /* bit s set = emit stream s; 0 = whatever the reference would write for these options */
+    int32_t keep_on_device;     /* 1: leave stream bytes in HBM only (host accessors then copy lazily) */
+    int32_t reserved;
+} sgp_batch_opts;
+
+/* summary counters of a batch (merged across GPUs with an allreduce(sum) by the caller) */
+#define SGP_HIST_LEAF_BINS 1025
+typedef struct {
+    int64_t n_ok, n_failed;
+    int64_t attempts_total;           /* sum of "Attempts:" over replicates */
+    int64_t vertices_sampled;         /* vertices created over all attempts (algorithmic work of the sampler) */
+    int64_t event_counts[17];         /* unpruned trees, indexed by GuestVertex.Event ordinal */
+    int64_t leaf_hist[SGP_HIST_LEAF_BINS];   /* sampled leaves per accepted tree (last bin = overflow) */
+    int64_t out_bytes[SGP_STREAM_COUNT];
+} sgp_summary;
+
+typedef struct {
+    double find_ms, build_ms, label_ms, emit_size_ms, emit_write_ms, d2h_ms, total_ms;   /* CUDA-event times of the last run */
+    int64_t kernel_launches;
+} sgp_timings;
+
+sgp_status sgp_context_create(int device, sgp_context** out);
+void sgp_context_destroy(sgp_context* ctx);
+const char* sgp_last_error(const sgp_context* ctx);
+
+/* Runs `<app> argv...` for opts->n_replicates replicates. app = "HostTreeGen" | "GuestTreeGen" | "DomainTreeGen" |
+ * "BranchRelaxer". Returns SGP_USAGE (with a batch holding the usage text) exactly when the reference would print usage. */
+sgp_status sgp_app_run(sgp_context* ctx, const char* app, int argc, const char* const* argv, const sgp_batch_opts* opts, sgp_batch** out);
+
+/* Batch accessors. Stream s is the concatenation over replicates, replicate i occupying bytes [offsets[i], offsets[i+1]). */
+int64_t sgp_batch_n(const sgp_batch* b);
+const char* sgp_batch_stream_data(sgp_batch* b, int stream);             /* host pointer (pinned), copies from HBM on first use */
+const void* sgp_batch_stream_device_data(const sgp_batch* b, int stream);/* device pointer */
+const uint64_t* sgp_batch_stream_offsets(sgp_batch* b, int stream);      /* n+1 entries, host */
+/* Copies stream bytes / the n+1 offsets from HBM into a caller-owned host buffer (pinned memory gives full PCIe rate). */
+sgp_status sgp_batch_copy_stream(sgp_batch* b, int stream, void* dst, uint64_t dst_capacity);
+sgp_status sgp_batch_copy_offsets(sgp_batch* b, int stream, uint64_t* dst /* n+1 */);
+uint64_t sgp_batch_stream_bytes(const sgp_batch* b, int stream);
+const char* sgp_batch_stream_suffix(const sgp_batch* b, int stream);     /* file suffix the reference uses, "" if unused */
+const int32_t* sgp_batch_status(sgp_batch* b);                           /* n entries, sgp_rep_status */
+const int32_t* sgp_batch_attempts(sgp_batch* b);                         /* n entries, value of "Attempts:" */
+const int32_t* sgp_batch_sampled_leaves(sgp_batch* b);                   /* n entries */
+const double* sgp_batch_root_times(sgp_batch* b);                        /* n entries: time of the pruned tree's root */
+const double* sgp_batch_total_times(sgp_batch* b);                       /* n entries: total unpruned branch time (unrounded) */
+const int32_t* sgp_batch_event_counts(sgp_batch* b);                     /* n x 17, unpruned trees */
+const char* sgp_batch_stdout(const sgp_batch* b);                        /* what the reference prints to stdout (usage, -q trees) */
+const char* sgp_batch_stderr(const sgp_batch* b);
+const char* sgp_batch_out_prefix(const sgp_batch* b);                    /* the <out prefix> positional ("" with -q) */
+void sgp_batch_summary(sgp_batch* b, sgp_summary* out);
+void sgp_batch_timings(const sgp_batch* b, sgp_timings* out);
+/* Writes the files the reference would write (n == 1: identical names; n > 1: one file per stream, replicates concatenated). */
+sgp_status sgp_batch_write_files(sgp_batch* b);
+void sgp_batch_free(sgp_batch* b);
+
+/* Probes used by the parity tests: run the device implementations of the Java-exact primitives on `n` inputs. */
+sgp_status sgp_probe_double_to_string(sgp_context* ctx, const double* v, int64_t n, char* out /* n*32 bytes, NUL padded */);
+sgp_status sgp_probe_math(sgp_context* ctx, int fn /* 0 log, 1 log10, 2 exp, 3 round8 */, const double* v, int64_t n, double* out);
+sgp_status sgp_probe_mt(sgp_context* ctx, int64_t seed, int64_t n_words, uint32_t* out_words);
+/* FP64/INT issue-rate microbenchmarks (roofline denominators for the sampler); returns giga-instructions per second. */
+sgp_status sgp_probe_issue_peaks(sgp_context* ctx, double* dfma_ginst, double* imad_ginst, double* dmul_dep_ginst);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,179 @@
+// Reference command-line grammar -> engine configuration.
+//
+// Mirrors (src/main/java/uc/sgp/sagephy/apps/SaGePhy/): HostTreeGenParameters.java:15-123, HostTreeGen.java:25-58,
+// GuestTreeGenParameters.java:24-164, GuestTreeGen.java:21-44. Defaults are the ones in the code (e.g. -db defaults to
+// "simple", -vph to true, the host stem to 0 -> 1e-64), not the README's. Options may appear anywhere; Boolean options take
+// no value; a token starting with '-' that is not an option and not a number is an error, as in JCommander.
+#include <cstdlib>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include "engine.hpp"
+#include "hostfmt.hpp"
+
+namespace sgp {
+
+namespace {
+
+struct Opt { const char* shortn; const char* longn; int arity; };
+
+struct Parsed {
+    std::map<std::string, std::vector<std::string>> val;   // keyed by short name
+    std::map<std::string, int> val_index;                  // index in args of the (last) value token
+    std::vector<std::string> positional;
+    bool on(const char* k) const { return val.count(k) != 0; }
+    std::string str(const char* k, const char* dflt) const { auto it = val.find(k); return it == val.end() ? std::string(dflt) : it->second.back(); }
+};
+
+Parsed scan(const std::vector<std::string>& args, const Opt* table, int n_opts) {
+    Parsed p;
+    for (size_t i = 0; i < args.size(); ++i) {
+        const std::string& tok = args[i];
+        const Opt* o = nullptr;
+        for (int k = 0; k < n_opts; ++k) if (tok == table[k].shortn || tok == table[k].longn) { o = &table[k]; break; }
+        if (o) {
+            if (o->arity == 0) { p.val[o->shortn].push_back("true"); continue; }
+            if (i + o->arity >= args.size()) throw SgpError("Expected a value after parameter " + tok);
+            for (int k = 0; k < o->arity; ++k) { p.val[o->shortn].push_back(args[++i]); p.val_index[o->shortn] = (int)i; }
+            continue;
+        }
+        const bool looks_numeric = tok.size() > 1 && tok[0] == '-' && ((tok[1] >= '0' && tok[1] <= '9') || tok[1] == '.');
+        if (tok.size() > 1 && tok[0] == '-' && !looks_numeric) throw SgpError("Unknown option: " + tok);
+        p.positional.push_back(tok);
+    }
+    return p;
+}
+
+double to_double(const std::string& s) {
+    size_t b = s.find_first_not_of(" \t\r\n"), e = s.find_last_not_of(" \t\r\n");
+    if (b == std::string::npos) throw SgpError("NumberFormatException: empty String");
+    std::string t = s.substr(b, e - b + 1);
+    char* end = nullptr; double v = std::strtod(t.c_str(), &end);
+    if (end == t.c_str() || *end) throw SgpError("NumberFormatException: For input string: \"" + s + "\"");
+    return v;
+}
+int to_int(const std::string& s) {
+    char* end = nullptr; long v = std::strtol(s.c_str(), &end, 10);
+    if (end == s.c_str() || *end) throw SgpError("NumberFormatException: For input string: \"" + s + "\"");
+    return (int)v;
+}
+long long to_i64(const std::string& s) {
+    char* end = nullptr; long long v = std::strtoll(s.c_str(), &end, 10);
+    if (end == s.c_str() || *end) throw SgpError("seed must be an integer in the signed 64-bit range: \"" + s + "\"");
+    return v;
+}
+std::string java_trim(const std::string& s) {
+    size_t b = 0, e = s.size();
+    while (b < e && (unsigned char)s[b] <= ' ') ++b;
+    while (e > b && (unsigned char)s[e - 1] <= ' ') --e;
+    return s.substr(b, e - b);
+}
+std::vector<int> load_sizes(const std::string& path) {
+    std::ifstream f(path);
+    if (!f) throw SgpError("FileNotFoundException: " + path);
+    std::vector<int> v; std::string line;
+    while (std::getline(f, line)) v.push_back(to_int(line));
+    if (v.empty()) throw SgpError("leaf sizes file is empty: " + path);
+    return v;
+}
+long long random_seed() {
+    unsigned long long v = 0;
+    std::ifstream f("/dev/urandom", std::ios::binary);
+    if (f) f.read((char*)&v, sizeof v);
+    return (long long)(v >> 2);     // keep seed + replicate index inside int64
+}
+
+const Opt kHostOpts[] = {
+    {"-h", "--help", 0}, {"-q", "--quiet", 0}, {"-s", "--seed", 1}, {"-min", "--min-leaves", 1}, {"-max", "--max-leaves", 1},
+    {"-sizes", "--leaf-sizes-file", 1}, {"-nox", "--no-auxiliary-tags", 0}, {"-p", "--leaf-sampling-probability", 1},
+    {"-bi", "--start-with-bifurcation", 0}, {"-a", "--max-attempts", 1}, {"-stem", "--override-stem", 1}, {"-vp", "--vertex-prefix", 1}};
+
+const Opt kGuestOpts[] = {
+    {"-h", "--help", 0}, {"-q", "--quiet", 0}, {"-s", "--seed", 1}, {"-min", "--min-leaves", 1}, {"-max", "--max-leaves", 1},
+    {"-minper", "--min-leaves-per-host-leaf", 1}, {"-maxper", "--max-leaves-per-host-leaf", 1}, {"-sizes", "--leaf-sizes-file", 1},
+    {"-nox", "--no-auxiliary-tags", 0}, {"-p", "--leaf-sampling-probability", 1}, {"-mpr", "--enforce-most-parsimonious-reconciliation", 0},
+    {"-a", "--max-attempts", 1}, {"-stem", "--override-host-stem", 1}, {"-vp", "--vertex-prefix", 1}, {"-vph", "--vertex-prefix-host-map", 0},
+    {"-hybrid", "--hybrid-host-graph", 3}, {"-rt", "--replacing-transfers", 1}, {"-db", "--distance-bias", 1}, {"-dbr", "--distance-bias-rate", 1},
+    {"-gb", "--gene-birth-sampling", 0}, {"-gbc", "--gene-birth-coefficient", 1}};
+
+void common_window(const Parsed& p, TreeGenConfig& cfg) {
+    cfg.P.min_leaves = to_int(p.str("-min", "2")); cfg.P.max_leaves = to_int(p.str("-max", "1000")); cfg.P.max_attempts = to_int(p.str("-a", "10000"));
+    if (p.on("-sizes")) cfg.sizes = load_sizes(p.str("-sizes", ""));
+    cfg.exclude_meta = p.on("-nox"); cfg.quiet = p.on("-q");
+    if (p.on("-s")) { cfg.has_seed = true; cfg.seed = to_i64(p.str("-s", "0")); cfg.seed_arg_index = p.val_index.at("-s"); }
+    else { cfg.has_seed = false; cfg.seed = random_seed(); cfg.seed_arg_index = -1; }
+}
+
+std::string slurp(const std::string& path) { std::ifstream f(path, std::ios::binary); std::stringstream ss; ss << f.rdbuf(); return ss.str(); }
+bool exists(const std::string& path) { std::ifstream f(path); return (bool)f; }
+std::string file_name(const std::string& path) { size_t k = path.find_last_of('/'); return k == std::string::npos ? path : path.substr(k + 1); }
+
+}  // namespace
+
+void parse_treegen_app(const std::string& app, const std::vector<std::string>& args, TreeGenConfig& cfg, AppResult& res) {
+    cfg.args = args;
+    if (app == "HostTreeGen") {
+        Parsed p = scan(args, kHostOpts, (int)(sizeof kHostOpts / sizeof kHostOpts[0]));
+        const size_t want = p.on("-q") ? 3 : 4;
+        if (args.empty() || p.on("-h") || p.positional.size() != want) {
+            res.status = 6;
+            res.out_text = "Usage:\n    java -jar sagephy-X.Y.Z.jar HostTreeGen [options] <time interval> <birth rate> <death rate> <out prefix>\n"
+                           "    (sagephy_b200: same options plus the batch options of sgp_batch_opts / `sagephy -n <replicates> -rng <philox|mt-replay>`)\n\n";
+            return;
+        }
+        cfg.app = 0;
+        common_window(p, cfg);
+        const double T = to_double(p.positional[0]);
+        if (T <= 0.0) throw SgpError("Invalid time interval.");
+        const std::string Ts = jdouble(T);
+        const bool bi = p.on("-bi");
+        const std::string newick = bi ? "(H0:" + Ts + ",H1:" + Ts + "):0.0;" : "H0:" + Ts + ";";
+        cfg.host.build(parse_newick(newick), nullptr, nullptr, false);
+        cfg.P.lambda = to_double(p.positional[1]); if (cfg.P.lambda < 0) throw SgpError("Invalid rate.");
+        cfg.P.mu = to_double(p.positional[2]); if (cfg.P.mu < 0) throw SgpError("Invalid rate.");
+        cfg.P.tau = 0; cfg.P.theta = 0; cfg.P.bias = 1 /* "" is treated as "simple"; unused with tau = 0 */; cfg.P.bias_rate = 1.0;
+        cfg.P.do_gene_birth = false; cfg.P.gene_birth = 0; cfg.P.ishost = true;
+        cfg.P.rho = to_double(p.str("-p", "1.0"));
+        if (cfg.P.rho < 0) throw SgpError("Invalid leaf sampling prob.");
+        if (cfg.P.rho > 1) throw SgpError("Cannot have leaf sampling probability outside [0,1].");
+        cfg.P.minper = bi ? 1 : 0; cfg.P.maxper = 2147483647;
+        cfg.vertex_prefix = p.str("-vp", "H"); cfg.append_sigma = false; cfg.is_species = true;
+        if (p.on("-stem")) { cfg.has_stem_override = true; cfg.stem_override = to_double(p.str("-stem", "0")); }
+        cfg.out_prefix = cfg.quiet ? std::string() : java_trim(p.positional[3]);
+        return;
+    }
+    if (app == "GuestTreeGen") {
+        Parsed p = scan(args, kGuestOpts, (int)(sizeof kGuestOpts / sizeof kGuestOpts[0]));
+        const size_t want = p.on("-q") ? 4 : 5;
+        if (args.empty() || p.on("-h") || p.positional.size() != want) {
+            res.status = 6;
+            res.out_text = "Usage:\n    java -jar sagephy-X.Y.Z.jar GuestTreeGen [options] <host tree> <dup rate> <loss rate> <trans rate> <out prefix>\n"
+                           "    (sagephy_b200: same options plus the batch options of sgp_batch_opts / `sagephy -n <replicates> -rng <philox|mt-replay>`)\n\n";
+            return;
+        }
+        if (p.on("-hybrid")) { res.status = 4; res.err_text = "-hybrid host graphs are outside the accelerated path (SURVEY.md section 2, row 17)\n"; return; }
+        cfg.app = 1;
+        common_window(p, cfg);
+        cfg.P.minper = to_int(p.str("-minper", "0")); cfg.P.maxper = to_int(p.str("-maxper", "10"));
+        cfg.P.lambda = to_double(p.positional[1]); cfg.P.mu = to_double(p.positional[2]); cfg.P.tau = to_double(p.positional[3]);
+        if (cfg.P.lambda < 0 || cfg.P.mu < 0 || cfg.P.tau < 0) throw SgpError("Cannot have rate less than 0.");
+        cfg.P.theta = to_double(p.str("-rt", "0.5"));
+        const std::string db = p.str("-db", "simple");
+        cfg.P.bias = db == "none" ? 0 : db == "exponential" ? 2 : 1;
+        cfg.P.bias_rate = to_double(p.str("-dbr", "1.0"));
+        cfg.P.do_gene_birth = p.on("-gb"); cfg.P.gene_birth = to_double(p.str("-gbc", "1.0")); cfg.P.ishost = false;
+        cfg.P.rho = to_double(p.str("-p", "1.0"));
+        if (cfg.P.rho < 0 || cfg.P.rho > 1) throw SgpError("Cannot have leaf sampling probability outside [0,1].");
+        cfg.vertex_prefix = p.str("-vp", "G"); cfg.append_sigma = true; cfg.is_species = false;
+        const double stem = p.on("-stem") ? to_double(p.str("-stem", "0")) : 0.0;
+        const std::string& hostarg = p.positional[0];
+        if (exists(hostarg)) { std::string nm = file_name(hostarg); cfg.host.build(parse_newick(slurp(hostarg)), &nm, &stem, cfg.P.bias != 0 && cfg.P.tau > 0); }
+        else cfg.host.build(parse_newick(hostarg), nullptr, &stem, cfg.P.bias != 0 && cfg.P.tau > 0);
+        cfg.out_prefix = cfg.quiet ? std::string() : java_trim(p.positional[4]);
+        return;
+    }
+    res.status = 4;
+    res.err_text = "Unknown or not yet accelerated application: " + app + "\n";
+}
+
+}  // namespace sgp

@@ -1,0 +1,161 @@
+// C ABI (include/sagephy_b200.h) over the C++ engine.
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include "../../include/sagephy_b200.h"
+#include "engine.hpp"
+
+using namespace sgp;
+
+struct sgp_context { std::unique_ptr<Context> ctx; std::string last_error; };
+struct sgp_batch { Batch b; std::string stdout_cache; bool stdout_ready = false; };
+
+namespace { thread_local std::string g_create_error; }
+
+extern "C" {
+
+sgp_status sgp_context_create(int device, sgp_context** out) {
+    if (!out) return SGP_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    try {
+        auto* c = new sgp_context();
+        c->ctx.reset(new Context(device));
+        *out = c;
+        return SGP_OK;
+    } catch (std::exception& e) {
+        g_create_error = e.what();
+        std::fprintf(stderr, "sagephy_b200: %s\n", e.what());
+        return SGP_ERR_NO_DEVICE;
+    }
+}
+void sgp_context_destroy(sgp_context* ctx) { delete ctx; }
+const char* sgp_last_error(const sgp_context* ctx) { return ctx ? ctx->last_error.c_str() : g_create_error.c_str(); }
+
+sgp_status sgp_app_run(sgp_context* ctx, const char* app, int argc, const char* const* argv, const sgp_batch_opts* opts, sgp_batch** out) {
+    if (!ctx || !app || !out || argc < 0) return SGP_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    sgp_batch_opts o{}; if (opts) o = *opts; if (o.n_replicates <= 0) o.n_replicates = 1;
+    std::vector<std::string> args; for (int i = 0; i < argc; ++i) args.emplace_back(argv[i] ? argv[i] : "");
+    auto* b = new sgp_batch();
+    try {
+        TreeGenConfig cfg; AppResult res;
+        parse_treegen_app(app, args, cfg, res);
+        b->b.out_text = res.out_text; b->b.err_text = res.err_text;
+        if (res.status == 6) { *out = b; return SGP_USAGE; }
+        if (res.status != 0) { ctx->last_error = res.err_text; *out = b; return (sgp_status)res.status; }
+        if (o.rng_mode == SGP_RNG_MT_REPLAY && !cfg.has_seed) {
+            // the reference would seed from /dev/random; replay of an unknown seed is meaningless but harmless
+        }
+        BatchOpts bo; bo.n = o.n_replicates; bo.offset = o.replicate_offset; bo.rng_mode = o.rng_mode; bo.stream_mask = o.stream_mask; bo.keep_on_device = o.keep_on_device != 0;
+        ctx->ctx->run_treegen(cfg, bo, b->b);
+        *out = b;
+        return SGP_OK;
+    } catch (SgpError& e) {
+        ctx->last_error = e.what();
+        b->b.err_text += std::string(e.what()) + "\n\nUse option -h or --help to show usage.\n";
+        *out = b;
+        const std::string w = e.what();
+        if (w.find("CUDA") != std::string::npos) return SGP_ERR_NO_DEVICE;
+        if (w.find("Newick") != std::string::npos || w.find("NumberFormat") != std::string::npos) return SGP_ERR_PARSE;
+        return SGP_ERR_INVALID_ARGUMENT;
+    } catch (std::exception& e) {
+        ctx->last_error = e.what(); b->b.err_text += e.what(); *out = b;
+        return SGP_ERR_INTERNAL;
+    }
+}
+
+int64_t sgp_batch_n(const sgp_batch* b) { return b ? b->b.n : 0; }
+const char* sgp_batch_stream_data(sgp_batch* b, int s) { return b ? b->b.stream_host(s) : nullptr; }
+const void* sgp_batch_stream_device_data(const sgp_batch* b, int s) { return (b && s >= 0 && s < 8) ? b->b.d_stream[s] : nullptr; }
+const uint64_t* sgp_batch_stream_offsets(sgp_batch* b, int s) {
+    if (!b || s < 0 || s >= 8 || !b->b.d_offsets) return nullptr;
+    b->b.fetch_offsets();
+    return (const uint64_t*)(b->b.h_offsets.data() + (size_t)s * (b->b.n + 1));
+}
+sgp_status sgp_batch_copy_stream(sgp_batch* b, int s, void* dst, uint64_t cap) {
+    if (!b || s < 0 || s >= 8 || !dst) return SGP_ERR_INVALID_ARGUMENT;
+    if (cap < b->b.stream_bytes[s]) return SGP_ERR_INVALID_ARGUMENT;
+    return b->b.copy_stream_to(s, dst) ? SGP_OK : SGP_ERR_NO_DEVICE;
+}
+sgp_status sgp_batch_copy_offsets(sgp_batch* b, int s, uint64_t* dst) {
+    if (!b || s < 0 || s >= 8 || !dst || !b->b.d_offsets) return SGP_ERR_INVALID_ARGUMENT;
+    return b->b.copy_offsets_to(s, (unsigned long long*)dst) ? SGP_OK : SGP_ERR_NO_DEVICE;
+}
+uint64_t sgp_batch_stream_bytes(const sgp_batch* b, int s) { return (b && s >= 0 && s < 8) ? b->b.stream_bytes[s] : 0; }
+const char* sgp_batch_stream_suffix(const sgp_batch* b, int s) { return (b && s >= 0 && s < 8) ? b->b.suffix[s] : ""; }
+const int32_t* sgp_batch_status(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_info(); return b->b.status.data(); }
+const int32_t* sgp_batch_attempts(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_info(); return b->b.attempts.data(); }
+const int32_t* sgp_batch_sampled_leaves(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_info(); return b->b.sampled.data(); }
+const double* sgp_batch_root_times(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_info(); return b->b.root_time.data(); }
+const double* sgp_batch_total_times(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_info(); return b->b.total_time.data(); }
+const int32_t* sgp_batch_event_counts(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_info(); return b->b.events.data(); }
+
+const char* sgp_batch_stdout(const sgp_batch* cb) {
+    sgp_batch* b = const_cast<sgp_batch*>(cb);
+    if (!b) return "";
+    if (!b->stdout_ready) {
+        b->stdout_cache = b->b.out_text;
+        if (b->b.quiet && b->b.d_stream[1]) { const char* t = b->b.stream_host(1); if (t) b->stdout_cache.append(t, b->b.stream_bytes[1]); }
+        b->stdout_ready = true;
+    }
+    return b->stdout_cache.c_str();
+}
+const char* sgp_batch_stderr(const sgp_batch* b) { return b ? b->b.err_text.c_str() : ""; }
+const char* sgp_batch_out_prefix(const sgp_batch* b) { return b ? b->b.out_prefix.c_str() : ""; }
+
+void sgp_batch_summary(sgp_batch* b, sgp_summary* out) {
+    if (!b || !out) return;
+    const Summary& s = b->b.summary;
+    out->n_ok = s.n_ok; out->n_failed = s.n_failed; out->attempts_total = s.attempts_total; out->vertices_sampled = s.vertices_sampled;
+    for (int i = 0; i < 17; ++i) out->event_counts[i] = s.event_counts[i];
+    for (int i = 0; i < SGP_HIST_LEAF_BINS; ++i) out->leaf_hist[i] = s.leaf_hist[i];
+    for (int i = 0; i < 8; ++i) out->out_bytes[i] = s.out_bytes[i];
+}
+void sgp_batch_timings(const sgp_batch* b, sgp_timings* out) {
+    if (!b || !out) return;
+    const Timings& t = b->b.timings;
+    out->find_ms = t.find_ms; out->build_ms = t.build_ms; out->label_ms = t.label_ms; out->emit_size_ms = t.emit_size_ms; out->emit_write_ms = t.emit_write_ms;
+    out->d2h_ms = t.d2h_ms; out->total_ms = t.total_ms; out->kernel_launches = t.launches;
+}
+
+sgp_status sgp_batch_write_files(sgp_batch* b) {
+    if (!b) return SGP_ERR_INVALID_ARGUMENT;
+    if (b->b.quiet || !b->b.d_offsets) return SGP_OK;
+    b->b.fetch_info();
+    bool all_failed = true; for (long long i = 0; i < b->b.n; ++i) if (b->b.status[i] == 0) all_failed = false;
+    for (int s = 0; s < 8; ++s) {
+        if (!b->b.suffix[s][0]) continue;
+        std::string sfx = b->b.suffix[s];
+        if (all_failed) {
+            // the reference writes only the failure note: <prefix>.info (HostTreeGen.java:65) / <prefix>.pruned.info (GuestTreeGen.java:50)
+            if (s != SGP_STREAM_PRUNED_INFO) continue;
+            if (b->b.app == 0) sfx = ".info";
+        }
+        const char* data = b->b.stream_host(s);
+        if (!data) return SGP_ERR_INTERNAL;
+        std::ofstream f(b->b.out_prefix + sfx, std::ios::binary);
+        if (!f) return SGP_ERR_INVALID_ARGUMENT;
+        f.write(data, (std::streamsize)b->b.stream_bytes[s]);
+    }
+    return SGP_OK;
+}
+void sgp_batch_free(sgp_batch* b) { delete b; }
+
+sgp_status sgp_probe_double_to_string(sgp_context* ctx, const double* v, int64_t n, char* out) {
+    if (!ctx) return SGP_ERR_INVALID_ARGUMENT;
+    try { ctx->ctx->probe_d2s(v, n, out); return SGP_OK; } catch (std::exception& e) { ctx->last_error = e.what(); return SGP_ERR_NO_DEVICE; }
+}
+sgp_status sgp_probe_math(sgp_context* ctx, int fn, const double* v, int64_t n, double* out) {
+    if (!ctx) return SGP_ERR_INVALID_ARGUMENT;
+    try { ctx->ctx->probe_math(fn, v, n, out); return SGP_OK; } catch (std::exception& e) { ctx->last_error = e.what(); return SGP_ERR_NO_DEVICE; }
+}
+sgp_status sgp_probe_mt(sgp_context* ctx, int64_t seed, int64_t n_words, uint32_t* out) {
+    if (!ctx) return SGP_ERR_INVALID_ARGUMENT;
+    try { ctx->ctx->probe_mt(seed, n_words, out); return SGP_OK; } catch (std::exception& e) { ctx->last_error = e.what(); return SGP_ERR_NO_DEVICE; }
+}
+sgp_status sgp_probe_issue_peaks(sgp_context* ctx, double* dfma, double* imad, double* ddep) {
+    if (!ctx) return SGP_ERR_INVALID_ARGUMENT;
+    try { ctx->ctx->probe_issue(dfma, imad, ddep); return SGP_OK; } catch (std::exception& e) { ctx->last_error = e.what(); return SGP_ERR_NO_DEVICE; }
+}
+
+}  // extern "C"

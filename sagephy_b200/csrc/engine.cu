@@ -1,0 +1,460 @@
+// Host orchestration of the tree-generator pipeline on one GPU:
+//   K0 tables -> K1 find (accepted attempt per replicate) -> scan -> K1 build (node arena) -> K3 label/prune
+//   -> K4 emit size -> scan -> K4 emit write -> summary reduction.
+#include <cub/device/device_scan.cuh>
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include "engine.hpp"
+#include "hostfmt.hpp"
+#include "launch.hpp"
+#include "rng.cuh"
+
+namespace sgp {
+
+const unsigned long long* d2s_g_table(); int d2s_g_table_len(); const double* p10_table(); int p10_table_len();
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) throw SgpError(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call); } while (0)
+
+namespace {
+
+template <class T> struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    void alloc(size_t count) { if (p) { cudaFree(p); p = nullptr; } n = count; if (count) CK(cudaMalloc(&p, count * sizeof(T))); }
+    void upload(const std::vector<T>& v) { alloc(v.size()); if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice)); }
+    T* release() { T* q = p; p = nullptr; n = 0; return q; }
+};
+
+struct HostOnDevice {
+    DevBuf<int32_t> parent, left, right, host_tag, v2e, ep_off, ep_arcs, leaf_rank;
+    DevBuf<double> vtime, ep_lo, ep_mid, ep_up, lca_time, ep_times;
+    DevHost view{};
+    void upload(const HostModel& h) {
+        parent.upload(h.parent); left.upload(h.left); right.upload(h.right); host_tag.upload(h.host_tag); v2e.upload(h.v2e);
+        ep_off.upload(h.ep_off); ep_arcs.upload(h.ep_arcs);
+        std::vector<int32_t> lr(h.nV, -1); for (int i = 0; i < h.nLeaves; ++i) lr[h.leaves[i]] = i;
+        leaf_rank.upload(lr);
+        vtime.upload(h.vtime); ep_lo.upload(h.ep_lo); ep_mid.upload(h.ep_mid); ep_up.upload(h.ep_up); lca_time.upload(h.lca_time);
+        std::vector<double> et(3 * (size_t)h.nE); for (int e = 0; e < h.nE; ++e) { et[3 * e] = h.ep_lo[e]; et[3 * e + 1] = h.ep_mid[e]; et[3 * e + 2] = h.ep_up[e]; }
+        ep_times.upload(et);
+        view.nV = h.nV; view.nE = h.nE; view.root = h.root; view.nLeaves = h.nLeaves; view.max_arcs = h.max_arcs; view.has_lca = !h.lca_time.empty();
+        view.parent = parent.p; view.left = left.p; view.right = right.p; view.host_tag = host_tag.p; view.v2e = v2e.p; view.ep_off = ep_off.p;
+        view.ep_arcs = ep_arcs.p; view.leaf_rank = leaf_rank.p; view.vtime = vtime.p; view.ep_lo = ep_lo.p; view.ep_mid = ep_mid.p; view.ep_up = ep_up.p;
+        view.lca_time = lca_time.p;
+    }
+};
+
+__global__ void k_extract_pool(const RepInfo* info, long long n, long long* out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = info[i].status == REP_OK ? info[i].n_pool : 0;
+}
+__global__ void k_collect_status(const RepInfo* info, long long n, int status, long long* list, unsigned long long* count) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && info[i].status == status) { unsigned long long k = atomicAdd(count, 1ULL); list[k] = i; }
+}
+
+__global__ void k_root_times(const RepInfo* info, const long long* node_off, const Node* nodes, long long n, double* out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RepInfo& x = info[i];
+    out[i] = (x.status == REP_OK && x.p_root >= 0) ? nodes[node_off[i] + x.p_root].abstime : 0.0;
+}
+
+struct DevSummary { unsigned long long n_ok, n_failed, attempts_total, vertices; unsigned long long ev[17]; unsigned long long leaf_hist[1025]; };
+__global__ void k_summary(const RepInfo* info, long long n, DevSummary* s) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RepInfo& x = info[i];
+    atomicAdd(&s->attempts_total, (unsigned long long)x.attempts);
+    atomicAdd(&s->vertices, (unsigned long long)x.vertices_sampled);
+    if (x.status == REP_OK) {
+        atomicAdd(&s->n_ok, 1ULL);
+        for (int e = 0; e < 17; ++e) if (x.cnt_u[e]) atomicAdd(&s->ev[e], (unsigned long long)x.cnt_u[e]);
+        int b = x.sampled_leaves; if (b > 1024) b = 1024; if (b < 0) b = 0;
+        atomicAdd(&s->leaf_hist[b], 1ULL);
+    } else atomicAdd(&s->n_failed, 1ULL);
+}
+
+// probes
+__global__ void k_probe_d2s(const double* v, long long n, char* out, MathTables T) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    char* o = out + i * 32; for (int k = 0; k < 32; ++k) o[k] = 0;
+    MemSink m{o}; put_double(m, T, v[i]);
+}
+__global__ void k_probe_math(int fn, const double* v, long long n, double* out, MathTables T) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x = v[i];
+    out[i] = fn == 0 ? jlog(x) : fn == 1 ? jlog10(x) : fn == 2 ? jexp(x) : round_sig(T, x, 8);
+}
+__global__ void k_probe_mt(long long seed, long long n, uint32_t* out, uint32_t* state) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    MtStream mt; mt.mt = state; mt.stride = 32;
+    uint32_t key[4]; seed_words_i64(seed, key); mt.seed(key);
+    for (long long i = 0; i < n; ++i) out[i] = mt.next_word();
+}
+// issue-rate microbenchmarks: independent chains per thread, enough ILP to saturate the pipe
+__global__ void k_peak_dfma(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7; const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) { a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c); a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c); }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void k_peak_imad(uint32_t* out, int iters) {
+    uint32_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7; const uint32_t b = 0xD2511F53u, c = 12345u;
+    for (int i = 0; i < iters; ++i) { a0 = a0 * b + c; a1 = a1 * b + c; a2 = a2 * b + c; a3 = a3 * b + c; a4 = a4 * b + c; a5 = a5 * b + c; a6 = a6 * b + c; a7 = a7 * b + c; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+__global__ void k_peak_ddep(double* out, int iters) {
+    double a = threadIdx.x * 1e-3 + 1.0; const double b = 1.0000001;
+    for (int i = 0; i < iters; ++i) { a = __dmul_rn(a, b); a = __dadd_rn(a, 1e-9); }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a;
+}
+
+struct EventTimer {
+    cudaEvent_t a, b; cudaStream_t s;
+    explicit EventTimer(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~EventTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    void start() { cudaEventRecord(a, s); }
+    double stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+};
+
+}  // namespace
+
+struct Context::Impl {
+    cudaStream_t stream = nullptr;
+    DevBuf<unsigned long long> g_table; DevBuf<double> p10;
+    MathTables T{};
+    int sm_count = 148;
+};
+
+Context::Context(int dev) : device(dev), impl(new Impl()) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) throw SgpError(std::string("no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") + "); sagephy_b200 has no CPU fallback");
+    if (dev < 0 || dev >= count) throw SgpError("invalid CUDA device index " + std::to_string(dev));
+    CK(cudaSetDevice(dev));
+    CK(cudaStreamCreate(&impl->stream));
+    std::vector<unsigned long long> g(d2s_g_table(), d2s_g_table() + d2s_g_table_len());
+    std::vector<double> p(p10_table(), p10_table() + p10_table_len());
+    impl->g_table.upload(g); impl->p10.upload(p);
+    impl->T.g = impl->g_table.p; impl->T.p10 = impl->p10.p;
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, dev));
+    impl->sm_count = prop.multiProcessorCount;
+}
+Context::~Context() { if (impl && impl->stream) { cudaSetDevice(device); cudaStreamDestroy(impl->stream); } }
+
+Batch::Batch() {}
+Batch::~Batch() {
+    cudaSetDevice(device);
+    for (int s = 0; s < 8; ++s) { if (d_stream[s]) cudaFree(d_stream[s]); if (h_stream[s]) cudaFreeHost(h_stream[s]); }
+    if (d_offsets) cudaFree(d_offsets);
+    if (d_info) cudaFree(d_info);
+}
+const char* Batch::stream_host(int s) {
+    if (s < 0 || s >= 8) return nullptr;
+    if (!h_stream[s]) {
+        cudaSetDevice(device);
+        size_t bytes = stream_bytes[s];
+        if (cudaMallocHost(&h_stream[s], bytes + 1) != cudaSuccess) return nullptr;
+        if (bytes) cudaMemcpy(h_stream[s], d_stream[s], bytes, cudaMemcpyDeviceToHost);
+        h_stream[s][bytes] = 0;
+    }
+    return h_stream[s];
+}
+bool Batch::copy_stream_to(int s, void* dst) {
+    cudaSetDevice(device);
+    if (!stream_bytes[s]) return true;
+    return cudaMemcpy(dst, d_stream[s], stream_bytes[s], cudaMemcpyDeviceToHost) == cudaSuccess;
+}
+bool Batch::copy_offsets_to(int s, unsigned long long* dst) {
+    cudaSetDevice(device);
+    return cudaMemcpy(dst, d_offsets + (size_t)s * (n + 1), (size_t)(n + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess;
+}
+void Batch::fetch_offsets() {
+    if (!h_offsets.empty() || !d_offsets) return;
+    cudaSetDevice(device);
+    h_offsets.resize((size_t)8 * (n + 1));
+    cudaMemcpy(h_offsets.data(), d_offsets, h_offsets.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+}
+void Batch::fetch_info() {
+    if (have_info || !d_info) return;
+    cudaSetDevice(device);
+    std::vector<RepInfo> inf((size_t)n);
+    cudaMemcpy(inf.data(), d_info, inf.size() * sizeof(RepInfo), cudaMemcpyDeviceToHost);
+    status.resize(n); attempts.resize(n); sampled.resize(n); root_time.assign(n, 0.0); total_time.resize(n); events.resize((size_t)n * 17);
+    for (long long i = 0; i < n; ++i) {
+        status[i] = inf[i].status; attempts[i] = inf[i].attempts; sampled[i] = inf[i].sampled_leaves; total_time[i] = inf[i].total_u;
+        for (int e = 0; e < 17; ++e) events[(size_t)i * 17 + e] = inf[i].cnt_u[e];
+    }
+    have_info = true;
+}
+
+static TinyHost make_tiny(const HostModel& h) {
+    TinyHost t{}; t.nV = h.nV; t.root = h.root;
+    for (int i = 0; i < h.nV; ++i) { t.left[i] = h.left[i]; t.right[i] = h.right[i]; t.parent[i] = h.parent[i]; t.v2e[i] = h.v2e[i]; t.vtime[i] = h.vtime[i]; }
+    for (int e = 0; e < h.nE; ++e) { t.ep_lo[e] = h.ep_lo[e]; t.ep_mid[e] = h.ep_mid[e]; t.ep_up[e] = h.ep_up[e]; }
+    t.tip = h.ep_up[h.nE - 1];
+    return t;
+}
+
+void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch& out) {
+    CK(cudaSetDevice(device));
+    cudaStream_t st = impl->stream;
+    const long long n = opts.n;
+    if (n <= 0) throw SgpError("replicate count must be positive");
+    const bool replay = opts.rng_mode == 1;
+    out.n = n; out.device = device; out.app = cfg.app; out.quiet = cfg.quiet; out.out_prefix = cfg.out_prefix;
+    Timings tm; EventTimer total(st), ph(st);
+    total.start();
+
+    SimParams P{};
+    P.lambda = cfg.P.lambda; P.mu = cfg.P.mu; P.tau = cfg.P.tau; P.theta = cfg.P.theta; P.rho = cfg.P.rho; P.bias_rate = cfg.P.bias_rate;
+    P.gene_birth = cfg.P.gene_birth; P.bias = cfg.P.bias; P.do_gene_birth = cfg.P.do_gene_birth; P.ishost = cfg.P.ishost;
+    P.min_leaves = cfg.P.min_leaves; P.max_leaves = cfg.P.max_leaves; P.minper = cfg.P.minper; P.maxper = cfg.P.maxper; P.max_attempts = cfg.P.max_attempts;
+    P.n_sizes = (int)cfg.sizes.size();
+    const unsigned long long seed = (unsigned long long)cfg.seed;
+
+    HostOnDevice hd; hd.upload(cfg.host);
+    DevBuf<int32_t> d_sizes; { std::vector<int32_t> s(cfg.sizes.begin(), cfg.sizes.end()); d_sizes.upload(s); }
+    DevBuf<RepInfo> info; info.alloc((size_t)n);
+    CK(cudaMemsetAsync(info.p, 0, (size_t)n * sizeof(RepInfo), st));
+    DevBuf<unsigned long long> counter; counter.alloc(1);
+
+    const bool fast_bd = !replay && cfg.P.tau == 0.0 && !cfg.P.do_gene_birth && cfg.host.nV <= 3;
+    const bool per_leaf = !(cfg.P.minper <= 0 && cfg.P.maxper >= cfg.P.max_leaves);
+    const int sm = impl->sm_count;
+
+    // ---- K1 find -----------------------------------------------------------------------------------------------------------
+    ph.start();
+    DevBuf<uint32_t> mt_state; DevBuf<int32_t> marks, leafcnt;
+    int max_workers = 0;
+    if (fast_bd) {
+        BdArgs a{}; a.P = P; a.H = make_tiny(cfg.host); a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.info = info.p;
+        a.work_counter = counter.p; a.sizes = d_sizes.p;
+        CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
+        int blocks = sm * 4; long long need = (n + 255) / 256; if (need < blocks) blocks = (int)need;
+        launch_bd_find(a, blocks, st); ++tm.launches;
+        CK(cudaGetLastError());
+    } else {
+        int cap = 1024; while (cap < 4 * cfg.P.max_leaves && cap < (1 << 20)) cap *= 2;
+        if (cfg.host.nLeaves > 64) while (cap < 8 * cfg.host.nLeaves) cap *= 2;
+        long long workers = std::min<long long>((long long)sm * 256, (n + 127) / 128 * 128);
+        DevBuf<long long> redo, keep; DevBuf<unsigned long long> redo_count;
+        const long long* rep_ids = nullptr; long long todo = n;
+        for (int round = 0;; ++round) {
+            // bound scratch to ~24 GiB
+            while ((double)workers * cap * (sizeof(Node) + 8.0) > 24.0 * (1ull << 30) && workers > 128) workers /= 2;
+            workers = std::max<long long>(128, workers / 128 * 128);
+            max_workers = std::max<long long>(max_workers, workers);
+            DevBuf<Node> s_nodes; DevBuf<int32_t> s_queue, s_pend;
+            s_nodes.alloc((size_t)workers * cap); s_queue.alloc((size_t)workers * cap); s_pend.alloc((size_t)workers * cap);
+            marks.alloc((size_t)workers * cfg.host.nV); leafcnt.alloc((size_t)workers * std::max(1, cfg.host.nLeaves));
+            if (replay) mt_state.alloc((size_t)(workers / 32 + 1) * 624 * 32);
+            FindArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = todo; a.rep_ids = rep_ids; a.rep_base = opts.offset; a.seed = seed; a.info = info.p;
+            a.work_counter = counter.p; a.scratch_nodes = s_nodes.p; a.scratch_queue = s_queue.p; a.scratch_pend = s_pend.p; a.cap = cap;
+            a.scratch_marks = marks.p; a.scratch_leafcnt = leafcnt.p; a.mt_state = mt_state.p; a.sizes = d_sizes.p; a.per_leaf_check = per_leaf;
+            CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
+            int blocks = (int)(workers / 128);
+            launch_find_general(replay, a, blocks, st);
+            ++tm.launches;
+            CK(cudaGetLastError());
+            // replicates that ran out of node capacity are re-run with a larger pool
+            redo.alloc((size_t)n); redo_count.alloc(1);
+            CK(cudaMemsetAsync(redo_count.p, 0, sizeof(unsigned long long), st));
+            k_collect_status<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(info.p, n, REP_NODE_OVERFLOW, redo.p, redo_count.p); ++tm.launches;
+            unsigned long long cnt = 0;
+            CK(cudaMemcpyAsync(&cnt, redo_count.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (cnt == 0 || cap >= (1 << 24) || round > 8) break;
+            keep.alloc((size_t)cnt);
+            CK(cudaMemcpyAsync(keep.p, redo.p, cnt * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+            CK(cudaStreamSynchronize(st));
+            rep_ids = keep.p; todo = (long long)cnt; cap *= 8; workers = std::min<long long>(workers, (todo + 127) / 128 * 128);
+        }
+    }
+    tm.find_ms = ph.stop();
+
+    // ---- node offsets ------------------------------------------------------------------------------------------------------
+    DevBuf<long long> pool, node_off; pool.alloc((size_t)n + 1); node_off.alloc((size_t)n + 1);
+    CK(cudaMemsetAsync(pool.p, 0, ((size_t)n + 1) * sizeof(long long), st));
+    k_extract_pool<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(info.p, n, pool.p); ++tm.launches;
+    {
+        size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, pool.p, node_off.p, (int)(n + 1), st);
+        DevBuf<char> tmp; tmp.alloc(tb);
+        cub::DeviceScan::ExclusiveSum(tmp.p, tb, pool.p, node_off.p, (int)(n + 1), st); ++tm.launches;
+        CK(cudaStreamSynchronize(st));
+    }
+    long long total_nodes = 0;
+    CK(cudaMemcpy(&total_nodes, node_off.p + n, sizeof(long long), cudaMemcpyDeviceToHost));
+    DevBuf<Node> nodes; DevBuf<int32_t> aux;
+    const long long aux_stride = std::max<long long>(total_nodes, 1);
+    nodes.alloc((size_t)std::max<long long>(total_nodes, 1)); aux.alloc((size_t)aux_stride * 4);
+
+    // ---- K1 build ------------------------------------------------------------------------------------------------------------
+    ph.start();
+    if (fast_bd) {
+        BdArgs a{}; a.P = P; a.H = make_tiny(cfg.host); a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.info = info.p;
+        a.node_off = node_off.p; a.nodes = nodes.p;
+        launch_bd_build(a, (int)((n + 255) / 256), st); ++tm.launches;
+    } else {
+        const long long threads = (n + 127) / 128 * 128;
+        marks.alloc((size_t)threads * cfg.host.nV);
+        if (replay) mt_state.alloc((size_t)(threads / 32 + 1) * 624 * 32);
+        BuildArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.info = info.p; a.node_off = node_off.p;
+        a.nodes = nodes.p; a.aux = aux.p; a.aux_stride = aux_stride; a.scratch_marks = marks.p; a.scratch_leafcnt = nullptr; a.mt_state = mt_state.p;
+        launch_build_general(replay, a, (int)(threads / 128), st);
+        ++tm.launches;
+    }
+    CK(cudaGetLastError());
+    tm.build_ms = ph.stop();
+
+    // ---- K3 label / prune ----------------------------------------------------------------------------------------------------
+    ph.start();
+    {
+        LabelArgs a{}; a.n = n; a.info = info.p; a.node_off = node_off.p; a.nodes = nodes.p; a.aux = aux.p; a.aux_stride = aux_stride; a.T = impl->T;
+        a.host_root_time = cfg.host.vtime[cfg.host.root]; a.has_stem_override = cfg.has_stem_override; a.stem_override = cfg.stem_override;
+        launch_label_prune(a, (int)((n + 127) / 128), st); ++tm.launches;
+        CK(cudaGetLastError());
+    }
+    tm.label_ms = ph.stop();
+
+    // ---- K4 emit ---------------------------------------------------------------------------------------------------------------
+    unsigned mask = opts.stream_mask;
+    if (mask == 0) {
+        if (cfg.quiet) mask = 1u << ST_PRUNED_TREE;
+        else {
+            mask = 0xFu;
+            if (cfg.app != 0 && !cfg.exclude_meta) mask |= 0xF0u;
+        }
+    }
+    // constant strings
+    std::string blob; std::vector<int32_t> gname, leafname;
+    EmitArgs e{};
+    auto add = [&](const std::string& s, int& off, int& len) { off = (int)blob.size(); len = (int)s.size(); blob += s; };
+    {
+        std::string pre = "[", post;
+        bool split = replay && cfg.seed_arg_index >= 0;
+        for (size_t i = 0; i < cfg.args.size(); ++i) {
+            std::string& dst = (split && (int)i > cfg.seed_arg_index) ? post : pre;
+            if ((int)i == cfg.seed_arg_index && split) { if (i) pre += ", "; continue; }
+            if (i) dst += ", ";
+            dst += cfg.args[i];
+        }
+        if (split) post += "]"; else pre += "]";
+        add(pre, e.args_pre_off, e.args_pre_len); add(post, e.args_post_off, e.args_post_len);
+        e.seed_mode = split ? 1 : 0; e.seed_base = cfg.seed;
+    }
+    add("# GUEST-TO-HOST MAP\nHost tree:\t" + cfg.host.header + "\nGuest vertex name:\tGuest vertex ID:\tGuest vertex type:\tGuest vertex time:\tHost vertex/arc ID:\tHost epoch ID:\n",
+        e.g2h_head_off, e.g2h_head_len);
+    { int o, l; add(cfg.host.has_tree_name ? cfg.host.tree_name : std::string("null"), o, l); gname.push_back(o); gname.push_back(l); }
+    for (int v = 0; v < cfg.host.nV; ++v) { int o, l; add(cfg.host.left[v] < 0 ? cfg.host.leaf_name[v] : std::string("null"), o, l); leafname.push_back(o); leafname.push_back(l); }
+    DevBuf<char> d_blob; { std::vector<char> b(blob.begin(), blob.end()); b.push_back(0); d_blob.upload(b); }
+    DevBuf<int32_t> d_gname, d_leafname; d_gname.upload(gname); d_leafname.upload(leafname);
+    DevBuf<unsigned long long> sizes, offsets; sizes.alloc((size_t)ST_COUNT * (n + 1)); offsets.alloc((size_t)ST_COUNT * (n + 1));
+    CK(cudaMemsetAsync(sizes.p, 0, (size_t)ST_COUNT * (n + 1) * sizeof(unsigned long long), st));
+    e.n = n; e.rep_base = opts.offset; e.info = info.p; e.node_off = node_off.p; e.nodes = nodes.p; e.aux = aux.p; e.aux_stride = aux_stride; e.T = impl->T;
+    e.app = cfg.app; e.exclude_meta = cfg.exclude_meta; e.append_sigma = cfg.append_sigma; e.is_species = cfg.is_species; e.stream_mask = mask;
+    e.prefix_len = (int)std::min<size_t>(cfg.vertex_prefix.size(), sizeof(e.prefix)); memcpy(e.prefix, cfg.vertex_prefix.data(), e.prefix_len);
+    if (cfg.vertex_prefix.size() > sizeof(e.prefix)) throw SgpError("vertex prefix longer than 24 bytes is not supported");
+    e.blob = d_blob.p; e.gname_off = d_gname.p; e.leafname_off = d_leafname.p; e.ep_times = hd.ep_times.p;
+    // sizes are laid out [stream][n+1] so that one scan per stream yields offsets with the total in the last slot
+    DevBuf<unsigned long long> sizes_n; sizes_n.alloc((size_t)ST_COUNT * n);
+    e.sizes = sizes_n.p; e.offsets = offsets.p;
+    const unsigned emit_blocks = (unsigned)((n * 32 + 127) / 128);
+    ph.start();
+    launch_emit(false, e, emit_blocks, st); ++tm.launches;
+    CK(cudaGetLastError());
+    {
+        size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, sizes.p, offsets.p, (int)(n + 1), st);
+        DevBuf<char> tmp; tmp.alloc(tb);
+        for (int s = 0; s < ST_COUNT; ++s) {
+            CK(cudaMemcpyAsync(sizes.p + (size_t)s * (n + 1), sizes_n.p + (size_t)s * n, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+            cub::DeviceScan::ExclusiveSum(tmp.p, tb, sizes.p + (size_t)s * (n + 1), offsets.p + (size_t)s * (n + 1), (int)(n + 1), st); ++tm.launches;
+        }
+        CK(cudaStreamSynchronize(st));
+    }
+    tm.emit_size_ms = ph.stop();
+    unsigned long long totals[ST_COUNT];
+    for (int s = 0; s < ST_COUNT; ++s) CK(cudaMemcpy(&totals[s], offsets.p + (size_t)s * (n + 1) + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int s = 0; s < ST_COUNT; ++s) { out.stream_bytes[s] = totals[s]; CK(cudaMalloc(&out.d_stream[s], std::max<unsigned long long>(totals[s], 1))); e.out[s] = out.d_stream[s]; }
+    ph.start();
+    launch_emit(true, e, emit_blocks, st); ++tm.launches;
+    CK(cudaGetLastError());
+    tm.emit_write_ms = ph.stop();
+
+    // ---- summary ---------------------------------------------------------------------------------------------------------------
+    {
+        DevBuf<DevSummary> ds; ds.alloc(1); CK(cudaMemsetAsync(ds.p, 0, sizeof(DevSummary), st));
+        k_summary<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(info.p, n, ds.p); ++tm.launches;
+        DevSummary hs; CK(cudaMemcpyAsync(&hs, ds.p, sizeof(hs), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+        Summary& S = out.summary; S.n_ok = (long long)hs.n_ok; S.n_failed = (long long)hs.n_failed; S.attempts_total = (long long)hs.attempts_total; S.vertices_sampled = (long long)hs.vertices;
+        for (int i = 0; i < 17; ++i) S.event_counts[i] = (long long)hs.ev[i];
+        for (int i = 0; i < 1025; ++i) S.leaf_hist[i] = (long long)hs.leaf_hist[i];
+        for (int s = 0; s < ST_COUNT; ++s) S.out_bytes[s] = (long long)totals[s];
+    }
+    out.d_offsets = offsets.release(); out.d_info = info.release();
+    static const char* host_sfx[8] = {".unpruned.tree", ".pruned.tree", ".unpruned.info", ".pruned.info", ".unpruned.guest2host", ".pruned.guest2host", ".unpruned.leafmap", ".pruned.leafmap"};
+    for (int s = 0; s < 8; ++s) out.suffix[s] = (mask & (1u << s)) ? host_sfx[s] : "";
+    tm.total_ms = total.stop();
+    out.timings = tm;
+    // per-replicate scalars for the accessors; pruned-root times come from the node arena, which is released on return
+    out.fetch_info();
+    {
+        DevBuf<double> rt; rt.alloc((size_t)n);
+        k_root_times<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const RepInfo*)out.d_info, node_off.p, nodes.p, n, rt.p);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out.root_time.data(), rt.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    if (!opts.keep_on_device) {
+        EventTimer d2h(st); d2h.start();
+        for (int s = 0; s < 8; ++s) if (mask & (1u << s)) out.stream_host(s);
+        out.fetch_offsets();
+        out.timings.d2h_ms = d2h.stop();
+    }
+}
+
+void Context::probe_d2s(const double* v, long long n, char* out) {
+    CK(cudaSetDevice(device));
+    DevBuf<double> dv; dv.alloc((size_t)n); DevBuf<char> dout; dout.alloc((size_t)n * 32);
+    CK(cudaMemcpy(dv.p, v, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    k_probe_d2s<<<(unsigned)((n + 255) / 256), 256, 0, impl->stream>>>(dv.p, n, dout.p, impl->T);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout.p, (size_t)n * 32, cudaMemcpyDeviceToHost, impl->stream)); CK(cudaStreamSynchronize(impl->stream));
+}
+void Context::probe_math(int fn, const double* v, long long n, double* out) {
+    CK(cudaSetDevice(device));
+    DevBuf<double> dv, dout; dv.alloc((size_t)n); dout.alloc((size_t)n);
+    CK(cudaMemcpy(dv.p, v, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    k_probe_math<<<(unsigned)((n + 255) / 256), 256, 0, impl->stream>>>(fn, dv.p, n, dout.p, impl->T);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, impl->stream)); CK(cudaStreamSynchronize(impl->stream));
+}
+void Context::probe_mt(long long seed, long long n_words, uint32_t* out) {
+    CK(cudaSetDevice(device));
+    DevBuf<uint32_t> state, dout; state.alloc(624 * 32); dout.alloc((size_t)n_words);
+    k_probe_mt<<<1, 32, 0, impl->stream>>>(seed, n_words, dout.p, state.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout.p, (size_t)n_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, impl->stream)); CK(cudaStreamSynchronize(impl->stream));
+}
+void Context::probe_issue(double* dfma, double* imad, double* ddep) {
+    CK(cudaSetDevice(device));
+    const int blocks = impl->sm_count * 8, threads = 256, iters = 20000;
+    DevBuf<double> od; od.alloc((size_t)blocks * threads); DevBuf<uint32_t> oi; oi.alloc((size_t)blocks * threads);
+    EventTimer t(impl->stream);
+    k_peak_dfma<<<blocks, threads, 0, impl->stream>>>(od.p, 100); CK(cudaStreamSynchronize(impl->stream));
+    t.start(); k_peak_dfma<<<blocks, threads, 0, impl->stream>>>(od.p, iters); double ms = t.stop();
+    *dfma = (double)blocks * threads / 32.0 * iters * 8.0 / (ms * 1e-3) * 1e-9;
+    t.start(); k_peak_imad<<<blocks, threads, 0, impl->stream>>>(oi.p, iters); ms = t.stop();
+    *imad = (double)blocks * threads / 32.0 * iters * 8.0 / (ms * 1e-3) * 1e-9;
+    t.start(); k_peak_ddep<<<blocks, threads, 0, impl->stream>>>(od.p, iters); ms = t.stop();
+    *ddep = (double)blocks * threads / 32.0 * iters * 2.0 / (ms * 1e-3) * 1e-9;
+    CK(cudaGetLastError());
+}
+
+}  // namespace sgp

@@ -1,0 +1,93 @@
+// Host-side engine interface (C++). The C ABI in capi.cpp is a thin shell over this.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+#include "host_model.hpp"
+
+namespace sgp {
+
+struct SimParamsHost {
+    double lambda = 0, mu = 0, tau = 0, theta = 0, rho = 1, bias_rate = 1, gene_birth = 1;
+    int bias = 0;             // 0 none, 1 simple, 2 exponential
+    bool do_gene_birth = false, ishost = false;
+    int min_leaves = 2, max_leaves = 1000, minper = 0, maxper = 10, max_attempts = 10000;
+};
+
+struct TreeGenConfig {
+    int app = 0;              // 0 HostTreeGen, 1 GuestTreeGen, 2 DomainTreeGen
+    SimParamsHost P;
+    HostModel host;
+    bool quiet = false, exclude_meta = false, append_sigma = false, is_species = false;
+    std::string vertex_prefix = "H", out_prefix;
+    bool has_stem_override = false; double stem_override = 0;   // HostTreeGen -stem (applied to the finished trees)
+    std::vector<int> sizes;
+    bool has_seed = false; long long seed = 0;
+    std::vector<std::string> args;      // the app's argv (for the "Arguments:" line)
+    int seed_arg_index = -1;            // position of the seed value inside args
+};
+
+struct BatchOpts {
+    long long n = 1, offset = 0;
+    int rng_mode = 0;         // 0 Philox, 1 MT replay
+    unsigned stream_mask = 0;
+    bool keep_on_device = false;
+};
+
+struct Timings { double find_ms = 0, build_ms = 0, label_ms = 0, emit_size_ms = 0, emit_write_ms = 0, d2h_ms = 0, total_ms = 0; long long launches = 0; };
+
+struct Summary {
+    long long n_ok = 0, n_failed = 0, attempts_total = 0, vertices_sampled = 0;
+    long long event_counts[17] = {0};
+    long long leaf_hist[1025] = {0};
+    long long out_bytes[8] = {0};
+};
+
+// Result of a run. Stream bytes live in device memory; host copies are made on demand into pinned memory.
+class Batch {
+public:
+    Batch();
+    ~Batch();
+    long long n = 0;
+    int device = 0;
+    int app = 0;
+    std::string out_text, err_text, out_prefix;
+    bool quiet = false;
+    const char* suffix[8] = {"", "", "", "", "", "", "", ""};
+    // device
+    char* d_stream[8] = {nullptr}; unsigned long long stream_bytes[8] = {0};
+    unsigned long long* d_offsets = nullptr;      // [8][n+1]
+    void* d_info = nullptr;                       // RepInfo[n]
+    // host (lazy)
+    char* h_stream[8] = {nullptr};
+    std::vector<unsigned long long> h_offsets;    // [8][n+1]
+    std::vector<int32_t> status, attempts, sampled, events; std::vector<double> root_time, total_time;
+    bool have_info = false;
+    Summary summary; Timings timings;
+    const char* stream_host(int s);
+    bool copy_stream_to(int s, void* dst);
+    bool copy_offsets_to(int s, unsigned long long* dst);
+    void fetch_info();
+    void fetch_offsets();
+};
+
+class Context {
+public:
+    explicit Context(int device);
+    ~Context();
+    int device;
+    std::string last_error;
+    struct Impl; std::unique_ptr<Impl> impl;
+    void run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch& out);
+    void probe_d2s(const double* v, long long n, char* out);
+    void probe_math(int fn, const double* v, long long n, double* out);
+    void probe_mt(long long seed, long long n_words, uint32_t* out);
+    void probe_issue(double* dfma, double* imad, double* ddep);
+};
+
+// apps.cpp: reference CLI grammar -> configs
+struct AppResult { int status = 0; std::string out_text, err_text; };   // status: 0 run, 6 usage, other = error code
+void parse_treegen_app(const std::string& app, const std::vector<std::string>& args, TreeGenConfig& cfg, AppResult& res);
+
+}  // namespace sgp

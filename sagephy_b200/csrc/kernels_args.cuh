@@ -1,0 +1,95 @@
+// Kernel argument blocks (plain structs passed by value), shared between the kernel translation units and the host engine.
+#pragma once
+#include "device_types.cuh"
+
+namespace sgp {
+
+// Tiny host tree (HostTreeGen: "H0:T;" or "(H0:T,H1:T):0.0;") passed by value to the BD fast path.
+struct TinyHost {
+    int32_t nV, root;
+    int32_t left[3], right[3], parent[3], v2e[3];
+    double vtime[3];
+    double ep_lo[2], ep_mid[2], ep_up[2];
+    double tip;
+};
+
+struct FindArgs {
+    SimParams P;
+    DevHost H;
+    MathTables T;
+    long long n;                 // replicates in this launch
+    const long long* rep_ids;    // optional indirection (re-runs of overflowed replicates); nullptr = identity
+    long long rep_base;          // global id of local replicate 0 (multi-GPU shard offset)
+    unsigned long long seed;     // Philox key / MT base seed (replicate i == reference run with -s seed+i)
+    RepInfo* info;               // [n_total]
+    unsigned long long* work_counter;
+    // scratch (general engine): per worker thread
+    Node* scratch_nodes; int32_t* scratch_queue; int32_t* scratch_pend; int cap;
+    int32_t* scratch_marks; int32_t* scratch_leafcnt;      // nV / nLeaves ints per worker
+    uint32_t* mt_state;          // 624 words per worker, warp-interleaved (replay mode)
+    const int32_t* sizes;        // -sizes list
+    int per_leaf_check;
+};
+
+struct BuildArgs {
+    SimParams P;
+    DevHost H;
+    MathTables T;
+    long long n; long long rep_base; unsigned long long seed;
+    RepInfo* info;
+    const long long* node_off;   // exclusive scan of n_pool
+    Node* nodes;                 // arena
+    int32_t* aux; long long aux_stride;    // 4 int arrays of length total_nodes: aux + k*aux_stride
+    int32_t* scratch_marks; int32_t* scratch_leafcnt;
+    uint32_t* mt_state;
+};
+
+struct BdArgs {
+    SimParams P;
+    TinyHost H;
+    MathTables T;
+    long long n; long long rep_base; unsigned long long seed;
+    RepInfo* info;
+    unsigned long long* work_counter;
+    const int32_t* sizes;
+    // build only
+    const long long* node_off; Node* nodes;
+};
+
+struct LabelArgs {
+    long long n;
+    RepInfo* info;
+    const long long* node_off;
+    Node* nodes;
+    int32_t* aux; long long aux_stride;     // ordU, ordP, bfsU, bfsP
+    MathTables T;
+    double host_root_time;                  // hostTree.getVertexTime(root)
+    int has_stem_override; double stem_override;    // HostTreeGen -stem (HostTreeGen.java:74-79)
+};
+
+enum Stream : int { ST_UNPRUNED_TREE = 0, ST_PRUNED_TREE = 1, ST_UNPRUNED_INFO = 2, ST_PRUNED_INFO = 3,
+                    ST_UNPRUNED_G2H = 4, ST_PRUNED_G2H = 5, ST_UNPRUNED_LEAFMAP = 6, ST_PRUNED_LEAFMAP = 7, ST_COUNT = 8 };
+
+struct EmitArgs {
+    long long n; long long rep_base;
+    const RepInfo* info;
+    const long long* node_off;
+    const Node* nodes;
+    const int32_t* aux; long long aux_stride;
+    MathTables T;
+    int app;                       // 0 HostTreeGen, 1 GuestTreeGen, 2 DomainTreeGen
+    int exclude_meta, append_sigma, is_species, do_ml_pruned;
+    unsigned stream_mask;
+    char prefix[24]; int prefix_len;
+    const char* blob;              // constant strings, see below
+    int args_pre_off, args_pre_len, args_post_off, args_post_len, seed_mode; long long seed_base;
+    int g2h_head_off, g2h_head_len;
+    const int32_t* gname_off;      // per host tree: offset/len pairs into blob (GUEST= value / file name)
+    const int32_t* leafname_off;   // per host vertex: offset/len pairs into blob (leafmap second column)
+    const double* ep_times;        // 3 doubles per epoch [lo, mid, up] (DISCPT index)
+    unsigned long long* sizes;     // [ST_COUNT][n]  (size pass output)
+    const unsigned long long* offsets;   // [ST_COUNT][n+1] (write pass input)
+    char* out[ST_COUNT];
+};
+
+}  // namespace sgp

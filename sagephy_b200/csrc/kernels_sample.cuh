@@ -1,0 +1,83 @@
+// Sampling kernels (K1): "find" passes decide which attempt of each replicate is accepted, "build" passes regenerate
+// that attempt into the exactly-sized node arena.
+#pragma once
+#include "sim.cuh"
+
+namespace sgp {
+
+
+template <bool REPLAY>
+__global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
+    const int worker = blockIdx.x * blockDim.x + threadIdx.x;
+    SimWork W;
+    W.nodes = a.scratch_nodes + (size_t)worker * a.cap; W.cap = a.cap;
+    W.queue = a.scratch_queue + (size_t)worker * a.cap; W.pend = a.scratch_pend + (size_t)worker * a.cap;
+    W.marks = a.scratch_marks + (size_t)worker * a.H.nV;
+    W.leaf_cnt = a.per_leaf_check ? a.scratch_leafcnt + (size_t)worker * a.H.nLeaves : nullptr;
+    W.mark_gen = 0;
+    for (int i = 0; i < a.H.nV; ++i) W.marks[i] = 0;
+    MtStream mt; PhiloxStream ph;
+    if (REPLAY) { mt.mt = a.mt_state + (size_t)(worker >> 5) * 624 * 32 + (worker & 31); mt.stride = 32; }
+    for (;;) {
+        long long slot = (long long)atomicAdd(a.work_counter, 1ULL);
+        if (slot >= a.n) break;
+        const long long r = a.rep_ids ? a.rep_ids[slot] : slot;
+        const long long gid = a.rep_base + r;
+        RepInfo inf; memset(&inf, 0, sizeof(inf));
+        inf.status = REP_PENDING; inf.exact = -1; inf.root = -1; inf.p_root = -1;
+        if (REPLAY) { uint32_t key[4]; seed_words_i64((long long)a.seed + gid, key); mt.seed(key); }
+        else ph.init(a.seed, (uint64_t)gid, 0xFFFFFFFFu);
+        if (a.P.n_sizes > 0) inf.exact = a.sizes[REPLAY ? mt.next_int(a.P.n_sizes) : ph.next_int(a.P.n_sizes)];
+        int attempts = 0; uint64_t verts = 0;
+        for (;;) {
+            if (attempts > a.P.max_attempts) { inf.status = REP_MAX_ATTEMPTS; break; }
+            uint64_t pos = 0;
+            if (REPLAY) pos = mt.position(); else ph.begin_attempt((uint32_t)attempts);
+            int n = 0, root = -1;
+            int st = REPLAY ? simulate_attempt(mt, a.P, a.H, a.T, W, n, root) : simulate_attempt(ph, a.P, a.H, a.T, W, n, root);
+            verts += (uint64_t)n;
+            if (st != REP_OK) { inf.status = st; break; }
+            ++attempts;
+            int sampled = 0;
+            if (attempt_ok(a.P, a.H, W, root, inf.exact, &sampled)) {
+                inf.status = REP_OK; inf.n_pool = n; inf.sampled_leaves = sampled;
+                if (REPLAY) { inf.acc_attempt = (uint32_t)pos; inf.acc_hi = (uint32_t)(pos >> 32); } else { inf.acc_attempt = (uint32_t)(attempts - 1); inf.acc_hi = 0; }
+                ++attempts;     // GuestTreeMachina.java:107
+                break;
+            }
+        }
+        inf.attempts = attempts; inf.vertices_sampled = verts;
+        a.info[r] = inf;
+    }
+}
+
+
+template <bool REPLAY>
+__global__ void __launch_bounds__(128) k_build_general(BuildArgs a) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int worker = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n) return;
+    RepInfo& inf = a.info[r];
+    if (inf.status != REP_OK) return;
+    const long long off = a.node_off[r];
+    SimWork W;
+    W.nodes = a.nodes + off; W.cap = inf.n_pool;
+    W.queue = a.aux + off; W.pend = a.aux + a.aux_stride + off;
+    W.marks = a.scratch_marks + (size_t)worker * a.H.nV; W.leaf_cnt = nullptr; W.mark_gen = 0;
+    for (int i = 0; i < a.H.nV; ++i) W.marks[i] = 0;
+    int n = 0, root = -1, st;
+    const long long gid = a.rep_base + r;
+    if (REPLAY) {
+        MtStream mt; mt.mt = a.mt_state + (size_t)(worker >> 5) * 624 * 32 + (worker & 31); mt.stride = 32;
+        uint32_t key[4]; seed_words_i64((long long)a.seed + gid, key); mt.seed(key);
+        mt.skip(((uint64_t)inf.acc_hi << 32) | inf.acc_attempt);
+        st = simulate_attempt(mt, a.P, a.H, a.T, W, n, root);
+    } else {
+        PhiloxStream ph; ph.init(a.seed, (uint64_t)gid, inf.acc_attempt);
+        st = simulate_attempt(ph, a.P, a.H, a.T, W, n, root);
+    }
+    if (st != REP_OK || n != inf.n_pool) { inf.status = REP_MODEL_ERROR; return; }
+    inf.root = root;
+}
+
+}  // namespace sgp

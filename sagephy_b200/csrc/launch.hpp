@@ -1,0 +1,13 @@
+// Host-callable launchers of the kernels (one translation unit per kernel family keeps nvcc compile times parallel).
+#pragma once
+#include <cuda_runtime.h>
+#include "kernels_args.cuh"
+
+namespace sgp {
+void launch_find_general(bool replay, const FindArgs& a, int blocks, cudaStream_t st);
+void launch_build_general(bool replay, const BuildArgs& a, int blocks, cudaStream_t st);
+void launch_bd_find(const BdArgs& a, int blocks, cudaStream_t st);
+void launch_bd_build(const BdArgs& a, int blocks, cudaStream_t st);
+void launch_label_prune(const LabelArgs& a, int blocks, cudaStream_t st);
+void launch_emit(bool write, const EmitArgs& a, unsigned blocks, cudaStream_t st);
+}  // namespace sgp

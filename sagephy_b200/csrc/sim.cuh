@@ -1,0 +1,304 @@
+// Guest-in-host sampler (device side).
+//
+//  general engine  — one thread simulates one attempt exactly as the reference does, vertex by vertex in the reference's
+//                    queue order, so that with MtStream the random stream is consumed in the reference's order
+//                    (apps/SaGePhy/GuestTreeInHostTreeCreator.java:110-321 createUnprunedTree, :372-423 createGuestVertex,
+//                    topology/Epoch.java:249-329 sampleArc/setDistance, topology/RBTreeEpochDiscretiser.java:662-683 sampleRoot).
+//  BD fast path    — transfer-free processes on a 1- or 2-leaf host (HostTreeGen) in Philox mode: depth-first expansion with
+//                    a small stack, vertex v of attempt a draws Philox block (v, a, replicate), so the count-only pass and
+//                    the build pass regenerate identical trees.
+#pragma once
+#include "kernels_args.cuh"
+#include "rng.cuh"
+
+namespace sgp {
+
+struct VertexDraw { double abstime, bl; int32_t epoch; uint8_t event; };
+
+// createGuestVertex (GuestTreeInHostTreeCreator.java:372-423). Exact Java arithmetic (jlog, true division, round8).
+template <class RNG>
+__device__ __forceinline__ VertexDraw draw_vertex(RNG& rng, const SimParams& P, const DevHost& H, const MathTables& T, int X, double start) {
+    VertexDraw d;
+    const bool isRoot = H.parent[X] < 0;
+    double sum = isRoot ? XADD(P.lambda, P.mu) : XADD(XADD(P.lambda, P.mu), P.tau);
+    if (sum == 0.0) sum = 1e-48;
+    const double low = H.vtime[X];
+    double u1 = rng.next_double();
+    double bt = XDIV(-jlog(XSUB(1.0, u1)), sum);
+    double et = XSUB(start, bt);
+    if (et <= low) {
+        et = low;
+        bt = round_sig(T, XSUB(start, et), 8);
+        if (H.left[X] < 0) d.event = (rng.next_double() < P.rho) ? EV_LEAF : EV_UNSAMPLED_LEAF;
+        else d.event = EV_SPECIATION;
+        d.epoch = H.v2e[X];
+    } else {
+        double rnd = rng.next_double();
+        if (isRoot) d.event = (rnd < XDIV(P.lambda, sum)) ? EV_DUPLICATION : EV_LOSS;
+        else if (rnd >= XDIV(XADD(P.mu, P.tau), sum)) d.event = EV_DUPLICATION;
+        else if (rnd < XDIV(P.mu, sum)) d.event = EV_LOSS;
+        else { double trn = rng.next_double(); d.event = (trn < P.theta) ? EV_REPLACING_TRANSFER : EV_ADDITIVE_TRANSFER; }
+        int e = H.v2e[X];
+        while (H.ep_up[e] < et) ++e;
+        d.epoch = e;
+    }
+    d.abstime = et; d.bl = bt;
+    return d;
+}
+
+// double-double helpers for the cumulative-weight selection (stands in for the reference's exact BigDecimal sums)
+struct DD { double hi, lo; };
+__device__ __forceinline__ DD dd_add_d(DD a, double b) {
+    double s = a.hi + b; double bb = s - a.hi; double err = (a.hi - (s - bb)) + (b - bb);
+    double lo = a.lo + err; double hi = s + lo; lo = lo - (hi - s);
+    return DD{hi, lo};
+}
+__device__ __forceinline__ DD dd_mul_d(DD a, double b) {
+    double p = a.hi * b; double e = fma(a.hi, b, -p); e = fma(a.lo, b, e);
+    double hi = p + e; double lo = e - (hi - p);
+    return DD{hi, lo};
+}
+__device__ __forceinline__ bool dd_gt(DD a, DD b) { return a.hi > b.hi || (a.hi == b.hi && a.lo > b.lo); }
+
+// Math.pow(Math.E, y) stand-in (CUDA pow; see DESIGN.md "numerics" for the tolerance argument).
+__device__ __forceinline__ double pow_e(double y) { return pow(2.718281828459045, y); }
+
+// Epoch.sampleArc with include == true. marks[x] == mark_gen flags an "empty" arc. Returns -5 if no candidate.
+template <class RNG>
+__device__ int sample_arc(RNG& rng, const SimParams& P, const DevHost& H, int epoch, int donor, double t, const int32_t* marks, int mark_gen) {
+    const int a0 = H.ep_off[epoch], a1 = H.ep_off[epoch + 1];
+    const int tag = H.host_tag[donor];
+    if (P.bias == 0) {
+        int k = 0;
+        for (int j = a0; j < a1; ++j) { int x = H.ep_arcs[j]; if (x != donor && !(marks && marks[x] == mark_gen) && H.host_tag[x] == tag) ++k; }
+        if (k < 1) return -5;
+        int pick = rng.next_int(k);
+        for (int j = a0; j < a1; ++j) { int x = H.ep_arcs[j]; if (x != donor && !(marks && marks[x] == mark_gen) && H.host_tag[x] == tag) { if (pick == 0) return x; --pick; } }
+        return -5;
+    }
+    // biased: weights in epoch arc order; key = running total; pick the first key > total * U, where an arc with
+    // weight 0 shares (and therefore overwrites) the previous key (TreeMap.put semantics, Epoch.java:323-324).
+    DD total{0.0, 0.0}; int k = 0;
+    for (int j = a0; j < a1; ++j) {
+        int x = H.ep_arcs[j];
+        if (x == donor || (marks && marks[x] == mark_gen) || H.host_tag[x] != tag) continue;
+        double dist = XMUL(2.0, XSUB(H.lca_time[(size_t)donor * H.nV + x], t));
+        double w = (P.bias == 2) ? XMUL(P.bias_rate, pow_e(XMUL(-P.bias_rate, dist))) : XDIV(1.0, dist);
+        if (w == dbl_inf()) w = 1.7976931348623157e308;
+        total = dd_add_d(total, w); ++k;
+    }
+    if (k < 1) return -5;
+    DD rnd = dd_mul_d(total, rng.next_double());
+    DD cum{0.0, 0.0}; int chosen = -5; bool found = false;
+    for (int j = a0; j < a1; ++j) {
+        int x = H.ep_arcs[j];
+        if (x == donor || (marks && marks[x] == mark_gen) || H.host_tag[x] != tag) continue;
+        double dist = XMUL(2.0, XSUB(H.lca_time[(size_t)donor * H.nV + x], t));
+        double w = (P.bias == 2) ? XMUL(P.bias_rate, pow_e(XMUL(-P.bias_rate, dist))) : XDIV(1.0, dist);
+        if (w == dbl_inf()) w = 1.7976931348623157e308;
+        if (found) { if (w == 0.0) { chosen = x; continue; } break; }
+        cum = dd_add_d(cum, w);
+        if (dd_gt(cum, rnd)) { chosen = x; found = true; }
+    }
+    return chosen;
+}
+
+// RBTreeEpochDiscretiser.sampleRoot
+template <class RNG>
+__device__ int sample_root(RNG& rng, const SimParams& P, const DevHost& H) {
+    const double tip = H.ep_up[H.nE - 1];
+    DD total{0.0, 0.0};
+    for (int i = 0; i < H.nV; ++i) total = dd_add_d(total, XMUL(P.gene_birth, pow_e(XMUL(-P.gene_birth, XSUB(tip, H.vtime[i])))));
+    DD rnd = dd_mul_d(total, rng.next_double());
+    DD cum{0.0, 0.0}; int chosen = H.nV - 1; bool found = false;
+    for (int i = 0; i < H.nV; ++i) {
+        double w = XMUL(P.gene_birth, pow_e(XMUL(-P.gene_birth, XSUB(tip, H.vtime[i]))));
+        if (found) { if (w == 0.0) { chosen = i; continue; } break; }
+        cum = dd_add_d(cum, w);
+        if (dd_gt(cum, rnd)) { chosen = i; found = true; }
+    }
+    return chosen;
+}
+
+// Workspace of one simulating thread.
+struct SimWork {
+    Node* nodes; int cap;         // node pool
+    int32_t* queue;               // FIFO of lineages ("alive"), cap entries
+    int32_t* pend;                // parked replacing transfers ("sortedlist"), cap entries
+    int32_t* marks;               // per host vertex: generation stamp of "empty arc" marks (nV entries) or nullptr
+    int32_t* leaf_cnt;            // per host leaf counters (nLeaves entries) or nullptr when the per-leaf window is vacuous
+    int mark_gen;
+};
+
+__device__ __forceinline__ int new_node(SimWork& W, int& n, const VertexDraw& d, int sigma) {
+    if (n >= W.cap) return -1;
+    Node& v = W.nodes[n];
+    v.abstime = d.abstime; v.bl = d.bl; v.sigma = sigma; v.left = -1; v.right = -1; v.parent = -1; v.epoch = d.epoch;
+    v.from_arc = -1; v.to_arc = -1; v.number = -1; v.p_bl = 0.0; v.p_left = -1; v.p_right = -1;
+    v.event = d.event; v.prun = PR_UNKNOWN; v.flags = 0; v.pad0 = 0; v.gtree = 0; v.from_g = -1; v.to_g = -1; v.chain_u = 0; v.chain_p = 0; v.pad1 = 0;
+    return n++;
+}
+
+// findVertex (GuestTreeInHostTreeCreator.java:332-346): first vertex in left-before-right pre-order on arc `to`
+// whose branch strictly spans time t.
+static __device__ int find_victim(const Node* N, int root, int to, double t) {
+    int v = root;
+    while (v >= 0) {
+        const Node& x = N[v];
+        if (x.sigma == to && x.abstime < t && XADD(x.abstime, x.bl) > t) return v;
+        if (x.left >= 0) { v = x.left; continue; }
+        for (;;) {
+            int p = N[v].parent;
+            if (p < 0) return -1;
+            if (N[p].left == v) { v = N[p].right; break; }
+            v = p;
+        }
+    }
+    return -1;
+}
+
+// One attempt of createUnprunedTree. Returns 0, or REP_NODE_OVERFLOW. n_out = vertices created, root_out = root index.
+template <class RNG>
+__device__ int simulate_attempt(RNG& rng, const SimParams& P, const DevHost& H, const MathTables& T, SimWork& W, int& n_out, int& root_out) {
+    int n = 0, qh = 0, qt = 0, np = 0;
+    int X0; double start;
+    if (P.ishost || !P.do_gene_birth) { X0 = H.root; start = H.ep_up[H.nE - 1]; }
+    else { X0 = sample_root(rng, P, H); start = H.ep_up[H.v2e[X0]]; }
+    int root = new_node(W, n, draw_vertex(rng, P, H, T, X0, start), X0);
+    if (root < 0) { n_out = n; return REP_NODE_OVERFLOW; }
+    W.queue[qt++] = root;
+    while (qh < qt) {
+        const int li = W.queue[qh++];
+        const uint8_t ev = W.nodes[li].event;
+        int lc = -1, rc = -1;
+        if (ev == EV_LOSS || ev == EV_REPLACING_LOSS || ev == EV_LEAF || ev == EV_UNSAMPLED_LEAF) {
+            // lineage ends
+        } else {
+            const int sigma = W.nodes[li].sigma; const double t = W.nodes[li].abstime; const int ep = W.nodes[li].epoch;
+            if (ev == EV_SPECIATION) {
+                int a = H.left[sigma], b = H.right[sigma];
+                lc = new_node(W, n, draw_vertex(rng, P, H, T, a, t), a); if (lc < 0) { n_out = n; return REP_NODE_OVERFLOW; }
+                rc = new_node(W, n, draw_vertex(rng, P, H, T, b, t), b); if (rc < 0) { n_out = n; return REP_NODE_OVERFLOW; }
+            } else if (ev == EV_DUPLICATION) {
+                lc = new_node(W, n, draw_vertex(rng, P, H, T, sigma, t), sigma); if (lc < 0) { n_out = n; return REP_NODE_OVERFLOW; }
+                rc = new_node(W, n, draw_vertex(rng, P, H, T, sigma, t), sigma); if (rc < 0) { n_out = n; return REP_NODE_OVERFLOW; }
+            } else if (ev == EV_ADDITIVE_TRANSFER) {
+                const bool stay_left = rng.next_double() < 0.5;
+                int stay = new_node(W, n, draw_vertex(rng, P, H, T, sigma, t), sigma); if (stay < 0) { n_out = n; return REP_NODE_OVERFLOW; }
+                int to = sample_arc(rng, P, H, ep, sigma, t, nullptr, 0);
+                int moved = new_node(W, n, draw_vertex(rng, P, H, T, to, t), to); if (moved < 0) { n_out = n; return REP_NODE_OVERFLOW; }
+                W.nodes[li].from_arc = sigma; W.nodes[li].to_arc = to;
+                lc = stay_left ? stay : moved; rc = stay_left ? moved : stay;
+            } else {   // EV_REPLACING_TRANSFER
+                const bool stay_left = rng.next_double() < 0.5;
+                int stay = new_node(W, n, draw_vertex(rng, P, H, T, sigma, t), sigma); if (stay < 0) { n_out = n; return REP_NODE_OVERFLOW; }
+                const int first_to = sample_arc(rng, P, H, ep, sigma, t, nullptr, 0);
+                int to = first_to;
+                int victim = find_victim(W.nodes, root, to, t);
+                const int n_arcs = H.ep_off[ep + 1] - H.ep_off[ep];
+                int n_empty = 0; const int gen = ++W.mark_gen;
+                while (victim < 0 && n_empty != n_arcs - 1) {
+                    if (W.marks[to] != gen) { W.marks[to] = gen; ++n_empty; }
+                    if (n_empty != n_arcs - 1) { to = sample_arc(rng, P, H, ep, sigma, t, W.marks, gen); victim = find_victim(W.nodes, root, to, t); }
+                }
+                W.nodes[li].from_arc = sigma;
+                int moved;
+                if (victim >= 0) {
+                    moved = new_node(W, n, draw_vertex(rng, P, H, T, to, t), to); if (moved < 0) { n_out = n; return REP_NODE_OVERFLOW; }
+                    W.nodes[li].to_arc = to;
+                    Node& vn = W.nodes[victim];
+                    vn.event = EV_REPLACING_LOSS; vn.abstime = t;
+                    // drop parked replacing transfers that sit in the victim's subtree (victim included)
+                    int w = 0;
+                    for (int i = 0; i < np; ++i) {
+                        int x = W.pend[i]; bool under = false;
+                        for (int y = x; y >= 0; y = W.nodes[y].parent) if (y == victim) { under = true; break; }
+                        if (!under) W.pend[w++] = x;
+                    }
+                    np = w;
+                    vn.left = -1; vn.right = -1;
+                } else {
+                    W.nodes[li].event = EV_ADDITIVE_TRANSFER;
+                    moved = new_node(W, n, draw_vertex(rng, P, H, T, first_to, t), first_to); if (moved < 0) { n_out = n; return REP_NODE_OVERFLOW; }
+                    W.nodes[li].to_arc = first_to;
+                }
+                lc = stay_left ? stay : moved; rc = stay_left ? moved : stay;
+            }
+            W.nodes[li].left = lc; W.nodes[li].right = rc;
+            W.nodes[lc].parent = li; W.nodes[rc].parent = li;
+            for (int s = 0; s < 2; ++s) {
+                int c = s == 0 ? lc : rc;
+                if (W.nodes[c].event != EV_REPLACING_TRANSFER) W.queue[qt++] = c;
+                else {
+                    bool replaced = false;     // TreeMap.put on an equal key overwrites the value
+                    for (int i = 0; i < np; ++i) if (W.nodes[W.pend[i]].abstime == W.nodes[c].abstime) { W.pend[i] = c; replaced = true; break; }
+                    if (!replaced) W.pend[np++] = c;
+                }
+            }
+        }
+        if (qh == qt && np > 0) {      // release the oldest parked replacing transfer (largest abstime)
+            int best = 0;
+            for (int i = 1; i < np; ++i) if (W.nodes[W.pend[i]].abstime > W.nodes[W.pend[best]].abstime) best = i;
+            W.queue[qt++] = W.pend[best];
+            W.pend[best] = W.pend[--np];
+        }
+    }
+    if (W.nodes[root].bl <= 1.0e-32) W.nodes[root].bl = 0.0;
+    n_out = n; root_out = root;
+    return REP_OK;
+}
+
+// GuestTreeMachina.unprunedIsOK (:124-169) on the attached tree. Returns sampled-leaf count through *sampled.
+static __device__ bool attempt_ok(const SimParams& P, const DevHost& H, const SimWork& W, int root, int exact, int* sampled_out) {
+    int sampled = 0;
+    const bool per_leaf = W.leaf_cnt != nullptr;
+    if (per_leaf) for (int i = 0; i < H.nLeaves; ++i) W.leaf_cnt[i] = 0;
+    int v = root;
+    while (v >= 0) {
+        const Node& x = W.nodes[v];
+        if (x.event == EV_LEAF) { ++sampled; if (per_leaf) W.leaf_cnt[H.leaf_rank[x.sigma]]++; }
+        if (x.left >= 0) { v = x.left; continue; }
+        for (;;) {
+            int p = W.nodes[v].parent;
+            if (p < 0) { v = -1; break; }
+            if (W.nodes[p].left == v) { v = W.nodes[p].right; break; }
+            v = p;
+        }
+    }
+    *sampled_out = sampled;
+    if (exact != -1 && sampled != exact) return false;
+    if (sampled < P.min_leaves || sampled > P.max_leaves) return false;
+    if (per_leaf) for (int i = 0; i < H.nLeaves; ++i) { int c = W.leaf_cnt[i]; if (c < P.minper || c > P.maxper) return false; }
+    return true;
+}
+
+// ---- BD fast path ----------------------------------------------------------------------------------------------------------
+// Tiny host (HostTreeGen: "H0:T;" or "(H0:T,H1:T):0.0;") passed by value.
+
+constexpr int kBdStack = 96;
+
+struct BdVertex { double et, bl; uint8_t event; };
+
+// Same decision tree as createGuestVertex with tau == 0; u1,u2 come from one Philox block.
+__device__ __forceinline__ BdVertex bd_vertex(const SimParams& P, const TinyHost& H, int X, double start, double u1, double u2, bool want_bl, const MathTables& T) {
+    BdVertex r;
+    const bool isRoot = H.parent[X] < 0;
+    double sum = P.lambda + P.mu;      // tau == 0 on this path
+    if (sum == 0.0) sum = 1e-48;
+    const double low = H.vtime[X];
+    double bt = XDIV(-jlog(XSUB(1.0, u1)), sum);
+    double et = XSUB(start, bt);
+    if (et <= low) {
+        et = low;
+        r.bl = want_bl ? round_sig(T, XSUB(start, et), 8) : 0.0;
+        if (H.left[X] < 0) r.event = (u2 < P.rho) ? EV_LEAF : EV_UNSAMPLED_LEAF; else r.event = EV_SPECIATION;
+    } else {
+        r.bl = bt;
+        if (isRoot) r.event = (u2 < XDIV(P.lambda, sum)) ? EV_DUPLICATION : EV_LOSS;
+        else r.event = (u2 >= XDIV(P.mu, sum)) ? EV_DUPLICATION : EV_LOSS;    // (mu+tau)/sum == mu/sum
+    }
+    r.et = et;
+    return r;
+}
+
+}  // namespace sgp

@@ -1,0 +1,94 @@
+"""ctypes access to the CPU oracle (oracle/liboracle.so) — test infrastructure only, never used by the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+
+_lib = None
+
+
+def oracle():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_LIB):
+            subprocess.check_call(["make", "-C", ORACLE_DIR])
+        L = C.CDLL(ORACLE_LIB)
+        L.oracle_run.argtypes = [C.c_int, C.POINTER(C.c_char_p)]; L.oracle_run.restype = C.c_void_p
+        L.oracle_n_files.argtypes = [C.c_void_p]; L.oracle_n_files.restype = C.c_int
+        L.oracle_file_name.argtypes = [C.c_void_p, C.c_int]; L.oracle_file_name.restype = C.c_char_p
+        L.oracle_file_data.argtypes = [C.c_void_p, C.c_int]; L.oracle_file_data.restype = C.c_void_p
+        L.oracle_file_len.argtypes = [C.c_void_p, C.c_int]; L.oracle_file_len.restype = C.c_longlong
+        L.oracle_stdout.argtypes = [C.c_void_p]; L.oracle_stdout.restype = C.c_char_p
+        L.oracle_stderr.argtypes = [C.c_void_p]; L.oracle_stderr.restype = C.c_char_p
+        L.oracle_attempts.argtypes = [C.c_void_p]; L.oracle_attempts.restype = C.c_int
+        L.oracle_status.argtypes = [C.c_void_p]; L.oracle_status.restype = C.c_int
+        L.oracle_free.argtypes = [C.c_void_p]
+        L.oracle_batch.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_longlong, C.c_longlong, C.c_void_p]; L.oracle_batch.restype = C.c_double
+        L.oracle_mt_words.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
+        L.oracle_mt_doubles.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
+        L.oracle_mt_ints.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
+        L.oracle_double_to_string.argtypes = [C.c_double, C.c_char_p, C.c_int]; L.oracle_double_to_string.restype = C.c_int
+        for f in ("oracle_log", "oracle_log10", "oracle_exp"):
+            getattr(L, f).argtypes = [C.c_double]; getattr(L, f).restype = C.c_double
+        L.oracle_round_sig.argtypes = [C.c_double, C.c_int]; L.oracle_round_sig.restype = C.c_double
+        _lib = L
+    return _lib
+
+
+def _argv(app, args):
+    toks = [app.encode()] + [str(a).encode() for a in args]
+    return len(toks), (C.c_char_p * len(toks))(*toks)
+
+
+def oracle_run(app, args):
+    """Runs one reference-style invocation. Returns dict(files={path: bytes}, stdout, stderr, attempts, status)."""
+    L = oracle()
+    n, arr = _argv(app, args)
+    h = L.oracle_run(n, arr)
+    try:
+        files = {}
+        for i in range(L.oracle_n_files(h)):
+            files[L.oracle_file_name(h, i).decode()] = C.string_at(L.oracle_file_data(h, i), L.oracle_file_len(h, i))
+        return dict(files=files, stdout=L.oracle_stdout(h).decode(), stderr=L.oracle_stderr(h).decode(),
+                    attempts=L.oracle_attempts(h), status=L.oracle_status(h))
+    finally:
+        L.oracle_free(h)
+
+
+def oracle_files(app, args):
+    return oracle_run(app, args)["files"]
+
+
+STAT_COLS = ["attempts", "status", "n_unpruned", "n_pruned", "sampled_leaves", "pruned_root_time", "total_time", "vertices_created", "out_bytes"]
+
+
+def oracle_batch(app, args, first, n, want_stats=True):
+    """Replicate i runs with seed + first + i. Returns (seconds, stats[n, 26])."""
+    L = oracle()
+    k, arr = _argv(app, args)
+    st = np.zeros((n, 26), dtype=np.float64) if want_stats else None
+    sec = L.oracle_batch(k, arr, first, n, st.ctypes.data if want_stats else None)
+    return sec, st
+
+
+def oracle_double_to_string(v: float) -> str:
+    buf = C.create_string_buffer(64)
+    oracle().oracle_double_to_string(v, buf, 64)
+    return buf.value.decode()
+
+
+def oracle_mt_words(seed, n):
+    out = np.empty(n, dtype=np.uint32)
+    oracle().oracle_mt_words(str(seed).encode(), n, out.ctypes.data)
+    return out
+
+
+def oracle_mt_doubles(seed, n):
+    out = np.empty(n, dtype=np.float64)
+    oracle().oracle_mt_doubles(str(seed).encode(), n, out.ctypes.data)
+    return out

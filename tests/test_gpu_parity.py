@@ -1,0 +1,226 @@
+"""GPU parity tests: everything goes through the C ABI (libsagephy_b200.so) and is compared with the CPU oracle.
+
+Bar: byte-exact text in MT seed-replay mode (replicate i == reference-style run with -s seed+i); two-sample KS p > 0.01
+between Philox throughput mode and the MT oracle for the continuous statistics, chi-square for the discrete ones."""
+import math
+import re
+
+import numpy as np
+import pytest
+from scipy import stats
+
+import sagephy_b200 as sg
+from oracle_util import oracle_batch, oracle_double_to_string, oracle_mt_words, oracle_run, oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def with_seed(args, seed):
+    a = list(args)
+    a[a.index("-s") + 1] = str(seed)
+    return a
+
+
+def assert_replay_parity(ctx, app, args, n, prefix):
+    seed0 = int(args[args.index("-s") + 1])
+    b = ctx.run(app, args, n=n, rng=sg.RNG_MT_REPLAY)
+    status = b.rep_status
+    for i in range(n):
+        want = oracle_run(app, with_seed(args, seed0 + i))
+        if want["status"] == 1:
+            assert status[i] == 1, (i, status[i])
+            assert b.replicate(3, i) == b"Failed to produce valid pruned tree within max allowed attempts.\n"
+            continue
+        assert status[i] == 0, (app, args, i, status[i])
+        assert b.attempts[i] == want["attempts"]
+        got = b.files(i)
+        assert set(prefix + k for k in got) == set(want["files"]), (sorted(got), sorted(want["files"]))
+        for sfx, data in got.items():
+            exp = want["files"][prefix + sfx]
+            if data != exp:
+                k = next((j for j in range(min(len(data), len(exp))) if data[j] != exp[j]), min(len(data), len(exp)))
+                raise AssertionError(f"{app} {args} replicate {i} stream {sfx}: first difference at byte {k}:\n"
+                                     f" gpu   : {data[max(0, k - 60):k + 60]!r}\n oracle: {exp[max(0, k - 60):k + 60]!r}")
+    return b
+
+
+# ---- device-side primitives ------------------------------------------------------------------------------------------------
+def test_device_double_to_string_matches_oracle(ctx):
+    rng = np.random.default_rng(3)
+    vals = np.concatenate([
+        rng.random(4000), -np.log1p(-rng.random(4000)) / 5.05, np.round(rng.random(2000), 8), rng.random(2000) * 1e-4, rng.random(2000) * 1e8,
+        rng.random(1000) * 10.0 ** rng.integers(-300, 300, 1000), 2.0 ** np.arange(-1074, 1024, 7.0),
+        np.array([0.0, 1.0, 100.0, 1e7, 9999999.999999998, 1e-3, 9.999999999999999e-4, 1e21, 1e22, 1e23, 4.9e-324, 1.7976931348623157e308, 1e-64, 1234567.0])])
+    got = ctx.double_to_string(vals)
+    for v, s in zip(vals, got):
+        assert s == oracle_double_to_string(float(v)), (v, s)
+
+
+def test_device_math_is_bit_exact_with_oracle(ctx):
+    L = oracle()
+    rng = np.random.default_rng(4)
+    x = np.concatenate([rng.random(20000), rng.random(5000) * 10.0 ** rng.integers(-100, 100, 5000), 1.0 - rng.random(5000) * 1e-9])
+    for fn, f in ((0, L.oracle_log), (1, L.oracle_log10)):
+        got = ctx.math(fn, x)
+        want = np.array([f(float(v)) for v in x])
+        assert (got.view(np.uint64) == want.view(np.uint64)).all()
+    y = (rng.random(20000) - 0.5) * 80
+    assert (ctx.math(2, y).view(np.uint64) == np.array([L.oracle_exp(float(v)) for v in y]).view(np.uint64)).all()
+    z = np.concatenate([x, -x[:1000], rng.random(5000) * 40])
+    assert (ctx.math(3, z).view(np.uint64) == np.array([L.oracle_round_sig(float(v), 8) for v in z]).view(np.uint64)).all()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 20260101, 2 ** 62, -1, -300])
+def test_device_mt19937_stream(ctx, seed):
+    assert (ctx.mt_words(seed, 3000) == oracle_mt_words(seed, 3000)).all()
+
+
+# ---- seed-replay parity: HostTreeGen -------------------------------------------------------------------------------------------
+HOST_CASES = [
+    ["-s", "1", "-min", "3", "-max", "4", "-p", "0.8", "1.0", "2.0", "0.5", "o"],
+    ["-s", "10", "1.0", "3.0", "0.3", "o"],                                                        # defaults
+    ["-s", "20", "-min", "10", "-max", "40", "-p", "0.6", "2.0", "1.5", "0.5", "o"],
+    ["-s", "30", "-bi", "-min", "4", "-max", "60", "1.0", "3.0", "0.2", "o"],                      # forced bifurcation, minper = 1
+    ["-s", "40", "-nox", "-min", "2", "-max", "30", "1.0", "2.5", "0.4", "o"],                     # no tags
+    ["-s", "50", "-stem", "0.25", "-vp", "Sp", "-min", "2", "-max", "30", "1.0", "2.5", "0.4", "o"],
+    ["-s", "60", "-min", "0", "-max", "50", "0.7", "1.0", "2.0", "o"],                             # empty pruned trees occur
+    ["-s", "70", "-min", "30", "-max", "30", "-a", "40", "1.0", "3.0", "0.3", "o"],                # some replicates hit max attempts
+    ["-s", "80", "-p", "0.35", "-min", "1", "-max", "20", "1.3", "2.0", "0.0", "o"],
+]
+
+
+@pytest.mark.parametrize("args", HOST_CASES, ids=[" ".join(a[2:-1]) for a in HOST_CASES])
+def test_host_tree_gen_replay_is_byte_exact(ctx, args):
+    assert_replay_parity(ctx, "HostTreeGen", args, 24, "o")
+
+
+def test_host_tree_gen_readme_config_replay(ctx):
+    # BASELINE config C1: HostTreeGen -min 100 -max 100 1.0 5.0 0.05 (about 289 attempts per accepted tree)
+    b = assert_replay_parity(ctx, "HostTreeGen", ["-s", "7", "-min", "100", "-max", "100", "1.0", "5.0", "0.05", "o"], 12, "o")
+    assert (b.sampled_leaves == 100).all()
+
+
+def test_host_tree_gen_quiet_and_usage(ctx):
+    args = ["-s", "5", "-q", "-min", "3", "-max", "20", "1.0", "2.0", "0.3"]
+    b = ctx.run("HostTreeGen", args, n=3, rng=sg.RNG_MT_REPLAY)
+    want = "".join(oracle_run("HostTreeGen", with_seed(args, 5 + i))["stdout"] for i in range(3))
+    assert b.stdout == want
+    u = ctx.run("HostTreeGen", ["1.0", "2.0"], n=1)
+    assert u.status_code == sg.STATUS_USAGE and u.stdout.startswith("Usage:")
+    with pytest.raises(sg.SagephyError):
+        ctx.run("HostTreeGen", ["-bogus", "1.0", "2.0", "0.3", "o"], n=1)
+
+
+# ---- seed-replay parity: GuestTreeGen --------------------------------------------------------------------------------------------
+HOST5 = "((A:0.4,B:0.4):0.6,(C:0.7,(D:0.2,E:0.2):0.5):0.3):0.2;"
+HOST8 = "(((a:0.1,b:0.1):0.5,(c:0.3,d:0.3):0.3):0.4,((e:0.2,f:0.2):0.6,(g:0.5,h:0.5):0.3):0.2):0.1;"
+GUEST_CASES = [
+    ["-s", "1", "-db", "none", HOST5, "0.5", "0.4", "0.0", "o"],                        # no transfers
+    ["-s", "2", "-db", "none", HOST5, "0.5", "0.4", "0.6", "o"],                        # uniform recipient
+    ["-s", "3", HOST5, "0.5", "0.4", "0.6", "o"],                                       # code default: -db simple
+    ["-s", "4", "-db", "exponential", "-dbr", "1.5", HOST8, "0.4", "0.3", "0.8", "o"],
+    ["-s", "5", "-rt", "1.0", "-db", "none", HOST8, "0.4", "0.3", "1.2", "o"],          # replacing only
+    ["-s", "6", "-rt", "0.0", HOST8, "0.4", "0.3", "1.0", "o"],                         # additive only
+    ["-s", "7", "-gb", "-gbc", "2.1", HOST8, "0.4", "0.3", "0.5", "o"],                 # gene birth sampling
+    ["-s", "8", "-nox", "-p", "0.7", HOST8, "0.6", "0.2", "0.4", "o"],
+    ["-s", "9", "-stem", "0.3", "-min", "3", "-max", "40", "-minper", "0", "-maxper", "6", HOST8, "0.8", "0.5", "0.5", "o"],
+    ["-s", "10", "-vp", "Gene", "-a", "3", "-min", "12", "-max", "14", HOST5, "0.5", "0.4", "0.3", "o"],   # many failures
+]
+
+
+@pytest.mark.parametrize("args", GUEST_CASES, ids=[" ".join(a[2:a.index(HOST5) if HOST5 in a else a.index(HOST8)]) or "plain" for a in GUEST_CASES])
+def test_guest_tree_gen_replay_is_byte_exact(ctx, args):
+    assert_replay_parity(ctx, "GuestTreeGen", args, 24, "o")
+
+
+def test_guest_tree_gen_on_generated_100_leaf_host(ctx, tmp_path):
+    # BASELINE config C3 shape: host = pruned tree of a C1 run, dup/loss/trans 0.3, additive + replacing transfers
+    host = oracle_run("HostTreeGen", ["-s", "7", "-min", "100", "-max", "100", "1.0", "5.0", "0.05", "sp"])["files"]["sp.pruned.tree"]
+    p = tmp_path / "species.pruned.tree"
+    p.write_bytes(host)
+    for db in ("none", "simple", "exponential"):
+        assert_replay_parity(ctx, "GuestTreeGen", ["-s", "100", "-db", db, str(p), "0.3", "0.3", "0.3", "o"], 6, "o")
+
+
+# ---- Philox throughput mode: distributions ---------------------------------------------------------------------------------------
+def ks_ok(a, b):
+    return stats.ks_2samp(a, b).pvalue > 0.01
+
+
+def chi2_two_sample_ok(a, b, max_bins=40):
+    lo, hi = int(min(a.min(), b.min())), int(max(a.max(), b.max()))
+    edges = np.unique(np.quantile(np.concatenate([a, b]), np.linspace(0, 1, max_bins + 1)).astype(int))
+    edges = np.concatenate([[lo - 1], edges[(edges > lo) & (edges < hi)], [hi]])
+    ha, _ = np.histogram(a, bins=edges + 0.5)
+    hb, _ = np.histogram(b, bins=edges + 0.5)
+    keep = (ha + hb) > 10
+    if keep.sum() < 2:
+        return True
+    return stats.chi2_contingency(np.vstack([ha[keep], hb[keep]]))[1] > 0.01
+
+
+def test_host_tree_gen_philox_matches_oracle_distributions(ctx):
+    n = 100000
+    args = ["-s", "20260101", "-min", "2", "-max", "1000", "-p", "0.8", "1.0", "3.0", "0.5", "x"]
+    b = ctx.run("HostTreeGen", args, n=n, rng=sg.RNG_PHILOX, stream_mask=0b0010)
+    assert (b.rep_status == 0).all()
+    sec, st = oracle_batch("HostTreeGen", args, 0, n)
+    assert chi2_two_sample_ok(b.sampled_leaves.astype(float), st[:, 4])
+    assert ks_ok(b.root_times, st[:, 5])                       # height of the pruned tree's root
+    assert ks_ok(b.total_times, st[:, 6])
+    ev = b.event_counts
+    for e in (4, 5, 3):                                         # duplications (births), losses, unsampled leaves
+        assert chi2_two_sample_ok(ev[:, e].astype(float), st[:, 9 + e]), e
+    assert chi2_two_sample_ok(b.attempts.astype(float), st[:, 0])
+    # closed form: P(2 <= K <= 1000) for the rho-thinned process is not needed here; check E[attempts] agreement instead
+    assert abs(b.attempts.mean() - st[:, 0].mean()) < 0.02
+
+
+def test_host_tree_gen_philox_acceptance_rate_closed_form(ctx):
+    # P(N = 100 | lam 5, mu 0.05, T 1) = 3.4593e-3 -> 289.08 trees per accept; Attempts = trees + 1
+    n = 4000
+    b = ctx.run("HostTreeGen", ["-s", "1", "-min", "100", "-max", "100", "1.0", "5.0", "0.05", "x"], n=n, rng=sg.RNG_PHILOX, stream_mask=0b0010)
+    assert (b.rep_status == 0).all() and (b.sampled_leaves == 100).all()
+    trees = b.attempts - 1
+    assert abs(trees.mean() - 289.08) < 4.5 * 289.08 / math.sqrt(n)
+    # results do not depend on how replicates are sharded: same global ids -> same bytes
+    c = ctx.run("HostTreeGen", ["-s", "1", "-min", "100", "-max", "100", "1.0", "5.0", "0.05", "x"], n=100, offset=1000, rng=sg.RNG_PHILOX, stream_mask=0b0010)
+    off = b.offsets(1)
+    assert c.stream(1) == b.stream(1)[int(off[1000]):int(off[1100])]
+
+
+def test_guest_tree_gen_philox_matches_oracle_distributions(ctx):
+    n = 30000
+    for db in ("none", "simple"):
+        args = ["-s", "777", "-db", db, HOST8, "0.5", "0.4", "0.7", "x"]
+        b = ctx.run("GuestTreeGen", args, n=n, rng=sg.RNG_PHILOX, stream_mask=0b0010)
+        ok = b.rep_status == 0
+        assert ok.all()
+        sec, st = oracle_batch("GuestTreeGen", args, 0, n)
+        assert chi2_two_sample_ok(b.sampled_leaves.astype(float), st[:, 4])
+        assert ks_ok(b.total_times, st[:, 6])
+        ev = b.event_counts
+        for e in (0, 4, 5, 6, 7, 8):
+            assert chi2_two_sample_ok(ev[:, e].astype(float), st[:, 9 + e]), (db, e)
+        assert chi2_two_sample_ok(b.attempts.astype(float), st[:, 0])
+
+
+# ---- size-independent properties at larger scale ---------------------------------------------------------------------------------
+def test_emitted_trees_are_well_formed_at_scale(ctx):
+    n = 20000
+    b = ctx.run("HostTreeGen", ["-s", "9", "-min", "100", "-max", "100", "-p", "0.8", "1.0", "5.0", "0.05", "x"], n=n, rng=sg.RNG_PHILOX)
+    assert (b.rep_status == 0).all()
+    pruned, off = b.stream(1), b.offsets(1)
+    assert off[-1] == len(pruned) and (np.diff(off.astype(np.int64)) > 0).all()
+    assert pruned.count(b"\n") == n and pruned.count(b"[NAME=PrunedTree];\n") == n
+    assert pruned.count(b"VERTEXTYPE=Leaf]") == 100 * n          # exactly 100 sampled leaves in every pruned tree
+    for i in (0, 1, n // 2, n - 1):
+        t = pruned[int(off[i]):int(off[i + 1])].decode()
+        bare = re.sub(r"\[[^\]]*\]", "", t)
+        assert bare.count("(") == bare.count(")") == 99 and bare.count(",") == 99
+        ids = sorted(int(x) for x in re.findall(r"\[ID=(\d+) ", t))
+        assert ids == list(range(199))
+        info = b.replicate(3, i).decode()
+        assert "No. of vertices:\t199\n" in info and "No. of extant leaves:\t100\n" in info
+    s = b.summary()
+    assert s.n_ok == n and s.leaf_hist[100] == n and s.out_bytes[1] == len(pruned)

@@ -1,0 +1,238 @@
+"""CPU tests: pin the oracle (the reference has no tests of its own, so the pins are closed forms, independent
+re-implementations and the worked example of SURVEY.md Appendix D) and check the C-ABI library loads."""
+import ctypes as C
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle_util import (oracle, oracle_batch, oracle_double_to_string, oracle_files, oracle_mt_doubles, oracle_mt_words,
+                         oracle_run)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+# ---- RNG -----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", [0, 1, 12345, 2 ** 31, 2 ** 63 - 1, (1 << 70) + 5, -1, -129, -(1 << 40)])
+def test_mt_seeding_matches_numpy_init_by_array(seed):
+    # PRNG.get16bytes + MersenneTwisterRNG2 ctor == MT19937 init_by_array over 4 big-endian words
+    nbytes = max(1, (seed.bit_length() + 8) // 8) if seed >= 0 else max(1, ((-seed - 1).bit_length() + 8) // 8)
+    raw = seed.to_bytes(nbytes, "big", signed=True)
+    # BigInteger.toByteArray is minimal: strip redundant sign bytes
+    while len(raw) > 1 and ((raw[0] == 0 and raw[1] < 0x80) or (raw[0] == 0xFF and raw[1] >= 0x80)):
+        raw = raw[1:]
+    sixteen = (b"\0" * 16 + raw)[-16:]
+    key = np.frombuffer(sixteen, dtype=">u4").astype(np.uint32)
+    bg = np.random.MT19937()
+    bg._legacy_seeding(key)
+    want = bg.random_raw(2000).astype(np.uint32)
+    got = oracle_mt_words(seed, 2000)
+    assert (want == got).all()
+
+
+def test_java_next_double_layout():
+    w = oracle_mt_words(77, 2000).astype(np.uint64)
+    d = oracle_mt_doubles(77, 1000)
+    want = (((w[0::2] >> np.uint64(6)) << np.uint64(27)) + (w[1::2] >> np.uint64(5))).astype(np.float64) * 2.0 ** -53
+    assert (d == want).all()
+    assert ((d >= 0) & (d < 1)).all()
+
+
+def test_java_next_int_bounded():
+    L = oracle()
+    for bound in (1, 2, 3, 7, 16, 100, 1000, 2 ** 30 + 1):
+        out = np.empty(5000, dtype=np.int32)
+        L.oracle_mt_ints(b"5", bound, 5000, out.ctypes.data)
+        assert out.min() >= 0 and out.max() < bound
+        if bound <= 16:
+            assert len(set(out.tolist())) == bound
+    # power of two path: (n * next(31)) >> 31
+    w = oracle_mt_words(5, 10)
+    out = np.empty(10, dtype=np.int32)
+    L.oracle_mt_ints(b"5", 16, 10, out.ctypes.data)
+    assert (out == ((16 * (w.astype(np.int64) >> 1)) >> 31)).all()
+
+
+# ---- Double.toString / fdlibm ----------------------------------------------------------------------------------------------
+JAVA_DOUBLE_STRINGS = {   # values documented for java.lang.Double.toString (JDK >= 19 shortest-repr behaviour)
+    1.0: "1.0", 100.0: "100.0", 1e7: "1.0E7", 9999999.0: "9999999.0", 0.001: "0.001", 0.0001: "1.0E-4", 1e-5: "1.0E-5",
+    1e23: "1.0E23", 2e23: "2.0E23", 4.9e-324: "4.9E-324", 1.7976931348623157e308: "1.7976931348623157E308", 0.1: "0.1",
+    0.3: "0.3", 1.0 / 3.0: "0.3333333333333333", 2.0 / 3.0: "0.6666666666666666", 123456789.0: "1.23456789E8", 0.5: "0.5",
+    1e-64: "1.0E-64", 2.2250738585072014e-308: "2.2250738585072014E-308", 1e21: "1.0E21", 12345.678: "12345.678",
+    8.41e21: "8.41E21", 5e-324 * 3: "1.5E-323", 0.0: "0.0", -2.5: "-2.5", float("inf"): "Infinity", float("nan"): "NaN",
+}
+
+
+def test_double_to_string_known_values():
+    for v, s in JAVA_DOUBLE_STRINGS.items():
+        assert oracle_double_to_string(v) == s, (v, oracle_double_to_string(v), s)
+    assert oracle_double_to_string(-0.0) == "-0.0"
+
+
+def test_double_to_string_round_trips_and_is_shortest():
+    rng = np.random.default_rng(1)
+    vals = np.concatenate([rng.random(3000), -np.log1p(-rng.random(3000)) / 5.05, np.round(rng.random(2000), 8),
+                           rng.random(1000) * 10.0 ** rng.integers(-30, 30, 1000)])
+    for v in vals:
+        s = oracle_double_to_string(float(v))
+        assert float(s.replace("E", "e")) == v
+        # Python's repr is also the shortest round-tripping decimal: same digit string
+        digits = re.sub(r"[.\-]|E.*$", "", s).strip("0")
+        pd = re.sub(r"[.\-]|e.*$", "", repr(float(v))).strip("0")
+        assert digits == pd, (v, s, repr(float(v)))
+
+
+def test_fdlibm_restatements_within_one_ulp():
+    L = oracle()
+    rng = np.random.default_rng(2)
+    for x in np.concatenate([rng.random(5000), rng.random(2000) * 10.0 ** rng.integers(-200, 200, 2000)]):
+        x = float(x)
+        if x <= 0:
+            continue
+        a, b = L.oracle_log(x), math.log(x)
+        assert abs(a - b) <= abs(math.ulp(b)), x
+        a, b = L.oracle_log10(x), math.log10(x)
+        assert abs(a - b) <= 2 * abs(math.ulp(b)) + 1e-300, x
+    for y in (rng.random(3000) - 0.5) * 60:
+        a, b = L.oracle_exp(float(y)), math.exp(float(y))
+        assert abs(a - b) <= math.ulp(b)
+    assert L.oracle_log(1.0) == 0.0 and L.oracle_exp(0.0) == 1.0 and L.oracle_log10(1000.0) == 3.0 and L.oracle_log10(1e22) == 22.0
+
+
+def test_round_to_significant_figures():
+    L = oracle()
+    assert L.oracle_round_sig(0.123456789, 8) == 0.12345679
+    assert L.oracle_round_sig(0.1085868017185789 + 0.24064737132287545, 8) == 0.34923417
+    assert L.oracle_round_sig(31.875615123, 8) == 31.875615
+    assert L.oracle_round_sig(0.0, 8) == 0.0
+    assert L.oracle_round_sig(1.0, 8) == 1.0
+    assert L.oracle_round_sig(-0.55233891499, 8) == -0.55233891
+
+
+# ---- golden: SURVEY.md Appendix D (independent hand restatement by the surveyor) -----------------------------------------
+def test_appendix_d_worked_example():
+    args = ["-s", "1", "-min", "3", "-max", "4", "-p", "0.8", "1.0", "2.0", "0.5", "out"]
+    r = oracle_run("HostTreeGen", args)
+    f = r["files"]
+    with open(os.path.join(GOLDEN, "survey_appendix_d.txt")) as fh:
+        gold = dict(line.rstrip("\n").split("\t", 1) for line in fh if "\t" in line)
+    assert f["out.unpruned.tree"].decode().strip() == gold["unpruned.tree"]
+    assert f["out.pruned.tree"].decode().strip() == gold["pruned.tree"]
+    info = f["out.unpruned.info"].decode()
+    assert "Attempts:\t9\n" in info and "No. of vertices:\t11\n" in info and "No. of extant leaves:\t6\n" in info
+    assert "No. of births:\t5\n" in info and "No. of deaths:\t0\n" in info and "Total branch time:\t3.1875615\n" in info
+    assert "Birth ML estimate:\t1.5685972\n" in info and "Death ML estimate:\t0.0\n" in info
+    pinfo = f["out.pruned.info"].decode()
+    assert "No. of vertices:\t7\n" in pinfo and "Total branch time:\t2.585425\n" in pinfo and "ML estimate" not in pinfo
+    assert info.startswith("# HOSTTREEGEN\nArguments:\t[-s, 1, -min, 3, -max, 4, -p, 0.8, 1.0, 2.0, 0.5, out]\n")
+
+
+# ---- closed-form known answers ----------------------------------------------------------------------
+def bd_pmf(n, lam, mu, T):
+    E = math.exp((lam - mu) * T)
+    beta = lam * (E - 1) / (lam * E - mu)
+    alpha = mu * (E - 1) / (lam * E - mu)
+    return alpha if n == 0 else (1 - alpha) * (1 - beta) * beta ** (n - 1)
+
+
+def test_leaf_count_distribution_matches_birth_death_closed_form():
+    lam, mu, T, n = 2.0, 0.5, 1.0, 20000
+    sec, st = oracle_batch("HostTreeGen", ["-s", "100", "-min", "0", "-max", "100000", str(T), str(lam), str(mu), "x"], 0, n)
+    leaves = st[:, 4].astype(int)
+    assert (st[:, 1] == 0).all() and (st[:, 0] == 2).all()          # every first attempt is accepted; Attempts = trees + 1
+    kmax = 15
+    obs = np.array([(leaves == k).sum() for k in range(kmax)] + [(leaves >= kmax).sum()], dtype=float)
+    p = np.array([bd_pmf(k, lam, mu, T) for k in range(kmax)]); p = np.append(p, 1 - p.sum())
+    chi2 = ((obs - n * p) ** 2 / (n * p)).sum()
+    assert chi2 < 45.0, chi2          # 15 dof: P(chi2 > 45) ~ 8e-5
+    # E[#losses] = mu (E - 1) / (lam - mu)
+    E = math.exp((lam - mu) * T)
+    losses = st[:, 9 + 5].mean()
+    assert abs(losses - mu * (E - 1) / (lam - mu)) < 0.05
+
+
+def test_acceptance_rate_of_readme_example():
+    # P(N = 100 | lam 5, mu 0.05, T 1) = 3.4593e-3  ->  289.08 trees per accepted tree (Attempts = trees + 1)
+    sec, st = oracle_batch("HostTreeGen", ["-s", "500", "-min", "100", "-max", "100", "1.0", "5.0", "0.05", "x"], 0, 60)
+    trees = st[:, 0] - 1
+    assert (st[:, 4] == 100).all() and (st[:, 3] == 199).all()
+    assert abs(trees.mean() - 289.08) < 4.5 * 289.08 / math.sqrt(60)
+
+
+# ---- structural invariants of the emitted files ----------------------------------------------------------------------------------
+def newick_leaves(s):
+    return re.findall(r"[(,]([A-Za-z]+\d+(?:_\d+)?):", s)
+
+
+def test_host_tree_gen_files_are_consistent():
+    f = oracle_files("HostTreeGen", ["-s", "42", "-min", "20", "-max", "30", "-p", "0.7", "1.0", "4.0", "0.4", "o"])
+    un, pr = f["o.unpruned.tree"].decode(), f["o.pruned.tree"].decode()
+    assert un.endswith("[NAME=UnprunedTree];\n") and pr.endswith("[NAME=PrunedTree];\n")
+    n_leaf = pr.count("VERTEXTYPE=Leaf]")
+    assert 20 <= n_leaf <= 30 and "UnsampledLeaf" not in pr and "Loss" not in pr
+    ids_pr = sorted(int(x) for x in re.findall(r"\[ID=(\d+) ", pr))
+    assert ids_pr == list(range(2 * n_leaf - 1))                  # survivors are numbered 0..2L-2 (PruningHelper.java:25-65)
+    ids_un = sorted(int(x) for x in re.findall(r"\[ID=(\d+) ", un))
+    assert ids_un == list(range(len(ids_un)))
+    bare = re.sub(r"\[[^\]]*\]", "", un)
+    assert bare.count("(") == bare.count(")") == (len(ids_un) - 1) // 2
+
+
+def test_guest_tree_gen_all_bias_modes_run_and_are_deterministic():
+    host = "((A:0.4,B:0.4):0.6,(C:0.7,(D:0.2,E:0.2):0.5):0.3):0.2;"
+    for extra in (["-db", "none"], ["-db", "simple"], ["-db", "exponential", "-dbr", "1.5"], ["-gb", "-gbc", "2.1"], ["-rt", "1.0"], ["-nox"]):
+        args = ["-s", "9"] + extra + [host, "0.6", "0.4", "0.8", "g"]
+        a, b = oracle_run("GuestTreeGen", args), oracle_run("GuestTreeGen", args)
+        assert a["status"] == 0, a["stderr"]
+        assert a["files"] == b["files"]
+        names = set(a["files"])
+        assert {"g.unpruned.tree", "g.pruned.tree", "g.unpruned.info", "g.pruned.info"} <= names
+        assert ("g.pruned.guest2host" in names) == ("-nox" not in extra)
+        if "-nox" not in extra:
+            g2h = a["files"]["g.unpruned.guest2host"].decode()
+            assert g2h.startswith("# GUEST-TO-HOST MAP\nHost tree:\t(")
+            assert "DISCTYPE=RBTreeEpochDiscretiser NMIN=1 NMAX=1 DELTAT=NaN NROOT=1];" in g2h
+            lm = a["files"]["g.pruned.leafmap"].decode().strip().split("\n")
+            assert all(re.fullmatch(r"G\d+_\d+\t[A-E]", row) for row in lm)
+
+
+def test_replacing_transfers_produce_replacing_losses():
+    host = "((A:0.4,B:0.4):0.6,(C:0.7,(D:0.2,E:0.2):0.5):0.3):0.2;"
+    tot_rt = tot_rl = 0
+    for seed in range(1, 30):
+        info = oracle_files("GuestTreeGen", ["-s", str(seed), "-rt", "1.0", "-db", "none", "-max", "100000", "-maxper", "100000", host, "0.5", "0.3", "1.0", "g"])["g.unpruned.info"].decode()
+        tot_rt += int(re.search(r"replacing transfers:\t(\d+)", info).group(1))
+        tot_rl += int(re.search(r"replacing losses:\t(\d+)", info).group(1))
+        assert int(re.search(r"additive transfers:\t(\d+)", info).group(1)) >= 0
+    assert tot_rt > 0 and tot_rl > 0 and tot_rl <= tot_rt      # a victim may later be detached together with its ancestor's subtree
+
+
+def test_max_attempts_failure_and_usage():
+    r = oracle_run("HostTreeGen", ["-s", "1", "-min", "500", "-max", "500", "-a", "5", "1.0", "1.0", "0.5", "f"])
+    assert r["status"] == 1 and r["files"] == {"f.info": b"Failed to produce valid pruned tree within max allowed attempts.\n"}
+    assert r["attempts"] == 6
+    assert oracle_run("HostTreeGen", ["1.0", "1.0"])["stdout"].startswith("Usage:")
+    assert oracle_run("GuestTreeGen", ["-h"])["stdout"].startswith("Usage:")
+
+
+# ---- the product library: loads on a CPU-only box, exports its ABI, and refuses to run without a GPU ---------------------------------
+def test_c_abi_library_exports_every_declared_symbol():
+    import sagephy_b200 as sg
+    lib = sg.load_library()
+    header = open(os.path.join(ROOT, "include", "sagephy_b200.h")).read()
+    declared = set(re.findall(r"\b(sgp_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(sg.EXPORTED_SYMBOLS), declared ^ set(sg.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert getattr(lib, sym) is not None
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    import sagephy_b200 as sg
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(sg.SagephyError):
+        sg.Context(0)
