@@ -364,6 +364,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     e.blob = d_blob.p; e.gname_off = d_gname.p; e.leafname_off = d_leafname.p; e.ep_times = hd.ep_times.p;
     // sizes are laid out [stream][n+1] so that one scan per stream yields offsets with the total in the last slot
     DevBuf<unsigned long long> sizes_n; sizes_n.alloc((size_t)ST_COUNT * n);
+    CK(cudaMemsetAsync(sizes_n.p, 0, (size_t)ST_COUNT * n * sizeof(unsigned long long), st));
     e.sizes = sizes_n.p; e.offsets = offsets.p;
     const unsigned emit_blocks = (unsigned)((n * 32 + 127) / 128);
     ph.start();
