@@ -74,7 +74,9 @@ typedef struct {
 typedef struct {
     int64_t n_ok, n_failed;
     int64_t attempts_total;           /* sum of "Attempts:" over replicates */
-    int64_t vertices_sampled;         /* vertices created over all attempts (algorithmic work of the sampler) */
+    int64_t vertices_sampled;         /* vertices created in attempts that ran to completion (work of the sampler) */
+    int64_t vertices_abandoned;       /* vertices of attempts cut off because a smaller attempt index was accepted (parallel search overhead) */
+    int64_t attempts_completed;       /* attempts that ran to completion (>= the attempts the sequential retry loop needs) */
     int64_t event_counts[17];         /* unpruned trees, indexed by GuestVertex.Event ordinal */
     int64_t leaf_hist[SGP_HIST_LEAF_BINS];   /* sampled leaves per accepted tree (last bin = overflow) */
     int64_t out_bytes[SGP_STREAM_COUNT];

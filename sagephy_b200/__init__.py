@@ -41,7 +41,7 @@ class BatchOpts(C.Structure):
 
 
 class SummaryStruct(C.Structure):
-    _fields_ = [("n_ok", C.c_int64), ("n_failed", C.c_int64), ("attempts_total", C.c_int64), ("vertices_sampled", C.c_int64),
+    _fields_ = [("n_ok", C.c_int64), ("n_failed", C.c_int64), ("attempts_total", C.c_int64), ("vertices_sampled", C.c_int64), ("vertices_abandoned", C.c_int64), ("attempts_completed", C.c_int64),
                 ("event_counts", C.c_int64 * 17), ("leaf_hist", C.c_int64 * 1025), ("out_bytes", C.c_int64 * 8)]
 
 
@@ -102,19 +102,21 @@ class Summary:
     n_failed: int
     attempts_total: int
     vertices_sampled: int
+    vertices_abandoned: int
+    attempts_completed: int
     event_counts: np.ndarray
     leaf_hist: np.ndarray
     out_bytes: np.ndarray
 
     def as_vector(self) -> np.ndarray:
         """Flat int64 vector (what the multi-GPU driver all-reduces)."""
-        return np.concatenate([np.array([self.n_ok, self.n_failed, self.attempts_total, self.vertices_sampled], dtype=np.int64),
+        return np.concatenate([np.array([self.n_ok, self.n_failed, self.attempts_total, self.vertices_sampled, self.vertices_abandoned, self.attempts_completed], dtype=np.int64),
                                self.event_counts, self.leaf_hist, self.out_bytes])
 
     @staticmethod
     def from_vector(v: np.ndarray) -> "Summary":
         v = np.asarray(v, dtype=np.int64)
-        return Summary(int(v[0]), int(v[1]), int(v[2]), int(v[3]), v[4:21].copy(), v[21:21 + 1025].copy(), v[21 + 1025:21 + 1025 + 8].copy())
+        return Summary(int(v[0]), int(v[1]), int(v[2]), int(v[3]), int(v[4]), int(v[5]), v[6:23].copy(), v[23:23 + 1025].copy(), v[23 + 1025:23 + 1025 + 8].copy())
 
 
 class Batch:
@@ -215,7 +217,7 @@ class Batch:
     def summary(self) -> Summary:
         s = SummaryStruct()
         self._lib.sgp_batch_summary(self._h, C.byref(s))
-        return Summary(s.n_ok, s.n_failed, s.attempts_total, s.vertices_sampled, np.array(s.event_counts, dtype=np.int64),
+        return Summary(s.n_ok, s.n_failed, s.attempts_total, s.vertices_sampled, s.vertices_abandoned, s.attempts_completed, np.array(s.event_counts, dtype=np.int64),
                        np.array(s.leaf_hist, dtype=np.int64), np.array(s.out_bytes, dtype=np.int64))
 
     def timings(self) -> dict:

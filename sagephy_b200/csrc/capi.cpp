@@ -106,7 +106,7 @@ const char* sgp_batch_out_prefix(const sgp_batch* b) { return b ? b->b.out_prefi
 void sgp_batch_summary(sgp_batch* b, sgp_summary* out) {
     if (!b || !out) return;
     const Summary& s = b->b.summary;
-    out->n_ok = s.n_ok; out->n_failed = s.n_failed; out->attempts_total = s.attempts_total; out->vertices_sampled = s.vertices_sampled;
+    out->n_ok = s.n_ok; out->n_failed = s.n_failed; out->attempts_total = s.attempts_total; out->vertices_sampled = s.vertices_sampled; out->vertices_abandoned = s.vertices_abandoned; out->attempts_completed = s.attempts_completed;
     for (int i = 0; i < 17; ++i) out->event_counts[i] = s.event_counts[i];
     for (int i = 0; i < SGP_HIST_LEAF_BINS; ++i) out->leaf_hist[i] = s.leaf_hist[i];
     for (int i = 0; i < 8; ++i) out->out_bytes[i] = s.out_bytes[i];

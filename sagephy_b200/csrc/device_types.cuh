@@ -53,7 +53,9 @@ struct RepInfo {
     double total_u, beneath_u, total_p, beneath_p;
     int32_t cnt_u[EV_COUNT];
     int32_t cnt_p[EV_COUNT];
-    uint64_t vertices_sampled;   // vertices created over all attempts of this replicate (work counter)
+    uint64_t vertices_sampled;   // vertices created in attempts that ran to completion (work counter)
+    uint64_t vertices_abandoned; // vertices of attempts that were cut off because a smaller attempt index had been accepted
+    int32_t attempts_completed; int32_t pad2;
 };
 
 enum RepStatus : int32_t { REP_OK = 0, REP_MAX_ATTEMPTS = 1, REP_NODE_OVERFLOW = 2, REP_STACK_OVERFLOW = 3, REP_MODEL_ERROR = 4, REP_PENDING = 5 };

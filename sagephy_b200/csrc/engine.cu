@@ -64,13 +64,15 @@ __global__ void k_root_times(const RepInfo* info, const long long* node_off, con
     out[i] = (x.status == REP_OK && x.p_root >= 0) ? nodes[node_off[i] + x.p_root].abstime : 0.0;
 }
 
-struct DevSummary { unsigned long long n_ok, n_failed, attempts_total, vertices; unsigned long long ev[17]; unsigned long long leaf_hist[1025]; };
+struct DevSummary { unsigned long long n_ok, n_failed, attempts_total, vertices, vertices_abandoned, attempts_completed; unsigned long long ev[17]; unsigned long long leaf_hist[1025]; };
 __global__ void k_summary(const RepInfo* info, long long n, DevSummary* s) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const RepInfo& x = info[i];
     atomicAdd(&s->attempts_total, (unsigned long long)x.attempts);
     atomicAdd(&s->vertices, (unsigned long long)x.vertices_sampled);
+    atomicAdd(&s->vertices_abandoned, (unsigned long long)x.vertices_abandoned);
+    atomicAdd(&s->attempts_completed, (unsigned long long)x.attempts_completed);
     if (x.status == REP_OK) {
         atomicAdd(&s->n_ok, 1ULL);
         for (int e = 0; e < 17; ++e) if (x.cnt_u[e]) atomicAdd(&s->ev[e], (unsigned long long)x.cnt_u[e]);
@@ -237,7 +239,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         BdArgs a{}; a.P = P; a.H = make_tiny(cfg.host); a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.info = info.p;
         a.work_counter = counter.p; a.sizes = d_sizes.p;
         CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
-        int blocks = sm * 4; long long need = (n + 255) / 256; if (need < blocks) blocks = (int)need;
+        int blocks = sm * 4; long long need = (n * 32 + 255) / 256; if (need < blocks) blocks = (int)need;
         launch_bd_find(a, blocks, st); ++tm.launches;
         CK(cudaGetLastError());
     } else {
@@ -365,10 +367,13 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     // sizes are laid out [stream][n+1] so that one scan per stream yields offsets with the total in the last slot
     DevBuf<unsigned long long> sizes_n; sizes_n.alloc((size_t)ST_COUNT * n);
     CK(cudaMemsetAsync(sizes_n.p, 0, (size_t)ST_COUNT * n * sizeof(unsigned long long), st));
+    DevBuf<uint16_t> plen; DevBuf<unsigned long long> dig_f; DevBuf<int16_t> dig_e;
+    plen.alloc((size_t)ST_COUNT * aux_stride); dig_f.alloc((size_t)2 * aux_stride); dig_e.alloc((size_t)2 * aux_stride);
+    e.plen = plen.p; e.dig_f = dig_f.p; e.dig_e = dig_e.p;
     e.sizes = sizes_n.p; e.offsets = offsets.p;
     const unsigned emit_blocks = (unsigned)((n * 32 + 127) / 128);
     ph.start();
-    launch_emit(false, e, emit_blocks, st); ++tm.launches;
+    tm.launches += launch_emit(false, e, emit_blocks, st);
     CK(cudaGetLastError());
     {
         size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, sizes.p, offsets.p, (int)(n + 1), st);
@@ -384,7 +389,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     for (int s = 0; s < ST_COUNT; ++s) CK(cudaMemcpy(&totals[s], offsets.p + (size_t)s * (n + 1) + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     for (int s = 0; s < ST_COUNT; ++s) { out.stream_bytes[s] = totals[s]; CK(cudaMalloc(&out.d_stream[s], std::max<unsigned long long>(totals[s], 1))); e.out[s] = out.d_stream[s]; }
     ph.start();
-    launch_emit(true, e, emit_blocks, st); ++tm.launches;
+    tm.launches += launch_emit(true, e, emit_blocks, st);
     CK(cudaGetLastError());
     tm.emit_write_ms = ph.stop();
 
@@ -393,7 +398,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         DevBuf<DevSummary> ds; ds.alloc(1); CK(cudaMemsetAsync(ds.p, 0, sizeof(DevSummary), st));
         k_summary<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(info.p, n, ds.p); ++tm.launches;
         DevSummary hs; CK(cudaMemcpyAsync(&hs, ds.p, sizeof(hs), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
-        Summary& S = out.summary; S.n_ok = (long long)hs.n_ok; S.n_failed = (long long)hs.n_failed; S.attempts_total = (long long)hs.attempts_total; S.vertices_sampled = (long long)hs.vertices;
+        Summary& S = out.summary; S.n_ok = (long long)hs.n_ok; S.n_failed = (long long)hs.n_failed; S.attempts_total = (long long)hs.attempts_total; S.vertices_sampled = (long long)hs.vertices; S.vertices_abandoned = (long long)hs.vertices_abandoned; S.attempts_completed = (long long)hs.attempts_completed;
         for (int i = 0; i < 17; ++i) S.event_counts[i] = (long long)hs.ev[i];
         for (int i = 0; i < 1025; ++i) S.leaf_hist[i] = (long long)hs.leaf_hist[i];
         for (int s = 0; s < ST_COUNT; ++s) S.out_bytes[s] = (long long)totals[s];

@@ -38,7 +38,7 @@ struct BatchOpts {
 struct Timings { double find_ms = 0, build_ms = 0, label_ms = 0, emit_size_ms = 0, emit_write_ms = 0, d2h_ms = 0, total_ms = 0; long long launches = 0; };
 
 struct Summary {
-    long long n_ok = 0, n_failed = 0, attempts_total = 0, vertices_sampled = 0;
+    long long n_ok = 0, n_failed = 0, attempts_total = 0, vertices_sampled = 0, vertices_abandoned = 0, attempts_completed = 0;
     long long event_counts[17] = {0};
     long long leaf_hist[1025] = {0};
     long long out_bytes[8] = {0};

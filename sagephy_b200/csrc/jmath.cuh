@@ -298,42 +298,75 @@ struct CountSink {
     long long n = 0;
     SGP_HD void put(char) { ++n; }
     SGP_HD void skip(int k) { n += k; }
+    SGP_HD char* reserve(int) { return nullptr; }
     static constexpr bool kCounts = true;
+    static constexpr bool kRandomAccess = false;
 };
 struct MemSink {
     char* p;
     SGP_HD void put(char c) { *p++ = c; }
+    SGP_HD void skip(int) {}
+    SGP_HD char* reserve(int n) { char* q = p; p += n; return q; }     // random-access window of n bytes
     static constexpr bool kCounts = false;
+    static constexpr bool kRandomAccess = true;
 };
 
 template <class Sink> SGP_HD void put_str(Sink& s, const char* z) { while (*z) s.put(*z++); }
-template <class Sink> SGP_HD void put_u64(Sink& s, uint64_t v) {
-    int n = dec_len_u64(v);
-    if (Sink::kCounts) { for (int i = 0; i < n; ++i) s.put('0'); return; }
-    char tmp[20];
-    for (int i = n - 1; i >= 0; --i) { tmp[i] = (char)('0' + (v % 10)); v /= 10; }
+SGP_HD int dec_len_u32(uint32_t v) {
+    return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
+}
+// n decimal digits of v (v < 10^n, n <= 10), most significant first, 32-bit arithmetic only
+template <class Sink> SGP_HD void put_u32_digits(Sink& s, uint32_t v, int n) {
+    if (Sink::kRandomAccess) {
+        char* d = s.reserve(n);
+        for (int i = n - 1; i >= 0; --i) { uint32_t q = v / 10u; d[i] = (char)('0' + (v - q * 10u)); v = q; }
+        return;
+    }
+    char tmp[10];
+    for (int i = n - 1; i >= 0; --i) { uint32_t q = v / 10u; tmp[i] = (char)('0' + (v - q * 10u)); v = q; }
     for (int i = 0; i < n; ++i) s.put(tmp[i]);
+}
+template <class Sink> SGP_HD void put_u32(Sink& s, uint32_t v) {
+    const int n = dec_len_u32(v);
+    if (Sink::kCounts) { s.skip(n); return; }
+    put_u32_digits(s, v, n);
+}
+template <class Sink> SGP_HD void put_u64(Sink& s, uint64_t v) {
+    if (v <= 0xffffffffull) { put_u32(s, (uint32_t)v); return; }
+    const int n = dec_len_u64(v);
+    if (Sink::kCounts) { s.skip(n); return; }
+    const uint64_t hi = v / 1000000000ull; const uint32_t lo = (uint32_t)(v - hi * 1000000000ull);
+    put_u64(s, hi); put_u32_digits(s, lo, 9);
 }
 template <class Sink> SGP_HD void put_i64(Sink& s, long long v) {
     if (v < 0) { s.put('-'); put_u64(s, (uint64_t)(-(v + 1)) + 1ull); } else put_u64(s, (uint64_t)v);
 }
-// digits of f, positions [from, to) counted from the most significant digit; n = total digits
+// digits of f (n digits in total), positions [from, to) counted from the most significant digit
 template <class Sink> SGP_HD void put_digits(Sink& s, uint64_t f, int n, int from, int to) {
+    if (Sink::kCounts) { s.skip(to - from); return; }
+    // split into <= 9-digit limbs so that the digit loop runs in 32-bit arithmetic
+    const uint64_t hi = f / 1000000000ull; uint32_t l0 = (uint32_t)(f - hi * 1000000000ull);
+    uint32_t l1 = (uint32_t)(hi % 1000000000ull);
+    if (Sink::kRandomAccess) {
+        // digit at position pos (0 = most significant) goes to d[pos - from] when from <= pos < to
+        char* d = s.reserve(to - from);
+        int pos = n - 1;
+        for (int i = 0; i < 9 && pos >= from; ++i, --pos) { uint32_t q = l0 / 10u; if (pos < to) d[pos - from] = (char)('0' + (l0 - q * 10u)); l0 = q; }
+        if (n > 9) { pos = n - 10; for (int i = 0; i < 9 && pos >= from; ++i, --pos) { uint32_t q = l1 / 10u; if (pos < to) d[pos - from] = (char)('0' + (l1 - q * 10u)); l1 = q; } }
+        return;
+    }
     char tmp[20];
-    for (int i = n - 1; i >= 0; --i) { tmp[i] = (char)('0' + (f % 10)); f /= 10; }
+    int pos = n - 1;
+    for (int i = 0; i < 9 && pos >= 0; ++i, --pos) { uint32_t q = l0 / 10u; tmp[pos] = (char)('0' + (l0 - q * 10u)); l0 = q; }
+    for (int i = 0; i < 9 && pos >= 0; ++i, --pos) { uint32_t q = l1 / 10u; tmp[pos] = (char)('0' + (l1 - q * 10u)); l1 = q; }
+    for (; pos >= 0; --pos) tmp[pos] = '0';
     for (int i = from; i < to; ++i) s.put(tmp[i]);
 }
 
-// java.lang.Double.toString
-template <class Sink> SGP_HD void put_double(Sink& s, const MathTables& T, double v) {
-    if (v != v) { put_str(s, "NaN"); return; }
-    if (dbl_hi(v) < 0) { s.put('-'); v = -v; }
-    if (v == dbl_inf()) { put_str(s, "Infinity"); return; }
-    if (v == 0.0) { put_str(s, "0.0"); return; }
-    uint64_t f; int e;
-    d2s_decimal(T, v, &f, &e);
-    int n = dec_len_u64(f);
-    int pe = n + e;          // v = 0.DIGITS x 10^pe
+// Layout part of java.lang.Double.toString for a finite v > 0 whose shortest decimal is f x 10^e.
+template <class Sink> SGP_HD void put_double_digits(Sink& s, double v, uint64_t f, int e) {
+    const int n = dec_len_u64(f);
+    const int pe = n + e;          // v = 0.DIGITS x 10^pe
     if (v >= 1e-3 && v < 1e7) {
         if (pe <= 0) {
             s.put('0'); s.put('.');
@@ -352,6 +385,17 @@ template <class Sink> SGP_HD void put_double(Sink& s, const MathTables& T, doubl
         s.put('E');
         put_i64(s, (long long)(pe - 1));
     }
+}
+
+// java.lang.Double.toString
+template <class Sink> SGP_HD void put_double(Sink& s, const MathTables& T, double v) {
+    if (v != v) { put_str(s, "NaN"); return; }
+    if (dbl_hi(v) < 0) { s.put('-'); v = -v; }
+    if (v == dbl_inf()) { put_str(s, "Infinity"); return; }
+    if (v == 0.0) { put_str(s, "0.0"); return; }
+    uint64_t f; int e;
+    d2s_decimal(T, v, &f, &e);
+    put_double_digits(s, v, f, e);
 }
 
 }  // namespace sgp

@@ -87,6 +87,9 @@ struct EmitArgs {
     const int32_t* gname_off;      // per host tree: offset/len pairs into blob (GUEST= value / file name)
     const int32_t* leafname_off;   // per host vertex: offset/len pairs into blob (leafmap second column)
     const double* ep_times;        // 3 doubles per epoch [lo, mid, up] (DISCPT index)
+    uint16_t* plen;                // [ST_COUNT][aux_stride] cached piece lengths (size pass -> write pass)
+    unsigned long long* dig_f;     // [2][aux_stride] cached shortest-decimal digits of branch lengths (unpruned, pruned)
+    int16_t* dig_e;                // [2][aux_stride] ... and their decimal exponents
     unsigned long long* sizes;     // [ST_COUNT][n]  (size pass output)
     const unsigned long long* offsets;   // [ST_COUNT][n+1] (write pass input)
     char* out[ST_COUNT];

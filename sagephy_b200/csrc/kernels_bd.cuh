@@ -1,71 +1,104 @@
 // BD fast path kernels (transfer-free processes on a 1- or 2-leaf host, Philox mode) — see sim.cuh.
+//
+// k_bd_find is the hot kernel of HostTreeGen batches: acceptance of a 100-leaf window is ~0.36 %, so ~276 attempts are
+// thrown away per accepted tree. It therefore only COUNTS (no vertex is stored) and it is warp-cooperative: the 32 lanes of a
+// warp work on the same replicate, each on its own attempt index claimed from a per-warp shared-memory counter, so
+//   * every loop iteration expands exactly one vertex in every lane (no divergence between "phases" of the algorithm),
+//   * the geometric tail of the attempt count is divided by 32 (no idle SMs at the end of a batch),
+//   * the accepted attempt is the smallest accepted index (ballot-free: shared-memory atomicMin), i.e. exactly what the
+//     sequential retry loop of GuestTreeMachina.sampleGuestTree (apps/SaGePhy/GuestTreeMachina.java:81-98) would accept.
+// k_bd_build regenerates the accepted attempt of each replicate into the exactly-sized node arena.
 #pragma once
 #include "sim.cuh"
 
 namespace sgp {
 
-// ---- BD fast path ------------------------------------------------------------------------------------------------------------
+constexpr int kBdFindThreads = 256;
 
-// Count-only pass: every loop iteration expands one vertex of the current attempt of the current replicate of this thread,
-// so the 32 lanes of a warp stay converged while they sit in different attempts / replicates.
-__global__ void __launch_bounds__(256) k_bd_find(BdArgs a) {
+__global__ void __launch_bounds__(kBdFindThreads) k_bd_find(BdArgs a) {
+    __shared__ int s_next[kBdFindThreads / 32];     // next unclaimed attempt index of the warp's replicate
+    __shared__ int s_best[kBdFindThreads / 32];     // smallest accepted attempt index so far
     double st_time[kBdStack]; int8_t st_arc[kBdStack];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
-    long long r = -1; uint32_t rep_lo = 0, rep_hi = 0;
-    int sp = 0; uint32_t vidx = 0; int attempts = 0; int sampled = 0, c0 = 0, c1 = 0; bool active = false, rejected = false; int exact = -1;
-    uint64_t verts = 0; int status = REP_PENDING;
+    const BdConsts C = bd_consts(a.P);
     const int leaf0 = a.H.nV == 1 ? 0 : a.H.left[a.H.root];
+    const bool two_leaves = a.H.nV > 1;
+    volatile int* v_best = &s_best[wib];
     for (;;) {
-        if (sp == 0) {
-            bool need_new_rep = !active;
-            if (active) {
-                // attempt finished
-                verts += vidx;
-                ++attempts;
-                bool ok = !rejected && sampled >= a.P.min_leaves && sampled <= a.P.max_leaves && (exact == -1 || sampled == exact);
-                if (ok && a.H.nV > 1) ok = c0 >= a.P.minper && c0 <= a.P.maxper && c1 >= a.P.minper && c1 <= a.P.maxper;
-                if (ok) { status = REP_OK; }
-                else if (attempts > a.P.max_attempts) { status = REP_MAX_ATTEMPTS; }
-                if (status != REP_PENDING) {
-                    RepInfo inf; memset(&inf, 0, sizeof(inf));
-                    inf.status = status; inf.exact = exact; inf.root = -1; inf.p_root = -1; inf.vertices_sampled = verts;
-                    if (status == REP_OK) { inf.acc_attempt = (uint32_t)(attempts - 1); inf.n_pool = (int)vidx; inf.sampled_leaves = sampled; inf.attempts = attempts + 1; }
-                    else inf.attempts = attempts;
-                    a.info[r] = inf;
-                    need_new_rep = true;
+        long long r = 0;
+        if (lane == 0) r = (long long)atomicAdd(a.work_counter, 1ULL);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= a.n) break;
+        const unsigned long long gid = (unsigned long long)(a.rep_base + r);
+        const uint32_t rep_lo = (uint32_t)gid, rep_hi = (uint32_t)(gid >> 32);
+        int exact = -1;
+        if (a.P.n_sizes > 0) { PhiloxStream ph; ph.init(a.seed, gid, 0xFFFFFFFFu); exact = a.sizes[ph.next_int(a.P.n_sizes)]; }
+        if (lane == 0) { s_next[wib] = 0; s_best[wib] = 0x7fffffff; }
+        __syncwarp();
+        bool idle = false; int my_a = -1, sp = 0; uint32_t vidx = 0; int sampled = 0, c0 = 0, c1 = 0; bool rejected = false, overflow = false;
+        int acc_a = 0x7fffffff, acc_n = 0, acc_sampled = 0;
+        unsigned long long v_completed = 0, v_abandoned = 0; int n_completed = 0;
+        U4 w_next{0, 0, 0, 0};
+        for (;;) {
+            if (sp == 0 && !idle) {
+                if (my_a >= 0) {          // attempt my_a ran to completion (or was cut short by the max-leaves test)
+                    v_completed += vidx; ++n_completed;
+                    bool ok = !rejected && sampled >= a.P.min_leaves && sampled <= a.P.max_leaves && (exact == -1 || sampled == exact);
+                    if (ok && two_leaves) ok = c0 >= a.P.minper && c0 <= a.P.maxper && c1 >= a.P.minper && c1 <= a.P.maxper;
+                    if (ok) { atomicMin(&s_best[wib], my_a); acc_a = my_a; acc_n = (int)vidx; acc_sampled = sampled; }
+                }
+                const int na = atomicAdd(&s_next[wib], 1);
+                if (na > *v_best || na > a.P.max_attempts) { my_a = -1; idle = true; }
+                else {
+                    my_a = na; st_time[0] = a.H.tip; st_arc[0] = (int8_t)a.H.root; sp = 1; vidx = 0; sampled = 0; c0 = 0; c1 = 0; rejected = false;
+                    w_next = philox4x32_10(0u, (uint32_t)my_a, rep_lo, rep_hi, k0, k1);
                 }
             }
-            if (need_new_rep) {
-                long long slot = (long long)atomicAdd(a.work_counter, 1ULL);
-                if (slot >= a.n) break;
-                r = slot; const unsigned long long gid = (unsigned long long)(a.rep_base + r);
-                rep_lo = (uint32_t)gid; rep_hi = (uint32_t)(gid >> 32);
-                attempts = 0; verts = 0; status = REP_PENDING; active = true; exact = -1;
-                if (a.P.n_sizes > 0) { PhiloxStream ph; ph.init(a.seed, gid, 0xFFFFFFFFu); exact = a.sizes[ph.next_int(a.P.n_sizes)]; }
+            if (__all_sync(0xffffffffu, idle)) break;
+            if (my_a >= 0) {
+                if (my_a > *v_best) { v_abandoned += vidx; sp = 0; my_a = -1; idle = true; continue; }     // a smaller index was accepted meanwhile
+                --sp;
+                const double start = st_time[sp]; const int X = st_arc[sp];
+                const U4 w = w_next;
+                ++vidx;
+                w_next = philox4x32_10(vidx, (uint32_t)my_a, rep_lo, rep_hi, k0, k1);     // next vertex's block: independent of this vertex's math
+                const BdVertex v = bd_vertex(C, a.H, X, start, w);
+                if (v.event == EV_LEAF) {
+                    ++sampled; if (X == leaf0) ++c0; else ++c1;
+                    if (sampled > a.P.max_leaves) { rejected = true; sp = 0; }          // the attempt can no longer be accepted
+                } else if (v.event == EV_DUPLICATION || v.event == EV_SPECIATION) {
+                    if (sp + 2 > kBdStack) { rejected = true; overflow = true; sp = 0; }
+                    else {
+                        const bool dup = v.event == EV_DUPLICATION;
+                        st_time[sp] = v.et; st_arc[sp] = (int8_t)(dup ? X : a.H.right[X]);
+                        st_time[sp + 1] = v.et; st_arc[sp + 1] = (int8_t)(dup ? X : a.H.left[X]); sp += 2;
+                    }
+                }
             }
-            // start attempt `attempts`
-            st_time[0] = a.H.tip; st_arc[0] = (int8_t)a.H.root; sp = 1; vidx = 0; sampled = 0; c0 = 0; c1 = 0; rejected = false;
         }
-        --sp;
-        const double start = st_time[sp]; const int X = st_arc[sp];
-        U4 w = philox4x32_10(vidx, (uint32_t)attempts, rep_lo, rep_hi, k0, k1);
-        ++vidx;
-        BdVertex v = bd_vertex(a.P, a.H, X, start, u01_from_words(w.x, w.y), u01_from_words(w.z, w.w), false, a.T);
-        if (v.event == EV_LEAF) {
-            ++sampled; if (X == leaf0) ++c0; else ++c1;
-            if (sampled > a.P.max_leaves) { rejected = true; sp = 0; }       // early abort: the attempt can no longer be accepted
-        } else if (v.event == EV_DUPLICATION) {
-            if (sp + 2 > kBdStack) { rejected = true; sp = 0; status = REP_STACK_OVERFLOW; }
-            else { st_time[sp] = v.et; st_arc[sp] = (int8_t)X; st_time[sp + 1] = v.et; st_arc[sp + 1] = (int8_t)X; sp += 2; }
-        } else if (v.event == EV_SPECIATION) {
-            if (sp + 2 > kBdStack) { rejected = true; sp = 0; status = REP_STACK_OVERFLOW; }
-            else { st_time[sp] = v.et; st_arc[sp] = (int8_t)a.H.right[X]; st_time[sp + 1] = v.et; st_arc[sp + 1] = (int8_t)a.H.left[X]; sp += 2; }
+        // resolve: the lane that owns the smallest accepted index reports
+        const int best = *v_best;
+        for (int o = 16; o > 0; o >>= 1) {
+            v_completed += __shfl_xor_sync(0xffffffffu, v_completed, o); v_abandoned += __shfl_xor_sync(0xffffffffu, v_abandoned, o);
+            n_completed += __shfl_xor_sync(0xffffffffu, n_completed, o);
         }
-        if (status == REP_STACK_OVERFLOW && sp == 0) {
-            // record and move on (the host re-runs such replicates through the general engine)
-            RepInfo inf; memset(&inf, 0, sizeof(inf)); inf.status = REP_STACK_OVERFLOW; inf.exact = exact; inf.root = -1; inf.p_root = -1; inf.attempts = attempts;
-            a.info[r] = inf; active = false;
+        const bool any_overflow = __any_sync(0xffffffffu, overflow);
+        if (best != 0x7fffffff) {
+            if (acc_a == best) {
+                RepInfo inf; memset(&inf, 0, sizeof(inf));
+                inf.status = REP_OK; inf.exact = exact; inf.root = -1; inf.p_root = -1; inf.acc_attempt = (uint32_t)best; inf.n_pool = acc_n;
+                inf.sampled_leaves = acc_sampled; inf.attempts = best + 2;       // trees generated (best + 1) + 1, GuestTreeMachina.java:97,107
+                inf.vertices_sampled = v_completed; inf.vertices_abandoned = v_abandoned; inf.attempts_completed = n_completed;
+                a.info[r] = inf;
+            }
+        } else if (lane == 0) {
+            RepInfo inf; memset(&inf, 0, sizeof(inf));
+            inf.status = any_overflow ? REP_STACK_OVERFLOW : REP_MAX_ATTEMPTS; inf.exact = exact; inf.root = -1; inf.p_root = -1;
+            inf.attempts = a.P.max_attempts + 1; inf.vertices_sampled = v_completed; inf.vertices_abandoned = v_abandoned; inf.attempts_completed = n_completed;
+            a.info[r] = inf;
         }
+        __syncwarp();
     }
 }
 
@@ -78,30 +111,31 @@ __global__ void __launch_bounds__(256) k_bd_build(BdArgs a) {
     Node* N = a.nodes + a.node_off[r];
     const unsigned long long gid = (unsigned long long)(a.rep_base + r);
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32), rep_lo = (uint32_t)gid, rep_hi = (uint32_t)(gid >> 32);
+    const BdConsts C = bd_consts(a.P);
     double st_time[kBdStack]; int8_t st_arc[kBdStack]; int32_t st_par[kBdStack];   // parent index; bit 31 set = right child
     int sp = 0; uint32_t vidx = 0;
     st_time[0] = a.H.tip; st_arc[0] = (int8_t)a.H.root; st_par[0] = -1; sp = 1;
     while (sp > 0) {
         --sp;
         const double start = st_time[sp]; const int X = st_arc[sp]; const int32_t pw = st_par[sp];
-        U4 w = philox4x32_10(vidx, inf.acc_attempt, rep_lo, rep_hi, k0, k1);
-        BdVertex v = bd_vertex(a.P, a.H, X, start, u01_from_words(w.x, w.y), u01_from_words(w.z, w.w), true, a.T);
+        const U4 w = philox4x32_10(vidx, inf.acc_attempt, rep_lo, rep_hi, k0, k1);
+        const BdVertex v = bd_vertex(C, a.H, X, start, w);
         const int me = (int)vidx++;
         Node& nd = N[me];
-        nd.abstime = v.et; nd.bl = v.bl; nd.sigma = X; nd.left = -1; nd.right = -1; nd.from_arc = -1; nd.to_arc = -1; nd.number = -1;
+        nd.abstime = v.et;
+        nd.bl = v.boundary ? round_sig(a.T, start - v.et, 8) : v.bt;       // GuestTreeInHostTreeCreator.java:385 vs :378
+        nd.sigma = X; nd.left = -1; nd.right = -1; nd.from_arc = -1; nd.to_arc = -1; nd.number = -1;
         nd.p_bl = 0.0; nd.p_left = -1; nd.p_right = -1; nd.event = v.event; nd.prun = PR_UNKNOWN; nd.flags = 0; nd.pad0 = 0; nd.gtree = 0;
         nd.from_g = -1; nd.to_g = -1; nd.chain_u = 0; nd.chain_p = 0; nd.pad1 = 0;
         int ep = a.H.v2e[X];
-        if (v.event == EV_DUPLICATION || v.event == EV_LOSS) { while (a.H.ep_up[ep] < v.et) ++ep; }
+        if (!v.boundary) { while (a.H.ep_up[ep] < v.et) ++ep; }
         nd.epoch = ep;
         if (pw == -1) nd.parent = -1;
         else { int p = pw & 0x7fffffff; nd.parent = p; if (pw < 0) N[p].right = me; else N[p].left = me; }
-        if (v.event == EV_DUPLICATION) {
-            st_time[sp] = v.et; st_arc[sp] = (int8_t)X; st_par[sp] = (int32_t)(0x80000000u | (uint32_t)me);
-            st_time[sp + 1] = v.et; st_arc[sp + 1] = (int8_t)X; st_par[sp + 1] = me; sp += 2;
-        } else if (v.event == EV_SPECIATION) {
-            st_time[sp] = v.et; st_arc[sp] = (int8_t)a.H.right[X]; st_par[sp] = (int32_t)(0x80000000u | (uint32_t)me);
-            st_time[sp + 1] = v.et; st_arc[sp + 1] = (int8_t)a.H.left[X]; st_par[sp + 1] = me; sp += 2;
+        if (v.event == EV_DUPLICATION || v.event == EV_SPECIATION) {
+            const bool dup = v.event == EV_DUPLICATION;
+            st_time[sp] = v.et; st_arc[sp] = (int8_t)(dup ? X : a.H.right[X]); st_par[sp] = (int32_t)(0x80000000u | (uint32_t)me);
+            st_time[sp + 1] = v.et; st_arc[sp + 1] = (int8_t)(dup ? X : a.H.left[X]); st_par[sp + 1] = me; sp += 2;
         }
     }
     if (N[0].bl <= 1.0e-32) N[0].bl = 0.0;

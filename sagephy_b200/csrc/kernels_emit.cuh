@@ -1,10 +1,14 @@
 // K4: text emission. One warp per replicate; every output file ("stream") of a replicate is a concatenation of
 // independent pieces whose byte offsets are an exclusive prefix sum of their lengths:
 //   *.tree       one piece per vertex in post-order:  ['(' x run | ')'] name ':' length [tag] [','] [tree tag ';' '\n']
-//   *.info       a single piece
+//   *.info       one piece per line
 //   *.guest2host constant header + one row per vertex in breadth-first order
 //   *.leafmap    one row per leaf in breadth-first order
-// The same formatter runs with a CountSink (size pass) and a MemSink (write pass).
+// Size pass  (k_emit<false>): piece lengths through a CountSink; lengths (u16) and the shortest decimal digits of every
+//            branch length (Schubfach result f x 10^e) are cached per piece so that nothing is formatted twice.
+// Write pass (k_emit<true>):  32 pieces at a time: cached lengths -> warp exclusive scan -> each lane formats its piece
+//            once into a shared-memory staging buffer laid out congruent (mod 16) to the destination -> the warp flushes
+//            the buffer with aligned 16-byte coalesced stores.
 //
 // Formats follow NewickVertex.toString (io/NewickVertex.java:412-435), NewickTree.toString (io/NewickTree.java:457-465),
 // GuestVertex.setMeta (apps/SaGePhy/GuestVertex.java:183-425), HostTreeGen.getInfo (apps/SaGePhy/HostTreeGen.java:99-110,124-174),
@@ -65,15 +69,19 @@ template <class Sink> __device__ void put_meta(Sink& s, const EmitArgs& a, const
     s.put(']');
 }
 
-// piece k (post-order rank) of a tree stream
-template <bool PRUNED, class Sink> __device__ void put_tree_piece(Sink& s, const EmitArgs& a, const Node* N, const int32_t* ord, int k, int root) {
+// piece k (post-order rank) of a tree stream; (f, e) = cached shortest decimal of the branch length (e == kNoDigits: none)
+constexpr int kNoDigits = 0x7fff;
+template <bool PRUNED, class Sink> __device__ void put_tree_piece(Sink& s, const EmitArgs& a, const Node* N, const int32_t* ord, int k, int root,
+                                                                  unsigned long long f, int e) {
     const int vi = ord[k];
     const Node& x = N[vi];
     const bool leaf = PRUNED ? x.p_left < 0 : x.left < 0;
     if (leaf) { const int c = PRUNED ? x.chain_p : x.chain_u; for (int i = 0; i < c; ++i) s.put('('); }
     else s.put(')');
     put_name(s, a, x);
-    s.put(':'); put_double(s, a.T, PRUNED ? x.p_bl : x.bl);
+    s.put(':');
+    const double bl = PRUNED ? x.p_bl : x.bl;
+    if (e != kNoDigits) put_double_digits(s, bl, f, e); else put_double(s, a.T, bl);
     if (!a.exclude_meta) put_meta(s, a, x);
     if (x.flags & (PRUNED ? NF_LEFT_P : NF_LEFT_U)) s.put(',');
     if (vi == root) {
@@ -85,44 +93,48 @@ template <bool PRUNED, class Sink> __device__ void put_tree_piece(Sink& s, const
 template <class Sink> __device__ void put_kv_int(Sink& s, const char* k, long long v) { put_str(s, k); put_i64(s, v); s.put('\n'); }
 template <class Sink> __device__ void put_kv_dbl(Sink& s, const EmitArgs& a, const char* k, double v) { put_str(s, k); put_double(s, a.T, v); s.put('\n'); }
 
-template <bool PRUNED, class Sink> __device__ void put_info(Sink& s, const EmitArgs& a, const RepInfo& inf, long long gid) {
-    put_str(s, a.app == 0 ? "# HOSTTREEGEN\n" : a.app == 1 ? "# GUESTTREEGEN\n" : "# DOMAINTREEGEN\n");
-    put_str(s, "Arguments:\t");
-    put_blob(s, a.blob, a.args_pre_off, a.args_pre_len);
-    if (a.seed_mode) { put_i64(s, a.seed_base + gid); put_blob(s, a.blob, a.args_post_off, a.args_post_len); }
-    s.put('\n');
-    put_kv_int(s, "Attempts:\t", inf.attempts);
+__device__ __forceinline__ int info_lines(const EmitArgs& a, bool pruned) { return a.app == 0 ? (pruned ? 8 : 10) : 18; }
+
+// line `ln` of an .info file
+template <bool PRUNED, class Sink> __device__ void put_info_line(Sink& s, const EmitArgs& a, const RepInfo& inf, long long gid, int ln) {
     const int32_t* c = PRUNED ? inf.cnt_p : inf.cnt_u;
     const int nv = PRUNED ? inf.n_p : inf.n_u;
+    if (ln == 0) { put_str(s, a.app == 0 ? "# HOSTTREEGEN\n" : a.app == 1 ? "# GUESTTREEGEN\n" : "# DOMAINTREEGEN\n"); return; }
+    if (ln == 1) {
+        put_str(s, "Arguments:\t");
+        put_blob(s, a.blob, a.args_pre_off, a.args_pre_len);
+        if (a.seed_mode) { put_i64(s, a.seed_base + gid); put_blob(s, a.blob, a.args_post_off, a.args_post_len); }
+        s.put('\n'); return;
+    }
+    if (ln == 2) { put_kv_int(s, "Attempts:\t", inf.attempts); return; }
+    if (ln == 3) { put_kv_int(s, "No. of vertices:\t", nv); return; }
+    if (ln == 4) { put_kv_int(s, "No. of extant leaves:\t", c[EV_LEAF] + c[EV_UNSAMPLED_LEAF]); return; }
     const double total = round_sig(a.T, PRUNED ? inf.total_p : inf.total_u, 8);
     if (a.app == 0) {
         const int births = c[EV_DUPLICATION] + c[EV_SPECIATION], deaths = c[EV_LOSS];
-        put_kv_int(s, "No. of vertices:\t", nv);
-        put_kv_int(s, "No. of extant leaves:\t", c[EV_LEAF] + c[EV_UNSAMPLED_LEAF]);
-        put_kv_int(s, "No. of births:\t", births);
-        put_kv_int(s, "No. of deaths:\t", deaths);
-        put_kv_dbl(s, a, "Total branch time:\t", total);
-        if (!PRUNED) {
-            put_kv_dbl(s, a, "Birth ML estimate:\t", round_sig(a.T, XDIV((double)births, total), 8));
-            put_kv_dbl(s, a, "Death ML estimate:\t", round_sig(a.T, XDIV((double)deaths, total), 8));
+        switch (ln) {
+            case 5: put_kv_int(s, "No. of births:\t", births); break;
+            case 6: put_kv_int(s, "No. of deaths:\t", deaths); break;
+            case 7: put_kv_dbl(s, a, "Total branch time:\t", total); break;
+            case 8: put_kv_dbl(s, a, "Birth ML estimate:\t", round_sig(a.T, XDIV((double)births, total), 8)); break;
+            case 9: put_kv_dbl(s, a, "Death ML estimate:\t", round_sig(a.T, XDIV((double)deaths, total), 8)); break;
         }
-    } else {
-        const double ben = round_sig(a.T, PRUNED ? inf.beneath_p : inf.beneath_u, 8);
-        put_kv_int(s, "No. of vertices:\t", nv);
-        put_kv_int(s, "No. of extant leaves:\t", c[EV_LEAF] + c[EV_UNSAMPLED_LEAF]);
-        put_kv_int(s, "No. of speciations:\t", c[EV_SPECIATION]);
-        put_kv_int(s, "No. of duplications:\t", c[EV_DUPLICATION]);
-        put_kv_int(s, "No. of losses:\t", c[EV_LOSS]);
-        put_kv_int(s, "No. of replacing losses:\t", c[EV_REPLACING_LOSS]);
-        put_kv_int(s, "No. of additive transfers:\t", c[EV_ADDITIVE_TRANSFER]);
-        put_kv_int(s, "No. of replacing transfers:\t", c[EV_REPLACING_TRANSFER]);
-        put_kv_dbl(s, a, "Total branch time:\t", total);
-        put_kv_dbl(s, a, "Total branch time beneath host stem:\t", ben);
-        put_kv_dbl(s, a, "Duplication ML estimate:\t", round_sig(a.T, XDIV((double)c[EV_DUPLICATION], total), 8));
-        put_kv_dbl(s, a, "Loss ML estimate:\t", round_sig(a.T, XDIV((double)c[EV_LOSS], total), 8));
-        put_kv_dbl(s, a, "Replacing Loss ML estimate:\t", round_sig(a.T, XDIV((double)c[EV_REPLACING_LOSS], total), 8));
-        put_kv_dbl(s, a, "Additive Transfer ML estimate:\t", round_sig(a.T, XDIV((double)c[EV_ADDITIVE_TRANSFER], total), 8));
-        put_kv_dbl(s, a, "Replacing Transfer ML estimate:\t", round_sig(a.T, XDIV((double)c[EV_REPLACING_TRANSFER], total), 8));
+        return;
+    }
+    switch (ln) {
+        case 5: put_kv_int(s, "No. of speciations:\t", c[EV_SPECIATION]); break;
+        case 6: put_kv_int(s, "No. of duplications:\t", c[EV_DUPLICATION]); break;
+        case 7: put_kv_int(s, "No. of losses:\t", c[EV_LOSS]); break;
+        case 8: put_kv_int(s, "No. of replacing losses:\t", c[EV_REPLACING_LOSS]); break;
+        case 9: put_kv_int(s, "No. of additive transfers:\t", c[EV_ADDITIVE_TRANSFER]); break;
+        case 10: put_kv_int(s, "No. of replacing transfers:\t", c[EV_REPLACING_TRANSFER]); break;
+        case 11: put_kv_dbl(s, a, "Total branch time:\t", total); break;
+        case 12: put_kv_dbl(s, a, "Total branch time beneath host stem:\t", round_sig(a.T, PRUNED ? inf.beneath_p : inf.beneath_u, 8)); break;
+        case 13: put_kv_dbl(s, a, "Duplication ML estimate:\t", round_sig(a.T, XDIV((double)c[EV_DUPLICATION], total), 8)); break;
+        case 14: put_kv_dbl(s, a, "Loss ML estimate:\t", round_sig(a.T, XDIV((double)c[EV_LOSS], total), 8)); break;
+        case 15: put_kv_dbl(s, a, "Replacing Loss ML estimate:\t", round_sig(a.T, XDIV((double)c[EV_REPLACING_LOSS], total), 8)); break;
+        case 16: put_kv_dbl(s, a, "Additive Transfer ML estimate:\t", round_sig(a.T, XDIV((double)c[EV_ADDITIVE_TRANSFER], total), 8)); break;
+        case 17: put_kv_dbl(s, a, "Replacing Transfer ML estimate:\t", round_sig(a.T, XDIV((double)c[EV_REPLACING_TRANSFER], total), 8)); break;
     }
 }
 
@@ -155,10 +167,6 @@ template <bool PRUNED, class Sink> __device__ void put_leafmap_row(Sink& s, cons
     s.put('\n');
 }
 
-__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 __device__ __forceinline__ unsigned warp_excl_scan_u32(unsigned v, unsigned* total) {
     unsigned x = v; const int lane = threadIdx.x & 31;
     for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
@@ -166,26 +174,59 @@ __device__ __forceinline__ unsigned warp_excl_scan_u32(unsigned v, unsigned* tot
     return x - v;
 }
 
-// Generic driver: pieces 0..n_pieces-1, piece lengths via CountSink, bytes via MemSink.
-template <bool WRITE, class F> __device__ unsigned long long emit_pieces(int n_pieces, char* base, F&& piece) {
+constexpr int kEmitWarps = 4;               // warps per block
+constexpr int kStageBytes = 5120;           // shared staging per warp (32 pieces; longer groups fall back to direct stores)
+
+// Flushes `total` staged bytes (stage[mis .. mis+total), mis = dst & 15) to dst with aligned 16-byte stores.
+__device__ __forceinline__ void flush_stage(const char* stage, int mis, char* dst, unsigned total) {
+    const int lane = threadIdx.x & 31;
+    unsigned head = (16u - (unsigned)mis) & 15u; if (head > total) head = total;
+    if ((unsigned)lane < head) dst[lane] = stage[mis + lane];
+    const unsigned body = (total - head) >> 4;
+    const uint4* src4 = reinterpret_cast<const uint4*>(stage + mis + head);
+    uint4* dst4 = reinterpret_cast<uint4*>(dst + head);
+    for (unsigned i = lane; i < body; i += 32) dst4[i] = src4[i];
+    const unsigned done = head + (body << 4);
+    if (done + lane < total) dst[done + lane] = stage[mis + done + lane];
+}
+
+// Pieces 0..n_pieces-1 of one stream of one replicate.
+//   SIZE pass : len(i) computed with a CountSink by `piece(CountSink&, i, true)`, stored through store_len(i, len).
+//   WRITE pass: len(i) read through load_len(i); bytes produced by `piece(MemSink&, i, false)`.
+template <bool WRITE, class F, class LL, class SL>
+__device__ unsigned long long emit_pieces(int n_pieces, char* base, char* stage, F&& piece, LL&& load_len, SL&& store_len) {
     const int lane = threadIdx.x & 31;
     unsigned long long running = 0;
     for (int i0 = 0; i0 < n_pieces; i0 += 32) {
         const int i = i0 + lane;
         unsigned len = 0;
-        if (i < n_pieces) { CountSink c; piece(c, i); len = (unsigned)c.n; }
-        unsigned total; unsigned off = warp_excl_scan_u32(len, &total);
-        if (WRITE && i < n_pieces && len) { MemSink m{base + running + off}; piece(m, i); }
+        if (i < n_pieces) {
+            if (WRITE) len = load_len(i);
+            else { CountSink c; piece(c, i); len = (unsigned)c.n; store_len(i, len); }
+        }
+        unsigned total; const unsigned off = warp_excl_scan_u32(len, &total);
+        if (WRITE && total) {
+            char* dst = base + running;
+            const int mis = (int)(reinterpret_cast<unsigned long long>(dst) & 15ull);
+            if (total + 16 <= (unsigned)kStageBytes) {
+                if (len) { MemSink m{stage + mis + off}; piece(m, i); }
+                __syncwarp();
+                flush_stage(stage, mis, dst, total);
+                __syncwarp();
+            } else if (len) { MemSink m{dst + off}; piece(m, i); }
+        }
         running += total;
     }
     return running;
 }
 
-template <bool WRITE>
-__global__ void __launch_bounds__(128) k_emit(EmitArgs a) {
+template <bool WRITE, int STREAM>
+__global__ void __launch_bounds__(kEmitWarps * 32, 4) k_emit(EmitArgs a) {
+    __shared__ __align__(16) char s_stage[kEmitWarps][kStageBytes];
     const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= a.n) return;
+    char* stage = s_stage[threadIdx.x >> 5];
     const RepInfo& inf = a.info[r];
     const long long gid = a.rep_base + r;
     const bool ok = inf.status == REP_OK;
@@ -193,44 +234,75 @@ __global__ void __launch_bounds__(128) k_emit(EmitArgs a) {
     const Node* N = a.nodes + off;
     const int32_t* ordU = a.aux + off; const int32_t* ordP = a.aux + a.aux_stride + off;
     const int32_t* bfsU = a.aux + 2 * a.aux_stride + off; const int32_t* bfsP = a.aux + 3 * a.aux_stride + off;
-    for (int st = 0; st < ST_COUNT; ++st) {
-        if (!(a.stream_mask & (1u << st))) continue;
+    auto no_load = [](int) { return 0u; };
+    auto no_store = [](int, unsigned) {};
+    {
+        constexpr int st = STREAM;
         char* base = WRITE ? a.out[st] + a.offsets[(size_t)st * (a.n + 1) + r] : nullptr;
+        uint16_t* plen = a.plen + (size_t)st * a.aux_stride + off;       // cached piece lengths of this stream
+        auto ld = [&](int i) { return (unsigned)plen[i]; };
+        auto sd = [&](int i, unsigned v) { plen[i] = (uint16_t)(v > 0xffffu ? 0xffffu : v); };
         unsigned long long bytes = 0;
         if (!ok) {
             // failed replicate: the reference writes only the failure note (to <prefix>.info / <prefix>.pruned.info)
             if (st == ST_PRUNED_INFO && inf.status == REP_MAX_ATTEMPTS) {
-                bytes = emit_pieces<WRITE>(1, base, [&](auto& s, int) { put_str(s, "Failed to produce valid pruned tree within max allowed attempts.\n"); });
+                auto pc = [&](auto& s, int) { put_str(s, "Failed to produce valid pruned tree within max allowed attempts.\n"); };
+                if (WRITE) bytes = emit_pieces<true>(1, base, stage, pc, [](int) { return 65u; }, no_store);
+                else bytes = emit_pieces<false>(1, base, stage, pc, no_load, no_store);
             }
-        } else switch (st) {
-            case ST_UNPRUNED_TREE:
-                bytes = emit_pieces<WRITE>(inf.n_u, base, [&](auto& s, int k) { put_tree_piece<false>(s, a, N, ordU, k, inf.root); });
-                break;
-            case ST_PRUNED_TREE:
-                if (inf.p_root >= 0) bytes = emit_pieces<WRITE>(inf.n_p, base, [&](auto& s, int k) { put_tree_piece<true>(s, a, N, ordP, k, inf.p_root); });
-                else bytes = emit_pieces<WRITE>(1, base, [&](auto& s, int) {
-                    if (a.exclude_meta) put_str(s, ";\n"); else put_str(s, a.app == 0 ? "[NAME=PrunedTree];" : "[NAME=PrunedTree];\n"); });
-                break;
-            case ST_UNPRUNED_INFO:
-                bytes = emit_pieces<WRITE>(1, base, [&](auto& s, int) { put_info<false>(s, a, inf, gid); });
-                break;
-            case ST_PRUNED_INFO:
-                bytes = emit_pieces<WRITE>(1, base, [&](auto& s, int) { put_info<true>(s, a, inf, gid); });
-                break;
-            case ST_UNPRUNED_G2H: case ST_PRUNED_G2H: {
-                const bool pr = st == ST_PRUNED_G2H;
+        } else {
+            if constexpr (st == ST_UNPRUNED_TREE || st == ST_PRUNED_TREE) {
+                constexpr bool pr = st == ST_PRUNED_TREE;
+                if (pr && inf.p_root < 0) {
+                    auto pc = [&](auto& s, int) { if (a.exclude_meta) put_str(s, ";\n"); else put_str(s, a.app == 0 ? "[NAME=PrunedTree];" : "[NAME=PrunedTree];\n"); };
+                    const unsigned l = a.exclude_meta ? 2u : (a.app == 0 ? 18u : 19u);
+                    if (WRITE) bytes = emit_pieces<true>(1, base, stage, pc, [l](int) { return l; }, no_store);
+                    else bytes = emit_pieces<false>(1, base, stage, pc, no_load, no_store);
+                } else {
+                unsigned long long* df = a.dig_f + (size_t)(pr ? 1 : 0) * a.aux_stride + off;
+                int16_t* de = a.dig_e + (size_t)(pr ? 1 : 0) * a.aux_stride + off;
+                const int32_t* ord = pr ? ordP : ordU; const int np = pr ? inf.n_p : inf.n_u; const int root = pr ? inf.p_root : inf.root;
+                if (WRITE) {
+                    auto pc = [&](auto& s, int k) { if (pr) put_tree_piece<true>(s, a, N, ord, k, root, df[k], (int)de[k]); else put_tree_piece<false>(s, a, N, ord, k, root, df[k], (int)de[k]); };
+                    bytes = emit_pieces<true>(np, base, stage, pc, ld, no_store);
+                } else {
+                    auto pc = [&](auto& s, int k) {
+                        const Node& x = N[ord[k]]; const double bl = pr ? x.p_bl : x.bl;
+                        uint64_t f = 0; int e = kNoDigits;
+                        if (bl > 0.0 && bl < dbl_inf()) d2s_decimal(a.T, bl, &f, &e);
+                        df[k] = (unsigned long long)f; de[k] = (int16_t)e;
+                        if (pr) put_tree_piece<true>(s, a, N, ord, k, root, f, e); else put_tree_piece<false>(s, a, N, ord, k, root, f, e);
+                    };
+                    bytes = emit_pieces<false>(np, base, stage, pc, no_load, sd);
+                }
+                }
+            }
+            if constexpr (st == ST_UNPRUNED_INFO || st == ST_PRUNED_INFO) {
+                constexpr bool pr = st == ST_PRUNED_INFO;
+                auto pc = [&](auto& s, int ln) { if (pr) put_info_line<true>(s, a, inf, gid, ln); else put_info_line<false>(s, a, inf, gid, ln); };
+                // info lines are cheap: their lengths are recomputed in the write pass instead of being cached
+                auto ld_info = [&](int ln) { CountSink c; if (pr) put_info_line<true>(c, a, inf, gid, ln); else put_info_line<false>(c, a, inf, gid, ln); return (unsigned)c.n; };
+                if (WRITE) bytes = emit_pieces<true>(info_lines(a, pr), base, stage, pc, ld_info, no_store);
+                else bytes = emit_pieces<false>(info_lines(a, pr), base, stage, pc, no_load, no_store);
+            }
+            if constexpr (st == ST_UNPRUNED_G2H || st == ST_PRUNED_G2H) {
+                constexpr bool pr = st == ST_PRUNED_G2H;
                 if (WRITE) for (int i = lane; i < a.g2h_head_len; i += 32) base[i] = a.blob[a.g2h_head_off + i];
                 bytes = (unsigned long long)a.g2h_head_len;
                 const int np = pr ? (inf.p_root >= 0 ? inf.n_p : 0) : inf.n_u;
-                bytes += emit_pieces<WRITE>(np, WRITE ? base + a.g2h_head_len : nullptr, [&](auto& s, int k) { put_g2h_row(s, a, N, pr ? bfsP : bfsU, k); });
-                break;
+                const int32_t* bfs = pr ? bfsP : bfsU;
+                auto pc = [&](auto& s, int k) { put_g2h_row(s, a, N, bfs, k); };
+                if (WRITE) bytes += emit_pieces<true>(np, base + a.g2h_head_len, stage, pc, ld, no_store);
+                else bytes += emit_pieces<false>(np, nullptr, stage, pc, no_load, sd);
             }
-            case ST_UNPRUNED_LEAFMAP:
-                bytes = emit_pieces<WRITE>(inf.n_u, base, [&](auto& s, int k) { put_leafmap_row<false>(s, a, N, bfsU, k); });
-                break;
-            case ST_PRUNED_LEAFMAP:
-                bytes = emit_pieces<WRITE>(inf.p_root >= 0 ? inf.n_p : 0, base, [&](auto& s, int k) { put_leafmap_row<true>(s, a, N, bfsP, k); });
-                break;
+            if constexpr (st == ST_UNPRUNED_LEAFMAP || st == ST_PRUNED_LEAFMAP) {
+                constexpr bool pr = st == ST_PRUNED_LEAFMAP;
+                const int np = pr ? (inf.p_root >= 0 ? inf.n_p : 0) : inf.n_u;
+                const int32_t* bfs = pr ? bfsP : bfsU;
+                auto pc = [&](auto& s, int k) { if (pr) put_leafmap_row<true>(s, a, N, bfs, k); else put_leafmap_row<false>(s, a, N, bfs, k); };
+                if (WRITE) bytes = emit_pieces<true>(np, base, stage, pc, ld, no_store);
+                else bytes = emit_pieces<false>(np, nullptr, stage, pc, no_load, sd);
+            }
         }
         if (!WRITE && lane == 0) a.sizes[(size_t)st * a.n + r] = bytes;
     }

@@ -9,5 +9,5 @@ void launch_build_general(bool replay, const BuildArgs& a, int blocks, cudaStrea
 void launch_bd_find(const BdArgs& a, int blocks, cudaStream_t st);
 void launch_bd_build(const BdArgs& a, int blocks, cudaStream_t st);
 void launch_label_prune(const LabelArgs& a, int blocks, cudaStream_t st);
-void launch_emit(bool write, const EmitArgs& a, unsigned blocks, cudaStream_t st);
+int launch_emit(bool write, const EmitArgs& a, unsigned blocks, cudaStream_t st);   // returns the number of kernels launched
 }  // namespace sgp

@@ -273,31 +273,41 @@ static __device__ bool attempt_ok(const SimParams& P, const DevHost& H, const Si
 }
 
 // ---- BD fast path ----------------------------------------------------------------------------------------------------------
-// Tiny host (HostTreeGen: "H0:T;" or "(H0:T,H1:T):0.0;") passed by value.
-
+// Throughput-mode vertex step for transfer-free processes on a tiny host. Not bound to Java's bit patterns (Philox
+// mode is validated distributionally), but the find pass and the build pass call this same function, so they regenerate
+// identical trees. One Philox4x32-10 block per vertex: words (x,y) -> waiting time, (z,w) -> event / leaf-sampling draw.
 constexpr int kBdStack = 96;
 
-struct BdVertex { double et, bl; uint8_t event; };
+struct BdVertex { double et, bt; uint8_t event; bool boundary; };
 
-// Same decision tree as createGuestVertex with tau == 0; u1,u2 come from one Philox block.
-__device__ __forceinline__ BdVertex bd_vertex(const SimParams& P, const TinyHost& H, int X, double start, double u1, double u2, bool want_bl, const MathTables& T) {
+struct BdConsts {
+    double inv_sum, thr_root, thr_nonroot, rho;     // 1/(lambda+mu); P(dup) on the root arc; mu/sum on other arcs
+};
+__device__ __forceinline__ BdConsts bd_consts(const SimParams& P) {
+    double sum = P.lambda + P.mu; if (sum == 0.0) sum = 1e-48;
+    BdConsts c; c.inv_sum = 1.0 / sum; c.thr_root = P.lambda / sum; c.thr_nonroot = P.mu / sum; c.rho = P.rho;
+    return c;
+}
+// 52 random bits -> x in [1,2); 2 - x = 1 - u lies in (0,1] (never 0, so the logarithm is finite)
+__device__ __forceinline__ double one_minus_u(uint32_t a, uint32_t b) {
+    return 2.0 - __hiloint2double((int)(0x3ff00000u | (a >> 12)), (int)b);
+}
+__device__ __forceinline__ double u01_52(uint32_t a, uint32_t b) {
+    return __hiloint2double((int)(0x3ff00000u | (a >> 12)), (int)b) - 1.0;
+}
+__device__ __forceinline__ BdVertex bd_vertex(const BdConsts& C, const TinyHost& H, int X, double start, U4 w) {
     BdVertex r;
-    const bool isRoot = H.parent[X] < 0;
-    double sum = P.lambda + P.mu;      // tau == 0 on this path
-    if (sum == 0.0) sum = 1e-48;
+    const bool isRoot = H.parent[X] < 0, hostLeaf = H.left[X] < 0;
     const double low = H.vtime[X];
-    double bt = XDIV(-jlog(XSUB(1.0, u1)), sum);
-    double et = XSUB(start, bt);
-    if (et <= low) {
-        et = low;
-        r.bl = want_bl ? round_sig(T, XSUB(start, et), 8) : 0.0;
-        if (H.left[X] < 0) r.event = (u2 < P.rho) ? EV_LEAF : EV_UNSAMPLED_LEAF; else r.event = EV_SPECIATION;
-    } else {
-        r.bl = bt;
-        if (isRoot) r.event = (u2 < XDIV(P.lambda, sum)) ? EV_DUPLICATION : EV_LOSS;
-        else r.event = (u2 >= XDIV(P.mu, sum)) ? EV_DUPLICATION : EV_LOSS;    // (mu+tau)/sum == mu/sum
-    }
-    r.et = et;
+    const double bt = -log(one_minus_u(w.x, w.y)) * C.inv_sum;
+    const double et = start - bt;
+    const double u2 = u01_52(w.z, w.w);
+    r.boundary = et <= low;
+    r.et = r.boundary ? low : et;
+    r.bt = bt;
+    const uint8_t ev_boundary = hostLeaf ? (u2 < C.rho ? EV_LEAF : EV_UNSAMPLED_LEAF) : EV_SPECIATION;
+    const uint8_t ev_inner = isRoot ? (u2 < C.thr_root ? EV_DUPLICATION : EV_LOSS) : (u2 >= C.thr_nonroot ? EV_DUPLICATION : EV_LOSS);
+    r.event = r.boundary ? ev_boundary : ev_inner;
     return r;
 }
 

@@ -13,7 +13,7 @@ const MathTables& host_math_tables() {
     return t;
 }
 
-namespace { struct StrSink { std::string s; void put(char c) { s.push_back(c); } static constexpr bool kCounts = false; }; }
+namespace { struct StrSink { std::string s; void put(char c) { s.push_back(c); } void skip(int) {} char* reserve(int) { return nullptr; } static constexpr bool kCounts = false; static constexpr bool kRandomAccess = false; }; }
 
 std::string jdouble(double v) { StrSink k; put_double(k, host_math_tables(), v); return k.s; }
 double host_round_sig(double v, int n) { return round_sig(host_math_tables(), v, n); }
