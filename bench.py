@@ -28,8 +28,8 @@ METRIC, UNIT = "accepted trees/sec", "trees/s"
 
 # Algorithmic instruction mix of one vertex expansion of the sampler (DESIGN.md "K1 roofline"): warp-level instructions
 # on the FP64 pipe and on the INT/other pipes needed by Philox4x32-10 + two 53-bit uniforms + fdlibm log + divide + compare.
-ALG_FP64_INST_PER_VERTEX = 62.0
-ALG_INT_INST_PER_VERTEX = 118.0
+ALG_FP64_INST_PER_VERTEX = 38.0     # -log(1-u)/sum, start-bt, 3 compares (CUDA log: 1 MUFU.RCP64H + 24 DFMA/DADD/DMUL + reconstruction)
+ALG_INT_INST_PER_VERTEX = 70.0      # Philox4x32-10: 20 IMAD.WIDE + 20 LOP3 + 6 key adds; 2 x (bits -> double); counters, stack, select
 
 
 def clocks_sampler(stop, rows, gpu_index):
@@ -211,11 +211,16 @@ def main():
                 hbm_peak = float(json.load(open(peaks_file))["hbm_gbs"]); hbm_src = "measured"
             except Exception:
                 pass
-        verts = float(total.vertices_sampled)
-        gverts = verts / (find_ms * 1e-3) * 1e-9 / world * world     # chip aggregate over ranks / max time
-        # issue-slot roofline of the sampler: time per vertex-warp is bounded below by each pipe's issue rate
-        r_fp64 = peaks["dfma_ginst_per_s"]; r_int = peaks["imad_ginst_per_s"]
-        t_vertex_warp = max(ALG_FP64_INST_PER_VERTEX / r_fp64, ALG_INT_INST_PER_VERTEX / r_int)     # ns per warp of 32 vertices
+        # algorithmic vertices = what the sequential retry loop expands: (attempts up to and including the accepted one) x
+        # mean vertices per attempt; attempts are i.i.d., so the mean over all completed attempts is unbiased
+        useful_attempts = float(total.attempts_total) - trees
+        verts_per_attempt = float(total.vertices_sampled) / max(float(total.attempts_completed), 1.0)
+        verts = useful_attempts * verts_per_attempt
+        verts_executed = float(total.vertices_sampled + total.vertices_abandoned)
+        gverts = verts / (find_ms * 1e-3) * 1e-9
+        # issue-slot roofline of the sampler: a warp-vertex needs ALG_FP64 slots on the FP64 pipe and ALG_FP64 + ALG_INT issue slots
+        r_fp64 = peaks["dfma_ginst_per_s"]; r_issue = peaks["mixed_int_ginst_per_s"]
+        t_vertex_warp = max(ALG_FP64_INST_PER_VERTEX / r_fp64, (ALG_FP64_INST_PER_VERTEX + ALG_INT_INST_PER_VERTEX) / r_issue)     # ns per warp of 32 vertices
         peak_gverts = 32.0 / t_vertex_warp * world
         out_bytes = float(np.sum(total.out_bytes))
         emit_alg_bytes = out_bytes + float(total.event_counts.sum()) * (80 + 16)      # node records + order arrays read once, text written once
@@ -235,6 +240,7 @@ def main():
             "phase_ms_per_step": {k: v / K for k, v in tim.items()},
             "gpu_launches": launches,
             "attempts_per_tree": float(total.attempts_total) / max(trees, 1), "vertices_per_tree": verts / max(trees, 1),
+            "vertices_executed_per_tree": verts_executed / max(trees, 1),
             "out_bytes_per_tree": out_bytes / max(trees, 1), "n_failed": int(total.n_failed),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": int(float(eo[1]) / e_steps / world),
                     "replicates_per_gpu_per_step": ne, "steps": e_steps},

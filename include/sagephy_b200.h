@@ -124,8 +124,9 @@ void sgp_batch_free(sgp_batch* b);
 sgp_status sgp_probe_double_to_string(sgp_context* ctx, const double* v, int64_t n, char* out /* n*32 bytes, NUL padded */);
 sgp_status sgp_probe_math(sgp_context* ctx, int fn /* 0 log, 1 log10, 2 exp, 3 round8 */, const double* v, int64_t n, double* out);
 sgp_status sgp_probe_mt(sgp_context* ctx, int64_t seed, int64_t n_words, uint32_t* out_words);
-/* FP64/INT issue-rate microbenchmarks (roofline denominators for the sampler); returns giga-instructions per second. */
-sgp_status sgp_probe_issue_peaks(sgp_context* ctx, double* dfma_ginst, double* imad_ginst, double* dmul_dep_ginst);
+/* Issue-rate microbenchmarks (roofline denominators for the sampler), giga warp-instructions per second, whole chip:
+ * independent DFMA chains, independent IMAD chains, and an IMAD + SHF + LOP3 mix (what Philox is made of). */
+sgp_status sgp_probe_issue_peaks(sgp_context* ctx, double* dfma_ginst, double* imad_ginst, double* mixed_int_ginst);
 
 #ifdef __cplusplus
 }

@@ -296,4 +296,4 @@ class Context:
         rc = self._lib.sgp_probe_issue_peaks(self._h, C.byref(a), C.byref(b), C.byref(c))
         if rc != 0:
             raise SagephyError("probe failed")
-        return {"dfma_ginst_per_s": a.value, "imad_ginst_per_s": b.value, "dmul_dadd_dependent_ginst_per_s": c.value}
+        return {"dfma_ginst_per_s": a.value, "imad_ginst_per_s": b.value, "mixed_int_ginst_per_s": c.value}

@@ -51,6 +51,7 @@ struct RepInfo {
     int32_t exact;           // -sizes draw (-1: none)
     int32_t pad;
     double total_u, beneath_u, total_p, beneath_p;
+    double p_root_time;      // time of the pruned tree's root (0 if the pruned tree is empty)
     int32_t cnt_u[EV_COUNT];
     int32_t cnt_p[EV_COUNT];
     uint64_t vertices_sampled;   // vertices created in attempts that ran to completion (work counter)

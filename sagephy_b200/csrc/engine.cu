@@ -19,13 +19,16 @@ const unsigned long long* d2s_g_table(); int d2s_g_table_len(); const double* p1
 
 namespace {
 
+// Device buffers come from the CUDA stream-ordered pool (release threshold = unlimited, see Context::Context), so
+// steady-state batches reuse memory instead of paying cudaMalloc/cudaFree per phase.
+thread_local cudaStream_t g_alloc_stream = nullptr;
 template <class T> struct DevBuf {
     T* p = nullptr; size_t n = 0;
     DevBuf() {}
     DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { if (p) cudaFree(p); }
-    void alloc(size_t count) { if (p) { cudaFree(p); p = nullptr; } n = count; if (count) CK(cudaMalloc(&p, count * sizeof(T))); }
-    void upload(const std::vector<T>& v) { alloc(v.size()); if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice)); }
+    ~DevBuf() { if (p) cudaFreeAsync(p, g_alloc_stream); }
+    void alloc(size_t count) { if (p) { cudaFreeAsync(p, g_alloc_stream); p = nullptr; } n = count; if (count) CK(cudaMallocAsync(&p, count * sizeof(T), g_alloc_stream)); }
+    void upload(const std::vector<T>& v) { alloc(v.size()); if (!v.empty()) { CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, g_alloc_stream)); CK(cudaStreamSynchronize(g_alloc_stream)); } }
     T* release() { T* q = p; p = nullptr; n = 0; return q; }
 };
 
@@ -55,13 +58,6 @@ __global__ void k_extract_pool(const RepInfo* info, long long n, long long* out)
 __global__ void k_collect_status(const RepInfo* info, long long n, int status, long long* list, unsigned long long* count) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && info[i].status == status) { unsigned long long k = atomicAdd(count, 1ULL); list[k] = i; }
-}
-
-__global__ void k_root_times(const RepInfo* info, const long long* node_off, const Node* nodes, long long n, double* out) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const RepInfo& x = info[i];
-    out[i] = (x.status == REP_OK && x.p_root >= 0) ? nodes[node_off[i] + x.p_root].abstime : 0.0;
 }
 
 struct DevSummary { unsigned long long n_ok, n_failed, attempts_total, vertices, vertices_abandoned, attempts_completed; unsigned long long ev[17]; unsigned long long leaf_hist[1025]; };
@@ -108,13 +104,18 @@ __global__ void k_peak_dfma(double* out, int iters) {
 }
 __global__ void k_peak_imad(uint32_t* out, int iters) {
     uint32_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7; const uint32_t b = 0xD2511F53u, c = 12345u;
-    for (int i = 0; i < iters; ++i) { a0 = a0 * b + c; a1 = a1 * b + c; a2 = a2 * b + c; a3 = a3 * b + c; a4 = a4 * b + c; a5 = a5 * b + c; a6 = a6 * b + c; a7 = a7 * b + c; }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    // a*a+c cannot be re-associated across iterations, so each statement is exactly one IMAD
+    for (int i = 0; i < iters; ++i) { a0 = a0 * a0 + c; a1 = a1 * a1 + c; a2 = a2 * a2 + c; a3 = a3 * a3 + c; a4 = a4 * a4 + c; a5 = a5 * a5 + c; a6 = a6 * a6 + c; a7 = a7 * a7 + c; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7 ^ b;
 }
-__global__ void k_peak_ddep(double* out, int iters) {
-    double a = threadIdx.x * 1e-3 + 1.0; const double b = 1.0000001;
-    for (int i = 0; i < iters; ++i) { a = __dmul_rn(a, b); a = __dadd_rn(a, 1e-9); }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = a;
+// mixed integer issue: IMAD (fma pipe) interleaved with LOP3 / shifts (alu pipe), the mix Philox is made of
+__global__ void k_peak_mixed(uint32_t* out, int iters) {
+    uint32_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, b0 = a0 * 7 + 1, b1 = b0 + 1, b2 = b0 + 2, b3 = b0 + 3; const uint32_t c = 12345u;
+    for (int i = 0; i < iters; ++i) {
+        a0 = a0 * a0 + c; b0 = (b0 ^ a1) ^ (b0 >> 7); a1 = a1 * a1 + c; b1 = (b1 ^ a2) ^ (b1 >> 7);
+        a2 = a2 * a2 + c; b2 = (b2 ^ a3) ^ (b2 >> 7); a3 = a3 * a3 + c; b3 = (b3 ^ a0) ^ (b3 >> 7);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ b0 ^ b1 ^ b2 ^ b3;
 }
 
 struct EventTimer {
@@ -141,6 +142,8 @@ Context::Context(int dev) : device(dev), impl(new Impl()) {
     if (dev < 0 || dev >= count) throw SgpError("invalid CUDA device index " + std::to_string(dev));
     CK(cudaSetDevice(dev));
     CK(cudaStreamCreate(&impl->stream));
+    g_alloc_stream = impl->stream;
+    { cudaMemPool_t pool; CK(cudaDeviceGetDefaultMemPool(&pool, dev)); unsigned long long thr = ~0ull; CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr)); }
     std::vector<unsigned long long> g(d2s_g_table(), d2s_g_table() + d2s_g_table_len());
     std::vector<double> p(p10_table(), p10_table() + p10_table_len());
     impl->g_table.upload(g); impl->p10.upload(p);
@@ -153,9 +156,9 @@ Context::~Context() { if (impl && impl->stream) { cudaSetDevice(device); cudaStr
 Batch::Batch() {}
 Batch::~Batch() {
     cudaSetDevice(device);
-    for (int s = 0; s < 8; ++s) { if (d_stream[s]) cudaFree(d_stream[s]); if (h_stream[s]) cudaFreeHost(h_stream[s]); }
-    if (d_offsets) cudaFree(d_offsets);
-    if (d_info) cudaFree(d_info);
+    auto rel = [&](void* q) { if (q && cudaFreeAsync(q, (cudaStream_t)stream) != cudaSuccess) { cudaGetLastError(); cudaFree(q); } };
+    for (int s = 0; s < 8; ++s) { rel(d_stream[s]); if (h_stream[s]) cudaFreeHost(h_stream[s]); }
+    rel(d_offsets); rel(d_info);
 }
 const char* Batch::stream_host(int s) {
     if (s < 0 || s >= 8) return nullptr;
@@ -190,7 +193,7 @@ void Batch::fetch_info() {
     cudaMemcpy(inf.data(), d_info, inf.size() * sizeof(RepInfo), cudaMemcpyDeviceToHost);
     status.resize(n); attempts.resize(n); sampled.resize(n); root_time.assign(n, 0.0); total_time.resize(n); events.resize((size_t)n * 17);
     for (long long i = 0; i < n; ++i) {
-        status[i] = inf[i].status; attempts[i] = inf[i].attempts; sampled[i] = inf[i].sampled_leaves; total_time[i] = inf[i].total_u;
+        status[i] = inf[i].status; attempts[i] = inf[i].attempts; sampled[i] = inf[i].sampled_leaves; total_time[i] = inf[i].total_u; root_time[i] = inf[i].p_root_time;
         for (int e = 0; e < 17; ++e) events[(size_t)i * 17 + e] = inf[i].cnt_u[e];
     }
     have_info = true;
@@ -207,9 +210,11 @@ static TinyHost make_tiny(const HostModel& h) {
 void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch& out) {
     CK(cudaSetDevice(device));
     cudaStream_t st = impl->stream;
+    g_alloc_stream = st;
     const long long n = opts.n;
     if (n <= 0) throw SgpError("replicate count must be positive");
     const bool replay = opts.rng_mode == 1;
+    out.stream = (void*)st;
     out.n = n; out.device = device; out.app = cfg.app; out.quiet = cfg.quiet; out.out_prefix = cfg.out_prefix;
     Timings tm; EventTimer total(st), ph(st);
     total.start();
@@ -386,8 +391,9 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     }
     tm.emit_size_ms = ph.stop();
     unsigned long long totals[ST_COUNT];
-    for (int s = 0; s < ST_COUNT; ++s) CK(cudaMemcpy(&totals[s], offsets.p + (size_t)s * (n + 1) + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    for (int s = 0; s < ST_COUNT; ++s) { out.stream_bytes[s] = totals[s]; CK(cudaMalloc(&out.d_stream[s], std::max<unsigned long long>(totals[s], 1))); e.out[s] = out.d_stream[s]; }
+    for (int s = 0; s < ST_COUNT; ++s) CK(cudaMemcpyAsync(&totals[s], offsets.p + (size_t)s * (n + 1) + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int s = 0; s < ST_COUNT; ++s) { out.stream_bytes[s] = totals[s]; CK(cudaMallocAsync(&out.d_stream[s], std::max<unsigned long long>(totals[s], 1), st)); e.out[s] = out.d_stream[s]; }
     ph.start();
     tm.launches += launch_emit(true, e, emit_blocks, st);
     CK(cudaGetLastError());
@@ -408,15 +414,6 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     for (int s = 0; s < 8; ++s) out.suffix[s] = (mask & (1u << s)) ? host_sfx[s] : "";
     tm.total_ms = total.stop();
     out.timings = tm;
-    // per-replicate scalars for the accessors; pruned-root times come from the node arena, which is released on return
-    out.fetch_info();
-    {
-        DevBuf<double> rt; rt.alloc((size_t)n);
-        k_root_times<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const RepInfo*)out.d_info, node_off.p, nodes.p, n, rt.p);
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(out.root_time.data(), rt.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-    }
     if (!opts.keep_on_device) {
         EventTimer d2h(st); d2h.start();
         for (int s = 0; s < 8; ++s) if (mask & (1u << s)) out.stream_host(s);
@@ -458,8 +455,9 @@ void Context::probe_issue(double* dfma, double* imad, double* ddep) {
     *dfma = (double)blocks * threads / 32.0 * iters * 8.0 / (ms * 1e-3) * 1e-9;
     t.start(); k_peak_imad<<<blocks, threads, 0, impl->stream>>>(oi.p, iters); ms = t.stop();
     *imad = (double)blocks * threads / 32.0 * iters * 8.0 / (ms * 1e-3) * 1e-9;
-    t.start(); k_peak_ddep<<<blocks, threads, 0, impl->stream>>>(od.p, iters); ms = t.stop();
-    *ddep = (double)blocks * threads / 32.0 * iters * 2.0 / (ms * 1e-3) * 1e-9;
+    // 4 IMAD + 4 (SHF + LOP3) per iteration = 12 issued instructions per warp
+    t.start(); k_peak_mixed<<<blocks, threads, 0, impl->stream>>>(oi.p, iters); ms = t.stop();
+    *ddep = (double)blocks * threads / 32.0 * iters * 12.0 / (ms * 1e-3) * 1e-9;
     CK(cudaGetLastError());
 }
 

@@ -51,6 +51,7 @@ public:
     ~Batch();
     long long n = 0;
     int device = 0;
+    void* stream = nullptr;   // cudaStream_t the device buffers were allocated on
     int app = 0;
     std::string out_text, err_text, out_prefix;
     bool quiet = false;

@@ -102,6 +102,96 @@ __global__ void __launch_bounds__(kBdFindThreads) k_bd_find(BdArgs a) {
     }
 }
 
+// Single-arc specialisation (HostTreeGen without -bi; requires vtime[0] == 0): no arc bookkeeping, and the lineage stack keeps
+// its top element in a register — a duplication continues with one child directly and parks the other, so a stack load is
+// issued one whole vertex step before its value is needed.
+__global__ void __launch_bounds__(kBdFindThreads) k_bd_find_single(BdArgs a) {
+    __shared__ int s_next[kBdFindThreads / 32];
+    __shared__ int s_best[kBdFindThreads / 32];
+    double st_time[kBdStack];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    const BdConsts C = bd_consts(a.P);
+    const double tip = a.H.tip;
+    const int min_leaves = a.P.min_leaves, max_leaves = a.P.max_leaves, max_attempts = a.P.max_attempts;
+    volatile int* v_best = &s_best[wib];
+    for (;;) {
+        long long r = 0;
+        if (lane == 0) r = (long long)atomicAdd(a.work_counter, 1ULL);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= a.n) break;
+        const unsigned long long gid = (unsigned long long)(a.rep_base + r);
+        const uint32_t rep_lo = (uint32_t)gid, rep_hi = (uint32_t)(gid >> 32);
+        int exact = -1;
+        if (a.P.n_sizes > 0) { PhiloxStream ph; ph.init(a.seed, gid, 0xFFFFFFFFu); exact = a.sizes[ph.next_int(a.P.n_sizes)]; }
+        if (lane == 0) { s_next[wib] = 0; s_best[wib] = 0x7fffffff; }
+        __syncwarp();
+        // lane state: attempt my_a (< 0: none), depth = pending lineages beyond `cur`; stack = st_time[0..sp) + tos
+        bool idle = false, running = false; int my_a = -1, sp = 0, depth = 0; uint32_t vidx = 0; int sampled = 0; bool overflow = false;
+        double cur = 0.0, tos = 0.0;
+        int acc_a = 0x7fffffff, acc_n = 0, acc_sampled = 0;
+        unsigned long long v_completed = 0, v_abandoned = 0; int n_completed = 0;
+        U4 w_next{0, 0, 0, 0};
+        for (;;) {
+            if (!running && !idle) {
+                const int na = atomicAdd(&s_next[wib], 1);
+                if (na > *v_best || na > max_attempts) idle = true;
+                else {
+                    my_a = na; running = true; cur = tip; depth = 0; sp = 0; vidx = 0; sampled = 0;
+                    w_next = philox4x32_10(0u, (uint32_t)my_a, rep_lo, rep_hi, k0, k1);
+                }
+            }
+            if (__all_sync(0xffffffffu, idle)) break;
+            if (running) {
+                if (my_a > *v_best) { v_abandoned += vidx; running = false; idle = true; continue; }
+                const U4 w = w_next;
+                ++vidx;
+                w_next = philox4x32_10(vidx, (uint32_t)my_a, rep_lo, rep_hi, k0, k1);
+                const BdVertex v = bd_vertex_single(C, cur, w);
+                bool finished = false, rejected = false;
+                if (v.event == EV_DUPLICATION) {
+                    // continue with one child, park the other
+                    if (depth > 0) { if (sp >= kBdStack) { overflow = true; rejected = true; finished = true; } else st_time[sp++] = tos; }
+                    tos = v.et; ++depth; cur = v.et;
+                } else {
+                    if (v.event == EV_LEAF) { ++sampled; if (sampled > max_leaves) { rejected = true; finished = true; } }
+                    if (!finished) {
+                        if (depth == 0) finished = true;
+                        else { cur = tos; --depth; if (depth > 0) tos = st_time[--sp]; }
+                    }
+                }
+                if (finished) {
+                    running = false;
+                    v_completed += vidx; ++n_completed;
+                    const bool ok = !rejected && sampled >= min_leaves && sampled <= max_leaves && (exact == -1 || sampled == exact);
+                    if (ok) { atomicMin(&s_best[wib], my_a); acc_a = my_a; acc_n = (int)vidx; acc_sampled = sampled; }
+                }
+            }
+        }
+        const int best = *v_best;
+        for (int o = 16; o > 0; o >>= 1) {
+            v_completed += __shfl_xor_sync(0xffffffffu, v_completed, o); v_abandoned += __shfl_xor_sync(0xffffffffu, v_abandoned, o);
+            n_completed += __shfl_xor_sync(0xffffffffu, n_completed, o);
+        }
+        const bool any_overflow = __any_sync(0xffffffffu, overflow);
+        if (best != 0x7fffffff) {
+            if (acc_a == best) {
+                RepInfo inf; memset(&inf, 0, sizeof(inf));
+                inf.status = REP_OK; inf.exact = exact; inf.root = -1; inf.p_root = -1; inf.acc_attempt = (uint32_t)best; inf.n_pool = acc_n;
+                inf.sampled_leaves = acc_sampled; inf.attempts = best + 2;
+                inf.vertices_sampled = v_completed; inf.vertices_abandoned = v_abandoned; inf.attempts_completed = n_completed;
+                a.info[r] = inf;
+            }
+        } else if (lane == 0) {
+            RepInfo inf; memset(&inf, 0, sizeof(inf));
+            inf.status = any_overflow ? REP_STACK_OVERFLOW : REP_MAX_ATTEMPTS; inf.exact = exact; inf.root = -1; inf.p_root = -1;
+            inf.attempts = max_attempts + 1; inf.vertices_sampled = v_completed; inf.vertices_abandoned = v_abandoned; inf.attempts_completed = n_completed;
+            a.info[r] = inf;
+        }
+        __syncwarp();
+    }
+}
+
 // Build pass: regenerates the accepted attempt depth-first straight into the arena (no scratch).
 __global__ void __launch_bounds__(256) k_bd_build(BdArgs a) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -119,7 +209,7 @@ __global__ void __launch_bounds__(256) k_bd_build(BdArgs a) {
         --sp;
         const double start = st_time[sp]; const int X = st_arc[sp]; const int32_t pw = st_par[sp];
         const U4 w = philox4x32_10(vidx, inf.acc_attempt, rep_lo, rep_hi, k0, k1);
-        const BdVertex v = bd_vertex(C, a.H, X, start, w);
+        const BdVertex v = a.H.nV == 1 ? bd_vertex_single(C, start, w) : bd_vertex(C, a.H, X, start, w);
         const int me = (int)vidx++;
         Node& nd = N[me];
         nd.abstime = v.et;

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(128) k_label_prune(LabelArgs a) {
     }
     if (a.has_stem_override) { N[root].bl = a.stem_override; if (p_root >= 0) N[p_root].p_bl = a.stem_override; }
     // ---- breadth-first orders and the getInfo reductions (sum order = BFS order)
-    inf.p_root = p_root; inf.n_u = up; inf.n_p = nu;
+    inf.p_root = p_root; inf.n_u = up; inf.n_p = nu; inf.p_root_time = p_root >= 0 ? N[p_root].abstime : 0.0;
     for (int e = 0; e < EV_COUNT; ++e) { inf.cnt_u[e] = 0; inf.cnt_p[e] = 0; }
     double tot = 0.0, ben = 0.0;
     {

@@ -299,8 +299,9 @@ __device__ __forceinline__ BdVertex bd_vertex(const BdConsts& C, const TinyHost&
     BdVertex r;
     const bool isRoot = H.parent[X] < 0, hostLeaf = H.left[X] < 0;
     const double low = H.vtime[X];
-    const double bt = -log(one_minus_u(w.x, w.y)) * C.inv_sum;
-    const double et = start - bt;
+    // explicit (non-contractable) multiply / subtract: the find and build kernels must round identically
+    const double bt = __dmul_rn(-log(one_minus_u(w.x, w.y)), C.inv_sum);
+    const double et = __dsub_rn(start, bt);
     const double u2 = u01_52(w.z, w.w);
     r.boundary = et <= low;
     r.et = r.boundary ? low : et;
@@ -308,6 +309,20 @@ __device__ __forceinline__ BdVertex bd_vertex(const BdConsts& C, const TinyHost&
     const uint8_t ev_boundary = hostLeaf ? (u2 < C.rho ? EV_LEAF : EV_UNSAMPLED_LEAF) : EV_SPECIATION;
     const uint8_t ev_inner = isRoot ? (u2 < C.thr_root ? EV_DUPLICATION : EV_LOSS) : (u2 >= C.thr_nonroot ? EV_DUPLICATION : EV_LOSS);
     r.event = r.boundary ? ev_boundary : ev_inner;
+    return r;
+}
+
+
+// Single-arc host ("H0:T;"): every boundary vertex is a host leaf, every interior event is on the root arc.
+__device__ __forceinline__ BdVertex bd_vertex_single(const BdConsts& C, double start, U4 w) {
+    BdVertex r;
+    const double bt = __dmul_rn(-log(one_minus_u(w.x, w.y)), C.inv_sum);
+    const double et = __dsub_rn(start, bt);
+    const double u2 = u01_52(w.z, w.w);
+    r.boundary = et <= 0.0;
+    r.et = r.boundary ? 0.0 : et;
+    r.bt = bt;
+    r.event = r.boundary ? (u2 < C.rho ? EV_LEAF : EV_UNSAMPLED_LEAF) : (u2 < C.thr_root ? EV_DUPLICATION : EV_LOSS);
     return r;
 }
 
