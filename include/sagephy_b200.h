@@ -58,6 +58,7 @@ typedef enum {
     SGP_STREAM_PRUNED_LEAFMAP = 7,    /* .pruned.leafmap       */
     SGP_STREAM_COUNT = 8
 } sgp_stream;
+/* BranchRelaxer batches use stream 0 for the relaxed trees (file = the -o value, or stdout) and stream 1 for <-o value>.info */
 
 /* Batch extension of the reference CLI (everything else in argv is the reference's own grammar). */
 typedef struct {
@@ -66,8 +67,11 @@ typedef struct {
     int32_t rng_mode;           /* sgp_rng_mode; MT replay: replicate i == reference run with -s (seed + i) */
     uint32_t stream_mask;       /* bit s set = emit stream s; 0 = whatever the reference would write for these options */
     int32_t keep_on_device;     /* 1: leave stream bytes in HBM only (host accessors then copy lazily) */
-    int32_t reserved;
+    int32_t flags;              /* SGP_FLAG_* */
 } sgp_batch_opts;
+
+/* BranchRelaxer only: the <tree> positional (file or string) holds one Newick tree per line; replicate i relaxes tree i % T. */
+#define SGP_FLAG_MULTI_TREE_INPUT 1
 
 /* summary counters of a batch (merged across GPUs with an allreduce(sum) by the caller) */
 #define SGP_HIST_LEAF_BINS 1025
@@ -103,6 +107,9 @@ const uint64_t* sgp_batch_stream_offsets(sgp_batch* b, int stream);      /* n+1 
 /* Copies stream bytes / the n+1 offsets from HBM into a caller-owned host buffer (pinned memory gives full PCIe rate). */
 sgp_status sgp_batch_copy_stream(sgp_batch* b, int stream, void* dst, uint64_t dst_capacity);
 sgp_status sgp_batch_copy_offsets(sgp_batch* b, int stream, uint64_t* dst /* n+1 */);
+uint32_t sgp_batch_stream_mask(const sgp_batch* b);                      /* bit s set = stream s was emitted */
+/* BranchRelaxer: flat per-branch arrays (replicate-major, vertex-id order): which = 0 rates, 1 relaxed lengths. */
+const double* sgp_batch_values(sgp_batch* b, int which, int64_t* count);
 uint64_t sgp_batch_stream_bytes(const sgp_batch* b, int stream);
 const char* sgp_batch_stream_suffix(const sgp_batch* b, int stream);     /* file suffix the reference uses, "" if unused */
 const int32_t* sgp_batch_status(sgp_batch* b);                           /* n entries, sgp_rep_status */
@@ -122,7 +129,7 @@ void sgp_batch_free(sgp_batch* b);
 
 /* Probes used by the parity tests: run the device implementations of the Java-exact primitives on `n` inputs. */
 sgp_status sgp_probe_double_to_string(sgp_context* ctx, const double* v, int64_t n, char* out /* n*32 bytes, NUL padded */);
-sgp_status sgp_probe_math(sgp_context* ctx, int fn /* 0 log, 1 log10, 2 exp, 3 round8 */, const double* v, int64_t n, double* out);
+sgp_status sgp_probe_math(sgp_context* ctx, int fn /* 0 log, 1 log10, 2 exp, 3 round8, 4 normal quantile, 5 pow(x,0.37), 6 chi2 quantile k=4, 7 chi2 quantile k=0.25, 8 pow(e,x) */, const double* v, int64_t n, double* out);
 sgp_status sgp_probe_mt(sgp_context* ctx, int64_t seed, int64_t n_words, uint32_t* out_words);
 /* Issue-rate microbenchmarks (roofline denominators for the sampler), giga warp-instructions per second, whole chip:
  * independent DFMA chains, independent IMAD chains, and an IMAD + SHF + LOP3 mix (what Philox is made of). */

@@ -14,6 +14,7 @@
 #include "jmath.hpp"
 #include "jrandom.hpp"
 #include "newick.hpp"
+#include "jpow.hpp"
 
 namespace oracle {
 
@@ -224,9 +225,8 @@ public:
         }
         return m;
     }
-    // Math.pow(Math.E, y): restated as exp-like through libm pow (fdlibm pow not ported; differs by < 1 ulp, which
-    // can only flip a recipient choice on a ~1e-16-probability tie). Recorded in DESIGN.md.
-    static double j_pow_e(double y) { return std::pow(2.718281828459045, y); }
+    // Math.pow(Math.E, y) through the fdlibm pow restatement (jpow.hpp)
+    static double j_pow_e(double y) { return j_pow(2.718281828459045, y); }
 
     // Epoch.sampleArc :249-296. Returns -5 when there is no candidate.
     int sample_arc(EpochO& ep, JavaMT& prng, int excludeArc, int fromArcIdx, double eventTime, const std::string& bias,

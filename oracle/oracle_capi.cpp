@@ -3,6 +3,7 @@
 #include <chrono>
 #include <cstring>
 #include "apps.hpp"
+#include "relax.hpp"
 
 using namespace oracle;
 
@@ -15,6 +16,7 @@ void dispatch(const std::vector<std::string>& argv, Outputs& o, RepStats* st) {
     const std::string& app = argv[0];
     if (app == "HostTreeGen") run_host_tree_gen(rest, o, st);
     else if (app == "GuestTreeGen") run_guest_tree_gen(rest, o, st);
+    else if (app == "BranchRelaxer") run_branch_relaxer(rest, o, st);
     else { o.out += "Unknown application: " + app + "\n"; if (st) st->status = 2; }
 }
 
@@ -76,6 +78,9 @@ double oracle_log(double x) { return j_log(x); }
 double oracle_log10(double x) { return j_log10(x); }
 double oracle_exp(double x) { return j_exp(x); }
 double oracle_round_sig(double x, int n) { return round_sig(x, n); }
+double oracle_pow(double x, double y) { return j_pow(x, y); }
+double oracle_normal_quantile(double p) { return normal_quantile(p); }
+double oracle_gamma_quantile(double p, double k, double theta) { return chi2_quantile(p, 2 * k) * theta / 2; }
 long long oracle_round(double x) { return j_round(x); }
 
 }  // extern "C"

@@ -1,0 +1,266 @@
+// ORACLE — test infrastructure only (see oracle/README.md). PARITY UNPINNED.
+//
+// BranchRelaxer and its IID rate models. Restates
+//   apps/SaGePhy/BranchRelaxer.java:48-141,148-197        (main loop, isOK, getRelaxedLengths, toNewickTree)
+//   apps/SaGePhy/BranchRelaxerParameters.java:80-117,167-179 (model factory, tree loading)
+//   apps/SaGePhy/{Constant,IIDExponential,IIDGamma,IIDLogNormal,IIDNormal,IIDUniform,IIDSamplesFromFile}RateModel.java
+//   math/LogNormalDistribution.java:39-48,196-205, math/Normal.java:17-36,48-86, math/NormalDistribution.java:44-54,217-221,
+//   math/GammaDistribution.java:53-62,255-257, math/Gamma.java:16-57,83-88,127-204, math/ChiSquared.java:23-84,
+//   math/UniformDistribution.java:40-49,210-212, math/RealInterval.java:177-240, math/ExponentialDistribution.java:79-81,155-159
+//   topology/RTree.java:53-86, io/NewickTreeWriter.java:100-113, topology/DoubleMap.java:183-185 (Arrays.toString)
+//   java.util.Random.nextGaussian / nextBoolean (JDK specification: polar method on StrictMath.log / sqrt)
+#pragma once
+#include "apps.hpp"
+#include "jpow.hpp"
+
+namespace oracle {
+
+inline double JavaMT::nextGaussian() {
+    if (have_gauss) { have_gauss = false; return next_gauss; }
+    double v1, v2, s;
+    do { v1 = 2 * nextDouble() - 1; v2 = 2 * nextDouble() - 1; s = v1 * v1 + v2 * v2; } while (s >= 1 || s == 0);
+    double multiplier = std::sqrt(-2 * j_log(s) / s);
+    next_gauss = v2 * multiplier; have_gauss = true;
+    return v1 * multiplier;
+}
+
+inline double normal_cdf(double x) {     // math/Normal.java:17-36
+    if (x < -39) return 0.0;
+    if (x > 9) return 1.0;
+    const double b1 = 0.319381530, b2 = -0.356563782, b3 = 1.781477937, b4 = -1.821255978, b5 = 1.330274429, p = 0.2316419, c = 0.39894228;
+    if (x >= 0.0) { double t = 1.0 / (1.0 + p * x); return (1.0 - c * j_exp(-x * x / 2.0) * t * (t * (t * (t * (t * b5 + b4) + b3) + b2) + b1)); }
+    double t = 1.0 / (1.0 - p * x);
+    return (c * j_exp(-x * x / 2.0) * t * (t * (t * (t * (t * b5 + b4) + b3) + b2) + b1));
+}
+inline double normal_quantile(double p) {    // math/Normal.java:48-86 (Voutier 2010)
+    if (p < 0.0 || p > 1.0) throw std::invalid_argument("IllegalArgumentException: Cannot compute quantile for probability not in [0,1].");
+    if (0.025 <= p && p <= 0.975) {
+        const double a0 = 0.151015505647689, a1 = -0.5303572634357367, a2 = 1.365020122861334, b0 = 0.132089632343748, b1 = -0.7607324991323768;
+        double q = p - 0.5; double r = j_pow(q, 2);
+        return (q * (a2 + (a1 * r + a0) / (r * r + b1 * r + b0)));
+    }
+    if (1e-50 < p && p < 1.0 - 1e-16) {
+        const double c3 = -1.000182518730158122, cp0 = 16.682320830719986527, cp1 = 4.120411523939115059, cp2 = 0.029814187308200211,
+                     d0 = 7.173787663925508066, d1 = 8.759693508958633869;
+        if (p < 0.5) { double r = std::sqrt(j_log(1.0 / j_pow(p, 2))); return (c3 * r + cp2 + (cp1 * r + cp0) / (r * r + d1 * r + d0)); }
+        double r = std::sqrt(j_log(1.0 / j_pow(1.0 - p, 2)));
+        return -(c3 * r + cp2 + (cp1 * r + cp0) / (r * r + d1 * r + d0));
+    }
+    return (p < 0.5 ? -HUGE_VAL : HUGE_VAL);
+}
+inline double ln_gamma(double xx) {      // math/Gamma.java:44-57
+    static const double LANCZOS[14] = {57.1562356658629235, -59.5979603554754912, 14.1360979747417471, -0.491913816097520199, .339946499848118887e-4,
+        .465236289270485756e-4, -.983744753048795646e-4, .158088703224912494e-3, -.210264441724104883e-3, .217439618115212643e-3,
+        -.164318106536763890e-3, .844182239838527433e-4, -.261908384015814087e-4, .368991826595316234e-5};
+    const double SQRT_2_PI = std::sqrt(2 * 3.141592653589793);
+    double x = xx, y = xx;
+    double tmp = x + 5.24218750000000000;
+    tmp = (x + 0.5) * j_log(tmp) - tmp;
+    double ser = 0.999999999999997092;
+    for (int j = 0; j < 14; ++j) ser += LANCZOS[j] / ++y;
+    return (tmp + j_log(SQRT_2_PI * ser / x));
+}
+inline double inc_gamma_ratio(double x, double k) {     // math/Gamma.java:127-204 (AS 32)
+    if (x < 0.0 || k <= 0.0) throw std::invalid_argument("IllegalArgumentException: Invalid parameters for incomplete gamma ratio.");
+    if (x == 0.0) return 0.0;
+    const double accuracy = 1.0e-8, overflow = 1.0e30, xbig = 1.0E6, alimit = 1000.0;
+    double g_in = 0.0, g = ln_gamma(k);
+    double factor = j_exp(k * j_log(x) - x - g);
+    if (k > alimit) { double pn1 = 3 * std::sqrt(k) * (j_pow(x / k, 1.0 / 3.0) + 1.0 / (9.0 * k) - 1.0); return normal_cdf(pn1); }
+    if (x > xbig) return 1.0;
+    if (x > 1.0 && x >= k) {
+        double a = 1.0 - k, b = a + x + 1.0, term = 0.0, pn[6];
+        pn[0] = 1.0; pn[1] = x; pn[2] = x + 1.0; pn[3] = x * b;
+        g_in = pn[2] / pn[3];
+        double dif = 1.0, rn = 0.0;
+        for (;;) {
+            a += 1.0; b += 2.0; term += 1.0;
+            double an = a * term;
+            for (int i = 0; i < 2; i++) pn[i + 4] = b * pn[i + 2] - an * pn[i];
+            if (pn[5] != 0.0) {
+                rn = pn[4] / pn[5]; dif = std::fabs(g_in - rn);
+                if (dif <= accuracy) { if (dif <= accuracy * rn) return 1.0 - factor * g_in; }
+                g_in = rn;
+            }
+            for (int i = 0; i < 4; i++) pn[i] = pn[i + 2];
+            if (std::fabs(pn[4]) >= overflow) for (int i = 0; i < 4; i++) pn[i] = pn[i] / overflow;
+        }
+    }
+    g_in = 1.0; double term = 1.0, rn = k;
+    do { rn += 1.0; term *= x / rn; g_in += term; } while (term > accuracy);
+    return g_in * factor / k;
+}
+inline double chi2_quantile(double p, double k) {     // math/ChiSquared.java:23-84 (AS 91)
+    if (p < 2e-6 || p > 0.999998 || k <= 0.0) throw std::invalid_argument("IllegalArgumentException: Invalid arguments for chi^2 quantile function.");
+    const double E = 0.5e-6, AA = j_log(2.0);
+    double XX = 0.5 * k, C = XX - 1.0, G = ln_gamma(XX), ch;
+    if (k < (-1.24 * j_log(p))) {
+        ch = j_pow(p * XX * j_exp(G + XX * AA), 1.0 / XX);
+        if (ch < E) return ch;
+    } else if (k <= 0.32) {
+        ch = 0.4; double a = j_log(1.0 - p), Q;
+        do {
+            Q = ch;
+            double P1 = 1.0 + ch * (4.67 + ch), P2 = ch * (6.73 + ch * (6.66 + ch));
+            double T = -0.5 + (4.67 + 2.0 * ch) / P1 - (6.73 + ch * (13.32 + 3.0 * ch)) / P2;
+            ch = ch - (1.0 - j_exp(a + G + 0.5 * ch + C * AA) * P2 / P1) / T;
+        } while (std::fabs(Q / ch - 1) > 0.01);
+    } else {
+        double X = normal_quantile(p), P1 = 0.222222 / k;
+        ch = k * j_pow((X * std::sqrt(P1) + 1.0 - P1), 3);
+        if (ch > (2.2 * k + 6.0)) ch = -2.0 * (j_log(1.0 - p) - C * j_log(0.5 * ch) + G);
+    }
+    double Q;
+    do {
+        Q = ch;
+        double P1 = 0.5 * ch, P2 = p - inc_gamma_ratio(P1, XX);
+        double T = P2 * j_exp(XX * AA + G + P1 - C * j_log(ch));
+        double B = T / ch, A = 0.5 * T - B * C;
+        double S1 = (210 + A * (140 + A * (105 + A * (84 + A * (70 + 60 * A))))) / 420;
+        double S2 = (420 + A * (735 + A * (966 + A * (1141 + 1278 * A)))) / 2520;
+        double S3 = (210 + A * (462 + A * (707 + 932 * A))) / 2520;
+        double S4 = (252 + A * (672 + 1182 * A) + C * (294 + A * (889 + 1740 * A))) / 5040;
+        double S5 = (84 + 264 * A + C * (175 + 606 * A)) / 2520;
+        double S6 = (120 + C * (346 + 127 * C)) / 5040;
+        ch = ch + T * (1 + 0.5 * T * S1 - B * C * (S1 - B * (S2 - B * (S3 - B * (S4 - B * (S5 - B * S6))))));
+    } while (std::fabs(Q / ch - 1) > E);
+    return ch;
+}
+
+struct RateModelO {
+    enum Kind { CONSTANT, EXPONENTIAL, GAMMA, LOGNORMAL, NORMAL, UNIFORM, SAMPLES } kind = CONSTANT;
+    double a = 0, b = 0, sigma = 0; std::vector<double> samples; std::string file;
+    std::string name() const {
+        static const char* n[] = {"ConstantRates", "IIDExponentialRates", "IIDGammaRates", "IIDLogNormalRates", "IIDNormalRates", "IIDUniformRates", "IIDSamplesFromFileRates"};
+        return n[kind];
+    }
+    // java.util.HashMap iteration order of the parameter names (bucket = (h ^ h>>>16) & (cap-1)); all key sets here are
+    // single-character-hash friendly: {"mu","sigma2"}: hash("mu")=3496 -> bucket 0 of 2... computed in params() explicitly.
+    std::vector<std::pair<std::string, std::string>> params() const;
+    double sample(JavaMT& prng) const {
+        switch (kind) {
+            case CONSTANT: return a;
+            case EXPONENTIAL: return -j_log(1.0 - prng.nextDouble()) / a;
+            case GAMMA: return chi2_quantile(prng.nextDouble(), 2 * a) * b / 2;
+            case LOGNORMAL: return j_exp(normal_quantile(prng.nextDouble()) * sigma + a);
+            case NORMAL: return prng.nextGaussian() * sigma + a;
+            case UNIFORM: { double d = prng.nextDouble(); return prng.nextBoolean() ? (b - a) * d + a : (b - a) * (1.0 - d) + a; }
+            case SAMPLES: return samples[prng.nextInt((int)samples.size())];
+        }
+        return 0;
+    }
+};
+
+inline int java_string_hash(const std::string& s) { int32_t h = 0; for (unsigned char c : s) h = 31 * h + c; return h; }
+inline std::vector<std::pair<std::string, std::string>> hashmap_order(std::vector<std::pair<std::string, std::string>> kv, int initialCapacity) {
+    // HashMap(initialCapacity): table size = next power of two >= initialCapacity (min 1), doubled while size > 0.75 * cap
+    int cap = 1; while (cap < initialCapacity) cap <<= 1;
+    size_t inserted = 0; std::vector<std::vector<std::pair<std::string, std::string>>> tab(cap);
+    auto bucket = [&](const std::string& k, int c) { uint32_t h = (uint32_t)java_string_hash(k); h ^= (h >> 16); return (int)(h & (uint32_t)(c - 1)); };
+    for (auto& e : kv) {
+        tab[bucket(e.first, cap)].push_back(e); ++inserted;
+        if ((double)inserted > 0.75 * cap) {
+            int nc = cap * 2; std::vector<std::vector<std::pair<std::string, std::string>>> nt(nc);
+            for (auto& bk : tab) for (auto& x : bk) nt[bucket(x.first, nc)].push_back(x);
+            tab.swap(nt); cap = nc;
+        }
+    }
+    std::vector<std::pair<std::string, std::string>> out;
+    for (auto& bk : tab) for (auto& x : bk) out.push_back(x);
+    return out;
+}
+inline std::vector<std::pair<std::string, std::string>> RateModelO::params() const {
+    auto D = [](double v) { return java_double_to_string(v); };
+    switch (kind) {
+        case CONSTANT: return hashmap_order({{"rate", D(a)}}, 1);
+        case EXPONENTIAL: return hashmap_order({{"lambda", D(a)}}, 1);
+        case GAMMA: return hashmap_order({{"k", D(a)}, {"theta", D(b)}}, 2);
+        case LOGNORMAL: return hashmap_order({{"mu", D(a)}, {"sigma2", D(sigma * sigma)}}, 2);
+        case NORMAL: return hashmap_order({{"mu", D(a)}, {"sigma2", D(b)}}, 2);
+        case UNIFORM: return hashmap_order({{"a", D(a)}, {"b", D(b)}}, 2);
+        case SAMPLES: return hashmap_order({{"filename", file}}, 2);
+    }
+    return {};
+}
+
+inline const std::vector<OptSpec>& relax_specs() {
+    static const std::vector<OptSpec> s = {{{"-h", "--help"}, 0}, {{"-o", "--output-file"}, 1}, {{"-s", "--seed"}, 1}, {{"-x", "--auxiliary-tags"}, 0},
+        {{"-innms", "--keep-interior-names"}, 0}, {{"-min", "--min-rate"}, 1}, {{"-max", "--max-rate"}, 1}, {{"-a", "--max-attempts"}, 1}};
+    return s;
+}
+inline bool ieq(const std::string& a, const char* b) { if (a.size() != std::strlen(b)) return false; for (size_t i = 0; i < a.size(); ++i) if (std::tolower((unsigned char)a[i]) != std::tolower((unsigned char)b[i])) return false; return true; }
+
+inline void relax_to_string(const NTree& t, const NVertex* v, const std::vector<double>& len, const std::vector<double>& orig, const std::vector<double>& rate,
+                            bool keepInterior, bool withMeta, std::string& sb) {
+    if (!v->children.empty()) {
+        sb.push_back('(');
+        for (size_t i = 0; i < v->children.size(); ++i) { if (i) sb.push_back(','); relax_to_string(t, v->children[i], len, orig, rate, keepInterior, withMeta, sb); }
+        sb.push_back(')');
+    }
+    int x = v->number;
+    if (v->name && (v->is_leaf() || keepInterior)) sb += *v->name;
+    if (!std::isnan(len[x])) { sb.push_back(':'); sb += java_double_to_string(len[x]); }
+    if (withMeta) sb += "[ID=" + std::to_string(x) + " ORIGBL=" + java_double_to_string(orig[x]) + " RATE=" + java_double_to_string(rate[x]) + "]";
+}
+inline std::string arr_to_string(const std::vector<double>& a) { std::string s = "["; for (size_t i = 0; i < a.size(); ++i) { if (i) s += ", "; s += java_double_to_string(a[i]); } return s + "]"; }
+
+inline void run_branch_relaxer(const std::vector<std::string>& args, Outputs& o, RepStats* st = nullptr) {
+    try {
+        ParsedArgs p = jc_parse(args, relax_specs());
+        if (p.has("-h") || args.size() < 1) { o.out += "Usage:\n    java -jar sagephy-X.Y.Z.jar BranchRelaxer [options] <tree> <model> <arg1> <arg2> <...>\n\n"; return; }
+        if (!p.has("-s")) throw std::invalid_argument("oracle: a seed (-s) is required (the reference would read /dev/random)");
+        JavaMT prng(p.get("-s", ""));
+        auto arg = [&](size_t i) -> const std::string& { if (i >= p.pos.size()) throw std::out_of_range("IndexOutOfBoundsException: Index: " + std::to_string(i) + ", Size: " + std::to_string(p.pos.size())); return p.pos[i]; };
+        RateModelO m; const std::string& model = arg(1);
+        if (ieq(model, "Constant")) { m.kind = RateModelO::CONSTANT; m.a = parse_double(arg(2)); }
+        else if (ieq(model, "IIDExponential")) { m.kind = RateModelO::EXPONENTIAL; m.a = parse_double(arg(2)); if (m.a <= 0) throw std::invalid_argument("IllegalArgumentException: Cannot have non-positive rate for exponential distribution."); }
+        else if (ieq(model, "IIDGamma")) { m.kind = RateModelO::GAMMA; m.a = parse_double(arg(2)); m.b = parse_double(arg(3)); if (m.a <= 0 || m.b <= 0) throw std::invalid_argument("IllegalArgumentException: Cannot have non-positive shape or scale for gamma distribution."); }
+        else if (ieq(model, "IIDLogNormal")) { m.kind = RateModelO::LOGNORMAL; m.a = parse_double(arg(2)); double s2 = parse_double(arg(3)); if (s2 <= 0) throw std::invalid_argument("IllegalArgumentException: Cannot have non-positive sigma^2 for log-normal distribution."); m.sigma = std::sqrt(s2); }
+        else if (ieq(model, "IIDNormal")) { m.kind = RateModelO::NORMAL; m.a = parse_double(arg(2)); m.b = parse_double(arg(3)); if (m.b <= 0) throw std::invalid_argument("IllegalArgumentException: Cannot have non-positive variance for normal distribution."); m.sigma = std::sqrt(m.b); }
+        else if (ieq(model, "IIDUniform")) { m.kind = RateModelO::UNIFORM; m.a = parse_double(arg(2)); m.b = parse_double(arg(3)); if (m.a >= m.b) throw std::invalid_argument("IllegalArgumentException: Invalid range for uniform distribution."); }
+        else if (ieq(model, "IIDSamplesFromFile")) {
+            m.kind = RateModelO::SAMPLES; m.file = arg(2);
+            std::ifstream f(m.file); if (!f) throw std::invalid_argument("IllegalArgumentException: java.io.FileNotFoundException: " + m.file);
+            std::string line; while (std::getline(f, line)) m.samples.push_back(parse_double(line));
+        } else throw std::invalid_argument("oracle: rate model outside the accelerated path (autocorrelated / RK11 models, SURVEY.md §2 row 16): " + model);
+        std::unique_ptr<NTree> t = file_exists(arg(0)) ? nw_read_tree(read_file(arg(0))) : nw_read_tree(arg(0));
+        auto bfs = t->vertices_bfs(); int n = (int)bfs.size();
+        for (NVertex* v : bfs) if (v->children.size() == 1) throw TopologyException("Cannot create RTree from collapsable NewickTree.");
+        for (NVertex* v : bfs) if (v->is_leaf() && !v->name) throw std::runtime_error("NullPointerException: Missing leaf name in vertex " + std::to_string(v->number) + ".");
+        std::vector<double> orig(n, std::nan("")); bool has = false;
+        for (NVertex* v : bfs) if (v->bl) { orig[v->number] = *v->bl; has = true; }
+        if (!has) throw NewickIOException("Cannot create time map; times missing in tree.");
+        int root = t->root->number, ignore = -1;
+        if (std::isnan(orig[root])) { orig[root] = 0.0; ignore = root; }
+        double mn = parse_double(p.get("-min", "1e-64")), mx = parse_double(p.get("-max", "1e64"));
+        int maxAttempts = parse_int(p.get("-a", "10000")), attempts = 0;
+        std::vector<double> rates(n);
+        for (;;) {
+            if (attempts > maxAttempts) { o.err += "Failed to create valid rates within max allowed attempts.\n"; if (st) { st->status = 1; st->attempts = attempts; } return; }
+            if (m.kind == RateModelO::SAMPLES) { /* the reference re-reads the file on every call; same values */ }
+            for (int x = 0; x < n; ++x) rates[x] = m.sample(prng);
+            ++attempts;
+            bool ok = true;
+            for (int x = 0; x < n; ++x) { if (x == ignore) continue; if (rates[x] < mn || rates[x] > mx) { ok = false; break; } }
+            if (ok) break;
+        }
+        std::vector<double> rel(n); for (int x = 0; x < n; ++x) rel[x] = orig[x] * rates[x];
+        std::string tree; relax_to_string(*t, t->root, rel, orig, rates, p.has("-innms"), p.has("-x"), tree); tree.push_back(';');
+        if (!p.has("-o")) o.out += tree + "\n";
+        else {
+            std::string of = trim_java(p.get("-o", ""));
+            o.file(of, tree + "\n");
+            std::string info = "# BRANCHLENGTHRELAXER\nArguments:\t" + arrays_to_string(args) + "\nAttempts:\t" + std::to_string(attempts) + "\n";
+            info += "Original lengths:\t" + arr_to_string(orig) + "\nRates:\t" + arr_to_string(rates) + "\nRelaxed lengths:\t" + arr_to_string(rel) + "\n";
+            info += "Model:\t" + m.name() + "\nModel parameters:\n";
+            for (auto& kv : m.params()) info += "\t" + kv.first + "\t" + kv.second + "\n";
+            o.file(of + ".info", info);
+        }
+        if (st) { st->attempts = attempts; st->n_unpruned = n; double tot = 0; for (double v : rel) tot += v; st->total_time = tot; }
+    } catch (std::exception& e) {
+        o.err += std::string(e.what()) + "\n\nUse option -h or --help to show usage.\n";
+        if (st) st->status = 2;
+    }
+}
+
+}  // namespace oracle

@@ -23,12 +23,13 @@ EVENT_NAMES = ("SPECIATION", "CODIVERGENCE", "LEAF", "UNSAMPLED_LEAF", "DUPLICAT
                "ADDITIVE_TRANSFER", "REPLACING_TRANSFER") + tuple(
     f"{k}_TRANSFER_{g}_{s}" for k in ("ADDITIVE", "REPLACING") for g in ("INTRAGENE", "INTERGENE") for s in ("INTRASPECIES", "INTERSPECIES"))
 RNG_PHILOX, RNG_MT_REPLAY = 0, 1
+FLAG_MULTI_TREE_INPUT = 1
 STATUS_OK, STATUS_USAGE = 0, 6
 
 # every symbol include/sagephy_b200.h declares (checked by the CPU test-suite)
 EXPORTED_SYMBOLS = (
     "sgp_context_create", "sgp_context_destroy", "sgp_last_error", "sgp_app_run", "sgp_batch_n", "sgp_batch_stream_data",
-    "sgp_batch_stream_device_data", "sgp_batch_stream_offsets", "sgp_batch_copy_stream", "sgp_batch_copy_offsets", "sgp_batch_stream_bytes", "sgp_batch_stream_suffix",
+    "sgp_batch_stream_device_data", "sgp_batch_stream_offsets", "sgp_batch_copy_stream", "sgp_batch_copy_offsets", "sgp_batch_stream_mask", "sgp_batch_values", "sgp_batch_stream_bytes", "sgp_batch_stream_suffix",
     "sgp_batch_status", "sgp_batch_attempts", "sgp_batch_sampled_leaves", "sgp_batch_root_times", "sgp_batch_total_times",
     "sgp_batch_event_counts", "sgp_batch_stdout", "sgp_batch_stderr", "sgp_batch_out_prefix", "sgp_batch_summary",
     "sgp_batch_timings", "sgp_batch_write_files", "sgp_batch_free", "sgp_probe_double_to_string", "sgp_probe_math",
@@ -37,7 +38,7 @@ EXPORTED_SYMBOLS = (
 
 class BatchOpts(C.Structure):
     _fields_ = [("n_replicates", C.c_int64), ("replicate_offset", C.c_int64), ("rng_mode", C.c_int32),
-                ("stream_mask", C.c_uint32), ("keep_on_device", C.c_int32), ("reserved", C.c_int32)]
+                ("stream_mask", C.c_uint32), ("keep_on_device", C.c_int32), ("flags", C.c_int32)]
 
 
 class SummaryStruct(C.Structure):
@@ -73,6 +74,8 @@ def load_library() -> C.CDLL:
     L.sgp_batch_stream_offsets.argtypes = [vp, C.c_int]; L.sgp_batch_stream_offsets.restype = C.POINTER(C.c_uint64)
     L.sgp_batch_copy_stream.argtypes = [vp, C.c_int, vp, C.c_uint64]; L.sgp_batch_copy_stream.restype = C.c_int
     L.sgp_batch_copy_offsets.argtypes = [vp, C.c_int, vp]; L.sgp_batch_copy_offsets.restype = C.c_int
+    L.sgp_batch_stream_mask.argtypes = [vp]; L.sgp_batch_stream_mask.restype = C.c_uint32
+    L.sgp_batch_values.argtypes = [vp, C.c_int, C.POINTER(C.c_int64)]; L.sgp_batch_values.restype = C.POINTER(C.c_double)
     L.sgp_batch_stream_bytes.argtypes = [vp, C.c_int]; L.sgp_batch_stream_bytes.restype = C.c_uint64
     L.sgp_batch_stream_suffix.argtypes = [vp, C.c_int]; L.sgp_batch_stream_suffix.restype = cp
     for name, typ in (("sgp_batch_status", C.c_int32), ("sgp_batch_attempts", C.c_int32), ("sgp_batch_sampled_leaves", C.c_int32),
@@ -191,11 +194,17 @@ class Batch:
     def files(self, i: int = 0) -> dict:
         """{suffix: bytes} of replicate i — what the reference would have written for that run."""
         out = {}
+        mask = int(self._lib.sgp_batch_stream_mask(self._h))
         for s in range(8):
-            sfx = self.stream_suffix(s)
-            if sfx:
-                out[sfx] = self.replicate(s, i)
+            if mask & (1 << s):
+                out[self.stream_suffix(s)] = self.replicate(s, i)
         return out
+
+    def values(self, which: int) -> np.ndarray:
+        """BranchRelaxer: flat per-branch doubles (0 = rates, 1 = relaxed lengths), replicate-major."""
+        cnt = C.c_int64()
+        p = self._lib.sgp_batch_values(self._h, which, C.byref(cnt))
+        return np.ctypeslib.as_array(p, shape=(cnt.value,)).copy()
 
     def _arr(self, fn, shape, dtype):
         p = getattr(self._lib, fn)(self._h)
@@ -254,11 +263,11 @@ class Context:
             pass
 
     def run(self, app: str, args, n: int = 1, rng: int = RNG_PHILOX, offset: int = 0, stream_mask: int = 0,
-            keep_on_device: bool = False, check: bool = True) -> Batch:
+            keep_on_device: bool = False, check: bool = True, flags: int = 0) -> Batch:
         """Runs ``<app> args...`` (reference CLI grammar) for n replicates."""
         argv = [str(a).encode() for a in args]
         arr = (C.c_char_p * len(argv))(*argv)
-        opts = BatchOpts(n, offset, rng, stream_mask, 1 if keep_on_device else 0, 0)
+        opts = BatchOpts(n, offset, rng, stream_mask, 1 if keep_on_device else 0, flags)
         h = C.c_void_p()
         rc = self._lib.sgp_app_run(self._h, app.encode(), len(argv), arr, C.byref(opts), C.byref(h))
         b = Batch(self._lib, h, rc)

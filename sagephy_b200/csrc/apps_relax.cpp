@@ -1,0 +1,123 @@
+// BranchRelaxer front-end: reference grammar -> RelaxConfig.
+// Mirrors apps/SaGePhy/BranchRelaxerParameters.java:28-117 (options, model factory, tree loading) and
+// BranchRelaxer.java:79-93 (RTree / names / lengths preparation, root without length -> 0 and ignored by the range check).
+#include <climits>
+#include "apps_common.hpp"
+
+namespace sgp {
+using namespace cli;
+
+namespace {
+const Opt kRelaxOpts[] = {{"-h", "--help", 0}, {"-o", "--output-file", 1}, {"-s", "--seed", 1}, {"-x", "--auxiliary-tags", 0},
+    {"-innms", "--keep-interior-names", 0}, {"-min", "--min-rate", 1}, {"-max", "--max-rate", 1}, {"-a", "--max-attempts", 1}};
+
+bool same_nocase(const std::string& a, const char* b) {
+    size_t n = 0; while (b[n]) ++n;
+    if (a.size() != n) return false;
+    for (size_t i = 0; i < n; ++i) { char x = a[i], y = b[i]; if (x >= 'A' && x <= 'Z') x += 32; if (y >= 'A' && y <= 'Z') y += 32; if (x != y) return false; }
+    return true;
+}
+// iteration order of a java.util.HashMap<String,String> filled by put() in the given order
+std::vector<std::pair<std::string, std::string>> java_hashmap_order(const std::vector<std::pair<std::string, std::string>>& kv, int initial_capacity) {
+    auto hash = [](const std::string& s) { uint32_t h = 0; for (unsigned char c : s) h = 31u * h + c; return h ^ (h >> 16); };
+    int cap = 1; while (cap < initial_capacity) cap <<= 1;
+    size_t count = 0;
+    for (size_t i = 0; i < kv.size(); ++i) { ++count; if ((double)count > 0.75 * cap) cap <<= 1; }
+    std::vector<std::pair<std::string, std::string>> out;     // bucket order, insertion order inside a bucket
+    for (int b = 0; b < cap; ++b) for (auto& e : kv) if ((int)(hash(e.first) & (uint32_t)(cap - 1)) == b) out.push_back(e);
+    return out;
+}
+RelaxTreeTemplate make_template(const FlatTree& t, bool keep_interior) {
+    RelaxTreeTemplate r; r.nV = t.n; r.root = t.root;
+    for (int v = 0; v < t.n; ++v) {
+        if (t.n_children[v] == 1) throw SgpError("Cannot create RTree from collapsable NewickTree.");
+        if (t.n_children[v] == 0 && !t.has_name[v]) throw SgpError("Missing leaf name in vertex " + std::to_string(v) + ".");
+    }
+    r.orig.assign(t.n, std::nan("")); bool any = false;
+    for (int v = 0; v < t.n; ++v) if (t.has_bl[v]) { r.orig[v] = t.bl[v]; any = true; }
+    if (!any) throw SgpError("Cannot create time map; times missing in tree.");
+    if (std::isnan(r.orig[r.root])) { r.orig[r.root] = 0.0; r.ignore = r.root; }
+    r.chain.assign(t.n, 0); r.flags.assign(t.n, 0); r.names.resize(t.n);
+    for (int i = 0; i < t.n; ++i) {          // BFS order: parents before children
+        const int v = t.bfs[i]; const int p = t.parent[v];
+        const bool first = p >= 0 && t.first_child[p] == v;
+        r.chain[v] = (int16_t)(first ? r.chain[p] + 1 : 0);
+        uint8_t f = 0;
+        if (t.n_children[v] == 0) f |= 1;
+        if (p >= 0 && t.next_sibling[v] >= 0) f |= 2;
+        if (t.has_name[v] && (t.n_children[v] == 0 || keep_interior)) { f |= 4; r.names[v] = t.name[v]; }
+        r.flags[v] = f;
+    }
+    return r;
+}
+}  // namespace
+
+void parse_relax_app(const std::vector<std::string>& args, bool multi_tree_input, RelaxConfig& cfg, AppResult& res) {
+    cfg.args = args;
+    Parsed p = scan(args, kRelaxOpts, (int)(sizeof kRelaxOpts / sizeof kRelaxOpts[0]));
+    if (p.on("-h") || args.empty()) {
+        res.status = 6;
+        res.out_text = "Usage:\n    java -jar sagephy-X.Y.Z.jar BranchRelaxer [options] <tree> <model> <arg1> <arg2> <...>\n"
+                       "Supported models (accelerated): Constant <rate>, IIDGamma <k> <theta>, IIDLogNormal <mu> <sigma2>, IIDNormal <mu> <sigma2>,\n"
+                       "    IIDUniform <a> <b>, IIDExponential <lambda>, IIDSamplesFromFile <filename>\n\n";
+        return;
+    }
+    auto arg = [&](size_t i) -> const std::string& {
+        if (i >= p.positional.size()) throw SgpError("IndexOutOfBoundsException: Index: " + std::to_string(i) + ", Size: " + std::to_string(p.positional.size()));
+        return p.positional[i];
+    };
+    if (p.on("-s")) { cfg.has_seed = true; cfg.seed = to_i64(p.str("-s", "0")); cfg.seed_arg_index = p.val_index.at("-s"); }
+    else { cfg.has_seed = false; cfg.seed = random_seed(); }
+    const std::string& model = arg(1);
+    std::vector<std::pair<std::string, std::string>> kv; int hcap = 2;
+    if (same_nocase(model, "Constant")) { cfg.model = 0; cfg.pa = to_double(arg(2)); cfg.model_name = "ConstantRates"; kv = {{"rate", jdouble(cfg.pa)}}; hcap = 1; }
+    else if (same_nocase(model, "IIDExponential")) {
+        cfg.model = 1; cfg.pa = to_double(arg(2)); if (cfg.pa <= 0) throw SgpError("Cannot have non-positive rate for exponential distribution.");
+        cfg.model_name = "IIDExponentialRates"; kv = {{"lambda", jdouble(cfg.pa)}}; hcap = 1;
+    } else if (same_nocase(model, "IIDGamma")) {
+        cfg.model = 2; cfg.pa = to_double(arg(2)); cfg.pb = to_double(arg(3));
+        if (cfg.pa <= 0 || cfg.pb <= 0) throw SgpError("Cannot have non-positive shape or scale for gamma distribution.");
+        cfg.model_name = "IIDGammaRates"; kv = {{"k", jdouble(cfg.pa)}, {"theta", jdouble(cfg.pb)}};
+    } else if (same_nocase(model, "IIDLogNormal")) {
+        cfg.model = 3; cfg.pa = to_double(arg(2)); const double s2 = to_double(arg(3));
+        if (s2 <= 0) throw SgpError("Cannot have non-positive sigma^2 for log-normal distribution.");
+        cfg.sigma = std::sqrt(s2); cfg.model_name = "IIDLogNormalRates"; kv = {{"mu", jdouble(cfg.pa)}, {"sigma2", jdouble(cfg.sigma * cfg.sigma)}};
+    } else if (same_nocase(model, "IIDNormal")) {
+        cfg.model = 4; cfg.pa = to_double(arg(2)); cfg.pb = to_double(arg(3));
+        if (cfg.pb <= 0) throw SgpError("Cannot have non-positive variance for normal distribution.");
+        cfg.sigma = std::sqrt(cfg.pb); cfg.model_name = "IIDNormalRates"; kv = {{"mu", jdouble(cfg.pa)}, {"sigma2", jdouble(cfg.pb)}};
+    } else if (same_nocase(model, "IIDUniform")) {
+        cfg.model = 5; cfg.pa = to_double(arg(2)); cfg.pb = to_double(arg(3));
+        if (cfg.pa >= cfg.pb) throw SgpError("Invalid range for uniform distribution.");
+        cfg.model_name = "IIDUniformRates"; kv = {{"a", jdouble(cfg.pa)}, {"b", jdouble(cfg.pb)}};
+    } else if (same_nocase(model, "IIDSamplesFromFile")) {
+        cfg.model = 6; cfg.model_name = "IIDSamplesFromFileRates";
+        std::ifstream f(arg(2)); if (!f) throw SgpError("java.io.FileNotFoundException: " + arg(2));
+        std::string line; while (std::getline(f, line)) cfg.samples.push_back(to_double(line));
+        if (cfg.samples.empty()) throw SgpError("samples file is empty: " + arg(2));
+        char buf[PATH_MAX]; const char* rp = realpath(arg(2).c_str(), buf);
+        kv = {{"filename", rp ? std::string(rp) : arg(2)}};
+    } else {
+        res.status = 4;
+        res.err_text = "rate model outside the accelerated path (autocorrelated / RK11 models are a later row of the scope table): " + model + "\n";
+        return;
+    }
+    cfg.params = java_hashmap_order(kv, hcap);
+    cfg.min_rate = to_double(p.str("-min", "1e-64")); cfg.max_rate = to_double(p.str("-max", "1e64")); cfg.max_attempts = to_int(p.str("-a", "10000"));
+    cfg.do_meta = p.on("-x"); cfg.keep_interior = p.on("-innms");
+    cfg.has_outfile = p.on("-o"); if (cfg.has_outfile) cfg.outfile = java_trim(p.str("-o", ""));
+    const std::string text = exists(arg(0)) ? slurp(arg(0)) : arg(0);
+    if (!multi_tree_input) cfg.trees.push_back(make_template(parse_newick(text), cfg.keep_interior));
+    else {
+        size_t b = 0;
+        while (b < text.size()) {
+            size_t e = text.find('\n', b); if (e == std::string::npos) e = text.size();
+            std::string line = text.substr(b, e - b); b = e + 1;
+            if (line.find_first_not_of(" \t\r") == std::string::npos) continue;
+            cfg.trees.push_back(make_template(parse_newick(line), cfg.keep_interior));
+        }
+        if (cfg.trees.empty()) throw SgpError("no tree found in the multi-tree input");
+    }
+}
+
+}  // namespace sgp

@@ -38,6 +38,17 @@ sgp_status sgp_app_run(sgp_context* ctx, const char* app, int argc, const char* 
     std::vector<std::string> args; for (int i = 0; i < argc; ++i) args.emplace_back(argv[i] ? argv[i] : "");
     auto* b = new sgp_batch();
     try {
+        if (std::string(app) == "BranchRelaxer") {
+            RelaxConfig rc; AppResult rr;
+            parse_relax_app(args, (o.flags & SGP_FLAG_MULTI_TREE_INPUT) != 0, rc, rr);
+            b->b.out_text = rr.out_text; b->b.err_text = rr.err_text;
+            if (rr.status == 6) { *out = b; return SGP_USAGE; }
+            if (rr.status != 0) { ctx->last_error = rr.err_text; *out = b; return (sgp_status)rr.status; }
+            BatchOpts bo; bo.n = o.n_replicates; bo.offset = o.replicate_offset; bo.rng_mode = o.rng_mode; bo.stream_mask = o.stream_mask; bo.keep_on_device = o.keep_on_device != 0;
+            ctx->ctx->run_relax(rc, bo, b->b);
+            *out = b;
+            return SGP_OK;
+        }
         TreeGenConfig cfg; AppResult res;
         parse_treegen_app(app, args, cfg, res);
         b->b.out_text = res.out_text; b->b.err_text = res.err_text;
@@ -81,6 +92,12 @@ sgp_status sgp_batch_copy_offsets(sgp_batch* b, int s, uint64_t* dst) {
     if (!b || s < 0 || s >= 8 || !dst || !b->b.d_offsets) return SGP_ERR_INVALID_ARGUMENT;
     return b->b.copy_offsets_to(s, (unsigned long long*)dst) ? SGP_OK : SGP_ERR_NO_DEVICE;
 }
+uint32_t sgp_batch_stream_mask(const sgp_batch* b) { return b ? b->b.stream_mask : 0u; }
+const double* sgp_batch_values(sgp_batch* b, int which, int64_t* count) {
+    if (!b) return nullptr;
+    if (count) *count = b->b.n_values;
+    return b->b.values_host(which);
+}
 uint64_t sgp_batch_stream_bytes(const sgp_batch* b, int s) { return (b && s >= 0 && s < 8) ? b->b.stream_bytes[s] : 0; }
 const char* sgp_batch_stream_suffix(const sgp_batch* b, int s) { return (b && s >= 0 && s < 8) ? b->b.suffix[s] : ""; }
 const int32_t* sgp_batch_status(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_info(); return b->b.status.data(); }
@@ -95,7 +112,8 @@ const char* sgp_batch_stdout(const sgp_batch* cb) {
     if (!b) return "";
     if (!b->stdout_ready) {
         b->stdout_cache = b->b.out_text;
-        if (b->b.quiet && b->b.d_stream[1]) { const char* t = b->b.stream_host(1); if (t) b->stdout_cache.append(t, b->b.stream_bytes[1]); }
+        const int qs = b->b.app == 3 ? 0 : 1;      // BranchRelaxer prints the relaxed tree, the generators the pruned tree
+        if (b->b.quiet && b->b.d_stream[qs]) { const char* t = b->b.stream_host(qs); if (t) b->stdout_cache.append(t, b->b.stream_bytes[qs]); }
         b->stdout_ready = true;
     }
     return b->stdout_cache.c_str();
@@ -124,7 +142,7 @@ sgp_status sgp_batch_write_files(sgp_batch* b) {
     b->b.fetch_info();
     bool all_failed = true; for (long long i = 0; i < b->b.n; ++i) if (b->b.status[i] == 0) all_failed = false;
     for (int s = 0; s < 8; ++s) {
-        if (!b->b.suffix[s][0]) continue;
+        if (!(b->b.stream_mask & (1u << s))) continue;
         std::string sfx = b->b.suffix[s];
         if (all_failed) {
             // the reference writes only the failure note: <prefix>.info (HostTreeGen.java:65) / <prefix>.pruned.info (GuestTreeGen.java:50)

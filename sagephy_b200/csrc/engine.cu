@@ -10,6 +10,7 @@
 #include "hostfmt.hpp"
 #include "launch.hpp"
 #include "rng.cuh"
+#include "jmath_ext.cuh"
 
 namespace sgp {
 
@@ -88,7 +89,9 @@ __global__ void k_probe_math(int fn, const double* v, long long n, double* out, 
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double x = v[i];
-    out[i] = fn == 0 ? jlog(x) : fn == 1 ? jlog10(x) : fn == 2 ? jexp(x) : round_sig(T, x, 8);
+    int err = 0;
+    out[i] = fn == 0 ? jlog(x) : fn == 1 ? jlog10(x) : fn == 2 ? jexp(x) : fn == 3 ? round_sig(T, x, 8) : fn == 4 ? jnormal_quantile(x)
+           : fn == 5 ? jpow(x, 0.37) : fn == 6 ? jchi2_quantile(x, 4.0, &err) : fn == 7 ? jchi2_quantile(x, 0.25, &err) : jpow(2.718281828459045, x);
 }
 __global__ void k_probe_mt(long long seed, long long n, uint32_t* out, uint32_t* state) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -151,14 +154,21 @@ Context::Context(int dev) : device(dev), impl(new Impl()) {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, dev));
     impl->sm_count = prop.multiProcessorCount;
 }
-Context::~Context() { if (impl && impl->stream) { cudaSetDevice(device); cudaStreamDestroy(impl->stream); } }
+Context::~Context() {
+    if (impl && impl->stream) {
+        cudaSetDevice(device); g_alloc_stream = impl->stream;
+        impl->g_table.alloc(0); impl->p10.alloc(0);       // release pool memory before the stream goes away
+        cudaStreamSynchronize(impl->stream); cudaStreamDestroy(impl->stream); impl->stream = nullptr; g_alloc_stream = nullptr;
+    }
+}
 
 Batch::Batch() {}
 Batch::~Batch() {
     cudaSetDevice(device);
-    auto rel = [&](void* q) { if (q && cudaFreeAsync(q, (cudaStream_t)stream) != cudaSuccess) { cudaGetLastError(); cudaFree(q); } };
+    // plain cudaFree: the owning context (and its stream) may already be gone when a batch is released
+    auto rel = [&](void* q) { if (q) cudaFree(q); };
     for (int s = 0; s < 8; ++s) { rel(d_stream[s]); if (h_stream[s]) cudaFreeHost(h_stream[s]); }
-    rel(d_offsets); rel(d_info);
+    rel(d_offsets); rel(d_info); rel(d_values[0]); rel(d_values[1]);
 }
 const char* Batch::stream_host(int s) {
     if (s < 0 || s >= 8) return nullptr;
@@ -412,6 +422,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     out.d_offsets = offsets.release(); out.d_info = info.release();
     static const char* host_sfx[8] = {".unpruned.tree", ".pruned.tree", ".unpruned.info", ".pruned.info", ".unpruned.guest2host", ".pruned.guest2host", ".unpruned.leafmap", ".pruned.leafmap"};
     for (int s = 0; s < 8; ++s) out.suffix[s] = (mask & (1u << s)) ? host_sfx[s] : "";
+    out.stream_mask = mask;
     tm.total_ms = total.stop();
     out.timings = tm;
     if (!opts.keep_on_device) {
@@ -420,6 +431,124 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         out.fetch_offsets();
         out.timings.d2h_ms = d2h.stop();
     }
+}
+
+// ---- BranchRelaxer -----------------------------------------------------------------------------------------------------------
+const double* Batch::values_host(int which) {
+    if (which < 0 || which > 1 || !d_values[which]) return nullptr;
+    if (h_values[which].empty() && n_values) {
+        cudaSetDevice(device);
+        h_values[which].resize((size_t)n_values);
+        cudaMemcpy(h_values[which].data(), d_values[which], (size_t)n_values * sizeof(double), cudaMemcpyDeviceToHost);
+    }
+    return h_values[which].data();
+}
+
+void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& out) {
+    CK(cudaSetDevice(device));
+    cudaStream_t st = impl->stream; g_alloc_stream = st;
+    const long long n = opts.n;
+    if (n <= 0) throw SgpError("replicate count must be positive");
+    const bool replay = opts.rng_mode == 1;
+    out.stream = (void*)st; out.n = n; out.device = device; out.app = 3; out.quiet = !cfg.has_outfile; out.out_prefix = cfg.outfile;
+    Timings tm; EventTimer total(st), ph(st); total.start();
+
+    // flatten the tree templates
+    const int T = (int)cfg.trees.size();
+    std::vector<RelaxTreeView> views(T); std::vector<double> orig; std::vector<int16_t> chain; std::vector<uint8_t> flags; std::vector<int32_t> name_off; std::string blob;
+    long long sum_v = 0;
+    for (int t = 0; t < T; ++t) {
+        const RelaxTreeTemplate& tt = cfg.trees[t];
+        views[t].nV = tt.nV; views[t].root = tt.root; views[t].ignore = tt.ignore; views[t].v0 = sum_v; sum_v += tt.nV;
+        orig.insert(orig.end(), tt.orig.begin(), tt.orig.end()); chain.insert(chain.end(), tt.chain.begin(), tt.chain.end()); flags.insert(flags.end(), tt.flags.begin(), tt.flags.end());
+        for (int v = 0; v < tt.nV; ++v) { name_off.push_back((int32_t)blob.size()); name_off.push_back((int32_t)tt.names[v].size()); blob += tt.names[v]; }
+    }
+    const long long rounds = (n + T - 1) / T; const long long slots = rounds * sum_v;
+    RelaxArgs a{};
+    auto add = [&](const std::string& s, int& off, int& len) { off = (int)blob.size(); len = (int)s.size(); blob += s; };
+    {
+        std::string pre = "[", post; const bool split = replay && cfg.seed_arg_index >= 0;
+        for (size_t i = 0; i < cfg.args.size(); ++i) {
+            std::string& dst = (split && (int)i > cfg.seed_arg_index) ? post : pre;
+            if ((int)i == cfg.seed_arg_index && split) { if (i) pre += ", "; continue; }
+            if (i) dst += ", ";
+            dst += cfg.args[i];
+        }
+        if (split) post += "]"; else pre += "]";
+        add(pre, a.args_pre_off, a.args_pre_len); add(post, a.args_post_off, a.args_post_len); a.seed_mode = split ? 1 : 0; a.seed_base = cfg.seed;
+        std::string tail = "Model:\t" + cfg.model_name + "\nModel parameters:\n";
+        for (auto& kv : cfg.params) tail += "\t" + kv.first + "\t" + kv.second + "\n";
+        add(tail, a.model_tail_off, a.model_tail_len);
+    }
+    DevBuf<RelaxTreeView> d_views; d_views.upload(views);
+    DevBuf<double> d_orig, d_samples, rates, relaxed; d_orig.upload(orig); d_samples.upload(cfg.samples);
+    DevBuf<int16_t> d_chain; d_chain.upload(chain); DevBuf<uint8_t> d_flags; d_flags.upload(flags); DevBuf<int32_t> d_name; d_name.upload(name_off);
+    DevBuf<char> d_blob; { std::vector<char> b(blob.begin(), blob.end()); b.push_back(0); d_blob.upload(b); }
+    rates.alloc((size_t)slots); relaxed.alloc((size_t)slots);
+    DevBuf<int32_t> attempts, status; attempts.alloc((size_t)n); status.alloc((size_t)n);
+    CK(cudaMemsetAsync(attempts.p, 0, (size_t)n * sizeof(int32_t), st)); CK(cudaMemsetAsync(status.p, 0, (size_t)n * sizeof(int32_t), st));
+    DevBuf<uint32_t> mt_state; if (replay) mt_state.alloc((size_t)((n + 127) / 128 * 128 / 32 + 1) * 624 * 32);
+    a.n = n; a.rep_base = opts.offset; a.seed = (unsigned long long)cfg.seed; a.model = cfg.model; a.pa = cfg.pa; a.pb = cfg.pb; a.sigma = cfg.sigma;
+    a.min_rate = cfg.min_rate; a.max_rate = cfg.max_rate; a.max_attempts = cfg.max_attempts; a.samples = d_samples.p; a.n_samples = (int)cfg.samples.size();
+    a.n_trees = T; a.sum_v = sum_v; a.trees = d_views.p; a.orig = d_orig.p; a.chain = d_chain.p; a.vflags = d_flags.p; a.name_off = d_name.p; a.blob = d_blob.p;
+    a.T = impl->T; a.rates = rates.p; a.relaxed = relaxed.p; a.attempts = attempts.p; a.status = status.p; a.mt_state = mt_state.p;
+    a.do_meta = cfg.do_meta; a.has_outfile = cfg.has_outfile;
+
+    // ---- K5 rates + lengths ------------------------------------------------------------------------------------------------
+    ph.start();
+    if (replay) {
+        // status 0 -> REP_PENDING marker expected by the kernel
+        launch_relax_rates(true, a, 0, 0, st); ++tm.launches;
+    } else {
+        launch_relax_apply(a, slots, st); tm.launches += 2;          // attempt 0 in parallel
+        launch_relax_rates(false, a, 1, 1, st); ++tm.launches;       // flagged replicates continue from attempt 1
+    }
+    CK(cudaGetLastError());
+    tm.find_ms = ph.stop();
+
+    // ---- emission ------------------------------------------------------------------------------------------------------------
+    const unsigned mask = opts.stream_mask ? opts.stream_mask : (cfg.has_outfile ? 3u : 1u);
+    DevBuf<unsigned long long> sizes, sizes_n, offsets;
+    sizes.alloc((size_t)2 * (n + 1)); sizes_n.alloc((size_t)2 * n); offsets.alloc((size_t)8 * (n + 1));
+    CK(cudaMemsetAsync(sizes.p, 0, (size_t)2 * (n + 1) * sizeof(unsigned long long), st)); CK(cudaMemsetAsync(sizes_n.p, 0, (size_t)2 * n * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(offsets.p, 0, (size_t)8 * (n + 1) * sizeof(unsigned long long), st));
+    DevBuf<uint16_t> plen_tree, plen_info; plen_tree.alloc((size_t)slots); plen_info.alloc((size_t)(3 * slots + 8 * n));
+    a.plen_tree = plen_tree.p; a.plen_info = plen_info.p; a.sizes = sizes_n.p; a.offsets = offsets.p;
+    a.has_outfile = (mask & 2u) ? 1 : 0;
+    unsigned long long totals[2] = {0, 0};
+    if (mask & 3u) {
+        ph.start();
+        launch_relax_emit(false, a, st); ++tm.launches; CK(cudaGetLastError());
+        size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, sizes.p, offsets.p, (int)(n + 1), st);
+        DevBuf<char> tmp; tmp.alloc(tb);
+        for (int s = 0; s < 2; ++s) {
+            CK(cudaMemcpyAsync(sizes.p + (size_t)s * (n + 1), sizes_n.p + (size_t)s * n, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+            cub::DeviceScan::ExclusiveSum(tmp.p, tb, sizes.p + (size_t)s * (n + 1), offsets.p + (size_t)s * (n + 1), (int)(n + 1), st); ++tm.launches;
+        }
+        for (int s = 0; s < 2; ++s) CK(cudaMemcpyAsync(&totals[s], offsets.p + (size_t)s * (n + 1) + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        tm.emit_size_ms = ph.stop();
+        for (int s = 0; s < 2; ++s) { out.stream_bytes[s] = totals[s]; CK(cudaMallocAsync(&out.d_stream[s], std::max<unsigned long long>(totals[s], 1), st)); a.out[s] = out.d_stream[s]; }
+        ph.start();
+        launch_relax_emit(true, a, st); ++tm.launches; CK(cudaGetLastError());
+        tm.emit_write_ms = ph.stop();
+    }
+    out.stream_mask = mask & 3u;
+    out.suffix[0] = ""; out.suffix[1] = ".info";
+    // per-replicate scalars
+    out.status.resize((size_t)n); out.attempts.resize((size_t)n); out.sampled.assign((size_t)n, 0); out.root_time.assign((size_t)n, 0.0); out.total_time.assign((size_t)n, 0.0);
+    out.events.assign((size_t)n * 17, 0);
+    CK(cudaMemcpyAsync(out.status.data(), status.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out.attempts.data(), attempts.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    out.have_info = true;
+    Summary& S = out.summary;
+    for (long long i = 0; i < n; ++i) { if (out.status[i] == REP_OK) ++S.n_ok; else ++S.n_failed; S.attempts_total += out.attempts[i]; }
+    S.vertices_sampled = slots; S.out_bytes[0] = (long long)totals[0]; S.out_bytes[1] = (long long)totals[1];
+    out.d_offsets = offsets.release();
+    out.d_values[0] = rates.release(); out.d_values[1] = relaxed.release(); out.n_values = slots;
+    tm.total_ms = total.stop(); out.timings = tm;
+    if (!opts.keep_on_device) { for (int s = 0; s < 2; ++s) if (mask & (1u << s)) out.stream_host(s); out.fetch_offsets(); }
 }
 
 void Context::probe_d2s(const double* v, long long n, char* out) {

@@ -28,11 +28,28 @@ struct TreeGenConfig {
     int seed_arg_index = -1;            // position of the seed value inside args
 };
 
+struct RelaxTreeTemplate {
+    int nV = 0, root = -1, ignore = -1;
+    std::vector<double> orig; std::vector<int16_t> chain; std::vector<uint8_t> flags; std::vector<std::string> names;
+};
+
+struct RelaxConfig {
+    int model = 0; double pa = 0, pb = 0, sigma = 0;
+    std::vector<double> samples;
+    double min_rate = 1e-64, max_rate = 1e64; int max_attempts = 10000;
+    bool do_meta = false, keep_interior = false, has_outfile = false; std::string outfile;
+    std::vector<RelaxTreeTemplate> trees;
+    bool has_seed = false; long long seed = 0;
+    std::vector<std::string> args; int seed_arg_index = -1;
+    std::string model_name; std::vector<std::pair<std::string, std::string>> params;   // in java.util.HashMap iteration order
+};
+
 struct BatchOpts {
     long long n = 1, offset = 0;
     int rng_mode = 0;         // 0 Philox, 1 MT replay
     unsigned stream_mask = 0;
     bool keep_on_device = false;
+    bool multi_tree_input = false;
 };
 
 struct Timings { double find_ms = 0, build_ms = 0, label_ms = 0, emit_size_ms = 0, emit_write_ms = 0, d2h_ms = 0, total_ms = 0; long long launches = 0; };
@@ -60,6 +77,10 @@ public:
     char* d_stream[8] = {nullptr}; unsigned long long stream_bytes[8] = {0};
     unsigned long long* d_offsets = nullptr;      // [8][n+1]
     void* d_info = nullptr;                       // RepInfo[n]
+    unsigned stream_mask = 0;
+    double* d_values[2] = {nullptr, nullptr}; long long n_values = 0;   // BranchRelaxer: rates, relaxed lengths (flat, replicate-major)
+    std::vector<double> h_values[2];
+    const double* values_host(int which);
     // host (lazy)
     char* h_stream[8] = {nullptr};
     std::vector<unsigned long long> h_offsets;    // [8][n+1]
@@ -81,6 +102,7 @@ public:
     std::string last_error;
     struct Impl; std::unique_ptr<Impl> impl;
     void run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch& out);
+    void run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& out);
     void probe_d2s(const double* v, long long n, char* out);
     void probe_math(int fn, const double* v, long long n, double* out);
     void probe_mt(long long seed, long long n_words, uint32_t* out);
@@ -90,5 +112,6 @@ public:
 // apps.cpp: reference CLI grammar -> configs
 struct AppResult { int status = 0; std::string out_text, err_text; };   // status: 0 run, 6 usage, other = error code
 void parse_treegen_app(const std::string& app, const std::vector<std::string>& args, TreeGenConfig& cfg, AppResult& res);
+void parse_relax_app(const std::vector<std::string>& args, bool multi_tree_input, RelaxConfig& cfg, AppResult& res);
 
 }  // namespace sgp

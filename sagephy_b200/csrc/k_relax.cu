@@ -1,0 +1,16 @@
+#include "kernels_relax.cuh"
+#include "launch.hpp"
+namespace sgp {
+void launch_relax_rates(bool replay, const RelaxArgs& a, int first_attempt, int only_flagged, cudaStream_t st) {
+    const int blocks = (int)((a.n + 127) / 128);
+    if (replay) k_relax_rates<true><<<blocks, 128, 0, st>>>(a, first_attempt, only_flagged); else k_relax_rates<false><<<blocks, 128, 0, st>>>(a, first_attempt, only_flagged);
+}
+void launch_relax_apply(const RelaxArgs& a, long long total_slots, cudaStream_t st) {
+    k_relax_apply<<<(unsigned)((total_slots + 255) / 256), 256, 0, st>>>(a, total_slots);
+    k_relax_finish_apply<<<(unsigned)((a.n + 255) / 256), 256, 0, st>>>(a);
+}
+void launch_relax_emit(bool write, const RelaxArgs& a, cudaStream_t st) {
+    const unsigned blocks = (unsigned)((a.n * 32 + kEmitWarps * 32 - 1) / (kEmitWarps * 32));
+    if (write) k_relax_emit<true><<<blocks, kEmitWarps * 32, 0, st>>>(a); else k_relax_emit<false><<<blocks, kEmitWarps * 32, 0, st>>>(a);
+}
+}  // namespace sgp

@@ -96,3 +96,42 @@ struct EmitArgs {
 };
 
 }  // namespace sgp
+
+namespace sgp {
+
+// ---- BranchRelaxer ------------------------------------------------------------------------------------------------------------
+enum RelaxModel : int { RM_CONSTANT = 0, RM_EXPONENTIAL = 1, RM_GAMMA = 2, RM_LOGNORMAL = 3, RM_NORMAL = 4, RM_UNIFORM = 5, RM_SAMPLES = 6 };
+
+// One input tree ("template"): vertex ids are the reference's post-order numbers, so id order == Newick emission order.
+struct RelaxTreeView {
+    int32_t nV, root, ignore;          // ignore: root vertex whose missing length was replaced by 0 (-1 otherwise)
+    long long v0;                      // offset of this tree's vertices in the flat per-vertex template arrays
+};
+
+struct RelaxArgs {
+    long long n; long long rep_base; unsigned long long seed;
+    int model; double pa, pb, sigma;   // model parameters (a, b, sqrt(variance))
+    double min_rate, max_rate; int max_attempts;
+    const double* samples; int n_samples;
+    int n_trees; long long sum_v;      // replicate r relaxes template r % n_trees; its vertex slot base is (r / n_trees) * sum_v + v0
+    const RelaxTreeView* trees;
+    const double* orig;                // per template vertex: original length (NaN: absent)
+    const int16_t* chain;              // '(' run before a leaf
+    const uint8_t* vflags;             // bit0: leaf, bit1: a ',' follows (not the last child), bit2: print the name
+    const int32_t* name_off;           // offset/len pairs into blob
+    const char* blob;
+    MathTables T;
+    double* rates; double* relaxed;    // [total vertex slots]
+    int32_t* attempts; int32_t* status;// [n]
+    uint32_t* mt_state;
+    // emission
+    int do_meta; int has_outfile;
+    int args_pre_off, args_pre_len, args_post_off, args_post_len, seed_mode; long long seed_base;
+    int model_tail_off, model_tail_len;            // "Model:\t...\nModel parameters:\n..." (constant per run)
+    uint16_t* plen_tree; uint16_t* plen_info;      // cached piece lengths: [vertex slots], [3 * vertex slots + 8 * n]
+    unsigned long long* sizes;                     // [2][n]
+    const unsigned long long* offsets;             // [2][n+1]
+    char* out[2];
+};
+
+}  // namespace sgp

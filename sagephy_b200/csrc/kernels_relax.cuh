@@ -1,0 +1,206 @@
+// K5: BranchRelaxer — per-branch rate sampling (IID models), retry until every rate lies in [min, max], length x rate, and
+// emission of the relaxed Newick tree + .info report.
+//
+// Reference behaviour: apps/SaGePhy/BranchRelaxer.java:94-101 (retry loop), :148-158 (isOK), :166-173 (lengths x rates),
+// :186-197 + io/NewickTreeWriter.java:100-113 (tree text), :118-135 (.info text); rate models in apps/SaGePhy/IID*RateModel.java
+// on top of math/{LogNormal,Normal,Gamma,Uniform,Exponential}Distribution.java.
+//
+//   k_relax_rates<REPLAY> one thread per replicate draws the rate vector in vertex-id order from the replicate's stream
+//                         (MT19937 replay: exactly the reference's draw order; Philox: block (vertex, attempt, replicate)).
+//   k_relax_apply         Philox fast path: one thread per (replicate, vertex) evaluates attempt 0 in parallel — 8 B read +
+//                         16 B written per branch, coalesced; replicates with a rate outside [min, max] are flagged and
+//                         finished by k_relax_rates starting from attempt 1.
+//   k_relax_emit<WRITE>   same piece machinery as the tree generators (kernels_emit.cuh).
+#pragma once
+#include "kernels_emit.cuh"
+#include "jmath_ext.cuh"
+#include "rng.cuh"
+
+namespace sgp {
+
+// java.util.Random.nextGaussian on an MT stream (polar method; the second deviate is cached)
+struct GaussCache { bool have; double next; };
+__device__ inline double mt_next_gaussian(MtStream& mt, GaussCache& gc) {
+    if (gc.have) { gc.have = false; return gc.next; }
+    double v1, v2, s;
+    do {
+        v1 = XSUB(XMUL(2.0, mt.next_double()), 1.0); v2 = XSUB(XMUL(2.0, mt.next_double()), 1.0);
+        s = XADD(XMUL(v1, v1), XMUL(v2, v2));
+    } while (s >= 1 || s == 0);
+    const double mult = jsqrt(XDIV(XMUL(-2.0, jlog(s)), s));
+    gc.next = XMUL(v2, mult); gc.have = true;
+    return XMUL(v1, mult);
+}
+
+// rate from the reference's quantile transforms; *err set when the reference would throw (gamma outside [2e-6, 0.999998])
+__device__ inline double rate_from_uniform(const RelaxArgs& a, double u, int* err) {
+    switch (a.model) {
+        case RM_EXPONENTIAL: return XDIV(-jlog(XSUB(1.0, u)), a.pa);
+        case RM_GAMMA: return XDIV(XMUL(jchi2_quantile(u, XMUL(2.0, a.pa), err), a.pb), 2.0);
+        case RM_LOGNORMAL: return jexp(XADD(XMUL(jnormal_quantile(u), a.sigma), a.pa));
+        default: return a.pa;
+    }
+}
+
+template <bool REPLAY>
+__device__ inline double draw_rate(const RelaxArgs& a, MtStream& mt, GaussCache& gc, unsigned long long gid, uint32_t attempt, int x, int* err) {
+    if (a.model == RM_CONSTANT) return a.pa;
+    if (REPLAY) {
+        switch (a.model) {
+            case RM_NORMAL: return XADD(XMUL(mt_next_gaussian(mt, gc), a.sigma), a.pa);
+            case RM_UNIFORM: { const double d = mt.next_double(); const bool up = mt.next(1) != 0; const double w = XSUB(a.pb, a.pa);
+                               return up ? XADD(XMUL(w, d), a.pa) : XADD(XMUL(w, XSUB(1.0, d)), a.pa); }
+            case RM_SAMPLES: return a.samples[mt.next_int(a.n_samples)];
+            default: return rate_from_uniform(a, mt.next_double(), err);
+        }
+    }
+    // Philox: vertex x of attempt `attempt` owns the counter blocks (x, attempt | trial << 24, replicate)
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    switch (a.model) {
+        case RM_NORMAL: {
+            for (uint32_t trial = 0;; ++trial) {
+                const U4 w = philox4x32_10((uint32_t)x, attempt ^ (trial << 20) ^ 0x80000000u, (uint32_t)gid, (uint32_t)(gid >> 32), k0, k1);
+                const double v1 = 2.0 * u01_from_words(w.x, w.y) - 1.0, v2 = 2.0 * u01_from_words(w.z, w.w) - 1.0, s = v1 * v1 + v2 * v2;
+                if (s < 1 && s != 0) return v1 * sqrt(-2.0 * log(s) / s) * a.sigma + a.pa;
+            }
+        }
+        case RM_UNIFORM: { const U4 w = philox4x32_10((uint32_t)x, attempt, (uint32_t)gid, (uint32_t)(gid >> 32), k0, k1);
+                           const double d = u01_from_words(w.x, w.y); return (w.z & 1u) ? (a.pb - a.pa) * d + a.pa : (a.pb - a.pa) * (1.0 - d) + a.pa; }
+        case RM_SAMPLES: { PhiloxStream ph; ph.init(a.seed, gid, attempt); ph.block = (uint32_t)x << 8; return a.samples[ph.next_int(a.n_samples)]; }
+        default: { const U4 w = philox4x32_10((uint32_t)x, attempt, (uint32_t)gid, (uint32_t)(gid >> 32), k0, k1);
+                   return rate_from_uniform(a, u01_from_words(w.x, w.y), err); }
+    }
+}
+
+__device__ __forceinline__ long long relax_slot(const RelaxArgs& a, long long r, const RelaxTreeView** tv) {
+    const long long t = r % a.n_trees; *tv = &a.trees[t];
+    return (r / a.n_trees) * a.sum_v + a.trees[t].v0;
+}
+
+// status[r] on entry: 0 = run from attempt `first_attempt`; anything else = skip. REP_* codes on exit.
+template <bool REPLAY>
+__global__ void __launch_bounds__(128) k_relax_rates(RelaxArgs a, int first_attempt, int only_flagged) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n) return;
+    if (only_flagged && a.status[r] != REP_PENDING) return;
+    const RelaxTreeView* tv; const long long base = relax_slot(a, r, &tv);
+    const int nV = tv->nV; const unsigned long long gid = (unsigned long long)(a.rep_base + r);
+    MtStream mt; GaussCache gc{false, 0.0};
+    if (REPLAY) { const int worker = blockIdx.x * blockDim.x + threadIdx.x; mt.mt = a.mt_state + (size_t)(worker >> 5) * 624 * 32 + (worker & 31); mt.stride = 32;
+                  uint32_t key[4]; seed_words_i64((long long)a.seed + (long long)gid, key); mt.seed(key); }
+    int attempts = first_attempt; int status = REP_PENDING;
+    for (;;) {
+        if (attempts > a.max_attempts) { status = REP_MAX_ATTEMPTS; break; }
+        bool ok = true; int err = 0;
+        for (int x = 0; x < nV; ++x) {
+            const double rate = draw_rate<REPLAY>(a, mt, gc, gid, (uint32_t)attempts, x, &err);
+            a.rates[base + x] = rate;
+            if (x != tv->ignore && (rate < a.min_rate || rate > a.max_rate)) ok = false;      // isOK: rates are NOT short-circuited in the draw
+        }
+        ++attempts;
+        if (err) { status = REP_MODEL_ERROR; break; }       // the reference aborts with an exception (ChiSquared.java:24)
+        if (ok) { status = REP_OK; break; }
+    }
+    a.attempts[r] = attempts; a.status[r] = status;
+    if (status == REP_OK) for (int x = 0; x < nV; ++x) a.relaxed[base + x] = XMUL(a.orig[tv->v0 + x], a.rates[base + x]);
+}
+
+// Philox fast path, attempt 0, one thread per (replicate, vertex).
+__global__ void __launch_bounds__(256) k_relax_apply(RelaxArgs a, long long total_slots) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_slots) return;
+    // slot -> (replicate, vertex): slots are grouped by rounds of n_trees replicates
+    const long long round = g / a.sum_v; const long long in_round = g - round * a.sum_v;
+    int lo = 0, hi = a.n_trees - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (a.trees[mid].v0 <= in_round) lo = mid; else hi = mid - 1; }
+    const long long r = round * a.n_trees + lo;
+    if (r >= a.n) return;
+    const RelaxTreeView& tv = a.trees[lo];
+    const int x = (int)(in_round - tv.v0);
+    MtStream mt; GaussCache gc{false, 0.0}; int err = 0;
+    const double rate = draw_rate<false>(a, mt, gc, (unsigned long long)(a.rep_base + r), 0u, x, &err);
+    a.rates[g] = rate;
+    a.relaxed[g] = XMUL(a.orig[tv.v0 + x], rate);
+    if (err) atomicMax(&a.status[r], (int)REP_MODEL_ERROR);
+    else if (x != tv.ignore && (rate < a.min_rate || rate > a.max_rate)) atomicMax(&a.status[r], (int)REP_PENDING);
+}
+__global__ void k_relax_finish_apply(RelaxArgs a) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n) return;
+    if (a.status[r] == 0) { a.status[r] = REP_OK; a.attempts[r] = 1; }       // status was zero-initialised == "no violation seen"
+}
+
+// ---- emission -------------------------------------------------------------------------------------------------------------------
+template <class Sink> __device__ void put_relax_vertex(Sink& s, const RelaxArgs& a, const RelaxTreeView& tv, long long base, int x) {
+    const long long t = tv.v0 + x; const uint8_t f = a.vflags[t];
+    if (f & 1) { for (int i = 0; i < a.chain[t]; ++i) s.put('('); } else s.put(')');
+    if (f & 4) put_blob(s, a.blob, a.name_off[2 * t], a.name_off[2 * t + 1]);
+    const double len = a.relaxed[base + x];
+    if (len == len) { s.put(':'); put_double(s, a.T, len); }
+    if (a.do_meta) {
+        put_str(s, "[ID="); put_i64(s, x); put_str(s, " ORIGBL="); put_double(s, a.T, a.orig[t]); put_str(s, " RATE="); put_double(s, a.T, a.rates[base + x]); s.put(']');
+    }
+    if (f & 2) s.put(',');
+    if (x == tv.root) { s.put(';'); s.put('\n'); }
+}
+// info pieces: 0 header, 1 args, 2 attempts, then 3 arrays x nV elements, then the constant model tail
+template <class Sink> __device__ void put_relax_info(Sink& s, const RelaxArgs& a, const RelaxTreeView& tv, long long base, long long gid, int attempts, int k) {
+    const int nV = tv.nV;
+    if (k == 0) { put_str(s, "# BRANCHLENGTHRELAXER\n"); return; }
+    if (k == 1) {
+        put_str(s, "Arguments:\t"); put_blob(s, a.blob, a.args_pre_off, a.args_pre_len);
+        if (a.seed_mode) { put_i64(s, a.seed_base + gid); put_blob(s, a.blob, a.args_post_off, a.args_post_len); }
+        s.put('\n'); return;
+    }
+    if (k == 2) { put_str(s, "Attempts:\t"); put_i64(s, attempts); s.put('\n'); return; }
+    k -= 3;
+    if (k < 3 * nV) {
+        const int arr = k / nV, x = k - arr * nV;
+        if (x == 0) put_str(s, arr == 0 ? "Original lengths:\t[" : arr == 1 ? "Rates:\t[" : "Relaxed lengths:\t[");
+        else { s.put(','); s.put(' '); }
+        put_double(s, a.T, arr == 0 ? a.orig[tv.v0 + x] : arr == 1 ? a.rates[base + x] : a.relaxed[base + x]);
+        if (x == nV - 1) { s.put(']'); s.put('\n'); }
+        return;
+    }
+    put_blob(s, a.blob, a.model_tail_off, a.model_tail_len);
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(kEmitWarps * 32, 4) k_relax_emit(RelaxArgs a) {
+    __shared__ __align__(16) char s_stage[kEmitWarps][kStageBytes];
+    const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= a.n) return;
+    char* stage = s_stage[threadIdx.x >> 5];
+    const RelaxTreeView* tvp; const long long base = relax_slot(a, r, &tvp); const RelaxTreeView tv = *tvp;
+    const long long gid = a.rep_base + r;
+    const bool ok = a.status[r] == REP_OK;
+    auto no_store = [](int, unsigned) {}; auto no_load = [](int) { return 0u; };
+    // stream 0: relaxed tree
+    {
+        char* out = WRITE ? a.out[0] + a.offsets[r] : nullptr;
+        uint16_t* pl = a.plen_tree + base;
+        unsigned long long bytes = 0;
+        if (ok) {
+            auto pc = [&](auto& s, int x) { put_relax_vertex(s, a, tv, base, x); };
+            if (WRITE) bytes = emit_pieces<true>(tv.nV, out, stage, pc, [&](int i) { return (unsigned)pl[i]; }, no_store);
+            else bytes = emit_pieces<false>(tv.nV, out, stage, pc, no_load, [&](int i, unsigned v) { pl[i] = (uint16_t)v; });
+        }
+        if (!WRITE && lane == 0) a.sizes[r] = bytes;
+    }
+    // stream 1: .info (only with -o)
+    if (a.has_outfile) {
+        char* out = WRITE ? a.out[1] + a.offsets[(size_t)(a.n + 1) + r] : nullptr;
+        uint16_t* pl = a.plen_info + 3 * base + 8 * r;
+        unsigned long long bytes = 0;
+        if (ok) {
+            const int np = 3 + 3 * tv.nV + 1; const int att = a.attempts[r];
+            auto pc = [&](auto& s, int k) { put_relax_info(s, a, tv, base, gid, att, k); };
+            if (WRITE) bytes = emit_pieces<true>(np, out, stage, pc, [&](int i) { return (unsigned)pl[i]; }, no_store);
+            else bytes = emit_pieces<false>(np, out, stage, pc, no_load, [&](int i, unsigned v) { pl[i] = (uint16_t)v; });
+        }
+        if (!WRITE && lane == 0) a.sizes[(size_t)a.n + r] = bytes;
+    }
+}
+
+}  // namespace sgp

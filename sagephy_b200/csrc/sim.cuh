@@ -10,6 +10,7 @@
 #pragma once
 #include "kernels_args.cuh"
 #include "rng.cuh"
+#include "jmath_ext.cuh"
 
 namespace sgp {
 
@@ -60,8 +61,8 @@ __device__ __forceinline__ DD dd_mul_d(DD a, double b) {
 }
 __device__ __forceinline__ bool dd_gt(DD a, DD b) { return a.hi > b.hi || (a.hi == b.hi && a.lo > b.lo); }
 
-// Math.pow(Math.E, y) stand-in (CUDA pow; see DESIGN.md "numerics" for the tolerance argument).
-__device__ __forceinline__ double pow_e(double y) { return pow(2.718281828459045, y); }
+// Math.pow(Math.E, y) through the fdlibm pow restatement (bit-identical to the oracle's)
+static __device__ __noinline__ double pow_e(double y) { return jpow(2.718281828459045, y); }
 
 // Epoch.sampleArc with include == true. marks[x] == mark_gen flags an "empty" arc. Returns -5 if no candidate.
 template <class RNG>

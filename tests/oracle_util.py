@@ -35,6 +35,9 @@ def oracle():
         L.oracle_double_to_string.argtypes = [C.c_double, C.c_char_p, C.c_int]; L.oracle_double_to_string.restype = C.c_int
         for f in ("oracle_log", "oracle_log10", "oracle_exp"):
             getattr(L, f).argtypes = [C.c_double]; getattr(L, f).restype = C.c_double
+        L.oracle_pow.argtypes = [C.c_double, C.c_double]; L.oracle_pow.restype = C.c_double
+        L.oracle_normal_quantile.argtypes = [C.c_double]; L.oracle_normal_quantile.restype = C.c_double
+        L.oracle_gamma_quantile.argtypes = [C.c_double, C.c_double, C.c_double]; L.oracle_gamma_quantile.restype = C.c_double
         L.oracle_round_sig.argtypes = [C.c_double, C.c_int]; L.oracle_round_sig.restype = C.c_double
         _lib = L
     return _lib

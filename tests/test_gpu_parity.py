@@ -70,6 +70,22 @@ def test_device_math_is_bit_exact_with_oracle(ctx):
     assert (ctx.math(3, z).view(np.uint64) == np.array([L.oracle_round_sig(float(v), 8) for v in z]).view(np.uint64)).all()
 
 
+def test_device_pow_and_quantiles_are_bit_exact_with_oracle(ctx):
+    L = oracle()
+    rng = np.random.default_rng(5)
+    x = rng.random(20000) * 10 + 1e-3
+    assert (ctx.math(5, x).view(np.uint64) == np.array([L.oracle_pow(float(v), 0.37) for v in x]).view(np.uint64)).all()
+    y = (rng.random(20000) - 0.7) * 30
+    assert (ctx.math(8, y).view(np.uint64) == np.array([L.oracle_pow(2.718281828459045, float(v)) for v in y]).view(np.uint64)).all()
+    p = np.concatenate([rng.random(20000), rng.random(3000) * 0.03, 1 - rng.random(3000) * 0.03])
+    assert (ctx.math(4, p).view(np.uint64) == np.array([L.oracle_normal_quantile(float(v)) for v in p]).view(np.uint64)).all()
+    q = 2e-6 + rng.random(20000) * (0.999998 - 2e-6)
+    for fn, k in ((6, 4.0), (7, 0.25)):
+        got = ctx.math(fn, q)
+        want = np.array([L.oracle_gamma_quantile(float(v), k / 2, 2.0) for v in q])
+        assert (got.view(np.uint64) == want.view(np.uint64)).all()
+
+
 @pytest.mark.parametrize("seed", [0, 1, 20260101, 2 ** 62, -1, -300])
 def test_device_mt19937_stream(ctx, seed):
     assert (ctx.mt_words(seed, 3000) == oracle_mt_words(seed, 3000)).all()
@@ -224,3 +240,85 @@ def test_emitted_trees_are_well_formed_at_scale(ctx):
         assert "No. of vertices:\t199\n" in info and "No. of extant leaves:\t100\n" in info
     s = b.summary()
     assert s.n_ok == n and s.leaf_hist[100] == n and s.out_bytes[1] == len(pruned)
+
+
+# ---- BranchRelaxer ---------------------------------------------------------------------------------------------------------------
+RELAX_TREE = "((A:0.5,B:0.5)X:0.3,(C:0.2,D:0.2,E:0.2)Y:0.6)R:0.1;"          # multifurcating, named interior vertices, stem
+RELAX_TREE_NOSTEM = "(((a:0.1,b:0.1):0.5,(c:0.3,d:0.3):0.3):0.4,((e:0.2,f:0.2):0.6,(g:0.5,h:0.5):0.3):0.2);"
+RELAX_CASES = [
+    ["-s", "1", "-x", "-innms", "-o", "rel.tree", RELAX_TREE, "IIDLogNormal", "0", "0.25"],
+    ["-s", "2", "-o", "rel.tree", RELAX_TREE_NOSTEM, "IIDGamma", "2", "0.5"],
+    ["-s", "3", "-x", "-o", "rel.tree", RELAX_TREE, "IIDGamma", "0.1", "3.0"],
+    ["-s", "4", "-o", "rel.tree", RELAX_TREE_NOSTEM, "IIDNormal", "1.0", "0.09"],          # negative rates force retries
+    ["-s", "5", "-x", "-o", "rel.tree", RELAX_TREE, "IIDUniform", "0.5", "1.5"],
+    ["-s", "6", "-o", "rel.tree", RELAX_TREE, "IIDExponential", "2.0"],
+    ["-s", "7", "-x", "-o", "rel.tree", RELAX_TREE_NOSTEM, "Constant", "1.7"],
+    ["-s", "8", "-min", "0.8", "-max", "1.3", "-a", "50", "-o", "rel.tree", RELAX_TREE, "IIDLogNormal", "0", "0.04"],   # tight window: many attempts, some failures
+    ["-s", "9", RELAX_TREE_NOSTEM, "iidlognormal", "0.1", "0.5"],                              # stdout, case-insensitive model name
+]
+
+
+@pytest.mark.parametrize("args", RELAX_CASES, ids=[" ".join(a[2:]).replace(RELAX_TREE, "T1").replace(RELAX_TREE_NOSTEM, "T2") for a in RELAX_CASES])
+def test_branch_relaxer_replay_is_byte_exact(ctx, args):
+    n = 16
+    seed0 = int(args[1])
+    b = ctx.run("BranchRelaxer", args, n=n, rng=sg.RNG_MT_REPLAY)
+    has_out = "-o" in args
+    stdout = ""
+    for i in range(n):
+        want = oracle_run("BranchRelaxer", with_seed(args, seed0 + i))
+        if want["status"] == 1:
+            assert b.rep_status[i] == 1
+            continue
+        assert b.rep_status[i] == 0 and b.attempts[i] == want["attempts"], (i, b.rep_status[i], b.attempts[i], want["attempts"])
+        if has_out:
+            got = b.files(i)
+            assert got[""] == want["files"]["rel.tree"], (got[""], want["files"]["rel.tree"])
+            assert got[".info"] == want["files"]["rel.tree.info"]
+        else:
+            stdout += want["stdout"]
+    if not has_out:
+        assert b.stdout == stdout
+
+
+def test_branch_relaxer_samples_from_file_and_multi_tree(ctx, tmp_path):
+    f = tmp_path / "rates.txt"
+    f.write_text("0.5\n1.0\n1.5\n2.0\n0.25\n")
+    args = ["-s", "12", "-x", "-o", "rel.tree", RELAX_TREE, "IIDSamplesFromFile", str(f)]
+    b = ctx.run("BranchRelaxer", args, n=8, rng=sg.RNG_MT_REPLAY)
+    for i in range(8):
+        want = oracle_run("BranchRelaxer", with_seed(args, 12 + i))["files"]
+        assert b.files(i)[""] == want["rel.tree"] and b.files(i)[".info"] == want["rel.tree.info"]
+    # multi-tree input: replicate i relaxes tree i % T with seed + i
+    trees = [RELAX_TREE, RELAX_TREE_NOSTEM, "(x:1.0,y:2.0,z:3.0):0.5;"]
+    m = tmp_path / "trees.nwk"
+    m.write_text("\n".join(trees) + "\n")
+    b = ctx.run("BranchRelaxer", ["-s", "40", "-x", str(m), "IIDLogNormal", "0", "0.25"], n=9, rng=sg.RNG_MT_REPLAY, flags=sg.FLAG_MULTI_TREE_INPUT)
+    want = "".join(oracle_run("BranchRelaxer", ["-s", str(40 + i), "-x", trees[i % 3], "IIDLogNormal", "0", "0.25"])["stdout"] for i in range(9))
+    assert b.stdout == want
+
+
+def test_branch_relaxer_philox_matches_reference_distributions(ctx):
+    n = 20000
+    nv = 15      # vertices of RELAX_TREE_NOSTEM
+    for model, extra, fn in (("IIDLogNormal", ["0", "0.25"], lambda u: None), ("IIDGamma", ["2", "0.5"], None), ("IIDNormal", ["1.0", "0.01"], None),
+                             ("IIDUniform", ["0.5", "1.5"], None), ("IIDExponential", ["2.0"], None)):
+        args = ["-s", "99", RELAX_TREE_NOSTEM, model] + extra
+        b = ctx.run("BranchRelaxer", args, n=n, rng=sg.RNG_PHILOX)
+        st = b.rep_status
+        if model == "IIDGamma":
+            # the reference aborts a run whose uniform leaves [2e-6, 0.999998] (ChiSquared.java:24): ~4e-6 per branch
+            assert set(np.unique(st)) <= {0, 4} and (st == 4).sum() < 12
+        else:
+            assert (st == 0).all()
+        rates = b.values(0).reshape(n, nv)[st == 0]
+        r = ctx.run("BranchRelaxer", args, n=4000, rng=sg.RNG_MT_REPLAY)          # reference stream (MT) through the same quantile code
+        ref = r.values(0).reshape(4000, nv)
+        assert ks_ok(rates[:, 3], ref[:, 3]) and ks_ok(rates[:, 10], ref[:, 7])
+        rel, orig = b.values(1).reshape(n, nv)[st == 0], np.array([0.1, 0.1, 0.5, 0.3, 0.3, 0.3, 0.4, 0.2, 0.2, 0.6, 0.5, 0.5, 0.3, 0.2, 0.0])
+        assert np.array_equal(rel, rates * orig)
+    # closed form for the gamma model: mean k*theta, variance k*theta^2
+    b = ctx.run("BranchRelaxer", ["-s", "5", RELAX_TREE_NOSTEM, "IIDGamma", "2", "0.5"], n=n, rng=sg.RNG_PHILOX)
+    g = b.values(0).reshape(n, nv)[b.rep_status == 0].ravel()
+    assert abs(g.mean() - 1.0) < 0.01 and abs(g.var() - 0.5) < 0.02
+    assert stats.kstest(g[::7], "gamma", args=(2, 0, 0.5)).pvalue > 0.001
