@@ -119,6 +119,7 @@ def main():
     import torch
     import torch.distributed as dist
     import sagephy_b200 as sg
+    from sagephy_b200.sharding import allreduce_summary
 
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -141,10 +142,8 @@ def main():
         return ctx.run("HostTreeGen", C2_ARGS, n=n_rep, rng=sg.RNG_PHILOX, offset=off, keep_on_device=keep)
 
     def merge(summary):
-        v = torch.from_numpy(summary.as_vector()).cuda()
-        if world > 1:
-            dist.all_reduce(v)          # NCCL: the only collective on the path (summary histograms)
-        return sg.Summary.from_vector(v.cpu().numpy())
+        # NCCL all-reduce(sum) of the int64 summary vector: the only collective on the path
+        return sg.Summary.from_vector(allreduce_summary(summary.as_vector(), device="cuda"))
 
     # roofline denominators measured live (FP64 / INT issue rates)
     peaks = ctx.issue_peaks()
