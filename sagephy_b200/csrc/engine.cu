@@ -258,9 +258,9 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         launch_bd_find(a, blocks, st); ++tm.launches;
         CK(cudaGetLastError());
     } else {
-        int cap = 1024; while (cap < 4 * cfg.P.max_leaves && cap < (1 << 20)) cap *= 2;
-        if (cfg.host.nLeaves > 64) while (cap < 8 * cfg.host.nLeaves) cap *= 2;
-        long long workers = std::min<long long>((long long)sm * 256, (n + 127) / 128 * 128);
+        // node capacity of a worker's scratch pool: typical trees fit; the rare larger ones are re-run with 8x the capacity
+        int cap = 1024; while (cap < 6 * cfg.host.nLeaves && cap < (1 << 16)) cap *= 2;
+        long long workers = std::min<long long>((long long)sm * 1024, (n + 127) / 128 * 128);
         DevBuf<long long> redo, keep; DevBuf<unsigned long long> redo_count;
         const long long* rep_ids = nullptr; long long todo = n;
         for (int round = 0;; ++round) {
@@ -368,6 +368,10 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     }
     add("# GUEST-TO-HOST MAP\nHost tree:\t" + cfg.host.header + "\nGuest vertex name:\tGuest vertex ID:\tGuest vertex type:\tGuest vertex time:\tHost vertex/arc ID:\tHost epoch ID:\n",
         e.g2h_head_off, e.g2h_head_len);
+    {
+        const std::string head = blob.substr(e.g2h_head_off, e.g2h_head_len);
+        for (int k = 0; k < 16; ++k) { while ((int)(blob.size() % 16) != k) blob.push_back(' '); e.g2h_head_off16[k] = (int)blob.size(); blob += head; }
+    }
     { int o, l; add(cfg.host.has_tree_name ? cfg.host.tree_name : std::string("null"), o, l); gname.push_back(o); gname.push_back(l); }
     for (int v = 0; v < cfg.host.nV; ++v) { int o, l; add(cfg.host.left[v] < 0 ? cfg.host.leaf_name[v] : std::string("null"), o, l); leafname.push_back(o); leafname.push_back(l); }
     DevBuf<char> d_blob; { std::vector<char> b(blob.begin(), blob.end()); b.push_back(0); d_blob.upload(b); }

@@ -95,10 +95,10 @@ template <class Sink> __device__ void put_kv_dbl(Sink& s, const EmitArgs& a, con
 
 __device__ __forceinline__ int info_lines(const EmitArgs& a, bool pruned) { return a.app == 0 ? (pruned ? 8 : 10) : 18; }
 
-// line `ln` of an .info file
+// line `ln` of an .info file. Lanes format different lines in the same trip, so the line-specific part only SELECTS data
+// (key string, integer or double operand); the expensive work (round8, shortest-digit conversion) runs on one shared path.
 template <bool PRUNED, class Sink> __device__ void put_info_line(Sink& s, const EmitArgs& a, const RepInfo& inf, long long gid, int ln) {
     const int32_t* c = PRUNED ? inf.cnt_p : inf.cnt_u;
-    const int nv = PRUNED ? inf.n_p : inf.n_u;
     if (ln == 0) { put_str(s, a.app == 0 ? "# HOSTTREEGEN\n" : a.app == 1 ? "# GUESTTREEGEN\n" : "# DOMAINTREEGEN\n"); return; }
     if (ln == 1) {
         put_str(s, "Arguments:\t");
@@ -106,36 +106,42 @@ template <bool PRUNED, class Sink> __device__ void put_info_line(Sink& s, const 
         if (a.seed_mode) { put_i64(s, a.seed_base + gid); put_blob(s, a.blob, a.args_post_off, a.args_post_len); }
         s.put('\n'); return;
     }
-    if (ln == 2) { put_kv_int(s, "Attempts:\t", inf.attempts); return; }
-    if (ln == 3) { put_kv_int(s, "No. of vertices:\t", nv); return; }
-    if (ln == 4) { put_kv_int(s, "No. of extant leaves:\t", c[EV_LEAF] + c[EV_UNSAMPLED_LEAF]); return; }
-    const double total = round_sig(a.T, PRUNED ? inf.total_p : inf.total_u, 8);
-    if (a.app == 0) {
+    const char* key = ""; bool is_double = false; long long iv = 0; double num = 0.0; bool ratio = false;
+    if (ln == 2) { key = "Attempts:\t"; iv = inf.attempts; }
+    else if (ln == 3) { key = "No. of vertices:\t"; iv = PRUNED ? inf.n_p : inf.n_u; }
+    else if (ln == 4) { key = "No. of extant leaves:\t"; iv = c[EV_LEAF] + c[EV_UNSAMPLED_LEAF]; }
+    else if (a.app == 0) {
         const int births = c[EV_DUPLICATION] + c[EV_SPECIATION], deaths = c[EV_LOSS];
         switch (ln) {
-            case 5: put_kv_int(s, "No. of births:\t", births); break;
-            case 6: put_kv_int(s, "No. of deaths:\t", deaths); break;
-            case 7: put_kv_dbl(s, a, "Total branch time:\t", total); break;
-            case 8: put_kv_dbl(s, a, "Birth ML estimate:\t", round_sig(a.T, XDIV((double)births, total), 8)); break;
-            case 9: put_kv_dbl(s, a, "Death ML estimate:\t", round_sig(a.T, XDIV((double)deaths, total), 8)); break;
+            case 5: key = "No. of births:\t"; iv = births; break;
+            case 6: key = "No. of deaths:\t"; iv = deaths; break;
+            case 7: key = "Total branch time:\t"; is_double = true; num = PRUNED ? inf.total_p : inf.total_u; break;
+            case 8: key = "Birth ML estimate:\t"; is_double = true; ratio = true; num = (double)births; break;
+            default: key = "Death ML estimate:\t"; is_double = true; ratio = true; num = (double)deaths; break;
         }
-        return;
+    } else {
+        switch (ln) {
+            case 5: key = "No. of speciations:\t"; iv = c[EV_SPECIATION]; break;
+            case 6: key = "No. of duplications:\t"; iv = c[EV_DUPLICATION]; break;
+            case 7: key = "No. of losses:\t"; iv = c[EV_LOSS]; break;
+            case 8: key = "No. of replacing losses:\t"; iv = c[EV_REPLACING_LOSS]; break;
+            case 9: key = "No. of additive transfers:\t"; iv = c[EV_ADDITIVE_TRANSFER]; break;
+            case 10: key = "No. of replacing transfers:\t"; iv = c[EV_REPLACING_TRANSFER]; break;
+            case 11: key = "Total branch time:\t"; is_double = true; num = PRUNED ? inf.total_p : inf.total_u; break;
+            case 12: key = "Total branch time beneath host stem:\t"; is_double = true; num = PRUNED ? inf.beneath_p : inf.beneath_u; break;
+            case 13: key = "Duplication ML estimate:\t"; is_double = true; ratio = true; num = (double)c[EV_DUPLICATION]; break;
+            case 14: key = "Loss ML estimate:\t"; is_double = true; ratio = true; num = (double)c[EV_LOSS]; break;
+            case 15: key = "Replacing Loss ML estimate:\t"; is_double = true; ratio = true; num = (double)c[EV_REPLACING_LOSS]; break;
+            case 16: key = "Additive Transfer ML estimate:\t"; is_double = true; ratio = true; num = (double)c[EV_ADDITIVE_TRANSFER]; break;
+            default: key = "Replacing Transfer ML estimate:\t"; is_double = true; ratio = true; num = (double)c[EV_REPLACING_TRANSFER]; break;
+        }
     }
-    switch (ln) {
-        case 5: put_kv_int(s, "No. of speciations:\t", c[EV_SPECIATION]); break;
-        case 6: put_kv_int(s, "No. of duplications:\t", c[EV_DUPLICATION]); break;
-        case 7: put_kv_int(s, "No. of losses:\t", c[EV_LOSS]); break;
-        case 8: put_kv_int(s, "No. of replacing losses:\t", c[EV_REPLACING_LOSS]); break;
-        case 9: put_kv_int(s, "No. of additive transfers:\t", c[EV_ADDITIVE_TRANSFER]); break;
-        case 10: put_kv_int(s, "No. of replacing transfers:\t", c[EV_REPLACING_TRANSFER]); break;
-        case 11: put_kv_dbl(s, a, "Total branch time:\t", total); break;
-        case 12: put_kv_dbl(s, a, "Total branch time beneath host stem:\t", round_sig(a.T, PRUNED ? inf.beneath_p : inf.beneath_u, 8)); break;
-        case 13: put_kv_dbl(s, a, "Duplication ML estimate:\t", round_sig(a.T, XDIV((double)c[EV_DUPLICATION], total), 8)); break;
-        case 14: put_kv_dbl(s, a, "Loss ML estimate:\t", round_sig(a.T, XDIV((double)c[EV_LOSS], total), 8)); break;
-        case 15: put_kv_dbl(s, a, "Replacing Loss ML estimate:\t", round_sig(a.T, XDIV((double)c[EV_REPLACING_LOSS], total), 8)); break;
-        case 16: put_kv_dbl(s, a, "Additive Transfer ML estimate:\t", round_sig(a.T, XDIV((double)c[EV_ADDITIVE_TRANSFER], total), 8)); break;
-        case 17: put_kv_dbl(s, a, "Replacing Transfer ML estimate:\t", round_sig(a.T, XDIV((double)c[EV_REPLACING_TRANSFER], total), 8)); break;
-    }
+    put_str(s, key);
+    if (is_double) {
+        if (ratio) num = XDIV(num, round_sig(a.T, PRUNED ? inf.total_p : inf.total_u, 8));
+        put_double(s, a.T, round_sig(a.T, num, 8));
+    } else put_i64(s, iv);
+    s.put('\n');
 }
 
 __device__ __forceinline__ const char* event_enum_name(int e) {
@@ -279,15 +285,38 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) k_emit(EmitArgs a) {
             }
             if constexpr (st == ST_UNPRUNED_INFO || st == ST_PRUNED_INFO) {
                 constexpr bool pr = st == ST_PRUNED_INFO;
-                auto pc = [&](auto& s, int ln) { if (pr) put_info_line<true>(s, a, inf, gid, ln); else put_info_line<false>(s, a, inf, gid, ln); };
-                // info lines are cheap: their lengths are recomputed in the write pass instead of being cached
-                auto ld_info = [&](int ln) { CountSink c; if (pr) put_info_line<true>(c, a, inf, gid, ln); else put_info_line<false>(c, a, inf, gid, ln); return (unsigned)c.n; };
-                if (WRITE) bytes = emit_pieces<true>(info_lines(a, pr), base, stage, pc, ld_info, no_store);
-                else bytes = emit_pieces<false>(info_lines(a, pr), base, stage, pc, no_load, no_store);
+                // lines 0-1 ("# APP" and "Arguments: [...]", which may embed a whole Newick host tree): warp-cooperative copy
+                const char* h0 = a.app == 0 ? "# HOSTTREEGEN\nArguments:\t" : a.app == 1 ? "# GUESTTREEGEN\nArguments:\t" : "# DOMAINTREEGEN\nArguments:\t";
+                const int h0len = a.app == 0 ? 25 : a.app == 1 ? 26 : 27;
+                const long long seedv = a.seed_base + gid;
+                const int seedlen = a.seed_mode ? (seedv < 0 ? 1 : 0) + dec_len_u64((uint64_t)(seedv < 0 ? -seedv : seedv)) : 0;
+                unsigned long long o = 0;
+                if (WRITE) {
+                    for (int i = lane; i < h0len; i += 32) base[i] = h0[i];
+                    for (int i = lane; i < a.args_pre_len; i += 32) base[h0len + i] = a.blob[a.args_pre_off + i];
+                }
+                o = (unsigned long long)h0len + a.args_pre_len;
+                if (a.seed_mode) {
+                    if (WRITE) {
+                        if (lane == 0) { MemSink m{base + o}; put_i64(m, seedv); }
+                        for (int i = lane; i < a.args_post_len; i += 32) base[o + seedlen + i] = a.blob[a.args_post_off + i];
+                    }
+                    o += (unsigned long long)seedlen + a.args_post_len;
+                }
+                if (WRITE && lane == 0) base[o] = '\n';
+                o += 1;
+                auto pc = [&](auto& s, int ln) { if (pr) put_info_line<true>(s, a, inf, gid, ln + 2); else put_info_line<false>(s, a, inf, gid, ln + 2); };
+                // the remaining lines are cheap: their lengths are recomputed in the write pass instead of being cached
+                auto ld_info = [&](int ln) { CountSink c; if (pr) put_info_line<true>(c, a, inf, gid, ln + 2); else put_info_line<false>(c, a, inf, gid, ln + 2); return (unsigned)c.n; };
+                if (WRITE) bytes = o + emit_pieces<true>(info_lines(a, pr) - 2, base + o, stage, pc, ld_info, no_store);
+                else bytes = o + emit_pieces<false>(info_lines(a, pr) - 2, base, stage, pc, no_load, no_store);
             }
             if constexpr (st == ST_UNPRUNED_G2H || st == ST_PRUNED_G2H) {
                 constexpr bool pr = st == ST_PRUNED_G2H;
-                if (WRITE) for (int i = lane; i < a.g2h_head_len; i += 32) base[i] = a.blob[a.g2h_head_off + i];
+                if (WRITE) {
+                    const int mis = (int)(reinterpret_cast<unsigned long long>(base) & 15ull);
+                    flush_stage(a.blob + a.g2h_head_off16[mis] - mis, mis, base, (unsigned)a.g2h_head_len);      // source congruent to destination mod 16
+                }
                 bytes = (unsigned long long)a.g2h_head_len;
                 const int np = pr ? (inf.p_root >= 0 ? inf.n_p : 0) : inf.n_u;
                 const int32_t* bfs = pr ? bfsP : bfsU;

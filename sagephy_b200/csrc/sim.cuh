@@ -159,58 +159,76 @@ static __device__ int find_victim(const Node* N, int root, int to, double t) {
 }
 
 // One attempt of createUnprunedTree. Returns 0, or REP_NODE_OVERFLOW. n_out = vertices created, root_out = root index.
+//
+// Written as a state machine with ONE vertex-creation site: every loop trip either fetches the next lineage from the queue
+// (stage 0) or creates exactly one vertex (stages 1-3) through the single draw_vertex call below. Threads of a warp simulate
+// different replicates, so they can only re-converge on code that is textually shared — the expensive Java-exact vertex draw
+// (log, divide, round8) is therefore executed by all creating lanes together instead of at eight separate call sites.
+// The order in which random numbers are consumed is exactly the reference's (coin -> staying child -> sampleArc(s) ->
+// moving child; left child before right child).
 template <class RNG>
 __device__ int simulate_attempt(RNG& rng, const SimParams& P, const DevHost& H, const MathTables& T, SimWork& W, int& n_out, int& root_out) {
     int n = 0, qh = 0, qt = 0, np = 0;
-    int X0; double start;
-    if (P.ishost || !P.do_gene_birth) { X0 = H.root; start = H.ep_up[H.nE - 1]; }
-    else { X0 = sample_root(rng, P, H); start = H.ep_up[H.v2e[X0]]; }
-    int root = new_node(W, n, draw_vertex(rng, P, H, T, X0, start), X0);
-    if (root < 0) { n_out = n; return REP_NODE_OVERFLOW; }
-    W.queue[qt++] = root;
-    while (qh < qt) {
-        const int li = W.queue[qh++];
-        const uint8_t ev = W.nodes[li].event;
-        int lc = -1, rc = -1;
-        if (ev == EV_LOSS || ev == EV_REPLACING_LOSS || ev == EV_LEAF || ev == EV_UNSAMPLED_LEAF) {
-            // lineage ends
-        } else {
-            const int sigma = W.nodes[li].sigma; const double t = W.nodes[li].abstime; const int ep = W.nodes[li].epoch;
-            if (ev == EV_SPECIATION) {
-                int a = H.left[sigma], b = H.right[sigma];
-                lc = new_node(W, n, draw_vertex(rng, P, H, T, a, t), a); if (lc < 0) { n_out = n; return REP_NODE_OVERFLOW; }
-                rc = new_node(W, n, draw_vertex(rng, P, H, T, b, t), b); if (rc < 0) { n_out = n; return REP_NODE_OVERFLOW; }
-            } else if (ev == EV_DUPLICATION) {
-                lc = new_node(W, n, draw_vertex(rng, P, H, T, sigma, t), sigma); if (lc < 0) { n_out = n; return REP_NODE_OVERFLOW; }
-                rc = new_node(W, n, draw_vertex(rng, P, H, T, sigma, t), sigma); if (rc < 0) { n_out = n; return REP_NODE_OVERFLOW; }
-            } else if (ev == EV_ADDITIVE_TRANSFER) {
-                const bool stay_left = rng.next_double() < 0.5;
-                int stay = new_node(W, n, draw_vertex(rng, P, H, T, sigma, t), sigma); if (stay < 0) { n_out = n; return REP_NODE_OVERFLOW; }
-                int to = sample_arc(rng, P, H, ep, sigma, t, nullptr, 0);
-                int moved = new_node(W, n, draw_vertex(rng, P, H, T, to, t), to); if (moved < 0) { n_out = n; return REP_NODE_OVERFLOW; }
-                W.nodes[li].from_arc = sigma; W.nodes[li].to_arc = to;
-                lc = stay_left ? stay : moved; rc = stay_left ? moved : stay;
-            } else {   // EV_REPLACING_TRANSFER
-                const bool stay_left = rng.next_double() < 0.5;
-                int stay = new_node(W, n, draw_vertex(rng, P, H, T, sigma, t), sigma); if (stay < 0) { n_out = n; return REP_NODE_OVERFLOW; }
-                const int first_to = sample_arc(rng, P, H, ep, sigma, t, nullptr, 0);
+    int stage = 3;                 // 3: create the root, 0: fetch a lineage, 1: create first vertex of the pair, 2: create second
+    int li = -1, c1 = -1; uint8_t ev = 0; bool stay_left = true;
+    int X; double t;               // arc and start time of the vertex to create next
+    if (P.ishost || !P.do_gene_birth) { X = H.root; t = H.ep_up[H.nE - 1]; }
+    else { X = sample_root(rng, P, H); t = H.ep_up[H.v2e[X]]; }
+    int root = -1, sigma = 0, ep = 0, first_to = -1, victim = -1;
+    for (;;) {
+        if (stage == 0) {
+            if (qh == qt) {
+                if (np == 0) break;
+                int best = 0;      // release the oldest parked replacing transfer (largest abstime)
+                for (int i = 1; i < np; ++i) if (W.nodes[W.pend[i]].abstime > W.nodes[W.pend[best]].abstime) best = i;
+                W.queue[qt++] = W.pend[best];
+                W.pend[best] = W.pend[--np];
+            }
+            li = W.queue[qh++];
+            const Node& ln = W.nodes[li];
+            ev = ln.event;
+            if (ev == EV_LOSS || ev == EV_REPLACING_LOSS || ev == EV_LEAF || ev == EV_UNSAMPLED_LEAF) continue;     // lineage ends
+            sigma = ln.sigma; t = ln.abstime; ep = ln.epoch;
+            if (ev == EV_SPECIATION) X = H.left[sigma];
+            else { X = sigma; if (ev != EV_DUPLICATION) stay_left = rng.next_double() < 0.5; }
+            stage = 1;
+            continue;
+        }
+        if (stage == 2) {
+            // arc of the second vertex
+            if (ev == EV_SPECIATION) X = H.right[sigma];
+            else if (ev == EV_DUPLICATION) X = sigma;
+            else if (ev == EV_ADDITIVE_TRANSFER) { X = sample_arc(rng, P, H, ep, sigma, t, nullptr, 0); first_to = X; victim = -1; }
+            else {   // EV_REPLACING_TRANSFER: look for a lineage to replace, arc by arc
+                first_to = sample_arc(rng, P, H, ep, sigma, t, nullptr, 0);
                 int to = first_to;
-                int victim = find_victim(W.nodes, root, to, t);
+                victim = find_victim(W.nodes, root, to, t);
                 const int n_arcs = H.ep_off[ep + 1] - H.ep_off[ep];
                 int n_empty = 0; const int gen = ++W.mark_gen;
                 while (victim < 0 && n_empty != n_arcs - 1) {
                     if (W.marks[to] != gen) { W.marks[to] = gen; ++n_empty; }
                     if (n_empty != n_arcs - 1) { to = sample_arc(rng, P, H, ep, sigma, t, W.marks, gen); victim = find_victim(W.nodes, root, to, t); }
                 }
-                W.nodes[li].from_arc = sigma;
-                int moved;
+                X = victim >= 0 ? to : first_to;
+            }
+        }
+        // ---- the single vertex-creation site
+        const VertexDraw d = draw_vertex(rng, P, H, T, X, t);
+        const int idx = new_node(W, n, d, X);
+        if (idx < 0) { n_out = n; return REP_NODE_OVERFLOW; }
+        if (stage == 3) { root = idx; W.queue[qt++] = root; stage = 0; continue; }
+        if (stage == 1) { c1 = idx; stage = 2; continue; }
+        // ---- stage 2 done: attach the pair
+        int lc, rc;
+        if (ev == EV_SPECIATION || ev == EV_DUPLICATION) { lc = c1; rc = idx; }
+        else {
+            Node& ln = W.nodes[li];
+            ln.from_arc = sigma; ln.to_arc = X;
+            if (ev == EV_REPLACING_TRANSFER) {
                 if (victim >= 0) {
-                    moved = new_node(W, n, draw_vertex(rng, P, H, T, to, t), to); if (moved < 0) { n_out = n; return REP_NODE_OVERFLOW; }
-                    W.nodes[li].to_arc = to;
                     Node& vn = W.nodes[victim];
                     vn.event = EV_REPLACING_LOSS; vn.abstime = t;
-                    // drop parked replacing transfers that sit in the victim's subtree (victim included)
-                    int w = 0;
+                    int w = 0;          // drop parked replacing transfers that sit in the victim's subtree (victim included)
                     for (int i = 0; i < np; ++i) {
                         int x = W.pend[i]; bool under = false;
                         for (int y = x; y >= 0; y = W.nodes[y].parent) if (y == victim) { under = true; break; }
@@ -218,31 +236,22 @@ __device__ int simulate_attempt(RNG& rng, const SimParams& P, const DevHost& H, 
                     }
                     np = w;
                     vn.left = -1; vn.right = -1;
-                } else {
-                    W.nodes[li].event = EV_ADDITIVE_TRANSFER;
-                    moved = new_node(W, n, draw_vertex(rng, P, H, T, first_to, t), first_to); if (moved < 0) { n_out = n; return REP_NODE_OVERFLOW; }
-                    W.nodes[li].to_arc = first_to;
-                }
-                lc = stay_left ? stay : moved; rc = stay_left ? moved : stay;
+                } else ln.event = EV_ADDITIVE_TRANSFER;      // nothing to replace anywhere: degrade (GuestTreeInHostTreeCreator.java:228-233)
             }
-            W.nodes[li].left = lc; W.nodes[li].right = rc;
-            W.nodes[lc].parent = li; W.nodes[rc].parent = li;
-            for (int s = 0; s < 2; ++s) {
-                int c = s == 0 ? lc : rc;
-                if (W.nodes[c].event != EV_REPLACING_TRANSFER) W.queue[qt++] = c;
-                else {
-                    bool replaced = false;     // TreeMap.put on an equal key overwrites the value
-                    for (int i = 0; i < np; ++i) if (W.nodes[W.pend[i]].abstime == W.nodes[c].abstime) { W.pend[i] = c; replaced = true; break; }
-                    if (!replaced) W.pend[np++] = c;
-                }
+            lc = stay_left ? c1 : idx; rc = stay_left ? idx : c1;
+        }
+        W.nodes[li].left = lc; W.nodes[li].right = rc;
+        W.nodes[lc].parent = li; W.nodes[rc].parent = li;
+        for (int s = 0; s < 2; ++s) {
+            const int c = s == 0 ? lc : rc;
+            if (W.nodes[c].event != EV_REPLACING_TRANSFER) W.queue[qt++] = c;
+            else {
+                bool replaced = false;     // TreeMap.put on an equal key overwrites the value
+                for (int i = 0; i < np; ++i) if (W.nodes[W.pend[i]].abstime == W.nodes[c].abstime) { W.pend[i] = c; replaced = true; break; }
+                if (!replaced) W.pend[np++] = c;
             }
         }
-        if (qh == qt && np > 0) {      // release the oldest parked replacing transfer (largest abstime)
-            int best = 0;
-            for (int i = 1; i < np; ++i) if (W.nodes[W.pend[i]].abstime > W.nodes[W.pend[best]].abstime) best = i;
-            W.queue[qt++] = W.pend[best];
-            W.pend[best] = W.pend[--np];
-        }
+        stage = 0;
     }
     if (W.nodes[root].bl <= 1.0e-32) W.nodes[root].bl = 0.0;
     n_out = n; root_out = root;
