@@ -6,6 +6,7 @@
 //   JCommander 1.18 grammar as used there: options anywhere, Boolean options have arity 0, others take the next token,
 //   everything else is a positional ("main parameter"); an unknown "-x" token raises (caught by main -> stack trace).
 #pragma once
+#include <dirent.h>
 #include <fstream>
 #include <map>
 #include <sstream>
@@ -232,6 +233,91 @@ inline void run_guest_tree_gen(const std::vector<std::string>& args, Outputs& o,
                 o.file(prefix + ".pruned.guest2host", motor.sigma(r.pruned));
                 o.file(prefix + ".unpruned.leafmap", motor.leaf_map(r.unpruned));
                 o.file(prefix + ".pruned.leafmap", motor.leaf_map(r.pruned));
+            }
+        }
+        if (st) { fill_stats(*st, r); st->vertices_created = motor.vertices_created; }
+    } catch (std::exception& e) {
+        o.err += std::string(e.what()) + "\n\nUse option -h or --help to show usage.\n";
+        if (st) st->status = 2;
+    }
+}
+
+
+// ---- DomainTreeGen (apps/SaGePhy/DomainTreeGen.java:21-107, DomainTreeGenParameters.java:30-151) ---------------------------------
+inline const std::vector<OptSpec>& domain_specs() {
+    static const std::vector<OptSpec> s = {
+        {{"-h", "--help"}, 0}, {{"-q", "--quiet"}, 0}, {{"-s", "--seed"}, 1}, {{"-min", "--min-leaves"}, 1}, {{"-max", "--max-leaves"}, 1},
+        {{"-minper", "--min-leaves-per-host-leaf"}, 1}, {{"-maxper", "--max-leaves-per-host-leaf"}, 1}, {{"-sizes", "--leaf-sizes-file"}, 1},
+        {{"-nox", "--no-auxiliary-tags"}, 0}, {{"-p", "--leaf-sampling-probability"}, 1}, {{"-mpr", "--enforce-most-parsimonious-reconciliation"}, 0},
+        {{"-a", "--max-attempts"}, 1}, {{"-stem", "--override-host-stem"}, 1}, {{"-vp", "--vertex-prefix"}, 1}, {{"-vph", "--vertex-prefix-host-map"}, 0},
+        {{"-hybrid", "--hybrid-host-graph"}, 3}, {{"-rt", "--replacing-transfers"}, 1}, {{"-db", "--distance-bias"}, 1}, {{"-dbr", "--distance-bias-rate"}, 1},
+        {{"-dbs", "--domain-birth-sampling"}, 0}, {{"-dbc", "--domain-birth-coefficient"}, 1}, {{"-ig", "--inter-gene-transfers"}, 1},
+        {{"-is", "--inter-species-transfers"}, 1}, {{"-all", "--all-gene-trees"}, 0}};
+    return s;
+}
+// Gene-tree files of the directory in lexicographic file-name order (the reference uses File.listFiles(), whose order is
+// OS-dependent; both the oracle and the product fix it to sorted order — SURVEY H7).
+inline std::vector<std::string> list_dir_sorted(const std::string& dir) {
+    std::vector<std::string> v; DIR* d = opendir(dir.c_str());
+    if (!d) throw std::runtime_error("NullPointerException: cannot list gene tree directory " + dir);
+    while (dirent* e = readdir(d)) { std::string n = e->d_name; if (n == "." || n == "..") continue; v.push_back(dir + "/" + n); }
+    closedir(d); std::sort(v.begin(), v.end()); return v;
+}
+
+inline void run_domain_tree_gen(const std::vector<std::string>& args, Outputs& o, RepStats* st = nullptr) {
+    try {
+        ParsedArgs p = jc_parse(args, domain_specs());
+        bool quiet = p.has("-q");
+        size_t noargs = quiet ? 5 : 6;
+        if (args.empty() || p.has("-h") || p.pos.size() != noargs) {
+            o.out += "Usage:\n    java -jar sagephy-X.Y.Z.jar DomainTreeGen [options] <host tree file or string> <guest tree directory> <dup rate> <loss rate> <trans rate> <out prefix>\n\n";
+            return;
+        }
+        if (p.has("-hybrid")) throw std::invalid_argument("oracle: -hybrid host graphs are out of scope (SURVEY.md §2 row 17)");
+        std::vector<int> sizes; bool hasSizes = p.has("-sizes");
+        if (hasSizes) sizes = read_leaf_sizes(p.get("-sizes", ""));
+        bool excludeMeta = p.has("-nox");
+        if (!p.has("-s")) throw std::invalid_argument("oracle: a seed (-s) is required (the reference would read /dev/random)");
+        Machina machina(p.get("-s", ""), parse_int(p.get("-min", "2")), parse_int(p.get("-max", "1000")), parse_int(p.get("-minper", "0")),
+                        parse_int(p.get("-maxper", "10")), hasSizes ? &sizes : nullptr, parse_int(p.get("-a", "10000")), p.get("-vp", "D"), excludeMeta, true, false);
+        std::unique_ptr<NTree> spNewick; std::optional<std::string> spName;
+        if (file_exists(p.pos[0])) { spNewick = nw_read_tree(read_file(p.pos[0])); spName = base_name(p.pos[0]); } else spNewick = nw_read_tree(p.pos[0]);
+        std::optional<double> stem = p.has("-stem") ? parse_double(p.get("-stem", "")) : 0.0;
+        HostModel species(*spNewick, spName, stem);
+        std::vector<std::unique_ptr<NTree>> geneNewicks; std::vector<std::unique_ptr<HostModel>> geneModels; std::vector<HostModel*> genePtrs;
+        for (const std::string& f : list_dir_sorted(p.pos[1])) {
+            geneNewicks.push_back(nw_read_tree(read_file(f)));
+            geneModels.push_back(std::make_unique<HostModel>(*geneNewicks.back(), std::optional<std::string>(base_name(f)), std::nullopt));
+            genePtrs.push_back(geneModels.back().get());
+        }
+        if (genePtrs.empty()) throw std::invalid_argument("IllegalArgumentException: n must be positive (no gene trees in directory)");
+        DomainCreator motor(species, genePtrs, parse_double(p.pos[2]), parse_double(p.pos[3]), parse_double(p.pos[4]), parse_double(p.get("-rt", "0.5")),
+                            p.get("-db", "none"), parse_double(p.get("-dbr", "1.0")), p.has("-dbs"), parse_double(p.get("-dbc", "1.0")),
+                            parse_double(p.get("-ig", "0.5")), parse_double(p.get("-is", "0.5")), parse_double(p.get("-p", "1.0")));
+        std::string prefix = quiet ? "" : trim_java(p.pos[5]);
+        MachinaResult r;
+        try { r = machina.sample(motor, p.has("-all")); }
+        catch (MaxAttemptsException&) {
+            if (!quiet) o.file(prefix + ".pruned.info", std::string(kFailMsg) + "\n");
+            o.err += std::string(kFailMsg) + "\n";
+            if (st) { st->status = 1; st->attempts = machina.attempts; }
+            return;
+        }
+        const char* um = excludeMeta ? nullptr : "[NAME=UnprunedTree]"; const char* pm = excludeMeta ? nullptr : "[NAME=PrunedTree]";
+        if (quiet) {
+            if (excludeMeta) o.out += (r.pruned ? gtree_to_string(r.pruned, pm) : std::string(";")) + "\n";
+            else o.out += (r.pruned ? gtree_to_string(r.pruned, pm) : std::string("[NAME=PrunedTree];")) + "\n";
+        } else {
+            o.file(prefix + ".unpruned.tree", gtree_to_string(r.unpruned, um) + "\n");
+            if (excludeMeta) o.file(prefix + ".pruned.tree", r.pruned ? gtree_to_string(r.pruned, pm) + "\n" : std::string(";\n"));
+            else o.file(prefix + ".pruned.tree", r.pruned ? gtree_to_string(r.pruned, pm) + "\n" : std::string("[NAME=PrunedTree];\n"));
+            std::string head = "# DOMAINTREEGEN\nArguments:\t" + arrays_to_string(args) + "\nAttempts:\t" + std::to_string(r.attempts) + "\n";
+            o.file(prefix + ".unpruned.info", head + motor.info(r.unpruned, true));
+            if (!r.pruned) throw std::runtime_error("NullPointerException (pruned tree is empty)");
+            o.file(prefix + ".pruned.info", head + motor.info(r.pruned, true));
+            if (!excludeMeta) {
+                o.file(prefix + ".unpruned.guest2host", motor.sigma(r.unpruned)); o.file(prefix + ".pruned.guest2host", motor.sigma(r.pruned));
+                o.file(prefix + ".unpruned.leafmap", motor.leaf_map(r.unpruned)); o.file(prefix + ".pruned.leafmap", motor.leaf_map(r.pruned));
             }
         }
         if (st) { fill_stats(*st, r); st->vertices_created = motor.vertices_created; }

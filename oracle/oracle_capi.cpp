@@ -17,6 +17,7 @@ void dispatch(const std::vector<std::string>& argv, Outputs& o, RepStats* st) {
     if (app == "HostTreeGen") run_host_tree_gen(rest, o, st);
     else if (app == "GuestTreeGen") run_guest_tree_gen(rest, o, st);
     else if (app == "BranchRelaxer") run_branch_relaxer(rest, o, st);
+    else if (app == "DomainTreeGen") run_domain_tree_gen(rest, o, st);
     else { o.out += "Unknown application: " + app + "\n"; if (st) st->status = 2; }
 }
 

@@ -286,6 +286,224 @@ public:
     }
 };
 
+// ---- DomainTreeInHostTreeCreator (apps/SaGePhy/DomainTreeInHostTreeCreator.java:101-1300) ---------------------------------------
+// A domain tree evolving inside a forest of gene trees. The eight transfer kinds share one code path here, parameterised by
+// (additive | replacing) x (intra | inter gene) x (intra | inter species); the reference spells out all sixteen branches.
+class DomainCreator : public Creator {
+public:
+    HostModel& species; std::vector<HostModel*> genes; std::vector<std::string> gene_names;
+    double lambda, mu, tau, theta; std::string bias; double bias_rate; bool doBirth; double birth; double inter_gene, inter_species, rho;
+    std::vector<int> used; GVertex* root = nullptr; uint64_t vertices_created = 0;
+
+    DomainCreator(HostModel& sp, std::vector<HostModel*> g, double l, double m, double t, double th, std::string b, double br, bool db, double dbc,
+                  double ig, double is, double rho_)
+        : species(sp), genes(std::move(g)), lambda(l), mu(m), tau(t), theta(th), bias(std::move(b)), bias_rate(br), doBirth(db), birth(dbc),
+          inter_gene(ig), inter_species(is), rho(rho_) {
+        if (lambda < 0 || mu < 0 || tau < 0 || birth < 0) throw std::invalid_argument("IllegalArgumentException: Cannot have rate less than 0.");
+        if (theta < 0 || theta > 1 || inter_gene < 0 || inter_gene > 1 || inter_species < 0 || inter_species > 1 || rho < 0 || rho > 1)
+            throw std::invalid_argument("IllegalArgumentException: Cannot have probability outside [0,1].");
+        for (HostModel* h : genes) gene_names.push_back(h->tree_name ? *h->tree_name : std::string("null"));
+    }
+    int tree_index(const HostModel* h) const { for (size_t i = 0; i < genes.size(); ++i) if (genes[i] == h) return (int)i; return -1; }
+
+    GVertex* create_guest_vertex(int X, double startTime, JavaMT& prng, Arena& arena, HostModel* g) {      // :1042-1120
+        ++vertices_created;
+        bool isRoot = g->is_root(X);
+        double sum = isRoot ? lambda + mu : lambda + mu + tau;
+        if (sum == 0.0) sum = 1e-48;
+        double lowerTime = g->vertex_time(X);
+        double branchTime = exp_sample(prng, sum);
+        double eventTime = startTime - branchTime;
+        Event event; EpochO* epoch;
+        if (eventTime <= lowerTime) {
+            eventTime = lowerTime;
+            branchTime = round_sig(startTime - eventTime, 8);
+            if (g->is_leaf(X)) event = (prng.nextDouble() < rho ? Event::LEAF : Event::UNSAMPLED_LEAF); else event = Event::CODIVERGENCE;
+            epoch = &g->epochs[g->epoch_no_above(X)];
+        } else {
+            double rnd = prng.nextDouble();
+            if (isRoot) event = (rnd < lambda / sum) ? Event::DUPLICATION : Event::LOSS;
+            else if (rnd >= (mu + tau) / sum) event = Event::DUPLICATION;
+            else if (rnd < mu / sum) event = Event::LOSS;
+            else {
+                double trn = prng.nextDouble(), trn_gen = prng.nextDouble(), trn_spe = prng.nextDouble();
+                int base = (trn < theta) ? (int)Event::RT_INTRAGENE_INTRASPECIES : (int)Event::AT_INTRAGENE_INTRASPECIES;
+                event = (Event)(base + (trn_gen < inter_gene ? 2 : 0) + (trn_spe < inter_species ? 1 : 0));
+            }
+            int epno = g->epoch_no_above(X);
+            while (g->epochs[epno].upper() < eventTime) ++epno;
+            epoch = &g->epochs[epno];
+        }
+        used[tree_index(g)]++;
+        GVertex* v = arena.make();
+        v->event = event; v->sigma = X; v->epoch = epoch; v->abstime = eventTime; v->bl = branchTime; v->tree = g;
+        return v;
+    }
+
+    static GVertex* find_vertex(GVertex* node, const GVertex* x, const HostModel* g) {     // :948-964
+        if (!node) return nullptr;
+        if (node->sigma == x->toArc && node->tree == g && node != x->right() && node != x->left() && node->abstime < x->abstime && (node->abstime + node->bl) > x->abstime) return node;
+        GVertex* n = find_vertex(node->left(), x, g);
+        if (!n) n = find_vertex(node->right(), x, g);
+        return n;
+    }
+
+    // sampleInterGeneArc :1004-1033. Returns (-5, null) when there is no candidate.
+    std::pair<int, HostModel*> sample_inter_gene_arc(GVertex* lin, bool intraSpecies, const std::vector<int>* emptyArcs, JavaMT& prng) {
+        std::vector<std::pair<int, HostModel*>> cand;
+        int hostArc = lin->tree->host_tag[lin->sigma];
+        for (HostModel* tr : genes) {
+            if (tr == lin->tree) continue;
+            for (int i = 0; i < tr->k; ++i) {
+                int arcHost = tr->host_tag[i];
+                if (i != lin->sigma && (!emptyArcs || std::find(emptyArcs->begin(), emptyArcs->end(), i) == emptyArcs->end()) &&
+                    tr->vertex_time(i) < lin->abstime && tr->vertex_upper_time(i) > lin->abstime && (intraSpecies ? (arcHost == hostArc) : (arcHost != hostArc)))
+                    cand.push_back({i, tr});
+            }
+        }
+        if (cand.empty()) return {-5, nullptr};
+        int c = prng.nextInt((int)cand.size());
+        lin->epoch->transferedToArc = cand[c].first;
+        return cand[c];
+    }
+
+    GVertex* create_unpruned_tree(JavaMT& prng, Arena& arena) override {      // :158-937
+        std::deque<GVertex*> alive; std::map<double, GVertex*> sorted;
+        int first_guest = prng.nextInt((int)genes.size());
+        used.assign(genes.size(), 0);
+        HostModel* g0 = genes[first_guest];
+        if (doBirth) { int r0 = g0->sample_root(prng, birth); root = create_guest_vertex(r0, g0->vertex_upper_time(r0), prng, arena, g0); }
+        else root = create_guest_vertex(g0->root, g0->tip_to_leaf_time(), prng, arena, g0);
+        alive.push_back(root);
+        auto release = [&]() { if (alive.empty() && !sorted.empty()) { auto it = std::prev(sorted.end()); alive.push_back(it->second); sorted.erase(it); } };
+        auto is_repl = [](Event e) { return (int)e >= (int)Event::RT_INTRAGENE_INTRASPECIES; };
+        while (!alive.empty()) {
+            GVertex* lin = alive.front(); alive.pop_front();
+            if (lin->event == Event::LOSS || lin->event == Event::REPLACING_LOSS || lin->event == Event::LEAF || lin->event == Event::UNSAMPLED_LEAF) { release(); continue; }
+            GVertex *lc = nullptr, *rc = nullptr;
+            if (lin->event == Event::CODIVERGENCE) {
+                lc = create_guest_vertex(lin->tree->left[lin->sigma], lin->abstime, prng, arena, lin->tree);
+                rc = create_guest_vertex(lin->tree->right[lin->sigma], lin->abstime, prng, arena, lin->tree);
+            } else if (lin->event == Event::DUPLICATION) {
+                lc = create_guest_vertex(lin->sigma, lin->abstime, prng, arena, lin->tree);
+                rc = create_guest_vertex(lin->sigma, lin->abstime, prng, arena, lin->tree);
+            } else if ((int)lin->event >= (int)Event::AT_INTRAGENE_INTRASPECIES) {
+                const int code = ((int)lin->event - (int)Event::AT_INTRAGENE_INTRASPECIES) & 3;
+                const bool replacing = is_repl(lin->event), inter = (code & 2) != 0, include = (code & 1) == 0;
+                const bool stayLeft = prng.nextDouble() < 0.5;
+                const int hostArc = lin->tree->host_tag[lin->sigma];
+                int to; HostModel* totree;
+                if (!inter) { to = lin->tree->sample_arc(*lin->epoch, prng, lin->sigma, 0, lin->abstime, bias, bias_rate, nullptr, hostArc, include); totree = lin->tree; }
+                else { auto pr = sample_inter_gene_arc(lin, include, nullptr, prng); to = pr.first; totree = pr.second; }
+                const int firstTo = to; HostModel* origGene = totree;
+                if (to == -5) {
+                    // swap (:984-1002): the transfer vertex is replaced in place by a freshly sampled vertex
+                    GVertex* child = create_guest_vertex(lin->sigma, lin->abstime, prng, arena, lin->tree);
+                    if (lin != root) { GVertex* par = lin->parent; if (par->lc == lin) par->lc = child; else par->rc = child; } else root = child;
+                    if (child != root) child->parent = lin->parent;
+                    lin->parent = nullptr; lin = nullptr;
+                    if (stayLeft) lc = child; else rc = child;
+                } else {
+                    GVertex* stay = create_guest_vertex(lin->sigma, lin->abstime, prng, arena, lin->tree);
+                    GVertex* moved;
+                    lin->fromArc = lin->sigma; lin->toArc = lin->epoch->transferedToArc;
+                    if (!replacing) moved = create_guest_vertex(to, lin->abstime, prng, arena, totree);
+                    else {
+                        GVertex* node = find_vertex(root, lin, totree);
+                        std::vector<int> emptyArcs;
+                        while (!node && (int)emptyArcs.size() != lin->epoch->n_arcs() - 1 && lin->toArc != -5) {
+                            if (std::find(emptyArcs.begin(), emptyArcs.end(), lin->toArc) == emptyArcs.end()) emptyArcs.push_back(lin->toArc);
+                            if ((int)emptyArcs.size() != lin->epoch->n_arcs() - 1) {
+                                if (!inter) lin->toArc = lin->tree->sample_arc(*lin->epoch, prng, lin->sigma, 0, lin->abstime, bias, bias_rate, &emptyArcs, hostArc, include);
+                                else { auto pr = sample_inter_gene_arc(lin, include, &emptyArcs, prng); lin->toArc = pr.first; totree = pr.second; }
+                                node = find_vertex(root, lin, totree);
+                            }
+                        }
+                        if (node) {
+                            moved = create_guest_vertex(lin->toArc, lin->abstime, prng, arena, totree);
+                            node->event = Event::REPLACING_LOSS; node->abstime = lin->abstime;
+                            for (auto it = sorted.begin(); it != sorted.end();) { if (GuestInHostCreator::is_ancestor(node, it->second)) it = sorted.erase(it); else ++it; }
+                            node->clear_children();
+                        } else {
+                            moved = create_guest_vertex(firstTo, lin->abstime, prng, arena, origGene);
+                            lin->event = (Event)((int)lin->event - 4);      // the additive kind with the same gene / species scope
+                            lin->toArc = firstTo; lin->epoch->transferedToArc = firstTo;
+                        }
+                    }
+                    lin->fromGuest = &gene_names[tree_index(lin->tree)]; lin->toGuest = &gene_names[tree_index(moved->tree)];
+                    if (stayLeft) { lc = stay; rc = moved; } else { rc = stay; lc = moved; }
+                }
+            } else throw std::runtime_error("UnsupportedOperationException: Unexpected event type.");
+            if (lin) { lin->set_children(lc, rc); lc->parent = lin; rc->parent = lin; }
+            if (lc) { if (!is_repl(lc->event)) alive.push_back(lc); else sorted[lc->abstime] = lc; }
+            if (rc) { if (!is_repl(rc->event)) alive.push_back(rc); else sorted[rc->abstime] = rc; }
+            release();
+        }
+        if (root->bl <= 1.0e-32) root->bl = 0.0;
+        return root;
+    }
+
+    std::vector<int> host_leaves() const override { return species.leaves(); }
+    bool any_unused() const override { for (int u : used) if (u == 0) return true; return false; }
+
+    std::string info(const GVertex* guestRoot, bool doML) const override {       // :1128-1252
+        int cnt[17] = {0}; int nV = 0; double totalTime = 0.0, beneath = 0.0;
+        std::deque<const GVertex*> q; if (guestRoot) q.push_back(guestRoot);
+        double hostRootTime = species.vertex_time(species.root);
+        while (!q.empty()) {
+            const GVertex* v = q.front(); q.pop_front();
+            if (!v->is_leaf()) { q.push_back(v->left()); q.push_back(v->right()); }
+            ++nV; totalTime += v->bl; beneath += std::max(std::min(hostRootTime - v->abstime, v->bl), 0.0);
+            if (v->event == Event::SPECIATION || v->event == Event::ADDITIVE_TRANSFER || v->event == Event::REPLACING_TRANSFER) throw std::runtime_error("UnsupportedOperationException: Unexpected event type.");
+            cnt[(int)v->event]++;
+        }
+        totalTime = round_sig(totalTime, 8); beneath = round_sig(beneath, 8);
+        std::string sb;
+        auto I = [&](const std::string& k, int v) { sb += k; sb += std::to_string(v); sb.push_back('\n'); };
+        auto D = [&](const std::string& k, double v) { sb += k; sb += java_double_to_string(v); sb.push_back('\n'); };
+        static const char* scope[4] = {"intragene intraspecies", "intragene interspecies", "intergene intraspecies", "intergene interspecies"};
+        static const char* Scope[4] = {"Intragene Intraspecies", "Intragene Interspecies", "Intergene Intraspecies", "Intergene Interspecies"};
+        I("No. of vertices:\t", nV); I("No. of extant leaves:\t", cnt[(int)Event::LEAF] + cnt[(int)Event::UNSAMPLED_LEAF]);
+        I("No. of co-divergences:\t", cnt[(int)Event::CODIVERGENCE]); I("No. of duplications:\t", cnt[(int)Event::DUPLICATION]);
+        I("No. of losses:\t", cnt[(int)Event::LOSS]); I("No. of replacing losses:\t", cnt[(int)Event::REPLACING_LOSS]);
+        for (int k = 0; k < 4; ++k) I(std::string("No. of additive transfers ") + scope[k] + ":\t", cnt[(int)Event::AT_INTRAGENE_INTRASPECIES + k]);
+        for (int k = 0; k < 4; ++k) I(std::string("No. of replacing transfers ") + scope[k] + ":\t", cnt[(int)Event::RT_INTRAGENE_INTRASPECIES + k]);
+        D("Total branch time:\t", totalTime); D("Total branch time beneath host stem:\t", beneath);
+        if (doML) {
+            D("Duplication ML estimate:\t", round_sig(cnt[(int)Event::DUPLICATION] / totalTime, 8)); D("Loss ML estimate:\t", round_sig(cnt[(int)Event::LOSS] / totalTime, 8));
+            D("Replacing Loss ML estimate:\t", round_sig(cnt[(int)Event::REPLACING_LOSS] / totalTime, 8));
+            for (int k = 0; k < 4; ++k) D(std::string("Additive Transfer ") + Scope[k] + " ML estimate:\t", round_sig(cnt[(int)Event::AT_INTRAGENE_INTRASPECIES + k] / totalTime, 8));
+            for (int k = 0; k < 4; ++k) D(std::string("Replacing Transfer ") + Scope[k] + " ML estimate:\t", round_sig(cnt[(int)Event::RT_INTRAGENE_INTRASPECIES + k] / totalTime, 8));
+        }
+        return sb;
+    }
+    std::string leaf_map(const GVertex* guestRoot) const override {      // :1255-1273 (three columns)
+        std::string sb; std::deque<const GVertex*> q; if (guestRoot) q.push_back(guestRoot);
+        while (!q.empty()) {
+            const GVertex* v = q.front(); q.pop_front();
+            if (!v->is_leaf()) { q.push_back(v->left()); q.push_back(v->right()); }
+            else if (v->event == Event::LEAF || v->event == Event::UNSAMPLED_LEAF) {
+                sb += v->name(); sb.push_back('\t'); sb += (v->tree->names[v->sigma] ? *v->tree->names[v->sigma] : std::string("null")); sb.push_back('\t');
+                sb += (v->tree->tree_name ? *v->tree->tree_name : std::string("null")); sb.push_back('\n');
+            }
+        }
+        return sb;
+    }
+    std::string sigma(const GVertex* guestRoot) const override {         // :1276-1300 (host tree = gene tree of the root vertex)
+        std::string sb = "# GUEST-TO-HOST MAP\n";
+        sb += "Host tree:\t" + guestRoot->tree->to_string() + "\n";
+        sb += "Guest vertex name:\tGuest vertex ID:\tGuest vertex type:\tGuest vertex time:\tHost vertex/arc ID:\tHost epoch ID:\n";
+        std::deque<const GVertex*> q; q.push_back(guestRoot);
+        while (!q.empty()) {
+            const GVertex* v = q.front(); q.pop_front();
+            if (!v->is_leaf()) { q.push_back(v->left()); q.push_back(v->right()); }
+            sb += v->name(); sb.push_back('\t'); sb += std::to_string(v->number); sb.push_back('\t'); sb += event_java_name(v->event); sb.push_back('\t');
+            sb += java_double_to_string(v->abstime); sb.push_back('\t'); sb += std::to_string(v->sigma); sb.push_back('\t'); sb += std::to_string(v->epoch->no); sb.push_back('\n');
+        }
+        return sb;
+    }
+};
+
 // ---- PruningHelper ------------------------------------------------------------------------------------------------------
 inline void set_label(GVertex* v, int no, const std::string& prefix, bool appendSigma) { v->number = no; v->name_prefix = &prefix; v->name_sigma = appendSigma; }
 inline int label_unprunable(GVertex* v, int nextNo, const std::string& prefix, bool appendSigma) {      // PruningHelper.java:25-65
