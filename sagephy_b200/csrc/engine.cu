@@ -237,12 +237,18 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     const unsigned long long seed = (unsigned long long)cfg.seed;
 
     HostOnDevice hd; hd.upload(cfg.host);
+    const bool domain = cfg.app == 2;
+    std::vector<std::unique_ptr<HostOnDevice>> gene_dev; std::vector<DevHost> gene_views; int max_gene_nv = 1;
+    for (const HostModel& g : cfg.genes) { gene_dev.emplace_back(new HostOnDevice()); gene_dev.back()->upload(g); gene_views.push_back(gene_dev.back()->view); max_gene_nv = std::max(max_gene_nv, g.nV); }
+    max_gene_nv = std::max(max_gene_nv, cfg.host.nV);
+    DevBuf<DevHost> d_genes; d_genes.upload(gene_views);
+    DevBuf<int32_t> scratch_used;
     DevBuf<int32_t> d_sizes; { std::vector<int32_t> s(cfg.sizes.begin(), cfg.sizes.end()); d_sizes.upload(s); }
     DevBuf<RepInfo> info; info.alloc((size_t)n);
     CK(cudaMemsetAsync(info.p, 0, (size_t)n * sizeof(RepInfo), st));
     DevBuf<unsigned long long> counter; counter.alloc(1);
 
-    const bool fast_bd = !replay && cfg.P.tau == 0.0 && !cfg.P.do_gene_birth && cfg.host.nV <= 3;
+    const bool fast_bd = !domain && !replay && cfg.P.tau == 0.0 && !cfg.P.do_gene_birth && cfg.host.nV <= 3;
     const bool per_leaf = !(cfg.P.minper <= 0 && cfg.P.maxper >= cfg.P.max_leaves);
     const int sm = impl->sm_count;
 
@@ -259,7 +265,9 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         CK(cudaGetLastError());
     } else {
         // node capacity of a worker's scratch pool: typical trees fit; the rare larger ones are re-run with 8x the capacity
-        int cap = 1024; while (cap < 6 * cfg.host.nLeaves && cap < (1 << 16)) cap *= 2;
+        int ref_leaves = cfg.host.nLeaves; for (const HostModel& g : cfg.genes) ref_leaves = std::max(ref_leaves, g.nLeaves);
+        int cap = 1024; while (cap < 6 * ref_leaves && cap < (1 << 16)) cap *= 2;
+        const int mark_n = domain ? max_gene_nv : cfg.host.nV, cnt_n = domain ? max_gene_nv : std::max(1, cfg.host.nLeaves);
         long long workers = std::min<long long>((long long)sm * 1024, (n + 127) / 128 * 128);
         DevBuf<long long> redo, keep; DevBuf<unsigned long long> redo_count;
         const long long* rep_ids = nullptr; long long todo = n;
@@ -270,14 +278,17 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             max_workers = std::max<long long>(max_workers, workers);
             DevBuf<Node> s_nodes; DevBuf<int32_t> s_queue, s_pend;
             s_nodes.alloc((size_t)workers * cap); s_queue.alloc((size_t)workers * cap); s_pend.alloc((size_t)workers * cap);
-            marks.alloc((size_t)workers * cfg.host.nV); leafcnt.alloc((size_t)workers * std::max(1, cfg.host.nLeaves));
+            marks.alloc((size_t)workers * mark_n); leafcnt.alloc((size_t)workers * cnt_n);
+            if (domain) scratch_used.alloc((size_t)workers * cfg.genes.size());
             if (replay) mt_state.alloc((size_t)(workers / 32 + 1) * 624 * 32);
             FindArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = todo; a.rep_ids = rep_ids; a.rep_base = opts.offset; a.seed = seed; a.info = info.p;
             a.work_counter = counter.p; a.scratch_nodes = s_nodes.p; a.scratch_queue = s_queue.p; a.scratch_pend = s_pend.p; a.cap = cap;
             a.scratch_marks = marks.p; a.scratch_leafcnt = leafcnt.p; a.mt_state = mt_state.p; a.sizes = d_sizes.p; a.per_leaf_check = per_leaf;
+            a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
+            a.scratch_used = scratch_used.p;
             CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
             int blocks = (int)(workers / 128);
-            launch_find_general(replay, a, blocks, st);
+            launch_find_general(replay, domain, a, blocks, st);
             ++tm.launches;
             CK(cudaGetLastError());
             // replicates that ran out of node capacity are re-run with a larger pool
@@ -320,11 +331,14 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         launch_bd_build(a, (int)((n + 255) / 256), st); ++tm.launches;
     } else {
         const long long threads = (n + 127) / 128 * 128;
-        marks.alloc((size_t)threads * cfg.host.nV);
+        marks.alloc((size_t)threads * (domain ? max_gene_nv : cfg.host.nV));
+        if (domain) scratch_used.alloc((size_t)threads * cfg.genes.size());
         if (replay) mt_state.alloc((size_t)(threads / 32 + 1) * 624 * 32);
         BuildArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.info = info.p; a.node_off = node_off.p;
         a.nodes = nodes.p; a.aux = aux.p; a.aux_stride = aux_stride; a.scratch_marks = marks.p; a.scratch_leafcnt = nullptr; a.mt_state = mt_state.p;
-        launch_build_general(replay, a, (int)(threads / 128), st);
+        a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
+        a.scratch_used = scratch_used.p;
+        launch_build_general(replay, domain, a, (int)(threads / 128), st);
         ++tm.launches;
     }
     CK(cudaGetLastError());
@@ -372,10 +386,24 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         const std::string head = blob.substr(e.g2h_head_off, e.g2h_head_len);
         for (int k = 0; k < 16; ++k) { while ((int)(blob.size() % 16) != k) blob.push_back(' '); e.g2h_head_off16[k] = (int)blob.size(); blob += head; }
     }
-    { int o, l; add(cfg.host.has_tree_name ? cfg.host.tree_name : std::string("null"), o, l); gname.push_back(o); gname.push_back(l); }
-    for (int v = 0; v < cfg.host.nV; ++v) { int o, l; add(cfg.host.left[v] < 0 ? cfg.host.leaf_name[v] : std::string("null"), o, l); leafname.push_back(o); leafname.push_back(l); }
+    std::vector<int32_t> leaf_base, g2h_gene; std::vector<double> ep_times_all;
+    if (!domain) {
+        { int o, l; add(cfg.host.has_tree_name ? cfg.host.tree_name : std::string("null"), o, l); gname.push_back(o); gname.push_back(l); }
+        for (int v = 0; v < cfg.host.nV; ++v) { int o, l; add(cfg.host.left[v] < 0 ? cfg.host.leaf_name[v] : std::string("null"), o, l); leafname.push_back(o); leafname.push_back(l); }
+    } else {
+        for (const HostModel& g : cfg.genes) {
+            { int o, l; add(g.has_tree_name ? g.tree_name : std::string("null"), o, l); gname.push_back(o); gname.push_back(l); }
+            leaf_base.push_back((int32_t)(leafname.size() / 2));
+            for (int v = 0; v < g.nV; ++v) { int o, l; add(g.left[v] < 0 ? g.leaf_name[v] : std::string("null"), o, l); leafname.push_back(o); leafname.push_back(l); }
+            { int o, l; add("# GUEST-TO-HOST MAP\nHost tree:\t" + g.header + "\nGuest vertex name:\tGuest vertex ID:\tGuest vertex type:\tGuest vertex time:\tHost vertex/arc ID:\tHost epoch ID:\n", o, l);
+              g2h_gene.push_back(o); g2h_gene.push_back(l); }
+        }
+    }
     DevBuf<char> d_blob; { std::vector<char> b(blob.begin(), blob.end()); b.push_back(0); d_blob.upload(b); }
-    DevBuf<int32_t> d_gname, d_leafname; d_gname.upload(gname); d_leafname.upload(leafname);
+    std::vector<double> gene_ept; std::vector<int32_t> gene_epb;
+    for (const HostModel& gm : cfg.genes) { gene_epb.push_back((int32_t)(gene_ept.size() / 3)); for (int q = 0; q < gm.nE; ++q) { gene_ept.push_back(gm.ep_lo[q]); gene_ept.push_back(gm.ep_mid[q]); gene_ept.push_back(gm.ep_up[q]); } }
+    DevBuf<double> d_gene_ept; d_gene_ept.upload(gene_ept); DevBuf<int32_t> d_gene_epb; d_gene_epb.upload(gene_epb);
+    DevBuf<int32_t> d_gname, d_leafname, d_leaf_base, d_g2h_gene; d_gname.upload(gname); d_leafname.upload(leafname); d_leaf_base.upload(leaf_base); d_g2h_gene.upload(g2h_gene);
     DevBuf<unsigned long long> sizes, offsets; sizes.alloc((size_t)ST_COUNT * (n + 1)); offsets.alloc((size_t)ST_COUNT * (n + 1));
     CK(cudaMemsetAsync(sizes.p, 0, (size_t)ST_COUNT * (n + 1) * sizeof(unsigned long long), st));
     e.n = n; e.rep_base = opts.offset; e.info = info.p; e.node_off = node_off.p; e.nodes = nodes.p; e.aux = aux.p; e.aux_stride = aux_stride; e.T = impl->T;
@@ -383,6 +411,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     e.prefix_len = (int)std::min<size_t>(cfg.vertex_prefix.size(), sizeof(e.prefix)); memcpy(e.prefix, cfg.vertex_prefix.data(), e.prefix_len);
     if (cfg.vertex_prefix.size() > sizeof(e.prefix)) throw SgpError("vertex prefix longer than 24 bytes is not supported");
     e.blob = d_blob.p; e.gname_off = d_gname.p; e.leafname_off = d_leafname.p; e.ep_times = hd.ep_times.p;
+    e.leaf_base = d_leaf_base.p; e.g2h_gene_off = d_g2h_gene.p; e.gene_ep_times = d_gene_ept.p; e.gene_ep_base = d_gene_epb.p;
     // sizes are laid out [stream][n+1] so that one scan per stream yields offsets with the total in the last slot
     DevBuf<unsigned long long> sizes_n; sizes_n.alloc((size_t)ST_COUNT * n);
     CK(cudaMemsetAsync(sizes_n.p, 0, (size_t)ST_COUNT * n * sizeof(unsigned long long), st));

@@ -18,7 +18,9 @@ struct SimParamsHost {
 struct TreeGenConfig {
     int app = 0;              // 0 HostTreeGen, 1 GuestTreeGen, 2 DomainTreeGen
     SimParamsHost P;
-    HostModel host;
+    HostModel host;                      // HostTreeGen: the 1- or 2-leaf start tree; GuestTreeGen: species tree; DomainTreeGen: species tree
+    std::vector<HostModel> genes;        // DomainTreeGen: gene trees (sorted by file name)
+    double inter_gene = 0.5, inter_species = 0.5; bool all_genes = false;
     bool quiet = false, exclude_meta = false, append_sigma = false, is_species = false;
     std::string vertex_prefix = "H", out_prefix;
     bool has_stem_override = false; double stem_override = 0;   // HostTreeGen -stem (applied to the finished trees)

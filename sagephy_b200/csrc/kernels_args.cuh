@@ -29,6 +29,9 @@ struct FindArgs {
     uint32_t* mt_state;          // 624 words per worker, warp-interleaved (replay mode)
     const int32_t* sizes;        // -sizes list
     int per_leaf_check;
+    // DomainTreeGen: forest of gene trees (H above is then the species tree)
+    const DevHost* genes; int n_genes; int max_gene_nv; int all_genes; double inter_gene, inter_species;
+    int32_t* scratch_used;       // n_genes ints per worker
 };
 
 struct BuildArgs {
@@ -42,6 +45,8 @@ struct BuildArgs {
     int32_t* aux; long long aux_stride;    // 4 int arrays of length total_nodes: aux + k*aux_stride
     int32_t* scratch_marks; int32_t* scratch_leafcnt;
     uint32_t* mt_state;
+    const DevHost* genes; int n_genes; int max_gene_nv; int all_genes; double inter_gene, inter_species;
+    int32_t* scratch_used;
 };
 
 struct BdArgs {
@@ -87,7 +92,10 @@ struct EmitArgs {
     int g2h_head_off16[16];        // 16 copies of the header, copy k starting at a blob offset == k (mod 16): aligned 16-byte copies for any destination
     const int32_t* gname_off;      // per host tree: offset/len pairs into blob (GUEST= value / file name)
     const int32_t* leafname_off;   // per host vertex: offset/len pairs into blob (leafmap second column)
+    const int32_t* leaf_base;      // DomainTreeGen: first entry of gene tree g in leafname_off; g2h header of gene g = g2h_gene_off[2g], [2g+1]
+    const int32_t* g2h_gene_off;
     const double* ep_times;        // 3 doubles per epoch [lo, mid, up] (DISCPT index)
+    const double* gene_ep_times; const int32_t* gene_ep_base;     // DomainTreeGen: epochs of gene tree g start at gene_ep_base[g]
     uint16_t* plen;                // [ST_COUNT][aux_stride] cached piece lengths (size pass -> write pass)
     unsigned long long* dig_f;     // [2][aux_stride] cached shortest-decimal digits of branch lengths (unpruned, pruned)
     int16_t* dig_e;                // [2][aux_stride] ... and their decimal exponents

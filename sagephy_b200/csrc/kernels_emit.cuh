@@ -30,7 +30,7 @@ template <class Sink> __device__ void put_name(Sink& s, const EmitArgs& a, const
 }
 
 template <class Sink> __device__ void put_discpt(Sink& s, const EmitArgs& a, const Node& x) {
-    const double* t = a.ep_times + 3 * (size_t)x.epoch;
+    const double* t = a.app == 2 ? a.gene_ep_times + 3 * (size_t)(a.gene_ep_base[x.gtree] + x.epoch) : a.ep_times + 3 * (size_t)x.epoch;
     int j = 0; while (j < 3) { if (t[j] >= x.abstime) break; ++j; }
     put_str(s, "DISCPT=("); put_i64(s, x.epoch); s.put(','); put_i64(s, j); s.put(')');
 }
@@ -93,7 +93,7 @@ template <bool PRUNED, class Sink> __device__ void put_tree_piece(Sink& s, const
 template <class Sink> __device__ void put_kv_int(Sink& s, const char* k, long long v) { put_str(s, k); put_i64(s, v); s.put('\n'); }
 template <class Sink> __device__ void put_kv_dbl(Sink& s, const EmitArgs& a, const char* k, double v) { put_str(s, k); put_double(s, a.T, v); s.put('\n'); }
 
-__device__ __forceinline__ int info_lines(const EmitArgs& a, bool pruned) { return a.app == 0 ? (pruned ? 8 : 10) : 18; }
+__device__ __forceinline__ int info_lines(const EmitArgs& a, bool pruned) { return a.app == 0 ? (pruned ? 8 : 10) : a.app == 1 ? 18 : 30; }
 
 // line `ln` of an .info file. Lanes format different lines in the same trip, so the line-specific part only SELECTS data
 // (key string, integer or double operand); the expensive work (round8, shortest-digit conversion) runs on one shared path.
@@ -119,6 +119,27 @@ template <bool PRUNED, class Sink> __device__ void put_info_line(Sink& s, const 
             case 8: key = "Birth ML estimate:\t"; is_double = true; ratio = true; num = (double)births; break;
             default: key = "Death ML estimate:\t"; is_double = true; ratio = true; num = (double)deaths; break;
         }
+    } else if (a.app == 2) {
+        // DomainTreeInHostTreeCreator.getInfo :1128-1252
+        static const char* const kCnt[8] = {"No. of additive transfers intragene intraspecies:\t", "No. of additive transfers intragene interspecies:\t",
+            "No. of additive transfers intergene intraspecies:\t", "No. of additive transfers intergene interspecies:\t",
+            "No. of replacing transfers intragene intraspecies:\t", "No. of replacing transfers intragene interspecies:\t",
+            "No. of replacing transfers intergene intraspecies:\t", "No. of replacing transfers intergene interspecies:\t"};
+        static const char* const kMl[8] = {"Additive Transfer Intragene Intraspecies ML estimate:\t", "Additive Transfer Intragene Interspecies ML estimate:\t",
+            "Additive Transfer Intergene Intraspecies ML estimate:\t", "Additive Transfer Intergene Interspecies ML estimate:\t",
+            "Replacing Transfer Intragene Intraspecies ML estimate:\t", "Replacing Transfer Intragene Interspecies ML estimate:\t",
+            "Replacing Transfer Intergene Intraspecies ML estimate:\t", "Replacing Transfer Intergene Interspecies ML estimate:\t"};
+        if (ln == 5) { key = "No. of co-divergences:\t"; iv = c[EV_CODIVERGENCE]; }
+        else if (ln == 6) { key = "No. of duplications:\t"; iv = c[EV_DUPLICATION]; }
+        else if (ln == 7) { key = "No. of losses:\t"; iv = c[EV_LOSS]; }
+        else if (ln == 8) { key = "No. of replacing losses:\t"; iv = c[EV_REPLACING_LOSS]; }
+        else if (ln <= 16) { key = kCnt[ln - 9]; iv = c[EV_AT_GG_SS + ln - 9]; }
+        else if (ln == 17) { key = "Total branch time:\t"; is_double = true; num = PRUNED ? inf.total_p : inf.total_u; }
+        else if (ln == 18) { key = "Total branch time beneath host stem:\t"; is_double = true; num = PRUNED ? inf.beneath_p : inf.beneath_u; }
+        else if (ln == 19) { key = "Duplication ML estimate:\t"; is_double = true; ratio = true; num = (double)c[EV_DUPLICATION]; }
+        else if (ln == 20) { key = "Loss ML estimate:\t"; is_double = true; ratio = true; num = (double)c[EV_LOSS]; }
+        else if (ln == 21) { key = "Replacing Loss ML estimate:\t"; is_double = true; ratio = true; num = (double)c[EV_REPLACING_LOSS]; }
+        else { key = kMl[ln - 22]; is_double = true; ratio = true; num = (double)c[EV_AT_GG_SS + ln - 22]; }
     } else {
         switch (ln) {
             case 5: key = "No. of speciations:\t"; iv = c[EV_SPECIATION]; break;
@@ -169,7 +190,9 @@ template <bool PRUNED, class Sink> __device__ void put_leafmap_row(Sink& s, cons
     const bool leaf = PRUNED ? x.p_left < 0 : x.left < 0;
     if (!leaf || !(x.event == EV_LEAF || x.event == EV_UNSAMPLED_LEAF)) return;
     put_name(s, a, x); s.put('\t');
-    put_blob(s, a.blob, a.leafname_off[2 * x.sigma], a.leafname_off[2 * x.sigma + 1]);
+    const int li = (a.app == 2 ? a.leaf_base[x.gtree] : 0) + x.sigma;
+    put_blob(s, a.blob, a.leafname_off[2 * li], a.leafname_off[2 * li + 1]);
+    if (a.app == 2) { s.put('\t'); put_blob(s, a.blob, a.gname_off[2 * x.gtree], a.gname_off[2 * x.gtree + 1]); }    // DomainTreeInHostTreeCreator.getLeafMap :1266
     s.put('\n');
 }
 
@@ -313,15 +336,21 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) k_emit(EmitArgs a) {
             }
             if constexpr (st == ST_UNPRUNED_G2H || st == ST_PRUNED_G2H) {
                 constexpr bool pr = st == ST_PRUNED_G2H;
-                if (WRITE) {
+                int head_len = a.g2h_head_len;
+                if (a.app == 2) {
+                    // DomainTreeGen prints the gene tree of the ROOT vertex as "Host tree" (getSigma :1279)
+                    const int rg = N[pr ? (inf.p_root >= 0 ? inf.p_root : inf.root) : inf.root].gtree;
+                    head_len = a.g2h_gene_off[2 * rg + 1];
+                    if (WRITE) for (int i = lane; i < head_len; i += 32) base[i] = a.blob[a.g2h_gene_off[2 * rg] + i];
+                } else if (WRITE) {
                     const int mis = (int)(reinterpret_cast<unsigned long long>(base) & 15ull);
                     flush_stage(a.blob + a.g2h_head_off16[mis] - mis, mis, base, (unsigned)a.g2h_head_len);      // source congruent to destination mod 16
                 }
-                bytes = (unsigned long long)a.g2h_head_len;
+                bytes = (unsigned long long)head_len;
                 const int np = pr ? (inf.p_root >= 0 ? inf.n_p : 0) : inf.n_u;
                 const int32_t* bfs = pr ? bfsP : bfsU;
                 auto pc = [&](auto& s, int k) { put_g2h_row(s, a, N, bfs, k); };
-                if (WRITE) bytes += emit_pieces<true>(np, base + a.g2h_head_len, stage, pc, ld, no_store);
+                if (WRITE) bytes += emit_pieces<true>(np, base + head_len, stage, pc, ld, no_store);
                 else bytes += emit_pieces<false>(np, nullptr, stage, pc, no_load, sd);
             }
             if constexpr (st == ST_UNPRUNED_LEAFMAP || st == ST_PRUNED_LEAFMAP) {

@@ -1,21 +1,23 @@
 // Sampling kernels (K1): "find" passes decide which attempt of each replicate is accepted, "build" passes regenerate
 // that attempt into the exactly-sized node arena.
 #pragma once
-#include "sim.cuh"
+#include "sim_domain.cuh"
 
 namespace sgp {
 
 
-template <bool REPLAY>
+template <bool REPLAY, bool DOMAIN>
 __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
     const int worker = blockIdx.x * blockDim.x + threadIdx.x;
     SimWork W;
     W.nodes = a.scratch_nodes + (size_t)worker * a.cap; W.cap = a.cap;
     W.queue = a.scratch_queue + (size_t)worker * a.cap; W.pend = a.scratch_pend + (size_t)worker * a.cap;
-    W.marks = a.scratch_marks + (size_t)worker * a.H.nV;
-    W.leaf_cnt = a.per_leaf_check ? a.scratch_leafcnt + (size_t)worker * a.H.nLeaves : nullptr;
+    const int mark_n = DOMAIN ? a.max_gene_nv : a.H.nV, cnt_n = DOMAIN ? a.max_gene_nv : a.H.nLeaves;
+    W.marks = a.scratch_marks + (size_t)worker * mark_n;
+    W.leaf_cnt = a.per_leaf_check ? a.scratch_leafcnt + (size_t)worker * cnt_n : nullptr;
     W.mark_gen = 0;
-    for (int i = 0; i < a.H.nV; ++i) W.marks[i] = 0;
+    for (int i = 0; i < mark_n; ++i) W.marks[i] = 0;
+    DomainEnv E{a.genes, a.n_genes, a.inter_gene, a.inter_species, DOMAIN ? a.scratch_used + (size_t)worker * a.n_genes : nullptr};
     MtStream mt; PhiloxStream ph;
     if (REPLAY) { mt.mt = a.mt_state + (size_t)(worker >> 5) * 624 * 32 + (worker & 31); mt.stride = 32; }
     for (;;) {
@@ -34,12 +36,16 @@ __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
             uint64_t pos = 0;
             if (REPLAY) pos = mt.position(); else ph.begin_attempt((uint32_t)attempts);
             int n = 0, root = -1;
-            int st = REPLAY ? simulate_attempt(mt, a.P, a.H, a.T, W, n, root) : simulate_attempt(ph, a.P, a.H, a.T, W, n, root);
+            int st;
+            if (DOMAIN) st = REPLAY ? simulate_attempt_domain(mt, a.P, E, a.T, W, n, root) : simulate_attempt_domain(ph, a.P, E, a.T, W, n, root);
+            else st = REPLAY ? simulate_attempt(mt, a.P, a.H, a.T, W, n, root) : simulate_attempt(ph, a.P, a.H, a.T, W, n, root);
             verts += (uint64_t)n;
             if (st != REP_OK) { inf.status = st; break; }
             ++attempts;
             int sampled = 0;
-            if (attempt_ok(a.P, a.H, W, root, inf.exact, &sampled)) {
+            const bool ok = DOMAIN ? attempt_ok_domain(a.P, a.H, E, W, root, inf.exact, a.max_gene_nv, a.per_leaf_check != 0, a.all_genes != 0, &sampled)
+                                   : attempt_ok(a.P, a.H, W, root, inf.exact, &sampled);
+            if (ok) {
                 inf.status = REP_OK; inf.n_pool = n; inf.sampled_leaves = sampled;
                 if (REPLAY) { inf.acc_attempt = (uint32_t)pos; inf.acc_hi = (uint32_t)(pos >> 32); } else { inf.acc_attempt = (uint32_t)(attempts - 1); inf.acc_hi = 0; }
                 ++attempts;     // GuestTreeMachina.java:107
@@ -52,7 +58,7 @@ __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
 }
 
 
-template <bool REPLAY>
+template <bool REPLAY, bool DOMAIN>
 __global__ void __launch_bounds__(128) k_build_general(BuildArgs a) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int worker = blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,18 +69,20 @@ __global__ void __launch_bounds__(128) k_build_general(BuildArgs a) {
     SimWork W;
     W.nodes = a.nodes + off; W.cap = inf.n_pool;
     W.queue = a.aux + off; W.pend = a.aux + a.aux_stride + off;
-    W.marks = a.scratch_marks + (size_t)worker * a.H.nV; W.leaf_cnt = nullptr; W.mark_gen = 0;
-    for (int i = 0; i < a.H.nV; ++i) W.marks[i] = 0;
+    const int mark_n = DOMAIN ? a.max_gene_nv : a.H.nV;
+    W.marks = a.scratch_marks + (size_t)worker * mark_n; W.leaf_cnt = nullptr; W.mark_gen = 0;
+    for (int i = 0; i < mark_n; ++i) W.marks[i] = 0;
+    DomainEnv E{a.genes, a.n_genes, a.inter_gene, a.inter_species, DOMAIN ? a.scratch_used + (size_t)worker * a.n_genes : nullptr};
     int n = 0, root = -1, st;
     const long long gid = a.rep_base + r;
     if (REPLAY) {
         MtStream mt; mt.mt = a.mt_state + (size_t)(worker >> 5) * 624 * 32 + (worker & 31); mt.stride = 32;
         uint32_t key[4]; seed_words_i64((long long)a.seed + gid, key); mt.seed(key);
         mt.skip(((uint64_t)inf.acc_hi << 32) | inf.acc_attempt);
-        st = simulate_attempt(mt, a.P, a.H, a.T, W, n, root);
+        st = DOMAIN ? simulate_attempt_domain(mt, a.P, E, a.T, W, n, root) : simulate_attempt(mt, a.P, a.H, a.T, W, n, root);
     } else {
         PhiloxStream ph; ph.init(a.seed, (uint64_t)gid, inf.acc_attempt);
-        st = simulate_attempt(ph, a.P, a.H, a.T, W, n, root);
+        st = DOMAIN ? simulate_attempt_domain(ph, a.P, E, a.T, W, n, root) : simulate_attempt(ph, a.P, a.H, a.T, W, n, root);
     }
     if (st != REP_OK || n != inf.n_pool) { inf.status = REP_MODEL_ERROR; return; }
     inf.root = root;

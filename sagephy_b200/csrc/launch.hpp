@@ -4,8 +4,8 @@
 #include "kernels_args.cuh"
 
 namespace sgp {
-void launch_find_general(bool replay, const FindArgs& a, int blocks, cudaStream_t st);
-void launch_build_general(bool replay, const BuildArgs& a, int blocks, cudaStream_t st);
+void launch_find_general(bool replay, bool domain, const FindArgs& a, int blocks, cudaStream_t st);
+void launch_build_general(bool replay, bool domain, const BuildArgs& a, int blocks, cudaStream_t st);
 void launch_bd_find(const BdArgs& a, int blocks, cudaStream_t st);
 void launch_bd_build(const BdArgs& a, int blocks, cudaStream_t st);
 void launch_label_prune(const LabelArgs& a, int blocks, cudaStream_t st);

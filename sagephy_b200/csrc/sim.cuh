@@ -64,17 +64,17 @@ __device__ __forceinline__ bool dd_gt(DD a, DD b) { return a.hi > b.hi || (a.hi 
 // Math.pow(Math.E, y) through the fdlibm pow restatement (bit-identical to the oracle's)
 static __device__ __noinline__ double pow_e(double y) { return jpow(2.718281828459045, y); }
 
-// Epoch.sampleArc with include == true. marks[x] == mark_gen flags an "empty" arc. Returns -5 if no candidate.
+// Epoch.sampleArc (include: recipients must carry the same / a different HOST tag as the donor). marks[x] == mark_gen flags an "empty" arc. Returns -5 if no candidate.
 template <class RNG>
-__device__ int sample_arc(RNG& rng, const SimParams& P, const DevHost& H, int epoch, int donor, double t, const int32_t* marks, int mark_gen) {
+__device__ int sample_arc(RNG& rng, const SimParams& P, const DevHost& H, int epoch, int donor, double t, const int32_t* marks, int mark_gen, bool include = true) {
     const int a0 = H.ep_off[epoch], a1 = H.ep_off[epoch + 1];
     const int tag = H.host_tag[donor];
     if (P.bias == 0) {
         int k = 0;
-        for (int j = a0; j < a1; ++j) { int x = H.ep_arcs[j]; if (x != donor && !(marks && marks[x] == mark_gen) && H.host_tag[x] == tag) ++k; }
+        for (int j = a0; j < a1; ++j) { int x = H.ep_arcs[j]; if (x != donor && !(marks && marks[x] == mark_gen) && ((H.host_tag[x] == tag) == include)) ++k; }
         if (k < 1) return -5;
         int pick = rng.next_int(k);
-        for (int j = a0; j < a1; ++j) { int x = H.ep_arcs[j]; if (x != donor && !(marks && marks[x] == mark_gen) && H.host_tag[x] == tag) { if (pick == 0) return x; --pick; } }
+        for (int j = a0; j < a1; ++j) { int x = H.ep_arcs[j]; if (x != donor && !(marks && marks[x] == mark_gen) && ((H.host_tag[x] == tag) == include)) { if (pick == 0) return x; --pick; } }
         return -5;
     }
     // biased: weights in epoch arc order; key = running total; pick the first key > total * U, where an arc with
@@ -82,7 +82,7 @@ __device__ int sample_arc(RNG& rng, const SimParams& P, const DevHost& H, int ep
     DD total{0.0, 0.0}; int k = 0;
     for (int j = a0; j < a1; ++j) {
         int x = H.ep_arcs[j];
-        if (x == donor || (marks && marks[x] == mark_gen) || H.host_tag[x] != tag) continue;
+        if (x == donor || (marks && marks[x] == mark_gen) || ((H.host_tag[x] == tag) != include)) continue;
         double dist = XMUL(2.0, XSUB(H.lca_time[(size_t)donor * H.nV + x], t));
         double w = (P.bias == 2) ? XMUL(P.bias_rate, pow_e(XMUL(-P.bias_rate, dist))) : XDIV(1.0, dist);
         if (w == dbl_inf()) w = 1.7976931348623157e308;
@@ -93,7 +93,7 @@ __device__ int sample_arc(RNG& rng, const SimParams& P, const DevHost& H, int ep
     DD cum{0.0, 0.0}; int chosen = -5; bool found = false;
     for (int j = a0; j < a1; ++j) {
         int x = H.ep_arcs[j];
-        if (x == donor || (marks && marks[x] == mark_gen) || H.host_tag[x] != tag) continue;
+        if (x == donor || (marks && marks[x] == mark_gen) || ((H.host_tag[x] == tag) != include)) continue;
         double dist = XMUL(2.0, XSUB(H.lca_time[(size_t)donor * H.nV + x], t));
         double w = (P.bias == 2) ? XMUL(P.bias_rate, pow_e(XMUL(-P.bias_rate, dist))) : XDIV(1.0, dist);
         if (w == dbl_inf()) w = 1.7976931348623157e308;

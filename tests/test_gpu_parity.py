@@ -322,3 +322,46 @@ def test_branch_relaxer_philox_matches_reference_distributions(ctx):
     g = b.values(0).reshape(n, nv)[b.rep_status == 0].ravel()
     assert abs(g.mean() - 1.0) < 0.01 and abs(g.var() - 0.5) < 0.02
     assert stats.kstest(g[::7], "gamma", args=(2, 0, 0.5)).pvalue > 0.001
+
+
+# ---- DomainTreeGen ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gene_dir(tmp_path_factory):
+    """Gene trees for the domain tests: pruned GuestTreeGen trees (oracle) on HOST8, as files gene1.tree..gene4.tree."""
+    d = tmp_path_factory.mktemp("genes")
+    for i in range(1, 5):
+        f = oracle_run("GuestTreeGen", ["-s", str(i), "-db", "none", HOST8, "0.4", "0.2", "0.2", "g"])["files"]
+        (d / f"gene{i}.tree").write_bytes(f["g.pruned.tree"])
+    return str(d)
+
+
+DOMAIN_CASES = [
+    ["-s", "1"],                                               # defaults: -db none, -ig 0.5, -is 0.5, -rt 0.5
+    ["-s", "2", "-ig", "0.9", "-is", "0.7", "-all"],            # README example shape: mostly inter-gene, all gene trees required
+    ["-s", "3", "-rt", "1.0", "-ig", "0.3"],                     # replacing only
+    ["-s", "4", "-rt", "0.0", "-is", "1.0"],                     # additive, always inter-species (many swaps inside one species)
+    ["-s", "5", "-db", "simple", "-ig", "0.2"],                  # distance-biased intra-gene recipients
+    ["-s", "6", "-db", "exponential", "-dbr", "2.0", "-ig", "0.0"],
+    ["-s", "7", "-dbs", "-dbc", "2.0", "-p", "0.8"],             # domain birth sampling
+    ["-s", "8", "-nox", "-vp", "Dom", "-min", "3", "-max", "60", "-maxper", "40"],
+]
+
+
+@pytest.mark.parametrize("opts", DOMAIN_CASES, ids=[" ".join(o[2:]) or "defaults" for o in DOMAIN_CASES])
+def test_domain_tree_gen_replay_is_byte_exact(ctx, gene_dir, opts):
+    args = opts + [HOST8, gene_dir, "0.4", "0.3", "0.9", "o"]
+    assert_replay_parity(ctx, "DomainTreeGen", args, 24, "o")
+
+
+def test_domain_tree_gen_philox_matches_oracle_distributions(ctx, gene_dir):
+    n = 20000
+    args = ["-s", "31", "-ig", "0.6", "-is", "0.5", HOST8, gene_dir, "0.4", "0.3", "0.8", "x"]
+    b = ctx.run("DomainTreeGen", args, n=n, rng=sg.RNG_PHILOX, stream_mask=0b0010)
+    assert (b.rep_status == 0).all()
+    sec, st = oracle_batch("DomainTreeGen", args, 0, n)
+    assert chi2_two_sample_ok(b.sampled_leaves.astype(float), st[:, 4])
+    assert ks_ok(b.total_times, st[:, 6])
+    ev = b.event_counts
+    for e in (1, 4, 5, 6, 9, 10, 11, 12, 13, 14, 15, 16):
+        assert chi2_two_sample_ok(ev[:, e].astype(float), st[:, 9 + e]), e
+    assert chi2_two_sample_ok(b.attempts.astype(float), st[:, 0])
