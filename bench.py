@@ -85,7 +85,7 @@ def run_reference_arm(args):
         return
     cores = os.cpu_count() or 1
     procs = max(1, cores)
-    per_step = max(procs * 4, 64)
+    per_step = max(procs * 64, 256)         # ~1-2 s of work on all host cores per step
     for _ in range(args.warmup):
         cpu_reference(max(procs, per_step // 8), procs)
     t0 = time.perf_counter(); ok = 0
