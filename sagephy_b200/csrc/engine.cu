@@ -242,6 +242,10 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     for (const HostModel& g : cfg.genes) { gene_dev.emplace_back(new HostOnDevice()); gene_dev.back()->upload(g); gene_views.push_back(gene_dev.back()->view); max_gene_nv = std::max(max_gene_nv, g.nV); }
     max_gene_nv = std::max(max_gene_nv, cfg.host.nV);
     DevBuf<DevHost> d_genes; d_genes.upload(gene_views);
+    std::vector<double> fl_lo, fl_up; std::vector<int32_t> fl_tag, fl_start;
+    for (const HostModel& g : cfg.genes) { fl_start.push_back((int32_t)fl_lo.size()); for (int v = 0; v < g.nV; ++v) { fl_lo.push_back(g.vtime[v]); fl_up.push_back(g.ep_up[g.v2e[v]]); fl_tag.push_back(g.host_tag[v]); } }
+    fl_start.push_back((int32_t)fl_lo.size());
+    DevBuf<double> d_fl_lo, d_fl_up; DevBuf<int32_t> d_fl_tag, d_fl_start; d_fl_lo.upload(fl_lo); d_fl_up.upload(fl_up); d_fl_tag.upload(fl_tag); d_fl_start.upload(fl_start);
     DevBuf<int32_t> scratch_used;
     DevBuf<int32_t> d_sizes; { std::vector<int32_t> s(cfg.sizes.begin(), cfg.sizes.end()); d_sizes.upload(s); }
     DevBuf<RepInfo> info; info.alloc((size_t)n);
@@ -285,7 +289,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             a.work_counter = counter.p; a.scratch_nodes = s_nodes.p; a.scratch_queue = s_queue.p; a.scratch_pend = s_pend.p; a.cap = cap;
             a.scratch_marks = marks.p; a.scratch_leafcnt = leafcnt.p; a.mt_state = mt_state.p; a.sizes = d_sizes.p; a.per_leaf_check = per_leaf;
             a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
-            a.scratch_used = scratch_used.p;
+            a.scratch_used = scratch_used.p; a.fl_lo = d_fl_lo.p; a.fl_up = d_fl_up.p; a.fl_tag = d_fl_tag.p; a.fl_start = d_fl_start.p;
             CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
             int blocks = (int)(workers / 128);
             launch_find_general(replay, domain, a, blocks, st);
@@ -337,7 +341,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         BuildArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.info = info.p; a.node_off = node_off.p;
         a.nodes = nodes.p; a.aux = aux.p; a.aux_stride = aux_stride; a.scratch_marks = marks.p; a.scratch_leafcnt = nullptr; a.mt_state = mt_state.p;
         a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
-        a.scratch_used = scratch_used.p;
+        a.scratch_used = scratch_used.p; a.fl_lo = d_fl_lo.p; a.fl_up = d_fl_up.p; a.fl_tag = d_fl_tag.p; a.fl_start = d_fl_start.p;
         launch_build_general(replay, domain, a, (int)(threads / 128), st);
         ++tm.launches;
     }
