@@ -107,6 +107,11 @@ const uint64_t* sgp_batch_stream_offsets(sgp_batch* b, int stream);      /* n+1 
 /* Copies stream bytes / the n+1 offsets from HBM into a caller-owned host buffer (pinned memory gives full PCIe rate). */
 sgp_status sgp_batch_copy_stream(sgp_batch* b, int stream, void* dst, uint64_t dst_capacity);
 sgp_status sgp_batch_copy_offsets(sgp_batch* b, int stream, uint64_t* dst /* n+1 */);
+/* Asynchronous variants: enqueue the copy on the context's copy stream so that it overlaps the kernels of the next
+ * sgp_app_run on the same context (dst must be pinned). The batch must stay alive until sgp_context_wait_copies returns. */
+sgp_status sgp_batch_copy_stream_async(sgp_batch* b, int stream, void* dst, uint64_t dst_capacity);
+sgp_status sgp_batch_copy_offsets_async(sgp_batch* b, int stream, uint64_t* dst /* n+1 */);
+sgp_status sgp_context_wait_copies(sgp_context* ctx);
 uint32_t sgp_batch_stream_mask(const sgp_batch* b);                      /* bit s set = stream s was emitted */
 /* BranchRelaxer: flat per-branch arrays (replicate-major, vertex-id order): which = 0 rates, 1 relaxed lengths. */
 const double* sgp_batch_values(sgp_batch* b, int which, int64_t* count);
@@ -129,7 +134,7 @@ void sgp_batch_free(sgp_batch* b);
 
 /* Probes used by the parity tests: run the device implementations of the Java-exact primitives on `n` inputs. */
 sgp_status sgp_probe_double_to_string(sgp_context* ctx, const double* v, int64_t n, char* out /* n*32 bytes, NUL padded */);
-sgp_status sgp_probe_math(sgp_context* ctx, int fn /* 0 log, 1 log10, 2 exp, 3 round8, 4 normal quantile, 5 pow(x,0.37), 6 chi2 quantile k=4, 7 chi2 quantile k=0.25, 8 pow(e,x) */, const double* v, int64_t n, double* out);
+sgp_status sgp_probe_math(sgp_context* ctx, int fn /* 0 log, 1 log10, 2 exp, 3 round8, 4 normal quantile, 5 pow(x,0.37), 6 chi2 quantile k=4, 7 chi2 quantile k=0.25, 8 pow(e,x), 9 throughput-mode log on (0,1] */, const double* v, int64_t n, double* out);
 sgp_status sgp_probe_mt(sgp_context* ctx, int64_t seed, int64_t n_words, uint32_t* out_words);
 /* Issue-rate microbenchmarks (roofline denominators for the sampler), giga warp-instructions per second, whole chip:
  * independent DFMA chains, independent IMAD chains, and an IMAD + SHF + LOP3 mix (what Philox is made of). */

@@ -29,7 +29,7 @@ STATUS_OK, STATUS_USAGE = 0, 6
 # every symbol include/sagephy_b200.h declares (checked by the CPU test-suite)
 EXPORTED_SYMBOLS = (
     "sgp_context_create", "sgp_context_destroy", "sgp_last_error", "sgp_app_run", "sgp_batch_n", "sgp_batch_stream_data",
-    "sgp_batch_stream_device_data", "sgp_batch_stream_offsets", "sgp_batch_copy_stream", "sgp_batch_copy_offsets", "sgp_batch_stream_mask", "sgp_batch_values", "sgp_batch_stream_bytes", "sgp_batch_stream_suffix",
+    "sgp_batch_stream_device_data", "sgp_batch_stream_offsets", "sgp_batch_copy_stream", "sgp_batch_copy_offsets", "sgp_batch_copy_stream_async", "sgp_batch_copy_offsets_async", "sgp_context_wait_copies", "sgp_batch_stream_mask", "sgp_batch_values", "sgp_batch_stream_bytes", "sgp_batch_stream_suffix",
     "sgp_batch_status", "sgp_batch_attempts", "sgp_batch_sampled_leaves", "sgp_batch_root_times", "sgp_batch_total_times",
     "sgp_batch_event_counts", "sgp_batch_stdout", "sgp_batch_stderr", "sgp_batch_out_prefix", "sgp_batch_summary",
     "sgp_batch_timings", "sgp_batch_write_files", "sgp_batch_free", "sgp_probe_double_to_string", "sgp_probe_math",
@@ -74,6 +74,9 @@ def load_library() -> C.CDLL:
     L.sgp_batch_stream_offsets.argtypes = [vp, C.c_int]; L.sgp_batch_stream_offsets.restype = C.POINTER(C.c_uint64)
     L.sgp_batch_copy_stream.argtypes = [vp, C.c_int, vp, C.c_uint64]; L.sgp_batch_copy_stream.restype = C.c_int
     L.sgp_batch_copy_offsets.argtypes = [vp, C.c_int, vp]; L.sgp_batch_copy_offsets.restype = C.c_int
+    L.sgp_batch_copy_stream_async.argtypes = [vp, C.c_int, vp, C.c_uint64]; L.sgp_batch_copy_stream_async.restype = C.c_int
+    L.sgp_batch_copy_offsets_async.argtypes = [vp, C.c_int, vp]; L.sgp_batch_copy_offsets_async.restype = C.c_int
+    L.sgp_context_wait_copies.argtypes = [vp]; L.sgp_context_wait_copies.restype = C.c_int
     L.sgp_batch_stream_mask.argtypes = [vp]; L.sgp_batch_stream_mask.restype = C.c_uint32
     L.sgp_batch_values.argtypes = [vp, C.c_int, C.POINTER(C.c_int64)]; L.sgp_batch_values.restype = C.POINTER(C.c_double)
     L.sgp_batch_stream_bytes.argtypes = [vp, C.c_int]; L.sgp_batch_stream_bytes.restype = C.c_uint64
@@ -178,6 +181,18 @@ class Batch:
             raise SagephyError(f"sgp_batch_copy_stream failed ({rc})")
         return self.stream_bytes(s)
 
+    def copy_stream_into_async(self, s: int, dst_ptr: int, capacity: int) -> int:
+        """Enqueues the copy on the context's copy stream (overlaps the next run); call Context.wait_copies() before reading."""
+        rc = self._lib.sgp_batch_copy_stream_async(self._h, s, C.c_void_p(dst_ptr), capacity)
+        if rc != 0:
+            raise SagephyError(f"sgp_batch_copy_stream_async failed ({rc})")
+        return self.stream_bytes(s)
+
+    def copy_offsets_into_async(self, s: int, dst_ptr: int) -> None:
+        rc = self._lib.sgp_batch_copy_offsets_async(self._h, s, C.c_void_p(dst_ptr))
+        if rc != 0:
+            raise SagephyError(f"sgp_batch_copy_offsets_async failed ({rc})")
+
     def copy_offsets_into(self, s: int, dst_ptr: int) -> None:
         rc = self._lib.sgp_batch_copy_offsets(self._h, s, C.c_void_p(dst_ptr))
         if rc != 0:
@@ -274,6 +289,9 @@ class Context:
         if check and rc not in (STATUS_OK, STATUS_USAGE):
             raise SagephyError(f"{app} failed ({rc}): {self._lib.sgp_last_error(self._h).decode()} {b.stderr if h else ''}")
         return b
+
+    def wait_copies(self):
+        self._lib.sgp_context_wait_copies(self._h)
 
     # probes (parity tests of the device-side Java-exact primitives)
     def double_to_string(self, values) -> list:

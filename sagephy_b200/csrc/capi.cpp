@@ -8,7 +8,7 @@
 using namespace sgp;
 
 struct sgp_context { std::unique_ptr<Context> ctx; std::string last_error; };
-struct sgp_batch { Batch b; std::string stdout_cache; bool stdout_ready = false; };
+struct sgp_batch { Batch b; std::string stdout_cache; bool stdout_ready = false; sgp_context* owner = nullptr; };
 
 namespace { thread_local std::string g_create_error; }
 
@@ -36,7 +36,7 @@ sgp_status sgp_app_run(sgp_context* ctx, const char* app, int argc, const char* 
     *out = nullptr;
     sgp_batch_opts o{}; if (opts) o = *opts; if (o.n_replicates <= 0) o.n_replicates = 1;
     std::vector<std::string> args; for (int i = 0; i < argc; ++i) args.emplace_back(argv[i] ? argv[i] : "");
-    auto* b = new sgp_batch();
+    auto* b = new sgp_batch(); b->owner = ctx;
     try {
         if (std::string(app) == "BranchRelaxer") {
             RelaxConfig rc; AppResult rr;
@@ -92,6 +92,15 @@ sgp_status sgp_batch_copy_offsets(sgp_batch* b, int s, uint64_t* dst) {
     if (!b || s < 0 || s >= 8 || !dst || !b->b.d_offsets) return SGP_ERR_INVALID_ARGUMENT;
     return b->b.copy_offsets_to(s, (unsigned long long*)dst) ? SGP_OK : SGP_ERR_NO_DEVICE;
 }
+sgp_status sgp_batch_copy_stream_async(sgp_batch* b, int s, void* dst, uint64_t cap) {
+    if (!b || !b->owner || s < 0 || s >= 8 || !dst || cap < b->b.stream_bytes[s]) return SGP_ERR_INVALID_ARGUMENT;
+    return b->b.copy_stream_to_async(s, dst, b->owner->ctx->copy_stream()) ? SGP_OK : SGP_ERR_NO_DEVICE;
+}
+sgp_status sgp_batch_copy_offsets_async(sgp_batch* b, int s, uint64_t* dst) {
+    if (!b || !b->owner || s < 0 || s >= 8 || !dst || !b->b.d_offsets) return SGP_ERR_INVALID_ARGUMENT;
+    return b->b.copy_offsets_to_async(s, (unsigned long long*)dst, b->owner->ctx->copy_stream()) ? SGP_OK : SGP_ERR_NO_DEVICE;
+}
+sgp_status sgp_context_wait_copies(sgp_context* ctx) { if (!ctx) return SGP_ERR_INVALID_ARGUMENT; ctx->ctx->wait_copies(); return SGP_OK; }
 uint32_t sgp_batch_stream_mask(const sgp_batch* b) { return b ? b->b.stream_mask : 0u; }
 const double* sgp_batch_values(sgp_batch* b, int which, int64_t* count) {
     if (!b) return nullptr;

@@ -11,6 +11,7 @@
 #include "launch.hpp"
 #include "rng.cuh"
 #include "jmath_ext.cuh"
+#include "sim.cuh"
 
 namespace sgp {
 
@@ -91,7 +92,7 @@ __global__ void k_probe_math(int fn, const double* v, long long n, double* out, 
     double x = v[i];
     int err = 0;
     out[i] = fn == 0 ? jlog(x) : fn == 1 ? jlog10(x) : fn == 2 ? jexp(x) : fn == 3 ? round_sig(T, x, 8) : fn == 4 ? jnormal_quantile(x)
-           : fn == 5 ? jpow(x, 0.37) : fn == 6 ? jchi2_quantile(x, 4.0, &err) : fn == 7 ? jchi2_quantile(x, 0.25, &err) : jpow(2.718281828459045, x);
+           : fn == 5 ? jpow(x, 0.37) : fn == 6 ? jchi2_quantile(x, 4.0, &err) : fn == 7 ? jchi2_quantile(x, 0.25, &err) : fn == 8 ? jpow(2.718281828459045, x) : log_unit(x);
 }
 __global__ void k_probe_mt(long long seed, long long n, uint32_t* out, uint32_t* state) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -133,6 +134,7 @@ struct EventTimer {
 
 struct Context::Impl {
     cudaStream_t stream = nullptr;
+    cudaStream_t copy = nullptr;
     DevBuf<unsigned long long> g_table; DevBuf<double> p10;
     MathTables T{};
     int sm_count = 148;
@@ -145,6 +147,7 @@ Context::Context(int dev) : device(dev), impl(new Impl()) {
     if (dev < 0 || dev >= count) throw SgpError("invalid CUDA device index " + std::to_string(dev));
     CK(cudaSetDevice(dev));
     CK(cudaStreamCreate(&impl->stream));
+    CK(cudaStreamCreateWithFlags(&impl->copy, cudaStreamNonBlocking));
     g_alloc_stream = impl->stream;
     { cudaMemPool_t pool; CK(cudaDeviceGetDefaultMemPool(&pool, dev)); unsigned long long thr = ~0ull; CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr)); }
     std::vector<unsigned long long> g(d2s_g_table(), d2s_g_table() + d2s_g_table_len());
@@ -159,6 +162,7 @@ Context::~Context() {
         cudaSetDevice(device); g_alloc_stream = impl->stream;
         impl->g_table.alloc(0); impl->p10.alloc(0);       // release pool memory before the stream goes away
         cudaStreamSynchronize(impl->stream); cudaStreamDestroy(impl->stream); impl->stream = nullptr; g_alloc_stream = nullptr;
+        if (impl->copy) { cudaStreamSynchronize(impl->copy); cudaStreamDestroy(impl->copy); impl->copy = nullptr; }
     }
 }
 
@@ -185,6 +189,17 @@ bool Batch::copy_stream_to(int s, void* dst) {
     cudaSetDevice(device);
     if (!stream_bytes[s]) return true;
     return cudaMemcpy(dst, d_stream[s], stream_bytes[s], cudaMemcpyDeviceToHost) == cudaSuccess;
+}
+void* Context::copy_stream() { return (void*)impl->copy; }
+void Context::wait_copies() { cudaSetDevice(device); cudaStreamSynchronize(impl->copy); }
+bool Batch::copy_stream_to_async(int s, void* dst, void* cs) {
+    cudaSetDevice(device);
+    if (!stream_bytes[s]) return true;
+    return cudaMemcpyAsync(dst, d_stream[s], stream_bytes[s], cudaMemcpyDeviceToHost, (cudaStream_t)cs) == cudaSuccess;
+}
+bool Batch::copy_offsets_to_async(int s, unsigned long long* dst, void* cs) {
+    cudaSetDevice(device);
+    return cudaMemcpyAsync(dst, d_offsets + (size_t)s * (n + 1), (size_t)(n + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, (cudaStream_t)cs) == cudaSuccess;
 }
 bool Batch::copy_offsets_to(int s, unsigned long long* dst) {
     cudaSetDevice(device);

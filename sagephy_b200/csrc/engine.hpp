@@ -91,6 +91,8 @@ public:
     Summary summary; Timings timings;
     const char* stream_host(int s);
     bool copy_stream_to(int s, void* dst);
+    bool copy_stream_to_async(int s, void* dst, void* copy_stream);
+    bool copy_offsets_to_async(int s, unsigned long long* dst, void* copy_stream);
     bool copy_offsets_to(int s, unsigned long long* dst);
     void fetch_info();
     void fetch_offsets();
@@ -105,6 +107,8 @@ public:
     struct Impl; std::unique_ptr<Impl> impl;
     void run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch& out);
     void run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& out);
+    void* copy_stream();          // second CUDA stream for device->host copies that overlap the next batch's kernels
+    void wait_copies();
     void probe_d2s(const double* v, long long n, char* out);
     void probe_math(int fn, const double* v, long long n, double* out);
     void probe_mt(long long seed, long long n_words, uint32_t* out);

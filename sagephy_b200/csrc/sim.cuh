@@ -305,12 +305,34 @@ __device__ __forceinline__ double one_minus_u(uint32_t a, uint32_t b) {
 __device__ __forceinline__ double u01_52(uint32_t a, uint32_t b) {
     return __hiloint2double((int)(0x3ff00000u | (a >> 12)), (int)b) - 1.0;
 }
+// Natural logarithm for 0 < x <= 1 with x a normal double (one_minus_u never produces 0, subnormals, infinities or NaNs), so
+// none of the special-case handling of the library routine is needed: exponent split, m in [sqrt(1/2), sqrt(2)),
+// s = f/(2+f) through rcp.approx + two Newton steps, then the classic degree-7 (in s^2) polynomial. Max error ~1 ulp.
+// Throughput mode only; the find and build passes both call it, so they agree bit for bit.
+__device__ __forceinline__ double log_unit(double x) {
+    int hi = __double2hiint(x); const int lo = __double2loint(x);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;
+    if (hi >= 0x3ff6a09f) { hi -= 0x00100000; e += 1; }
+    const double f = __hiloint2double(hi, lo) - 1.0;
+    const double y = 2.0 + f;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+    r = fma(fma(-y, r, 1.0), r, r);
+    r = fma(fma(-y, r, 1.0), r, r);
+    const double s = f * r, z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01), 6.666666666666735130e-01);
+    const double R = t2 + t1, hfsq = 0.5 * f * f, dk = (double)e;
+    return dk * 6.93147180369123816490e-01 - ((hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)) - f);
+}
+
 __device__ __forceinline__ BdVertex bd_vertex(const BdConsts& C, const TinyHost& H, int X, double start, U4 w) {
     BdVertex r;
     const bool isRoot = H.parent[X] < 0, hostLeaf = H.left[X] < 0;
     const double low = H.vtime[X];
     // explicit (non-contractable) multiply / subtract: the find and build kernels must round identically
-    const double bt = __dmul_rn(-log(one_minus_u(w.x, w.y)), C.inv_sum);
+    const double bt = __dmul_rn(-log_unit(one_minus_u(w.x, w.y)), C.inv_sum);
     const double et = __dsub_rn(start, bt);
     const double u2 = u01_52(w.z, w.w);
     r.boundary = et <= low;
@@ -326,7 +348,7 @@ __device__ __forceinline__ BdVertex bd_vertex(const BdConsts& C, const TinyHost&
 // Single-arc host ("H0:T;"): every boundary vertex is a host leaf, every interior event is on the root arc.
 __device__ __forceinline__ BdVertex bd_vertex_single(const BdConsts& C, double start, U4 w) {
     BdVertex r;
-    const double bt = __dmul_rn(-log(one_minus_u(w.x, w.y)), C.inv_sum);
+    const double bt = __dmul_rn(-log_unit(one_minus_u(w.x, w.y)), C.inv_sum);
     const double et = __dsub_rn(start, bt);
     const double u2 = u01_52(w.z, w.w);
     r.boundary = et <= 0.0;

@@ -86,6 +86,16 @@ def test_device_pow_and_quantiles_are_bit_exact_with_oracle(ctx):
         assert (got.view(np.uint64) == want.view(np.uint64)).all()
 
 
+def test_throughput_mode_log_is_accurate(ctx):
+    # log_unit (Philox path only): 0 < x <= 1, normal doubles; tolerance 2 ulp against libm
+    rng = np.random.default_rng(6)
+    x = np.concatenate([1.0 - rng.random(50000) * (1 - 2.0 ** -52), rng.random(20000), 2.0 ** -rng.integers(0, 52, 2000).astype(float), np.array([1.0, 2.0 ** -52, 0.5, 0.7071067811865476])])
+    got, want = ctx.math(9, x), np.log(x)
+    err = np.abs(got - want) / np.maximum(np.spacing(np.abs(want)), 1e-300)
+    assert err.max() <= 2.0, (err.max(), x[err.argmax()])
+    assert got[-4] == 0.0
+
+
 @pytest.mark.parametrize("seed", [0, 1, 20260101, 2 ** 62, -1, -300])
 def test_device_mt19937_stream(ctx, seed):
     assert (ctx.mt_words(seed, 3000) == oracle_mt_words(seed, 3000)).all()
