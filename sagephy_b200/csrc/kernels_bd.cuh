@@ -102,19 +102,22 @@ __global__ void __launch_bounds__(kBdFindThreads) k_bd_find(BdArgs a) {
     }
 }
 
-// Single-arc specialisation (HostTreeGen without -bi; requires vtime[0] == 0): no arc bookkeeping, and the lineage stack keeps
-// its top element in a register — a duplication continues with one child directly and parks the other, so a stack load is
-// issued one whole vertex step before its value is needed.
+// Single-arc specialisation (HostTreeGen without -bi; requires vtime[0] == 0): no arc bookkeeping, and the vertex step is
+// branch-free. The lineage stack keeps its top element in a register: st[d] is the start time of parked lineage d (1-based,
+// st[0] is a dummy so that the refill load never needs a guard), `tos` mirrors st[depth]. A duplication stores the sibling and
+// continues with one child; every other event continues with `tos` and issues the refill load one whole vertex step before its
+// value can be needed. Lanes of a warp take different events every trip, so selects instead of branches halve the issue count.
 __global__ void __launch_bounds__(kBdFindThreads) k_bd_find_single(BdArgs a) {
     __shared__ int s_next[kBdFindThreads / 32];
     __shared__ int s_best[kBdFindThreads / 32];
-    double st_time[kBdStack];
+    double st[kBdStack + 1];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const BdConsts C = bd_consts(a.P);
     const double tip = a.H.tip;
     const int min_leaves = a.P.min_leaves, max_leaves = a.P.max_leaves, max_attempts = a.P.max_attempts;
     volatile int* v_best = &s_best[wib];
+    st[0] = 0.0;
     for (;;) {
         long long r = 0;
         if (lane == 0) r = (long long)atomicAdd(a.work_counter, 1ULL);
@@ -126,44 +129,41 @@ __global__ void __launch_bounds__(kBdFindThreads) k_bd_find_single(BdArgs a) {
         if (a.P.n_sizes > 0) { PhiloxStream ph; ph.init(a.seed, gid, 0xFFFFFFFFu); exact = a.sizes[ph.next_int(a.P.n_sizes)]; }
         if (lane == 0) { s_next[wib] = 0; s_best[wib] = 0x7fffffff; }
         __syncwarp();
-        // lane state: attempt my_a (< 0: none), depth = pending lineages beyond `cur`; stack = st_time[0..sp) + tos
-        bool idle = false, running = false; int my_a = -1, sp = 0, depth = 0; uint32_t vidx = 0; int sampled = 0; bool overflow = false;
+        // lane state: 0 = needs an attempt, 1 = running attempt my_a, 2 = idle (nothing left to claim)
+        int state = 0, my_a = -1, depth = 0; uint32_t vidx = 0; int sampled = 0; bool overflow = false;
         double cur = 0.0, tos = 0.0;
         int acc_a = 0x7fffffff, acc_n = 0, acc_sampled = 0;
         unsigned long long v_completed = 0, v_abandoned = 0; int n_completed = 0;
         U4 w_next{0, 0, 0, 0};
         for (;;) {
-            if (!running && !idle) {
+            if (state == 0) {
                 const int na = atomicAdd(&s_next[wib], 1);
-                if (na > *v_best || na > max_attempts) idle = true;
+                if (na > *v_best || na > max_attempts) state = 2;
                 else {
-                    my_a = na; running = true; cur = tip; depth = 0; sp = 0; vidx = 0; sampled = 0;
+                    my_a = na; state = 1; cur = tip; tos = 0.0; depth = 0; vidx = 0; sampled = 0;
                     w_next = philox4x32_10(0u, (uint32_t)my_a, rep_lo, rep_hi, k0, k1);
                 }
             }
-            if (__all_sync(0xffffffffu, idle)) break;
-            if (running) {
-                if (my_a > *v_best) { v_abandoned += vidx; running = false; idle = true; continue; }
+            if (__all_sync(0xffffffffu, state == 2)) break;
+            if (state == 1) {
+                if (my_a > *v_best) { v_abandoned += vidx; state = 2; continue; }      // a smaller index was accepted meanwhile
                 const U4 w = w_next;
                 ++vidx;
-                w_next = philox4x32_10(vidx, (uint32_t)my_a, rep_lo, rep_hi, k0, k1);
+                w_next = philox4x32_10(vidx, (uint32_t)my_a, rep_lo, rep_hi, k0, k1);   // next vertex's block: independent of this vertex's math
                 const BdVertex v = bd_vertex_single(C, cur, w);
-                bool finished = false, rejected = false;
-                if (v.event == EV_DUPLICATION) {
-                    // continue with one child, park the other
-                    if (depth > 0) { if (sp >= kBdStack) { overflow = true; rejected = true; finished = true; } else st_time[sp++] = tos; }
-                    tos = v.et; ++depth; cur = v.et;
-                } else {
-                    if (v.event == EV_LEAF) { ++sampled; if (sampled > max_leaves) { rejected = true; finished = true; } }
-                    if (!finished) {
-                        if (depth == 0) finished = true;
-                        else { cur = tos; --depth; if (depth > 0) tos = st_time[--sp]; }
-                    }
-                }
-                if (finished) {
-                    running = false;
+                const bool dup = v.event == EV_DUPLICATION;
+                sampled += v.event == EV_LEAF ? 1 : 0;
+                const bool ovf = dup && depth >= kBdStack;
+                if (dup && !ovf) st[depth + 1] = v.et;
+                const int nd = dup ? depth + 1 : depth - 1;
+                const double refill = st[nd > 0 ? (nd <= kBdStack ? nd : 0) : 0];
+                cur = dup ? v.et : tos;
+                tos = dup ? v.et : refill;
+                depth = nd;
+                if (nd < 0 || sampled > max_leaves || ovf) {       // ran to completion, or can no longer be accepted
+                    state = 0; overflow |= ovf;
                     v_completed += vidx; ++n_completed;
-                    const bool ok = !rejected && sampled >= min_leaves && sampled <= max_leaves && (exact == -1 || sampled == exact);
+                    const bool ok = !ovf && sampled >= min_leaves && sampled <= max_leaves && (exact == -1 || sampled == exact);
                     if (ok) { atomicMin(&s_best[wib], my_a); acc_a = my_a; acc_n = (int)vidx; acc_sampled = sampled; }
                 }
             }
