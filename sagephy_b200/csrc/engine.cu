@@ -276,7 +276,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     DevBuf<uint32_t> mt_state; DevBuf<int32_t> marks, leafcnt;
     int max_workers = 0;
     if (fast_bd) {
-        BdArgs a{}; a.P = P; a.H = make_tiny(cfg.host); a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.info = info.p;
+        BdArgs a{}; a.P = P; a.H = make_tiny(cfg.host); a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.keys = philox_keys(seed); a.info = info.p;
         a.work_counter = counter.p; a.sizes = d_sizes.p;
         CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
         int blocks = sm * 4; long long need = (n * 32 + 255) / 256; if (need < blocks) blocks = (int)need;
@@ -345,7 +345,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     // ---- K1 build ------------------------------------------------------------------------------------------------------------
     ph.start();
     if (fast_bd) {
-        BdArgs a{}; a.P = P; a.H = make_tiny(cfg.host); a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.info = info.p;
+        BdArgs a{}; a.P = P; a.H = make_tiny(cfg.host); a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.keys = philox_keys(seed); a.info = info.p;
         a.node_off = node_off.p; a.nodes = nodes.p;
         launch_bd_build(a, (int)((n + 255) / 256), st); ++tm.launches;
     } else {

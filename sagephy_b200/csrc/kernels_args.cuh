@@ -1,6 +1,7 @@
 // Kernel argument blocks (plain structs passed by value), shared between the kernel translation units and the host engine.
 #pragma once
 #include "device_types.cuh"
+#include "rng.cuh"
 
 namespace sgp {
 
@@ -56,6 +57,7 @@ struct BdArgs {
     TinyHost H;
     MathTables T;
     long long n; long long rep_base; unsigned long long seed;
+    PhiloxKeys keys;                  // round keys of `seed`
     RepInfo* info;
     unsigned long long* work_counter;
     const int32_t* sizes;

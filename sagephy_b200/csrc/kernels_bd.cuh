@@ -112,7 +112,6 @@ __global__ void __launch_bounds__(kBdFindThreads) k_bd_find_single(BdArgs a) {
     __shared__ int s_best[kBdFindThreads / 32];
     double st[kBdStack + 1];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const BdConsts C = bd_consts(a.P);
     const double tip = a.H.tip;
     const int min_leaves = a.P.min_leaves, max_leaves = a.P.max_leaves, max_attempts = a.P.max_attempts;
@@ -141,7 +140,7 @@ __global__ void __launch_bounds__(kBdFindThreads) k_bd_find_single(BdArgs a) {
                 if (na > *v_best || na > max_attempts) state = 2;
                 else {
                     my_a = na; state = 1; cur = tip; tos = 0.0; depth = 0; vidx = 0; sampled = 0;
-                    w_next = philox4x32_10(0u, (uint32_t)my_a, rep_lo, rep_hi, k0, k1);
+                    w_next = philox4x32_10_rk(0u, (uint32_t)my_a, rep_lo, rep_hi, a.keys);
                 }
             }
             if (__all_sync(0xffffffffu, state == 2)) break;
@@ -149,7 +148,7 @@ __global__ void __launch_bounds__(kBdFindThreads) k_bd_find_single(BdArgs a) {
                 if (my_a > *v_best) { v_abandoned += vidx; state = 2; continue; }      // a smaller index was accepted meanwhile
                 const U4 w = w_next;
                 ++vidx;
-                w_next = philox4x32_10(vidx, (uint32_t)my_a, rep_lo, rep_hi, k0, k1);   // next vertex's block: independent of this vertex's math
+                w_next = philox4x32_10_rk(vidx, (uint32_t)my_a, rep_lo, rep_hi, a.keys);   // next vertex's block: independent of this vertex's math
                 const BdVertex v = bd_vertex_single(C, cur, w);
                 const bool dup = v.event == EV_DUPLICATION;
                 sampled += v.event == EV_LEAF ? 1 : 0;

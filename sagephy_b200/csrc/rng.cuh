@@ -37,6 +37,32 @@ SGP_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint
     return U4{c0, c1, c2, c3};
 }
 
+// Same function with the ten round keys precomputed (rk[2r], rk[2r+1] = key + r * Weyl): callers that keep `rk` in the kernel
+// parameter block get the keys as constant-bank operands instead of recomputing the schedule for every block.
+struct PhiloxKeys { uint32_t rk[20]; };
+SGP_HD PhiloxKeys philox_keys(uint64_t seed) {
+    PhiloxKeys K; uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { K.rk[2 * r] = k0; K.rk[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    return K;
+}
+SGP_HD U4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& K) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+#if defined(__CUDA_ARCH__)
+        asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo0), "=r"(hi0) : "r"(c0), "r"(M0));
+        asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo1), "=r"(hi1) : "r"(c2), "r"(M1));
+#else
+        { const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+          hi0 = (uint32_t)(p0 >> 32); lo0 = (uint32_t)p0; hi1 = (uint32_t)(p1 >> 32); lo1 = (uint32_t)p1; }
+#endif
+        uint32_t n0 = hi1 ^ c1 ^ K.rk[2 * r], n1 = lo1, n2 = hi0 ^ c3 ^ K.rk[2 * r + 1], n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    }
+    return U4{c0, c1, c2, c3};
+}
+
 // Two 32-bit words -> a double in [0,1) laid out like java.util.Random.nextDouble: (26 high bits, 27 high bits) * 2^-53.
 SGP_HD double u01_from_words(uint32_t a, uint32_t b) {
     uint64_t m = ((uint64_t)(a >> 6) << 27) + (uint64_t)(b >> 5);

@@ -309,6 +309,12 @@ __device__ __forceinline__ double u01_52(uint32_t a, uint32_t b) {
 // none of the special-case handling of the library routine is needed: exponent split, m in [sqrt(1/2), sqrt(2)),
 // s = f/(2+f) through rcp.approx + two Newton steps, then the classic degree-7 (in s^2) polynomial. Max error ~1 ulp.
 // Throughput mode only; the find and build passes both call it, so they agree bit for bit.
+// Coefficients live in constant memory so that they reach the FP64 pipe as constant-bank operands (as literals the compiler
+// rebuilds each of them with two uniform-register moves per use, which costs issue slots in the sampler's inner loop).
+__constant__ static double kLogUnitC[9] = {
+    1.531383769920937332e-01, 2.222219843214978396e-01, 3.999999999940941908e-01,
+    1.479819860511658591e-01, 1.818357216161805012e-01, 2.857142874366239149e-01, 6.666666666666735130e-01,
+    6.93147180369123816490e-01, 1.90821492927058770002e-10};
 __device__ __forceinline__ double log_unit(double x) {
     int hi = __double2hiint(x); const int lo = __double2loint(x);
     int e = (hi >> 20) - 1023;
@@ -321,10 +327,10 @@ __device__ __forceinline__ double log_unit(double x) {
     r = fma(fma(-y, r, 1.0), r, r);
     r = fma(fma(-y, r, 1.0), r, r);
     const double s = f * r, z = s * s, w = z * z;
-    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
-    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01), 6.666666666666735130e-01);
+    const double t1 = w * fma(w, fma(w, kLogUnitC[0], kLogUnitC[1]), kLogUnitC[2]);
+    const double t2 = z * fma(w, fma(w, fma(w, kLogUnitC[3], kLogUnitC[4]), kLogUnitC[5]), kLogUnitC[6]);
     const double R = t2 + t1, hfsq = 0.5 * f * f, dk = (double)e;
-    return dk * 6.93147180369123816490e-01 - ((hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)) - f);
+    return dk * kLogUnitC[7] - ((hfsq - fma(s, hfsq + R, dk * kLogUnitC[8])) - f);
 }
 
 __device__ __forceinline__ BdVertex bd_vertex(const BdConsts& C, const TinyHost& H, int X, double start, U4 w) {
