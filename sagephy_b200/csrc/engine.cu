@@ -53,9 +53,12 @@ struct HostOnDevice {
     }
 };
 
-__global__ void k_extract_pool(const RepInfo* info, long long n, long long* out) {
+__global__ void k_extract_pool(const RepInfo* info, long long n, long long* out, int* max_pool) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = info[i].status == REP_OK ? info[i].n_pool : 0;
+    int v = 0;
+    if (i < n) { v = info[i].status == REP_OK ? info[i].n_pool : 0; out[i] = v; }
+    v = __reduce_max_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(max_pool, v);
 }
 __global__ void k_collect_status(const RepInfo* info, long long n, int status, long long* list, unsigned long long* count) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -329,7 +332,9 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     // ---- node offsets ------------------------------------------------------------------------------------------------------
     DevBuf<long long> pool, node_off; pool.alloc((size_t)n + 1); node_off.alloc((size_t)n + 1);
     CK(cudaMemsetAsync(pool.p, 0, ((size_t)n + 1) * sizeof(long long), st));
-    k_extract_pool<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(info.p, n, pool.p); ++tm.launches;
+    DevBuf<int> max_pool_d; max_pool_d.alloc(1);
+    CK(cudaMemsetAsync(max_pool_d.p, 0, sizeof(int), st));
+    k_extract_pool<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(info.p, n, pool.p, max_pool_d.p); ++tm.launches;
     {
         size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, pool.p, node_off.p, (int)(n + 1), st);
         DevBuf<char> tmp; tmp.alloc(tb);
@@ -338,6 +343,8 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     }
     long long total_nodes = 0;
     CK(cudaMemcpy(&total_nodes, node_off.p + n, sizeof(long long), cudaMemcpyDeviceToHost));
+    int max_pool = 0;
+    CK(cudaMemcpy(&max_pool, max_pool_d.p, sizeof(int), cudaMemcpyDeviceToHost));
     DevBuf<Node> nodes; DevBuf<int32_t> aux;
     const long long aux_stride = std::max<long long>(total_nodes, 1);
     nodes.alloc((size_t)std::max<long long>(total_nodes, 1)); aux.alloc((size_t)aux_stride * 4);
@@ -368,7 +375,8 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     {
         LabelArgs a{}; a.n = n; a.info = info.p; a.node_off = node_off.p; a.nodes = nodes.p; a.aux = aux.p; a.aux_stride = aux_stride; a.T = impl->T;
         a.host_root_time = cfg.host.vtime[cfg.host.root]; a.has_stem_override = cfg.has_stem_override; a.stem_override = cfg.stem_override;
-        launch_label_prune(a, (int)((n + 127) / 128), st); ++tm.launches;
+        a.pool = pool.p;
+        tm.launches += launch_label_prune(a, max_pool, impl->sm_count, st);
         CK(cudaGetLastError());
     }
     tm.label_ms = ph.stop();

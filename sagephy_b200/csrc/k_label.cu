@@ -1,5 +1,29 @@
 #include "kernels_label.cuh"
 #include "launch.hpp"
+#include <algorithm>
+#include <cstdlib>
 namespace sgp {
-void launch_label_prune(const LabelArgs& a, int blocks, cudaStream_t st) { k_label_prune<<<blocks, 128, 0, st>>>(a); }
+// One launch per size class so that the shared-memory stage of a warp is never much larger than its tree (the stage size sets
+// how many trees an SM works on at a time); whatever exceeds the largest stage goes to the thread-per-tree kernel.
+int launch_label_prune(LabelArgs a, int max_pool, int sm_count, cudaStream_t st) {
+    static const int caps[] = {48, 64, 96, 128, 160, 192, 224, 256, 288, 320, 384, 448, 512, 640, 768, 1024, 1280, 1536, 2048, 2340};
+    static bool attr_set = false;
+    const int kMaxSmem = 227 * 1024;
+    if (!attr_set) { cudaFuncSetAttribute(k_label_prune_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 1024); attr_set = true; }
+    int launches = 0, lo = 0;
+    const bool thread_only = getenv("SGP_LABEL_THREAD_KERNEL") != nullptr;      // test hook: exercise the fallback on small trees
+    for (int cap : caps) {
+        if (thread_only) break;
+        a.min_pool = lo; a.cap = cap;
+        const size_t smem = (size_t)cap * kLabelBytesPerNode + kLabelExtraBytes;
+        const int per_sm = (int)std::min<size_t>(32, (size_t)kMaxSmem / (smem + 1536));     // + static shared memory and the per-block reservation
+        const long long want = (a.n + 31) / 32;
+        const int blocks = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count * per_sm));
+        k_label_prune_warp<<<blocks, 32, smem, st>>>(a); ++launches;
+        lo = cap;
+        if (cap >= max_pool) break;
+    }
+    if (max_pool > lo) { a.cap = lo; k_label_prune<<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(a); ++launches; }
+    return launches;
+}
 }  // namespace sgp

@@ -74,6 +74,8 @@ struct LabelArgs {
     MathTables T;
     double host_root_time;                  // hostTree.getVertexTime(root)
     int has_stem_override; double stem_override;    // HostTreeGen -stem (HostTreeGen.java:74-79)
+    const long long* pool;                  // vertices per replicate (0: failed)
+    int min_pool, cap;                      // warp kernel: size class (min_pool, cap]; thread kernel: trees above cap
 };
 
 enum Stream : int { ST_UNPRUNED_TREE = 0, ST_PRUNED_TREE = 1, ST_UNPRUNED_INFO = 2, ST_PRUNED_INFO = 3,

@@ -1,5 +1,4 @@
-// K3: labelling, pruning and per-tree statistics — one thread per accepted replicate, no recursion (parent links make
-// every traversal stackless).
+// K3: labelling, pruning and per-tree statistics. No recursion: parent links make every traversal stackless.
 //
 // Reference behaviour (apps/SaGePhy/PruningHelper.java):
 //   :25-65  labelUnprunableVertices — prunability lattice; survivors numbered 0.. in post-order
@@ -7,48 +6,51 @@
 //   :98-145 prune                   — pruned copy; a vertex with one surviving child collapses into that child, whose length
 //                                      becomes round8(child + parent)
 // plus the breadth-first reductions of getInfo (GuestTreeInHostTreeCreator.java:431-511, HostTreeGen.java:124-174).
+//
+// Two kernels share the traversal code:
+//   k_label_prune_warp — one warp per tree, the tree's node records staged in shared memory (coalesced 16-byte loads and
+//                        stores, each record crosses HBM exactly once in each direction), traversals as level-synchronous
+//                        sweeps with all lanes busy.
+//   k_label_prune      — one thread per tree straight on global memory with the reference's serial traversals, for trees that
+//                        do not fit the shared-memory stage.
 #pragma once
 #include "kernels_args.cuh"
 
 namespace sgp {
 
-
-__global__ void __launch_bounds__(128) k_label_prune(LabelArgs a) {
-    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.n) return;
-    RepInfo& inf = a.info[r];
-    if (inf.status != REP_OK) return;
-    const long long off = a.node_off[r];
-    Node* N = a.nodes + off;
-    int32_t* ordU = a.aux + off; int32_t* ordP = a.aux + a.aux_stride + off;
-    int32_t* bfsU = a.aux + 2 * a.aux_stride + off; int32_t* bfsP = a.aux + 3 * a.aux_stride + off;
-    int32_t* pr = bfsP;     // temporary: pruned representative of each subtree
-    const int root = inf.root;
+// Post-order walk: prunability, numbering, pruned structure. ordU / ordP receive the post-orders, pr is scratch (pruned
+// representative of each subtree). Vertices that do not survive get number = -2 - (rank among them), fixed up afterwards.
+template <class I>
+__device__ __forceinline__ int label_postorder(Node* N, I* ordU, I* ordP, I* pr, int root, const MathTables& T, int& nu_out, int& up_out) {
     int nu = 0, np = 0, up = 0;
-    // ---- post-order walk: prunability, numbering, pruned structure
     int v = root;
     for (;;) {
         while (N[v].left >= 0) v = N[v].left;
         bool done = false;
         for (;;) {
             Node& x = N[v];
-            if (x.left < 0) {
-                x.prun = (x.event == EV_LEAF) ? PR_UNPRUNABLE : PR_PRUNABLE;
-                if (x.event == EV_LEAF) { pr[v] = v; x.p_bl = x.bl; x.p_left = -1; x.p_right = -1; } else pr[v] = -1;
+            const int xl = x.left;
+            uint8_t prun;
+            if (xl < 0) {
+                const bool leaf = x.event == EV_LEAF;
+                prun = leaf ? PR_UNPRUNABLE : PR_PRUNABLE;
+                if (leaf) { pr[v] = (I)v; x.p_bl = x.bl; x.p_left = -1; x.p_right = -1; } else pr[v] = (I)-1;
             } else {
-                const uint8_t pl = N[x.left].prun, pq = N[x.right].prun;
-                if (pl == PR_PRUNABLE && pq == PR_PRUNABLE) { x.prun = PR_PRUNABLE; pr[v] = -1; }
+                const int xr = x.right;
+                const uint8_t pl = N[xl].prun, pq = N[xr].prun;
+                if (pl == PR_PRUNABLE && pq == PR_PRUNABLE) { prun = PR_PRUNABLE; pr[v] = (I)-1; }
                 else if (pl == PR_PRUNABLE || pq == PR_PRUNABLE) {
-                    x.prun = PR_COLLAPSABLE;
-                    const int c = pr[pl == PR_PRUNABLE ? x.right : x.left];
-                    N[c].p_bl = round_sig(a.T, XADD(N[c].p_bl, x.bl), 8);
-                    pr[v] = c;
+                    prun = PR_COLLAPSABLE;
+                    const int c = pr[pl == PR_PRUNABLE ? xr : xl];
+                    N[c].p_bl = round_sig(T, XADD(N[c].p_bl, x.bl), 8);
+                    pr[v] = (I)c;
                 } else {
-                    x.prun = PR_UNPRUNABLE; x.p_left = pr[x.left]; x.p_right = pr[x.right]; x.p_bl = x.bl; pr[v] = v;
+                    prun = PR_UNPRUNABLE; x.p_left = pr[xl]; x.p_right = pr[xr]; x.p_bl = x.bl; pr[v] = (I)v;
                 }
             }
-            if (x.prun == PR_UNPRUNABLE) { x.number = nu; ordP[nu] = v; ++nu; } else { x.number = -2 - np; ++np; }
-            ordU[up++] = v;
+            x.prun = prun;
+            if (prun == PR_UNPRUNABLE) { x.number = nu; ordP[nu] = (I)v; ++nu; } else { x.number = -2 - np; ++np; }
+            ordU[up++] = (I)v;
             const int p = x.parent;
             if (p < 0) { done = true; break; }
             if (N[p].left == v) { v = N[p].right; break; }
@@ -56,46 +58,242 @@ __global__ void __launch_bounds__(128) k_label_prune(LabelArgs a) {
         }
         if (done) break;
     }
-    const int p_root = pr[root];
+    nu_out = nu; up_out = up;
+    return pr[root];
+}
+
+// Breadth-first pass over the unpruned (PRUNED = false) or pruned view: BFS order into q, getInfo sums in BFS order, event
+// counts, left-child marks and '(' run lengths (a parent is always visited before its children). The pruned pass writes its
+// marks into Node::pad0 so that both passes can run concurrently; the caller folds them into Node::flags afterwards.
+template <class I>
+__device__ __forceinline__ void label_bfs(Node* N, I* q, int start, bool pruned, double host_root_time, int32_t* cnt, double& tot_out, double& ben_out) {
+    double tot = 0.0, ben = 0.0;
+    if (start >= 0) {
+        int h = 0, t = 0; q[t++] = (I)start;
+        while (h < t) {
+            Node& x = N[q[h++]];
+            const int l = pruned ? x.p_left : x.left, r = pruned ? x.p_right : x.right;
+            const double len = pruned ? x.p_bl : x.bl;
+            if (pruned) x.pad0 |= NF_IN_PRUNED;
+            if (l >= 0) {
+                q[t++] = (I)l; q[t++] = (I)r;
+                if (pruned) { Node& L = N[l]; L.pad0 |= NF_LEFT_P; L.chain_p = (int16_t)(x.chain_p + 1); N[r].chain_p = 0; }
+                else { Node& L = N[l]; L.flags |= NF_LEFT_U; L.chain_u = (int16_t)(x.chain_u + 1); N[r].chain_u = 0; }
+            }
+            tot = XADD(tot, len);
+            ben = XADD(ben, fmax(fmin(XSUB(host_root_time, x.abstime), len), 0.0));
+            cnt[x.event]++;
+        }
+    }
+    tot_out = tot; ben_out = ben;
+}
+
+// Shared-memory bytes per vertex of the warp kernel: the record + nine int16 work arrays.
+constexpr int kLabelBytesPerNode = (int)sizeof(Node) + 9 * (int)sizeof(int16_t);
+constexpr int kLabelExtraBytes = 16;
+
+// One warp per tree, all lanes busy. The serial recursions of the reference are restated as level-synchronous sweeps over the
+// breadth-first order (a tree of ~270 vertices has ~30 levels, so a sweep is ~35 warp steps instead of ~270 dependent ones):
+//   1. breadth-first order of the unpruned tree, level boundaries, left-child marks / '(' runs, event counts
+//   2. bottom-up: subtree size, survivors per subtree, prunability, pruned representative, pruned children
+//   2b. collapse chains (one lane per chain, chains are independent): len = round8(len + parent) going up, PruningHelper.java:131-139
+//   3. top-down: position of every vertex in the post-order (= vertices before its subtree + subtree size - 1), the same among
+//      survivors only; vertex numbers (survivors first, PruningHelper.java:25-90) and both post-order arrays follow directly
+//   4. breadth-first order of the pruned view with its marks and counts
+//   5. the getInfo sums, which are order-dependent floating-point sums: lane 0 adds the unpruned, lane 1 the pruned tree
+__global__ void __launch_bounds__(32) k_label_prune_warp(LabelArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int32_t s_cnt[2][EV_COUNT];
+    __shared__ double s_sum[2][2];
+    const int cap = a.cap;
+    Node* sN = reinterpret_cast<Node*>(smem);
+    int16_t* bfsU = reinterpret_cast<int16_t*>(smem + (size_t)cap * sizeof(Node));
+    int16_t *ordU = bfsU + cap, *ordP = ordU + cap, *bfsP = ordP + cap, *pr = bfsP /* dead before bfsP is written */;
+    int16_t *sz = bfsP + cap, *ns = sz + cap, *off = ns + cap, *offS = off + cap, *lvl = offS + cap;     // lvl: cap + 2 entries
+    const int lane = threadIdx.x;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // every trip looks at 32 consecutive replicates and works through those of this launch's size class
+    for (long long base = (long long)blockIdx.x * 32; base < a.n; base += (long long)gridDim.x * 32) {
+      int np_lane = 0;
+      if (base + lane < a.n) np_lane = (int)a.pool[base + lane];          // 0 for failed replicates
+      unsigned todo = __ballot_sync(0xffffffffu, np_lane > a.min_pool && np_lane <= a.cap);
+      while (todo) {
+        const int b = __ffs(todo) - 1; todo &= todo - 1;
+        const long long r = base + b;
+        const int n_pool = __shfl_sync(0xffffffffu, np_lane, b);
+        RepInfo& inf = a.info[r];
+        const long long goff = a.node_off[r];
+        const int root = inf.root;
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(a.nodes + goff); uint4* dst = reinterpret_cast<uint4*>(sN);
+            const int nq = n_pool * (int)(sizeof(Node) / 16);
+            for (int i = lane; i < nq; i += 32) dst[i] = src[i];
+            for (int i = lane; i < 2 * EV_COUNT; i += 32) (&s_cnt[0][0])[i] = 0;
+            if (lane == 0) { bfsU[0] = (int16_t)root; lvl[0] = 0; off[root] = 0; offS[root] = 0; }
+        }
+        __syncwarp();
+        // ---- 1. breadth-first order, levels
+        int D = 0, up;
+        {
+            int lo = 0, hi = 1;
+            while (lo < hi) {
+                ++D; if (lane == 0) lvl[D] = (int16_t)hi;
+                int t = hi;
+                for (int b0 = lo; b0 < hi; b0 += 32) {
+                    const int k = b0 + lane; int l = -1, rr = -1;
+                    if (k < hi) {
+                        Node& x = sN[bfsU[k]]; l = x.left; rr = x.right;
+                        if (l >= 0) { Node& L = sN[l]; L.flags |= NF_LEFT_U; L.chain_u = (int16_t)(x.chain_u + 1); sN[rr].chain_u = 0; }
+                        atomicAdd(&s_cnt[0][x.event], 1);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, l >= 0);
+                    if (l >= 0) { const int pos = t + 2 * __popc(m & lt_mask); bfsU[pos] = (int16_t)l; bfsU[pos + 1] = (int16_t)rr; }
+                    t += 2 * __popc(m);
+                }
+                __syncwarp();
+                lo = hi; hi = t;
+            }
+            up = hi;
+        }
+        // ---- 2. bottom-up
+        for (int d = D - 1; d >= 0; --d) {
+            const int lo = lvl[d], hi = lvl[d + 1];
+            for (int k = lo + lane; k < hi; k += 32) {
+                const int v = bfsU[k]; Node& x = sN[v];
+                const int l = x.left;
+                uint8_t prun; int size = 1, surv = 0;
+                if (l < 0) {
+                    const bool leaf = x.event == EV_LEAF;
+                    prun = leaf ? PR_UNPRUNABLE : PR_PRUNABLE; surv = leaf ? 1 : 0;
+                    if (leaf) { pr[v] = (int16_t)v; x.p_bl = x.bl; x.p_left = -1; x.p_right = -1; } else pr[v] = -1;
+                } else {
+                    const int rr = x.right;
+                    const uint8_t pl = sN[l].prun, pq = sN[rr].prun;
+                    size += sz[l] + sz[rr]; surv = ns[l] + ns[rr];
+                    if (pl == PR_PRUNABLE && pq == PR_PRUNABLE) { prun = PR_PRUNABLE; pr[v] = -1; }
+                    else if (pl == PR_PRUNABLE || pq == PR_PRUNABLE) { prun = PR_COLLAPSABLE; pr[v] = pr[pl == PR_PRUNABLE ? rr : l]; }
+                    else { prun = PR_UNPRUNABLE; ++surv; x.p_left = pr[l]; x.p_right = pr[rr]; x.p_bl = x.bl; pr[v] = (int16_t)v; }
+                }
+                x.prun = prun; sz[v] = (int16_t)size; ns[v] = (int16_t)surv;
+            }
+            __syncwarp();
+        }
+        const int nu = ns[root], p_root = pr[root];
+        // ---- 2b. collapse chains: gather the survivors whose parent collapses (list in ordU, which step 3 rewrites), then fold
+        {
+            int n_chain = 0;
+            for (int b0 = 0; b0 < up; b0 += 32) {
+                const int k = b0 + lane; bool start = false; int v = -1;
+                if (k < up) { v = bfsU[k]; const Node& x = sN[v]; start = x.prun == PR_UNPRUNABLE && x.parent >= 0 && sN[x.parent].prun == PR_COLLAPSABLE; }
+                const unsigned m = __ballot_sync(0xffffffffu, start);
+                if (start) ordU[n_chain + __popc(m & lt_mask)] = (int16_t)v;        // ordU is free until step 3
+                n_chain += __popc(m);
+            }
+            __syncwarp();
+            for (int k = lane; k < n_chain; k += 32) {
+                Node& c = sN[ordU[k]];
+                double len = c.p_bl; int p = c.parent;
+                while (p >= 0 && sN[p].prun == PR_COLLAPSABLE) { len = round_sig(a.T, XADD(len, sN[p].bl), 8); p = sN[p].parent; }
+                c.p_bl = len;
+            }
+            __syncwarp();
+        }
+        // ---- 3. top-down: post-order positions and vertex numbers
+        for (int d = 0; d < D; ++d) {
+            const int lo = lvl[d], hi = lvl[d + 1];
+            for (int k = lo + lane; k < hi; k += 32) {
+                const int v = bfsU[k]; Node& x = sN[v];
+                const int o = off[v], os = offS[v], size = sz[v], surv = ns[v];
+                const int post = o + size - 1;
+                ordU[post] = (int16_t)v;
+                if (x.prun == PR_UNPRUNABLE) { const int ps = os + surv - 1; x.number = ps; ordP[ps] = (int16_t)v; }
+                else x.number = nu + post - (os + surv);
+                const int l = x.left;
+                if (l >= 0) { const int rr = x.right; off[l] = (int16_t)o; offS[l] = (int16_t)os; off[rr] = (int16_t)(o + sz[l]); offS[rr] = (int16_t)(os + ns[l]); }
+            }
+            __syncwarp();
+        }
+        if (lane == 0 && a.has_stem_override) { sN[root].bl = a.stem_override; if (p_root >= 0) sN[p_root].p_bl = a.stem_override; }
+        // ---- 4. breadth-first order of the pruned view (pr is dead from here on)
+        if (p_root >= 0) {
+            if (lane == 0) bfsP[0] = (int16_t)p_root;
+            __syncwarp();
+            int lo = 0, hi = 1;
+            while (lo < hi) {
+                int t = hi;
+                for (int b0 = lo; b0 < hi; b0 += 32) {
+                    const int k = b0 + lane; int l = -1, rr = -1;
+                    if (k < hi) {
+                        Node& x = sN[bfsP[k]]; l = x.p_left; rr = x.p_right;
+                        x.flags |= NF_IN_PRUNED;
+                        if (l >= 0) { Node& L = sN[l]; L.flags |= NF_LEFT_P; L.chain_p = (int16_t)(x.chain_p + 1); sN[rr].chain_p = 0; }
+                        atomicAdd(&s_cnt[1][x.event], 1);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, l >= 0);
+                    if (l >= 0) { const int pos = t + 2 * __popc(m & lt_mask); bfsP[pos] = (int16_t)l; bfsP[pos + 1] = (int16_t)rr; }
+                    t += 2 * __popc(m);
+                }
+                __syncwarp();
+                lo = hi; hi = t;
+            }
+        }
+        __syncwarp();
+        // ---- 5. getInfo sums in breadth-first order (GuestTreeInHostTreeCreator.java:431-511)
+        if (lane < 2) {
+            const bool pruned = lane == 1;
+            const int16_t* q = pruned ? bfsP : bfsU; const int cnt = pruned ? nu : up;
+            double tot = 0.0, ben = 0.0;
+            for (int k = 0; k < cnt; ++k) {
+                const Node& x = sN[q[k]];
+                const double len = pruned ? x.p_bl : x.bl;
+                tot = XADD(tot, len);
+                ben = XADD(ben, fmax(fmin(XSUB(a.host_root_time, x.abstime), len), 0.0));
+            }
+            s_sum[lane][0] = tot; s_sum[lane][1] = ben;
+        }
+        __syncwarp();
+        {
+            uint4* dst = reinterpret_cast<uint4*>(a.nodes + goff); const uint4* src = reinterpret_cast<const uint4*>(sN);
+            const int nq = n_pool * (int)(sizeof(Node) / 16);
+            for (int i = lane; i < nq; i += 32) dst[i] = src[i];
+            int32_t* gOrdU = a.aux + goff; int32_t* gOrdP = a.aux + a.aux_stride + goff;
+            int32_t* gBfsU = a.aux + 2 * a.aux_stride + goff; int32_t* gBfsP = a.aux + 3 * a.aux_stride + goff;
+            for (int k = lane; k < up; k += 32) { gOrdU[k] = ordU[k]; gBfsU[k] = bfsU[k]; }
+            for (int k = lane; k < nu; k += 32) { gOrdP[k] = ordP[k]; gBfsP[k] = bfsP[k]; }
+            if (lane < EV_COUNT) { inf.cnt_u[lane] = s_cnt[0][lane]; inf.cnt_p[lane] = s_cnt[1][lane]; }
+            if (lane == 0) {
+                inf.p_root = p_root; inf.n_u = up; inf.n_p = nu; inf.p_root_time = p_root >= 0 ? sN[p_root].abstime : 0.0;
+                inf.total_u = s_sum[0][0]; inf.beneath_u = s_sum[0][1]; inf.total_p = s_sum[1][0]; inf.beneath_p = s_sum[1][1];
+            }
+        }
+        __syncwarp();
+      }
+    }
+}
+
+// Fallback for trees with more than `min_pool` vertices (those the warp kernel skipped): one thread per tree on global memory.
+__global__ void __launch_bounds__(128) k_label_prune(LabelArgs a) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n) return;
+    RepInfo& inf = a.info[r];
+    if (inf.status != REP_OK || inf.n_pool <= a.cap) return;
+    const long long off = a.node_off[r];
+    Node* N = a.nodes + off;
+    int32_t* ordU = a.aux + off; int32_t* ordP = a.aux + a.aux_stride + off;
+    int32_t* bfsU = a.aux + 2 * a.aux_stride + off; int32_t* bfsP = a.aux + 3 * a.aux_stride + off;
+    const int root = inf.root;
+    int nu = 0, up = 0;
+    const int p_root = label_postorder<int32_t>(N, ordU, ordP, bfsP, root, a.T, nu, up);
     for (int k = 0; k < up; ++k) { Node& x = N[ordU[k]]; if (x.number < -1) x.number = nu + (-2 - x.number); }
-    // ---- top-down: left-child flags and '(' run lengths (reverse post-order visits parents before children)
-    for (int k = up - 1; k >= 0; --k) {
-        Node& x = N[ordU[k]];
-        if (x.left >= 0) { Node& L = N[x.left]; L.flags |= NF_LEFT_U; L.chain_u = (int16_t)(x.chain_u + 1); N[x.right].chain_u = 0; }
-    }
-    for (int k = nu - 1; k >= 0; --k) {
-        Node& x = N[ordP[k]];
-        x.flags |= NF_IN_PRUNED;
-        if (x.p_left >= 0) { Node& L = N[x.p_left]; L.flags |= NF_LEFT_P; L.chain_p = (int16_t)(x.chain_p + 1); N[x.p_right].chain_p = 0; }
-    }
     if (a.has_stem_override) { N[root].bl = a.stem_override; if (p_root >= 0) N[p_root].p_bl = a.stem_override; }
-    // ---- breadth-first orders and the getInfo reductions (sum order = BFS order)
     inf.p_root = p_root; inf.n_u = up; inf.n_p = nu; inf.p_root_time = p_root >= 0 ? N[p_root].abstime : 0.0;
     for (int e = 0; e < EV_COUNT; ++e) { inf.cnt_u[e] = 0; inf.cnt_p[e] = 0; }
-    double tot = 0.0, ben = 0.0;
-    {
-        int h = 0, t = 0; bfsU[t++] = root;
-        while (h < t) {
-            const Node& x = N[bfsU[h++]];
-            if (x.left >= 0) { bfsU[t++] = x.left; bfsU[t++] = x.right; }
-            tot = XADD(tot, x.bl);
-            ben = XADD(ben, fmax(fmin(XSUB(a.host_root_time, x.abstime), x.bl), 0.0));
-            inf.cnt_u[x.event]++;
-        }
-    }
+    double tot, ben;
+    label_bfs<int32_t>(N, bfsU, root, false, a.host_root_time, inf.cnt_u, tot, ben);
     inf.total_u = tot; inf.beneath_u = ben;
-    tot = 0.0; ben = 0.0;
-    if (p_root >= 0) {
-        int h = 0, t = 0; bfsP[t++] = p_root;
-        while (h < t) {
-            const Node& x = N[bfsP[h++]];
-            if (x.p_left >= 0) { bfsP[t++] = x.p_left; bfsP[t++] = x.p_right; }
-            tot = XADD(tot, x.p_bl);
-            ben = XADD(ben, fmax(fmin(XSUB(a.host_root_time, x.abstime), x.p_bl), 0.0));
-            inf.cnt_p[x.event]++;
-        }
-    }
+    label_bfs<int32_t>(N, bfsP, p_root, true, a.host_root_time, inf.cnt_p, tot, ben);
     inf.total_p = tot; inf.beneath_p = ben;
+    for (int k = 0; k < up; ++k) { Node& x = N[ordU[k]]; x.flags |= x.pad0; x.pad0 = 0; }
 }
 
 }  // namespace sgp

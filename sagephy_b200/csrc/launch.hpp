@@ -8,7 +8,7 @@ void launch_find_general(bool replay, bool domain, const FindArgs& a, int blocks
 void launch_build_general(bool replay, bool domain, const BuildArgs& a, int blocks, cudaStream_t st);
 void launch_bd_find(const BdArgs& a, int blocks, cudaStream_t st);
 void launch_bd_build(const BdArgs& a, int blocks, cudaStream_t st);
-void launch_label_prune(const LabelArgs& a, int blocks, cudaStream_t st);
+int launch_label_prune(LabelArgs a, int max_pool, int sm_count, cudaStream_t st);          // returns the number of kernels launched
 int launch_emit(bool write, const EmitArgs& a, unsigned blocks, cudaStream_t st);   // returns the number of kernels launched
 void launch_relax_rates(bool replay, const RelaxArgs& a, int first_attempt, int only_flagged, cudaStream_t st);
 void launch_relax_apply(const RelaxArgs& a, long long total_slots, cudaStream_t st);

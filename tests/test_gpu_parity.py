@@ -168,6 +168,21 @@ def test_guest_tree_gen_on_generated_100_leaf_host(ctx, tmp_path):
         assert_replay_parity(ctx, "GuestTreeGen", ["-s", "100", "-db", db, str(p), "0.3", "0.3", "0.3", "o"], 6, "o")
 
 
+def test_label_kernels_agree(ctx, monkeypatch):
+    # The warp-per-tree (shared-memory, level-synchronous) and thread-per-tree (serial, for oversized trees) label kernels must
+    # produce the same bytes; SGP_LABEL_THREAD_KERNEL routes every tree through the latter.
+    monkeypatch.setenv("SGP_LABEL_THREAD_KERNEL", "1")
+    assert_replay_parity(ctx, "HostTreeGen", HOST_CASES[2], 24, "o")
+    assert_replay_parity(ctx, "HostTreeGen", HOST_CASES[5], 24, "o")
+    assert_replay_parity(ctx, "GuestTreeGen", GUEST_CASES[4], 24, "o")
+    args = ["-s", "11", "-min", "20", "-max", "60", "-p", "0.7", "1.0", "4.0", "0.5", "o"]
+    slow = ctx.run("HostTreeGen", args, n=2000, rng=sg.RNG_PHILOX)
+    monkeypatch.delenv("SGP_LABEL_THREAD_KERNEL")
+    fast = ctx.run("HostTreeGen", args, n=2000, rng=sg.RNG_PHILOX)
+    for st in range(4):
+        assert bytes(slow.stream(st)) == bytes(fast.stream(st))
+
+
 # ---- Philox throughput mode: distributions ---------------------------------------------------------------------------------------
 def ks_ok(a, b):
     return stats.ks_2samp(a, b).pvalue > 0.01
