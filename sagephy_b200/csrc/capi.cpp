@@ -112,9 +112,9 @@ const char* sgp_batch_stream_suffix(const sgp_batch* b, int s) { return (b && s 
 const int32_t* sgp_batch_status(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_info(); return b->b.status.data(); }
 const int32_t* sgp_batch_attempts(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_info(); return b->b.attempts.data(); }
 const int32_t* sgp_batch_sampled_leaves(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_info(); return b->b.sampled.data(); }
-const double* sgp_batch_root_times(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_info(); return b->b.root_time.data(); }
-const double* sgp_batch_total_times(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_info(); return b->b.total_time.data(); }
-const int32_t* sgp_batch_event_counts(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_info(); return b->b.events.data(); }
+const double* sgp_batch_root_times(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_stats(); return b->b.root_time.data(); }
+const double* sgp_batch_total_times(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_stats(); return b->b.total_time.data(); }
+const int32_t* sgp_batch_event_counts(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_stats(); return b->b.events.data(); }
 
 const char* sgp_batch_stdout(const sgp_batch* cb) {
     sgp_batch* b = const_cast<sgp_batch*>(cb);

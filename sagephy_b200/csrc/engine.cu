@@ -138,10 +138,24 @@ struct EventTimer {
 struct Context::Impl {
     cudaStream_t stream = nullptr;
     cudaStream_t copy = nullptr;
+    // Small device->host results (counts, totals, the summary block) travel through a mapped pinned mailbox written by a
+    // kernel, not through cudaMemcpy: a DMA copy would queue behind a caller's bulk copies that are still in flight on the
+    // copy stream (Batch::copy_stream_to_async) and stall the next batch's compute for their whole duration.
+    unsigned char* mailbox = nullptr; static constexpr size_t kMailboxBytes = 32768;
+    void post(size_t off, const void* dsrc, size_t bytes);
+    template <class T> T take(size_t off) const { T v; memcpy(&v, mailbox + off, sizeof(T)); return v; }
     DevBuf<unsigned long long> g_table; DevBuf<double> p10;
     MathTables T{};
     int sm_count = 148;
 };
+
+__global__ void k_post_words(uint32_t* dst, const uint32_t* src, int words) {
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+}
+void Context::Impl::post(size_t off, const void* dsrc, size_t bytes) {
+    if (off + bytes > kMailboxBytes || (bytes & 3) || (off & 3)) throw SgpError("internal: mailbox overflow");
+    k_post_words<<<1, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(mailbox + off), static_cast<const uint32_t*>(dsrc), (int)(bytes / 4));
+}
 
 Context::Context(int dev) : device(dev), impl(new Impl()) {
     int count = 0;
@@ -151,6 +165,7 @@ Context::Context(int dev) : device(dev), impl(new Impl()) {
     CK(cudaSetDevice(dev));
     CK(cudaStreamCreate(&impl->stream));
     CK(cudaStreamCreateWithFlags(&impl->copy, cudaStreamNonBlocking));
+    CK(cudaHostAlloc((void**)&impl->mailbox, Impl::kMailboxBytes, cudaHostAllocMapped | cudaHostAllocPortable));
     g_alloc_stream = impl->stream;
     { cudaMemPool_t pool; CK(cudaDeviceGetDefaultMemPool(&pool, dev)); unsigned long long thr = ~0ull; CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr)); }
     std::vector<unsigned long long> g(d2s_g_table(), d2s_g_table() + d2s_g_table_len());
@@ -166,6 +181,7 @@ Context::~Context() {
         impl->g_table.alloc(0); impl->p10.alloc(0);       // release pool memory before the stream goes away
         cudaStreamSynchronize(impl->stream); cudaStreamDestroy(impl->stream); impl->stream = nullptr; g_alloc_stream = nullptr;
         if (impl->copy) { cudaStreamSynchronize(impl->copy); cudaStreamDestroy(impl->copy); impl->copy = nullptr; }
+        if (impl->mailbox) { cudaFreeHost(impl->mailbox); impl->mailbox = nullptr; }
     }
 }
 
@@ -214,17 +230,50 @@ void Batch::fetch_offsets() {
     h_offsets.resize((size_t)8 * (n + 1));
     cudaMemcpy(h_offsets.data(), d_offsets, h_offsets.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
 }
+// Per-replicate fields are gathered into compact arrays on the device first, so a caller that only wants the status codes of a
+// large batch moves 12 bytes per replicate over PCIe instead of the 256-byte records.
+__global__ void k_gather_info_small(const RepInfo* info, long long n, int32_t* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { out[i] = info[i].status; out[n + i] = info[i].attempts; out[2 * n + i] = info[i].sampled_leaves; }
+}
+__global__ void k_gather_info_stats(const RepInfo* info, long long n, double* times, int32_t* events) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        times[i] = info[i].total_u; times[n + i] = info[i].p_root_time;
+        for (int e = 0; e < EV_COUNT; ++e) events[i * EV_COUNT + e] = info[i].cnt_u[e];
+    }
+}
 void Batch::fetch_info() {
     if (have_info || !d_info) return;
     cudaSetDevice(device);
-    std::vector<RepInfo> inf((size_t)n);
-    cudaMemcpy(inf.data(), d_info, inf.size() * sizeof(RepInfo), cudaMemcpyDeviceToHost);
-    status.resize(n); attempts.resize(n); sampled.resize(n); root_time.assign(n, 0.0); total_time.resize(n); events.resize((size_t)n * 17);
-    for (long long i = 0; i < n; ++i) {
-        status[i] = inf[i].status; attempts[i] = inf[i].attempts; sampled[i] = inf[i].sampled_leaves; total_time[i] = inf[i].total_u; root_time[i] = inf[i].p_root_time;
-        for (int e = 0; e < 17; ++e) events[(size_t)i * 17 + e] = inf[i].cnt_u[e];
+    status.resize(n); attempts.resize(n); sampled.resize(n);
+    if (n > 0) {
+        int32_t* tmp = nullptr;
+        // stream-ordered allocation on the default stream: cudaMalloc / cudaFree would synchronise the whole device, including a
+        // caller's copies that are still in flight on the copy stream
+        if (cudaMallocAsync(&tmp, (size_t)n * 3 * sizeof(int32_t), 0) != cudaSuccess) throw SgpError("out of device memory while fetching replicate status");
+        k_gather_info_small<<<(unsigned)((n + 255) / 256), 256>>>((const RepInfo*)d_info, n, tmp);
+        cudaMemcpy(status.data(), tmp, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+        cudaMemcpy(attempts.data(), tmp + n, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+        cudaMemcpy(sampled.data(), tmp + 2 * n, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+        cudaFreeAsync(tmp, 0);
     }
     have_info = true;
+}
+void Batch::fetch_stats() {
+    if (have_stats || !d_info) return;
+    cudaSetDevice(device);
+    root_time.assign(n, 0.0); total_time.resize(n); events.resize((size_t)n * 17);
+    if (n > 0) {
+        double* t = nullptr; int32_t* ev = nullptr;
+        if (cudaMallocAsync(&t, (size_t)n * 2 * sizeof(double), 0) != cudaSuccess || cudaMallocAsync(&ev, (size_t)n * EV_COUNT * sizeof(int32_t), 0) != cudaSuccess) { if (t) cudaFreeAsync(t, 0); throw SgpError("out of device memory while fetching replicate statistics"); }
+        k_gather_info_stats<<<(unsigned)((n + 255) / 256), 256>>>((const RepInfo*)d_info, n, t, ev);
+        cudaMemcpy(total_time.data(), t, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+        cudaMemcpy(root_time.data(), t + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+        cudaMemcpy(events.data(), ev, (size_t)n * EV_COUNT * sizeof(int32_t), cudaMemcpyDeviceToHost);
+        cudaFreeAsync(t, 0); cudaFreeAsync(ev, 0);
+    }
+    have_stats = true;
 }
 
 static TinyHost make_tiny(const HostModel& h) {
@@ -317,9 +366,9 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             redo.alloc((size_t)n); redo_count.alloc(1);
             CK(cudaMemsetAsync(redo_count.p, 0, sizeof(unsigned long long), st));
             k_collect_status<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(info.p, n, REP_NODE_OVERFLOW, redo.p, redo_count.p); ++tm.launches;
-            unsigned long long cnt = 0;
-            CK(cudaMemcpyAsync(&cnt, redo_count.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+            impl->post(0, redo_count.p, sizeof(unsigned long long));
             CK(cudaStreamSynchronize(st));
+            const unsigned long long cnt = impl->take<unsigned long long>(0);
             if (cnt == 0 || cap >= (1 << 24) || round > 8) break;
             keep.alloc((size_t)cnt);
             CK(cudaMemcpyAsync(keep.p, redo.p, cnt * sizeof(long long), cudaMemcpyDeviceToDevice, st));
@@ -339,12 +388,11 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, pool.p, node_off.p, (int)(n + 1), st);
         DevBuf<char> tmp; tmp.alloc(tb);
         cub::DeviceScan::ExclusiveSum(tmp.p, tb, pool.p, node_off.p, (int)(n + 1), st); ++tm.launches;
+        impl->post(0, node_off.p + n, sizeof(long long)); impl->post(8, max_pool_d.p, sizeof(int));
         CK(cudaStreamSynchronize(st));
     }
-    long long total_nodes = 0;
-    CK(cudaMemcpy(&total_nodes, node_off.p + n, sizeof(long long), cudaMemcpyDeviceToHost));
-    int max_pool = 0;
-    CK(cudaMemcpy(&max_pool, max_pool_d.p, sizeof(int), cudaMemcpyDeviceToHost));
+    const long long total_nodes = impl->take<long long>(0);
+    const int max_pool = impl->take<int>(8);
     DevBuf<Node> nodes; DevBuf<int32_t> aux;
     const long long aux_stride = std::max<long long>(total_nodes, 1);
     nodes.alloc((size_t)std::max<long long>(total_nodes, 1)); aux.alloc((size_t)aux_stride * 4);
@@ -461,8 +509,9 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     }
     tm.emit_size_ms = ph.stop();
     unsigned long long totals[ST_COUNT];
-    for (int s = 0; s < ST_COUNT; ++s) CK(cudaMemcpyAsync(&totals[s], offsets.p + (size_t)s * (n + 1) + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    for (int s = 0; s < ST_COUNT; ++s) impl->post((size_t)s * 8, offsets.p + (size_t)s * (n + 1) + n, sizeof(unsigned long long));
     CK(cudaStreamSynchronize(st));
+    for (int s = 0; s < ST_COUNT; ++s) totals[s] = impl->take<unsigned long long>((size_t)s * 8);
     for (int s = 0; s < ST_COUNT; ++s) { out.stream_bytes[s] = totals[s]; CK(cudaMallocAsync(&out.d_stream[s], std::max<unsigned long long>(totals[s], 1), st)); e.out[s] = out.d_stream[s]; }
     ph.start();
     tm.launches += launch_emit(true, e, emit_blocks, st);
@@ -473,7 +522,8 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     {
         DevBuf<DevSummary> ds; ds.alloc(1); CK(cudaMemsetAsync(ds.p, 0, sizeof(DevSummary), st));
         k_summary<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(info.p, n, ds.p); ++tm.launches;
-        DevSummary hs; CK(cudaMemcpyAsync(&hs, ds.p, sizeof(hs), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+        impl->post(0, ds.p, sizeof(DevSummary)); CK(cudaStreamSynchronize(st));
+        const DevSummary hs = impl->take<DevSummary>(0);
         Summary& S = out.summary; S.n_ok = (long long)hs.n_ok; S.n_failed = (long long)hs.n_failed; S.attempts_total = (long long)hs.attempts_total; S.vertices_sampled = (long long)hs.vertices; S.vertices_abandoned = (long long)hs.vertices_abandoned; S.attempts_completed = (long long)hs.attempts_completed;
         for (int i = 0; i < 17; ++i) S.event_counts[i] = (long long)hs.ev[i];
         for (int i = 0; i < 1025; ++i) S.leaf_hist[i] = (long long)hs.leaf_hist[i];
@@ -585,8 +635,9 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
             CK(cudaMemcpyAsync(sizes.p + (size_t)s * (n + 1), sizes_n.p + (size_t)s * n, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
             cub::DeviceScan::ExclusiveSum(tmp.p, tb, sizes.p + (size_t)s * (n + 1), offsets.p + (size_t)s * (n + 1), (int)(n + 1), st); ++tm.launches;
         }
-        for (int s = 0; s < 2; ++s) CK(cudaMemcpyAsync(&totals[s], offsets.p + (size_t)s * (n + 1) + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        for (int s = 0; s < 2; ++s) impl->post((size_t)s * 8, offsets.p + (size_t)s * (n + 1) + n, sizeof(unsigned long long));
         CK(cudaStreamSynchronize(st));
+        for (int s = 0; s < 2; ++s) totals[s] = impl->take<unsigned long long>((size_t)s * 8);
         tm.emit_size_ms = ph.stop();
         for (int s = 0; s < 2; ++s) { out.stream_bytes[s] = totals[s]; CK(cudaMallocAsync(&out.d_stream[s], std::max<unsigned long long>(totals[s], 1), st)); a.out[s] = out.d_stream[s]; }
         ph.start();
@@ -601,7 +652,7 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
     CK(cudaMemcpyAsync(out.status.data(), status.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out.attempts.data(), attempts.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    out.have_info = true;
+    out.have_info = true; out.have_stats = true;
     Summary& S = out.summary;
     for (long long i = 0; i < n; ++i) { if (out.status[i] == REP_OK) ++S.n_ok; else ++S.n_failed; S.attempts_total += out.attempts[i]; }
     S.vertices_sampled = slots; S.out_bytes[0] = (long long)totals[0]; S.out_bytes[1] = (long long)totals[1];

@@ -87,14 +87,15 @@ public:
     char* h_stream[8] = {nullptr};
     std::vector<unsigned long long> h_offsets;    // [8][n+1]
     std::vector<int32_t> status, attempts, sampled, events; std::vector<double> root_time, total_time;
-    bool have_info = false;
+    bool have_info = false, have_stats = false;
     Summary summary; Timings timings;
     const char* stream_host(int s);
     bool copy_stream_to(int s, void* dst);
     bool copy_stream_to_async(int s, void* dst, void* copy_stream);
     bool copy_offsets_to_async(int s, unsigned long long* dst, void* copy_stream);
     bool copy_offsets_to(int s, unsigned long long* dst);
-    void fetch_info();
+    void fetch_info();        // status, attempts, sampled leaves
+    void fetch_stats();       // tree times, event counts
     void fetch_offsets();
 };
 
