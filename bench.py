@@ -26,10 +26,19 @@ WORKLOAD = "C2: HostTreeGen -min 100 -max 100 -p 0.8 -a 10000 1.0 5.0 0.05, Phil
 C2_ARGS = ["-s", "20260101", "-min", "100", "-max", "100", "-p", "0.8", "-a", "10000", "1.0", "5.0", "0.05", "bench"]
 METRIC, UNIT = "accepted trees/sec", "trees/s"
 
-# Algorithmic instruction mix of one vertex expansion of the sampler (DESIGN.md "K1 roofline"): warp-level instructions
-# on the FP64 pipe and on the INT/other pipes needed by Philox4x32-10 + two 53-bit uniforms + fdlibm log + divide + compare.
-ALG_FP64_INST_PER_VERTEX = 38.0     # -log(1-u)/sum, start-bt, 3 compares (CUDA log: 1 MUFU.RCP64H + 24 DFMA/DADD/DMUL + reconstruction)
-ALG_INT_INST_PER_VERTEX = 70.0      # Philox4x32-10: 20 IMAD.WIDE + 20 LOP3 + 6 key adds; 2 x (bits -> double); counters, stack, select
+# Algorithmic instruction mix of one vertex expansion of the sampler (DESIGN.md "K1 roofline"), in warp-level instructions:
+#   FP64 pipe  : 1-u, exponent split, reciprocal (1 MUFU + 4 DFMA), s = f/(2+f), degree-7 polynomial in s^2, reconstruction,
+#                times 1/(lambda+mu), start - bt, bits -> second uniform, 3 compares                                  = 32
+#   IMAD.WIDE  : Philox4x32-10, two 32x32->64 products per round                                                       = 20
+#   other      : 20 three-input XORs of Philox, 4 for the two 52-bit mantissas, counters / leaf count / stack / selects = 40
+# FP64 and IMAD issue at half rate on B200 (measured below), so the bound is the sum of the three dispatch times.
+ALG_FP64_INST_PER_VERTEX = 32.0
+ALG_IMAD_INST_PER_VERTEX = 20.0
+ALG_ALU_INST_PER_VERTEX = 40.0
+# DRAM traffic per replicate from the `ncu --set full` capture profiles/r01_c2_full_metrics.csv (200 000 replicates per launch):
+# dram__bytes_read.sum + dram__bytes_write.sum of k_bd_find_single, and of the four k_emit<write> launches together.
+NCU_FIND_DRAM_BYTES_PER_REPLICATE = (0.008397 + 0.095860) * 1e9 / 200000
+NCU_EMIT_WRITE_DRAM_BYTES_PER_REPLICATE = (4.993873 + 2.746872 + 4.501460 + 2.103417 + 0.048675 + 0.013591 + 0.052093 + 0.010538) * 1e9 / 200000
 
 
 def clocks_sampler(stop, rows, gpu_index):
@@ -223,9 +232,11 @@ def main():
         verts = useful_attempts * verts_per_attempt
         verts_executed = float(total.vertices_sampled + total.vertices_abandoned)
         gverts = verts / (find_ms * 1e-3) * 1e-9
-        # issue-slot roofline of the sampler: a warp-vertex needs ALG_FP64 slots on the FP64 pipe and ALG_FP64 + ALG_INT issue slots
-        r_fp64 = peaks["dfma_ginst_per_s"]; r_issue = peaks["mixed_int_ginst_per_s"]
-        t_vertex_warp = max(ALG_FP64_INST_PER_VERTEX / r_fp64, (ALG_FP64_INST_PER_VERTEX + ALG_INT_INST_PER_VERTEX) / r_issue)     # ns per warp of 32 vertices
+        # issue roofline of the sampler: time of one warp-vertex = its FP64, IMAD and other instructions at their measured
+        # issue rates (the ALU rate follows from the IMAD+SHF+LOP3 mix probe: 3/R_mixed = 1/R_imad + 2/R_alu)
+        r_fp64 = peaks["dfma_ginst_per_s"]; r_imad = peaks["imad_ginst_per_s"]; r_mixed = peaks["mixed_int_ginst_per_s"]
+        r_alu = 2.0 / max(3.0 / r_mixed - 1.0 / r_imad, 1e-9)
+        t_vertex_warp = ALG_FP64_INST_PER_VERTEX / r_fp64 + ALG_IMAD_INST_PER_VERTEX / r_imad + ALG_ALU_INST_PER_VERTEX / r_alu     # ns per warp of 32 vertices
         peak_gverts = 32.0 / t_vertex_warp * world
         out_bytes = float(np.sum(total.out_bytes))
         emit_alg_bytes = out_bytes + float(total.event_counts.sum()) * (80 + 16)      # node records + order arrays read once, text written once
@@ -250,10 +261,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": int(float(eo[1]) / e_steps / world),
                     "replicates_per_gpu_per_step": ne, "steps": e_steps},
             "roofline": {"bound": "issue", "kernel": "k_bd_find", "achieved": gverts, "peak": peak_gverts, "unit": "Gvertex/s", "frac": gverts / peak_gverts,
-                         "traffic": None, "alg_inst_per_vertex": {"fp64": ALG_FP64_INST_PER_VERTEX, "int": ALG_INT_INST_PER_VERTEX},
-                         "measured_issue_peaks_ginst_per_s": peaks, "share_of_step": find_ms / dev_ms},
+                         "traffic": NCU_FIND_DRAM_BYTES_PER_REPLICATE * n, "traffic_unit": "bytes per launch (ncu, scaled from a 200k-replicate capture)",
+                         "alg_inst_per_vertex": {"fp64": ALG_FP64_INST_PER_VERTEX, "imad_wide": ALG_IMAD_INST_PER_VERTEX, "alu": ALG_ALU_INST_PER_VERTEX},
+                         "measured_issue_peaks_ginst_per_s": dict(peaks, alu_derived_ginst_per_s=r_alu), "share_of_step": find_ms / dev_ms},
             "roofline_emit": {"bound": "hbm", "kernel": "k_emit<write>", "achieved": emit_gbs, "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
-                              "frac": emit_gbs / hbm_peak, "traffic": None, "share_of_step": emitw_ms / dev_ms},
+                              "frac": emit_gbs / hbm_peak, "traffic": NCU_EMIT_WRITE_DRAM_BYTES_PER_REPLICATE * n, "algorithmic_bytes": emit_alg_bytes / K / world,
+                              "traffic_unit": "bytes per step over the four write launches (ncu, scaled from a 200k-replicate capture)", "share_of_step": emitw_ms / dev_ms},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": f"{cpu_n} replicates of the same workload (MT19937 stream), single thread, C++ restatement of the Java path"},
             "clocks": summarise_clocks(rows),
