@@ -72,6 +72,9 @@ typedef struct {
 
 /* BranchRelaxer only: the <tree> positional (file or string) holds one Newick tree per line; replicate i relaxes tree i % T. */
 #define SGP_FLAG_MULTI_TREE_INPUT 1
+/* Tree generators only: keep the vertex records of the accepted trees on the device so that the batch can feed
+ * sgp_relax_run_on_batch without a host round trip (costs ~100 bytes of HBM per vertex until the batch is freed). */
+#define SGP_FLAG_KEEP_TREES 2
 
 /* summary counters of a batch (merged across GPUs with an allreduce(sum) by the caller) */
 #define SGP_HIST_LEAF_BINS 1025
@@ -98,6 +101,17 @@ const char* sgp_last_error(const sgp_context* ctx);
 /* Runs `<app> argv...` for opts->n_replicates replicates. app = "HostTreeGen" | "GuestTreeGen" | "DomainTreeGen" |
  * "BranchRelaxer". Returns SGP_USAGE (with a batch holding the usage text) exactly when the reference would print usage. */
 sgp_status sgp_app_run(sgp_context* ctx, const char* app, int argc, const char* const* argv, const sgp_batch_opts* opts, sgp_batch** out);
+
+/* Chained stage: BranchRelaxer over the trees of a tree-generator batch that is still resident on the
+ * device — the in-memory equivalent of writing <prefix>.pruned.tree / .unpruned.tree per replicate and launching
+ * `java ... BranchRelaxer <that file> <model> <args>` on each (apps/SaGePhy/BranchRelaxerParameters.java:80-117 reads the file,
+ * io/NewickTreeReader.java:158-296 numbers its vertices in post-order). `src` must come from sgp_app_run with
+ * SGP_FLAG_KEEP_TREES and live on the same context; which_tree = SGP_STREAM_PRUNED_TREE or SGP_STREAM_UNPRUNED_TREE.
+ * argv is BranchRelaxer's own argv; its <tree> positional is only echoed in the "Arguments:" line of the .info stream.
+ * Replicate i relaxes tree (i mod n_src) with the seed / Philox coordinates of replicate i, so n_replicates = k * n_src gives
+ * k independent draws per tree. Source replicates that failed (or whose pruned tree is empty) yield SGP_REP_MODEL_ERROR. */
+sgp_status sgp_relax_run_on_batch(sgp_context* ctx, sgp_batch* src, int which_tree, int argc, const char* const* argv,
+                                  const sgp_batch_opts* opts, sgp_batch** out);
 
 /* Batch accessors. Stream s is the concatenation over replicates, replicate i occupying bytes [offsets[i], offsets[i+1]). */
 int64_t sgp_batch_n(const sgp_batch* b);

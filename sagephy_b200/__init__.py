@@ -24,11 +24,13 @@ EVENT_NAMES = ("SPECIATION", "CODIVERGENCE", "LEAF", "UNSAMPLED_LEAF", "DUPLICAT
     f"{k}_TRANSFER_{g}_{s}" for k in ("ADDITIVE", "REPLACING") for g in ("INTRAGENE", "INTERGENE") for s in ("INTRASPECIES", "INTERSPECIES"))
 RNG_PHILOX, RNG_MT_REPLAY = 0, 1
 FLAG_MULTI_TREE_INPUT = 1
+FLAG_KEEP_TREES = 2
+STREAM_UNPRUNED_TREE, STREAM_PRUNED_TREE = 0, 1
 STATUS_OK, STATUS_USAGE = 0, 6
 
 # every symbol include/sagephy_b200.h declares (checked by the CPU test-suite)
 EXPORTED_SYMBOLS = (
-    "sgp_context_create", "sgp_context_destroy", "sgp_last_error", "sgp_app_run", "sgp_batch_n", "sgp_batch_stream_data",
+    "sgp_context_create", "sgp_context_destroy", "sgp_last_error", "sgp_app_run", "sgp_relax_run_on_batch", "sgp_batch_n", "sgp_batch_stream_data",
     "sgp_batch_stream_device_data", "sgp_batch_stream_offsets", "sgp_batch_copy_stream", "sgp_batch_copy_offsets", "sgp_batch_copy_stream_async", "sgp_batch_copy_offsets_async", "sgp_context_wait_copies", "sgp_batch_stream_mask", "sgp_batch_values", "sgp_batch_stream_bytes", "sgp_batch_stream_suffix",
     "sgp_batch_status", "sgp_batch_attempts", "sgp_batch_sampled_leaves", "sgp_batch_root_times", "sgp_batch_total_times",
     "sgp_batch_event_counts", "sgp_batch_stdout", "sgp_batch_stderr", "sgp_batch_out_prefix", "sgp_batch_summary",
@@ -68,6 +70,7 @@ def load_library() -> C.CDLL:
     L.sgp_context_destroy.argtypes = [vp]
     L.sgp_last_error.argtypes = [vp]; L.sgp_last_error.restype = cp
     L.sgp_app_run.argtypes = [vp, cp, C.c_int, C.POINTER(cp), C.POINTER(BatchOpts), C.POINTER(vp)]; L.sgp_app_run.restype = C.c_int
+    L.sgp_relax_run_on_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(cp), C.POINTER(BatchOpts), C.POINTER(vp)]; L.sgp_relax_run_on_batch.restype = C.c_int
     L.sgp_batch_n.argtypes = [vp]; L.sgp_batch_n.restype = i64
     L.sgp_batch_stream_data.argtypes = [vp, C.c_int]; L.sgp_batch_stream_data.restype = vp
     L.sgp_batch_stream_device_data.argtypes = [vp, C.c_int]; L.sgp_batch_stream_device_data.restype = vp
@@ -288,6 +291,20 @@ class Context:
         b = Batch(self._lib, h, rc)
         if check and rc not in (STATUS_OK, STATUS_USAGE):
             raise SagephyError(f"{app} failed ({rc}): {self._lib.sgp_last_error(self._h).decode()} {b.stderr if h else ''}")
+        return b
+
+    def relax_on_batch(self, src: "Batch", args, which: int = 1, n: int = 0, rng: int = RNG_PHILOX, offset: int = 0, stream_mask: int = 0,
+                       keep_on_device: bool = False, check: bool = True) -> "Batch":
+        """Chained stage: ``BranchRelaxer args...`` over the trees of a generator batch made with FLAG_KEEP_TREES (no host
+        round trip). which = STREAM_PRUNED_TREE | STREAM_UNPRUNED_TREE; n = 0 means one replicate per source tree."""
+        argv = [str(a).encode() for a in args]
+        arr = (C.c_char_p * len(argv))(*argv)
+        opts = BatchOpts(n, offset, rng, stream_mask, 1 if keep_on_device else 0, 0)
+        h = C.c_void_p()
+        rc = self._lib.sgp_relax_run_on_batch(self._h, src._h, which, len(argv), arr, C.byref(opts), C.byref(h))
+        b = Batch(self._lib, h, rc)
+        if check and rc not in (STATUS_OK, STATUS_USAGE):
+            raise SagephyError(f"chained BranchRelaxer failed ({rc}): {self._lib.sgp_last_error(self._h).decode()} {b.stderr if h else ''}")
         return b
 
     def wait_copies(self):

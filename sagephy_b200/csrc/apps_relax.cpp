@@ -52,7 +52,7 @@ RelaxTreeTemplate make_template(const FlatTree& t, bool keep_interior) {
 }
 }  // namespace
 
-void parse_relax_app(const std::vector<std::string>& args, bool multi_tree_input, RelaxConfig& cfg, AppResult& res) {
+void parse_relax_app(const std::vector<std::string>& args, bool multi_tree_input, RelaxConfig& cfg, AppResult& res, bool trees_from_batch) {
     cfg.args = args;
     Parsed p = scan(args, kRelaxOpts, (int)(sizeof kRelaxOpts / sizeof kRelaxOpts[0]));
     if (p.on("-h") || args.empty()) {
@@ -106,6 +106,7 @@ void parse_relax_app(const std::vector<std::string>& args, bool multi_tree_input
     cfg.min_rate = to_double(p.str("-min", "1e-64")); cfg.max_rate = to_double(p.str("-max", "1e64")); cfg.max_attempts = to_int(p.str("-a", "10000"));
     cfg.do_meta = p.on("-x"); cfg.keep_interior = p.on("-innms");
     cfg.has_outfile = p.on("-o"); if (cfg.has_outfile) cfg.outfile = java_trim(p.str("-o", ""));
+    if (trees_from_batch) { (void)arg(0); return; }      // chained stage: the trees are already on the device
     const std::string text = exists(arg(0)) ? slurp(arg(0)) : arg(0);
     if (!multi_tree_input) cfg.trees.push_back(make_template(parse_newick(text), cfg.keep_interior));
     else {

@@ -57,7 +57,7 @@ sgp_status sgp_app_run(sgp_context* ctx, const char* app, int argc, const char* 
         if (o.rng_mode == SGP_RNG_MT_REPLAY && !cfg.has_seed) {
             // the reference would seed from /dev/random; replay of an unknown seed is meaningless but harmless
         }
-        BatchOpts bo; bo.n = o.n_replicates; bo.offset = o.replicate_offset; bo.rng_mode = o.rng_mode; bo.stream_mask = o.stream_mask; bo.keep_on_device = o.keep_on_device != 0;
+        BatchOpts bo; bo.n = o.n_replicates; bo.offset = o.replicate_offset; bo.rng_mode = o.rng_mode; bo.stream_mask = o.stream_mask; bo.keep_on_device = o.keep_on_device != 0; bo.keep_trees = (o.flags & SGP_FLAG_KEEP_TREES) != 0;
         ctx->ctx->run_treegen(cfg, bo, b->b);
         *out = b;
         return SGP_OK;
@@ -69,6 +69,33 @@ sgp_status sgp_app_run(sgp_context* ctx, const char* app, int argc, const char* 
         if (w.find("CUDA") != std::string::npos) return SGP_ERR_NO_DEVICE;
         if (w.find("Newick") != std::string::npos || w.find("NumberFormat") != std::string::npos) return SGP_ERR_PARSE;
         return SGP_ERR_INVALID_ARGUMENT;
+    } catch (std::exception& e) {
+        ctx->last_error = e.what(); b->b.err_text += e.what(); *out = b;
+        return SGP_ERR_INTERNAL;
+    }
+}
+
+sgp_status sgp_relax_run_on_batch(sgp_context* ctx, sgp_batch* src, int which_tree, int argc, const char* const* argv, const sgp_batch_opts* opts, sgp_batch** out) {
+    if (!ctx || !src || !out || argc < 0) return SGP_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (which_tree != SGP_STREAM_PRUNED_TREE && which_tree != SGP_STREAM_UNPRUNED_TREE) { ctx->last_error = "which_tree must be SGP_STREAM_PRUNED_TREE or SGP_STREAM_UNPRUNED_TREE"; return SGP_ERR_INVALID_ARGUMENT; }
+    if (src->owner != ctx || !src->b.d_nodes) { ctx->last_error = "source batch holds no trees on this context (run the generator with SGP_FLAG_KEEP_TREES)"; return SGP_ERR_INVALID_ARGUMENT; }
+    sgp_batch_opts o{}; if (opts) o = *opts; if (o.n_replicates <= 0) o.n_replicates = src->b.n;
+    std::vector<std::string> args; for (int i = 0; i < argc; ++i) args.emplace_back(argv[i] ? argv[i] : "");
+    auto* b = new sgp_batch(); b->owner = ctx;
+    try {
+        RelaxConfig rc; AppResult rr;
+        parse_relax_app(args, false, rc, rr, true);
+        b->b.out_text = rr.out_text; b->b.err_text = rr.err_text;
+        if (rr.status == 6) { *out = b; return SGP_USAGE; }
+        if (rr.status != 0) { ctx->last_error = rr.err_text; *out = b; return (sgp_status)rr.status; }
+        BatchOpts bo; bo.n = o.n_replicates; bo.offset = o.replicate_offset; bo.rng_mode = o.rng_mode; bo.stream_mask = o.stream_mask; bo.keep_on_device = o.keep_on_device != 0;
+        ctx->ctx->run_relax(rc, bo, b->b, &src->b, which_tree == SGP_STREAM_PRUNED_TREE);
+        *out = b;
+        return SGP_OK;
+    } catch (SgpError& e) {
+        ctx->last_error = e.what(); b->b.err_text += std::string(e.what()) + "\n"; *out = b;
+        return std::string(e.what()).find("CUDA") != std::string::npos ? SGP_ERR_NO_DEVICE : SGP_ERR_INVALID_ARGUMENT;
     } catch (std::exception& e) {
         ctx->last_error = e.what(); b->b.err_text += e.what(); *out = b;
         return SGP_ERR_INTERNAL;

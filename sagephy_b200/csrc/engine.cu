@@ -191,7 +191,7 @@ Batch::~Batch() {
     // plain cudaFree: the owning context (and its stream) may already be gone when a batch is released
     auto rel = [&](void* q) { if (q) cudaFree(q); };
     for (int s = 0; s < 8; ++s) { rel(d_stream[s]); if (h_stream[s]) cudaFreeHost(h_stream[s]); }
-    rel(d_offsets); rel(d_info); rel(d_values[0]); rel(d_values[1]);
+    rel(d_offsets); rel(d_info); rel(d_values[0]); rel(d_values[1]); rel(d_nodes); rel(d_aux); rel(d_node_off);
 }
 const char* Batch::stream_host(int s) {
     if (s < 0 || s >= 8) return nullptr;
@@ -530,6 +530,10 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         for (int s = 0; s < ST_COUNT; ++s) S.out_bytes[s] = (long long)totals[s];
     }
     out.d_offsets = offsets.release(); out.d_info = info.release();
+    if (opts.keep_trees) {
+        out.d_nodes = nodes.release(); out.d_aux = aux.release(); out.d_node_off = node_off.release(); out.aux_stride = aux_stride;
+        out.name_prefix = cfg.vertex_prefix; out.name_append_sigma = cfg.append_sigma;
+    }
     static const char* host_sfx[8] = {".unpruned.tree", ".pruned.tree", ".unpruned.info", ".pruned.info", ".unpruned.guest2host", ".pruned.guest2host", ".unpruned.leafmap", ".pruned.leafmap"};
     for (int s = 0; s < 8; ++s) out.suffix[s] = (mask & (1u << s)) ? host_sfx[s] : "";
     out.stream_mask = mask;
@@ -554,7 +558,7 @@ const double* Batch::values_host(int which) {
     return h_values[which].data();
 }
 
-void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& out) {
+void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& out, const Batch* src, bool src_pruned) {
     CK(cudaSetDevice(device));
     cudaStream_t st = impl->stream; g_alloc_stream = st;
     const long long n = opts.n;
@@ -563,11 +567,30 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
     out.stream = (void*)st; out.n = n; out.device = device; out.app = 3; out.quiet = !cfg.has_outfile; out.out_prefix = cfg.outfile;
     Timings tm; EventTimer total(st), ph(st); total.start();
 
-    // flatten the tree templates
-    const int T = (int)cfg.trees.size();
-    std::vector<RelaxTreeView> views(T); std::vector<double> orig; std::vector<int16_t> chain; std::vector<uint8_t> flags; std::vector<int32_t> name_off; std::string blob;
+    // tree templates: flattened host templates, or (chained stage) ingested on the device from a generator batch
+    const bool chained = src != nullptr;
+    if (chained && (!src->d_nodes || !src->d_info || src->device != device)) throw SgpError("source batch holds no trees on this device");
+    const int T = chained ? (int)src->n : (int)cfg.trees.size();
+    std::vector<RelaxTreeView> views(chained ? 0 : T); std::vector<double> orig; std::vector<int16_t> chain; std::vector<uint8_t> flags; std::vector<int32_t> name_off; std::string blob;
     long long sum_v = 0;
-    for (int t = 0; t < T; ++t) {
+    DevBuf<RelaxTreeView> d_views; DevBuf<double> d_orig; DevBuf<int16_t> d_chain; DevBuf<uint8_t> d_flags; DevBuf<int32_t> d_name, d_num, d_sig;
+    if (chained) {
+        IngestArgs g{}; g.n_src = src->n; g.info = (const RepInfo*)src->d_info; g.node_off = src->d_node_off; g.nodes = (const Node*)src->d_nodes;
+        g.aux = src->d_aux; g.aux_stride = src->aux_stride; g.pruned = src_pruned ? 1 : 0; g.keep_interior = cfg.keep_interior ? 1 : 0;
+        DevBuf<long long> nv, v0; nv.alloc((size_t)T + 1); v0.alloc((size_t)T + 1);
+        g.nv = nv.p; launch_ingest_count(g, st); ++tm.launches;
+        size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, nv.p, v0.p, T + 1, st);
+        DevBuf<char> tmp; tmp.alloc(tb);
+        cub::DeviceScan::ExclusiveSum(tmp.p, tb, nv.p, v0.p, T + 1, st); ++tm.launches;
+        impl->post(0, v0.p + T, sizeof(long long)); CK(cudaStreamSynchronize(st));
+        sum_v = impl->take<long long>(0);
+        const size_t cnt = (size_t)std::max<long long>(sum_v, 1);
+        d_views.alloc((size_t)T); d_orig.alloc(cnt); d_chain.alloc(cnt); d_flags.alloc(cnt); d_num.alloc(cnt); d_sig.alloc(cnt);
+        g.v0 = v0.p; g.views = d_views.p; g.orig = d_orig.p; g.chain = d_chain.p; g.vflags = d_flags.p; g.number = d_num.p; g.sigma = d_sig.p;
+        launch_ingest_fill(g, st); ++tm.launches;
+        CK(cudaGetLastError()); CK(cudaStreamSynchronize(st));          // nv / v0 go out of scope here
+    }
+    for (int t = 0; t < T && !chained; ++t) {
         const RelaxTreeTemplate& tt = cfg.trees[t];
         views[t].nV = tt.nV; views[t].root = tt.root; views[t].ignore = tt.ignore; views[t].v0 = sum_v; sum_v += tt.nV;
         orig.insert(orig.end(), tt.orig.begin(), tt.orig.end()); chain.insert(chain.end(), tt.chain.begin(), tt.chain.end()); flags.insert(flags.end(), tt.flags.begin(), tt.flags.end());
@@ -590,9 +613,13 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
         for (auto& kv : cfg.params) tail += "\t" + kv.first + "\t" + kv.second + "\n";
         add(tail, a.model_tail_off, a.model_tail_len);
     }
-    DevBuf<RelaxTreeView> d_views; d_views.upload(views);
-    DevBuf<double> d_orig, d_samples, rates, relaxed; d_orig.upload(orig); d_samples.upload(cfg.samples);
-    DevBuf<int16_t> d_chain; d_chain.upload(chain); DevBuf<uint8_t> d_flags; d_flags.upload(flags); DevBuf<int32_t> d_name; d_name.upload(name_off);
+    DevBuf<double> d_samples, rates, relaxed; d_samples.upload(cfg.samples);
+    if (!chained) { d_views.upload(views); d_orig.upload(orig); d_chain.upload(chain); d_flags.upload(flags); d_name.upload(name_off); }
+    else {
+        a.syn_names = 1; a.syn_number = d_num.p; a.syn_sigma = d_sig.p; a.syn_append_sigma = src->name_append_sigma ? 1 : 0;
+        if (src->name_prefix.size() > sizeof(a.syn_prefix)) throw SgpError("vertex prefix longer than 24 bytes is not supported");
+        a.syn_prefix_len = (int)src->name_prefix.size(); memcpy(a.syn_prefix, src->name_prefix.data(), src->name_prefix.size());
+    }
     DevBuf<char> d_blob; { std::vector<char> b(blob.begin(), blob.end()); b.push_back(0); d_blob.upload(b); }
     rates.alloc((size_t)slots); relaxed.alloc((size_t)slots);
     DevBuf<int32_t> attempts, status; attempts.alloc((size_t)n); status.alloc((size_t)n);
@@ -610,7 +637,8 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
         // status 0 -> REP_PENDING marker expected by the kernel
         launch_relax_rates(true, a, 0, 0, st); ++tm.launches;
     } else {
-        launch_relax_apply(a, slots, st); tm.launches += 2;          // attempt 0 in parallel
+        if (chained) launch_relax_apply_per_rep(a, st); else launch_relax_apply(a, slots, st);          // attempt 0 in parallel
+        tm.launches += 2;
         launch_relax_rates(false, a, 1, 1, st); ++tm.launches;       // flagged replicates continue from attempt 1
     }
     CK(cudaGetLastError());

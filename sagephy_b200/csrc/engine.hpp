@@ -52,6 +52,7 @@ struct BatchOpts {
     unsigned stream_mask = 0;
     bool keep_on_device = false;
     bool multi_tree_input = false;
+    bool keep_trees = false;  // tree generators: leave the vertex records on the device for a chained stage
 };
 
 struct Timings { double find_ms = 0, build_ms = 0, label_ms = 0, emit_size_ms = 0, emit_write_ms = 0, d2h_ms = 0, total_ms = 0; long long launches = 0; };
@@ -79,6 +80,9 @@ public:
     char* d_stream[8] = {nullptr}; unsigned long long stream_bytes[8] = {0};
     unsigned long long* d_offsets = nullptr;      // [8][n+1]
     void* d_info = nullptr;                       // RepInfo[n]
+    // kept only with BatchOpts::keep_trees: vertex records, order arrays (4 x aux_stride), first record of each replicate
+    void* d_nodes = nullptr; int32_t* d_aux = nullptr; long long* d_node_off = nullptr; long long aux_stride = 0;
+    std::string name_prefix; bool name_append_sigma = false;
     unsigned stream_mask = 0;
     double* d_values[2] = {nullptr, nullptr}; long long n_values = 0;   // BranchRelaxer: rates, relaxed lengths (flat, replicate-major)
     std::vector<double> h_values[2];
@@ -107,7 +111,8 @@ public:
     std::string last_error;
     struct Impl; std::unique_ptr<Impl> impl;
     void run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch& out);
-    void run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& out);
+    // src != nullptr: chained run over the trees of a tree-generator batch (pruned or unpruned view), cfg.trees is ignored
+    void run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& out, const Batch* src = nullptr, bool src_pruned = true);
     void* copy_stream();          // second CUDA stream for device->host copies that overlap the next batch's kernels
     void wait_copies();
     void probe_d2s(const double* v, long long n, char* out);
@@ -119,6 +124,6 @@ public:
 // apps.cpp: reference CLI grammar -> configs
 struct AppResult { int status = 0; std::string out_text, err_text; };   // status: 0 run, 6 usage, other = error code
 void parse_treegen_app(const std::string& app, const std::vector<std::string>& args, TreeGenConfig& cfg, AppResult& res);
-void parse_relax_app(const std::vector<std::string>& args, bool multi_tree_input, RelaxConfig& cfg, AppResult& res);
+void parse_relax_app(const std::vector<std::string>& args, bool multi_tree_input, RelaxConfig& cfg, AppResult& res, bool trees_from_batch = false);
 
 }  // namespace sgp

@@ -9,6 +9,12 @@ void launch_relax_apply(const RelaxArgs& a, long long total_slots, cudaStream_t 
     k_relax_apply<<<(unsigned)((total_slots + 255) / 256), 256, 0, st>>>(a, total_slots);
     k_relax_finish_apply<<<(unsigned)((a.n + 255) / 256), 256, 0, st>>>(a);
 }
+void launch_relax_apply_per_rep(const RelaxArgs& a, cudaStream_t st) {
+    k_relax_apply_per_rep<<<(unsigned)a.n, 256, 0, st>>>(a);
+    k_relax_finish_apply<<<(unsigned)((a.n + 255) / 256), 256, 0, st>>>(a);
+}
+void launch_ingest_count(const IngestArgs& g, cudaStream_t st) { k_ingest_count<<<(unsigned)((g.n_src + 256) / 256), 256, 0, st>>>(g); }
+void launch_ingest_fill(const IngestArgs& g, cudaStream_t st) { k_ingest_fill<<<(unsigned)((g.n_src * 32 + 255) / 256), 256, 0, st>>>(g); }
 void launch_relax_emit(bool write, const RelaxArgs& a, cudaStream_t st) {
     const unsigned blocks = (unsigned)((a.n * 32 + kEmitWarps * 32 - 1) / (kEmitWarps * 32));
     if (write) k_relax_emit<true><<<blocks, kEmitWarps * 32, 0, st>>>(a); else k_relax_emit<false><<<blocks, kEmitWarps * 32, 0, st>>>(a);

@@ -135,6 +135,8 @@ struct RelaxArgs {
     const uint8_t* vflags;             // bit0: leaf, bit1: a ',' follows (not the last child), bit2: print the name
     const int32_t* name_off;           // offset/len pairs into blob
     const char* blob;
+    // chained stage (trees ingested from a tree-generator batch): names are <prefix><number>[_<sigma>] as the generator prints them
+    int syn_names; const int32_t* syn_number; const int32_t* syn_sigma; char syn_prefix[24]; int syn_prefix_len, syn_append_sigma;
     MathTables T;
     double* rates; double* relaxed;    // [total vertex slots]
     int32_t* attempts; int32_t* status;// [n]
@@ -147,6 +149,15 @@ struct RelaxArgs {
     unsigned long long* sizes;                     // [2][n]
     const unsigned long long* offsets;             // [2][n+1]
     char* out[2];
+};
+
+// Device-side ingest of generator trees into BranchRelaxer templates (chained stage).
+struct IngestArgs {
+    long long n_src; const RepInfo* info; const long long* node_off; const Node* nodes; const int32_t* aux; long long aux_stride;
+    int pruned, keep_interior;
+    long long* nv;                     // [n_src + 1] vertices per tree (0: unusable source replicate), then scanned into v0
+    const long long* v0;
+    RelaxTreeView* views; double* orig; int16_t* chain; uint8_t* vflags; int32_t* number; int32_t* sigma;
 };
 
 }  // namespace sgp

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(128) k_relax_rates(RelaxArgs a, int first_atte
     if (only_flagged && a.status[r] != REP_PENDING) return;
     const RelaxTreeView* tv; const long long base = relax_slot(a, r, &tv);
     const int nV = tv->nV; const unsigned long long gid = (unsigned long long)(a.rep_base + r);
+    if (nV == 0) { a.status[r] = REP_MODEL_ERROR; a.attempts[r] = 0; return; }       // chained stage: the source replicate has no tree
     MtStream mt; GaussCache gc{false, 0.0};
     if (REPLAY) { const int worker = blockIdx.x * blockDim.x + threadIdx.x; mt.mt = a.mt_state + (size_t)(worker >> 5) * 624 * 32 + (worker & 31); mt.stride = 32;
                   uint32_t key[4]; seed_words_i64((long long)a.seed + (long long)gid, key); mt.seed(key); }
@@ -124,17 +125,71 @@ __global__ void __launch_bounds__(256) k_relax_apply(RelaxArgs a, long long tota
     if (err) atomicMax(&a.status[r], (int)REP_MODEL_ERROR);
     else if (x != tv.ignore && (rate < a.min_rate || rate > a.max_rate)) atomicMax(&a.status[r], (int)REP_PENDING);
 }
+// Same work with one block per replicate: used when every replicate has its own tree (chained stage), where the slot -> tree
+// search of k_relax_apply would be a 20-step binary search per vertex.
+__global__ void __launch_bounds__(256) k_relax_apply_per_rep(RelaxArgs a) {
+    const long long r = blockIdx.x;
+    const RelaxTreeView* tvp; const long long base = relax_slot(a, r, &tvp);
+    const RelaxTreeView tv = *tvp;
+    for (int x = threadIdx.x; x < tv.nV; x += blockDim.x) {
+        MtStream mt; GaussCache gc{false, 0.0}; int err = 0;
+        const double rate = draw_rate<false>(a, mt, gc, (unsigned long long)(a.rep_base + r), 0u, x, &err);
+        a.rates[base + x] = rate;
+        a.relaxed[base + x] = XMUL(a.orig[tv.v0 + x], rate);
+        if (err) atomicMax(&a.status[r], (int)REP_MODEL_ERROR);
+        else if (x != tv.ignore && (rate < a.min_rate || rate > a.max_rate)) atomicMax(&a.status[r], (int)REP_PENDING);
+    }
+}
 __global__ void k_relax_finish_apply(RelaxArgs a) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.n) return;
+    if (a.trees[r % a.n_trees].nV == 0) { a.status[r] = REP_MODEL_ERROR; a.attempts[r] = 0; return; }
     if (a.status[r] == 0) { a.status[r] = REP_OK; a.attempts[r] = 1; }       // status was zero-initialised == "no violation seen"
+}
+
+// ---- chained stage: generator trees -> templates ---------------------------------------------------------------------------
+// What io/NewickTreeReader.java:158-296 + BranchRelaxer.java:79-93 would extract from the generator's own Newick text: vertices
+// numbered in post-order (= the order the text lists them), lengths (Double.toString round-trips, so the parsed value is the
+// stored double), leaf / sibling structure, names.
+__global__ void k_ingest_count(IngestArgs g) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > g.n_src) return;
+    long long nv = 0;
+    if (r < g.n_src && g.info[r].status == REP_OK) nv = g.pruned ? g.info[r].n_p : g.info[r].n_u;
+    g.nv[r] = nv;
+}
+__global__ void __launch_bounds__(256) k_ingest_fill(IngestArgs g) {
+    const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= g.n_src) return;
+    const long long v0 = g.v0[r]; const int nV = (int)(g.v0[r + 1] - v0);
+    if (lane == 0) { RelaxTreeView tv; tv.nV = nV; tv.root = nV - 1; tv.ignore = -1; tv.v0 = v0; g.views[r] = tv; }
+    if (nV == 0) return;
+    const Node* N = g.nodes + g.node_off[r];
+    const int32_t* ord = g.aux + (g.pruned ? g.aux_stride : 0) + g.node_off[r];        // post-order of the chosen view
+    for (int k = lane; k < nV; k += 32) {
+        const Node& x = N[ord[k]];
+        const bool leaf = g.pruned ? x.p_left < 0 : x.left < 0;
+        uint8_t f = leaf ? 1 : 0;
+        if (x.flags & (g.pruned ? NF_LEFT_P : NF_LEFT_U)) f |= 2;      // a first child: a ',' follows it
+        if (leaf || g.keep_interior) f |= 4;
+        g.orig[v0 + k] = g.pruned ? x.p_bl : x.bl;
+        g.chain[v0 + k] = g.pruned ? x.chain_p : x.chain_u;
+        g.vflags[v0 + k] = f; g.number[v0 + k] = x.number; g.sigma[v0 + k] = x.sigma;
+    }
 }
 
 // ---- emission -------------------------------------------------------------------------------------------------------------------
 template <class Sink> __device__ void put_relax_vertex(Sink& s, const RelaxArgs& a, const RelaxTreeView& tv, long long base, int x) {
     const long long t = tv.v0 + x; const uint8_t f = a.vflags[t];
     if (f & 1) { for (int i = 0; i < a.chain[t]; ++i) s.put('('); } else s.put(')');
-    if (f & 4) put_blob(s, a.blob, a.name_off[2 * t], a.name_off[2 * t + 1]);
+    if (f & 4) {
+        if (a.syn_names) {
+            for (int i = 0; i < a.syn_prefix_len; ++i) s.put(a.syn_prefix[i]);
+            put_i64(s, a.syn_number[t]);
+            if (a.syn_append_sigma) { s.put('_'); put_i64(s, a.syn_sigma[t]); }
+        } else put_blob(s, a.blob, a.name_off[2 * t], a.name_off[2 * t + 1]);
+    }
     const double len = a.relaxed[base + x];
     if (len == len) { s.put(':'); put_double(s, a.T, len); }
     if (a.do_meta) {
@@ -194,10 +249,29 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) k_relax_emit(RelaxArgs a) 
         uint16_t* pl = a.plen_info + 3 * base + 8 * r;
         unsigned long long bytes = 0;
         if (ok) {
-            const int np = 3 + 3 * tv.nV + 1; const int att = a.attempts[r];
-            auto pc = [&](auto& s, int k) { put_relax_info(s, a, tv, base, gid, att, k); };
-            if (WRITE) bytes = emit_pieces<true>(np, out, stage, pc, [&](int i) { return (unsigned)pl[i]; }, no_store);
-            else bytes = emit_pieces<false>(np, out, stage, pc, no_load, [&](int i, unsigned v) { pl[i] = (uint16_t)v; });
+            // lines 0-1 ("# BRANCHLENGTHRELAXER" and "Arguments: [...]", which may embed whole Newick trees and exceed the 16-bit
+            // piece-length cache): warp-cooperative copy, length known in closed form
+            const char* h0 = "# BRANCHLENGTHRELAXER\nArguments:\t"; const int h0len = 33;
+            const long long seedv = a.seed_base + gid;
+            const int seedlen = a.seed_mode ? (seedv < 0 ? 1 : 0) + dec_len_u64((uint64_t)(seedv < 0 ? -seedv : seedv)) : 0;
+            if (WRITE) {
+                for (int i = lane; i < h0len; i += 32) out[i] = h0[i];
+                for (int i = lane; i < a.args_pre_len; i += 32) out[h0len + i] = a.blob[a.args_pre_off + i];
+            }
+            unsigned long long o = (unsigned long long)h0len + a.args_pre_len;
+            if (a.seed_mode) {
+                if (WRITE) {
+                    if (lane == 0) { MemSink m{out + o}; put_i64(m, seedv); }
+                    for (int i = lane; i < a.args_post_len; i += 32) out[o + seedlen + i] = a.blob[a.args_post_off + i];
+                }
+                o += (unsigned long long)seedlen + a.args_post_len;
+            }
+            if (WRITE && lane == 0) out[o] = '\n';
+            o += 1;
+            const int np = 1 + 3 * tv.nV + 1; const int att = a.attempts[r];
+            auto pc = [&](auto& s, int k) { put_relax_info(s, a, tv, base, gid, att, k + 2); };
+            if (WRITE) bytes = o + emit_pieces<true>(np, out + o, stage, pc, [&](int i) { return (unsigned)pl[i]; }, no_store);
+            else bytes = o + emit_pieces<false>(np, out, stage, pc, no_load, [&](int i, unsigned v) { pl[i] = (uint16_t)v; });
         }
         if (!WRITE && lane == 0) a.sizes[(size_t)a.n + r] = bytes;
     }

@@ -12,5 +12,8 @@ int launch_label_prune(LabelArgs a, int max_pool, int sm_count, cudaStream_t st)
 int launch_emit(bool write, const EmitArgs& a, unsigned blocks, cudaStream_t st);   // returns the number of kernels launched
 void launch_relax_rates(bool replay, const RelaxArgs& a, int first_attempt, int only_flagged, cudaStream_t st);
 void launch_relax_apply(const RelaxArgs& a, long long total_slots, cudaStream_t st);
+void launch_relax_apply_per_rep(const RelaxArgs& a, cudaStream_t st);
+void launch_ingest_count(const IngestArgs& g, cudaStream_t st);
+void launch_ingest_fill(const IngestArgs& g, cudaStream_t st);
 void launch_relax_emit(bool write, const RelaxArgs& a, cudaStream_t st);
 }  // namespace sgp

@@ -349,6 +349,60 @@ def test_branch_relaxer_philox_matches_reference_distributions(ctx):
     assert stats.kstest(g[::7], "gamma", args=(2, 0, 0.5)).pvalue > 0.001
 
 
+# ---- chained stage: generator batch -> BranchRelaxer without a host round trip --------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", [sg.STREAM_PRUNED_TREE, sg.STREAM_UNPRUNED_TREE], ids=["pruned", "unpruned"])
+def test_chained_relaxer_equals_reference_on_the_emitted_newick(ctx, which):
+    # The chained stage must give what the reference gives when BranchRelaxer is launched on each emitted tree file.
+    # "-min 0" on the generator makes some pruned trees empty (";"): those replicates must fail, not crash.
+    gen_args = ["-s", "21", "-min", "0", "-max", "40", "-minper", "0", HOST8, "0.5", "0.4", "0.5", "g"]
+    n = 24
+    src = ctx.run("GuestTreeGen", gen_args, n=n, rng=sg.RNG_MT_REPLAY, flags=sg.FLAG_KEEP_TREES)
+    for model in (["IIDLogNormal", "0", "0.25"], ["IIDGamma", "2", "0.5"], ["IIDUniform", "0.5", "1.5"]):
+        for extra in ([], ["-x", "-innms"]):
+            args = ["-s", "300"] + extra + ["chained-input"] + model
+            out = ctx.relax_on_batch(src, args, which=which, rng=sg.RNG_MT_REPLAY)
+            assert out.n == n
+            n_checked = 0
+            for i in range(n):
+                text = src.replicate(which, i).decode()
+                if src.rep_status[i] != 0 or text.strip() in ("", ";"):
+                    assert out.rep_status[i] != 0
+                    continue
+                want = oracle_run("BranchRelaxer", ["-s", str(300 + i)] + extra + [text.strip()] + model)
+                if want["status"] != 0 or not want["stdout"]:
+                    assert out.rep_status[i] != 0, (i, want["stderr"][:200])
+                    continue
+                assert out.rep_status[i] == 0, (i, out.rep_status[i])
+                assert out.replicate(0, i).decode() == want["stdout"], (which, model, extra, i)
+                n_checked += 1
+            assert n_checked >= n // 2
+            out.free()
+    src.free()
+
+
+@pytest.mark.gpu
+def test_chained_relaxer_equals_text_path_in_throughput_mode(ctx):
+    # Philox mode: chaining on the device and re-parsing the emitted text on the host must give the same bytes, also with
+    # several draws per tree (replicate i relaxes tree i mod n_src).
+    n = 500
+    src = ctx.run("HostTreeGen", ["-s", "5", "-min", "4", "-max", "30", "-p", "0.8", "1.0", "3.0", "0.3", "h"], n=n, rng=sg.RNG_PHILOX, flags=sg.FLAG_KEEP_TREES)
+    assert (src.rep_status == 0).all()
+    trees = "".join(src.replicate(sg.STREAM_PRUNED_TREE, i).decode() for i in range(n))
+    for args in (["-s", "9", "-o", "r", "x", "IIDLogNormal", "0", "0.25"], ["-s", "9", "-x", "x", "IIDGamma", "2", "0.5"]):
+        chained = ctx.relax_on_batch(src, args, which=sg.STREAM_PRUNED_TREE, n=3 * n, rng=sg.RNG_PHILOX)
+        targs = list(args); targs[targs.index("x")] = trees
+        text = ctx.run("BranchRelaxer", targs, n=3 * n, rng=sg.RNG_PHILOX, flags=sg.FLAG_MULTI_TREE_INPUT)
+        assert (chained.rep_status == text.rep_status).all()
+        assert bytes(chained.stream(0)) == bytes(text.stream(0))
+        np.testing.assert_array_equal(chained.values(1), text.values(1))
+        chained.free(); text.free()
+    # a batch made without FLAG_KEEP_TREES cannot be chained
+    plain = ctx.run("HostTreeGen", ["-s", "5", "1.0", "3.0", "0.3", "h"], n=4, rng=sg.RNG_PHILOX)
+    with pytest.raises(sg.SagephyError):
+        ctx.relax_on_batch(plain, ["x", "IIDLogNormal", "0", "0.25"])
+
+
 # ---- DomainTreeGen ---------------------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def gene_dir(tmp_path_factory):
