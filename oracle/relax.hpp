@@ -12,6 +12,7 @@
 #pragma once
 #include "apps.hpp"
 #include "jpow.hpp"
+#include <set>
 
 namespace oracle {
 
@@ -128,11 +129,73 @@ inline double chi2_quantile(double p, double k) {     // math/ChiSquared.java:23
 }
 
 struct RateModelO {
-    enum Kind { CONSTANT, EXPONENTIAL, GAMMA, LOGNORMAL, NORMAL, UNIFORM, SAMPLES } kind = CONSTANT;
-    double a = 0, b = 0, sigma = 0; std::vector<double> samples; std::string file;
+    enum Kind { CONSTANT, EXPONENTIAL, GAMMA, LOGNORMAL, NORMAL, UNIFORM, SAMPLES, ACTK98, ACRY07, ACABY02, ACLBPL07 } kind = CONSTANT;
+    double a = 0, b = 0, c = 0, d = 0, sigma = 0; std::vector<double> samples; std::string file;
     std::string name() const {
-        static const char* n[] = {"ConstantRates", "IIDExponentialRates", "IIDGammaRates", "IIDLogNormalRates", "IIDNormalRates", "IIDUniformRates", "IIDSamplesFromFileRates"};
+        static const char* n[] = {"ConstantRates", "IIDExponentialRates", "IIDGammaRates", "IIDLogNormalRates", "IIDNormalRates", "IIDUniformRates", "IIDSamplesFromFileRates",
+                                  "ThorneKishino98Rates", "RannalaYang07Rates", "ArisBrosouYang02Rates", "LepageBryantPhillipeLartillot07Rates"};
         return n[kind];
+    }
+    bool strict_tree() const { return kind == ACTK98 || kind == ACRY07; }      // lengthsMustBeUltrametric()
+    // new LogNormalDistribution(mu, sigma2).sampleValue(prng)  (math/LogNormalDistribution.java:39-48,196-205)
+    static double lognormal(double mu, double sigma2, JavaMT& prng) {
+        if (sigma2 <= 0.0) throw std::invalid_argument("IllegalArgumentException: Cannot have non-positive sigma^2 for log-normal distribution.");
+        const double sg = std::sqrt(sigma2);
+        return j_exp(normal_quantile(prng.nextDouble()) * sg + mu);
+    }
+    // getRates of the autocorrelated models: vertices in RTree.getTopologicalOrdering() order (breadth first from the root,
+    // topology/RTree.java:488-500); topo[i] / parent[] hold vertex numbers.
+    void rates_autocorrelated(const std::vector<int>& topo, const std::vector<int>& parent, const std::vector<double>& len, JavaMT& prng, std::vector<double>& rates) const {
+        const int n = (int)topo.size();
+        if (kind == ACTK98) {                       // apps/SaGePhy/ACThorneKishino98RateModel.java:58-74
+            rates[topo[0]] = a;
+            for (int i = 1; i < n; ++i) {
+                const int x = topo[i], xp = parent[x];
+                const double deltat = (len[x] + len[xp]) / 2;
+                const double sigma2 = b * deltat;
+                rates[x] = lognormal(j_log(rates[xp]) - sigma2 / 2, sigma2, prng);
+            }
+        } else if (kind == ACRY07) {                // apps/SaGePhy/ACRannalaYang07RateModel.java:56-88
+            std::vector<double> vr(n);
+            const int root = topo[0]; double dt = len[root];
+            if (dt == 0.0) { rates[root] = a; vr[root] = a; }
+            else {
+                double r = lognormal(j_log(a) - dt * b / 2, dt * b, prng); rates[root] = r;
+                r = lognormal(j_log(r) - dt * b / 2, dt * b, prng); vr[root] = r;
+            }
+            for (int i = 1; i < n; ++i) {
+                const int x = topo[i], xp = parent[x];
+                dt = len[x] / 2;
+                double r = lognormal(j_log(vr[xp]) - dt * b / 2, dt * b, prng); rates[x] = r;
+                r = lognormal(j_log(r) - dt * b / 2, dt * b, prng); vr[x] = r;
+            }
+        } else if (kind == ACABY02) {               // apps/SaGePhy/ACArisBrosouYang02RateModel.java:49-64
+            rates[topo[0]] = a;
+            for (int i = 1; i < n; ++i) {
+                const int x = topo[i], xp = parent[x];
+                const double lambda = 1.0 / rates[xp];
+                if (lambda <= 0) throw std::invalid_argument("IllegalArgumentException: Invalid rate for exponential distribution.");
+                rates[x] = -j_log(1.0 - prng.nextDouble()) / lambda;
+            }
+        } else {                                    // apps/SaGePhy/ACLepageBryantPhillipeLartillot07RateModel.java:75-115 (CIR, 200 Euler steps per branch)
+            const int STEPS = 200;
+            std::vector<double> vr(n);
+            for (int j = 0; j < n; ++j) {
+                const int x = topo[j];
+                double ir = j == 0 ? a : vr[parent[x]];
+                double r = 0.0;
+                const double dt = len[x] / STEPS;
+                if (j == 0 && dt == 0.0) { vr[x] = a; rates[x] = a; continue; }
+                if (dt <= 0.0) throw std::invalid_argument("IllegalArgumentException: Cannot have non-positive variance for normal distribution.");
+                const double sd = std::sqrt(dt);
+                for (int i = 0; i < STEPS; ++i) {
+                    const double root_ir = std::sqrt(ir);
+                    ir = ir + c * (b - ir) * dt + d * root_ir * (prng.nextGaussian() * sd + 0.0);
+                    r += ir;
+                }
+                vr[x] = ir; rates[x] = r / STEPS;
+            }
+        }
     }
     // java.util.HashMap iteration order of the parameter names (bucket = (h ^ h>>>16) & (cap-1)); all key sets here are
     // single-character-hash friendly: {"mu","sigma2"}: hash("mu")=3496 -> bucket 0 of 2... computed in params() explicitly.
@@ -146,6 +209,7 @@ struct RateModelO {
             case NORMAL: return prng.nextGaussian() * sigma + a;
             case UNIFORM: { double d = prng.nextDouble(); return prng.nextBoolean() ? (b - a) * d + a : (b - a) * (1.0 - d) + a; }
             case SAMPLES: return samples[prng.nextInt((int)samples.size())];
+            default: break;      // autocorrelated models: rates_autocorrelated
         }
         return 0;
     }
@@ -179,6 +243,10 @@ inline std::vector<std::pair<std::string, std::string>> RateModelO::params() con
         case NORMAL: return hashmap_order({{"mu", D(a)}, {"sigma2", D(b)}}, 2);
         case UNIFORM: return hashmap_order({{"a", D(a)}, {"b", D(b)}}, 2);
         case SAMPLES: return hashmap_order({{"filename", file}}, 2);
+        case ACTK98: return hashmap_order({{"start rate", D(a)}, {"v", D(b)}}, 2);
+        case ACRY07: return hashmap_order({{"start rate", D(a)}, {"sigma2", D(b)}}, 2);
+        case ACABY02: return hashmap_order({{"start rate", D(a)}}, 1);
+        case ACLBPL07: return hashmap_order({{"start rate", D(a)}, {"mu", D(b)}, {"theta", D(c)}, {"sigma", D(d)}}, 2);
     }
     return {};
 }
@@ -222,9 +290,30 @@ inline void run_branch_relaxer(const std::vector<std::string>& args, Outputs& o,
             m.kind = RateModelO::SAMPLES; m.file = arg(2);
             std::ifstream f(m.file); if (!f) throw std::invalid_argument("IllegalArgumentException: java.io.FileNotFoundException: " + m.file);
             std::string line; while (std::getline(f, line)) m.samples.push_back(parse_double(line));
-        } else throw std::invalid_argument("oracle: rate model outside the accelerated path (autocorrelated / RK11 models, SURVEY.md §2 row 16): " + model);
+        }
+        else if (ieq(model, "ACTK98")) { m.kind = RateModelO::ACTK98; m.a = parse_double(arg(2)); m.b = parse_double(arg(3)); }
+        else if (ieq(model, "ACRY07")) { m.kind = RateModelO::ACRY07; m.a = parse_double(arg(2)); m.b = parse_double(arg(3)); }
+        else if (ieq(model, "ACABY02")) { m.kind = RateModelO::ACABY02; m.a = parse_double(arg(2)); }
+        else if (ieq(model, "ACLBPL07")) {
+            m.kind = RateModelO::ACLBPL07; m.a = parse_double(arg(2)); m.b = parse_double(arg(3)); m.c = parse_double(arg(4)); m.d = parse_double(arg(5));
+            if (2 * m.c * m.b < m.d * m.d) throw std::invalid_argument("IllegalArgumentException: Invalid parameters for CIR process: 0 rate may be achieved.");
+        } else throw std::invalid_argument("oracle: rate model outside the accelerated path (IIDRK11 needs a host tree and a guest-to-host map): " + model);
         std::unique_ptr<NTree> t = file_exists(arg(0)) ? nw_read_tree(read_file(arg(0))) : nw_read_tree(arg(0));
         auto bfs = t->vertices_bfs(); int n = (int)bfs.size();
+        if (m.strict_tree()) {
+            // PrIMENewickTreeVerifier.runStandardTestSuite (io/PrIMENewickTreeVerifier.java:37-46) as far as plain Newick input can
+            // trip it: leaf names present and unique (:79-94), branch lengths on every vertex but the root (:101-103,143-152)
+            bool any_name = false, any_bl = false; for (NVertex* v : bfs) { any_name |= (bool)v->name; any_bl |= (bool)v->bl; }
+            if (any_name) {
+                std::set<std::string> seen;
+                for (NVertex* v : bfs) {
+                    if (!v->is_leaf()) continue;
+                    if (!v->name) throw NewickIOException("Missing name on Newick vertex " + std::to_string(v->number) + ".");
+                    if (!seen.insert(*v->name).second) throw NewickIOException("Duplicate vertex name '" + *v->name + "' found in vertex " + std::to_string(v->number) + ".");
+                }
+            }
+            if (any_bl) for (int i = 0; i < n; ++i) for (NVertex* v : bfs) if (v->number == i && !v->bl && v != t->root) throw NewickIOException("Missing branch length on Newick vertex " + std::to_string(i) + ".");
+        }
         for (NVertex* v : bfs) if (v->children.size() == 1) throw TopologyException("Cannot create RTree from collapsable NewickTree.");
         for (NVertex* v : bfs) if (v->is_leaf() && !v->name) throw std::runtime_error("NullPointerException: Missing leaf name in vertex " + std::to_string(v->number) + ".");
         std::vector<double> orig(n, std::nan("")); bool has = false;
@@ -235,10 +324,13 @@ inline void run_branch_relaxer(const std::vector<std::string>& args, Outputs& o,
         double mn = parse_double(p.get("-min", "1e-64")), mx = parse_double(p.get("-max", "1e64"));
         int maxAttempts = parse_int(p.get("-a", "10000")), attempts = 0;
         std::vector<double> rates(n);
+        std::vector<int> topo(n), parent(n, -1);
+        for (int i = 0; i < n; ++i) { topo[i] = bfs[i]->number; if (bfs[i]->parent) parent[bfs[i]->number] = bfs[i]->parent->number; }
         for (;;) {
             if (attempts > maxAttempts) { o.err += "Failed to create valid rates within max allowed attempts.\n"; if (st) { st->status = 1; st->attempts = attempts; } return; }
             if (m.kind == RateModelO::SAMPLES) { /* the reference re-reads the file on every call; same values */ }
-            for (int x = 0; x < n; ++x) rates[x] = m.sample(prng);
+            if (m.kind >= RateModelO::ACTK98) m.rates_autocorrelated(topo, parent, orig, prng, rates);
+            else for (int x = 0; x < n; ++x) rates[x] = m.sample(prng);
             ++attempts;
             bool ok = true;
             for (int x = 0; x < n; ++x) { if (x == ignore) continue; if (rates[x] < mn || rates[x] > mx) { ok = false; break; } }

@@ -2,6 +2,7 @@
 // Mirrors apps/SaGePhy/BranchRelaxerParameters.java:28-117 (options, model factory, tree loading) and
 // BranchRelaxer.java:79-93 (RTree / names / lengths preparation, root without length -> 0 and ignored by the range check).
 #include <climits>
+#include <set>
 #include "apps_common.hpp"
 
 namespace sgp {
@@ -27,8 +28,26 @@ std::vector<std::pair<std::string, std::string>> java_hashmap_order(const std::v
     for (int b = 0; b < cap; ++b) for (auto& e : kv) if ((int)(hash(e.first) & (uint32_t)(cap - 1)) == b) out.push_back(e);
     return out;
 }
-RelaxTreeTemplate make_template(const FlatTree& t, bool keep_interior) {
+// strict = PrIMENewickTreeVerifier.runStandardTestSuite (io/PrIMENewickTreeVerifier.java:37-46), which the reference runs for the
+// models whose lengthsMustBeUltrametric() is true; for plain Newick input it can fail on leaf names (:79-94) and on missing
+// branch lengths (:101-103,143-152). Arc/vertex-time tags are not modelled.
+RelaxTreeTemplate make_template(const FlatTree& t, bool keep_interior, bool strict) {
     RelaxTreeTemplate r; r.nV = t.n; r.root = t.root;
+    if (strict) {
+        bool any_name = false, any_bl = false;
+        for (int v = 0; v < t.n; ++v) { any_name |= (bool)t.has_name[v]; any_bl |= (bool)t.has_bl[v]; }
+        if (any_name) {
+            std::set<std::string> seen;
+            for (int i = 0; i < t.n; ++i) {
+                const int v = t.bfs[i];
+                if (t.n_children[v] != 0) continue;
+                if (!t.has_name[v]) throw SgpError("NewickIOException: Missing name on Newick vertex " + std::to_string(v) + ".");
+                if (!seen.insert(t.name[v]).second) throw SgpError("NewickIOException: Duplicate vertex name '" + t.name[v] + "' found in vertex " + std::to_string(v) + ".");
+            }
+        }
+        if (any_bl) for (int v = 0; v < t.n; ++v) if (!t.has_bl[v] && v != t.root) throw SgpError("NewickIOException: Missing branch length on Newick vertex " + std::to_string(v) + ".");
+    }
+    r.topo.assign(t.bfs.begin(), t.bfs.end()); r.parent.assign(t.parent.begin(), t.parent.end());
     for (int v = 0; v < t.n; ++v) {
         if (t.n_children[v] == 1) throw SgpError("Cannot create RTree from collapsable NewickTree.");
         if (t.n_children[v] == 0 && !t.has_name[v]) throw SgpError("Missing leaf name in vertex " + std::to_string(v) + ".");
@@ -59,7 +78,8 @@ void parse_relax_app(const std::vector<std::string>& args, bool multi_tree_input
         res.status = 6;
         res.out_text = "Usage:\n    java -jar sagephy-X.Y.Z.jar BranchRelaxer [options] <tree> <model> <arg1> <arg2> <...>\n"
                        "Supported models (accelerated): Constant <rate>, IIDGamma <k> <theta>, IIDLogNormal <mu> <sigma2>, IIDNormal <mu> <sigma2>,\n"
-                       "    IIDUniform <a> <b>, IIDExponential <lambda>, IIDSamplesFromFile <filename>\n\n";
+                       "    IIDUniform <a> <b>, IIDExponential <lambda>, IIDSamplesFromFile <filename>,\n"
+                       "    ACTK98 <start rate> <v>, ACRY07 <start rate> <sigma2>, ACABY02 <start rate>, ACLBPL07 <start rate> <mu> <theta> <sigma>\n\n";
         return;
     }
     auto arg = [&](size_t i) -> const std::string& {
@@ -69,7 +89,7 @@ void parse_relax_app(const std::vector<std::string>& args, bool multi_tree_input
     if (p.on("-s")) { cfg.has_seed = true; cfg.seed = to_i64(p.str("-s", "0")); cfg.seed_arg_index = p.val_index.at("-s"); }
     else { cfg.has_seed = false; cfg.seed = random_seed(); }
     const std::string& model = arg(1);
-    std::vector<std::pair<std::string, std::string>> kv; int hcap = 2;
+    std::vector<std::pair<std::string, std::string>> kv; int hcap = 2; bool strict = false;
     if (same_nocase(model, "Constant")) { cfg.model = 0; cfg.pa = to_double(arg(2)); cfg.model_name = "ConstantRates"; kv = {{"rate", jdouble(cfg.pa)}}; hcap = 1; }
     else if (same_nocase(model, "IIDExponential")) {
         cfg.model = 1; cfg.pa = to_double(arg(2)); if (cfg.pa <= 0) throw SgpError("Cannot have non-positive rate for exponential distribution.");
@@ -97,9 +117,22 @@ void parse_relax_app(const std::vector<std::string>& args, bool multi_tree_input
         if (cfg.samples.empty()) throw SgpError("samples file is empty: " + arg(2));
         char buf[PATH_MAX]; const char* rp = realpath(arg(2).c_str(), buf);
         kv = {{"filename", rp ? std::string(rp) : arg(2)}};
+    } else if (same_nocase(model, "ACTK98")) {          // apps/SaGePhy/ACThorneKishino98RateModel.java
+        cfg.model = 7; cfg.pa = to_double(arg(2)); cfg.pb = to_double(arg(3)); cfg.model_name = "ThorneKishino98Rates";
+        kv = {{"start rate", jdouble(cfg.pa)}, {"v", jdouble(cfg.pb)}}; strict = true;
+    } else if (same_nocase(model, "ACRY07")) {          // apps/SaGePhy/ACRannalaYang07RateModel.java
+        cfg.model = 8; cfg.pa = to_double(arg(2)); cfg.pb = to_double(arg(3)); cfg.model_name = "RannalaYang07Rates";
+        kv = {{"start rate", jdouble(cfg.pa)}, {"sigma2", jdouble(cfg.pb)}}; strict = true;
+    } else if (same_nocase(model, "ACABY02")) {         // apps/SaGePhy/ACArisBrosouYang02RateModel.java
+        cfg.model = 9; cfg.pa = to_double(arg(2)); cfg.model_name = "ArisBrosouYang02Rates"; kv = {{"start rate", jdouble(cfg.pa)}}; hcap = 1;
+    } else if (same_nocase(model, "ACLBPL07")) {        // apps/SaGePhy/ACLepageBryantPhillipeLartillot07RateModel.java
+        cfg.model = 10; cfg.pa = to_double(arg(2)); cfg.pb = to_double(arg(3)); cfg.pc = to_double(arg(4)); cfg.pd = to_double(arg(5));
+        if (2 * cfg.pc * cfg.pb < cfg.pd * cfg.pd) throw SgpError("Invalid parameters for CIR process: 0 rate may be achieved.");
+        cfg.model_name = "LepageBryantPhillipeLartillot07Rates";
+        kv = {{"start rate", jdouble(cfg.pa)}, {"mu", jdouble(cfg.pb)}, {"theta", jdouble(cfg.pc)}, {"sigma", jdouble(cfg.pd)}};
     } else {
         res.status = 4;
-        res.err_text = "rate model outside the accelerated path (autocorrelated / RK11 models are a later row of the scope table): " + model + "\n";
+        res.err_text = "rate model outside the accelerated path (IIDRK11 needs a host tree and a guest-to-host map; not in the scope table yet): " + model + "\n";
         return;
     }
     cfg.params = java_hashmap_order(kv, hcap);
@@ -108,14 +141,14 @@ void parse_relax_app(const std::vector<std::string>& args, bool multi_tree_input
     cfg.has_outfile = p.on("-o"); if (cfg.has_outfile) cfg.outfile = java_trim(p.str("-o", ""));
     if (trees_from_batch) { (void)arg(0); return; }      // chained stage: the trees are already on the device
     const std::string text = exists(arg(0)) ? slurp(arg(0)) : arg(0);
-    if (!multi_tree_input) cfg.trees.push_back(make_template(parse_newick(text), cfg.keep_interior));
+    if (!multi_tree_input) cfg.trees.push_back(make_template(parse_newick(text), cfg.keep_interior, strict));
     else {
         size_t b = 0;
         while (b < text.size()) {
             size_t e = text.find('\n', b); if (e == std::string::npos) e = text.size();
             std::string line = text.substr(b, e - b); b = e + 1;
             if (line.find_first_not_of(" \t\r") == std::string::npos) continue;
-            cfg.trees.push_back(make_template(parse_newick(line), cfg.keep_interior));
+            cfg.trees.push_back(make_template(parse_newick(line), cfg.keep_interior, strict));
         }
         if (cfg.trees.empty()) throw SgpError("no tree found in the multi-tree input");
     }

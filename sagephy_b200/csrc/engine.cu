@@ -573,7 +573,9 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
     const int T = chained ? (int)src->n : (int)cfg.trees.size();
     std::vector<RelaxTreeView> views(chained ? 0 : T); std::vector<double> orig; std::vector<int16_t> chain; std::vector<uint8_t> flags; std::vector<int32_t> name_off; std::string blob;
     long long sum_v = 0;
-    DevBuf<RelaxTreeView> d_views; DevBuf<double> d_orig; DevBuf<int16_t> d_chain; DevBuf<uint8_t> d_flags; DevBuf<int32_t> d_name, d_num, d_sig;
+    DevBuf<RelaxTreeView> d_views; DevBuf<double> d_orig; DevBuf<int16_t> d_chain; DevBuf<uint8_t> d_flags; DevBuf<int32_t> d_name, d_num, d_sig, d_topo, d_parent;
+    const bool autocorr = cfg.model >= RM_ACTK98;
+    std::vector<int32_t> topo, parent;
     if (chained) {
         IngestArgs g{}; g.n_src = src->n; g.info = (const RepInfo*)src->d_info; g.node_off = src->d_node_off; g.nodes = (const Node*)src->d_nodes;
         g.aux = src->d_aux; g.aux_stride = src->aux_stride; g.pruned = src_pruned ? 1 : 0; g.keep_interior = cfg.keep_interior ? 1 : 0;
@@ -587,6 +589,8 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
         const size_t cnt = (size_t)std::max<long long>(sum_v, 1);
         d_views.alloc((size_t)T); d_orig.alloc(cnt); d_chain.alloc(cnt); d_flags.alloc(cnt); d_num.alloc(cnt); d_sig.alloc(cnt);
         g.v0 = v0.p; g.views = d_views.p; g.orig = d_orig.p; g.chain = d_chain.p; g.vflags = d_flags.p; g.number = d_num.p; g.sigma = d_sig.p;
+        DevBuf<int32_t> post_id;
+        if (autocorr) { d_topo.alloc(cnt); d_parent.alloc(cnt); post_id.alloc((size_t)std::max<long long>(src->aux_stride, 1)); g.topo = d_topo.p; g.parent = d_parent.p; g.post_id = post_id.p; }
         launch_ingest_fill(g, st); ++tm.launches;
         CK(cudaGetLastError()); CK(cudaStreamSynchronize(st));          // nv / v0 go out of scope here
     }
@@ -594,6 +598,7 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
         const RelaxTreeTemplate& tt = cfg.trees[t];
         views[t].nV = tt.nV; views[t].root = tt.root; views[t].ignore = tt.ignore; views[t].v0 = sum_v; sum_v += tt.nV;
         orig.insert(orig.end(), tt.orig.begin(), tt.orig.end()); chain.insert(chain.end(), tt.chain.begin(), tt.chain.end()); flags.insert(flags.end(), tt.flags.begin(), tt.flags.end());
+        if (autocorr) { topo.insert(topo.end(), tt.topo.begin(), tt.topo.end()); parent.insert(parent.end(), tt.parent.begin(), tt.parent.end()); }
         for (int v = 0; v < tt.nV; ++v) { name_off.push_back((int32_t)blob.size()); name_off.push_back((int32_t)tt.names[v].size()); blob += tt.names[v]; }
     }
     const long long rounds = (n + T - 1) / T; const long long slots = rounds * sum_v;
@@ -614,7 +619,7 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
         add(tail, a.model_tail_off, a.model_tail_len);
     }
     DevBuf<double> d_samples, rates, relaxed; d_samples.upload(cfg.samples);
-    if (!chained) { d_views.upload(views); d_orig.upload(orig); d_chain.upload(chain); d_flags.upload(flags); d_name.upload(name_off); }
+    if (!chained) { d_views.upload(views); d_orig.upload(orig); d_chain.upload(chain); d_flags.upload(flags); d_name.upload(name_off); if (autocorr) { d_topo.upload(topo); d_parent.upload(parent); } }
     else {
         a.syn_names = 1; a.syn_number = d_num.p; a.syn_sigma = d_sig.p; a.syn_append_sigma = src->name_append_sigma ? 1 : 0;
         if (src->name_prefix.size() > sizeof(a.syn_prefix)) throw SgpError("vertex prefix longer than 24 bytes is not supported");
@@ -625,7 +630,7 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
     DevBuf<int32_t> attempts, status; attempts.alloc((size_t)n); status.alloc((size_t)n);
     CK(cudaMemsetAsync(attempts.p, 0, (size_t)n * sizeof(int32_t), st)); CK(cudaMemsetAsync(status.p, 0, (size_t)n * sizeof(int32_t), st));
     DevBuf<uint32_t> mt_state; if (replay) mt_state.alloc((size_t)((n + 127) / 128 * 128 / 32 + 1) * 624 * 32);
-    a.n = n; a.rep_base = opts.offset; a.seed = (unsigned long long)cfg.seed; a.model = cfg.model; a.pa = cfg.pa; a.pb = cfg.pb; a.sigma = cfg.sigma;
+    a.n = n; a.rep_base = opts.offset; a.seed = (unsigned long long)cfg.seed; a.model = cfg.model; a.pa = cfg.pa; a.pb = cfg.pb; a.pc = cfg.pc; a.pd = cfg.pd; a.sigma = cfg.sigma; a.topo = d_topo.p; a.parent = d_parent.p;
     a.min_rate = cfg.min_rate; a.max_rate = cfg.max_rate; a.max_attempts = cfg.max_attempts; a.samples = d_samples.p; a.n_samples = (int)cfg.samples.size();
     a.n_trees = T; a.sum_v = sum_v; a.trees = d_views.p; a.orig = d_orig.p; a.chain = d_chain.p; a.vflags = d_flags.p; a.name_off = d_name.p; a.blob = d_blob.p;
     a.T = impl->T; a.rates = rates.p; a.relaxed = relaxed.p; a.attempts = attempts.p; a.status = status.p; a.mt_state = mt_state.p;
@@ -633,9 +638,9 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
 
     // ---- K5 rates + lengths ------------------------------------------------------------------------------------------------
     ph.start();
-    if (replay) {
-        // status 0 -> REP_PENDING marker expected by the kernel
-        launch_relax_rates(true, a, 0, 0, st); ++tm.launches;
+    if (replay || autocorr) {
+        // one thread per replicate from attempt 0 (the autocorrelated models are sequential along the tree in either RNG mode)
+        launch_relax_rates(replay, a, 0, 0, st); ++tm.launches;
     } else {
         if (chained) launch_relax_apply_per_rep(a, st); else launch_relax_apply(a, slots, st);          // attempt 0 in parallel
         tm.launches += 2;

@@ -33,10 +33,11 @@ struct TreeGenConfig {
 struct RelaxTreeTemplate {
     int nV = 0, root = -1, ignore = -1;
     std::vector<double> orig; std::vector<int16_t> chain; std::vector<uint8_t> flags; std::vector<std::string> names;
+    std::vector<int32_t> topo, parent;    // RTree.getTopologicalOrdering() (BFS from the root) and parent ids, for the autocorrelated models
 };
 
 struct RelaxConfig {
-    int model = 0; double pa = 0, pb = 0, sigma = 0;
+    int model = 0; double pa = 0, pb = 0, pc = 0, pd = 0, sigma = 0;
     std::vector<double> samples;
     double min_rate = 1e-64, max_rate = 1e64; int max_attempts = 10000;
     bool do_meta = false, keep_interior = false, has_outfile = false; std::string outfile;

@@ -115,7 +115,8 @@ struct EmitArgs {
 namespace sgp {
 
 // ---- BranchRelaxer ------------------------------------------------------------------------------------------------------------
-enum RelaxModel : int { RM_CONSTANT = 0, RM_EXPONENTIAL = 1, RM_GAMMA = 2, RM_LOGNORMAL = 3, RM_NORMAL = 4, RM_UNIFORM = 5, RM_SAMPLES = 6 };
+enum RelaxModel : int { RM_CONSTANT = 0, RM_EXPONENTIAL = 1, RM_GAMMA = 2, RM_LOGNORMAL = 3, RM_NORMAL = 4, RM_UNIFORM = 5, RM_SAMPLES = 6,
+                        RM_ACTK98 = 7, RM_ACRY07 = 8, RM_ACABY02 = 9, RM_ACLBPL07 = 10 };      // autocorrelated: parent -> child along the tree
 
 // One input tree ("template"): vertex ids are the reference's post-order numbers, so id order == Newick emission order.
 struct RelaxTreeView {
@@ -126,6 +127,9 @@ struct RelaxTreeView {
 struct RelaxArgs {
     long long n; long long rep_base; unsigned long long seed;
     int model; double pa, pb, sigma;   // model parameters (a, b, sqrt(variance))
+    double pc, pd;                     // ACLBPL07: theta, sigma (pa = start rate, pb = mu)
+    const int32_t* topo;               // per template vertex slot: vertex ids in RTree.getTopologicalOrdering() order (BFS from the root)
+    const int32_t* parent;             // per template vertex: parent id (-1: root)
     double min_rate, max_rate; int max_attempts;
     const double* samples; int n_samples;
     int n_trees; long long sum_v;      // replicate r relaxes template r % n_trees; its vertex slot base is (r / n_trees) * sum_v + v0
@@ -158,6 +162,8 @@ struct IngestArgs {
     long long* nv;                     // [n_src + 1] vertices per tree (0: unusable source replicate), then scanned into v0
     const long long* v0;
     RelaxTreeView* views; double* orig; int16_t* chain; uint8_t* vflags; int32_t* number; int32_t* sigma;
+    int32_t* topo; int32_t* parent;    // autocorrelated models
+    int32_t* post_id;                  // scratch, one entry per source vertex record: its id in the chosen view's post-order
 };
 
 }  // namespace sgp

@@ -72,6 +72,89 @@ __device__ inline double draw_rate(const RelaxArgs& a, MtStream& mt, GaussCache&
     }
 }
 
+// ---- autocorrelated models (rates depend on the parent's rate; vertices in RTree.getTopologicalOrdering() order) ---------------
+// One uniform / Gaussian per call: MT replay takes the next value of the replicate's stream (the reference's draw order);
+// Philox addresses draw `k` of vertex x of attempt `attempt`.
+template <bool REPLAY>
+__device__ inline double ac_uniform(const RelaxArgs& a, MtStream& mt, unsigned long long gid, uint32_t attempt, int x, uint32_t k) {
+    if (REPLAY) return mt.next_double();
+    const U4 w = philox4x32_10((uint32_t)x * 256u + k, attempt ^ 0x40000000u, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    return u01_from_words(w.x, w.y);
+}
+template <bool REPLAY>
+__device__ inline double ac_gaussian(const RelaxArgs& a, MtStream& mt, GaussCache& gc, unsigned long long gid, uint32_t attempt, int x, uint32_t k) {
+    if (REPLAY) return mt_next_gaussian(mt, gc);
+    for (uint32_t trial = 0;; ++trial) {
+        const U4 w = philox4x32_10((uint32_t)x * 256u + k, attempt ^ (trial << 20) ^ 0xC0000000u, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        const double v1 = XSUB(XMUL(2.0, u01_from_words(w.x, w.y)), 1.0), v2 = XSUB(XMUL(2.0, u01_from_words(w.z, w.w)), 1.0), s = XADD(XMUL(v1, v1), XMUL(v2, v2));
+        if (s < 1 && s != 0) return XMUL(v1, jsqrt(XDIV(XMUL(-2.0, jlog(s)), s)));
+    }
+}
+// new LogNormalDistribution(mu, sigma2).sampleValue(prng), math/LogNormalDistribution.java:39-48,196-205; *err when the constructor throws
+__device__ inline double ac_lognormal(double mu, double sigma2, double u, int* err) {
+    if (sigma2 <= 0.0) { *err = 1; return 0.0; }
+    return jexp(XADD(XMUL(jnormal_quantile(u), jsqrt(sigma2)), mu));
+}
+// Fills rates[base ..] for one attempt; vr (the `relaxed` slots, overwritten later) holds the vertex rates of ACRY07 / ACLBPL07.
+template <bool REPLAY>
+__device__ inline void ac_rates(const RelaxArgs& a, const RelaxTreeView& tv, long long base, MtStream& mt, GaussCache& gc, unsigned long long gid, uint32_t attempt, int* err) {
+    const int32_t* topo = a.topo + tv.v0; const int32_t* par = a.parent + tv.v0; const double* len = a.orig + tv.v0;
+    double* rates = a.rates + base; double* vr = a.relaxed + base;
+    const int n = tv.nV;
+    if (a.model == RM_ACTK98) {                 // apps/SaGePhy/ACThorneKishino98RateModel.java:58-74
+        rates[topo[0]] = a.pa;
+        for (int i = 1; i < n && !*err; ++i) {
+            const int x = topo[i], xp = par[x];
+            const double deltat = XDIV(XADD(len[x], len[xp]), 2.0);
+            const double sigma2 = XMUL(a.pb, deltat);
+            rates[x] = ac_lognormal(XSUB(jlog(rates[xp]), XDIV(sigma2, 2.0)), sigma2, ac_uniform<REPLAY>(a, mt, gid, attempt, x, 0), err);
+        }
+    } else if (a.model == RM_ACRY07) {          // apps/SaGePhy/ACRannalaYang07RateModel.java:56-88
+        const int root = topo[0]; double dt = len[root];
+        if (dt == 0.0) { rates[root] = a.pa; vr[root] = a.pa; }
+        else {
+            const double s2 = XMUL(dt, a.pb);
+            double r = ac_lognormal(XSUB(jlog(a.pa), XDIV(s2, 2.0)), s2, ac_uniform<REPLAY>(a, mt, gid, attempt, root, 0), err); rates[root] = r;
+            if (!*err) r = ac_lognormal(XSUB(jlog(r), XDIV(s2, 2.0)), s2, ac_uniform<REPLAY>(a, mt, gid, attempt, root, 1), err);
+            vr[root] = r;
+        }
+        for (int i = 1; i < n && !*err; ++i) {
+            const int x = topo[i], xp = par[x];
+            dt = XDIV(len[x], 2.0);
+            const double s2 = XMUL(dt, a.pb);
+            double r = ac_lognormal(XSUB(jlog(vr[xp]), XDIV(s2, 2.0)), s2, ac_uniform<REPLAY>(a, mt, gid, attempt, x, 0), err); rates[x] = r;
+            if (!*err) r = ac_lognormal(XSUB(jlog(r), XDIV(s2, 2.0)), s2, ac_uniform<REPLAY>(a, mt, gid, attempt, x, 1), err);
+            vr[x] = r;
+        }
+    } else if (a.model == RM_ACABY02) {         // apps/SaGePhy/ACArisBrosouYang02RateModel.java:49-64
+        rates[topo[0]] = a.pa;
+        for (int i = 1; i < n && !*err; ++i) {
+            const int x = topo[i], xp = par[x];
+            const double lambda = XDIV(1.0, rates[xp]);
+            if (lambda <= 0) { *err = 1; break; }           // ExponentialDistribution constructor throws
+            rates[x] = XDIV(-jlog(XSUB(1.0, ac_uniform<REPLAY>(a, mt, gid, attempt, x, 0))), lambda);
+        }
+    } else {                                    // apps/SaGePhy/ACLepageBryantPhillipeLartillot07RateModel.java:75-115: CIR, 200 Euler steps per branch
+        const int STEPS = 200;
+        for (int j = 0; j < n && !*err; ++j) {
+            const int x = topo[j];
+            double ir = j == 0 ? a.pa : vr[par[x]];
+            double r = 0.0;
+            const double dt = XDIV(len[x], (double)STEPS);
+            if (j == 0 && dt == 0.0) { vr[x] = a.pa; rates[x] = a.pa; continue; }
+            if (!(dt > 0.0) && !(dt != dt)) { *err = 1; break; }      // NormalDistribution(0, dt) throws for dt <= 0 (NaN passes the check)
+            const double sd = jsqrt(dt);
+            for (int i = 0; i < STEPS; ++i) {
+                const double root_ir = jsqrt(ir);
+                const double g = XADD(XMUL(ac_gaussian<REPLAY>(a, mt, gc, gid, attempt, x, (uint32_t)i), sd), 0.0);
+                ir = XADD(XADD(ir, XMUL(XMUL(a.pc, XSUB(a.pb, ir)), dt)), XMUL(XMUL(a.pd, root_ir), g));
+                r = XADD(r, ir);
+            }
+            vr[x] = ir; rates[x] = XDIV(r, (double)STEPS);
+        }
+    }
+}
+
 __device__ __forceinline__ long long relax_slot(const RelaxArgs& a, long long r, const RelaxTreeView** tv) {
     const long long t = r % a.n_trees; *tv = &a.trees[t];
     return (r / a.n_trees) * a.sum_v + a.trees[t].v0;
@@ -93,6 +176,10 @@ __global__ void __launch_bounds__(128) k_relax_rates(RelaxArgs a, int first_atte
     for (;;) {
         if (attempts > a.max_attempts) { status = REP_MAX_ATTEMPTS; break; }
         bool ok = true; int err = 0;
+        if (a.model >= RM_ACTK98) {
+            ac_rates<REPLAY>(a, *tv, base, mt, gc, gid, (uint32_t)attempts, &err);
+            if (!err) for (int x = 0; x < nV; ++x) { const double rate = a.rates[base + x]; if (x != tv->ignore && (rate < a.min_rate || rate > a.max_rate)) ok = false; }
+        } else
         for (int x = 0; x < nV; ++x) {
             const double rate = draw_rate<REPLAY>(a, mt, gc, gid, (uint32_t)attempts, x, &err);
             a.rates[base + x] = rate;
@@ -167,6 +254,20 @@ __global__ void __launch_bounds__(256) k_ingest_fill(IngestArgs g) {
     if (nV == 0) return;
     const Node* N = g.nodes + g.node_off[r];
     const int32_t* ord = g.aux + (g.pruned ? g.aux_stride : 0) + g.node_off[r];        // post-order of the chosen view
+    if (g.topo) {
+        // ids of the chosen view: position in its post-order; then BFS order and parents in those ids
+        int32_t* pid = g.post_id + g.node_off[r];
+        const int32_t* bfs = g.aux + (g.pruned ? 3 : 2) * g.aux_stride + g.node_off[r];
+        for (int k = lane; k < nV; k += 32) pid[ord[k]] = k;
+        __syncwarp();
+        if (lane == 0) g.parent[v0 + nV - 1] = -1;          // the root is last in post-order
+        for (int k = lane; k < nV; k += 32) {
+            g.topo[v0 + k] = pid[bfs[k]];
+            const Node& x = N[ord[k]];
+            const int l = g.pruned ? x.p_left : x.left, rr = g.pruned ? x.p_right : x.right;
+            if (l >= 0) { g.parent[v0 + pid[l]] = k; g.parent[v0 + pid[rr]] = k; }
+        }
+    }
     for (int k = lane; k < nV; k += 32) {
         const Node& x = N[ord[k]];
         const bool leaf = g.pruned ? x.p_left < 0 : x.left < 0;

@@ -280,6 +280,16 @@ RELAX_CASES = [
     ["-s", "7", "-x", "-o", "rel.tree", RELAX_TREE_NOSTEM, "Constant", "1.7"],
     ["-s", "8", "-min", "0.8", "-max", "1.3", "-a", "50", "-o", "rel.tree", RELAX_TREE, "IIDLogNormal", "0", "0.04"],   # tight window: many attempts, some failures
     ["-s", "9", RELAX_TREE_NOSTEM, "iidlognormal", "0.1", "0.5"],                              # stdout, case-insensitive model name
+    # autocorrelated models: rates follow the parent's rate along RTree.getTopologicalOrdering()
+    ["-s", "10", "-x", "-o", "rel.tree", RELAX_TREE, "ACTK98", "1.0", "0.5"],
+    ["-s", "11", "-o", "rel.tree", RELAX_TREE_NOSTEM, "ACTK98", "0.7", "2.0"],
+    ["-s", "12", "-x", "-o", "rel.tree", RELAX_TREE, "ACRY07", "1.0", "0.5"],                  # stem: two draws at the root
+    ["-s", "13", "-o", "rel.tree", RELAX_TREE_NOSTEM, "acry07", "1.3", "1.5"],                 # no stem: root keeps the start rate
+    ["-s", "14", "-x", "-o", "rel.tree", RELAX_TREE, "ACABY02", "1.0"],
+    ["-s", "15", "-x", "-innms", "-o", "rel.tree", RELAX_TREE, "ACLBPL07", "1.0", "1.0", "2.0", "0.5"],   # CIR, 200 Gaussian steps per branch
+    ["-s", "16", "-o", "rel.tree", RELAX_TREE_NOSTEM, "ACLBPL07", "0.5", "1.2", "4.0", "1.5"],
+    ["-s", "17", "-min", "0.6", "-max", "1.6", "-a", "30", "-o", "rel.tree", RELAX_TREE, "ACTK98", "1.0", "0.3"],   # retries, some failures
+    ["-s", "18", "-o", "rel.tree", "((a:0.0,b:0.1):0.2,c:0.3):0.1;", "ACRY07", "1.0", "0.5"],   # zero-length branch: the reference throws
 ]
 
 
@@ -294,6 +304,9 @@ def test_branch_relaxer_replay_is_byte_exact(ctx, args):
         want = oracle_run("BranchRelaxer", with_seed(args, seed0 + i))
         if want["status"] == 1:
             assert b.rep_status[i] == 1
+            continue
+        if want["status"] == 2:          # exception in the reference (stack trace, no output)
+            assert b.rep_status[i] == 4, (i, b.rep_status[i], want["stderr"][:120])
             continue
         assert b.rep_status[i] == 0 and b.attempts[i] == want["attempts"], (i, b.rep_status[i], b.attempts[i], want["attempts"])
         if has_out:
@@ -349,6 +362,33 @@ def test_branch_relaxer_philox_matches_reference_distributions(ctx):
     assert stats.kstest(g[::7], "gamma", args=(2, 0, 0.5)).pvalue > 0.001
 
 
+def test_branch_relaxer_autocorrelated_models(ctx):
+    # strict tree validation of the models with lengthsMustBeUltrametric() (io/PrIMENewickTreeVerifier.java:37-46)
+    for tree in ("(a:0.1,a:0.1):0.2;", "((a:0.1,b:0.1),c:0.2):0.1;"):
+        want = oracle_run("BranchRelaxer", ["-s", "1", tree, "ACTK98", "1.0", "0.5"])
+        assert want["status"] == 2 and "NewickIOException" not in want["stdout"]
+        with pytest.raises(sg.SagephyError):
+            ctx.run("BranchRelaxer", ["-s", "1", tree, "ACTK98", "1.0", "0.5"], n=2, rng=sg.RNG_MT_REPLAY)
+        ok = ctx.run("BranchRelaxer", ["-s", "1", tree, "ACABY02", "1.0"], n=2, rng=sg.RNG_MT_REPLAY)      # not strict
+        assert ok.stdout == "".join(oracle_run("BranchRelaxer", ["-s", str(1 + i), tree, "ACABY02", "1.0"])["stdout"] for i in range(2))
+    with pytest.raises(sg.SagephyError):
+        ctx.run("BranchRelaxer", ["-s", "1", RELAX_TREE, "ACLBPL07", "1.0", "0.1", "0.1", "1.0"], n=1)      # 2*theta*mu < sigma^2
+    # Philox mode draws from the same conditional distributions as the MT stream (same code, other uniforms)
+    n, nv = 20000, 15
+    for model in (["ACTK98", "1.0", "0.5"], ["ACRY07", "1.0", "0.5"], ["ACABY02", "1.0"], ["ACLBPL07", "1.0", "1.0", "2.0", "0.5"]):
+        args = ["-s", "77", RELAX_TREE_NOSTEM] + model
+        b = ctx.run("BranchRelaxer", args, n=n, rng=sg.RNG_PHILOX)
+        r = ctx.run("BranchRelaxer", args, n=4000, rng=sg.RNG_MT_REPLAY)
+        assert (b.rep_status == 0).all() and (r.rep_status == 0).all()
+        got, ref = b.values(0).reshape(n, nv), r.values(0).reshape(4000, nv)
+        for x in (0, 6, 13):
+            assert ks_ok(got[:, x], ref[:, x]), (model, x)
+        # parent-child dependence is there: vertex 0 (leaf a) follows vertex 2 (its parent)
+        if model[0] != "ACLBPL07":
+            assert abs(np.corrcoef(np.log(got[:, 0]), np.log(got[:, 2]))[0, 1] - np.corrcoef(np.log(ref[:, 0]), np.log(ref[:, 2]))[0, 1]) < 0.05
+        assert np.array_equal(b.values(1).reshape(n, nv), got * np.array([0.1, 0.1, 0.5, 0.3, 0.3, 0.3, 0.4, 0.2, 0.2, 0.6, 0.5, 0.5, 0.3, 0.2, 0.0]))
+
+
 # ---- chained stage: generator batch -> BranchRelaxer without a host round trip --------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("which", [sg.STREAM_PRUNED_TREE, sg.STREAM_UNPRUNED_TREE], ids=["pruned", "unpruned"])
@@ -358,7 +398,7 @@ def test_chained_relaxer_equals_reference_on_the_emitted_newick(ctx, which):
     gen_args = ["-s", "21", "-min", "0", "-max", "40", "-minper", "0", HOST8, "0.5", "0.4", "0.5", "g"]
     n = 24
     src = ctx.run("GuestTreeGen", gen_args, n=n, rng=sg.RNG_MT_REPLAY, flags=sg.FLAG_KEEP_TREES)
-    for model in (["IIDLogNormal", "0", "0.25"], ["IIDGamma", "2", "0.5"], ["IIDUniform", "0.5", "1.5"]):
+    for model in (["IIDLogNormal", "0", "0.25"], ["IIDGamma", "2", "0.5"], ["IIDUniform", "0.5", "1.5"], ["ACTK98", "1.0", "0.5"], ["ACLBPL07", "1.0", "1.0", "2.0", "0.5"]):
         for extra in ([], ["-x", "-innms"]):
             args = ["-s", "300"] + extra + ["chained-input"] + model
             out = ctx.relax_on_batch(src, args, which=which, rng=sg.RNG_MT_REPLAY)
