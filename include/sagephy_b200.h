@@ -144,6 +144,14 @@ void sgp_batch_summary(sgp_batch* b, sgp_summary* out);
 void sgp_batch_timings(const sgp_batch* b, sgp_timings* out);
 /* Writes the files the reference would write (n == 1: identical names; n > 1: one file per stream, replicates concatenated). */
 sgp_status sgp_batch_write_files(sgp_batch* b);
+/* Output layouts for n > 1 (downstream tools such as the reference's partial.py read one tree / leaf map per
+ * file, partial.py:6-21,67-103):
+ *   SGP_LAYOUT_PACKED        one file per stream, replicates concatenated, plus "<file>.idx": a "#sagephy-idx app=<App> n=<n> first=<k>" line,
+ *                            then one line "offset<TAB>length<TAB>status" per replicate (tools/unpack_batch.py splits it again)
+ *   SGP_LAYOUT_PER_REPLICATE replicate i written exactly as the reference run with output prefix "<prefix>_<i>" would write it
+ *                            (first_index + i is used in the name; failed replicates write only their failure note). */
+typedef enum { SGP_LAYOUT_PACKED = 0, SGP_LAYOUT_PER_REPLICATE = 1 } sgp_layout;
+sgp_status sgp_batch_write_files_layout(sgp_batch* b, int layout, int64_t first_index);
 void sgp_batch_free(sgp_batch* b);
 
 /* Probes used by the parity tests: run the device implementations of the Java-exact primitives on `n` inputs. */

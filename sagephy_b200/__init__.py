@@ -25,6 +25,7 @@ EVENT_NAMES = ("SPECIATION", "CODIVERGENCE", "LEAF", "UNSAMPLED_LEAF", "DUPLICAT
 RNG_PHILOX, RNG_MT_REPLAY = 0, 1
 FLAG_MULTI_TREE_INPUT = 1
 FLAG_KEEP_TREES = 2
+LAYOUT_PACKED, LAYOUT_PER_REPLICATE = 0, 1
 STREAM_UNPRUNED_TREE, STREAM_PRUNED_TREE = 0, 1
 STATUS_OK, STATUS_USAGE = 0, 6
 
@@ -34,7 +35,7 @@ EXPORTED_SYMBOLS = (
     "sgp_batch_stream_device_data", "sgp_batch_stream_offsets", "sgp_batch_copy_stream", "sgp_batch_copy_offsets", "sgp_batch_copy_stream_async", "sgp_batch_copy_offsets_async", "sgp_context_wait_copies", "sgp_batch_stream_mask", "sgp_batch_values", "sgp_batch_stream_bytes", "sgp_batch_stream_suffix",
     "sgp_batch_status", "sgp_batch_attempts", "sgp_batch_sampled_leaves", "sgp_batch_root_times", "sgp_batch_total_times",
     "sgp_batch_event_counts", "sgp_batch_stdout", "sgp_batch_stderr", "sgp_batch_out_prefix", "sgp_batch_summary",
-    "sgp_batch_timings", "sgp_batch_write_files", "sgp_batch_free", "sgp_probe_double_to_string", "sgp_probe_math",
+    "sgp_batch_timings", "sgp_batch_write_files", "sgp_batch_write_files_layout", "sgp_batch_free", "sgp_probe_double_to_string", "sgp_probe_math",
     "sgp_probe_mt", "sgp_probe_issue_peaks")
 
 
@@ -92,6 +93,7 @@ def load_library() -> C.CDLL:
     L.sgp_batch_summary.argtypes = [vp, C.POINTER(SummaryStruct)]
     L.sgp_batch_timings.argtypes = [vp, C.POINTER(TimingsStruct)]
     L.sgp_batch_write_files.argtypes = [vp]; L.sgp_batch_write_files.restype = C.c_int
+    L.sgp_batch_write_files_layout.argtypes = [vp, C.c_int, C.c_int64]; L.sgp_batch_write_files_layout.restype = C.c_int
     L.sgp_batch_free.argtypes = [vp]
     L.sgp_probe_double_to_string.argtypes = [vp, C.POINTER(C.c_double), i64, C.c_char_p]; L.sgp_probe_double_to_string.restype = C.c_int
     L.sgp_probe_math.argtypes = [vp, C.c_int, C.POINTER(C.c_double), i64, C.POINTER(C.c_double)]; L.sgp_probe_math.restype = C.c_int
@@ -252,7 +254,13 @@ class Batch:
         self._lib.sgp_batch_timings(self._h, C.byref(t))
         return {k: getattr(t, k) for k, _ in TimingsStruct._fields_}
 
-    def write_files(self):
+    def write_files(self, layout=None, first_index: int = 0):
+        """layout None: the reference's own file names (n = 1); LAYOUT_PACKED / LAYOUT_PER_REPLICATE: see sagephy_b200.h."""
+        if layout is not None:
+            rc = self._lib.sgp_batch_write_files_layout(self._h, int(layout), int(first_index))
+            if rc != STATUS_OK:
+                raise SagephyError(f"sgp_batch_write_files_layout failed ({rc})")
+            return
         rc = self._lib.sgp_batch_write_files(self._h)
         if rc != 0:
             raise SagephyError(f"sgp_batch_write_files failed ({rc})")

@@ -193,6 +193,40 @@ sgp_status sgp_batch_write_files(sgp_batch* b) {
     }
     return SGP_OK;
 }
+sgp_status sgp_batch_write_files_layout(sgp_batch* b, int layout, int64_t first_index) {
+    if (!b || (layout != SGP_LAYOUT_PACKED && layout != SGP_LAYOUT_PER_REPLICATE)) return SGP_ERR_INVALID_ARGUMENT;
+    if (b->b.quiet || !b->b.d_offsets) return SGP_OK;
+    b->b.fetch_info(); b->b.fetch_offsets();
+    const long long n = b->b.n;
+    for (int s = 0; s < 8; ++s) {
+        if (!(b->b.stream_mask & (1u << s))) continue;
+        const char* data = b->b.stream_host(s);
+        if (!data && b->b.stream_bytes[s]) return SGP_ERR_INTERNAL;
+        const unsigned long long* off = b->b.h_offsets.data() + (size_t)s * (n + 1);
+        const std::string sfx = b->b.suffix[s];
+        if (layout == SGP_LAYOUT_PACKED) {
+            std::ofstream f(b->b.out_prefix + sfx, std::ios::binary), idx(b->b.out_prefix + sfx + ".idx", std::ios::binary);
+            if (!f || !idx) return SGP_ERR_INVALID_ARGUMENT;
+            f.write(data, (std::streamsize)b->b.stream_bytes[s]);
+            static const char* kApps[] = {"HostTreeGen", "GuestTreeGen", "DomainTreeGen", "BranchRelaxer"};
+            idx << "#sagephy-idx app=" << kApps[b->b.app & 3] << " n=" << n << " first=" << first_index << '\n';
+            for (long long i = 0; i < n; ++i) idx << off[i] << '\t' << (off[i + 1] - off[i]) << '\t' << b->b.status[i] << '\n';
+        } else {
+            for (long long i = 0; i < n; ++i) {
+                std::string name = sfx;
+                if (b->b.status[i] != 0) {
+                    // a failed reference run leaves only the failure note (HostTreeGen.java:65: <prefix>.info; GuestTreeGen.java:50: <prefix>.pruned.info)
+                    if (s != SGP_STREAM_PRUNED_INFO || off[i + 1] == off[i]) continue;
+                    if (b->b.app == 0) name = ".info";
+                }
+                std::ofstream f(b->b.out_prefix + "_" + std::to_string(first_index + i) + name, std::ios::binary);
+                if (!f) return SGP_ERR_INVALID_ARGUMENT;
+                f.write(data + off[i], (std::streamsize)(off[i + 1] - off[i]));
+            }
+        }
+    }
+    return SGP_OK;
+}
 void sgp_batch_free(sgp_batch* b) { delete b; }
 
 sgp_status sgp_probe_double_to_string(sgp_context* ctx, const double* v, int64_t n, char* out) {

@@ -4,6 +4,8 @@
 //   -n / --replicates N         number of replicates (default 1 => the same files the reference writes)
 //   -rng / --rng philox|mt-replay   (default: mt-replay when -s is given and N == 1, else philox)
 //   -gpu / --gpu K              CUDA device index (default 0)
+//   --out-layout packed|per-replicate   for N > 1: one file per stream + .idx (default), or one set of files per replicate named
+//                               <prefix>_<i>.* (what N reference runs with prefixes <prefix>_0 ... would leave behind)
 // Exit code is 0 in every case the reference exits 0 (including usage and max-attempts failures).
 #include <cstdio>
 #include <cstdlib>
@@ -20,12 +22,13 @@ int main(int argc, char** argv) {
     std::string app = argv[1];
     std::vector<const char*> rest;
     sgp_batch_opts o; std::memset(&o, 0, sizeof o); o.n_replicates = 1; o.rng_mode = -1;
-    int gpu = 0; bool has_seed = false;
+    int gpu = 0; bool has_seed = false; int layout = -1;
     for (int i = 2; i < argc; ++i) {
         std::string t = argv[i];
         if ((t == "-n" || t == "--replicates") && i + 1 < argc) { o.n_replicates = std::atoll(argv[++i]); continue; }
         if ((t == "-rng" || t == "--rng") && i + 1 < argc) { std::string m = argv[++i]; o.rng_mode = (m == "mt-replay" || m == "mt") ? SGP_RNG_MT_REPLAY : SGP_RNG_PHILOX; continue; }
         if ((t == "-gpu" || t == "--gpu") && i + 1 < argc) { gpu = std::atoi(argv[++i]); continue; }
+        if (t == "--out-layout" && i + 1 < argc) { layout = std::string(argv[++i]) == "per-replicate" ? SGP_LAYOUT_PER_REPLICATE : SGP_LAYOUT_PACKED; continue; }
         if (t == "-s" || t == "--seed") has_seed = true;
         rest.push_back(argv[i]);
     }
@@ -41,7 +44,8 @@ int main(int argc, char** argv) {
             const int32_t* status = sgp_batch_status(b);
             bool any_fail = false; for (int64_t i = 0; i < sgp_batch_n(b); ++i) if (status[i] != SGP_REP_OK) any_fail = true;
             if (any_fail) std::fputs("Failed to produce valid pruned tree within max allowed attempts.\n", stderr);
-            sgp_batch_write_files(b);
+            if (o.n_replicates == 1 && layout < 0) sgp_batch_write_files(b);             // the reference's own file names
+            else sgp_batch_write_files_layout(b, layout < 0 ? SGP_LAYOUT_PACKED : layout, o.replicate_offset);
         }
         sgp_batch_free(b);
     }

@@ -3,6 +3,7 @@
 Bar: byte-exact text in MT seed-replay mode (replicate i == reference-style run with -s seed+i); two-sample KS p > 0.01
 between Philox throughput mode and the MT oracle for the continuous statistics, chi-square for the discrete ones."""
 import math
+import os
 import re
 
 import numpy as np
@@ -181,6 +182,35 @@ def test_label_kernels_agree(ctx, monkeypatch):
     fast = ctx.run("HostTreeGen", args, n=2000, rng=sg.RNG_PHILOX)
     for st in range(4):
         assert bytes(slow.stream(st)) == bytes(fast.stream(st))
+
+
+def test_output_layouts_match_separate_reference_runs(ctx, tmp_path):
+    # per-replicate layout == what N reference runs with prefixes <prefix>_<i> leave behind; the packed
+    # layout + tools/unpack_batch.py gives the same files again. "-a 40" makes some replicates fail (failure note only).
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("unpack_batch", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "unpack_batch.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    for app, core in (("HostTreeGen", ["-min", "30", "-max", "30", "-a", "40", "1.0", "3.0", "0.3"]), ("GuestTreeGen", ["-a", "3", "-min", "12", "-max", "14", HOST5, "0.5", "0.4", "0.3"])):
+        n, first = 10, 5
+        want = {}
+        for i in range(n):
+            w = oracle_run(app, ["-s", str(70 + i)] + core + [f"o_{first + i}"])
+            want.update({k: v for k, v in w["files"].items()})
+        for layout in (sg.LAYOUT_PER_REPLICATE, sg.LAYOUT_PACKED):
+            d = tmp_path / f"{app}_{layout}"; d.mkdir()
+            b = ctx.run(app, ["-s", "70"] + core + [str(d / "o")], n=n, rng=sg.RNG_MT_REPLAY)
+            b.write_files(layout=layout, first_index=first)
+            if layout == sg.LAYOUT_PACKED:
+                assert mod.unpack(str(d / "o"), out_dir=str(d / "split")) > 0
+                got_dir = d / "split"
+            else:
+                got_dir = d
+            got = {p.name: p.read_bytes() for p in got_dir.iterdir() if p.is_file() and not p.name.endswith(".idx") and p.name != "o" and "_" in p.name}
+            assert set(got) == set(want), (sorted(set(got) ^ set(want)))
+            for k in want:
+                # the "Arguments:" line echoes the output prefix, which differs by construction (tmp dir vs bare name)
+                strip = lambda t: b"\n".join(l for l in t.split(b"\n") if not l.startswith(b"Arguments:"))
+                assert strip(got[k]) == strip(want[k]), (app, layout, k)
 
 
 # ---- Philox throughput mode: distributions ---------------------------------------------------------------------------------------

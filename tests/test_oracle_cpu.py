@@ -236,3 +236,26 @@ def test_no_cpu_fallback_without_device():
         pytest.skip("a GPU is present")
     with pytest.raises(sg.SagephyError):
         sg.Context(0)
+
+
+def test_unpack_batch_tool_splits_packed_streams(tmp_path):
+    # tools/unpack_batch.py: packed stream + .idx -> one file per replicate, named like separate reference runs
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("unpack_batch", os.path.join(ROOT, "tools", "unpack_batch.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    prefix = str(tmp_path / "run")
+    parts = [b"(a:1,b:2);\n", b"", b"((x:1,y:1):1,z:2);\n"]
+    notes = [b"# info 0\n", b"Failed to produce valid pruned tree within max allowed attempts.\n", b"# info 2\n"]
+    for sfx, chunks in ((".pruned.tree", parts), (".pruned.info", notes)):
+        with open(prefix + sfx, "wb") as f:
+            f.write(b"".join(chunks))
+        with open(prefix + sfx + ".idx", "w") as f:
+            f.write("#sagephy-idx app=HostTreeGen n=3 first=10\n")
+            off = 0
+            for i, c in enumerate(chunks):
+                f.write(f"{off}\t{len(c)}\t{1 if i == 1 else 0}\n"); off += len(c)
+    assert mod.unpack(prefix) == 5
+    assert (tmp_path / "run_10.pruned.tree").read_bytes() == parts[0] and (tmp_path / "run_12.pruned.tree").read_bytes() == parts[2]
+    assert not (tmp_path / "run_11.pruned.tree").exists()
+    assert (tmp_path / "run_11.info").read_bytes() == notes[1]          # HostTreeGen's failure note goes to <prefix>.info
+    assert (tmp_path / "run_12.pruned.info").read_bytes() == notes[2]
