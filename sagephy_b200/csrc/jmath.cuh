@@ -312,6 +312,13 @@ struct MemSink {
 };
 
 template <class Sink> SGP_HD void put_str(Sink& s, const char* z) { while (*z) s.put(*z++); }
+// String literal: the length is a compile-time constant (the size pass adds it in one step) and the unrolled stores carry the
+// characters as immediates — no per-character load, test and branch as in put_str.
+template <class Sink, int N> SGP_HD void put_lit(Sink& s, const char (&z)[N]) {
+    if (Sink::kCounts) { s.skip(N - 1); return; }
+#pragma unroll
+    for (int i = 0; i < N - 1; ++i) s.put(z[i]);
+}
 SGP_HD int dec_len_u32(uint32_t v) {
     return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
 }

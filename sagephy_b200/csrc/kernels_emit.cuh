@@ -32,38 +32,38 @@ template <class Sink> __device__ void put_name(Sink& s, const EmitArgs& a, const
 template <class Sink> __device__ void put_discpt(Sink& s, const EmitArgs& a, const Node& x) {
     const double* t = a.app == 2 ? a.gene_ep_times + 3 * (size_t)(a.gene_ep_base[x.gtree] + x.epoch) : a.ep_times + 3 * (size_t)x.epoch;
     int j = 0; while (j < 3) { if (t[j] >= x.abstime) break; ++j; }
-    put_str(s, "DISCPT=("); put_i64(s, x.epoch); s.put(','); put_i64(s, j); s.put(')');
+    put_lit(s, "DISCPT=("); put_i64(s, x.epoch); s.put(','); put_i64(s, j); s.put(')');
 }
 
 template <class Sink> __device__ void put_meta(Sink& s, const EmitArgs& a, const Node& x) {
-    put_str(s, "[ID="); put_i64(s, x.number);
+    put_lit(s, "[ID="); put_i64(s, x.number);
     if (!a.is_species) {
-        put_str(s, " HOST="); put_i64(s, x.sigma); put_str(s, " GUEST=");
+        put_lit(s, " HOST="); put_i64(s, x.sigma); put_lit(s, " GUEST=");
         put_blob(s, a.blob, a.gname_off[2 * x.gtree], a.gname_off[2 * x.gtree + 1]);
     }
     switch (x.event) {
-        case EV_DUPLICATION: put_str(s, a.is_species ? " VERTEXTYPE=Speciation " : " VERTEXTYPE=Duplication "); put_discpt(s, a, x); break;
-        case EV_LOSS: put_str(s, " VERTEXTYPE=Loss"); break;
-        case EV_REPLACING_LOSS: put_str(s, " VERTEXTYPE=Replacing Loss"); break;
-        case EV_SPECIATION: put_str(s, " VERTEXTYPE=Speciation "); put_discpt(s, a, x); break;
-        case EV_CODIVERGENCE: put_str(s, " VERTEXTYPE=Co-divergence "); put_discpt(s, a, x); break;
-        case EV_LEAF: put_str(s, " VERTEXTYPE=Leaf"); break;
-        case EV_UNSAMPLED_LEAF: put_str(s, " VERTEXTYPE=UnsampledLeaf"); break;
+        case EV_DUPLICATION: if (a.is_species) put_lit(s, " VERTEXTYPE=Speciation "); else put_lit(s, " VERTEXTYPE=Duplication "); put_discpt(s, a, x); break;
+        case EV_LOSS: put_lit(s, " VERTEXTYPE=Loss"); break;
+        case EV_REPLACING_LOSS: put_lit(s, " VERTEXTYPE=Replacing Loss"); break;
+        case EV_SPECIATION: put_lit(s, " VERTEXTYPE=Speciation "); put_discpt(s, a, x); break;
+        case EV_CODIVERGENCE: put_lit(s, " VERTEXTYPE=Co-divergence "); put_discpt(s, a, x); break;
+        case EV_LEAF: put_lit(s, " VERTEXTYPE=Leaf"); break;
+        case EV_UNSAMPLED_LEAF: put_lit(s, " VERTEXTYPE=UnsampledLeaf"); break;
         default: {
             const bool additive = x.event == EV_ADDITIVE_TRANSFER || (x.event >= EV_AT_GG_SS && x.event <= EV_AT_DG_DS);
-            put_str(s, additive ? " VERTEXTYPE=Additive Transfer" : " VERTEXTYPE=Replacing Transfer");
+            if (additive) put_lit(s, " VERTEXTYPE=Additive Transfer"); else put_lit(s, " VERTEXTYPE=Replacing Transfer");
             if (x.event >= EV_AT_GG_SS) {
                 const int k = (x.event - EV_AT_GG_SS) & 3;
-                put_str(s, (k & 2) ? " Intergene" : " Intragene"); put_str(s, (k & 1) ? " Interspecies" : " Intraspecies");
+                if (k & 2) put_lit(s, " Intergene"); else put_lit(s, " Intragene"); if (k & 1) put_lit(s, " Interspecies"); else put_lit(s, " Intraspecies");
             }
-            put_str(s, " FROMTOLINEAGE=("); put_i64(s, x.from_arc); s.put(','); put_i64(s, x.to_arc);
+            put_lit(s, " FROMTOLINEAGE=("); put_i64(s, x.from_arc); s.put(','); put_i64(s, x.to_arc);
             if (x.event >= EV_AT_GG_SS) {
                 s.put(';');
-                if (x.from_g >= 0) put_blob(s, a.blob, a.gname_off[2 * x.from_g], a.gname_off[2 * x.from_g + 1]); else put_str(s, "null");
+                if (x.from_g >= 0) put_blob(s, a.blob, a.gname_off[2 * x.from_g], a.gname_off[2 * x.from_g + 1]); else put_lit(s, "null");
                 s.put(',');
-                if (x.to_g >= 0) put_blob(s, a.blob, a.gname_off[2 * x.to_g], a.gname_off[2 * x.to_g + 1]); else put_str(s, "null");
+                if (x.to_g >= 0) put_blob(s, a.blob, a.gname_off[2 * x.to_g], a.gname_off[2 * x.to_g + 1]); else put_lit(s, "null");
             }
-            put_str(s, ") "); put_discpt(s, a, x);
+            put_lit(s, ") "); put_discpt(s, a, x);
         }
     }
     s.put(']');
@@ -85,7 +85,7 @@ template <bool PRUNED, class Sink> __device__ void put_tree_piece(Sink& s, const
     if (!a.exclude_meta) put_meta(s, a, x);
     if (x.flags & (PRUNED ? NF_LEFT_P : NF_LEFT_U)) s.put(',');
     if (vi == root) {
-        if (!a.exclude_meta) put_str(s, PRUNED ? "[NAME=PrunedTree]" : "[NAME=UnprunedTree]");
+        if (!a.exclude_meta) { if (PRUNED) put_lit(s, "[NAME=PrunedTree]"); else put_lit(s, "[NAME=UnprunedTree]"); }
         s.put(';'); s.put('\n');
     }
 }
@@ -101,7 +101,7 @@ template <bool PRUNED, class Sink> __device__ void put_info_line(Sink& s, const 
     const int32_t* c = PRUNED ? inf.cnt_p : inf.cnt_u;
     if (ln == 0) { put_str(s, a.app == 0 ? "# HOSTTREEGEN\n" : a.app == 1 ? "# GUESTTREEGEN\n" : "# DOMAINTREEGEN\n"); return; }
     if (ln == 1) {
-        put_str(s, "Arguments:\t");
+        put_lit(s, "Arguments:\t");
         put_blob(s, a.blob, a.args_pre_off, a.args_pre_len);
         if (a.seed_mode) { put_i64(s, a.seed_base + gid); put_blob(s, a.blob, a.args_post_off, a.args_post_len); }
         s.put('\n'); return;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) k_emit(EmitArgs a) {
         if (!ok) {
             // failed replicate: the reference writes only the failure note (to <prefix>.info / <prefix>.pruned.info)
             if (st == ST_PRUNED_INFO && inf.status == REP_MAX_ATTEMPTS) {
-                auto pc = [&](auto& s, int) { put_str(s, "Failed to produce valid pruned tree within max allowed attempts.\n"); };
+                auto pc = [&](auto& s, int) { put_lit(s, "Failed to produce valid pruned tree within max allowed attempts.\n"); };
                 if (WRITE) bytes = emit_pieces<true>(1, base, stage, pc, [](int) { return 65u; }, no_store);
                 else bytes = emit_pieces<false>(1, base, stage, pc, no_load, no_store);
             }
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) k_emit(EmitArgs a) {
             if constexpr (st == ST_UNPRUNED_TREE || st == ST_PRUNED_TREE) {
                 constexpr bool pr = st == ST_PRUNED_TREE;
                 if (pr && inf.p_root < 0) {
-                    auto pc = [&](auto& s, int) { if (a.exclude_meta) put_str(s, ";\n"); else put_str(s, a.app == 0 ? "[NAME=PrunedTree];" : "[NAME=PrunedTree];\n"); };
+                    auto pc = [&](auto& s, int) { if (a.exclude_meta) put_lit(s, ";\n"); else put_str(s, a.app == 0 ? "[NAME=PrunedTree];" : "[NAME=PrunedTree];\n"); };
                     const unsigned l = a.exclude_meta ? 2u : (a.app == 0 ? 18u : 19u);
                     if (WRITE) bytes = emit_pieces<true>(1, base, stage, pc, [l](int) { return l; }, no_store);
                     else bytes = emit_pieces<false>(1, base, stage, pc, no_load, no_store);

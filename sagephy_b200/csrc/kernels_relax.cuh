@@ -294,7 +294,7 @@ template <class Sink> __device__ void put_relax_vertex(Sink& s, const RelaxArgs&
     const double len = a.relaxed[base + x];
     if (len == len) { s.put(':'); put_double(s, a.T, len); }
     if (a.do_meta) {
-        put_str(s, "[ID="); put_i64(s, x); put_str(s, " ORIGBL="); put_double(s, a.T, a.orig[t]); put_str(s, " RATE="); put_double(s, a.T, a.rates[base + x]); s.put(']');
+        put_lit(s, "[ID="); put_i64(s, x); put_lit(s, " ORIGBL="); put_double(s, a.T, a.orig[t]); put_lit(s, " RATE="); put_double(s, a.T, a.rates[base + x]); s.put(']');
     }
     if (f & 2) s.put(',');
     if (x == tv.root) { s.put(';'); s.put('\n'); }
@@ -302,13 +302,13 @@ template <class Sink> __device__ void put_relax_vertex(Sink& s, const RelaxArgs&
 // info pieces: 0 header, 1 args, 2 attempts, then 3 arrays x nV elements, then the constant model tail
 template <class Sink> __device__ void put_relax_info(Sink& s, const RelaxArgs& a, const RelaxTreeView& tv, long long base, long long gid, int attempts, int k) {
     const int nV = tv.nV;
-    if (k == 0) { put_str(s, "# BRANCHLENGTHRELAXER\n"); return; }
+    if (k == 0) { put_lit(s, "# BRANCHLENGTHRELAXER\n"); return; }
     if (k == 1) {
-        put_str(s, "Arguments:\t"); put_blob(s, a.blob, a.args_pre_off, a.args_pre_len);
+        put_lit(s, "Arguments:\t"); put_blob(s, a.blob, a.args_pre_off, a.args_pre_len);
         if (a.seed_mode) { put_i64(s, a.seed_base + gid); put_blob(s, a.blob, a.args_post_off, a.args_post_len); }
         s.put('\n'); return;
     }
-    if (k == 2) { put_str(s, "Attempts:\t"); put_i64(s, attempts); s.put('\n'); return; }
+    if (k == 2) { put_lit(s, "Attempts:\t"); put_i64(s, attempts); s.put('\n'); return; }
     k -= 3;
     if (k < 3 * nV) {
         const int arr = k / nV, x = k - arr * nV;
