@@ -213,6 +213,23 @@ def test_output_layouts_match_separate_reference_runs(ctx, tmp_path):
                 assert strip(got[k]) == strip(want[k]), (app, layout, k)
 
 
+def test_leaf_sizes_file_option(ctx, tmp_path):
+    # -sizes: the wanted number of sampled leaves is drawn uniformly from a one-column file before the retry loop starts
+    # (GuestTreeMachina.java:76) and every attempt is tested against it exactly (:159-163)
+    f = tmp_path / "sizes.txt"
+    f.write_text("3\n5\n8\n5\n12\n")
+    assert_replay_parity(ctx, "HostTreeGen", ["-s", "90", "-sizes", str(f), "-min", "2", "-max", "20", "-p", "0.9", "1.0", "2.5", "0.3", "o"], 24, "o")
+    assert_replay_parity(ctx, "HostTreeGen", ["-s", "91", "-bi", "-sizes", str(f), "-min", "2", "-max", "20", "1.0", "2.5", "0.3", "o"], 16, "o")
+    assert_replay_parity(ctx, "GuestTreeGen", ["-s", "92", "-sizes", str(f), "-min", "2", "-max", "30", "-minper", "0", HOST5, "0.5", "0.4", "0.3", "o"], 16, "o")
+    # Philox fast path: every accepted tree has one of the listed sizes, in the listed proportions (5 appears twice)
+    n = 20000
+    b = ctx.run("HostTreeGen", ["-s", "93", "-sizes", str(f), "-min", "2", "-max", "20", "-p", "0.9", "1.0", "2.5", "0.3", "o"], n=n, rng=sg.RNG_PHILOX, stream_mask=0b0010)
+    assert (b.rep_status == 0).all()
+    k, c = np.unique(b.sampled_leaves, return_counts=True)
+    assert list(k) == [3, 5, 8, 12]
+    assert stats.chisquare(c, f_exp=n * np.array([0.2, 0.4, 0.2, 0.2])).pvalue > 0.001
+
+
 # ---- Philox throughput mode: distributions ---------------------------------------------------------------------------------------
 def ks_ok(a, b):
     return stats.ks_2samp(a, b).pvalue > 0.01
