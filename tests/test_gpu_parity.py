@@ -16,14 +16,18 @@ from oracle_util import oracle_batch, oracle_double_to_string, oracle_mt_words, 
 pytestmark = pytest.mark.gpu
 
 
+def seed_index(args):
+    return (args.index("-s") if "-s" in args else args.index("--seed")) + 1
+
+
 def with_seed(args, seed):
     a = list(args)
-    a[a.index("-s") + 1] = str(seed)
+    a[seed_index(a)] = str(seed)
     return a
 
 
 def assert_replay_parity(ctx, app, args, n, prefix):
-    seed0 = int(args[args.index("-s") + 1])
+    seed0 = int(args[seed_index(args)])
     b = ctx.run(app, args, n=n, rng=sg.RNG_MT_REPLAY)
     status = b.rep_status
     for i in range(n):
@@ -152,12 +156,19 @@ GUEST_CASES = [
     ["-s", "8", "-nox", "-p", "0.7", HOST8, "0.6", "0.2", "0.4", "o"],
     ["-s", "9", "-stem", "0.3", "-min", "3", "-max", "40", "-minper", "0", "-maxper", "6", HOST8, "0.8", "0.5", "0.5", "o"],
     ["-s", "10", "-vp", "Gene", "-a", "3", "-min", "12", "-max", "14", HOST5, "0.5", "0.4", "0.3", "o"],   # many failures
+    ["--seed", "11", "-vph", "-mpr", "--distance-bias", "none", "--replacing-transfers", "0.3", "--leaf-sampling-probability", "0.9", HOST8, "0.5", "0.4", "0.6", "o"],   # long names, host-suffixed vertex names, -mpr (accepted and ignored)
 ]
 
 
 @pytest.mark.parametrize("args", GUEST_CASES, ids=[" ".join(a[2:a.index(HOST5) if HOST5 in a else a.index(HOST8)]) or "plain" for a in GUEST_CASES])
 def test_guest_tree_gen_replay_is_byte_exact(ctx, args):
     assert_replay_parity(ctx, "GuestTreeGen", args, 24, "o")
+
+
+def test_guest_tree_gen_quiet_prints_the_pruned_tree(ctx):
+    args = ["-s", "15", "-q", "-db", "none", HOST5, "0.5", "0.4", "0.5"]            # GuestTreeGen.java:59-64
+    b = ctx.run("GuestTreeGen", args, n=4, rng=sg.RNG_MT_REPLAY)
+    assert b.stdout == "".join(oracle_run("GuestTreeGen", with_seed(args, 15 + i))["stdout"] for i in range(4))
 
 
 def test_guest_tree_gen_on_generated_100_leaf_host(ctx, tmp_path):
