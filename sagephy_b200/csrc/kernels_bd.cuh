@@ -134,39 +134,37 @@ __global__ void __launch_bounds__(kBdFindThreads) k_bd_find_single(BdArgs a) {
         int acc_a = 0x7fffffff, acc_n = 0, acc_sampled = 0;
         unsigned long long v_completed = 0, v_abandoned = 0; int n_completed = 0;
         U4 w_next{0, 0, 0, 0};
+        // Per-lane loop: a lane leaves it when there is nothing left to claim and waits for the others at the reconvergence
+        // point below (no warp vote per vertex step).
         for (;;) {
             if (state == 0) {
                 const int na = atomicAdd(&s_next[wib], 1);
-                if (na > *v_best || na > max_attempts) state = 2;
-                else {
-                    my_a = na; state = 1; cur = tip; tos = 0.0; depth = 0; vidx = 0; sampled = 0;
-                    w_next = philox4x32_10_rk(0u, (uint32_t)my_a, rep_lo, rep_hi, a.keys);
-                }
+                if (na > *v_best || na > max_attempts) break;
+                my_a = na; state = 1; cur = tip; tos = 0.0; depth = 0; vidx = 0; sampled = 0;
+                w_next = philox4x32_10_rk(0u, (uint32_t)my_a, rep_lo, rep_hi, a.keys);
             }
-            if (__all_sync(0xffffffffu, state == 2)) break;
-            if (state == 1) {
-                if (my_a > *v_best) { v_abandoned += vidx; state = 2; continue; }      // a smaller index was accepted meanwhile
-                const U4 w = w_next;
-                ++vidx;
-                w_next = philox4x32_10_rk(vidx, (uint32_t)my_a, rep_lo, rep_hi, a.keys);   // next vertex's block: independent of this vertex's math
-                const BdVertex v = bd_vertex_single(C, cur, w);
-                const bool dup = v.event == EV_DUPLICATION;
-                sampled += v.event == EV_LEAF ? 1 : 0;
-                const bool ovf = dup && depth >= kBdStack;
-                if (dup && !ovf) st[depth + 1] = v.et;
-                const int nd = dup ? depth + 1 : depth - 1;
-                const double refill = st[nd > 0 ? (nd <= kBdStack ? nd : 0) : 0];
-                cur = dup ? v.et : tos;
-                tos = dup ? v.et : refill;
-                depth = nd;
-                if (nd < 0 || sampled > max_leaves || ovf) {       // ran to completion, or can no longer be accepted
-                    state = 0; overflow |= ovf;
-                    v_completed += vidx; ++n_completed;
-                    const bool ok = !ovf && sampled >= min_leaves && sampled <= max_leaves && (exact == -1 || sampled == exact);
-                    if (ok) { atomicMin(&s_best[wib], my_a); acc_a = my_a; acc_n = (int)vidx; acc_sampled = sampled; }
-                }
+            if (my_a > *v_best) { v_abandoned += vidx; break; }      // a smaller index was accepted meanwhile
+            const U4 w = w_next;
+            ++vidx;
+            w_next = philox4x32_10_rk(vidx, (uint32_t)my_a, rep_lo, rep_hi, a.keys);   // next vertex's block: independent of this vertex's math
+            const BdVertex v = bd_vertex_single(C, cur, w);
+            const bool dup = v.event == EV_DUPLICATION;
+            sampled += v.event == EV_LEAF ? 1 : 0;
+            const bool ovf = dup && depth >= kBdStack;
+            if (dup && !ovf) st[depth + 1] = v.et;
+            const int nd = dup ? depth + 1 : depth - 1;
+            const double refill = st[nd > 0 ? (nd <= kBdStack ? nd : 0) : 0];
+            cur = dup ? v.et : tos;
+            tos = dup ? v.et : refill;
+            depth = nd;
+            if (nd < 0 || sampled > max_leaves || ovf) {       // ran to completion, or can no longer be accepted
+                state = 0; overflow |= ovf;
+                v_completed += vidx; ++n_completed;
+                const bool ok = !ovf && sampled >= min_leaves && sampled <= max_leaves && (exact == -1 || sampled == exact);
+                if (ok) { atomicMin(&s_best[wib], my_a); acc_a = my_a; acc_n = (int)vidx; acc_sampled = sampled; }
             }
         }
+        __syncwarp();
         const int best = *v_best;
         for (int o = 16; o > 0; o >>= 1) {
             v_completed += __shfl_xor_sync(0xffffffffu, v_completed, o); v_abandoned += __shfl_xor_sync(0xffffffffu, v_abandoned, o);
