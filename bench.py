@@ -27,14 +27,15 @@ C2_ARGS = ["-s", "20260101", "-min", "100", "-max", "100", "-p", "0.8", "-a", "1
 METRIC, UNIT = "accepted trees/sec", "trees/s"
 
 # Algorithmic instruction mix of one vertex expansion of the sampler (DESIGN.md "K1 roofline"), in warp-level instructions:
-#   FP64 pipe  : 1-u, exponent split, reciprocal (1 MUFU + 4 DFMA), s = f/(2+f), degree-7 polynomial in s^2, reconstruction,
-#                times 1/(lambda+mu), start - bt, bits -> second uniform, 3 compares                                  = 32
+#   FP64 pipe  : 1-u, table-driven log (r = m/c - 1, degree-6 log1p, exponent and table terms: 10), times 1/(lambda+mu),
+#                start - bt, bits -> second uniform, 3 compares                                                        = 17
 #   IMAD.WIDE  : Philox4x32-10, two 32x32->64 products per round                                                       = 20
-#   other      : 20 three-input XORs of Philox, 4 for the two 52-bit mantissas, counters / leaf count / stack / selects = 40
+#   other      : 20 three-input XORs of Philox, 4 for the two 52-bit mantissas, table index + shared-memory load (4),
+#                counters / leaf count / stack / selects                                                               = 44
 # FP64 and IMAD issue at half rate on B200 (measured below), so the bound is the sum of the three dispatch times.
-ALG_FP64_INST_PER_VERTEX = 32.0
+ALG_FP64_INST_PER_VERTEX = 17.0
 ALG_IMAD_INST_PER_VERTEX = 20.0
-ALG_ALU_INST_PER_VERTEX = 40.0
+ALG_ALU_INST_PER_VERTEX = 44.0
 # DRAM traffic per replicate from the `ncu --set full` capture profiles/r01_c2_full_metrics.csv (200 000 replicates per launch):
 # dram__bytes_read.sum + dram__bytes_write.sum of k_bd_find_single, and of the four k_emit<write> launches together.
 NCU_FIND_DRAM_BYTES_PER_REPLICATE = (0.008397 + 0.095860) * 1e9 / 200000

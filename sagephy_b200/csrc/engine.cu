@@ -90,12 +90,14 @@ __global__ void k_probe_d2s(const double* v, long long n, char* out, MathTables 
     MemSink m{o}; put_double(m, T, v[i]);
 }
 __global__ void k_probe_math(int fn, const double* v, long long n, double* out, MathTables T) {
+    __shared__ double2 s_logtab[128];
+    load_log_table(s_logtab);
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double x = v[i];
     int err = 0;
     out[i] = fn == 0 ? jlog(x) : fn == 1 ? jlog10(x) : fn == 2 ? jexp(x) : fn == 3 ? round_sig(T, x, 8) : fn == 4 ? jnormal_quantile(x)
-           : fn == 5 ? jpow(x, 0.37) : fn == 6 ? jchi2_quantile(x, 4.0, &err) : fn == 7 ? jchi2_quantile(x, 0.25, &err) : fn == 8 ? jpow(2.718281828459045, x) : log_unit(x);
+           : fn == 5 ? jpow(x, 0.37) : fn == 6 ? jchi2_quantile(x, 4.0, &err) : fn == 7 ? jchi2_quantile(x, 0.25, &err) : fn == 8 ? jpow(2.718281828459045, x) : log_unit(x, s_logtab);
 }
 __global__ void k_probe_mt(long long seed, long long n, uint32_t* out, uint32_t* state) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;

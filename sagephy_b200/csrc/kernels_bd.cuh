@@ -16,6 +16,8 @@ namespace sgp {
 constexpr int kBdFindThreads = 256;
 
 __global__ void __launch_bounds__(kBdFindThreads) k_bd_find(BdArgs a) {
+    __shared__ double2 s_logtab[128];
+    load_log_table(s_logtab);
     __shared__ int s_next[kBdFindThreads / 32];     // next unclaimed attempt index of the warp's replicate
     __shared__ int s_best[kBdFindThreads / 32];     // smallest accepted attempt index so far
     double st_time[kBdStack]; int8_t st_arc[kBdStack];
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(kBdFindThreads) k_bd_find(BdArgs a) {
                 const U4 w = w_next;
                 ++vidx;
                 w_next = philox4x32_10(vidx, (uint32_t)my_a, rep_lo, rep_hi, k0, k1);     // next vertex's block: independent of this vertex's math
-                const BdVertex v = bd_vertex(C, a.H, X, start, w);
+                const BdVertex v = bd_vertex(C, a.H, X, start, w, s_logtab);
                 if (v.event == EV_LEAF) {
                     ++sampled; if (X == leaf0) ++c0; else ++c1;
                     if (sampled > a.P.max_leaves) { rejected = true; sp = 0; }          // the attempt can no longer be accepted
@@ -107,7 +109,9 @@ __global__ void __launch_bounds__(kBdFindThreads) k_bd_find(BdArgs a) {
 // st[0] is a dummy so that the refill load never needs a guard), `tos` mirrors st[depth]. A duplication stores the sibling and
 // continues with one child; every other event continues with `tos` and issues the refill load one whole vertex step before its
 // value can be needed. Lanes of a warp take different events every trip, so selects instead of branches halve the issue count.
-__global__ void __launch_bounds__(kBdFindThreads) k_bd_find_single(BdArgs a) {
+__global__ void __launch_bounds__(kBdFindThreads, 4) k_bd_find_single(BdArgs a) {
+    __shared__ double2 s_logtab[128];
+    load_log_table(s_logtab);
     __shared__ int s_next[kBdFindThreads / 32];
     __shared__ int s_best[kBdFindThreads / 32];
     double st[kBdStack + 1];
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(kBdFindThreads) k_bd_find_single(BdArgs a) {
         if (lane == 0) { s_next[wib] = 0; s_best[wib] = 0x7fffffff; }
         __syncwarp();
         // lane state: 0 = needs an attempt, 1 = running attempt my_a, 2 = idle (nothing left to claim)
-        int state = 0, my_a = -1, depth = 0; uint32_t vidx = 0; int sampled = 0; bool overflow = false;
+        int state = 0, my_a = -1, depth = 0; uint32_t vidx = 0; int sampled = 0; bool overflow = false, cut_short = false;
         double cur = 0.0, tos = 0.0;
         int acc_a = 0x7fffffff, acc_n = 0, acc_sampled = 0;
         unsigned long long v_completed = 0, v_abandoned = 0; int n_completed = 0;
@@ -143,11 +147,11 @@ __global__ void __launch_bounds__(kBdFindThreads) k_bd_find_single(BdArgs a) {
                 my_a = na; state = 1; cur = tip; tos = 0.0; depth = 0; vidx = 0; sampled = 0;
                 w_next = philox4x32_10_rk(0u, (uint32_t)my_a, rep_lo, rep_hi, a.keys);
             }
-            if (my_a > *v_best) { v_abandoned += vidx; break; }      // a smaller index was accepted meanwhile
+            if (my_a > *v_best) { cut_short = true; break; }      // a smaller index was accepted meanwhile
             const U4 w = w_next;
             ++vidx;
             w_next = philox4x32_10_rk(vidx, (uint32_t)my_a, rep_lo, rep_hi, a.keys);   // next vertex's block: independent of this vertex's math
-            const BdVertex v = bd_vertex_single(C, cur, w);
+            const BdVertex v = bd_vertex_single(C, cur, w, s_logtab);
             const bool dup = v.event == EV_DUPLICATION;
             sampled += v.event == EV_LEAF ? 1 : 0;
             const bool ovf = dup && depth >= kBdStack;
@@ -164,6 +168,7 @@ __global__ void __launch_bounds__(kBdFindThreads) k_bd_find_single(BdArgs a) {
                 if (ok) { atomicMin(&s_best[wib], my_a); acc_a = my_a; acc_n = (int)vidx; acc_sampled = sampled; }
             }
         }
+        if (cut_short) v_abandoned += vidx;
         __syncwarp();
         const int best = *v_best;
         for (int o = 16; o > 0; o >>= 1) {
@@ -191,6 +196,8 @@ __global__ void __launch_bounds__(kBdFindThreads) k_bd_find_single(BdArgs a) {
 
 // Build pass: regenerates the accepted attempt depth-first straight into the arena (no scratch).
 __global__ void __launch_bounds__(256) k_bd_build(BdArgs a) {
+    __shared__ double2 s_logtab[128];
+    load_log_table(s_logtab);
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.n) return;
     RepInfo& inf = a.info[r];
@@ -206,7 +213,7 @@ __global__ void __launch_bounds__(256) k_bd_build(BdArgs a) {
         --sp;
         const double start = st_time[sp]; const int X = st_arc[sp]; const int32_t pw = st_par[sp];
         const U4 w = philox4x32_10(vidx, inf.acc_attempt, rep_lo, rep_hi, k0, k1);
-        const BdVertex v = a.H.nV == 1 ? bd_vertex_single(C, start, w) : bd_vertex(C, a.H, X, start, w);
+        const BdVertex v = a.H.nV == 1 ? bd_vertex_single(C, start, w, s_logtab) : bd_vertex(C, a.H, X, start, w, s_logtab);
         const int me = (int)vidx++;
         Node& nd = N[me];
         nd.abstime = v.et;

@@ -306,39 +306,42 @@ __device__ __forceinline__ double u01_52(uint32_t a, uint32_t b) {
     return __hiloint2double((int)(0x3ff00000u | (a >> 12)), (int)b) - 1.0;
 }
 // Natural logarithm for 0 < x <= 1 with x a normal double (one_minus_u never produces 0, subnormals, infinities or NaNs), so
-// none of the special-case handling of the library routine is needed: exponent split, m in [sqrt(1/2), sqrt(2)),
-// s = f/(2+f) through rcp.approx + two Newton steps, then the classic degree-7 (in s^2) polynomial. Max error ~1 ulp.
-// Throughput mode only; the find and build passes both call it, so they agree bit for bit.
-// Coefficients live in constant memory so that they reach the FP64 pipe as constant-bank operands (as literals the compiler
-// rebuilds each of them with two uniform-register moves per use, which costs issue slots in the sampler's inner loop).
-__constant__ static double kLogUnitC[9] = {
-    1.531383769920937332e-01, 2.222219843214978396e-01, 3.999999999940941908e-01,
-    1.479819860511658591e-01, 1.818357216161805012e-01, 2.857142874366239149e-01, 6.666666666666735130e-01,
-    6.93147180369123816490e-01, 1.90821492927058770002e-10};
-__device__ __forceinline__ double log_unit(double x) {
-    int hi = __double2hiint(x); const int lo = __double2loint(x);
-    int e = (hi >> 20) - 1023;
-    hi = (hi & 0x000fffff) | 0x3ff00000;
-    if (hi >= 0x3ff6a09f) { hi -= 0x00100000; e += 1; }
-    const double f = __hiloint2double(hi, lo) - 1.0;
-    const double y = 2.0 + f;
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
-    r = fma(fma(-y, r, 1.0), r, r);
-    r = fma(fma(-y, r, 1.0), r, r);
-    const double s = f * r, z = s * s, w = z * z;
-    const double t1 = w * fma(w, fma(w, kLogUnitC[0], kLogUnitC[1]), kLogUnitC[2]);
-    const double t2 = z * fma(w, fma(w, fma(w, kLogUnitC[3], kLogUnitC[4]), kLogUnitC[5]), kLogUnitC[6]);
-    const double R = t2 + t1, hfsq = 0.5 * f * f, dk = (double)e;
-    return dk * kLogUnitC[7] - ((hfsq - fma(s, hfsq + R, dk * kLogUnitC[8])) - f);
+// none of the special-case handling of the library routine is needed. Table-driven (Tang): the top 7 mantissa bits select
+// c_j ~ m, r = m / c_j - 1 with |r| < 2^-8, log x = (e + K_j) ln 2 + log c_j + log1p(r) with a degree-6 polynomial — 10 FP64
+// instructions instead of the 27 of the reciprocal + degree-14 version. Buckets above sqrt(2) are treated as m / 2 (K_j = 1) so
+// that arguments just below 1 keep a small table term. Absolute error < 3e-16 (about 1 ulp for x < 0.9), which is what an
+// exponential waiting time needs. Throughput mode only; the find and build passes both call it, so they agree bit for bit.
+// The table (generated by tools/gen_tables.py) is copied to shared memory by each block: lanes index it with different j.
+constexpr int kLogTabSplit = 53;
+__device__ static const double kLogTab[256] = {
+#include "log_tables.inc"
+};
+__constant__ static double kLogPolyC[4] = {1.0 / 3.0, 0.2, -1.0 / 6.0, 6.93147180559945286227e-01};
+__device__ __forceinline__ void load_log_table(double2* s_tab) {
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) s_tab[i] = make_double2(kLogTab[2 * i], kLogTab[2 * i + 1]);
+    __syncthreads();
+}
+__device__ __forceinline__ double log_unit(double x, const double2* s_tab) {
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    const int j = (hi >> 13) & 0x7f;
+    const int e = (hi >> 20) - 1023 + (j >= kLogTabSplit ? 1 : 0);
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double2 c = s_tab[j];
+    const double r = fma(m, c.x, -1.0);
+    double p = fma(r, kLogPolyC[2], kLogPolyC[1]);       // log1p(r) = r + r^2 (-1/2 + r (1/3 + r (-1/4 + r (1/5 - r/6))))
+    p = fma(r, p, -0.25);
+    p = fma(r, p, kLogPolyC[0]);
+    p = fma(r, p, -0.5);
+    p = fma(__dmul_rn(r, r), p, r);
+    return __dadd_rn(fma((double)e, kLogPolyC[3], c.y), p);
 }
 
-__device__ __forceinline__ BdVertex bd_vertex(const BdConsts& C, const TinyHost& H, int X, double start, U4 w) {
+__device__ __forceinline__ BdVertex bd_vertex(const BdConsts& C, const TinyHost& H, int X, double start, U4 w, const double2* s_tab) {
     BdVertex r;
     const bool isRoot = H.parent[X] < 0, hostLeaf = H.left[X] < 0;
     const double low = H.vtime[X];
     // explicit (non-contractable) multiply / subtract: the find and build kernels must round identically
-    const double bt = __dmul_rn(-log_unit(one_minus_u(w.x, w.y)), C.inv_sum);
+    const double bt = __dmul_rn(-log_unit(one_minus_u(w.x, w.y), s_tab), C.inv_sum);
     const double et = __dsub_rn(start, bt);
     const double u2 = u01_52(w.z, w.w);
     r.boundary = et <= low;
@@ -352,9 +355,9 @@ __device__ __forceinline__ BdVertex bd_vertex(const BdConsts& C, const TinyHost&
 
 
 // Single-arc host ("H0:T;"): every boundary vertex is a host leaf, every interior event is on the root arc.
-__device__ __forceinline__ BdVertex bd_vertex_single(const BdConsts& C, double start, U4 w) {
+__device__ __forceinline__ BdVertex bd_vertex_single(const BdConsts& C, double start, U4 w, const double2* s_tab) {
     BdVertex r;
-    const double bt = __dmul_rn(-log_unit(one_minus_u(w.x, w.y)), C.inv_sum);
+    const double bt = __dmul_rn(-log_unit(one_minus_u(w.x, w.y), s_tab), C.inv_sum);
     const double et = __dsub_rn(start, bt);
     const double u2 = u01_52(w.z, w.w);
     r.boundary = et <= 0.0;
