@@ -38,8 +38,8 @@ ALG_IMAD_INST_PER_VERTEX = 20.0
 ALG_ALU_INST_PER_VERTEX = 44.0
 # DRAM traffic per replicate from the `ncu --set full` capture profiles/r01_c2_full_metrics.csv (200 000 replicates per launch):
 # dram__bytes_read.sum + dram__bytes_write.sum of k_bd_find_single, and of the four k_emit<write> launches together.
-NCU_FIND_DRAM_BYTES_PER_REPLICATE = (0.008397 + 0.095860) * 1e9 / 200000
-NCU_EMIT_WRITE_DRAM_BYTES_PER_REPLICATE = (4.993873 + 2.746872 + 4.501460 + 2.103417 + 0.048675 + 0.013591 + 0.052093 + 0.010538) * 1e9 / 200000
+NCU_FIND_DRAM_BYTES_PER_REPLICATE = (0.008984 + 0.076104) * 1e9 / 200000
+NCU_EMIT_WRITE_DRAM_BYTES_PER_REPLICATE = (4.995798 + 2.746934 + 4.501152 + 2.103177 + 0.048685 + 0.015023 + 0.052106 + 0.010014) * 1e9 / 200000
 
 
 def clocks_sampler(stop, rows, gpu_index):
