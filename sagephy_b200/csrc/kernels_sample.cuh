@@ -20,6 +20,58 @@ __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
     DomainEnv E{a.genes, a.n_genes, a.inter_gene, a.inter_species, DOMAIN ? a.scratch_used + (size_t)worker * a.n_genes : nullptr, a.fl_lo, a.fl_up, a.fl_tag, a.fl_start};
     MtStream mt; PhiloxStream ph;
     if (REPLAY) { mt.mt = a.mt_state + (size_t)(worker >> 5) * 624 * 32 + (worker & 31); mt.stride = 32; }
+    if constexpr (!DOMAIN) {
+        // Flat loop: every trip, lanes without a replicate claim one, transfers waiting for a recipient are served by the whole
+        // warp, and every lane with an attempt in progress takes one step of it. All 32 lanes stay in the loop until the batch
+        // is exhausted (the cooperative pieces need them).
+        SimState S; S.stage = -1; S.xfer_pending = false;
+        bool have = false, exhausted = false;
+        long long r = 0; RepInfo inf; int attempts = 0; uint64_t verts = 0, pos = 0;
+        for (;;) {
+            if (!have && !exhausted) {
+                const long long slot = (long long)atomicAdd(a.work_counter, 1ULL);
+                if (slot >= a.n) exhausted = true;
+                else {
+                    r = a.rep_ids ? a.rep_ids[slot] : slot;
+                    const long long gid = a.rep_base + r;
+                    memset(&inf, 0, sizeof(inf));
+                    inf.status = REP_PENDING; inf.exact = -1; inf.root = -1; inf.p_root = -1;
+                    if (REPLAY) { uint32_t key[4]; seed_words_i64((long long)a.seed + gid, key); mt.seed(key); }
+                    else ph.init(a.seed, (uint64_t)gid, 0xFFFFFFFFu);
+                    if (a.P.n_sizes > 0) inf.exact = a.sizes[REPLAY ? mt.next_int(a.P.n_sizes) : ph.next_int(a.P.n_sizes)];
+                    attempts = 0; verts = 0; have = true; S.stage = -1;
+                }
+            }
+            if (have && S.stage < 0) {          // start the next attempt of this replicate (GuestTreeMachina.java:81-98)
+                if (attempts > a.P.max_attempts) { inf.status = REP_MAX_ATTEMPTS; inf.attempts = attempts; inf.vertices_sampled = verts; a.info[r] = inf; have = false; }
+                else {
+                    if (REPLAY) { pos = mt.position(); sim_begin(S, mt, a.P, a.H); } else { ph.begin_attempt((uint32_t)attempts); sim_begin(S, ph, a.P, a.H); }
+                }
+            }
+            if (!__ballot_sync(0xffffffffu, have || !exhausted)) break;
+            if (REPLAY) coop_resolve_transfers(S, mt, a.P, a.H, W); else coop_resolve_transfers(S, ph, a.P, a.H, W);
+            if (have && S.stage >= 0) {
+                const int st = REPLAY ? sim_step(S, mt, a.P, a.H, a.T, W) : sim_step(S, ph, a.P, a.H, a.T, W);
+                if (st >= 0) {
+                    verts += (uint64_t)S.n;
+                    const int n = S.n, root = S.root;
+                    S.stage = -1;
+                    if (st != REP_OK) { inf.status = st; inf.attempts = attempts; inf.vertices_sampled = verts; a.info[r] = inf; have = false; }
+                    else {
+                        ++attempts;
+                        int sampled = 0;
+                        if (attempt_ok(a.P, a.H, W, root, inf.exact, &sampled)) {
+                            inf.status = REP_OK; inf.n_pool = n; inf.sampled_leaves = sampled;
+                            if (REPLAY) { inf.acc_attempt = (uint32_t)pos; inf.acc_hi = (uint32_t)(pos >> 32); } else { inf.acc_attempt = (uint32_t)(attempts - 1); inf.acc_hi = 0; }
+                            ++attempts;     // GuestTreeMachina.java:107
+                            inf.attempts = attempts; inf.vertices_sampled = verts; a.info[r] = inf; have = false;
+                        }
+                    }
+                }
+            }
+        }
+        return;
+    }
     for (;;) {
         long long slot = (long long)atomicAdd(a.work_counter, 1ULL);
         if (slot >= a.n) break;
@@ -38,7 +90,7 @@ __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
             int n = 0, root = -1;
             int st;
             if (DOMAIN) st = REPLAY ? simulate_attempt_domain(mt, a.P, E, a.T, W, n, root) : simulate_attempt_domain(ph, a.P, E, a.T, W, n, root);
-            else st = REPLAY ? simulate_attempt(mt, a.P, a.H, a.T, W, n, root) : simulate_attempt(ph, a.P, a.H, a.T, W, n, root);
+            else st = REP_MODEL_ERROR;      // not reached: the non-domain engine is the cooperative loop above
             verts += (uint64_t)n;
             if (st != REP_OK) { inf.status = st; break; }
             ++attempts;
@@ -62,27 +114,39 @@ template <bool REPLAY, bool DOMAIN>
 __global__ void __launch_bounds__(128) k_build_general(BuildArgs a) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int worker = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.n) return;
-    RepInfo& inf = a.info[r];
-    if (inf.status != REP_OK) return;
-    const long long off = a.node_off[r];
+    // all lanes of a warp stay: lanes without a tree to build still help with the cooperative pieces
+    const bool active = r < a.n && a.info[r < a.n ? r : 0].status == REP_OK;
+    if (DOMAIN && !active) return;
+    RepInfo& inf = a.info[active ? r : 0];
+    const long long off = active ? a.node_off[r] : 0;
     SimWork W;
-    W.nodes = a.nodes + off; W.cap = inf.n_pool;
+    W.nodes = a.nodes + off; W.cap = active ? inf.n_pool : 0;
     W.queue = a.aux + off; W.pend = a.aux + a.aux_stride + off;
     const int mark_n = DOMAIN ? a.max_gene_nv : a.H.nV;
     W.marks = a.scratch_marks + (size_t)worker * mark_n; W.leaf_cnt = nullptr; W.mark_gen = 0;
     for (int i = 0; i < mark_n; ++i) W.marks[i] = 0;
     DomainEnv E{a.genes, a.n_genes, a.inter_gene, a.inter_species, DOMAIN ? a.scratch_used + (size_t)worker * a.n_genes : nullptr, a.fl_lo, a.fl_up, a.fl_tag, a.fl_start};
-    int n = 0, root = -1, st;
+    int n = 0, root = -1, st = REP_OK;
     const long long gid = a.rep_base + r;
+    MtStream mt; PhiloxStream ph;
     if (REPLAY) {
-        MtStream mt; mt.mt = a.mt_state + (size_t)(worker >> 5) * 624 * 32 + (worker & 31); mt.stride = 32;
-        uint32_t key[4]; seed_words_i64((long long)a.seed + gid, key); mt.seed(key);
-        mt.skip(((uint64_t)inf.acc_hi << 32) | inf.acc_attempt);
-        st = DOMAIN ? simulate_attempt_domain(mt, a.P, E, a.T, W, n, root) : simulate_attempt(mt, a.P, a.H, a.T, W, n, root);
+        mt.mt = a.mt_state + (size_t)(worker >> 5) * 624 * 32 + (worker & 31); mt.stride = 32;
+        if (active) { uint32_t key[4]; seed_words_i64((long long)a.seed + gid, key); mt.seed(key); mt.skip(((uint64_t)inf.acc_hi << 32) | inf.acc_attempt); }
+    } else if (active) ph.init(a.seed, (uint64_t)gid, inf.acc_attempt);
+    if constexpr (DOMAIN) {
+        st = REPLAY ? simulate_attempt_domain(mt, a.P, E, a.T, W, n, root) : simulate_attempt_domain(ph, a.P, E, a.T, W, n, root);
     } else {
-        PhiloxStream ph; ph.init(a.seed, (uint64_t)gid, inf.acc_attempt);
-        st = DOMAIN ? simulate_attempt_domain(ph, a.P, E, a.T, W, n, root) : simulate_attempt(ph, a.P, a.H, a.T, W, n, root);
+        SimState S; S.stage = -1; S.xfer_pending = false;
+        if (active) { if (REPLAY) sim_begin(S, mt, a.P, a.H); else sim_begin(S, ph, a.P, a.H); }
+        for (;;) {
+            if (!__ballot_sync(0xffffffffu, S.stage >= 0)) break;
+            if (REPLAY) coop_resolve_transfers(S, mt, a.P, a.H, W); else coop_resolve_transfers(S, ph, a.P, a.H, W);
+            if (S.stage >= 0) {
+                const int rc = REPLAY ? sim_step(S, mt, a.P, a.H, a.T, W) : sim_step(S, ph, a.P, a.H, a.T, W);
+                if (rc >= 0) { st = rc; n = S.n; root = S.root; S.stage = -1; }
+            }
+        }
+        if (!active) return;
     }
     if (st != REP_OK || n != inf.n_pool) { inf.status = REP_MODEL_ERROR; return; }
     inf.root = root;

@@ -158,104 +158,258 @@ static __device__ int find_victim(const Node* N, int root, int to, double t) {
     return -1;
 }
 
-// One attempt of createUnprunedTree. Returns 0, or REP_NODE_OVERFLOW. n_out = vertices created, root_out = root index.
-//
-// Written as a state machine with ONE vertex-creation site: every loop trip either fetches the next lineage from the queue
-// (stage 0) or creates exactly one vertex (stages 1-3) through the single draw_vertex call below. Threads of a warp simulate
-// different replicates, so they can only re-converge on code that is textually shared — the expensive Java-exact vertex draw
-// (log, divide, round8) is therefore executed by all creating lanes together instead of at eight separate call sites.
+// ---- warp-cooperative pieces ---------------------------------------------------------------------------------------------------
+// A warp simulates 32 replicates, one per lane, and all lanes take one step of their attempts per loop trip (sim_step). The two
+// operations that are linear in the host epoch or in the guest tree — the recipient draw of a transfer (Epoch.sampleArc) and the
+// victim search of a replacing transfer (findVertex) — are not run by the owning lane alone (31 lanes would wait for it): the
+// lanes that need one are served one after the other by the whole warp. `leader` is the owning lane; all scalar arguments are
+// warp-uniform (broadcast by the caller); only the leader's random stream is advanced.
+__device__ __forceinline__ DD dd_add_dd(DD a, DD b) {
+    double s = a.hi + b.hi; double bb = s - a.hi; double err = (a.hi - (s - bb)) + (b.hi - bb);
+    double lo = (a.lo + b.lo) + err; double hi = s + lo; lo = lo - (hi - s);
+    return DD{hi, lo};
+}
+__device__ __forceinline__ DD dd_shfl(DD v, int src) { return DD{__shfl_sync(0xffffffffu, v.hi, src), __shfl_sync(0xffffffffu, v.lo, src)}; }
+
+__device__ __forceinline__ bool arc_eligible(const DevHost& H, int x, int donor, int tag, const int32_t* marks, int mark_gen, bool include) {
+    return x != donor && !(marks && marks[x] == mark_gen) && ((H.host_tag[x] == tag) == include);
+}
+__device__ __forceinline__ double arc_weight(const SimParams& P, const DevHost& H, int x, int donor, double t) {
+    const double dist = XMUL(2.0, XSUB(H.lca_time[(size_t)donor * H.nV + x], t));
+    double w = (P.bias == 2) ? XMUL(P.bias_rate, pow_e(XMUL(-P.bias_rate, dist))) : XDIV(1.0, dist);
+    if (w == dbl_inf()) w = 1.7976931348623157e308;
+    return w;
+}
+
+// Epoch.sampleArc by the whole warp: same selection rule as sample_arc above (first cumulative key > total * U, zero weights
+// overwrite the previous key); the double-double sums are formed by a warp scan instead of a serial loop, which moves them by
+// ~1e-32 relative — the same order as the double-double stand-in for BigDecimal itself (numerics).
+template <class RNG>
+__device__ int coop_sample_arc(int leader, RNG& rng, const SimParams& P, const DevHost& H, int epoch, int donor, double t, const int32_t* marks, int mark_gen, bool include = true) {
+    const int lane = threadIdx.x & 31;
+    const int a0 = H.ep_off[epoch], a1 = H.ep_off[epoch + 1];
+    const int tag = H.host_tag[donor];
+    if (P.bias == 0) {
+        int k = 0;
+        for (int base = a0; base < a1; base += 32) {
+            const int j = base + lane; const bool el = j < a1 && arc_eligible(H, H.ep_arcs[j], donor, tag, marks, mark_gen, include);
+            k += __popc(__ballot_sync(0xffffffffu, el));
+        }
+        if (k < 1) return -5;
+        int pick = 0; if (lane == leader) pick = rng.next_int(k);
+        pick = __shfl_sync(0xffffffffu, pick, leader);
+        for (int base = a0; base < a1; base += 32) {
+            const int j = base + lane; const int x = j < a1 ? H.ep_arcs[j] : -1;
+            const bool el = j < a1 && arc_eligible(H, x, donor, tag, marks, mark_gen, include);
+            const unsigned m = __ballot_sync(0xffffffffu, el); const int c = __popc(m);
+            if (pick < c) return __shfl_sync(0xffffffffu, x, __fns(m, 0, pick + 1));
+            pick -= c;
+        }
+        return -5;
+    }
+    DD mine{0.0, 0.0}; int k = 0;
+    for (int base = a0; base < a1; base += 32) {
+        const int j = base + lane; const int x = j < a1 ? H.ep_arcs[j] : -1;
+        const bool el = j < a1 && arc_eligible(H, x, donor, tag, marks, mark_gen, include);
+        if (el) mine = dd_add_d(mine, arc_weight(P, H, x, donor, t));
+        k += __popc(__ballot_sync(0xffffffffu, el));
+    }
+    if (k < 1) return -5;
+    for (int o = 16; o > 0; o >>= 1) { const DD other{__shfl_down_sync(0xffffffffu, mine.hi, o), __shfl_down_sync(0xffffffffu, mine.lo, o)}; if (lane < o) mine = dd_add_dd(mine, other); }
+    const DD total = dd_shfl(mine, 0);
+    DD rnd{0.0, 0.0}; if (lane == leader) rnd = dd_mul_d(total, rng.next_double());
+    rnd = dd_shfl(rnd, leader);
+    DD carry{0.0, 0.0};
+    for (int base = a0; base < a1; base += 32) {
+        const int j = base + lane; const int x = j < a1 ? H.ep_arcs[j] : -1;
+        const bool el = j < a1 && arc_eligible(H, x, donor, tag, marks, mark_gen, include);
+        DD v{el ? arc_weight(P, H, x, donor, t) : 0.0, 0.0};
+        for (int o = 1; o < 32; o <<= 1) { const DD other{__shfl_up_sync(0xffffffffu, v.hi, o), __shfl_up_sync(0xffffffffu, v.lo, o)}; if (lane >= o) v = dd_add_dd(other, v); }
+        const DD cum = dd_add_dd(carry, v);
+        const unsigned hit = __ballot_sync(0xffffffffu, el && dd_gt(cum, rnd));
+        if (hit) {
+            int chosen = __shfl_sync(0xffffffffu, x, __ffs(hit) - 1);
+            for (int jj = base + __ffs(hit); jj < a1; ++jj) {        // arcs of weight 0 that follow share the key and overwrite it
+                const int x2 = H.ep_arcs[jj];
+                if (!arc_eligible(H, x2, donor, tag, marks, mark_gen, include)) continue;
+                if (arc_weight(P, H, x2, donor, t) == 0.0) chosen = x2; else break;
+            }
+            return chosen;
+        }
+        carry = dd_shfl(cum, 31);
+    }
+    return -5;
+}
+
+// is `v` still attached to the tree under `root`? (replaced subtrees and not-yet-attached children stay in the pool)
+__device__ __forceinline__ bool node_attached(const Node* N, int v, int root) {
+    while (v != root) {
+        const int p = N[v].parent;
+        if (p < 0 || (N[p].left != v && N[p].right != v)) return false;
+        v = p;
+    }
+    return true;
+}
+// does a come before b in left-before-right pre-order? (both attached, a != b)
+__device__ __forceinline__ bool preorder_before(const Node* N, int a, int b) {
+    int da = 0, db = 0;
+    for (int v = a; N[v].parent >= 0; v = N[v].parent) ++da;
+    for (int v = b; N[v].parent >= 0; v = N[v].parent) ++db;
+    int x = a, y = b;
+    while (da > db) { x = N[x].parent; --da; }
+    while (db > da) { y = N[y].parent; --db; }
+    if (x == y) return x == a;                  // one is an ancestor of the other: the ancestor comes first
+    while (N[x].parent != N[y].parent) { x = N[x].parent; y = N[y].parent; }
+    return N[N[x].parent].left == x;
+}
+// findVertex by the whole warp: every lane tests a slice of the node pool, the pre-order-first attached match wins.
+static __device__ int coop_find_victim(const Node* N, int n, int root, int to, double t) {
+    const int lane = threadIdx.x & 31;
+    int best = -1;
+    for (int base = 0; base < n; base += 32) {
+        const int v = base + lane;
+        bool match = false;
+        if (v < n) { const Node& x = N[v]; match = x.sigma == to && x.abstime < t && XADD(x.abstime, x.bl) > t; }
+        unsigned m = __ballot_sync(0xffffffffu, match);
+        while (m) {
+            const int cand = base + __ffs(m) - 1; m &= m - 1;
+            if (!node_attached(N, cand, root)) continue;
+            if (best < 0 || preorder_before(N, cand, best)) best = cand;
+        }
+    }
+    return best;
+}
+
+// State of one attempt of createUnprunedTree between steps (a state machine with ONE vertex-creation site: every step either
+// fetches the next lineage from the queue (stage 0) or creates exactly one vertex (stages 1-3), so the expensive Java-exact
+// vertex draw — log, divide, round8 — is executed by all creating lanes together).
 // The order in which random numbers are consumed is exactly the reference's (coin -> staying child -> sampleArc(s) ->
 // moving child; left child before right child).
+struct SimState {
+    int n, qh, qt, np;
+    int stage;                     // -1: no attempt in progress; 3: create the root, 0: fetch a lineage, 1: first vertex of the pair, 2: second
+    int li, c1, X, root, sigma, ep, first_to, victim;
+    uint8_t ev; bool stay_left, xfer_pending;
+    double t;                      // start time of the vertex to create next
+};
+
 template <class RNG>
-__device__ int simulate_attempt(RNG& rng, const SimParams& P, const DevHost& H, const MathTables& T, SimWork& W, int& n_out, int& root_out) {
-    int n = 0, qh = 0, qt = 0, np = 0;
-    int stage = 3;                 // 3: create the root, 0: fetch a lineage, 1: create first vertex of the pair, 2: create second
-    int li = -1, c1 = -1; uint8_t ev = 0; bool stay_left = true;
-    int X; double t;               // arc and start time of the vertex to create next
-    if (P.ishost || !P.do_gene_birth) { X = H.root; t = H.ep_up[H.nE - 1]; }
-    else { X = sample_root(rng, P, H); t = H.ep_up[H.v2e[X]]; }
-    int root = -1, sigma = 0, ep = 0, first_to = -1, victim = -1;
-    for (;;) {
-        if (stage == 0) {
-            if (qh == qt) {
-                if (np == 0) break;
-                int best = 0;      // release the oldest parked replacing transfer (largest abstime)
-                for (int i = 1; i < np; ++i) if (W.nodes[W.pend[i]].abstime > W.nodes[W.pend[best]].abstime) best = i;
-                W.queue[qt++] = W.pend[best];
-                W.pend[best] = W.pend[--np];
-            }
-            li = W.queue[qh++];
-            const Node& ln = W.nodes[li];
-            ev = ln.event;
-            if (ev == EV_LOSS || ev == EV_REPLACING_LOSS || ev == EV_LEAF || ev == EV_UNSAMPLED_LEAF) continue;     // lineage ends
-            sigma = ln.sigma; t = ln.abstime; ep = ln.epoch;
-            if (ev == EV_SPECIATION) X = H.left[sigma];
-            else { X = sigma; if (ev != EV_DUPLICATION) stay_left = rng.next_double() < 0.5; }
-            stage = 1;
-            continue;
-        }
-        if (stage == 2) {
-            // arc of the second vertex
-            if (ev == EV_SPECIATION) X = H.right[sigma];
-            else if (ev == EV_DUPLICATION) X = sigma;
-            else if (ev == EV_ADDITIVE_TRANSFER) { X = sample_arc(rng, P, H, ep, sigma, t, nullptr, 0); first_to = X; victim = -1; }
-            else {   // EV_REPLACING_TRANSFER: look for a lineage to replace, arc by arc
-                first_to = sample_arc(rng, P, H, ep, sigma, t, nullptr, 0);
-                int to = first_to;
-                victim = find_victim(W.nodes, root, to, t);
-                const int n_arcs = H.ep_off[ep + 1] - H.ep_off[ep];
-                int n_empty = 0; const int gen = ++W.mark_gen;
-                while (victim < 0 && n_empty != n_arcs - 1) {
-                    if (W.marks[to] != gen) { W.marks[to] = gen; ++n_empty; }
-                    if (n_empty != n_arcs - 1) { to = sample_arc(rng, P, H, ep, sigma, t, W.marks, gen); victim = find_victim(W.nodes, root, to, t); }
-                }
-                X = victim >= 0 ? to : first_to;
-            }
-        }
-        // ---- the single vertex-creation site
-        const VertexDraw d = draw_vertex(rng, P, H, T, X, t);
-        const int idx = new_node(W, n, d, X);
-        if (idx < 0) { n_out = n; return REP_NODE_OVERFLOW; }
-        if (stage == 3) { root = idx; W.queue[qt++] = root; stage = 0; continue; }
-        if (stage == 1) { c1 = idx; stage = 2; continue; }
-        // ---- stage 2 done: attach the pair
-        int lc, rc;
-        if (ev == EV_SPECIATION || ev == EV_DUPLICATION) { lc = c1; rc = idx; }
+__device__ __forceinline__ void sim_begin(SimState& S, RNG& rng, const SimParams& P, const DevHost& H) {
+    S.n = 0; S.qh = 0; S.qt = 0; S.np = 0; S.stage = 3; S.li = -1; S.c1 = -1; S.ev = 0; S.stay_left = true; S.xfer_pending = false;
+    if (P.ishost || !P.do_gene_birth) { S.X = H.root; S.t = H.ep_up[H.nE - 1]; }
+    else { S.X = sample_root(rng, P, H); S.t = H.ep_up[H.v2e[S.X]]; }
+    S.root = -1; S.sigma = 0; S.ep = 0; S.first_to = -1; S.victim = -1;
+}
+
+// Transfers waiting for their recipient (stage 2 of a transfer vertex): served lane by lane by the whole warp.
+// GuestTreeInHostTreeCreator.java:171-189 (additive) and :191-279 (replacing: look for a lineage to replace, arc by arc).
+template <class RNG>
+__device__ void coop_resolve_transfers(SimState& S, RNG& rng, const SimParams& P, const DevHost& H, SimWork& W) {
+    unsigned req = __ballot_sync(0xffffffffu, S.stage == 2 && S.xfer_pending);
+    const int lane = threadIdx.x & 31;
+    while (req) {
+        const int leader = __ffs(req) - 1; req &= req - 1;
+        const int ep = __shfl_sync(0xffffffffu, S.ep, leader), donor = __shfl_sync(0xffffffffu, S.sigma, leader), root = __shfl_sync(0xffffffffu, S.root, leader);
+        const int n = __shfl_sync(0xffffffffu, S.n, leader), ev = __shfl_sync(0xffffffffu, (int)S.ev, leader);
+        const double t = __shfl_sync(0xffffffffu, S.t, leader);
+        const Node* N = reinterpret_cast<const Node*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(W.nodes), leader));
+        int32_t* marks = reinterpret_cast<int32_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(W.marks), leader));
+        int X, first_to, victim = -1;
+        if (ev == EV_ADDITIVE_TRANSFER) { X = coop_sample_arc(leader, rng, P, H, ep, donor, t, nullptr, 0); first_to = X; }
         else {
-            Node& ln = W.nodes[li];
-            ln.from_arc = sigma; ln.to_arc = X;
-            if (ev == EV_REPLACING_TRANSFER) {
-                if (victim >= 0) {
-                    Node& vn = W.nodes[victim];
-                    vn.event = EV_REPLACING_LOSS; vn.abstime = t;
-                    int w = 0;          // drop parked replacing transfers that sit in the victim's subtree (victim included)
-                    for (int i = 0; i < np; ++i) {
-                        int x = W.pend[i]; bool under = false;
-                        for (int y = x; y >= 0; y = W.nodes[y].parent) if (y == victim) { under = true; break; }
-                        if (!under) W.pend[w++] = x;
-                    }
-                    np = w;
-                    vn.left = -1; vn.right = -1;
-                } else ln.event = EV_ADDITIVE_TRANSFER;      // nothing to replace anywhere: degrade (GuestTreeInHostTreeCreator.java:228-233)
+            first_to = coop_sample_arc(leader, rng, P, H, ep, donor, t, nullptr, 0);
+            int to = first_to;
+            victim = coop_find_victim(N, n, root, to, t);
+            const int n_arcs = H.ep_off[ep + 1] - H.ep_off[ep];
+            int n_empty = 0;
+            int gen = 0; if (lane == leader) gen = ++W.mark_gen;
+            gen = __shfl_sync(0xffffffffu, gen, leader);
+            while (victim < 0 && n_empty != n_arcs - 1) {
+                if (marks[to] != gen) { __syncwarp(); if (lane == leader) marks[to] = gen; __syncwarp(); ++n_empty; }
+                if (n_empty != n_arcs - 1) { to = coop_sample_arc(leader, rng, P, H, ep, donor, t, marks, gen); victim = coop_find_victim(N, n, root, to, t); }
             }
-            lc = stay_left ? c1 : idx; rc = stay_left ? idx : c1;
+            X = victim >= 0 ? to : first_to;
         }
-        W.nodes[li].left = lc; W.nodes[li].right = rc;
-        W.nodes[lc].parent = li; W.nodes[rc].parent = li;
-        for (int s = 0; s < 2; ++s) {
-            const int c = s == 0 ? lc : rc;
-            if (W.nodes[c].event != EV_REPLACING_TRANSFER) W.queue[qt++] = c;
-            else {
-                bool replaced = false;     // TreeMap.put on an equal key overwrites the value
-                for (int i = 0; i < np; ++i) if (W.nodes[W.pend[i]].abstime == W.nodes[c].abstime) { W.pend[i] = c; replaced = true; break; }
-                if (!replaced) W.pend[np++] = c;
-            }
-        }
-        stage = 0;
+        if (lane == leader) { S.X = X; S.first_to = first_to; S.victim = victim; S.xfer_pending = false; }
     }
-    if (W.nodes[root].bl <= 1.0e-32) W.nodes[root].bl = 0.0;
-    n_out = n; root_out = root;
-    return REP_OK;
+}
+
+// One step of the attempt. Returns -1 while the attempt goes on, REP_OK when the tree is complete, REP_NODE_OVERFLOW when the
+// pool is full. A transfer's second vertex needs its recipient arc first: the step then only raises xfer_pending and the next
+// coop_resolve_transfers call fills in X / first_to / victim.
+template <class RNG>
+__device__ int sim_step(SimState& S, RNG& rng, const SimParams& P, const DevHost& H, const MathTables& T, SimWork& W) {
+    if (S.stage == 0) {
+        if (S.qh == S.qt) {
+            if (S.np == 0) {
+                if (W.nodes[S.root].bl <= 1.0e-32) W.nodes[S.root].bl = 0.0;
+                return REP_OK;
+            }
+            int best = 0;      // release the oldest parked replacing transfer (largest abstime)
+            for (int i = 1; i < S.np; ++i) if (W.nodes[W.pend[i]].abstime > W.nodes[W.pend[best]].abstime) best = i;
+            W.queue[S.qt++] = W.pend[best];
+            W.pend[best] = W.pend[--S.np];
+        }
+        S.li = W.queue[S.qh++];
+        const Node& ln = W.nodes[S.li];
+        S.ev = ln.event;
+        if (S.ev == EV_LOSS || S.ev == EV_REPLACING_LOSS || S.ev == EV_LEAF || S.ev == EV_UNSAMPLED_LEAF) return -1;     // lineage ends
+        S.sigma = ln.sigma; S.t = ln.abstime; S.ep = ln.epoch;
+        if (S.ev == EV_SPECIATION) S.X = H.left[S.sigma];
+        else { S.X = S.sigma; if (S.ev != EV_DUPLICATION) S.stay_left = rng.next_double() < 0.5; }
+        S.stage = 1;
+        return -1;
+    }
+    if (S.stage == 2 && S.xfer_pending) return -1;          // waits for coop_resolve_transfers
+    // ---- the single vertex-creation site
+    const VertexDraw d = draw_vertex(rng, P, H, T, S.X, S.t);
+    const int idx = new_node(W, S.n, d, S.X);
+    if (idx < 0) return REP_NODE_OVERFLOW;
+    if (S.stage == 3) { S.root = idx; W.queue[S.qt++] = idx; S.stage = 0; return -1; }
+    if (S.stage == 1) {
+        S.c1 = idx; S.stage = 2;
+        // arc of the second vertex
+        if (S.ev == EV_SPECIATION) S.X = H.right[S.sigma];
+        else if (S.ev == EV_DUPLICATION) S.X = S.sigma;
+        else S.xfer_pending = true;
+        return -1;
+    }
+    // ---- stage 2 done: attach the pair
+    const int li = S.li, c1 = S.c1;
+    int lc, rc;
+    if (S.ev == EV_SPECIATION || S.ev == EV_DUPLICATION) { lc = c1; rc = idx; }
+    else {
+        Node& ln = W.nodes[li];
+        ln.from_arc = S.sigma; ln.to_arc = S.X;
+        if (S.ev == EV_REPLACING_TRANSFER) {
+            if (S.victim >= 0) {
+                Node& vn = W.nodes[S.victim];
+                vn.event = EV_REPLACING_LOSS; vn.abstime = S.t;
+                int w = 0;          // drop parked replacing transfers that sit in the victim's subtree (victim included)
+                for (int i = 0; i < S.np; ++i) {
+                    int x = W.pend[i]; bool under = false;
+                    for (int y = x; y >= 0; y = W.nodes[y].parent) if (y == S.victim) { under = true; break; }
+                    if (!under) W.pend[w++] = x;
+                }
+                S.np = w;
+                vn.left = -1; vn.right = -1;
+            } else ln.event = EV_ADDITIVE_TRANSFER;      // nothing to replace anywhere: degrade (GuestTreeInHostTreeCreator.java:228-233)
+        }
+        lc = S.stay_left ? c1 : idx; rc = S.stay_left ? idx : c1;
+    }
+    W.nodes[li].left = lc; W.nodes[li].right = rc;
+    W.nodes[lc].parent = li; W.nodes[rc].parent = li;
+    for (int s = 0; s < 2; ++s) {
+        const int c = s == 0 ? lc : rc;
+        if (W.nodes[c].event != EV_REPLACING_TRANSFER) W.queue[S.qt++] = c;
+        else {
+            bool replaced = false;     // TreeMap.put on an equal key overwrites the value
+            for (int i = 0; i < S.np; ++i) if (W.nodes[W.pend[i]].abstime == W.nodes[c].abstime) { W.pend[i] = c; replaced = true; break; }
+            if (!replaced) W.pend[S.np++] = c;
+        }
+    }
+    S.stage = 0;
+    return -1;
 }
 
 // GuestTreeMachina.unprunedIsOK (:124-169) on the attached tree. Returns sampled-leaf count through *sampled.

@@ -32,7 +32,8 @@ elif cfg in ("c5ln", "c5gamma"):
     app, args = "BranchRelaxer", ["-s", "20260101", tree] + (["IIDLogNormal", "0", "0.25"] if cfg == "c5ln" else ["IIDGamma", "2", "0.5"])
 else:
     host = open(os.path.join(ROOT, "tests", "golden", "species100.pruned.tree")).read()
-    app, args = "GuestTreeGen", ["-s", "20260101", host, "0.3", "0.3", "0.3", "bench"]
+    extra = sys.argv[3:]          # e.g. -db none, -rt 0.0
+    app, args = "GuestTreeGen", ["-s", "20260101"] + extra + [host, "0.3", "0.3", "0.3", "bench"]
 for rep in range(2):
     b = ctx.run(app, args, n=n, rng=sg.RNG_PHILOX, offset=rep * n, keep_on_device=True)
     t = b.timings(); s = b.summary()
