@@ -106,7 +106,7 @@ __device__ int sample_arc(RNG& rng, const SimParams& P, const DevHost& H, int ep
 
 // RBTreeEpochDiscretiser.sampleRoot
 template <class RNG>
-__device__ int sample_root(RNG& rng, const SimParams& P, const DevHost& H) {
+__device__ __noinline__ int sample_root(RNG& rng, const SimParams& P, const DevHost& H) {
     const double tip = H.ep_up[H.nE - 1];
     DD total{0.0, 0.0};
     for (int i = 0; i < H.nV; ++i) total = dd_add_d(total, XMUL(P.gene_birth, pow_e(XMUL(-P.gene_birth, XSUB(tip, H.vtime[i])))));
@@ -185,7 +185,7 @@ __device__ __forceinline__ double arc_weight(const SimParams& P, const DevHost& 
 // overwrite the previous key); the double-double sums are formed by a warp scan instead of a serial loop, which moves them by
 // ~1e-32 relative — the same order as the double-double stand-in for BigDecimal itself (numerics).
 template <class RNG>
-__device__ int coop_sample_arc(int leader, RNG& rng, const SimParams& P, const DevHost& H, int epoch, int donor, double t, const int32_t* marks, int mark_gen, bool include = true) {
+__device__ __noinline__ int coop_sample_arc(int leader, RNG& rng, const SimParams& P, const DevHost& H, int epoch, int donor, double t, const int32_t* marks, int mark_gen, bool include = true) {
     const int lane = threadIdx.x & 31;
     const int a0 = H.ep_off[epoch], a1 = H.ep_off[epoch + 1];
     const int tag = H.host_tag[donor];
@@ -263,7 +263,7 @@ __device__ __forceinline__ bool preorder_before(const Node* N, int a, int b) {
     return N[N[x].parent].left == x;
 }
 // findVertex by the whole warp: every lane tests a slice of the node pool, the pre-order-first attached match wins.
-static __device__ int coop_find_victim(const Node* N, int n, int root, int to, double t) {
+static __device__ __noinline__ int coop_find_victim(const Node* N, int n, int root, int to, double t) {
     const int lane = threadIdx.x & 31;
     int best = -1;
     for (int base = 0; base < n; base += 32) {
@@ -340,25 +340,28 @@ __device__ void coop_resolve_transfers(SimState& S, RNG& rng, const SimParams& P
 template <class RNG>
 __device__ int sim_step(SimState& S, RNG& rng, const SimParams& P, const DevHost& H, const MathTables& T, SimWork& W) {
     if (S.stage == 0) {
-        if (S.qh == S.qt) {
-            if (S.np == 0) {
-                if (W.nodes[S.root].bl <= 1.0e-32) W.nodes[S.root].bl = 0.0;
-                return REP_OK;
+        // fetch lineages until one needs children (ended lineages are skipped in the same step), then create its first child
+        for (;;) {
+            if (S.qh == S.qt) {
+                if (S.np == 0) {
+                    if (W.nodes[S.root].bl <= 1.0e-32) W.nodes[S.root].bl = 0.0;
+                    return REP_OK;
+                }
+                int best = 0;      // release the oldest parked replacing transfer (largest abstime)
+                for (int i = 1; i < S.np; ++i) if (W.nodes[W.pend[i]].abstime > W.nodes[W.pend[best]].abstime) best = i;
+                W.queue[S.qt++] = W.pend[best];
+                W.pend[best] = W.pend[--S.np];
             }
-            int best = 0;      // release the oldest parked replacing transfer (largest abstime)
-            for (int i = 1; i < S.np; ++i) if (W.nodes[W.pend[i]].abstime > W.nodes[W.pend[best]].abstime) best = i;
-            W.queue[S.qt++] = W.pend[best];
-            W.pend[best] = W.pend[--S.np];
+            S.li = W.queue[S.qh++];
+            const Node& ln = W.nodes[S.li];
+            S.ev = ln.event;
+            if (S.ev == EV_LOSS || S.ev == EV_REPLACING_LOSS || S.ev == EV_LEAF || S.ev == EV_UNSAMPLED_LEAF) continue;     // lineage ends
+            S.sigma = ln.sigma; S.t = ln.abstime; S.ep = ln.epoch;
+            if (S.ev == EV_SPECIATION) S.X = H.left[S.sigma];
+            else { S.X = S.sigma; if (S.ev != EV_DUPLICATION) S.stay_left = rng.next_double() < 0.5; }
+            S.stage = 1;
+            break;
         }
-        S.li = W.queue[S.qh++];
-        const Node& ln = W.nodes[S.li];
-        S.ev = ln.event;
-        if (S.ev == EV_LOSS || S.ev == EV_REPLACING_LOSS || S.ev == EV_LEAF || S.ev == EV_UNSAMPLED_LEAF) return -1;     // lineage ends
-        S.sigma = ln.sigma; S.t = ln.abstime; S.ep = ln.epoch;
-        if (S.ev == EV_SPECIATION) S.X = H.left[S.sigma];
-        else { S.X = S.sigma; if (S.ev != EV_DUPLICATION) S.stay_left = rng.next_double() < 0.5; }
-        S.stage = 1;
-        return -1;
     }
     if (S.stage == 2 && S.xfer_pending) return -1;          // waits for coop_resolve_transfers
     // ---- the single vertex-creation site
@@ -413,7 +416,7 @@ __device__ int sim_step(SimState& S, RNG& rng, const SimParams& P, const DevHost
 }
 
 // GuestTreeMachina.unprunedIsOK (:124-169) on the attached tree. Returns sampled-leaf count through *sampled.
-static __device__ bool attempt_ok(const SimParams& P, const DevHost& H, const SimWork& W, int root, int exact, int* sampled_out) {
+static __device__ __noinline__ bool attempt_ok(const SimParams& P, const DevHost& H, const SimWork& W, int root, int exact, int* sampled_out) {
     int sampled = 0;
     const bool per_leaf = W.leaf_cnt != nullptr;
     if (per_leaf) for (int i = 0; i < H.nLeaves; ++i) W.leaf_cnt[i] = 0;
