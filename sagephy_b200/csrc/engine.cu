@@ -311,10 +311,23 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     for (const HostModel& g : cfg.genes) { gene_dev.emplace_back(new HostOnDevice()); gene_dev.back()->upload(g); gene_views.push_back(gene_dev.back()->view); max_gene_nv = std::max(max_gene_nv, g.nV); }
     max_gene_nv = std::max(max_gene_nv, cfg.host.nV);
     DevBuf<DevHost> d_genes; d_genes.upload(gene_views);
-    std::vector<double> fl_lo, fl_up; std::vector<int32_t> fl_tag, fl_start;
-    for (const HostModel& g : cfg.genes) { fl_start.push_back((int32_t)fl_lo.size()); for (int v = 0; v < g.nV; ++v) { fl_lo.push_back(g.vtime[v]); fl_up.push_back(g.ep_up[g.v2e[v]]); fl_tag.push_back(g.host_tag[v]); } }
-    fl_start.push_back((int32_t)fl_lo.size());
-    DevBuf<double> d_fl_lo, d_fl_up; DevBuf<int32_t> d_fl_tag, d_fl_start; d_fl_lo.upload(fl_lo); d_fl_up.upload(fl_up); d_fl_tag.upload(fl_tag); d_fl_start.upload(fl_start);
+    // Inter-gene candidate index (DomainTreeInHostTreeCreator.sampleInterGeneArc :1004-1033 scans every vertex of every other gene
+    // tree for "vertex time < t < upper time of the epoch directly above the vertex"). That interval is the vertex's first epoch,
+    // and the epochs of a gene tree partition time, so the candidates of gene g at time t are the vertices filed under the one
+    // epoch that contains t: per gene, epoch -> vertex ids in ascending order (the reference's scan order).
+    std::vector<int32_t> ev_base, ev_off, ev_list;
+    for (const HostModel& g : cfg.genes) {
+        ev_base.push_back((int32_t)ev_off.size());
+        std::vector<std::vector<int32_t>> by_epoch((size_t)g.nE);
+        for (int v = 0; v < g.nV; ++v) {
+            const int e = g.v2e[v];
+            if (e < 0 || e >= g.nE || g.vtime[v] != g.ep_lo[e]) throw SgpError("internal: gene tree vertex does not start its epoch");
+            by_epoch[(size_t)e].push_back(v);
+        }
+        for (int e = 0; e < g.nE; ++e) { ev_off.push_back((int32_t)ev_list.size()); ev_list.insert(ev_list.end(), by_epoch[(size_t)e].begin(), by_epoch[(size_t)e].end()); }
+        ev_off.push_back((int32_t)ev_list.size());
+    }
+    DevBuf<int32_t> d_ev_base, d_ev_off, d_ev_list; d_ev_base.upload(ev_base); d_ev_off.upload(ev_off); d_ev_list.upload(ev_list);
     DevBuf<int32_t> scratch_used;
     DevBuf<int32_t> d_sizes; { std::vector<int32_t> s(cfg.sizes.begin(), cfg.sizes.end()); d_sizes.upload(s); }
     DevBuf<RepInfo> info; info.alloc((size_t)n);
@@ -358,7 +371,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             a.work_counter = counter.p; a.scratch_nodes = s_nodes.p; a.scratch_queue = s_queue.p; a.scratch_pend = s_pend.p; a.cap = cap;
             a.scratch_marks = marks.p; a.scratch_leafcnt = leafcnt.p; a.mt_state = mt_state.p; a.sizes = d_sizes.p; a.per_leaf_check = per_leaf;
             a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
-            a.scratch_used = scratch_used.p; a.fl_lo = d_fl_lo.p; a.fl_up = d_fl_up.p; a.fl_tag = d_fl_tag.p; a.fl_start = d_fl_start.p;
+            a.scratch_used = scratch_used.p; a.ev_base = d_ev_base.p; a.ev_off = d_ev_off.p; a.ev_list = d_ev_list.p;
             CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
             int blocks = (int)(workers / 128);
             launch_find_general(replay, domain, a, blocks, st);
@@ -413,7 +426,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         BuildArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.info = info.p; a.node_off = node_off.p;
         a.nodes = nodes.p; a.aux = aux.p; a.aux_stride = aux_stride; a.scratch_marks = marks.p; a.scratch_leafcnt = nullptr; a.mt_state = mt_state.p;
         a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
-        a.scratch_used = scratch_used.p; a.fl_lo = d_fl_lo.p; a.fl_up = d_fl_up.p; a.fl_tag = d_fl_tag.p; a.fl_start = d_fl_start.p;
+        a.scratch_used = scratch_used.p; a.ev_base = d_ev_base.p; a.ev_off = d_ev_off.p; a.ev_list = d_ev_list.p;
         launch_build_general(replay, domain, a, (int)(threads / 128), st);
         ++tm.launches;
     }

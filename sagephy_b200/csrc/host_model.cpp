@@ -202,15 +202,28 @@ void HostModel::build(const FlatTree& t, const std::string* name, const double* 
     vtime.assign(nV, 0); for (int v = 0; v < nV; ++v) vtime[v] = ep_lo[v2e[v]];
 
     if (need_lca) {
-        std::vector<int> depth(nV, 0);
-        for (int i = 0; i < nV; ++i) { int v = t.bfs[i]; depth[v] = parent[v] < 0 ? 0 : depth[parent[v]] + 1; }
+        // time of the last common ancestor of every vertex pair, O(V^2): in pre-order a subtree is a contiguous range, and the
+        // LCA of a vertex of the left subtree of v with a vertex of its right subtree is v (as is the LCA of v with any descendant)
+        std::vector<int> ord; ord.reserve((size_t)nV); std::vector<int> tin(nV, 0), tout(nV, 0);
+        {
+            std::vector<int> st{root};
+            while (!st.empty()) {
+                const int v = st.back(); st.pop_back();
+                tin[v] = (int)ord.size(); ord.push_back(v);
+                if (left[v] >= 0) { st.push_back(right[v]); st.push_back(left[v]); }
+            }
+            for (int i = nV - 1; i >= 0; --i) { const int v = ord[(size_t)i]; tout[v] = left[v] >= 0 ? tout[right[v]] : tin[v] + 1; }
+        }
         lca_time.assign((size_t)nV * nV, 0.0);
-        for (int x = 0; x < nV; ++x) for (int y = x; y < nV; ++y) {
-            int a = x, b = y;
-            while (depth[a] > depth[b]) a = parent[a];
-            while (depth[b] > depth[a]) b = parent[b];
-            while (a != b) { a = parent[a]; b = parent[b]; }
-            lca_time[(size_t)x * nV + y] = lca_time[(size_t)y * nV + x] = vtime[a];
+        for (int v = 0; v < nV; ++v) {
+            const double tv = vtime[v];
+            for (int i = tin[v]; i < tout[v]; ++i) { const int x = ord[(size_t)i]; lca_time[(size_t)v * nV + x] = lca_time[(size_t)x * nV + v] = tv; }
+            if (left[v] < 0) continue;
+            const int l = left[v], r = right[v];
+            for (int i = tin[l]; i < tout[l]; ++i) {
+                const int x = ord[(size_t)i]; double* row = &lca_time[(size_t)x * nV];
+                for (int j = tin[r]; j < tout[r]; ++j) { const int y = ord[(size_t)j]; row[y] = tv; lca_time[(size_t)y * nV + x] = tv; }
+            }
         }
     }
 

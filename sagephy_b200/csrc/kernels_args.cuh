@@ -33,7 +33,7 @@ struct FindArgs {
     // DomainTreeGen: forest of gene trees (H above is then the species tree)
     const DevHost* genes; int n_genes; int max_gene_nv; int all_genes; double inter_gene, inter_species;
     int32_t* scratch_used;       // n_genes ints per worker
-    const double* fl_lo; const double* fl_up; const int32_t* fl_tag; const int32_t* fl_start;    // flat inter-gene candidate table
+    const int32_t* ev_base; const int32_t* ev_off; const int32_t* ev_list;    // inter-gene candidate index: vertices of gene g whose first epoch is e = ev_list[ev_off[ev_base[g] + e] .. ev_off[ev_base[g] + e + 1])
 };
 
 struct BuildArgs {
@@ -49,7 +49,7 @@ struct BuildArgs {
     uint32_t* mt_state;
     const DevHost* genes; int n_genes; int max_gene_nv; int all_genes; double inter_gene, inter_species;
     int32_t* scratch_used;
-    const double* fl_lo; const double* fl_up; const int32_t* fl_tag; const int32_t* fl_start;
+    const int32_t* ev_base; const int32_t* ev_off; const int32_t* ev_list;
 };
 
 struct BdArgs {

@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
     W.leaf_cnt = a.per_leaf_check ? a.scratch_leafcnt + (size_t)worker * cnt_n : nullptr;
     W.mark_gen = 0;
     for (int i = 0; i < mark_n; ++i) W.marks[i] = 0;
-    DomainEnv E{a.genes, a.n_genes, a.inter_gene, a.inter_species, DOMAIN ? a.scratch_used + (size_t)worker * a.n_genes : nullptr, a.fl_lo, a.fl_up, a.fl_tag, a.fl_start};
+    DomainEnv E{a.genes, a.n_genes, a.inter_gene, a.inter_species, DOMAIN ? a.scratch_used + (size_t)worker * a.n_genes : nullptr, a.ev_base, a.ev_off, a.ev_list};
     MtStream mt; PhiloxStream ph;
     if (REPLAY) { mt.mt = a.mt_state + (size_t)(worker >> 5) * 624 * 32 + (worker & 31); mt.stride = 32; }
     if constexpr (!DOMAIN) {
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(128) k_build_general(BuildArgs a) {
     const int mark_n = DOMAIN ? a.max_gene_nv : a.H.nV;
     W.marks = a.scratch_marks + (size_t)worker * mark_n; W.leaf_cnt = nullptr; W.mark_gen = 0;
     for (int i = 0; i < mark_n; ++i) W.marks[i] = 0;
-    DomainEnv E{a.genes, a.n_genes, a.inter_gene, a.inter_species, DOMAIN ? a.scratch_used + (size_t)worker * a.n_genes : nullptr, a.fl_lo, a.fl_up, a.fl_tag, a.fl_start};
+    DomainEnv E{a.genes, a.n_genes, a.inter_gene, a.inter_species, DOMAIN ? a.scratch_used + (size_t)worker * a.n_genes : nullptr, a.ev_base, a.ev_off, a.ev_list};
     int n = 0, root = -1, st = REP_OK;
     const long long gid = a.rep_base + r;
     MtStream mt; PhiloxStream ph;

@@ -14,9 +14,8 @@ namespace sgp {
 struct DomainEnv {
     const DevHost* genes; int n_genes; double inter_gene, inter_species;
     int32_t* used;           // vertices created per gene tree in the current attempt
-    // flat candidate table over all (gene tree, vertex) pairs in the reference's scan order (gene-major, vertex id ascending):
-    // lower time of the arc's vertex, upper time of the epoch directly above it, HOST tag; gene g owns [fl_start[g], fl_start[g+1])
-    const double* fl_lo; const double* fl_up; const int32_t* fl_tag; const int32_t* fl_start;
+    // inter-gene candidate index: the vertices of gene g whose first epoch is e, ids ascending (engine.cu builds it)
+    const int32_t* ev_base; const int32_t* ev_off; const int32_t* ev_list;
 };
 
 template <class RNG>
@@ -62,12 +61,16 @@ __device__ int sample_inter_gene(RNG& rng, const DomainEnv& E, int g_from, int s
         if (pass == 1) { if (k < 1) { *g_to = -1; return -5; } pick = rng.next_int(k); }
         for (int g = 0; g < E.n_genes; ++g) {
             if (g == g_from) continue;
-            const int j0 = E.fl_start[g], j1 = E.fl_start[g + 1];
+            const DevHost& G = E.genes[g];
+            // the epoch of gene g that contains t: first epoch whose upper time exceeds t (epochs ascend and are contiguous)
+            int lo = 0, hi = G.nE;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (G.ep_up[mid] > t) hi = mid; else lo = mid + 1; }
+            if (lo >= G.nE || !(G.ep_lo[lo] < t)) continue;
+            const int j0 = E.ev_off[E.ev_base[g] + lo], j1 = E.ev_off[E.ev_base[g] + lo + 1];
             for (int j = j0; j < j1; ++j) {
-                if (!(E.fl_lo[j] < t && E.fl_up[j] > t)) continue;
-                const int i = j - j0;
+                const int i = E.ev_list[j];
                 if (i == sigma || (marks && marks[i] == gen)) continue;
-                if ((E.fl_tag[j] == tag) != intra_species) continue;
+                if ((G.host_tag[i] == tag) != intra_species) continue;
                 if (pass == 0) ++k;
                 else { if (pick == 0) { *g_to = g; return i; } --pick; }
             }
