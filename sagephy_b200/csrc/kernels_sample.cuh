@@ -1,10 +1,31 @@
-// Sampling kernels (K1): "find" passes decide which attempt of each replicate is accepted, "build" passes regenerate
+// Sampling kernels (K1) of the general engine: "find" decides which attempt of each replicate is accepted, "build" regenerates
 // that attempt into the exactly-sized node arena.
+//
+// A warp simulates 32 replicates, one per lane, in ONE flat loop: every trip, lanes without work claim a replicate (find) and
+// every lane with an attempt in progress takes one step of it (sim_step / domain_step: exactly one vertex is created per step),
+// so the lanes meet again at the top of each trip and share the expensive Java-exact vertex draw. The pieces that are linear in
+// the host epoch or the guest tree (recipient draws, victim searches) are served by the whole warp (coop_resolve_*). All 32
+// lanes stay in the loop until the warp has nothing left to do, because those pieces need them.
 #pragma once
+#include <type_traits>
 #include "sim_domain.cuh"
 
 namespace sgp {
 
+template <bool DOMAIN> using EngineState = typename std::conditional<DOMAIN, DomainState, SimState>::type;
+
+template <bool DOMAIN, class RNG, class ARGS>
+__device__ __forceinline__ void engine_begin(EngineState<DOMAIN>& S, RNG& rng, const ARGS& a, const DomainEnv& E) {
+    if constexpr (DOMAIN) domain_begin(S, rng, a.P, E); else sim_begin(S, rng, a.P, a.H);
+}
+template <bool DOMAIN, class RNG, class ARGS>
+__device__ __forceinline__ void engine_resolve(EngineState<DOMAIN>& S, RNG& rng, const ARGS& a, const DomainEnv& E, SimWork& W) {
+    if constexpr (DOMAIN) coop_resolve_domain(S, rng, a.P, E, W); else coop_resolve_transfers(S, rng, a.P, a.H, W);
+}
+template <bool DOMAIN, class RNG, class ARGS>
+__device__ __forceinline__ int engine_step(EngineState<DOMAIN>& S, RNG& rng, const ARGS& a, const DomainEnv& E, SimWork& W) {
+    if constexpr (DOMAIN) return domain_step(S, rng, a.P, E, a.T, W); else return sim_step(S, rng, a.P, a.H, a.T, W);
+}
 
 template <bool REPLAY, bool DOMAIN>
 __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
@@ -20,92 +41,52 @@ __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
     DomainEnv E{a.genes, a.n_genes, a.inter_gene, a.inter_species, DOMAIN ? a.scratch_used + (size_t)worker * a.n_genes : nullptr, a.ev_base, a.ev_off, a.ev_list};
     MtStream mt; PhiloxStream ph;
     if (REPLAY) { mt.mt = a.mt_state + (size_t)(worker >> 5) * 624 * 32 + (worker & 31); mt.stride = 32; }
-    if constexpr (!DOMAIN) {
-        // Flat loop: every trip, lanes without a replicate claim one, transfers waiting for a recipient are served by the whole
-        // warp, and every lane with an attempt in progress takes one step of it. All 32 lanes stay in the loop until the batch
-        // is exhausted (the cooperative pieces need them).
-        SimState S; S.stage = -1; S.xfer_pending = false;
-        bool have = false, exhausted = false;
-        long long r = 0; RepInfo inf; int attempts = 0; uint64_t verts = 0, pos = 0;
-        for (;;) {
-            if (!have && !exhausted) {
-                const long long slot = (long long)atomicAdd(a.work_counter, 1ULL);
-                if (slot >= a.n) exhausted = true;
-                else {
-                    r = a.rep_ids ? a.rep_ids[slot] : slot;
-                    const long long gid = a.rep_base + r;
-                    memset(&inf, 0, sizeof(inf));
-                    inf.status = REP_PENDING; inf.exact = -1; inf.root = -1; inf.p_root = -1;
-                    if (REPLAY) { uint32_t key[4]; seed_words_i64((long long)a.seed + gid, key); mt.seed(key); }
-                    else ph.init(a.seed, (uint64_t)gid, 0xFFFFFFFFu);
-                    if (a.P.n_sizes > 0) inf.exact = a.sizes[REPLAY ? mt.next_int(a.P.n_sizes) : ph.next_int(a.P.n_sizes)];
-                    attempts = 0; verts = 0; have = true; S.stage = -1;
-                }
+    EngineState<DOMAIN> S; S.stage = -1;
+    bool have = false, exhausted = false;
+    long long r = 0; RepInfo inf; int attempts = 0; uint64_t verts = 0, pos = 0;
+    for (;;) {
+        if (!have && !exhausted) {
+            const long long slot = (long long)atomicAdd(a.work_counter, 1ULL);
+            if (slot >= a.n) exhausted = true;
+            else {
+                r = a.rep_ids ? a.rep_ids[slot] : slot;
+                const long long gid = a.rep_base + r;
+                memset(&inf, 0, sizeof(inf));
+                inf.status = REP_PENDING; inf.exact = -1; inf.root = -1; inf.p_root = -1;
+                if (REPLAY) { uint32_t key[4]; seed_words_i64((long long)a.seed + gid, key); mt.seed(key); }
+                else ph.init(a.seed, (uint64_t)gid, 0xFFFFFFFFu);
+                if (a.P.n_sizes > 0) inf.exact = a.sizes[REPLAY ? mt.next_int(a.P.n_sizes) : ph.next_int(a.P.n_sizes)];
+                attempts = 0; verts = 0; have = true; S.stage = -1;
             }
-            if (have && S.stage < 0) {          // start the next attempt of this replicate (GuestTreeMachina.java:81-98)
-                if (attempts > a.P.max_attempts) { inf.status = REP_MAX_ATTEMPTS; inf.attempts = attempts; inf.vertices_sampled = verts; a.info[r] = inf; have = false; }
+        }
+        if (have && S.stage < 0) {          // start the next attempt of this replicate (GuestTreeMachina.java:81-98)
+            if (attempts > a.P.max_attempts) { inf.status = REP_MAX_ATTEMPTS; inf.attempts = attempts; inf.vertices_sampled = verts; a.info[r] = inf; have = false; }
+            else if (REPLAY) { pos = mt.position(); engine_begin<DOMAIN>(S, mt, a, E); }
+            else { ph.begin_attempt((uint32_t)attempts); engine_begin<DOMAIN>(S, ph, a, E); }
+        }
+        if (!__ballot_sync(0xffffffffu, have || !exhausted)) break;
+        if (REPLAY) engine_resolve<DOMAIN>(S, mt, a, E, W); else engine_resolve<DOMAIN>(S, ph, a, E, W);
+        if (have && S.stage >= 0) {
+            const int st = REPLAY ? engine_step<DOMAIN>(S, mt, a, E, W) : engine_step<DOMAIN>(S, ph, a, E, W);
+            if (st >= 0) {
+                verts += (uint64_t)S.n;
+                const int n = S.n, root = S.root;
+                S.stage = -1;
+                if (st != REP_OK) { inf.status = st; inf.attempts = attempts; inf.vertices_sampled = verts; a.info[r] = inf; have = false; }
                 else {
-                    if (REPLAY) { pos = mt.position(); sim_begin(S, mt, a.P, a.H); } else { ph.begin_attempt((uint32_t)attempts); sim_begin(S, ph, a.P, a.H); }
-                }
-            }
-            if (!__ballot_sync(0xffffffffu, have || !exhausted)) break;
-            if (REPLAY) coop_resolve_transfers(S, mt, a.P, a.H, W); else coop_resolve_transfers(S, ph, a.P, a.H, W);
-            if (have && S.stage >= 0) {
-                const int st = REPLAY ? sim_step(S, mt, a.P, a.H, a.T, W) : sim_step(S, ph, a.P, a.H, a.T, W);
-                if (st >= 0) {
-                    verts += (uint64_t)S.n;
-                    const int n = S.n, root = S.root;
-                    S.stage = -1;
-                    if (st != REP_OK) { inf.status = st; inf.attempts = attempts; inf.vertices_sampled = verts; a.info[r] = inf; have = false; }
-                    else {
-                        ++attempts;
-                        int sampled = 0;
-                        if (attempt_ok(a.P, a.H, W, root, inf.exact, &sampled)) {
-                            inf.status = REP_OK; inf.n_pool = n; inf.sampled_leaves = sampled;
-                            if (REPLAY) { inf.acc_attempt = (uint32_t)pos; inf.acc_hi = (uint32_t)(pos >> 32); } else { inf.acc_attempt = (uint32_t)(attempts - 1); inf.acc_hi = 0; }
-                            ++attempts;     // GuestTreeMachina.java:107
-                            inf.attempts = attempts; inf.vertices_sampled = verts; a.info[r] = inf; have = false;
-                        }
+                    ++attempts;
+                    int sampled = 0;
+                    const bool ok = DOMAIN ? attempt_ok_domain(a.P, a.H, E, W, root, inf.exact, a.max_gene_nv, a.per_leaf_check != 0, a.all_genes != 0, &sampled)
+                                           : attempt_ok(a.P, a.H, W, root, inf.exact, &sampled);
+                    if (ok) {
+                        inf.status = REP_OK; inf.n_pool = n; inf.sampled_leaves = sampled;
+                        if (REPLAY) { inf.acc_attempt = (uint32_t)pos; inf.acc_hi = (uint32_t)(pos >> 32); } else { inf.acc_attempt = (uint32_t)(attempts - 1); inf.acc_hi = 0; }
+                        ++attempts;     // GuestTreeMachina.java:107
+                        inf.attempts = attempts; inf.vertices_sampled = verts; a.info[r] = inf; have = false;
                     }
                 }
             }
         }
-        return;
-    }
-    for (;;) {
-        long long slot = (long long)atomicAdd(a.work_counter, 1ULL);
-        if (slot >= a.n) break;
-        const long long r = a.rep_ids ? a.rep_ids[slot] : slot;
-        const long long gid = a.rep_base + r;
-        RepInfo inf; memset(&inf, 0, sizeof(inf));
-        inf.status = REP_PENDING; inf.exact = -1; inf.root = -1; inf.p_root = -1;
-        if (REPLAY) { uint32_t key[4]; seed_words_i64((long long)a.seed + gid, key); mt.seed(key); }
-        else ph.init(a.seed, (uint64_t)gid, 0xFFFFFFFFu);
-        if (a.P.n_sizes > 0) inf.exact = a.sizes[REPLAY ? mt.next_int(a.P.n_sizes) : ph.next_int(a.P.n_sizes)];
-        int attempts = 0; uint64_t verts = 0;
-        for (;;) {
-            if (attempts > a.P.max_attempts) { inf.status = REP_MAX_ATTEMPTS; break; }
-            uint64_t pos = 0;
-            if (REPLAY) pos = mt.position(); else ph.begin_attempt((uint32_t)attempts);
-            int n = 0, root = -1;
-            int st;
-            if (DOMAIN) st = REPLAY ? simulate_attempt_domain(mt, a.P, E, a.T, W, n, root) : simulate_attempt_domain(ph, a.P, E, a.T, W, n, root);
-            else st = REP_MODEL_ERROR;      // not reached: the non-domain engine is the cooperative loop above
-            verts += (uint64_t)n;
-            if (st != REP_OK) { inf.status = st; break; }
-            ++attempts;
-            int sampled = 0;
-            const bool ok = DOMAIN ? attempt_ok_domain(a.P, a.H, E, W, root, inf.exact, a.max_gene_nv, a.per_leaf_check != 0, a.all_genes != 0, &sampled)
-                                   : attempt_ok(a.P, a.H, W, root, inf.exact, &sampled);
-            if (ok) {
-                inf.status = REP_OK; inf.n_pool = n; inf.sampled_leaves = sampled;
-                if (REPLAY) { inf.acc_attempt = (uint32_t)pos; inf.acc_hi = (uint32_t)(pos >> 32); } else { inf.acc_attempt = (uint32_t)(attempts - 1); inf.acc_hi = 0; }
-                ++attempts;     // GuestTreeMachina.java:107
-                break;
-            }
-        }
-        inf.attempts = attempts; inf.vertices_sampled = verts;
-        a.info[r] = inf;
     }
 }
 
@@ -116,7 +97,6 @@ __global__ void __launch_bounds__(128) k_build_general(BuildArgs a) {
     const int worker = blockIdx.x * blockDim.x + threadIdx.x;
     // all lanes of a warp stay: lanes without a tree to build still help with the cooperative pieces
     const bool active = r < a.n && a.info[r < a.n ? r : 0].status == REP_OK;
-    if (DOMAIN && !active) return;
     RepInfo& inf = a.info[active ? r : 0];
     const long long off = active ? a.node_off[r] : 0;
     SimWork W;
@@ -133,21 +113,17 @@ __global__ void __launch_bounds__(128) k_build_general(BuildArgs a) {
         mt.mt = a.mt_state + (size_t)(worker >> 5) * 624 * 32 + (worker & 31); mt.stride = 32;
         if (active) { uint32_t key[4]; seed_words_i64((long long)a.seed + gid, key); mt.seed(key); mt.skip(((uint64_t)inf.acc_hi << 32) | inf.acc_attempt); }
     } else if (active) ph.init(a.seed, (uint64_t)gid, inf.acc_attempt);
-    if constexpr (DOMAIN) {
-        st = REPLAY ? simulate_attempt_domain(mt, a.P, E, a.T, W, n, root) : simulate_attempt_domain(ph, a.P, E, a.T, W, n, root);
-    } else {
-        SimState S; S.stage = -1; S.xfer_pending = false;
-        if (active) { if (REPLAY) sim_begin(S, mt, a.P, a.H); else sim_begin(S, ph, a.P, a.H); }
-        for (;;) {
-            if (!__ballot_sync(0xffffffffu, S.stage >= 0)) break;
-            if (REPLAY) coop_resolve_transfers(S, mt, a.P, a.H, W); else coop_resolve_transfers(S, ph, a.P, a.H, W);
-            if (S.stage >= 0) {
-                const int rc = REPLAY ? sim_step(S, mt, a.P, a.H, a.T, W) : sim_step(S, ph, a.P, a.H, a.T, W);
-                if (rc >= 0) { st = rc; n = S.n; root = S.root; S.stage = -1; }
-            }
+    EngineState<DOMAIN> S; S.stage = -1;
+    if (active) { if (REPLAY) engine_begin<DOMAIN>(S, mt, a, E); else engine_begin<DOMAIN>(S, ph, a, E); }
+    for (;;) {
+        if (!__ballot_sync(0xffffffffu, S.stage >= 0)) break;
+        if (REPLAY) engine_resolve<DOMAIN>(S, mt, a, E, W); else engine_resolve<DOMAIN>(S, ph, a, E, W);
+        if (S.stage >= 0) {
+            const int rc = REPLAY ? engine_step<DOMAIN>(S, mt, a, E, W) : engine_step<DOMAIN>(S, ph, a, E, W);
+            if (rc >= 0) { st = rc; n = S.n; root = S.root; S.stage = -1; }
         }
-        if (!active) return;
     }
+    if (!active) return;
     if (st != REP_OK || n != inf.n_pool) { inf.status = REP_MODEL_ERROR; return; }
     inf.root = root;
 }

@@ -49,171 +49,258 @@ __device__ __forceinline__ VertexDraw draw_vertex_domain(RNG& rng, const SimPara
     return d;
 }
 
-// sampleInterGeneArc: uniform over the arcs (vertex ids) of the OTHER gene trees that are "alive" at time t in the reference's
-// sense (vertex time < t < upper time of the epoch directly above the vertex) with the requested species relation; ids are
-// compared / marked across trees exactly as the reference does. Returns -5 when there is no candidate.
+// ---- warp-cooperative engine (same scheme as sim.cuh: one step per lane per trip, linear-time pieces served by the warp) ----------
+// sampleInterGeneArc by the whole warp: lane l looks after genes l, l + 32, ... (epoch lookup + its short candidate list), a warp
+// scan of the per-lane counts turns the leader's draw into (lane, rank within the lane's candidates).
 template <class RNG>
-__device__ int sample_inter_gene(RNG& rng, const DomainEnv& E, int g_from, int sigma, double t, bool intra_species, const int32_t* marks, int gen, int* g_to) {
+__device__ __noinline__ int coop_sample_inter_gene(int leader, RNG& rng, const DomainEnv& E, int g_from, int sigma, double t, bool intra_species, const int32_t* marks, int gen, int* g_to) {
+    const int lane = threadIdx.x & 31;
     const int tag = E.genes[g_from].host_tag[sigma];
-    int k = 0;
+    int pick = 0, my_first = 0;
     for (int pass = 0; pass < 2; ++pass) {
-        int pick = 0;
-        if (pass == 1) { if (k < 1) { *g_to = -1; return -5; } pick = rng.next_int(k); }
-        for (int g = 0; g < E.n_genes; ++g) {
-            if (g == g_from) continue;
-            const DevHost& G = E.genes[g];
-            // the epoch of gene g that contains t: first epoch whose upper time exceeds t (epochs ascend and are contiguous)
-            int lo = 0, hi = G.nE;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (G.ep_up[mid] > t) hi = mid; else lo = mid + 1; }
-            if (lo >= G.nE || !(G.ep_lo[lo] < t)) continue;
-            const int j0 = E.ev_off[E.ev_base[g] + lo], j1 = E.ev_off[E.ev_base[g] + lo + 1];
-            for (int j = j0; j < j1; ++j) {
-                const int i = E.ev_list[j];
-                if (i == sigma || (marks && marks[i] == gen)) continue;
-                if ((G.host_tag[i] == tag) != intra_species) continue;
-                if (pass == 0) ++k;
-                else { if (pick == 0) { *g_to = g; return i; } --pick; }
+        int k = 0;          // pass 0: candidates in this lane's genes; pass 1: running rank
+        for (int g0 = 0; g0 < E.n_genes; g0 += 32) {
+            // gene-major order over ALL lanes: within a block of 32 genes, lane order == gene order; blocks are handled one after
+            // the other, so ranks are (block, lane, position) lexicographic == the reference's (gene, vertex id) order
+            const int g = g0 + lane;
+            int cnt = 0, j0 = 0, j1 = 0; const DevHost* G = nullptr;
+            if (g < E.n_genes && g != g_from) {
+                G = &E.genes[g];
+                int lo = 0, hi = G->nE;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (G->ep_up[mid] > t) hi = mid; else lo = mid + 1; }
+                if (lo < G->nE && G->ep_lo[lo] < t) { j0 = E.ev_off[E.ev_base[g] + lo]; j1 = E.ev_off[E.ev_base[g] + lo + 1]; }
+                for (int j = j0; j < j1; ++j) {
+                    const int i = E.ev_list[j];
+                    if (i == sigma || (marks && marks[i] == gen)) continue;
+                    if ((G->host_tag[i] == tag) != intra_species) continue;
+                    ++cnt;
+                }
             }
+            int incl = cnt;
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const int block_total = __shfl_sync(0xffffffffu, incl, 31);
+            if (pass == 1) {
+                const int before = k + incl - cnt;          // candidates ranked before this lane's first one
+                const bool mine = cnt > 0 && pick >= before && pick < before + cnt;
+                const unsigned who = __ballot_sync(0xffffffffu, mine);
+                if (who) {
+                    const int owner = __ffs(who) - 1;
+                    int res = -5;
+                    if (lane == owner) {
+                        int left = pick - before;
+                        for (int j = j0; j < j1; ++j) {
+                            const int i = E.ev_list[j];
+                            if (i == sigma || (marks && marks[i] == gen)) continue;
+                            if ((G->host_tag[i] == tag) != intra_species) continue;
+                            if (left == 0) { res = i; break; }
+                            --left;
+                        }
+                    }
+                    *g_to = g0 + owner;
+                    return __shfl_sync(0xffffffffu, res, owner);
+                }
+            }
+            k += block_total;
+        }
+        if (pass == 0) {
+            if (k < 1) { *g_to = -1; return -5; }
+            if (lane == leader) pick = rng.next_int(k);
+            pick = __shfl_sync(0xffffffffu, pick, leader);
         }
     }
+    (void)my_first;
     *g_to = -1; return -5;
 }
 
-static __device__ int find_victim_domain(const Node* N, int root, int to, int g_to, double t) {
-    int v = root;
-    while (v >= 0) {
-        const Node& x = N[v];
-        if (x.sigma == to && x.gtree == g_to && x.abstime < t && XADD(x.abstime, x.bl) > t) return v;
-        if (x.left >= 0) { v = x.left; continue; }
-        for (;;) {
-            int p = N[v].parent;
-            if (p < 0) return -1;
-            if (N[p].left == v) { v = N[p].right; break; }
-            v = p;
+// findVertex (:948-964) by the whole warp, see coop_find_victim
+static __device__ __noinline__ int coop_find_victim_domain(const Node* N, int n, int root, int to, int g_to, double t) {
+    const int lane = threadIdx.x & 31;
+    int best = -1;
+    for (int base = 0; base < n; base += 32) {
+        const int v = base + lane;
+        bool match = false;
+        if (v < n) { const Node& x = N[v]; match = x.sigma == to && x.gtree == g_to && x.abstime < t && XADD(x.abstime, x.bl) > t; }
+        unsigned m = __ballot_sync(0xffffffffu, match);
+        while (m) {
+            const int cand = base + __ffs(m) - 1; m &= m - 1;
+            if (!node_attached(N, cand, root)) continue;
+            if (best < 0 || preorder_before(N, cand, best)) best = cand;
         }
     }
-    return -1;
+    return best;
+}
+
+struct DomainState {
+    int n, qh, qt, np;
+    int stage;                     // -1 none; 3 root, 0 fetch, 1 first of pair, 2 second of pair, 4 swap replacement
+    int li, c1, g, X, root, sigma, ep, lg, to, g_to, first_to, orig_g, victim;
+    uint8_t ev; bool stay_left, transfer, replacing, inter, include;
+    bool need_first, need_victim;  // recipient draws waiting for the warp
+    double t;
+};
+
+template <class RNG>
+__device__ __forceinline__ void domain_begin(DomainState& S, RNG& rng, const SimParams& P, const DomainEnv& E) {
+    S.n = 0; S.qh = 0; S.qt = 0; S.np = 0;
+    for (int g = 0; g < E.n_genes; ++g) E.used[g] = 0;
+    S.stage = 3; S.li = -1; S.c1 = -1; S.ev = 0; S.stay_left = true; S.transfer = false; S.replacing = false; S.inter = false; S.include = true;
+    S.need_first = false; S.need_victim = false;
+    S.g = rng.next_int(E.n_genes);          // first_guest: first draw of every attempt
+    if (!P.do_gene_birth) { S.X = E.genes[S.g].root; S.t = E.genes[S.g].ep_up[E.genes[S.g].nE - 1]; }
+    else { S.X = sample_root(rng, P, E.genes[S.g]); S.t = E.genes[S.g].ep_up[E.genes[S.g].v2e[S.X]]; }
+    S.root = -1; S.sigma = 0; S.ep = 0; S.lg = 0; S.to = -5; S.g_to = -1; S.first_to = -5; S.orig_g = -1; S.victim = -1;
 }
 
 template <class RNG>
-__device__ int simulate_attempt_domain(RNG& rng, const SimParams& P, const DomainEnv& E, const MathTables& T, SimWork& W, int& n_out, int& root_out) {
-    int n = 0, qh = 0, qt = 0, np = 0;
-    for (int g = 0; g < E.n_genes; ++g) E.used[g] = 0;
-    int stage = 3;          // 3 root, 0 fetch, 1 first of pair, 2 second of pair, 4 swap replacement
-    int li = -1, c1 = -1; uint8_t ev = 0; bool stay_left = true, transfer = false, replacing = false, inter = false, include = true;
-    int g = rng.next_int(E.n_genes);          // first_guest: first draw of every attempt
-    int X; double t;
-    if (!P.do_gene_birth) { X = E.genes[g].root; t = E.genes[g].ep_up[E.genes[g].nE - 1]; }
-    else { X = sample_root(rng, P, E.genes[g]); t = E.genes[g].ep_up[E.genes[g].v2e[X]]; }
-    int root = -1, sigma = 0, ep = 0, lg = 0, to = -5, g_to = -1, first_to = -5, orig_g = -1, victim = -1;
-    for (;;) {
-        if (stage == 0) {
-            if (qh == qt) {
-                if (np == 0) break;
-                int best = 0;
-                for (int i = 1; i < np; ++i) if (W.nodes[W.pend[i]].abstime > W.nodes[W.pend[best]].abstime) best = i;
-                W.queue[qt++] = W.pend[best];
-                W.pend[best] = W.pend[--np];
-            }
-            li = W.queue[qh++];
-            const Node& ln = W.nodes[li];
-            ev = ln.event;
-            if (ev == EV_LOSS || ev == EV_REPLACING_LOSS || ev == EV_LEAF || ev == EV_UNSAMPLED_LEAF) continue;
-            sigma = ln.sigma; t = ln.abstime; ep = ln.epoch; lg = ln.gtree; g = lg;
-            transfer = ev >= EV_AT_GG_SS;
-            if (ev == EV_CODIVERGENCE) { X = E.genes[lg].left[sigma]; stage = 1; continue; }
-            X = sigma; stage = 1;
-            if (transfer) {
-                const int code = (ev - EV_AT_GG_SS) & 3;
-                replacing = ev >= EV_RT_GG_SS; inter = (code & 2) != 0; include = (code & 1) == 0;
-                stay_left = rng.next_double() < 0.5;
-                if (!inter) { to = sample_arc(rng, P, E.genes[lg], ep, sigma, t, nullptr, 0, include); g_to = lg; }
-                else to = sample_inter_gene(rng, E, lg, sigma, t, include, nullptr, 0, &g_to);
-                first_to = to; orig_g = g_to;
-                if (to == -5) stage = 4;       // nothing to transfer to: the transfer vertex is swapped for a fresh vertex
-            }
-            continue;
+__device__ void coop_resolve_domain(DomainState& S, RNG& rng, const SimParams& P, const DomainEnv& E, SimWork& W) {
+    const int lane = threadIdx.x & 31;
+    // (A) first recipient of a transfer, drawn right after the coin (createUnprunedTree :231-242)
+    unsigned req = __ballot_sync(0xffffffffu, S.stage >= 0 && S.need_first);
+    while (req) {
+        const int leader = __ffs(req) - 1; req &= req - 1;
+        const int lg = __shfl_sync(0xffffffffu, S.lg, leader), sigma = __shfl_sync(0xffffffffu, S.sigma, leader), ep = __shfl_sync(0xffffffffu, S.ep, leader);
+        const bool inter = __shfl_sync(0xffffffffu, (int)S.inter, leader) != 0, include = __shfl_sync(0xffffffffu, (int)S.include, leader) != 0;
+        const double t = __shfl_sync(0xffffffffu, S.t, leader);
+        int to, g_to = lg;
+        if (!inter) to = coop_sample_arc(leader, rng, P, E.genes[lg], ep, sigma, t, nullptr, 0, include);
+        else to = coop_sample_inter_gene(leader, rng, E, lg, sigma, t, include, nullptr, 0, &g_to);
+        if (lane == leader) {
+            S.to = to; S.g_to = g_to; S.first_to = to; S.orig_g = g_to; S.need_first = false;
+            if (to == -5) S.stage = 4;       // nothing to transfer to: the transfer vertex is swapped for a fresh vertex
         }
-        if (stage == 2) {
-            if (ev == EV_CODIVERGENCE) { X = E.genes[lg].right[sigma]; g = lg; }
-            else if (ev == EV_DUPLICATION) { X = sigma; g = lg; }
-            else if (!replacing) { X = to; g = g_to; victim = -1; }
-            else {
-                const DevHost& G = E.genes[lg];
-                victim = find_victim_domain(W.nodes, root, to, g_to, t);
-                const int n_arcs = G.ep_off[ep + 1] - G.ep_off[ep];
-                int n_empty = 0; const int gen = ++W.mark_gen;
-                while (victim < 0 && n_empty != n_arcs - 1 && to != -5) {
-                    if (W.marks[to] != gen) { W.marks[to] = gen; ++n_empty; }
-                    if (n_empty != n_arcs - 1) {
-                        if (!inter) to = sample_arc(rng, P, G, ep, sigma, t, W.marks, gen, include);
-                        else to = sample_inter_gene(rng, E, lg, sigma, t, include, W.marks, gen, &g_to);
-                        victim = to == -5 ? -1 : find_victim_domain(W.nodes, root, to, g_to, t);
-                    }
-                }
-                if (victim >= 0) { X = to; g = g_to; } else { X = first_to; g = orig_g; }
-            }
-        }
-        // ---- the single vertex-creation site
-        const VertexDraw d = draw_vertex_domain(rng, P, E, E.genes[g], T, X, t);
-        const int idx = new_node(W, n, d, X);
-        if (idx < 0) { n_out = n; return REP_NODE_OVERFLOW; }
-        W.nodes[idx].gtree = (int16_t)g;
-        E.used[g]++;
-        if (stage == 3) { root = idx; W.queue[qt++] = root; stage = 0; continue; }
-        if (stage == 1) { c1 = idx; stage = 2; continue; }
-        if (stage == 4) {
-            // swap (:984-1002): idx takes the place of the transfer vertex li
-            const int par = W.nodes[li].parent;
-            if (li != root) { if (W.nodes[par].left == li) W.nodes[par].left = idx; else W.nodes[par].right = idx; W.nodes[idx].parent = par; }
-            else root = idx;
-            W.nodes[li].parent = -1;
-            if (W.nodes[idx].event < EV_RT_GG_SS) W.queue[qt++] = idx;
-            else {
-                bool rep = false;
-                for (int i = 0; i < np; ++i) if (W.nodes[W.pend[i]].abstime == W.nodes[idx].abstime) { W.pend[i] = idx; rep = true; break; }
-                if (!rep) W.pend[np++] = idx;
-            }
-            stage = 0; continue;
-        }
-        // ---- stage 2 done: attach the pair
-        int lc, rc;
-        if (!transfer) { lc = c1; rc = idx; }
-        else {
-            Node& ln = W.nodes[li];
-            ln.from_arc = sigma; ln.to_arc = X; ln.from_g = (int16_t)lg; ln.to_g = (int16_t)g;
-            if (replacing) {
-                if (victim >= 0) {
-                    Node& vn = W.nodes[victim];
-                    vn.event = EV_REPLACING_LOSS; vn.abstime = t;
-                    int w = 0;
-                    for (int i = 0; i < np; ++i) {
-                        int x = W.pend[i]; bool under = false;
-                        for (int y = x; y >= 0; y = W.nodes[y].parent) if (y == victim) { under = true; break; }
-                        if (!under) W.pend[w++] = x;
-                    }
-                    np = w;
-                    vn.left = -1; vn.right = -1;
-                } else ln.event = (uint8_t)(ev - 4);        // degrade to the additive kind with the same gene / species scope
-            }
-            lc = stay_left ? c1 : idx; rc = stay_left ? idx : c1;
-        }
-        W.nodes[li].left = lc; W.nodes[li].right = rc;
-        W.nodes[lc].parent = li; W.nodes[rc].parent = li;
-        for (int s = 0; s < 2; ++s) {
-            const int c = s == 0 ? lc : rc;
-            if (W.nodes[c].event < EV_RT_GG_SS) W.queue[qt++] = c;
-            else {
-                bool rep = false;
-                for (int i = 0; i < np; ++i) if (W.nodes[W.pend[i]].abstime == W.nodes[c].abstime) { W.pend[i] = c; rep = true; break; }
-                if (!rep) W.pend[np++] = c;
-            }
-        }
-        stage = 0;
     }
-    if (W.nodes[root].bl <= 1.0e-32) W.nodes[root].bl = 0.0;
-    n_out = n; root_out = root;
-    return REP_OK;
+    // (B) replacing transfer: look for a lineage to replace, recipient by recipient
+    req = __ballot_sync(0xffffffffu, S.stage == 2 && S.need_victim);
+    while (req) {
+        const int leader = __ffs(req) - 1; req &= req - 1;
+        const int lg = __shfl_sync(0xffffffffu, S.lg, leader), sigma = __shfl_sync(0xffffffffu, S.sigma, leader), ep = __shfl_sync(0xffffffffu, S.ep, leader);
+        const int root = __shfl_sync(0xffffffffu, S.root, leader), n = __shfl_sync(0xffffffffu, S.n, leader);
+        int to = __shfl_sync(0xffffffffu, S.to, leader), g_to = __shfl_sync(0xffffffffu, S.g_to, leader);
+        const bool inter = __shfl_sync(0xffffffffu, (int)S.inter, leader) != 0, include = __shfl_sync(0xffffffffu, (int)S.include, leader) != 0;
+        const double t = __shfl_sync(0xffffffffu, S.t, leader);
+        const Node* N = reinterpret_cast<const Node*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(W.nodes), leader));
+        int32_t* marks = reinterpret_cast<int32_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(W.marks), leader));
+        const DevHost& G = E.genes[lg];
+        int victim = coop_find_victim_domain(N, n, root, to, g_to, t);
+        const int n_arcs = G.ep_off[ep + 1] - G.ep_off[ep];
+        int n_empty = 0;
+        int gen = 0; if (lane == leader) gen = ++W.mark_gen;
+        gen = __shfl_sync(0xffffffffu, gen, leader);
+        while (victim < 0 && n_empty != n_arcs - 1 && to != -5) {
+            if (marks[to] != gen) { __syncwarp(); if (lane == leader) marks[to] = gen; __syncwarp(); ++n_empty; }
+            if (n_empty != n_arcs - 1) {
+                if (!inter) to = coop_sample_arc(leader, rng, P, G, ep, sigma, t, marks, gen, include);
+                else to = coop_sample_inter_gene(leader, rng, E, lg, sigma, t, include, marks, gen, &g_to);
+                victim = to == -5 ? -1 : coop_find_victim_domain(N, n, root, to, g_to, t);
+            }
+        }
+        if (lane == leader) {
+            S.victim = victim; S.need_victim = false;
+            if (victim >= 0) { S.X = to; S.g = g_to; } else { S.X = S.first_to; S.g = S.orig_g; }
+        }
+    }
+}
+
+template <class RNG>
+__device__ int domain_step(DomainState& S, RNG& rng, const SimParams& P, const DomainEnv& E, const MathTables& T, SimWork& W) {
+    if (S.stage == 0) {
+        for (;;) {
+            if (S.qh == S.qt) {
+                if (S.np == 0) {
+                    if (W.nodes[S.root].bl <= 1.0e-32) W.nodes[S.root].bl = 0.0;
+                    return REP_OK;
+                }
+                int best = 0;
+                for (int i = 1; i < S.np; ++i) if (W.nodes[W.pend[i]].abstime > W.nodes[W.pend[best]].abstime) best = i;
+                W.queue[S.qt++] = W.pend[best];
+                W.pend[best] = W.pend[--S.np];
+            }
+            S.li = W.queue[S.qh++];
+            const Node& ln = W.nodes[S.li];
+            S.ev = ln.event;
+            if (S.ev == EV_LOSS || S.ev == EV_REPLACING_LOSS || S.ev == EV_LEAF || S.ev == EV_UNSAMPLED_LEAF) continue;
+            S.sigma = ln.sigma; S.t = ln.abstime; S.ep = ln.epoch; S.lg = ln.gtree; S.g = S.lg;
+            S.transfer = S.ev >= EV_AT_GG_SS;
+            S.stage = 1;
+            if (S.ev == EV_CODIVERGENCE) { S.X = E.genes[S.lg].left[S.sigma]; break; }
+            S.X = S.sigma;
+            if (S.transfer) {
+                const int code = (S.ev - EV_AT_GG_SS) & 3;
+                S.replacing = S.ev >= EV_RT_GG_SS; S.inter = (code & 2) != 0; S.include = (code & 1) == 0;
+                S.stay_left = rng.next_double() < 0.5;
+                S.need_first = true;             // the first recipient is drawn by the warp before the staying child is created
+                return -1;
+            }
+            break;
+        }
+    }
+    if (S.need_first || (S.stage == 2 && S.need_victim)) return -1;
+    // ---- the single vertex-creation site
+    const VertexDraw d = draw_vertex_domain(rng, P, E, E.genes[S.g], T, S.X, S.t);
+    const int idx = new_node(W, S.n, d, S.X);
+    if (idx < 0) return REP_NODE_OVERFLOW;
+    W.nodes[idx].gtree = (int16_t)S.g;
+    E.used[S.g]++;
+    if (S.stage == 3) { S.root = idx; W.queue[S.qt++] = idx; S.stage = 0; return -1; }
+    if (S.stage == 1) {
+        S.c1 = idx; S.stage = 2;
+        if (S.ev == EV_CODIVERGENCE) { S.X = E.genes[S.lg].right[S.sigma]; S.g = S.lg; }
+        else if (S.ev == EV_DUPLICATION) { S.X = S.sigma; S.g = S.lg; }
+        else if (!S.replacing) { S.X = S.to; S.g = S.g_to; S.victim = -1; }
+        else S.need_victim = true;
+        return -1;
+    }
+    const int li = S.li;
+    if (S.stage == 4) {
+        // swap (:984-1002): idx takes the place of the transfer vertex li
+        const int par = W.nodes[li].parent;
+        if (li != S.root) { if (W.nodes[par].left == li) W.nodes[par].left = idx; else W.nodes[par].right = idx; W.nodes[idx].parent = par; }
+        else S.root = idx;
+        W.nodes[li].parent = -1;
+        if (W.nodes[idx].event < EV_RT_GG_SS) W.queue[S.qt++] = idx;
+        else {
+            bool rep = false;
+            for (int i = 0; i < S.np; ++i) if (W.nodes[W.pend[i]].abstime == W.nodes[idx].abstime) { W.pend[i] = idx; rep = true; break; }
+            if (!rep) W.pend[S.np++] = idx;
+        }
+        S.stage = 0; return -1;
+    }
+    // ---- stage 2 done: attach the pair
+    const int c1 = S.c1;
+    int lc, rc;
+    if (!S.transfer) { lc = c1; rc = idx; }
+    else {
+        Node& ln = W.nodes[li];
+        ln.from_arc = S.sigma; ln.to_arc = S.X; ln.from_g = (int16_t)S.lg; ln.to_g = (int16_t)S.g;
+        if (S.replacing) {
+            if (S.victim >= 0) {
+                Node& vn = W.nodes[S.victim];
+                vn.event = EV_REPLACING_LOSS; vn.abstime = S.t;
+                int w = 0;
+                for (int i = 0; i < S.np; ++i) {
+                    int x = W.pend[i]; bool under = false;
+                    for (int y = x; y >= 0; y = W.nodes[y].parent) if (y == S.victim) { under = true; break; }
+                    if (!under) W.pend[w++] = x;
+                }
+                S.np = w;
+                vn.left = -1; vn.right = -1;
+            } else ln.event = (uint8_t)(S.ev - 4);        // degrade to the additive kind with the same gene / species scope
+        }
+        lc = S.stay_left ? c1 : idx; rc = S.stay_left ? idx : c1;
+    }
+    W.nodes[li].left = lc; W.nodes[li].right = rc;
+    W.nodes[lc].parent = li; W.nodes[rc].parent = li;
+    for (int s = 0; s < 2; ++s) {
+        const int c = s == 0 ? lc : rc;
+        if (W.nodes[c].event < EV_RT_GG_SS) W.queue[S.qt++] = c;
+        else {
+            bool rep = false;
+            for (int i = 0; i < S.np; ++i) if (W.nodes[W.pend[i]].abstime == W.nodes[c].abstime) { W.pend[i] = c; rep = true; break; }
+            if (!rep) W.pend[S.np++] = c;
+        }
+    }
+    S.stage = 0;
+    return -1;
 }
 
 // unprunedIsOK for DomainTreeGen: the per-host-leaf window compares SPECIES leaf ids with gene-tree vertex ids (as the
