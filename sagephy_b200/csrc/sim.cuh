@@ -1,9 +1,11 @@
 // Guest-in-host sampler (device side).
 //
-//  general engine  — one thread simulates one attempt exactly as the reference does, vertex by vertex in the reference's
+//  general engine  — one lane simulates one attempt exactly as the reference does, vertex by vertex in the reference's
 //                    queue order, so that with MtStream the random stream is consumed in the reference's order
 //                    (apps/SaGePhy/GuestTreeInHostTreeCreator.java:110-321 createUnprunedTree, :372-423 createGuestVertex,
 //                    topology/Epoch.java:249-329 sampleArc/setDistance, topology/RBTreeEpochDiscretiser.java:662-683 sampleRoot).
+//                    The 32 lanes of a warp advance in lock step (one vertex per lane per trip, sim_step) and serve each other's
+//                    recipient draws and victim searches (coop_*), see kernels_sample.cuh.
 //  BD fast path    — transfer-free processes on a 1- or 2-leaf host (HostTreeGen) in Philox mode: depth-first expansion with
 //                    a small stack, vertex v of attempt a draws Philox block (v, a, replicate), so the count-only pass and
 //                    the build pass regenerate identical trees.
@@ -64,46 +66,6 @@ __device__ __forceinline__ bool dd_gt(DD a, DD b) { return a.hi > b.hi || (a.hi 
 // Math.pow(Math.E, y) through the fdlibm pow restatement (bit-identical to the oracle's)
 static __device__ __noinline__ double pow_e(double y) { return jpow(2.718281828459045, y); }
 
-// Epoch.sampleArc (include: recipients must carry the same / a different HOST tag as the donor). marks[x] == mark_gen flags an "empty" arc. Returns -5 if no candidate.
-template <class RNG>
-__device__ int sample_arc(RNG& rng, const SimParams& P, const DevHost& H, int epoch, int donor, double t, const int32_t* marks, int mark_gen, bool include = true) {
-    const int a0 = H.ep_off[epoch], a1 = H.ep_off[epoch + 1];
-    const int tag = H.host_tag[donor];
-    if (P.bias == 0) {
-        int k = 0;
-        for (int j = a0; j < a1; ++j) { int x = H.ep_arcs[j]; if (x != donor && !(marks && marks[x] == mark_gen) && ((H.host_tag[x] == tag) == include)) ++k; }
-        if (k < 1) return -5;
-        int pick = rng.next_int(k);
-        for (int j = a0; j < a1; ++j) { int x = H.ep_arcs[j]; if (x != donor && !(marks && marks[x] == mark_gen) && ((H.host_tag[x] == tag) == include)) { if (pick == 0) return x; --pick; } }
-        return -5;
-    }
-    // biased: weights in epoch arc order; key = running total; pick the first key > total * U, where an arc with
-    // weight 0 shares (and therefore overwrites) the previous key (TreeMap.put semantics, Epoch.java:323-324).
-    DD total{0.0, 0.0}; int k = 0;
-    for (int j = a0; j < a1; ++j) {
-        int x = H.ep_arcs[j];
-        if (x == donor || (marks && marks[x] == mark_gen) || ((H.host_tag[x] == tag) != include)) continue;
-        double dist = XMUL(2.0, XSUB(H.lca_time[(size_t)donor * H.nV + x], t));
-        double w = (P.bias == 2) ? XMUL(P.bias_rate, pow_e(XMUL(-P.bias_rate, dist))) : XDIV(1.0, dist);
-        if (w == dbl_inf()) w = 1.7976931348623157e308;
-        total = dd_add_d(total, w); ++k;
-    }
-    if (k < 1) return -5;
-    DD rnd = dd_mul_d(total, rng.next_double());
-    DD cum{0.0, 0.0}; int chosen = -5; bool found = false;
-    for (int j = a0; j < a1; ++j) {
-        int x = H.ep_arcs[j];
-        if (x == donor || (marks && marks[x] == mark_gen) || ((H.host_tag[x] == tag) != include)) continue;
-        double dist = XMUL(2.0, XSUB(H.lca_time[(size_t)donor * H.nV + x], t));
-        double w = (P.bias == 2) ? XMUL(P.bias_rate, pow_e(XMUL(-P.bias_rate, dist))) : XDIV(1.0, dist);
-        if (w == dbl_inf()) w = 1.7976931348623157e308;
-        if (found) { if (w == 0.0) { chosen = x; continue; } break; }
-        cum = dd_add_d(cum, w);
-        if (dd_gt(cum, rnd)) { chosen = x; found = true; }
-    }
-    return chosen;
-}
-
 // RBTreeEpochDiscretiser.sampleRoot
 template <class RNG>
 __device__ __noinline__ int sample_root(RNG& rng, const SimParams& P, const DevHost& H) {
@@ -140,24 +102,6 @@ __device__ __forceinline__ int new_node(SimWork& W, int& n, const VertexDraw& d,
     return n++;
 }
 
-// findVertex (GuestTreeInHostTreeCreator.java:332-346): first vertex in left-before-right pre-order on arc `to`
-// whose branch strictly spans time t.
-static __device__ int find_victim(const Node* N, int root, int to, double t) {
-    int v = root;
-    while (v >= 0) {
-        const Node& x = N[v];
-        if (x.sigma == to && x.abstime < t && XADD(x.abstime, x.bl) > t) return v;
-        if (x.left >= 0) { v = x.left; continue; }
-        for (;;) {
-            int p = N[v].parent;
-            if (p < 0) return -1;
-            if (N[p].left == v) { v = N[p].right; break; }
-            v = p;
-        }
-    }
-    return -1;
-}
-
 // ---- warp-cooperative pieces ---------------------------------------------------------------------------------------------------
 // A warp simulates 32 replicates, one per lane, and all lanes take one step of their attempts per loop trip (sim_step). The two
 // operations that are linear in the host epoch or in the guest tree — the recipient draw of a transfer (Epoch.sampleArc) and the
@@ -181,8 +125,10 @@ __device__ __forceinline__ double arc_weight(const SimParams& P, const DevHost& 
     return w;
 }
 
-// Epoch.sampleArc by the whole warp: same selection rule as sample_arc above (first cumulative key > total * U, zero weights
-// overwrite the previous key); the double-double sums are formed by a warp scan instead of a serial loop, which moves them by
+// Epoch.sampleArc (topology/Epoch.java:249-329) by the whole warp. include: recipients must carry the same / a different HOST tag
+// as the donor; marks[x] == mark_gen flags an "empty" arc; returns -5 if there is no candidate. Uniform mode: nextInt(k) over the
+// eligible arcs in epoch order. Biased modes: weights in epoch arc order, key = running total, the first key > total * U wins and
+// an arc of weight 0 shares (and therefore overwrites) the previous key (TreeMap.put semantics, Epoch.java:323-324); the double-double sums are formed by a warp scan instead of a serial loop, which moves them by
 // ~1e-32 relative — the same order as the double-double stand-in for BigDecimal itself (numerics).
 template <class RNG>
 __device__ __noinline__ int coop_sample_arc(int leader, RNG& rng, const SimParams& P, const DevHost& H, int epoch, int donor, double t, const int32_t* marks, int mark_gen, bool include = true) {
@@ -262,7 +208,8 @@ __device__ __forceinline__ bool preorder_before(const Node* N, int a, int b) {
     while (N[x].parent != N[y].parent) { x = N[x].parent; y = N[y].parent; }
     return N[N[x].parent].left == x;
 }
-// findVertex by the whole warp: every lane tests a slice of the node pool, the pre-order-first attached match wins.
+// findVertex (GuestTreeInHostTreeCreator.java:332-346: first vertex in left-before-right pre-order on arc `to` whose branch
+// strictly spans time t) by the whole warp: every lane tests a slice of the node pool, the pre-order-first attached match wins.
 static __device__ __noinline__ int coop_find_victim(const Node* N, int n, int root, int to, double t) {
     const int lane = threadIdx.x & 31;
     int best = -1;
