@@ -250,7 +250,7 @@ __device__ unsigned long long emit_pieces(int n_pieces, char* base, char* stage,
 }
 
 template <bool WRITE, int STREAM>
-__global__ void __launch_bounds__(kEmitWarps * 32, 8) k_emit(EmitArgs a) {
+__global__ void __launch_bounds__(kEmitWarps * 32, WRITE ? 8 : 10) k_emit(EmitArgs a) {
     __shared__ __align__(16) char s_stage[kEmitWarps][kStageBytes];
     const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
