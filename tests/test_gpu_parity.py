@@ -167,6 +167,13 @@ def test_guest_tree_gen_replay_is_byte_exact(ctx, args):
     assert_replay_parity(ctx, "GuestTreeGen", args, 24, "o")
 
 
+def test_guest_tree_gen_large_trees_rerun_with_bigger_pools(ctx):
+    # trees beyond the first scratch-pool size (1024 vertices) are re-run with 8x the pool: same bytes as the oracle
+    args = ["-s", "41", "-db", "none", "-max", "100000", "-maxper", "100000", HOST8, "5.0", "0.2", "0.3", "o"]
+    b = assert_replay_parity(ctx, "GuestTreeGen", args, 6, "o")
+    assert b.sampled_leaves.max() > 600
+
+
 def test_guest_tree_gen_quiet_prints_the_pruned_tree(ctx):
     args = ["-s", "15", "-q", "-db", "none", HOST5, "0.5", "0.4", "0.5"]            # GuestTreeGen.java:59-64
     b = ctx.run("GuestTreeGen", args, n=4, rng=sg.RNG_MT_REPLAY)
