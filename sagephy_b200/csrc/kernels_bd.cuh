@@ -215,24 +215,32 @@ __global__ void __launch_bounds__(256) k_bd_build(BdArgs a) {
         const U4 w = philox4x32_10(vidx, inf.acc_attempt, rep_lo, rep_hi, k0, k1);
         const BdVertex v = a.H.nV == 1 ? bd_vertex_single(C, start, w, s_logtab) : bd_vertex(C, a.H, X, start, w, s_logtab);
         const int me = (int)vidx++;
-        Node& nd = N[me];
+        const bool internal = v.event == EV_DUPLICATION || v.event == EV_SPECIATION;
+        // the record is assembled in registers and leaves as five 16-byte stores (field-wise stores saturate the load/store unit:
+        // every one of them touches 32 different sectors per warp)
+        Node nd;
         nd.abstime = v.et;
         nd.bl = v.boundary ? round_sig(a.T, start - v.et, 8) : v.bt;       // GuestTreeInHostTreeCreator.java:385 vs :378
-        nd.sigma = X; nd.left = -1; nd.right = -1; nd.from_arc = -1; nd.to_arc = -1; nd.number = -1;
+        if (me == 0 && nd.bl <= 1.0e-32) nd.bl = 0.0;
+        nd.sigma = X; nd.left = internal ? me + 1 : -1; nd.right = -1; nd.from_arc = -1; nd.to_arc = -1; nd.number = -1;       // depth-first: the left child is the next vertex
         nd.p_bl = 0.0; nd.p_left = -1; nd.p_right = -1; nd.event = v.event; nd.prun = PR_UNKNOWN; nd.flags = 0; nd.pad0 = 0; nd.gtree = 0;
         nd.from_g = -1; nd.to_g = -1; nd.chain_u = 0; nd.chain_p = 0; nd.pad1 = 0;
         int ep = a.H.v2e[X];
         if (!v.boundary) { while (a.H.ep_up[ep] < v.et) ++ep; }
         nd.epoch = ep;
-        if (pw == -1) nd.parent = -1;
-        else { int p = pw & 0x7fffffff; nd.parent = p; if (pw < 0) N[p].right = me; else N[p].left = me; }
-        if (v.event == EV_DUPLICATION || v.event == EV_SPECIATION) {
+        nd.parent = pw == -1 ? -1 : (pw & 0x7fffffff);
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(&nd); uint4* dst = reinterpret_cast<uint4*>(&N[me]);
+#pragma unroll
+            for (int q = 0; q < (int)(sizeof(Node) / 16); ++q) dst[q] = src[q];
+        }
+        if (pw != -1 && pw < 0) N[pw & 0x7fffffff].right = me;             // right children are linked when they are created
+        if (internal) {
             const bool dup = v.event == EV_DUPLICATION;
             st_time[sp] = v.et; st_arc[sp] = (int8_t)(dup ? X : a.H.right[X]); st_par[sp] = (int32_t)(0x80000000u | (uint32_t)me);
             st_time[sp + 1] = v.et; st_arc[sp + 1] = (int8_t)(dup ? X : a.H.left[X]); st_par[sp + 1] = me; sp += 2;
         }
     }
-    if (N[0].bl <= 1.0e-32) N[0].bl = 0.0;
     inf.root = 0;
     if ((int)vidx != inf.n_pool) inf.status = REP_MODEL_ERROR;
 }
