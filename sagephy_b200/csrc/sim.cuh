@@ -95,10 +95,14 @@ struct SimWork {
 
 __device__ __forceinline__ int new_node(SimWork& W, int& n, const VertexDraw& d, int sigma) {
     if (n >= W.cap) return -1;
-    Node& v = W.nodes[n];
+    // assembled in registers, written as five 16-byte stores (field-wise stores touch 32 different sectors per warp each)
+    Node v;
     v.abstime = d.abstime; v.bl = d.bl; v.sigma = sigma; v.left = -1; v.right = -1; v.parent = -1; v.epoch = d.epoch;
     v.from_arc = -1; v.to_arc = -1; v.number = -1; v.p_bl = 0.0; v.p_left = -1; v.p_right = -1;
     v.event = d.event; v.prun = PR_UNKNOWN; v.flags = 0; v.pad0 = 0; v.gtree = 0; v.from_g = -1; v.to_g = -1; v.chain_u = 0; v.chain_p = 0; v.pad1 = 0;
+    const uint4* src = reinterpret_cast<const uint4*>(&v); uint4* dst = reinterpret_cast<uint4*>(&W.nodes[n]);
+#pragma unroll
+    for (int q = 0; q < (int)(sizeof(Node) / 16); ++q) dst[q] = src[q];
     return n++;
 }
 
