@@ -9,11 +9,15 @@
  *                           apps/SaGePhyStarter.java:75-103 (first token = app), apps/SaGePhy/HostTreeGen.java:25-116,
  *                           GuestTreeGen.java:21-107, DomainTreeGen.java:21-107, BranchRelaxer.java:48-141.
  *                           Same options, defaults (from the code) and positional counts, plus a replicate count.
- *   sgp_treegen_run      <- UnprunedGuestTreeCreator (apps/SaGePhy/UnprunedGuestTreeCreator.java:17-59) driven by
- *                           GuestTreeMachina.sampleGuestTree (apps/SaGePhy/GuestTreeMachina.java:69-115), followed by
- *                           PruningHelper / GuestVertex.setMeta / NewickTreeWriter / getInfo / getSigma / getLeafMap.
- *   sgp_relax_run        <- RateModel.getRates (apps/SaGePhy/RateModel.java:13-29) + BranchRelaxer.main's retry loop
- *                           and rescaling (apps/SaGePhy/BranchRelaxer.java:94-101,148-197).
+ *     tree generators    <- in-JVM seam 1: UnprunedGuestTreeCreator (apps/SaGePhy/UnprunedGuestTreeCreator.java:17-59) driven
+ *                           by GuestTreeMachina.sampleGuestTree (apps/SaGePhy/GuestTreeMachina.java:69-115), followed by
+ *                           PruningHelper / GuestVertex.setMeta / NewickTreeWriter / getInfo / getSigma / getLeafMap — all
+ *                           behind sgp_app_run("HostTreeGen" | "GuestTreeGen" | "DomainTreeGen", ...).
+ *     BranchRelaxer      <- in-JVM seam 2: RateModel.getRates (apps/SaGePhy/RateModel.java:13-29) + BranchRelaxer.main's retry
+ *                           loop and rescaling (apps/SaGePhy/BranchRelaxer.java:94-101,148-197) — sgp_app_run("BranchRelaxer").
+ *   sgp_relax_run_on_batch <- the file hand-over between two CLI runs (generator writes <prefix>.pruned.tree, BranchRelaxer
+ *                           reads it: apps/SaGePhy/BranchRelaxerParameters.java:167-179), kept on the device.
+ *   sgp_batch_write_files[_layout] <- the apps' own file fan-out (apps/SaGePhy/GuestTreeGen.java:66-101, HostTreeGen.java:82-110).
  *
  * All pointers are plain host pointers; no CUDA or torch types cross the boundary. Calls block until the outputs are
  * resident (in HBM for the *_device accessors, in pinned host memory for the host accessors). There is no CPU fallback:
