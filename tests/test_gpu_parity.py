@@ -250,6 +250,30 @@ def test_leaf_sizes_file_option(ctx, tmp_path):
     assert stats.chisquare(c, f_exp=n * np.array([0.2, 0.4, 0.2, 0.2])).pvalue > 0.001
 
 
+def test_native_cli_writes_the_reference_files(tmp_path):
+    # `sagephy <App> ...` is the stand-in for `java -jar sagephy.jar <App> ...` (apps/SaGePhyStarter.java:75-103)
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sagephy_b200", "sagephy")
+    core = ["-s", "3", "-min", "5", "-max", "12", "1.0", "3.0", "0.3", "species"]
+    subprocess.check_call([exe, "HostTreeGen"] + core, cwd=tmp_path)
+    want = oracle_run("HostTreeGen", core)["files"]
+    assert sorted(p.name for p in tmp_path.iterdir()) == sorted(want)
+    for name, data in want.items():
+        assert (tmp_path / name).read_bytes() == data, name
+    out = subprocess.run([exe, "HostTreeGen", "-q"] + core[:-1], cwd=tmp_path, capture_output=True, text=True, check=True).stdout
+    assert out == oracle_run("HostTreeGen", ["-q"] + core[:-1])["stdout"]
+    usage = subprocess.run([exe, "GuestTreeGen", "x"], cwd=tmp_path, capture_output=True, text=True)
+    assert usage.returncode == 0 and usage.stdout.startswith("Usage:")
+    d = tmp_path / "many"; d.mkdir()
+    subprocess.check_call([exe, "GuestTreeGen", "-n", "3", "-rng", "mt-replay", "--out-layout", "per-replicate", "-s", "4", "-db", "none", HOST5, "0.3", "0.2", "0.4", "gene"], cwd=d)
+    for i in range(3):
+        w = oracle_run("GuestTreeGen", ["-s", str(4 + i), "-db", "none", HOST5, "0.3", "0.2", "0.4", f"gene_{i}"])["files"]
+        for name, data in w.items():
+            got = (d / name).read_bytes()
+            strip = lambda t: b"\n".join(l for l in t.split(b"\n") if not l.startswith(b"Arguments:"))
+            assert strip(got) == strip(data), name
+
+
 # ---- Philox throughput mode: distributions ---------------------------------------------------------------------------------------
 def ks_ok(a, b):
     return stats.ks_2samp(a, b).pvalue > 0.01
