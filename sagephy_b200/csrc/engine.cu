@@ -2,6 +2,8 @@
 //   K0 tables -> K1 find (accepted attempt per replicate) -> scan -> K1 build (node arena) -> K3 label/prune
 //   -> K4 emit size -> scan -> K4 emit write -> summary reduction.
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_partition.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
@@ -64,6 +66,9 @@ __global__ void k_collect_status(const RepInfo* info, long long n, int status, l
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && info[i].status == status) { unsigned long long k = atomicAdd(count, 1ULL); list[k] = i; }
 }
+
+// build order: replicates whose tree is much larger than average go first (cub::DevicePartition keeps them in front)
+struct PoolAbove { const long long* pool; long long thr; __device__ bool operator()(long long i) const { return pool[i] > thr; } };
 
 struct DevSummary { unsigned long long n_ok, n_failed, attempts_total, vertices, vertices_abandoned, attempts_completed; unsigned long long ev[17]; unsigned long long leaf_hist[1025]; };
 __global__ void k_summary(const RepInfo* info, long long n, DevSummary* s) {
@@ -364,6 +369,12 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             max_workers = std::max<long long>(max_workers, workers);
             DevBuf<Node> s_nodes; DevBuf<int32_t> s_queue, s_pend;
             s_nodes.alloc((size_t)workers * cap); s_queue.alloc((size_t)workers * cap); s_pend.alloc((size_t)workers * cap);
+            // spare pools of 8x the size (~0.8 GB): trees that outgrow a worker's pool are redone at once inside this launch
+            DevBuf<Node> b_nodes; DevBuf<int32_t> b_queue, b_pend; DevBuf<int> b_next;
+            const int big_cap = (int)std::min<long long>((long long)cap * 8, 1 << 24);
+            const int big_count = (int)std::max<long long>(0, std::min<long long>(1024, (long long)((800ull << 20) / ((unsigned long long)big_cap * (sizeof(Node) + 8)))));
+            if (big_count > 0) { b_nodes.alloc((size_t)big_count * big_cap); b_queue.alloc((size_t)big_count * big_cap); b_pend.alloc((size_t)big_count * big_cap); }
+            b_next.alloc(1); CK(cudaMemsetAsync(b_next.p, 0, sizeof(int), st));
             marks.alloc((size_t)workers * mark_n); leafcnt.alloc((size_t)workers * cnt_n);
             if (domain) scratch_used.alloc((size_t)workers * cfg.genes.size());
             if (replay) mt_state.alloc((size_t)(workers / 32 + 1) * 624 * 32);
@@ -372,6 +383,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             a.scratch_marks = marks.p; a.scratch_leafcnt = leafcnt.p; a.mt_state = mt_state.p; a.sizes = d_sizes.p; a.per_leaf_check = per_leaf;
             a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
             a.scratch_used = scratch_used.p; a.ev_base = d_ev_base.p; a.ev_off = d_ev_off.p; a.ev_list = d_ev_list.p;
+            a.big_nodes = b_nodes.p; a.big_queue = b_queue.p; a.big_pend = b_pend.p; a.big_cap = big_cap; a.big_count = big_count; a.big_next = b_next.p;
             CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
             int blocks = (int)(workers / 128);
             launch_find_general(replay, domain, a, blocks, st);
@@ -427,6 +439,17 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         a.nodes = nodes.p; a.aux = aux.p; a.aux_stride = aux_stride; a.scratch_marks = marks.p; a.scratch_leafcnt = nullptr; a.mt_state = mt_state.p;
         a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
         a.scratch_used = scratch_used.p; a.ev_base = d_ev_base.p; a.ev_off = d_ev_off.p; a.ev_list = d_ev_list.p;
+        // a lane builds its tree alone, so the largest trees set the kernel's tail: start them first
+        DevBuf<long long> order, n_sel; DevBuf<char> ptmp;
+        if (n >= 4096) {
+            order.alloc((size_t)n); n_sel.alloc(1);
+            cub::CountingInputIterator<long long> ids(0);
+            PoolAbove big{pool.p, 2 * (total_nodes / n) + 64};
+            size_t pb = 0; cub::DevicePartition::If(nullptr, pb, ids, order.p, n_sel.p, (int)n, big, st);
+            ptmp.alloc(pb);
+            cub::DevicePartition::If(ptmp.p, pb, ids, order.p, n_sel.p, (int)n, big, st); ++tm.launches;
+            a.order = order.p;
+        }
         launch_build_general(replay, domain, a, (int)(threads / 128), st);
         ++tm.launches;
     }

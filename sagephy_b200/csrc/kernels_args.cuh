@@ -33,6 +33,9 @@ struct FindArgs {
     // DomainTreeGen: forest of gene trees (H above is then the species tree)
     const DevHost* genes; int n_genes; int max_gene_nv; int all_genes; double inter_gene, inter_species;
     int32_t* scratch_used;       // n_genes ints per worker
+    // spare scratch pools of big_cap vertices: a lane whose tree outgrows its own pool takes one (if any is left) and restarts the
+    // replicate at once instead of leaving it to a later, latency-bound launch
+    Node* big_nodes; int32_t* big_queue; int32_t* big_pend; int big_cap, big_count; int* big_next;
     const int32_t* ev_base; const int32_t* ev_off; const int32_t* ev_list;    // inter-gene candidate index: vertices of gene g whose first epoch is e = ev_list[ev_off[ev_base[g] + e] .. ev_off[ev_base[g] + e + 1])
 };
 
@@ -43,6 +46,7 @@ struct BuildArgs {
     long long n; long long rep_base; unsigned long long seed;
     RepInfo* info;
     const long long* node_off;   // exclusive scan of n_pool
+    const long long* order;      // thread t builds replicate order[t] (largest trees first: their serial latency is the kernel's tail); nullptr = identity
     Node* nodes;                 // arena
     int32_t* aux; long long aux_stride;    // 4 int arrays of length total_nodes: aux + k*aux_stride
     int32_t* scratch_marks; int32_t* scratch_leafcnt;

@@ -42,14 +42,16 @@ __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
     MtStream mt; PhiloxStream ph;
     if (REPLAY) { mt.mt = a.mt_state + (size_t)(worker >> 5) * 624 * 32 + (worker & 31); mt.stride = 32; }
     EngineState<DOMAIN> S; S.stage = -1;
-    bool have = false, exhausted = false;
+    bool have = false, exhausted = false, again = false, big = false;
     long long r = 0; RepInfo inf; int attempts = 0; uint64_t verts = 0, pos = 0;
     for (;;) {
         if (!have && !exhausted) {
-            const long long slot = (long long)atomicAdd(a.work_counter, 1ULL);
-            if (slot >= a.n) exhausted = true;
+            long long slot = 0;
+            if (!again) slot = (long long)atomicAdd(a.work_counter, 1ULL);
+            if (!again && slot >= a.n) exhausted = true;
             else {
-                r = a.rep_ids ? a.rep_ids[slot] : slot;
+                if (!again) r = a.rep_ids ? a.rep_ids[slot] : slot;
+                again = false;
                 const long long gid = a.rep_base + r;
                 memset(&inf, 0, sizeof(inf));
                 inf.status = REP_PENDING; inf.exact = -1; inf.root = -1; inf.p_root = -1;
@@ -72,8 +74,15 @@ __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
                 verts += (uint64_t)S.n;
                 const int n = S.n, root = S.root;
                 S.stage = -1;
-                if (st != REP_OK) { inf.status = st; inf.attempts = attempts; inf.vertices_sampled = verts; a.info[r] = inf; have = false; }
-                else {
+                if (st != REP_OK) {
+                    int spare = -1;
+                    if (st == REP_NODE_OVERFLOW && !big && a.big_count > 0) { spare = atomicAdd(a.big_next, 1); if (spare >= a.big_count) spare = -1; }
+                    if (spare >= 0) {
+                        // the tree outgrew the pool: move to a spare big pool and run the replicate again from its first attempt
+                        W.nodes = a.big_nodes + (size_t)spare * a.big_cap; W.queue = a.big_queue + (size_t)spare * a.big_cap; W.pend = a.big_pend + (size_t)spare * a.big_cap;
+                        W.cap = a.big_cap; big = true; again = true; have = false;
+                    } else { inf.status = st; inf.attempts = attempts; inf.vertices_sampled = verts; a.info[r] = inf; have = false; }
+                } else {
                     ++attempts;
                     int sampled = 0;
                     const bool ok = DOMAIN ? attempt_ok_domain(a.P, a.H, E, W, root, inf.exact, a.max_gene_nv, a.per_leaf_check != 0, a.all_genes != 0, &sampled)
@@ -93,7 +102,8 @@ __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
 
 template <bool REPLAY, bool DOMAIN>
 __global__ void __launch_bounds__(128) k_build_general(BuildArgs a) {
-    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = t < a.n ? (a.order ? a.order[t] : t) : a.n;
     const int worker = blockIdx.x * blockDim.x + threadIdx.x;
     // all lanes of a warp stay: lanes without a tree to build still help with the cooperative pieces
     const bool active = r < a.n && a.info[r < a.n ? r : 0].status == REP_OK;
