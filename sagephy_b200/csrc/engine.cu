@@ -149,6 +149,11 @@ struct Context::Impl {
     // kernel, not through cudaMemcpy: a DMA copy would queue behind a caller's bulk copies that are still in flight on the
     // copy stream (Batch::copy_stream_to_async) and stall the next batch's compute for their whole duration.
     unsigned char* mailbox = nullptr; static constexpr size_t kMailboxBytes = 32768;
+    // Large scratch of the general find kernel (up to ~25 GB): kept for the life of the context and only ever grown. Going
+    // through the stream-ordered pool for it made run times erratic near HBM capacity (a 15 GB request that does not fit the
+    // pool's free blocks costs hundreds of milliseconds of unmap / map).
+    void* scratch_buf[8] = {nullptr}; size_t scratch_bytes[8] = {0};
+    void* scratch(int slot, size_t bytes);
     void post(size_t off, const void* dsrc, size_t bytes);
     template <class T> T take(size_t off) const { T v; memcpy(&v, mailbox + off, sizeof(T)); return v; }
     DevBuf<unsigned long long> g_table; DevBuf<double> p10;
@@ -162,6 +167,14 @@ __global__ void k_post_words(uint32_t* dst, const uint32_t* src, int words) {
 void Context::Impl::post(size_t off, const void* dsrc, size_t bytes) {
     if (off + bytes > kMailboxBytes || (bytes & 3) || (off & 3)) throw SgpError("internal: mailbox overflow");
     k_post_words<<<1, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(mailbox + off), static_cast<const uint32_t*>(dsrc), (int)(bytes / 4));
+}
+
+void* Context::Impl::scratch(int slot, size_t bytes) {
+    if (bytes > scratch_bytes[slot]) {
+        if (scratch_buf[slot]) { CK(cudaStreamSynchronize(stream)); CK(cudaFree(scratch_buf[slot])); scratch_buf[slot] = nullptr; scratch_bytes[slot] = 0; }
+        CK(cudaMalloc(&scratch_buf[slot], bytes)); scratch_bytes[slot] = bytes;
+    }
+    return scratch_buf[slot];
 }
 
 Context::Context(int dev) : device(dev), impl(new Impl()) {
@@ -189,6 +202,7 @@ Context::~Context() {
         cudaStreamSynchronize(impl->stream); cudaStreamDestroy(impl->stream); impl->stream = nullptr; g_alloc_stream = nullptr;
         if (impl->copy) { cudaStreamSynchronize(impl->copy); cudaStreamDestroy(impl->copy); impl->copy = nullptr; }
         if (impl->mailbox) { cudaFreeHost(impl->mailbox); impl->mailbox = nullptr; }
+        for (int i = 0; i < 8; ++i) if (impl->scratch_buf[i]) { cudaFree(impl->scratch_buf[i]); impl->scratch_buf[i] = nullptr; }
     }
 }
 
@@ -367,23 +381,27 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             while ((double)workers * cap * (sizeof(Node) + 8.0) > 24.0 * (1ull << 30) && workers > 128) workers /= 2;
             workers = std::max<long long>(128, workers / 128 * 128);
             max_workers = std::max<long long>(max_workers, workers);
-            DevBuf<Node> s_nodes; DevBuf<int32_t> s_queue, s_pend;
-            s_nodes.alloc((size_t)workers * cap); s_queue.alloc((size_t)workers * cap); s_pend.alloc((size_t)workers * cap);
+            Node* s_nodes = (Node*)impl->scratch(0, (size_t)workers * cap * sizeof(Node));
+            int32_t* s_queue = (int32_t*)impl->scratch(1, (size_t)workers * cap * sizeof(int32_t)), *s_pend = (int32_t*)impl->scratch(2, (size_t)workers * cap * sizeof(int32_t));
             // spare pools of 8x the size (~0.8 GB): trees that outgrow a worker's pool are redone at once inside this launch
-            DevBuf<Node> b_nodes; DevBuf<int32_t> b_queue, b_pend; DevBuf<int> b_next;
+            DevBuf<int> b_next;
             const int big_cap = (int)std::min<long long>((long long)cap * 8, 1 << 24);
             const int big_count = (int)std::max<long long>(0, std::min<long long>(1024, (long long)((800ull << 20) / ((unsigned long long)big_cap * (sizeof(Node) + 8)))));
-            if (big_count > 0) { b_nodes.alloc((size_t)big_count * big_cap); b_queue.alloc((size_t)big_count * big_cap); b_pend.alloc((size_t)big_count * big_cap); }
+            Node* b_nodes = nullptr; int32_t* b_queue = nullptr, *b_pend = nullptr;
+            if (big_count > 0) {
+                b_nodes = (Node*)impl->scratch(3, (size_t)big_count * big_cap * sizeof(Node));
+                b_queue = (int32_t*)impl->scratch(4, (size_t)big_count * big_cap * sizeof(int32_t)); b_pend = (int32_t*)impl->scratch(5, (size_t)big_count * big_cap * sizeof(int32_t));
+            }
             b_next.alloc(1); CK(cudaMemsetAsync(b_next.p, 0, sizeof(int), st));
             marks.alloc((size_t)workers * mark_n); leafcnt.alloc((size_t)workers * cnt_n);
             if (domain) scratch_used.alloc((size_t)workers * cfg.genes.size());
             if (replay) mt_state.alloc((size_t)(workers / 32 + 1) * 624 * 32);
             FindArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = todo; a.rep_ids = rep_ids; a.rep_base = opts.offset; a.seed = seed; a.info = info.p;
-            a.work_counter = counter.p; a.scratch_nodes = s_nodes.p; a.scratch_queue = s_queue.p; a.scratch_pend = s_pend.p; a.cap = cap;
+            a.work_counter = counter.p; a.scratch_nodes = s_nodes; a.scratch_queue = s_queue; a.scratch_pend = s_pend; a.cap = cap;
             a.scratch_marks = marks.p; a.scratch_leafcnt = leafcnt.p; a.mt_state = mt_state.p; a.sizes = d_sizes.p; a.per_leaf_check = per_leaf;
             a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
             a.scratch_used = scratch_used.p; a.ev_base = d_ev_base.p; a.ev_off = d_ev_off.p; a.ev_list = d_ev_list.p;
-            a.big_nodes = b_nodes.p; a.big_queue = b_queue.p; a.big_pend = b_pend.p; a.big_cap = big_cap; a.big_count = big_count; a.big_next = b_next.p;
+            a.big_nodes = b_nodes; a.big_queue = b_queue; a.big_pend = b_pend; a.big_cap = big_cap; a.big_count = big_count; a.big_next = b_next.p;
             CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
             int blocks = (int)(workers / 128);
             launch_find_general(replay, domain, a, blocks, st);
@@ -431,11 +449,12 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         a.node_off = node_off.p; a.nodes = nodes.p;
         launch_bd_build(a, (int)((n + 255) / 256), st); ++tm.launches;
     } else {
-        const long long threads = (n + 127) / 128 * 128;
+        const long long threads = std::max<long long>(128, std::min<long long>((long long)sm * 1024, (n + 127) / 128 * 128));
         marks.alloc((size_t)threads * (domain ? max_gene_nv : cfg.host.nV));
         if (domain) scratch_used.alloc((size_t)threads * cfg.genes.size());
         if (replay) mt_state.alloc((size_t)(threads / 32 + 1) * 624 * 32);
-        BuildArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.info = info.p; a.node_off = node_off.p;
+        CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
+        BuildArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.info = info.p; a.node_off = node_off.p; a.work_counter = counter.p;
         a.nodes = nodes.p; a.aux = aux.p; a.aux_stride = aux_stride; a.scratch_marks = marks.p; a.scratch_leafcnt = nullptr; a.mt_state = mt_state.p;
         a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
         a.scratch_used = scratch_used.p; a.ev_base = d_ev_base.p; a.ev_off = d_ev_off.p; a.ev_list = d_ev_list.p;

@@ -46,7 +46,8 @@ struct BuildArgs {
     long long n; long long rep_base; unsigned long long seed;
     RepInfo* info;
     const long long* node_off;   // exclusive scan of n_pool
-    const long long* order;      // thread t builds replicate order[t] (largest trees first: their serial latency is the kernel's tail); nullptr = identity
+    unsigned long long* work_counter;   // build slots are claimed dynamically, like replicates in the find kernel
+    const long long* order;      // slot t builds replicate order[t] (largest trees first: their serial latency is the kernel's tail); nullptr = identity
     Node* nodes;                 // arena
     int32_t* aux; long long aux_stride;    // 4 int arrays of length total_nodes: aux + k*aux_stride
     int32_t* scratch_marks; int32_t* scratch_leafcnt;

@@ -102,40 +102,49 @@ __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
 
 template <bool REPLAY, bool DOMAIN>
 __global__ void __launch_bounds__(128) k_build_general(BuildArgs a) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long r = t < a.n ? (a.order ? a.order[t] : t) : a.n;
     const int worker = blockIdx.x * blockDim.x + threadIdx.x;
-    // all lanes of a warp stay: lanes without a tree to build still help with the cooperative pieces
-    const bool active = r < a.n && a.info[r < a.n ? r : 0].status == REP_OK;
-    RepInfo& inf = a.info[active ? r : 0];
-    const long long off = active ? a.node_off[r] : 0;
-    SimWork W;
-    W.nodes = a.nodes + off; W.cap = active ? inf.n_pool : 0;
-    W.queue = a.aux + off; W.pend = a.aux + a.aux_stride + off;
+    SimWork W; W.nodes = nullptr; W.cap = 0; W.queue = nullptr; W.pend = nullptr;
     const int mark_n = DOMAIN ? a.max_gene_nv : a.H.nV;
     W.marks = a.scratch_marks + (size_t)worker * mark_n; W.leaf_cnt = nullptr; W.mark_gen = 0;
     for (int i = 0; i < mark_n; ++i) W.marks[i] = 0;
     DomainEnv E{a.genes, a.n_genes, a.inter_gene, a.inter_species, DOMAIN ? a.scratch_used + (size_t)worker * a.n_genes : nullptr, a.ev_base, a.ev_off, a.ev_list};
-    int n = 0, root = -1, st = REP_OK;
-    const long long gid = a.rep_base + r;
     MtStream mt; PhiloxStream ph;
-    if (REPLAY) {
-        mt.mt = a.mt_state + (size_t)(worker >> 5) * 624 * 32 + (worker & 31); mt.stride = 32;
-        if (active) { uint32_t key[4]; seed_words_i64((long long)a.seed + gid, key); mt.seed(key); mt.skip(((uint64_t)inf.acc_hi << 32) | inf.acc_attempt); }
-    } else if (active) ph.init(a.seed, (uint64_t)gid, inf.acc_attempt);
+    if (REPLAY) { mt.mt = a.mt_state + (size_t)(worker >> 5) * 624 * 32 + (worker & 31); mt.stride = 32; }
     EngineState<DOMAIN> S; S.stage = -1;
-    if (active) { if (REPLAY) engine_begin<DOMAIN>(S, mt, a, E); else engine_begin<DOMAIN>(S, ph, a, E); }
+    bool have = false, exhausted = false;
+    long long r = 0;
+    // same flat loop as the find kernel: a lane that has finished its tree takes the next one (trees differ a lot in size; one
+    // tree per thread would leave most lanes of a warp waiting for its largest tree)
     for (;;) {
-        if (!__ballot_sync(0xffffffffu, S.stage >= 0)) break;
+        if (!have && !exhausted) {
+            const long long t = (long long)atomicAdd(a.work_counter, 1ULL);
+            if (t >= a.n) exhausted = true;
+            else {
+                r = a.order ? a.order[t] : t;
+                const RepInfo& inf = a.info[r];
+                if (inf.status == REP_OK) {
+                    const long long off = a.node_off[r];
+                    W.nodes = a.nodes + off; W.cap = inf.n_pool; W.queue = a.aux + off; W.pend = a.aux + a.aux_stride + off;
+                    const long long gid = a.rep_base + r;
+                    if (REPLAY) {
+                        uint32_t key[4]; seed_words_i64((long long)a.seed + gid, key); mt.seed(key); mt.skip(((uint64_t)inf.acc_hi << 32) | inf.acc_attempt);
+                        engine_begin<DOMAIN>(S, mt, a, E);
+                    } else { ph.init(a.seed, (uint64_t)gid, inf.acc_attempt); engine_begin<DOMAIN>(S, ph, a, E); }
+                    have = true;
+                }
+            }
+        }
+        if (!__ballot_sync(0xffffffffu, have || !exhausted)) break;
         if (REPLAY) engine_resolve<DOMAIN>(S, mt, a, E, W); else engine_resolve<DOMAIN>(S, ph, a, E, W);
-        if (S.stage >= 0) {
+        if (have) {
             const int rc = REPLAY ? engine_step<DOMAIN>(S, mt, a, E, W) : engine_step<DOMAIN>(S, ph, a, E, W);
-            if (rc >= 0) { st = rc; n = S.n; root = S.root; S.stage = -1; }
+            if (rc >= 0) {
+                RepInfo& inf = a.info[r];
+                if (rc != REP_OK || S.n != inf.n_pool) inf.status = REP_MODEL_ERROR; else inf.root = S.root;
+                S.stage = -1; have = false;
+            }
         }
     }
-    if (!active) return;
-    if (st != REP_OK || n != inf.n_pool) { inf.status = REP_MODEL_ERROR; return; }
-    inf.root = root;
 }
 
 }  // namespace sgp
