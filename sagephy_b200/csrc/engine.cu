@@ -511,6 +511,8 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         if (split) post += "]"; else pre += "]";
         add(pre, e.args_pre_off, e.args_pre_len); add(post, e.args_post_off, e.args_post_len);
         e.seed_mode = split ? 1 : 0; e.seed_base = cfg.seed;
+        e.args_pre_off16[0] = -1;
+        if (pre.size() >= 512) for (int k = 0; k < 16; ++k) { while ((int)(blob.size() % 16) != k) blob.push_back(' '); e.args_pre_off16[k] = (int)blob.size(); blob += pre; }
     }
     add("# GUEST-TO-HOST MAP\nHost tree:\t" + cfg.host.header + "\nGuest vertex name:\tGuest vertex ID:\tGuest vertex type:\tGuest vertex time:\tHost vertex/arc ID:\tHost epoch ID:\n",
         e.g2h_head_off, e.g2h_head_len);

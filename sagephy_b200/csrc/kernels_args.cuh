@@ -100,6 +100,7 @@ struct EmitArgs {
     const char* blob;              // constant strings, see below
     int args_pre_off, args_pre_len, args_post_off, args_post_len, seed_mode; long long seed_base;
     int g2h_head_off, g2h_head_len;
+    int args_pre_off16[16];        // same 16 shifted copies for the "Arguments:" text when it is long (it may embed a whole host tree); [0] < 0: not built
     int g2h_head_off16[16];        // 16 copies of the header, copy k starting at a blob offset == k (mod 16): aligned 16-byte copies for any destination
     const int32_t* gname_off;      // per host tree: offset/len pairs into blob (GUEST= value / file name)
     const int32_t* leafname_off;   // per host vertex: offset/len pairs into blob (leafmap second column)

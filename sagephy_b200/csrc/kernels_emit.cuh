@@ -316,7 +316,13 @@ __global__ void __launch_bounds__(kEmitWarps * 32, WRITE ? 8 : 10) k_emit(EmitAr
                 unsigned long long o = 0;
                 if (WRITE) {
                     for (int i = lane; i < h0len; i += 32) base[i] = h0[i];
-                    for (int i = lane; i < a.args_pre_len; i += 32) base[h0len + i] = a.blob[a.args_pre_off + i];
+                    if (a.args_pre_off16[0] >= 0) {
+                        // long argument text (a host tree given as a Newick string): aligned 16-byte copies from the copy of the
+                        // text whose blob offset is congruent to the destination mod 16
+                        char* dst = base + h0len;
+                        const int mis = (int)(reinterpret_cast<unsigned long long>(dst) & 15ull);
+                        flush_stage(a.blob + a.args_pre_off16[mis] - mis, mis, dst, (unsigned)a.args_pre_len);
+                    } else for (int i = lane; i < a.args_pre_len; i += 32) base[h0len + i] = a.blob[a.args_pre_off + i];
                 }
                 o = (unsigned long long)h0len + a.args_pre_len;
                 if (a.seed_mode) {

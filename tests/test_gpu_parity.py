@@ -187,6 +187,8 @@ def test_guest_tree_gen_on_generated_100_leaf_host(ctx, tmp_path):
     p.write_bytes(host)
     for db in ("none", "simple", "exponential"):
         assert_replay_parity(ctx, "GuestTreeGen", ["-s", "100", "-db", db, str(p), "0.3", "0.3", "0.3", "o"], 6, "o")
+    # the host tree given as a Newick string: the "Arguments:" line of both .info files then embeds ~12 KB of text
+    assert_replay_parity(ctx, "GuestTreeGen", ["-s", "200", "-db", "none", host.decode().strip(), "0.3", "0.3", "0.3", "o"], 5, "o")
 
 
 def test_label_kernels_agree(ctx, monkeypatch):
