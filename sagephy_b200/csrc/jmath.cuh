@@ -311,6 +311,21 @@ struct MemSink {
     static constexpr bool kRandomAccess = true;
 };
 
+#if defined(__CUDACC__)
+// Sink on a shared-memory staging buffer: byte stores as st.shared (a plain char* that may also point to global memory compiles
+// to generic stores, which is what the formatting code would otherwise use for every character).
+struct SmemSink {
+    uint32_t a;               // address in the shared window
+    struct Ref { uint32_t a; __device__ __forceinline__ void operator=(char c) const { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"((int)c)); } };
+    struct Win { uint32_t a; __device__ __forceinline__ Ref operator[](int i) const { return Ref{a + (uint32_t)i}; } };
+    __device__ __forceinline__ void put(char c) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"((int)c)); ++a; }
+    __device__ __forceinline__ void skip(int) {}
+    __device__ __forceinline__ Win reserve(int n) { Win w{a}; a += (uint32_t)n; return w; }
+    static constexpr bool kCounts = false;
+    static constexpr bool kRandomAccess = true;
+};
+#endif
+
 template <class Sink> SGP_HD void put_str(Sink& s, const char* z) { while (*z) s.put(*z++); }
 // String literal: the length is a compile-time constant (the size pass adds it in one step) and the unrolled stores carry the
 // characters as immediates — no per-character load, test and branch as in put_str.
@@ -325,7 +340,7 @@ SGP_HD int dec_len_u32(uint32_t v) {
 // n decimal digits of v (v < 10^n, n <= 10), most significant first, 32-bit arithmetic only
 template <class Sink> SGP_HD void put_u32_digits(Sink& s, uint32_t v, int n) {
     if (Sink::kRandomAccess) {
-        char* d = s.reserve(n);
+        auto d = s.reserve(n);
         for (int i = n - 1; i >= 0; --i) { uint32_t q = v / 10u; d[i] = (char)('0' + (v - q * 10u)); v = q; }
         return;
     }
@@ -356,7 +371,7 @@ template <class Sink> SGP_HD void put_digits(Sink& s, uint64_t f, int n, int fro
     uint32_t l1 = (uint32_t)(hi % 1000000000ull);
     if (Sink::kRandomAccess) {
         // digit at position pos (0 = most significant) goes to d[pos - from] when from <= pos < to
-        char* d = s.reserve(to - from);
+        auto d = s.reserve(to - from);
         int pos = n - 1;
         for (int i = 0; i < 9 && pos >= from; ++i, --pos) { uint32_t q = l0 / 10u; if (pos < to) d[pos - from] = (char)('0' + (l0 - q * 10u)); l0 = q; }
         if (n > 9) { pos = n - 10; for (int i = 0; i < 9 && pos >= from; ++i, --pos) { uint32_t q = l1 / 10u; if (pos < to) d[pos - from] = (char)('0' + (l1 - q * 10u)); l1 = q; } }

@@ -238,7 +238,7 @@ __device__ unsigned long long emit_pieces(int n_pieces, char* base, char* stage,
             char* dst = base + running;
             const int mis = (int)(reinterpret_cast<unsigned long long>(dst) & 15ull);
             if (total + 16 <= (unsigned)kStageBytes) {
-                if (len) { MemSink m{stage + mis + off}; piece(m, i); }
+                if (len) { SmemSink m{(uint32_t)__cvta_generic_to_shared(stage) + (uint32_t)mis + off}; piece(m, i); }
                 __syncwarp();
                 flush_stage(stage, mis, dst, total);
                 __syncwarp();
