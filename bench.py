@@ -38,8 +38,8 @@ ALG_IMAD_INST_PER_VERTEX = 20.0
 ALG_ALU_INST_PER_VERTEX = 44.0
 # DRAM traffic per replicate from the `ncu --set full` capture profiles/r01_c2_full_metrics.csv (200 000 replicates per launch):
 # dram__bytes_read.sum + dram__bytes_write.sum of k_bd_find_single, and of the four k_emit<write> launches together.
-NCU_FIND_DRAM_BYTES_PER_REPLICATE = (0.008984 + 0.076104) * 1e9 / 200000
-NCU_EMIT_WRITE_DRAM_BYTES_PER_REPLICATE = (4.995798 + 2.746934 + 4.501152 + 2.103177 + 0.048685 + 0.015023 + 0.052106 + 0.010014) * 1e9 / 200000
+NCU_FIND_DRAM_BYTES_PER_REPLICATE = (0.008465 + 0.092016) * 1e9 / 200000
+NCU_EMIT_WRITE_DRAM_BYTES_PER_REPLICATE = (5.014102 + 2.810351 + 4.534508 + 2.139986 + 0.050887 + 0.015014 + 0.054069 + 0.010760) * 1e9 / 200000
 
 
 def clocks_sampler(stop, rows, gpu_index):
