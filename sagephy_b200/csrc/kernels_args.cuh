@@ -47,6 +47,7 @@ struct BuildArgs {
     RepInfo* info;
     const long long* node_off;   // exclusive scan of n_pool
     unsigned long long* work_counter;   // build slots are claimed dynamically, like replicates in the find kernel
+    const long long* n_big;      // order[0 .. *n_big) are the replicates with unusually large trees
     const long long* order;      // slot t builds replicate order[t] (largest trees first: their serial latency is the kernel's tail); nullptr = identity
     Node* nodes;                 // arena
     int32_t* aux; long long aux_stride;    // 4 int arrays of length total_nodes: aux + k*aux_stride

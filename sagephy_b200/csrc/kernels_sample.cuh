@@ -120,7 +120,16 @@ __global__ void __launch_bounds__(128) k_build_general(BuildArgs a) {
             const long long t = (long long)atomicAdd(a.work_counter, 1ULL);
             if (t >= a.n) exhausted = true;
             else {
-                r = a.order ? a.order[t] : t;
+                if (!a.order) r = t;
+                else {
+                    // large trees are started early but one per warp: 32 of them in one warp would queue up behind each other's
+                    // cooperative recipient draws for their whole (long) life
+                    long long nb = *a.n_big; if (nb * 32 > a.n) nb = 0;
+                    const long long w = t >> 5;
+                    if ((t & 31) == 0 && w < nb) r = a.order[w];
+                    else { const long long before = (t + 31) >> 5 < nb ? (t + 31) >> 5 : nb; r = a.order[nb + (t - before)]; }
+                    if (nb == 0) r = a.order[t];
+                }
                 const RepInfo& inf = a.info[r];
                 if (inf.status == REP_OK) {
                     const long long off = a.node_off[r];
