@@ -55,6 +55,34 @@ def clocks_sampler(stop, rows, gpu_index):
         stop.wait(0.2)
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pins this rank's threads to the CPU cores of the NUMA node its GPU hangs off, so that the pinned host buffers of the
+    end-to-end pipeline are allocated (first touch) next to the GPU's PCIe root port. Best effort; returns the node or None."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id if hasattr(torch.cuda.get_device_properties(gpu_index), "pci_bus_id") else None
+        if bus is None:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)], capture_output=True, text=True, timeout=5).stdout.strip()
+            bus = out
+        bus = str(bus).lower()
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                      # nvidia-smi prints an 8-digit domain, sysfs uses 4
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def summarise_clocks(rows):
     if not rows:
         return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
@@ -135,6 +163,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = sg.Context(local)
@@ -260,7 +289,7 @@ def main():
             "vertices_executed_per_tree": verts_executed / max(trees, 1),
             "out_bytes_per_tree": out_bytes / max(trees, 1), "n_failed": int(total.n_failed),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": int(float(eo[1]) / e_steps / world),
-                    "replicates_per_gpu_per_step": ne, "steps": e_steps},
+                    "replicates_per_gpu_per_step": ne, "steps": e_steps, "host_numa_node": numa_node},
             "roofline": {"bound": "issue", "kernel": "k_bd_find", "achieved": gverts, "peak": peak_gverts, "unit": "Gvertex/s", "frac": gverts / peak_gverts,
                          "traffic": NCU_FIND_DRAM_BYTES_PER_REPLICATE * n, "traffic_unit": "bytes per launch (ncu, scaled from a 200k-replicate capture)",
                          "alg_inst_per_vertex": {"fp64": ALG_FP64_INST_PER_VERTEX, "imad_wide": ALG_IMAD_INST_PER_VERTEX, "alu": ALG_ALU_INST_PER_VERTEX},
