@@ -460,7 +460,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         a.scratch_used = scratch_used.p; a.ev_base = d_ev_base.p; a.ev_off = d_ev_off.p; a.ev_list = d_ev_list.p;
         // a lane builds its tree alone, so the largest trees set the kernel's tail: start them first
         DevBuf<long long> order, n_sel; DevBuf<char> ptmp;
-        if (n >= 4096 && !getenv("SGP_NO_ORDER")) {
+        if (n >= 4096) {
             order.alloc((size_t)n); n_sel.alloc(1);
             cub::CountingInputIterator<long long> ids(0);
             PoolAbove big{pool.p, 4 * (total_nodes / n) + 64};
