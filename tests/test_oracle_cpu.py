@@ -259,3 +259,35 @@ def test_unpack_batch_tool_splits_packed_streams(tmp_path):
     assert not (tmp_path / "run_11.pruned.tree").exists()
     assert (tmp_path / "run_11.info").read_bytes() == notes[1]          # HostTreeGen's failure note goes to <prefix>.info
     assert (tmp_path / "run_12.pruned.info").read_bytes() == notes[2]
+
+
+def test_autocorrelated_rate_models_have_the_documented_means():
+    # closed-form pins for the oracle's restatement of the AC models (apps/SaGePhy/AC*RateModel.java):
+    #   ACTK98 (corrected):  E[r(x) | r(parent)] = r(parent)              -> E[r] = start rate everywhere
+    #   ACRY07:              same martingale property for mid-point and vertex rates
+    #   ACABY02:             r(x) ~ Exp(mean r(parent))                   -> E[r] = start rate
+    #   ACLBPL07 (CIR):      mean reverts to mu: E[r_t] = mu + (r0 - mu) e^{-theta t}
+    import re
+    tree = "((a:0.3,b:0.3):0.4,c:0.7):0.2;"           # vertex ids (post-order): a=0 b=1 ab=2 c=3 root=4
+    n = 4000
+
+    def rates(model_args):
+        out = np.empty((n, 5))
+        for i in range(n):
+            r = oracle_run("BranchRelaxer", ["-s", str(1000 + i), "-o", "/x", tree] + model_args)
+            info = r["files"]["/x.info"].decode()
+            out[i] = [float(v) for v in re.search(r"Rates:\t\[(.*)\]", info).group(1).split(", ")]
+        return out
+
+    for args, tol in ((["ACTK98", "1.5", "0.5"], 0.04), (["ACRY07", "1.5", "0.5"], 0.04), (["ACABY02", "1.5"], 0.12)):
+        r = rates(args)
+        for x in (0, 2, 3):
+            assert abs(r[:, x].mean() - 1.5) < tol * 1.5 * (3 if args[0] == "ACABY02" and x == 0 else 1), (args, x, r[:, x].mean())
+    if True:
+        start, mu, theta, sigma = 0.5, 1.2, 4.0, 0.5
+        r = rates(["ACLBPL07", str(start), str(mu), str(theta), str(sigma)])
+        # branch rate = time average of the instantaneous rate over the branch; stem [0, 0.2], then c on [0.2, 0.9]
+        def avg(t0, t1):
+            return mu + (start - mu) * (math.exp(-theta * t0) - math.exp(-theta * t1)) / (theta * (t1 - t0))
+        assert abs(r[:, 4].mean() - avg(0.0, 0.2)) < 0.02, (r[:, 4].mean(), avg(0.0, 0.2))
+        assert abs(r[:, 3].mean() - avg(0.2, 0.9)) < 0.02, (r[:, 3].mean(), avg(0.2, 0.9))
