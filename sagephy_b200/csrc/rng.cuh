@@ -79,8 +79,11 @@ struct PhiloxStream {
         k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); rep_lo = (uint32_t)rep; rep_hi = (uint32_t)(rep >> 32);
         attempt = attempt_; block = 0; have = 0;
     }
+    // out of line: the general engine draws at dozens of sites, and a Philox block inlined at each of them (~60 instructions) made
+    // its kernels miss the instruction cache
+    SGP_HD_NOINL void refill() { buf = philox4x32_10(block++, attempt, rep_lo, rep_hi, k0, k1); have = 4; }
     SGP_HD uint32_t next_word() {
-        if (have == 0) { buf = philox4x32_10(block++, attempt, rep_lo, rep_hi, k0, k1); have = 4; }
+        if (have == 0) refill();
         uint32_t r = have == 4 ? buf.x : have == 3 ? buf.y : have == 2 ? buf.z : buf.w;
         --have;
         return r;
