@@ -120,7 +120,7 @@ struct MtStream {
     uint64_t drawn;    // words drawn so far (lets the build pass fast-forward to the accepted attempt)
     SGP_HD uint32_t& at(int i) { return mt[(size_t)i * stride]; }
 
-    SGP_HD void seed(const uint32_t key[4]) {
+    SGP_HD_NOINL void seed(const uint32_t key[4]) {
         at(0) = 19650218u;
         for (int i = 1; i < 624; ++i) { uint32_t p = at(i - 1); at(i) = 1812433253u * (p ^ (p >> 30)) + (uint32_t)i; }
         int i = 1, j = 0;
@@ -140,7 +140,7 @@ struct MtStream {
         at(0) = 0x80000000u;
         idx = 624; drawn = 0;
     }
-    SGP_HD void twist() {
+    SGP_HD_NOINL void twist() {        // out of line for the same reason as PhiloxStream::refill
         int kk; uint32_t y;
         for (kk = 0; kk < 624 - 397; ++kk) { y = (at(kk) & 0x80000000u) | (at(kk + 1) & 0x7fffffffu); at(kk) = at(kk + 397) ^ (y >> 1) ^ ((y & 1) ? 0x9908b0dfu : 0u); }
         for (; kk < 623; ++kk) { y = (at(kk) & 0x80000000u) | (at(kk + 1) & 0x7fffffffu); at(kk) = at(kk + (397 - 624)) ^ (y >> 1) ^ ((y & 1) ? 0x9908b0dfu : 0u); }
