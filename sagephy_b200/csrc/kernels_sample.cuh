@@ -29,8 +29,10 @@ __device__ __forceinline__ int engine_step(EngineState<DOMAIN>& S, RNG& rng, con
 
 template <bool REPLAY, bool DOMAIN>
 __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
+    __shared__ double2 s_logtab[128];
+    load_log_table(s_logtab);
     const int worker = blockIdx.x * blockDim.x + threadIdx.x;
-    SimWork W;
+    SimWork W; W.logtab = s_logtab;
     W.nodes = a.scratch_nodes + (size_t)worker * a.cap; W.cap = a.cap;
     W.queue = a.scratch_queue + (size_t)worker * a.cap; W.pend = a.scratch_pend + (size_t)worker * a.cap;
     const int mark_n = DOMAIN ? a.max_gene_nv : a.H.nV, cnt_n = DOMAIN ? a.max_gene_nv : a.H.nLeaves;
@@ -102,8 +104,10 @@ __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
 
 template <bool REPLAY, bool DOMAIN>
 __global__ void __launch_bounds__(128) k_build_general(BuildArgs a) {
+    __shared__ double2 s_logtab[128];
+    load_log_table(s_logtab);
     const int worker = blockIdx.x * blockDim.x + threadIdx.x;
-    SimWork W; W.nodes = nullptr; W.cap = 0; W.queue = nullptr; W.pend = nullptr;
+    SimWork W; W.logtab = s_logtab; W.nodes = nullptr; W.cap = 0; W.queue = nullptr; W.pend = nullptr;
     const int mark_n = DOMAIN ? a.max_gene_nv : a.H.nV;
     W.marks = a.scratch_marks + (size_t)worker * mark_n; W.leaf_cnt = nullptr; W.mark_gen = 0;
     for (int i = 0; i < mark_n; ++i) W.marks[i] = 0;

@@ -19,13 +19,16 @@ struct DomainEnv {
 };
 
 template <class RNG>
-__device__ __forceinline__ VertexDraw draw_vertex_domain(RNG& rng, const SimParams& P, const DomainEnv& E, const DevHost& G, const MathTables& T, int X, double start) {
+__device__ __forceinline__ VertexDraw draw_vertex_domain(RNG& rng, const SimParams& P, const DomainEnv& E, const DevHost& G, const MathTables& T, int X, double start, const double2* tab) {
     VertexDraw d;
     const bool isRoot = G.parent[X] < 0;
     double sum = isRoot ? XADD(P.lambda, P.mu) : XADD(XADD(P.lambda, P.mu), P.tau);
     if (sum == 0.0) sum = 1e-48;
     const double low = G.vtime[X];
-    double bt = XDIV(-jlog(XSUB(1.0, rng.next_double())), sum);
+    const double u1 = rng.next_double();
+    double bt;          // see draw_vertex (sim.cuh)
+    if constexpr (std::is_same<RNG, PhiloxStream>::value) bt = __dmul_rn(-log_unit(XSUB(1.0, u1), tab), __ddiv_rn(1.0, sum));
+    else bt = XDIV(-jlog(XSUB(1.0, u1)), sum);
     double et = XSUB(start, bt);
     if (et <= low) {
         et = low;
@@ -236,7 +239,7 @@ __device__ int domain_step(DomainState& S, RNG& rng, const SimParams& P, const D
     }
     if (S.need_first || (S.stage == 2 && S.need_victim)) return -1;
     // ---- the single vertex-creation site
-    const VertexDraw d = draw_vertex_domain(rng, P, E, E.genes[S.g], T, S.X, S.t);
+    const VertexDraw d = draw_vertex_domain(rng, P, E, E.genes[S.g], T, S.X, S.t, W.logtab);
     const int idx = new_node(W, S.n, d, S.X);
     if (idx < 0) return REP_NODE_OVERFLOW;
     W.nodes[idx].gtree = (int16_t)S.g;
