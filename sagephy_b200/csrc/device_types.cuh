@@ -74,6 +74,10 @@ struct SimParams {
     int32_t do_gene_birth, ishost;
     int32_t min_leaves, max_leaves, minper, maxper, max_attempts;
     int32_t n_sizes;         // > 0: -sizes list present
+    // createGuestVertex's rate sums and event thresholds for the root arc ([0]) and every other arc ([1]): sum, 1/sum,
+    // P(dup) boundary and P(loss) boundary. IEEE division is correctly rounded on host and device alike, so taking them from
+    // here instead of dividing per vertex does not change a bit (GuestTreeInHostTreeCreator.java:372-412).
+    double sum[2], inv_sum[2], thr_dup[2], thr_loss[2];
 };
 
 }  // namespace sgp

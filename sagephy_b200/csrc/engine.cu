@@ -322,6 +322,12 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     P.gene_birth = cfg.P.gene_birth; P.bias = cfg.P.bias; P.do_gene_birth = cfg.P.do_gene_birth; P.ishost = cfg.P.ishost;
     P.min_leaves = cfg.P.min_leaves; P.max_leaves = cfg.P.max_leaves; P.minper = cfg.P.minper; P.maxper = cfg.P.maxper; P.max_attempts = cfg.P.max_attempts;
     P.n_sizes = (int)cfg.sizes.size();
+    for (int k = 0; k < 2; ++k) {
+        double sum = k == 0 ? P.lambda + P.mu : (P.lambda + P.mu) + P.tau; if (sum == 0.0) sum = 1e-48;
+        P.sum[k] = sum; P.inv_sum[k] = 1.0 / sum;
+        P.thr_dup[k] = k == 0 ? P.lambda / sum : (P.mu + P.tau) / sum;      // root arc: dup if U < lambda/sum; others: dup if U >= (mu+tau)/sum
+        P.thr_loss[k] = P.mu / sum;
+    }
     const unsigned long long seed = (unsigned long long)cfg.seed;
 
     HostOnDevice hd; hd.upload(cfg.host);

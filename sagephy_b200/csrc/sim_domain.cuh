@@ -22,12 +22,12 @@ template <class RNG>
 __device__ __forceinline__ VertexDraw draw_vertex_domain(RNG& rng, const SimParams& P, const DomainEnv& E, const DevHost& G, const MathTables& T, int X, double start, const double2* tab) {
     VertexDraw d;
     const bool isRoot = G.parent[X] < 0;
-    double sum = isRoot ? XADD(P.lambda, P.mu) : XADD(XADD(P.lambda, P.mu), P.tau);
-    if (sum == 0.0) sum = 1e-48;
+    const int ks = isRoot ? 0 : 1;
+    const double sum = P.sum[ks];
     const double low = G.vtime[X];
     const double u1 = rng.next_double();
     double bt;          // see draw_vertex (sim.cuh)
-    if constexpr (std::is_same<RNG, PhiloxStream>::value) bt = __dmul_rn(-log_unit(XSUB(1.0, u1), tab), __ddiv_rn(1.0, sum));
+    if constexpr (std::is_same<RNG, PhiloxStream>::value) bt = __dmul_rn(-log_unit(XSUB(1.0, u1), tab), P.inv_sum[ks]);
     else bt = XDIV(-jlog(XSUB(1.0, u1)), sum);
     double et = XSUB(start, bt);
     if (et <= low) {
@@ -37,9 +37,9 @@ __device__ __forceinline__ VertexDraw draw_vertex_domain(RNG& rng, const SimPara
         d.epoch = G.v2e[X];
     } else {
         const double rnd = rng.next_double();
-        if (isRoot) d.event = (rnd < XDIV(P.lambda, sum)) ? EV_DUPLICATION : EV_LOSS;
-        else if (rnd >= XDIV(XADD(P.mu, P.tau), sum)) d.event = EV_DUPLICATION;
-        else if (rnd < XDIV(P.mu, sum)) d.event = EV_LOSS;
+        if (isRoot) d.event = (rnd < P.thr_dup[0]) ? EV_DUPLICATION : EV_LOSS;
+        else if (rnd >= P.thr_dup[1]) d.event = EV_DUPLICATION;
+        else if (rnd < P.thr_loss[1]) d.event = EV_LOSS;
         else {
             const double trn = rng.next_double(), trn_gen = rng.next_double(), trn_spe = rng.next_double();
             d.event = (uint8_t)((trn < P.theta ? EV_RT_GG_SS : EV_AT_GG_SS) + (trn_gen < E.inter_gene ? 2 : 0) + (trn_spe < E.inter_species ? 1 : 0));
