@@ -4,7 +4,7 @@
 // {additive, replacing} x {intra-, inter-gene} x {intra-, inter-species} x coin; folded into one parameterised path here),
 // findVertex :948-964, swap :984-1002, sampleInterGeneArc :1004-1033, createGuestVertex :1042-1120, and the `-all` /
 // per-leaf acceptance of GuestTreeMachina.unprunedIsOK (apps/SaGePhy/GuestTreeMachina.java:124-169).
-// Same single-creation-site state machine as simulate_attempt (sim.cuh). Draw order per transfer (differs from
+// Same single-creation-site state machine and warp-cooperative scheme as sim_step (sim.cuh). Draw order per transfer (differs from
 // GuestTreeGen): coin -> first recipient -> staying child -> further recipients (replacing only) -> moving child.
 #pragma once
 #include "sim.cuh"
