@@ -291,3 +291,23 @@ def test_autocorrelated_rate_models_have_the_documented_means():
             return mu + (start - mu) * (math.exp(-theta * t0) - math.exp(-theta * t1)) / (theta * (t1 - t0))
         assert abs(r[:, 4].mean() - avg(0.0, 0.2)) < 0.02, (r[:, 4].mean(), avg(0.0, 0.2))
         assert abs(r[:, 3].mean() - avg(0.2, 0.9)) < 0.02, (r[:, 3].mean(), avg(0.2, 0.9))
+
+
+def test_domain_tree_gen_on_one_gene_tree_matches_guest_tree_gen(tmp_path):
+    # Two independent restatements (DomainTreeInHostTreeCreator vs GuestTreeInHostTreeCreator) of the same process: with a single
+    # gene tree and intra-gene transfers only, a domain tree evolves inside that gene tree exactly as a gene tree evolves inside a
+    # species tree (both species-blind here: one HOST tag). The random streams are consumed differently (first_guest draw, three
+    # extra uniforms per transfer, recipient before staying child), so only distributions can agree.
+    from scipy import stats
+    species = "((A:0.6,B:0.6):0.4,C:1.0):0.1;"
+    # zero stem: GuestTreeGen discards the stem of its host tree, DomainTreeGen lets the domain evolve along the gene tree's stem
+    gene = "(((a:0.1,b:0.1):0.5,(c:0.3,d:0.3):0.3):0.4,((e:0.2,f:0.2):0.6,(g:0.5,h:0.5):0.3):0.2):0.0;"
+    gd = tmp_path / "genes"; gd.mkdir()
+    (gd / "g0.tree").write_text(gene + "\n")
+    n = 4000
+    common = ["-min", "1", "-max", "100000", "-minper", "0", "-maxper", "100000", "-db", "none"]
+    _, g = oracle_batch("GuestTreeGen", ["-s", "1"] + common + [gene, "0.6", "0.4", "0.5", "x"], 0, n)
+    _, d = oracle_batch("DomainTreeGen", ["-s", "900001"] + common + ["-ig", "0.0", "-is", "0.0", species, str(gd), "0.6", "0.4", "0.5", "x"], 0, n)
+    assert (g[:, 1] == 0).all() and (d[:, 1] == 0).all()
+    for col in (0, 4, 6, 7):       # attempts, sampled leaves, total branch time, vertices created
+        assert stats.ks_2samp(g[:, col], d[:, col]).pvalue > 0.001, (col, g[:, col].mean(), d[:, col].mean())
