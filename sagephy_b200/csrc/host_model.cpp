@@ -195,6 +195,9 @@ void HostModel::build(const FlatTree& t, const std::string* name, const double* 
         low_vertex = par; t_lo = t_up; ++e;
     }
     t_up = vt_raw[root] + at_raw[root];
+    // A gene tree read without a stem length has a NaN top time (DomainTreeGen does not override it as GuestTreeGen does for its
+    // host): with it no lineage ever reaches a vertex and every attempt grows until memory runs out. Refuse instead.
+    if (std::isnan(t_up)) throw SgpError("Newick tree has no usable top time (stem length missing on the root)");
     if (t_up + kMinSplice < t_lo) t_up = t_lo + kMinSplice;
     close_epoch(e, t_lo, t_up);
     v2e[low_vertex] = e;
