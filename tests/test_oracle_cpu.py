@@ -4,6 +4,8 @@ import ctypes as C
 import math
 import os
 import re
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -311,3 +313,28 @@ def test_domain_tree_gen_on_one_gene_tree_matches_guest_tree_gen(tmp_path):
     assert (g[:, 1] == 0).all() and (d[:, 1] == 0).all()
     for col in (0, 4, 6, 7):       # attempts, sampled leaves, total branch time, vertices created
         assert stats.ks_2samp(g[:, col], d[:, col]).pvalue > 0.001, (col, g[:, col].mean(), d[:, col].mean())
+
+
+def test_committed_bench_line_follows_the_contract():
+    # profiles/r01_bench_final.json is the line `python bench.py` printed on a B200 at the final commit of the round
+    import json
+    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_final.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+              "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert k in d, k
+    assert d["config"]["workload"].startswith("C2") and d["scaling"] == "weak" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"]) and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"]) and 0 < d["roofline"]["frac"] < 1
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] in ("port", "reference")
+    assert d["gpu_launches"] > 0 and d["warmup"] >= 3
+    assert not (set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"})
+    r = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_reference_arm.json")))
+    assert r["impl"] == "reference" and r["metric"] == d["metric"] and r["unit"] == d["unit"] and r["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_launch_list_summary_tool():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "summarize_launches.py"), os.path.join(ROOT, "profiles", "r01_launches_bench_c2.csv")],
+                         capture_output=True, text=True, check=True).stdout
+    first = out.splitlines()[1]
+    assert "k_bd_find_single" in first and float(first.split()[-1].rstrip("%")) > 50      # the sampler dominates the step
