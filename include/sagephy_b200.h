@@ -165,6 +165,14 @@ sgp_status sgp_probe_mt(sgp_context* ctx, int64_t seed, int64_t n_words, uint32_
 /* Issue-rate microbenchmarks (roofline denominators for the sampler), giga warp-instructions per second, whole chip:
  * independent DFMA chains, independent IMAD chains, and an IMAD + SHF + LOP3 mix (what Philox is made of). */
 sgp_status sgp_probe_issue_peaks(sgp_context* ctx, double* dfma_ginst, double* imad_ginst, double* mixed_int_ginst);
+/* Host-side table preparation ("K0", no GPU needed): parses a Newick host tree as GuestTreeGen would (stem override as given,
+ * NaN = keep the tree's own) and returns the tables the kernels consume, for CPU tests of the host logic.
+ * Sizes: parent/left/right/v2e/vtime [nV], ep_lo/ep_up [nE], ep_off [nE+1], ep_arcs [ep_off[nE]], lca_time [nV*nV].
+ * Any output pointer may be NULL; returns SGP_ERR_INVALID_ARGUMENT when a capacity (in elements) is too small. */
+sgp_status sgp_probe_host_model(const char* newick, double stem, int32_t* n_vertices, int32_t* n_epochs,
+                                int32_t* parent, int32_t* left, int32_t* right, int32_t* v2e, double* vtime, int32_t cap_v,
+                                double* ep_lo, double* ep_up, int32_t* ep_off, int32_t cap_e, int32_t* ep_arcs, int32_t cap_arcs,
+                                double* lca_time, int64_t cap_lca, char* error, int32_t error_cap);
 
 #ifdef __cplusplus
 }

@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = (
     "sgp_batch_status", "sgp_batch_attempts", "sgp_batch_sampled_leaves", "sgp_batch_root_times", "sgp_batch_total_times",
     "sgp_batch_event_counts", "sgp_batch_stdout", "sgp_batch_stderr", "sgp_batch_out_prefix", "sgp_batch_summary",
     "sgp_batch_timings", "sgp_batch_write_files", "sgp_batch_write_files_layout", "sgp_batch_free", "sgp_probe_double_to_string", "sgp_probe_math",
-    "sgp_probe_mt", "sgp_probe_issue_peaks")
+    "sgp_probe_mt", "sgp_probe_issue_peaks", "sgp_probe_host_model")
 
 
 class BatchOpts(C.Structure):

@@ -246,4 +246,25 @@ sgp_status sgp_probe_issue_peaks(sgp_context* ctx, double* dfma, double* imad, d
     try { ctx->ctx->probe_issue(dfma, imad, ddep); return SGP_OK; } catch (std::exception& e) { ctx->last_error = e.what(); return SGP_ERR_NO_DEVICE; }
 }
 
+sgp_status sgp_probe_host_model(const char* newick, double stem, int32_t* n_vertices, int32_t* n_epochs,
+                                int32_t* parent, int32_t* left, int32_t* right, int32_t* v2e, double* vtime, int32_t cap_v,
+                                double* ep_lo, double* ep_up, int32_t* ep_off, int32_t cap_e, int32_t* ep_arcs, int32_t cap_arcs,
+                                double* lca_time, int64_t cap_lca, char* error, int32_t error_cap) {
+    if (!newick) return SGP_ERR_INVALID_ARGUMENT;
+    try {
+        HostModel h;
+        const bool keep = stem != stem;
+        h.build(parse_newick(newick), nullptr, keep ? nullptr : &stem, lca_time != nullptr);
+        if (n_vertices) *n_vertices = h.nV;
+        if (n_epochs) *n_epochs = h.nE;
+        auto copy = [](auto* dst, const auto& src, long long cap) { if (!dst) return true; if ((long long)src.size() > cap) return false; for (size_t i = 0; i < src.size(); ++i) dst[i] = src[i]; return true; };
+        bool ok = copy(parent, h.parent, cap_v) && copy(left, h.left, cap_v) && copy(right, h.right, cap_v) && copy(v2e, h.v2e, cap_v) && copy(vtime, h.vtime, cap_v);
+        ok = ok && copy(ep_lo, h.ep_lo, cap_e) && copy(ep_up, h.ep_up, cap_e) && copy(ep_off, h.ep_off, (long long)cap_e + 1) && copy(ep_arcs, h.ep_arcs, cap_arcs) && copy(lca_time, h.lca_time, cap_lca);
+        return ok ? SGP_OK : SGP_ERR_INVALID_ARGUMENT;
+    } catch (std::exception& e) {
+        if (error && error_cap > 0) std::snprintf(error, (size_t)error_cap, "%s", e.what());
+        return SGP_ERR_PARSE;
+    }
+}
+
 }  // extern "C"

@@ -338,3 +338,69 @@ def test_launch_list_summary_tool():
                          capture_output=True, text=True, check=True).stdout
     first = out.splitlines()[1]
     assert "k_bd_find_single" in first and float(first.split()[-1].rstrip("%")) > 50      # the sampler dominates the step
+
+
+def _random_ultrametric_newick(rng, n_leaves):
+    """Random binary ultrametric tree (coalescent-like heights), Newick with branch lengths and a stem."""
+    nodes = [(f"L{i}", 0.0) for i in range(n_leaves)]
+    t = 0.0
+    while len(nodes) > 1:
+        t += float(rng.exponential(1.0 / (len(nodes) * (len(nodes) - 1))))
+        i = int(rng.integers(len(nodes) - 1))            # adjacent pairs keep the tree planar-consistent with its leaf order
+        (a, ta), (b, tb) = nodes[i], nodes[i + 1]
+        nodes[i:i + 2] = [(f"({a}:{t - ta!r},{b}:{t - tb!r})", t)]
+    return nodes[0][0] + ":0.05;"
+
+
+def test_host_tables_of_the_product_without_a_gpu():
+    # K0 (host_model.cpp) through sgp_probe_host_model: the LCA-time matrix against a naive ancestor walk, and the epoch
+    # tables against their defining properties (RBTreeEpochDiscretiser.java:146-221): epochs partition time in ascending order,
+    # epoch e holds the arcs that are contemporaries during it, a vertex's epoch starts at the vertex's time.
+    lib = C.CDLL(os.path.join(ROOT, "sagephy_b200", "libsagephy_b200.so"))
+    f = lib.sgp_probe_host_model
+    f.restype = C.c_int
+    rng = np.random.default_rng(12)
+    for n_leaves in (2, 3, 8, 37, 150):
+        nw = _random_ultrametric_newick(rng, n_leaves)
+        nV, nE = 2 * n_leaves - 1, n_leaves
+        i32 = lambda k: np.zeros(k, dtype=np.int32)
+        parent, left, right, v2e = i32(nV), i32(nV), i32(nV), i32(nV)
+        vtime, ep_lo, ep_up, ep_off = np.zeros(nV), np.zeros(nE), np.zeros(nE), i32(nE + 1)
+        ep_arcs, lca = i32(nE * (nE + 1) // 2 + 8), np.zeros(nV * nV)
+        nv_o, ne_o = C.c_int32(), C.c_int32()
+        err = C.create_string_buffer(256)
+        P = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = f(nw.encode(), C.c_double(0.0), C.byref(nv_o), C.byref(ne_o), P(parent), P(left), P(right), P(v2e), P(vtime), C.c_int32(nV),
+               P(ep_lo), P(ep_up), P(ep_off), C.c_int32(nE), P(ep_arcs), C.c_int32(len(ep_arcs)), P(lca), C.c_int64(nV * nV), err, C.c_int32(256))
+        assert rc == 0, err.value
+        assert nv_o.value == nV and ne_o.value == nE
+        root = int(np.where(parent < 0)[0][0])
+        # naive LCA
+        def anc(v):
+            out = [v]
+            while parent[out[-1]] >= 0:
+                out.append(int(parent[out[-1]]))
+            return out
+        chains = [anc(v) for v in range(nV)]
+        for x in range(nV):
+            sx = set(chains[x])
+            for y in range(x, nV):
+                a = next(v for v in chains[y] if v in sx)
+                assert lca[x * nV + y] == vtime[a] == lca[y * nV + x], (n_leaves, x, y)
+        # epochs
+        assert (np.diff(ep_up) >= 0).all() and (ep_lo[1:] == ep_up[:-1]).all() and ep_lo[0] == 0.0
+        assert ep_off[0] == 0 and (np.diff(ep_off) == np.arange(nE, 0, -1)).all()            # one arc fewer per epoch, 1 arc (the stem) at the top
+        for v in range(nV):
+            assert vtime[v] == ep_lo[v2e[v]]
+        for e in range(nE):
+            arcs = ep_arcs[ep_off[e]:ep_off[e + 1]]
+            for x in arcs:          # arc x = (x, parent(x)) spans the epoch
+                top = vtime[parent[x]] if parent[x] >= 0 else ep_up[-1]
+                assert vtime[x] <= ep_lo[e] and top >= ep_up[e] - 1e-12, (e, x)
+        assert list(ep_arcs[ep_off[nE - 1]:ep_off[nE]]) == [root]
+    # a tree without a stem keeps working for GuestTreeGen-style reading (stem override 0 -> 1e-64) ...
+    rc = f(b"((a:1,b:1):1,c:2);", C.c_double(0.0), C.byref(nv_o), C.byref(ne_o), *([None] * 5), C.c_int32(0), None, None, None, C.c_int32(0), None, C.c_int32(0), None, C.c_int64(0), err, C.c_int32(256))
+    assert rc == 0 and nv_o.value == 5
+    # ... and is refused when the stem is taken from the tree (DomainTreeGen's gene trees) and is missing there
+    rc = f(b"((a:1,b:1):1,c:2);", C.c_double(float("nan")), C.byref(nv_o), C.byref(ne_o), *([None] * 5), C.c_int32(0), None, None, None, C.c_int32(0), None, C.c_int32(0), None, C.c_int64(0), err, C.c_int32(256))
+    assert rc == 3 and b"top time" in err.value
