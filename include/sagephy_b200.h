@@ -161,7 +161,15 @@ void sgp_batch_free(sgp_batch* b);
 /* Probes used by the parity tests: run the device implementations of the Java-exact primitives on `n` inputs. */
 sgp_status sgp_probe_double_to_string(sgp_context* ctx, const double* v, int64_t n, char* out /* n*32 bytes, NUL padded */);
 sgp_status sgp_probe_math(sgp_context* ctx, int fn /* 0 log, 1 log10, 2 exp, 3 round8, 4 normal quantile, 5 pow(x,0.37), 6 chi2 quantile k=4, 7 chi2 quantile k=0.25, 8 pow(e,x), 9 throughput-mode log on (0,1] */, const double* v, int64_t n, double* out);
-sgp_status sgp_probe_mt(sgp_context* ctx, int64_t seed, int64_t n_words, uint32_t* out_words);
+/* MT19937 words of replicate `replicate_index` of a run seeded with the decimal integer `seed_decimal` (any size; the reference
+ * parses it with java.math.BigInteger and keeps the low 16 bytes: math/PRNG.java:29-37,58-60; replicate i uses seed + i). */
+sgp_status sgp_probe_mt(sgp_context* ctx, const char* seed_decimal, int64_t replicate_index, int64_t n_words, uint32_t* out_words);
+/* Host-side seed logic (no GPU needed): the four big-endian key words MT19937 is seeded with for seed + replicate_index, and the
+ * decimal text of seed + replicate_index as it appears in the "Arguments:" line of replay-mode .info output. */
+sgp_status sgp_probe_seed(const char* seed_decimal, int64_t replicate_index, uint32_t key_out[4], char* decimal_out, int32_t decimal_cap);
+/* Philox4x32-10 blocks for n (counter, key) pairs: variant 0 = key schedule computed per block, 1 = precomputed round keys (the
+ * sampler's form). ctx == NULL runs the host build of the same source (no GPU needed). Pinned by the Random123 known answers. */
+sgp_status sgp_probe_philox(sgp_context* ctx, int variant, const uint32_t* ctr /* n x 4 */, const uint32_t* key /* n x 2 */, int64_t n, uint32_t* out /* n x 4 */);
 /* Issue-rate microbenchmarks (roofline denominators for the sampler), giga warp-instructions per second, whole chip:
  * independent DFMA chains, independent IMAD chains, and an IMAD + SHF + LOP3 mix (what Philox is made of). */
 sgp_status sgp_probe_issue_peaks(sgp_context* ctx, double* dfma_ginst, double* imad_ginst, double* mixed_int_ginst);

@@ -12,37 +12,63 @@
 #include <cstring>
 #include <string>
 #include <stdexcept>
+#include <vector>
+#include <algorithm>
 
 namespace oracle {
 
-// BigInteger(seedString).toByteArray() -> minimal two's-complement big-endian bytes, then PRNG.get16bytes.
-// Seeds are supported over the signed 128-bit range (wider values would be truncated to the low 16 bytes by the
-// reference as well, but need arbitrary precision parsing that nothing on the path uses).
-inline void seed_to_16_bytes(const std::string& dec, uint8_t out[16]) {
+// BigInteger(seedString).toByteArray() -> minimal two's-complement big-endian bytes, then PRNG.get16bytes
+// (math/PRNG.java:29-37: keep the LAST 16 bytes, or right-align a shorter array in 16 zero bytes). Any number of digits.
+inline std::vector<uint8_t> decimal_to_twos_complement(const std::string& dec) {
     bool neg = false; size_t i = 0;
     if (i < dec.size() && (dec[i] == '-' || dec[i] == '+')) { neg = dec[i] == '-'; ++i; }
     if (i >= dec.size()) throw std::invalid_argument("NumberFormatException: Zero length BigInteger");
-    unsigned __int128 mag = 0;
+    std::vector<uint8_t> mag;        // big-endian magnitude
     for (; i < dec.size(); ++i) {
         if (dec[i] < '0' || dec[i] > '9') throw std::invalid_argument("NumberFormatException: For input string: \"" + dec + "\"");
-        mag = mag * 10 + (unsigned)(dec[i] - '0');
+        int carry = dec[i] - '0';
+        for (size_t k = mag.size(); k-- > 0;) { int t = mag[k] * 10 + carry; mag[k] = (uint8_t)(t & 0xff); carry = t >> 8; }
+        while (carry) { mag.insert(mag.begin(), (uint8_t)(carry & 0xff)); carry >>= 8; }
     }
-    unsigned __int128 tc = neg ? (~mag + 1) : mag;
-    uint8_t full[17];
-    full[0] = neg && mag != 0 ? 0xFF : 0x00;       // sign extension byte
-    for (int b = 0; b < 16; ++b) full[1 + b] = (uint8_t)(tc >> (8 * (15 - b)));
-    // minimal length: strip redundant leading sign bytes
-    int start = 0;
-    while (start < 16) {
-        uint8_t cur = full[start], nxt = full[start + 1];
-        if ((cur == 0x00 && (nxt & 0x80) == 0) || (cur == 0xFF && (nxt & 0x80) != 0)) ++start; else break;
+    while (!mag.empty() && mag.front() == 0) mag.erase(mag.begin());
+    if (mag.empty()) return std::vector<uint8_t>{0};
+    std::vector<uint8_t> b(mag.size() + 1, 0);            // one spare sign byte
+    std::copy(mag.begin(), mag.end(), b.begin() + 1);
+    if (neg) {                                            // negate: invert and add one
+        for (auto& x : b) x = (uint8_t)~x;
+        for (size_t k = b.size(); k-- > 0;) { if (++b[k] != 0) break; }
     }
-    int len = 17 - start;
+    // minimal length: drop a leading byte that only repeats the sign of the next one
+    while (b.size() > 1 && ((b[0] == 0x00 && (b[1] & 0x80) == 0) || (b[0] == 0xFF && (b[1] & 0x80) != 0))) b.erase(b.begin());
+    return b;
+}
+inline void seed_to_16_bytes(const std::string& dec, uint8_t out[16]) {
+    const std::vector<uint8_t> b = decimal_to_twos_complement(dec);
     std::memset(out, 0, 16);
-    int from = len > 16 ? len - 16 : 0;
-    int to = len < 16 ? 16 - len : 0;
-    int n = len < 16 ? len : 16;
-    std::memcpy(out + to, full + start + from, n);
+    const int len = (int)b.size();
+    const int from = len > 16 ? len - 16 : 0, to = len < 16 ? 16 - len : 0, n = len < 16 ? len : 16;
+    std::memcpy(out + to, b.data() + from, (size_t)n);
+}
+// decimal string + small non-negative offset, in decimal-string arithmetic (replicate i of a batch == run with -s seed+i)
+inline std::string decimal_add(const std::string& dec, unsigned long long add) {
+    bool neg = false; size_t i = 0;
+    if (i < dec.size() && (dec[i] == '-' || dec[i] == '+')) { neg = dec[i] == '-'; ++i; }
+    std::string d = dec.substr(i); size_t nz = d.find_first_not_of('0'); d = nz == std::string::npos ? "0" : d.substr(nz);
+    std::string a = std::to_string(add);
+    auto cmp = [](const std::string& x, const std::string& y) { return x.size() != y.size() ? (x.size() < y.size() ? -1 : 1) : x.compare(y); };
+    auto plus = [](const std::string& x, const std::string& y) {
+        std::string r; int c = 0;
+        for (int p = (int)x.size() - 1, q = (int)y.size() - 1; p >= 0 || q >= 0 || c; --p, --q) { int t = c + (p >= 0 ? x[p] - '0' : 0) + (q >= 0 ? y[q] - '0' : 0); r.insert(r.begin(), (char)('0' + t % 10)); c = t / 10; }
+        return r;
+    };
+    auto minus = [](const std::string& x, const std::string& y) {      // x >= y
+        std::string r; int bw = 0;
+        for (int p = (int)x.size() - 1, q = (int)y.size() - 1; p >= 0; --p, --q) { int t = (x[p] - '0') - bw - (q >= 0 ? y[q] - '0' : 0); bw = t < 0; if (t < 0) t += 10; r.insert(r.begin(), (char)('0' + t)); }
+        size_t z = r.find_first_not_of('0'); return z == std::string::npos ? std::string("0") : r.substr(z);
+    };
+    if (!neg || d == "0") return plus(d, a);
+    if (cmp(d, a) > 0) return "-" + minus(d, a);
+    return minus(a, d);
 }
 
 class JavaMT {

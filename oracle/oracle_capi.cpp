@@ -25,7 +25,7 @@ void dispatch(const std::vector<std::string>& argv, Outputs& o, RepStats* st) {
 std::vector<std::string> with_seed_offset(const std::vector<std::string>& argv, long long i) {
     std::vector<std::string> a = argv;
     for (size_t k = 0; k + 1 < a.size(); ++k)
-        if (a[k] == "-s" || a[k] == "--seed") { a[k + 1] = std::to_string(std::stoll(a[k + 1]) + i); break; }
+        if (a[k] == "-s" || a[k] == "--seed") { a[k + 1] = decimal_add(a[k + 1], (unsigned long long)i); break; }
     return a;
 }
 }  // namespace

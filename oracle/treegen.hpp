@@ -106,6 +106,9 @@ public:
     }
 
     GVertex* create_guest_vertex(int X, double startTime, JavaMT& prng, Arena& arena) {      // :372-423
+        // Epoch.sampleArc returns -5 when no arc of the epoch carries the donor's HOST tag (topology/Epoch.java:256-258,273-275);
+        // the reference then indexes its host arrays with -5 and dies with an ArrayIndexOutOfBoundsException
+        if (X < 0) throw std::out_of_range("ArrayIndexOutOfBoundsException: " + std::to_string(X));
         ++vertices_created;
         bool isRoot = host.is_root(X);
         double sum = isRoot ? lambda + mu : lambda + mu + tau;
@@ -193,6 +196,8 @@ public:
                 std::vector<int> emptyArcs;
                 while (!node && (int)emptyArcs.size() != lin->epoch->n_arcs() - 1) {
                     if (std::find(emptyArcs.begin(), emptyArcs.end(), lin->toArc) == emptyArcs.end()) emptyArcs.push_back(lin->toArc);
+                    // a second -5 (no candidate left, list still short of n_arcs - 1) changes nothing any more: the reference spins here forever
+                    else if (lin->toArc == -5) throw std::runtime_error("no recipient arc with the donor's HOST tag is left (the reference does not terminate here)");
                     if ((int)emptyArcs.size() != lin->epoch->n_arcs() - 1) {
                         lin->toArc = host.sample_arc(*lin->epoch, prng, lin->sigma, lin->epoch->find_index_of_arc(lin->sigma), lin->abstime, bias, bias_rate, &emptyArcs, hostArc, true);
                         node = find_vertex(root, lin);

@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = (
     "sgp_batch_status", "sgp_batch_attempts", "sgp_batch_sampled_leaves", "sgp_batch_root_times", "sgp_batch_total_times",
     "sgp_batch_event_counts", "sgp_batch_stdout", "sgp_batch_stderr", "sgp_batch_out_prefix", "sgp_batch_summary",
     "sgp_batch_timings", "sgp_batch_write_files", "sgp_batch_write_files_layout", "sgp_batch_free", "sgp_probe_double_to_string", "sgp_probe_math",
-    "sgp_probe_mt", "sgp_probe_issue_peaks", "sgp_probe_host_model")
+    "sgp_probe_mt", "sgp_probe_seed", "sgp_probe_philox", "sgp_probe_issue_peaks", "sgp_probe_host_model")
 
 
 class BatchOpts(C.Structure):
@@ -97,7 +97,9 @@ def load_library() -> C.CDLL:
     L.sgp_batch_free.argtypes = [vp]
     L.sgp_probe_double_to_string.argtypes = [vp, C.POINTER(C.c_double), i64, C.c_char_p]; L.sgp_probe_double_to_string.restype = C.c_int
     L.sgp_probe_math.argtypes = [vp, C.c_int, C.POINTER(C.c_double), i64, C.POINTER(C.c_double)]; L.sgp_probe_math.restype = C.c_int
-    L.sgp_probe_mt.argtypes = [vp, i64, i64, C.POINTER(C.c_uint32)]; L.sgp_probe_mt.restype = C.c_int
+    L.sgp_probe_mt.argtypes = [vp, cp, i64, i64, C.POINTER(C.c_uint32)]; L.sgp_probe_mt.restype = C.c_int
+    L.sgp_probe_seed.argtypes = [cp, i64, C.POINTER(C.c_uint32), C.c_char_p, C.c_int32]; L.sgp_probe_seed.restype = C.c_int
+    L.sgp_probe_philox.argtypes = [vp, C.c_int, vp, vp, i64, vp]; L.sgp_probe_philox.restype = C.c_int
     L.sgp_probe_issue_peaks.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]; L.sgp_probe_issue_peaks.restype = C.c_int
     _lib = L
     return L
@@ -105,6 +107,31 @@ def load_library() -> C.CDLL:
 
 class SagephyError(RuntimeError):
     pass
+
+
+def _philox(handle, ctr, key, variant):
+    L = load_library()
+    c = np.ascontiguousarray(ctr, dtype=np.uint32).reshape(-1, 4); k = np.ascontiguousarray(key, dtype=np.uint32).reshape(-1, 2)
+    out = np.empty_like(c)
+    rc = L.sgp_probe_philox(handle, variant, c.ctypes.data, k.ctypes.data, len(c), out.ctypes.data)
+    if rc != 0:
+        raise SagephyError(f"sgp_probe_philox failed ({rc})")
+    return out
+
+
+def philox_host(ctr, key, variant: int = 0) -> np.ndarray:
+    """Philox4x32-10 blocks from the host build of the library's generator (no GPU)."""
+    return _philox(None, ctr, key, variant)
+
+
+def seed_probe(seed, replicate: int = 0):
+    """Host-side seed logic of the library (no GPU): (4 big-endian MT key words, decimal text) of seed + replicate."""
+    L = load_library()
+    key = (C.c_uint32 * 4)(); buf = C.create_string_buffer(4096)
+    rc = L.sgp_probe_seed(str(seed).encode(), replicate, key, buf, 4096)
+    if rc != 0:
+        raise SagephyError(f"sgp_probe_seed failed ({rc})")
+    return [int(k) for k in key], buf.value.decode()
 
 
 @dataclass
@@ -336,12 +363,17 @@ class Context:
             raise SagephyError("probe failed")
         return out
 
-    def mt_words(self, seed: int, n: int) -> np.ndarray:
+    def mt_words(self, seed, n: int, replicate: int = 0) -> np.ndarray:
+        """MT19937 words of replicate `replicate` of a run with `-s seed` (seed: any Python int or decimal string)."""
         out = np.empty(n, dtype=np.uint32)
-        rc = self._lib.sgp_probe_mt(self._h, seed, n, out.ctypes.data_as(C.POINTER(C.c_uint32)))
+        rc = self._lib.sgp_probe_mt(self._h, str(seed).encode(), replicate, n, out.ctypes.data_as(C.POINTER(C.c_uint32)))
         if rc != 0:
             raise SagephyError("probe failed")
         return out
+
+    def philox(self, ctr, key, variant: int = 0) -> np.ndarray:
+        """Philox4x32-10 blocks computed on the device (variant 1 = precomputed round keys, the sampler's form)."""
+        return _philox(self._h, ctr, key, variant)
 
     def issue_peaks(self) -> dict:
         a, b, c = C.c_double(), C.c_double(), C.c_double()

@@ -50,7 +50,7 @@ void common_window(const Parsed& p, TreeGenConfig& cfg) {
     cfg.P.min_leaves = to_int(p.str("-min", "2")); cfg.P.max_leaves = to_int(p.str("-max", "1000")); cfg.P.max_attempts = to_int(p.str("-a", "10000"));
     if (p.on("-sizes")) cfg.sizes = load_sizes(p.str("-sizes", ""));
     cfg.exclude_meta = p.on("-nox"); cfg.quiet = p.on("-q");
-    if (p.on("-s")) { cfg.has_seed = true; cfg.seed = to_i64(p.str("-s", "0")); cfg.seed_arg_index = p.val_index.at("-s"); }
+    if (p.on("-s")) { cfg.has_seed = true; cfg.seed = parse_seed(p.str("-s", "0")); cfg.seed_arg_index = p.val_index.at("-s"); }
     else { cfg.has_seed = false; cfg.seed = random_seed(); cfg.seed_arg_index = -1; }
 }
 

@@ -86,7 +86,7 @@ void parse_relax_app(const std::vector<std::string>& args, bool multi_tree_input
         if (i >= p.positional.size()) throw SgpError("IndexOutOfBoundsException: Index: " + std::to_string(i) + ", Size: " + std::to_string(p.positional.size()));
         return p.positional[i];
     };
-    if (p.on("-s")) { cfg.has_seed = true; cfg.seed = to_i64(p.str("-s", "0")); cfg.seed_arg_index = p.val_index.at("-s"); }
+    if (p.on("-s")) { cfg.has_seed = true; cfg.seed = parse_seed(p.str("-s", "0")); cfg.seed_arg_index = p.val_index.at("-s"); }
     else { cfg.has_seed = false; cfg.seed = random_seed(); }
     const std::string& model = arg(1);
     std::vector<std::pair<std::string, std::string>> kv; int hcap = 2; bool strict = false;

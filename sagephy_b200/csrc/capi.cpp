@@ -4,6 +4,7 @@
 #include <fstream>
 #include "../../include/sagephy_b200.h"
 #include "engine.hpp"
+#include "apps_common.hpp"
 
 using namespace sgp;
 
@@ -237,9 +238,26 @@ sgp_status sgp_probe_math(sgp_context* ctx, int fn, const double* v, int64_t n, 
     if (!ctx) return SGP_ERR_INVALID_ARGUMENT;
     try { ctx->ctx->probe_math(fn, v, n, out); return SGP_OK; } catch (std::exception& e) { ctx->last_error = e.what(); return SGP_ERR_NO_DEVICE; }
 }
-sgp_status sgp_probe_mt(sgp_context* ctx, int64_t seed, int64_t n_words, uint32_t* out) {
-    if (!ctx) return SGP_ERR_INVALID_ARGUMENT;
-    try { ctx->ctx->probe_mt(seed, n_words, out); return SGP_OK; } catch (std::exception& e) { ctx->last_error = e.what(); return SGP_ERR_NO_DEVICE; }
+sgp_status sgp_probe_mt(sgp_context* ctx, const char* seed, int64_t rep, int64_t n_words, uint32_t* out) {
+    if (!ctx || !seed) return SGP_ERR_INVALID_ARGUMENT;
+    try { ctx->ctx->probe_mt(cli::parse_seed(seed), rep, n_words, out); return SGP_OK; }
+    catch (SgpError& e) { ctx->last_error = e.what(); return SGP_ERR_PARSE; }
+    catch (std::exception& e) { ctx->last_error = e.what(); return SGP_ERR_NO_DEVICE; }
+}
+sgp_status sgp_probe_seed(const char* seed, int64_t rep, uint32_t key_out[4], char* dec, int32_t cap) {
+    if (!seed || rep < 0) return SGP_ERR_INVALID_ARGUMENT;
+    try {
+        const SeedHost h = cli::parse_seed(seed);
+        std::string text;
+        host_seed_probe(h, (unsigned long long)rep, key_out, text);
+        if (dec) { if ((int)text.size() + 1 > cap) return SGP_ERR_INVALID_ARGUMENT; std::memcpy(dec, text.c_str(), text.size() + 1); }
+        return SGP_OK;
+    } catch (std::exception&) { return SGP_ERR_PARSE; }
+}
+sgp_status sgp_probe_philox(sgp_context* ctx, int variant, const uint32_t* ctr, const uint32_t* key, int64_t n, uint32_t* out) {
+    if (!ctr || !key || !out || n < 0) return SGP_ERR_INVALID_ARGUMENT;
+    if (!ctx) { host_philox_probe(variant, ctr, key, n, out); return SGP_OK; }
+    try { ctx->ctx->probe_philox(variant, ctr, key, n, out); return SGP_OK; } catch (std::exception& e) { ctx->last_error = e.what(); return SGP_ERR_NO_DEVICE; }
 }
 sgp_status sgp_probe_issue_peaks(sgp_context* ctx, double* dfma, double* imad, double* ddep) {
     if (!ctx) return SGP_ERR_INVALID_ARGUMENT;

@@ -104,11 +104,19 @@ __global__ void k_probe_math(int fn, const double* v, long long n, double* out, 
     out[i] = fn == 0 ? jlog(x) : fn == 1 ? jlog10(x) : fn == 2 ? jexp(x) : fn == 3 ? round_sig(T, x, 8) : fn == 4 ? jnormal_quantile(x)
            : fn == 5 ? jpow(x, 0.37) : fn == 6 ? jchi2_quantile(x, 4.0, &err) : fn == 7 ? jchi2_quantile(x, 0.25, &err) : fn == 8 ? jpow(2.718281828459045, x) : log_unit(x, s_logtab);
 }
-__global__ void k_probe_mt(long long seed, long long n, uint32_t* out, uint32_t* state) {
+__global__ void k_probe_mt(SeedSpec seed, long long offset, long long n, uint32_t* out, uint32_t* state) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     MtStream mt; mt.mt = state; mt.stride = 32;
-    uint32_t key[4]; seed_words_i64(seed, key); mt.seed(key);
+    uint32_t key[4]; seed_words(seed, (unsigned long long)offset, key); mt.seed(key);
     for (long long i = 0; i < n; ++i) out[i] = mt.next_word();
+}
+__global__ void k_probe_philox(int variant, const uint32_t* ctr, const uint32_t* key, long long n, uint32_t* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t* c = ctr + 4 * i; const uint32_t* k = key + 2 * i;
+    const U4 r = variant == 0 ? philox4x32_10(c[0], c[1], c[2], c[3], k[0], k[1])
+                              : philox4x32_10_rk(c[0], c[1], c[2], c[3], philox_keys((uint64_t)k[0] | ((uint64_t)k[1] << 32)));
+    out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
 }
 // issue-rate microbenchmarks: independent chains per thread, enough ILP to saturate the pipe
 __global__ void k_peak_dfma(double* out, int iters) {
@@ -297,6 +305,13 @@ void Batch::fetch_stats() {
     have_stats = true;
 }
 
+// device view of the run's seed; the leading decimal digits of a wide seed go into the constant-string blob
+static SeedSpec make_seed_spec(const SeedHost& h, std::string& blob) {
+    SeedSpec s{}; s.lo = h.lo; s.hi = h.hi; s.wide = h.wide ? 1 : 0; s.negative = h.negative ? 1 : 0; s.dec_lo19 = h.dec_lo19;
+    for (int k = 0; k < 2; ++k) { s.hs_off[k] = (int)blob.size(); s.hs_len[k] = (int)h.hs[k].size(); blob += h.hs[k]; }
+    return s;
+}
+
 static TinyHost make_tiny(const HostModel& h) {
     TinyHost t{}; t.nV = h.nV; t.root = h.root;
     for (int i = 0; i < h.nV; ++i) { t.left[i] = h.left[i]; t.right[i] = h.right[i]; t.parent[i] = h.parent[i]; t.v2e[i] = h.v2e[i]; t.vtime[i] = h.vtime[i]; }
@@ -328,7 +343,8 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         P.thr_dup[k] = k == 0 ? P.lambda / sum : (P.mu + P.tau) / sum;      // root arc: dup if U < lambda/sum; others: dup if U >= (mu+tau)/sum
         P.thr_loss[k] = P.mu / sum;
     }
-    const unsigned long long seed = (unsigned long long)cfg.seed;
+    const unsigned long long seed = cfg.seed.philox_key;
+    std::string seed_blob_dummy; const SeedSpec sseed = make_seed_spec(cfg.seed, seed_blob_dummy);      // MT keys need no blob
 
     HostOnDevice hd; hd.upload(cfg.host);
     const bool domain = cfg.app == 2;
@@ -402,7 +418,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             marks.alloc((size_t)workers * mark_n); leafcnt.alloc((size_t)workers * cnt_n);
             if (domain) scratch_used.alloc((size_t)workers * cfg.genes.size());
             if (replay) mt_state.alloc((size_t)(workers / 32 + 1) * 624 * 32);
-            FindArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = todo; a.rep_ids = rep_ids; a.rep_base = opts.offset; a.seed = seed; a.info = info.p;
+            FindArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = todo; a.rep_ids = rep_ids; a.rep_base = opts.offset; a.seed = seed; a.sseed = sseed; a.info = info.p;
             a.work_counter = counter.p; a.scratch_nodes = s_nodes; a.scratch_queue = s_queue; a.scratch_pend = s_pend; a.cap = cap;
             a.scratch_marks = marks.p; a.scratch_leafcnt = leafcnt.p; a.mt_state = mt_state.p; a.sizes = d_sizes.p; a.per_leaf_check = per_leaf;
             a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
@@ -460,7 +476,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         if (domain) scratch_used.alloc((size_t)threads * cfg.genes.size());
         if (replay) mt_state.alloc((size_t)(threads / 32 + 1) * 624 * 32);
         CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
-        BuildArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.info = info.p; a.node_off = node_off.p; a.work_counter = counter.p;
+        BuildArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.sseed = sseed; a.info = info.p; a.node_off = node_off.p; a.work_counter = counter.p;
         a.nodes = nodes.p; a.aux = aux.p; a.aux_stride = aux_stride; a.scratch_marks = marks.p; a.scratch_leafcnt = nullptr; a.mt_state = mt_state.p;
         a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
         a.scratch_used = scratch_used.p; a.ev_base = d_ev_base.p; a.ev_off = d_ev_off.p; a.ev_list = d_ev_list.p;
@@ -516,7 +532,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         }
         if (split) post += "]"; else pre += "]";
         add(pre, e.args_pre_off, e.args_pre_len); add(post, e.args_post_off, e.args_post_len);
-        e.seed_mode = split ? 1 : 0; e.seed_base = cfg.seed;
+        e.seed_mode = split ? 1 : 0; e.sseed = make_seed_spec(cfg.seed, blob);
         e.args_pre_off16[0] = -1;
         if (pre.size() >= 512) for (int k = 0; k < 16; ++k) { while ((int)(blob.size() % 16) != k) blob.push_back(' '); e.args_pre_off16[k] = (int)blob.size(); blob += pre; }
     }
@@ -678,7 +694,7 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
             dst += cfg.args[i];
         }
         if (split) post += "]"; else pre += "]";
-        add(pre, a.args_pre_off, a.args_pre_len); add(post, a.args_post_off, a.args_post_len); a.seed_mode = split ? 1 : 0; a.seed_base = cfg.seed;
+        add(pre, a.args_pre_off, a.args_pre_len); add(post, a.args_post_off, a.args_post_len); a.seed_mode = split ? 1 : 0; a.sseed = make_seed_spec(cfg.seed, blob);
         std::string tail = "Model:\t" + cfg.model_name + "\nModel parameters:\n";
         for (auto& kv : cfg.params) tail += "\t" + kv.first + "\t" + kv.second + "\n";
         add(tail, a.model_tail_off, a.model_tail_len);
@@ -695,7 +711,7 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
     DevBuf<int32_t> attempts, status; attempts.alloc((size_t)n); status.alloc((size_t)n);
     CK(cudaMemsetAsync(attempts.p, 0, (size_t)n * sizeof(int32_t), st)); CK(cudaMemsetAsync(status.p, 0, (size_t)n * sizeof(int32_t), st));
     DevBuf<uint32_t> mt_state; if (replay) mt_state.alloc((size_t)((n + 127) / 128 * 128 / 32 + 1) * 624 * 32);
-    a.n = n; a.rep_base = opts.offset; a.seed = (unsigned long long)cfg.seed; a.model = cfg.model; a.pa = cfg.pa; a.pb = cfg.pb; a.pc = cfg.pc; a.pd = cfg.pd; a.sigma = cfg.sigma; a.topo = d_topo.p; a.parent = d_parent.p;
+    a.n = n; a.rep_base = opts.offset; a.seed = cfg.seed.philox_key; a.model = cfg.model; a.pa = cfg.pa; a.pb = cfg.pb; a.pc = cfg.pc; a.pd = cfg.pd; a.sigma = cfg.sigma; a.topo = d_topo.p; a.parent = d_parent.p;
     a.min_rate = cfg.min_rate; a.max_rate = cfg.max_rate; a.max_attempts = cfg.max_attempts; a.samples = d_samples.p; a.n_samples = (int)cfg.samples.size();
     a.n_trees = T; a.sum_v = sum_v; a.trees = d_views.p; a.orig = d_orig.p; a.chain = d_chain.p; a.vflags = d_flags.p; a.name_off = d_name.p; a.blob = d_blob.p;
     a.T = impl->T; a.rates = rates.p; a.relaxed = relaxed.p; a.attempts = attempts.p; a.status = status.p; a.mt_state = mt_state.p;
@@ -776,12 +792,21 @@ void Context::probe_math(int fn, const double* v, long long n, double* out) {
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, dout.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, impl->stream)); CK(cudaStreamSynchronize(impl->stream));
 }
-void Context::probe_mt(long long seed, long long n_words, uint32_t* out) {
+void Context::probe_mt(const SeedHost& seed, long long offset, long long n_words, uint32_t* out) {
     CK(cudaSetDevice(device));
     DevBuf<uint32_t> state, dout; state.alloc(624 * 32); dout.alloc((size_t)n_words);
-    k_probe_mt<<<1, 32, 0, impl->stream>>>(seed, n_words, dout.p, state.p);
+    std::string unused; k_probe_mt<<<1, 32, 0, impl->stream>>>(make_seed_spec(seed, unused), offset, n_words, dout.p, state.p);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, dout.p, (size_t)n_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, impl->stream)); CK(cudaStreamSynchronize(impl->stream));
+}
+void Context::probe_philox(int variant, const uint32_t* ctr, const uint32_t* key, long long n, uint32_t* out) {
+    CK(cudaSetDevice(device));
+    if (n <= 0) return;
+    DevBuf<uint32_t> dc, dk, dout; dc.alloc((size_t)n * 4); dk.alloc((size_t)n * 2); dout.alloc((size_t)n * 4);
+    CK(cudaMemcpy(dc.p, ctr, (size_t)n * 16, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dk.p, key, (size_t)n * 8, cudaMemcpyHostToDevice));
+    k_probe_philox<<<(unsigned)((n + 127) / 128), 128, 0, impl->stream>>>(variant, dc.p, dk.p, n, dout.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout.p, (size_t)n * 16, cudaMemcpyDeviceToHost, impl->stream)); CK(cudaStreamSynchronize(impl->stream));
 }
 void Context::probe_issue(double* dfma, double* imad, double* ddep) {
     CK(cudaSetDevice(device));

@@ -15,6 +15,15 @@ struct SimParamsHost {
     int min_leaves = 2, max_leaves = 1000, minper = 0, maxper = 10, max_attempts = 10000;
 };
 
+// A run's seed: any decimal integer (the reference parses it with java.math.BigInteger), see SeedSpec in rng.cuh.
+struct SeedHost {
+    unsigned long long lo = 0, hi = 0;        // low 128 bits, two's complement
+    bool wide = false, negative = false;
+    unsigned long long dec_lo19 = 0; std::string hs[2];
+    unsigned long long philox_key = 0;
+    std::string text;                          // canonical decimal text
+};
+
 struct TreeGenConfig {
     int app = 0;              // 0 HostTreeGen, 1 GuestTreeGen, 2 DomainTreeGen
     SimParamsHost P;
@@ -25,7 +34,7 @@ struct TreeGenConfig {
     std::string vertex_prefix = "H", out_prefix;
     bool has_stem_override = false; double stem_override = 0;   // HostTreeGen -stem (applied to the finished trees)
     std::vector<int> sizes;
-    bool has_seed = false; long long seed = 0;
+    bool has_seed = false; SeedHost seed;
     std::vector<std::string> args;      // the app's argv (for the "Arguments:" line)
     int seed_arg_index = -1;            // position of the seed value inside args
 };
@@ -42,7 +51,7 @@ struct RelaxConfig {
     double min_rate = 1e-64, max_rate = 1e64; int max_attempts = 10000;
     bool do_meta = false, keep_interior = false, has_outfile = false; std::string outfile;
     std::vector<RelaxTreeTemplate> trees;
-    bool has_seed = false; long long seed = 0;
+    bool has_seed = false; SeedHost seed;
     std::vector<std::string> args; int seed_arg_index = -1;
     std::string model_name; std::vector<std::pair<std::string, std::string>> params;   // in java.util.HashMap iteration order
 };
@@ -118,9 +127,15 @@ public:
     void wait_copies();
     void probe_d2s(const double* v, long long n, char* out);
     void probe_math(int fn, const double* v, long long n, double* out);
-    void probe_mt(long long seed, long long n_words, uint32_t* out);
+    void probe_mt(const SeedHost& seed, long long offset, long long n_words, uint32_t* out);
     void probe_issue(double* dfma, double* imad, double* ddep);
+    void probe_philox(int variant, const uint32_t* ctr, const uint32_t* key, long long n, uint32_t* out);
 };
+
+// tables.cpp: the device's seed arithmetic (rng.cuh) compiled for the host: MT key words and decimal text of seed + i
+void host_seed_probe(const SeedHost& h, unsigned long long i, uint32_t key[4], std::string& text);
+
+void host_philox_probe(int variant, const uint32_t* ctr, const uint32_t* key, long long n, uint32_t* out);
 
 // apps.cpp: reference CLI grammar -> configs
 struct AppResult { int status = 0; std::string out_text, err_text; };   // status: 0 run, 6 usage, other = error code

@@ -1,5 +1,6 @@
 #include "kernels_label.cuh"
 #include "launch.hpp"
+#include "host_model.hpp"
 #include <algorithm>
 #include <cstdlib>
 namespace sgp {
@@ -7,9 +8,10 @@ namespace sgp {
 // how many trees an SM works on at a time); whatever exceeds the largest stage goes to the thread-per-tree kernel.
 int launch_label_prune(LabelArgs a, int max_pool, int sm_count, cudaStream_t st) {
     static const int caps[] = {48, 64, 96, 128, 160, 192, 224, 256, 288, 320, 384, 448, 512, 640, 768, 1024, 1280, 1536, 2048, 2340};
-    static bool attr_set = false;
     const int kMaxSmem = 227 * 1024;
-    if (!attr_set) { cudaFuncSetAttribute(k_label_prune_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 1024); attr_set = true; }
+    // the opt-in is per device (and per context of the calling thread): set it on every call, it costs nothing next to a launch
+    if (cudaFuncSetAttribute(k_label_prune_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 1024) != cudaSuccess)
+        throw SgpError("cannot opt in to large dynamic shared memory for the label kernel on this device");
     int launches = 0, lo = 0;
     const bool thread_only = getenv("SGP_LABEL_THREAD_KERNEL") != nullptr;      // test hook: exercise the fallback on small trees
     for (int cap : caps) {

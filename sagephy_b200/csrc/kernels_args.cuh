@@ -21,7 +21,8 @@ struct FindArgs {
     long long n;                 // replicates in this launch
     const long long* rep_ids;    // optional indirection (re-runs of overflowed replicates); nullptr = identity
     long long rep_base;          // global id of local replicate 0 (multi-GPU shard offset)
-    unsigned long long seed;     // Philox key / MT base seed (replicate i == reference run with -s seed+i)
+    unsigned long long seed;     // Philox key
+    SeedSpec sseed;              // MT base seed (replicate i == reference run with -s seed+i)
     RepInfo* info;               // [n_total]
     unsigned long long* work_counter;
     // scratch (general engine): per worker thread
@@ -43,7 +44,7 @@ struct BuildArgs {
     SimParams P;
     DevHost H;
     MathTables T;
-    long long n; long long rep_base; unsigned long long seed;
+    long long n; long long rep_base; unsigned long long seed; SeedSpec sseed;
     RepInfo* info;
     const long long* node_off;   // exclusive scan of n_pool
     unsigned long long* work_counter;   // build slots are claimed dynamically, like replicates in the find kernel
@@ -99,7 +100,7 @@ struct EmitArgs {
     unsigned stream_mask;
     char prefix[24]; int prefix_len;
     const char* blob;              // constant strings, see below
-    int args_pre_off, args_pre_len, args_post_off, args_post_len, seed_mode; long long seed_base;
+    int args_pre_off, args_pre_len, args_post_off, args_post_len, seed_mode; SeedSpec sseed;
     int g2h_head_off, g2h_head_len;
     int args_pre_off16[16];        // same 16 shifted copies for the "Arguments:" text when it is long (it may embed a whole host tree); [0] < 0: not built
     int g2h_head_off16[16];        // 16 copies of the header, copy k starting at a blob offset == k (mod 16): aligned 16-byte copies for any destination
@@ -154,7 +155,7 @@ struct RelaxArgs {
     uint32_t* mt_state;
     // emission
     int do_meta; int has_outfile;
-    int args_pre_off, args_pre_len, args_post_off, args_post_len, seed_mode; long long seed_base;
+    int args_pre_off, args_pre_len, args_post_off, args_post_len, seed_mode; SeedSpec sseed;
     int model_tail_off, model_tail_len;            // "Model:\t...\nModel parameters:\n..." (constant per run)
     uint16_t* plen_tree; uint16_t* plen_info;      // cached piece lengths: [vertex slots], [3 * vertex slots + 8 * n]
     unsigned long long* sizes;                     // [2][n]

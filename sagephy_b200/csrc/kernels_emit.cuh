@@ -103,7 +103,7 @@ template <bool PRUNED, class Sink> __device__ void put_info_line(Sink& s, const 
     if (ln == 1) {
         put_lit(s, "Arguments:\t");
         put_blob(s, a.blob, a.args_pre_off, a.args_pre_len);
-        if (a.seed_mode) { put_i64(s, a.seed_base + gid); put_blob(s, a.blob, a.args_post_off, a.args_post_len); }
+        if (a.seed_mode) { put_seed(s, a.sseed, a.blob, (unsigned long long)gid); put_blob(s, a.blob, a.args_post_off, a.args_post_len); }
         s.put('\n'); return;
     }
     const char* key = ""; bool is_double = false; long long iv = 0; double num = 0.0; bool ratio = false;
@@ -311,8 +311,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, WRITE ? 8 : 10) k_emit(EmitAr
                 // lines 0-1 ("# APP" and "Arguments: [...]", which may embed a whole Newick host tree): warp-cooperative copy
                 const char* h0 = a.app == 0 ? "# HOSTTREEGEN\nArguments:\t" : a.app == 1 ? "# GUESTTREEGEN\nArguments:\t" : "# DOMAINTREEGEN\nArguments:\t";
                 const int h0len = a.app == 0 ? 25 : a.app == 1 ? 26 : 27;
-                const long long seedv = a.seed_base + gid;
-                const int seedlen = a.seed_mode ? (seedv < 0 ? 1 : 0) + dec_len_u64((uint64_t)(seedv < 0 ? -seedv : seedv)) : 0;
+                const int seedlen = a.seed_mode ? seed_dec_len(a.sseed, a.blob, (unsigned long long)gid) : 0;
                 unsigned long long o = 0;
                 if (WRITE) {
                     for (int i = lane; i < h0len; i += 32) base[i] = h0[i];
@@ -327,7 +326,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, WRITE ? 8 : 10) k_emit(EmitAr
                 o = (unsigned long long)h0len + a.args_pre_len;
                 if (a.seed_mode) {
                     if (WRITE) {
-                        if (lane == 0) { MemSink m{base + o}; put_i64(m, seedv); }
+                        if (lane == 0) { MemSink m{base + o}; put_seed(m, a.sseed, a.blob, (unsigned long long)gid); }
                         for (int i = lane; i < a.args_post_len; i += 32) base[o + seedlen + i] = a.blob[a.args_post_off + i];
                     }
                     o += (unsigned long long)seedlen + a.args_post_len;

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(128) k_relax_rates(RelaxArgs a, int first_atte
     if (nV == 0) { a.status[r] = REP_MODEL_ERROR; a.attempts[r] = 0; return; }       // chained stage: the source replicate has no tree
     MtStream mt; GaussCache gc{false, 0.0};
     if (REPLAY) { const int worker = blockIdx.x * blockDim.x + threadIdx.x; mt.mt = a.mt_state + (size_t)(worker >> 5) * 624 * 32 + (worker & 31); mt.stride = 32;
-                  uint32_t key[4]; seed_words_i64((long long)a.seed + (long long)gid, key); mt.seed(key); }
+                  uint32_t key[4]; seed_words(a.sseed, (unsigned long long)gid, key); mt.seed(key); }
     int attempts = first_attempt; int status = REP_PENDING;
     for (;;) {
         if (attempts > a.max_attempts) { status = REP_MAX_ATTEMPTS; break; }
@@ -305,7 +305,7 @@ template <class Sink> __device__ void put_relax_info(Sink& s, const RelaxArgs& a
     if (k == 0) { put_lit(s, "# BRANCHLENGTHRELAXER\n"); return; }
     if (k == 1) {
         put_lit(s, "Arguments:\t"); put_blob(s, a.blob, a.args_pre_off, a.args_pre_len);
-        if (a.seed_mode) { put_i64(s, a.seed_base + gid); put_blob(s, a.blob, a.args_post_off, a.args_post_len); }
+        if (a.seed_mode) { put_seed(s, a.sseed, a.blob, (unsigned long long)gid); put_blob(s, a.blob, a.args_post_off, a.args_post_len); }
         s.put('\n'); return;
     }
     if (k == 2) { put_lit(s, "Attempts:\t"); put_i64(s, attempts); s.put('\n'); return; }
@@ -353,8 +353,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) k_relax_emit(RelaxArgs a) 
             // lines 0-1 ("# BRANCHLENGTHRELAXER" and "Arguments: [...]", which may embed whole Newick trees and exceed the 16-bit
             // piece-length cache): warp-cooperative copy, length known in closed form
             const char* h0 = "# BRANCHLENGTHRELAXER\nArguments:\t"; const int h0len = 33;
-            const long long seedv = a.seed_base + gid;
-            const int seedlen = a.seed_mode ? (seedv < 0 ? 1 : 0) + dec_len_u64((uint64_t)(seedv < 0 ? -seedv : seedv)) : 0;
+            const int seedlen = a.seed_mode ? seed_dec_len(a.sseed, a.blob, (unsigned long long)gid) : 0;
             if (WRITE) {
                 for (int i = lane; i < h0len; i += 32) out[i] = h0[i];
                 for (int i = lane; i < a.args_pre_len; i += 32) out[h0len + i] = a.blob[a.args_pre_off + i];
@@ -362,7 +361,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) k_relax_emit(RelaxArgs a) 
             unsigned long long o = (unsigned long long)h0len + a.args_pre_len;
             if (a.seed_mode) {
                 if (WRITE) {
-                    if (lane == 0) { MemSink m{out + o}; put_i64(m, seedv); }
+                    if (lane == 0) { MemSink m{out + o}; put_seed(m, a.sseed, a.blob, (unsigned long long)gid); }
                     for (int i = lane; i < a.args_post_len; i += 32) out[o + seedlen + i] = a.blob[a.args_post_off + i];
                 }
                 o += (unsigned long long)seedlen + a.args_post_len;

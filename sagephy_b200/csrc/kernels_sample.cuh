@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
                 const long long gid = a.rep_base + r;
                 memset(&inf, 0, sizeof(inf));
                 inf.status = REP_PENDING; inf.exact = -1; inf.root = -1; inf.p_root = -1;
-                if (REPLAY) { uint32_t key[4]; seed_words_i64((long long)a.seed + gid, key); mt.seed(key); }
+                if (REPLAY) { uint32_t key[4]; seed_words(a.sseed, (unsigned long long)gid, key); mt.seed(key); }
                 else ph.init(a.seed, (uint64_t)gid, 0xFFFFFFFFu);
                 if (a.P.n_sizes > 0) inf.exact = a.sizes[REPLAY ? mt.next_int(a.P.n_sizes) : ph.next_int(a.P.n_sizes)];
                 attempts = 0; verts = 0; have = true; S.stage = -1;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(128) k_build_general(BuildArgs a) {
                     W.nodes = a.nodes + off; W.cap = inf.n_pool; W.queue = a.aux + off; W.pend = a.aux + a.aux_stride + off;
                     const long long gid = a.rep_base + r;
                     if (REPLAY) {
-                        uint32_t key[4]; seed_words_i64((long long)a.seed + gid, key); mt.seed(key); mt.skip(((uint64_t)inf.acc_hi << 32) | inf.acc_attempt);
+                        uint32_t key[4]; seed_words(a.sseed, (unsigned long long)gid, key); mt.seed(key); mt.skip(((uint64_t)inf.acc_hi << 32) | inf.acc_attempt);
                         engine_begin<DOMAIN>(S, mt, a, E);
                     } else { ph.init(a.seed, (uint64_t)gid, inf.acc_attempt); engine_begin<DOMAIN>(S, ph, a, E); }
                     have = true;

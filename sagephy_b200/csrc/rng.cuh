@@ -111,6 +111,53 @@ SGP_HD void seed_words_i64(long long s, uint32_t key[4]) {
     key[0] = 0; key[1] = 0; key[2] = (uint32_t)(u >> 32); key[3] = (uint32_t)u;
 }
 
+// The seed of a run as the reference sees it: `new BigInteger(String)` of ANY size, of which PRNG.get16bytes keeps the low 16
+// bytes of the minimal two's-complement form, zero-padded on the left when shorter (math/PRNG.java:29-37,58-60;
+// GuestTreeMachina.java:47). Replicate i runs with seed + i in big-integer arithmetic, so the device carries
+//   * the low 128 bits of the two's-complement seed (enough for the MT key of every seed + i), and
+//   * `wide` = 1 when |seed| >= 2^120 + 2^64: seed + i then needs >= 16 bytes for every 0 <= i < 2^63, the key is simply
+//     (seed + i) mod 2^128 and the decimal text of seed + i is <leading digits, with or without a carry/borrow><19 digits>;
+//     otherwise seed + i fits a signed __int128 with room to spare and everything is done in that type.
+struct SeedSpec {
+    unsigned long long lo, hi;        // low 128 bits of the two's-complement seed
+    int32_t wide, negative;
+    unsigned long long dec_lo19;      // wide: the 19 least significant decimal digits of |seed| ...
+    int32_t hs_off[2], hs_len[2];     // ... and the digits above them: blob offset/length without ([0]) and with ([1]) a carry (borrow if negative)
+};
+SGP_HD void seed_words(const SeedSpec& s, unsigned long long i, uint32_t key[4]) {
+    unsigned __int128 v = (((unsigned __int128)s.hi << 64) | (unsigned __int128)s.lo) + (unsigned __int128)i;
+    if (!s.wide) {
+        const __int128 sv = (__int128)v;
+        int L = 1;      // minimal two's-complement byte length of seed + i
+        while (L < 16 && (sv < -((__int128)1 << (8 * L - 1)) || sv >= ((__int128)1 << (8 * L - 1)))) ++L;
+        if (L < 16) v &= (((unsigned __int128)1 << (8 * L)) - 1);
+    }
+    key[0] = (uint32_t)(v >> 96); key[1] = (uint32_t)(v >> 64); key[2] = (uint32_t)(v >> 32); key[3] = (uint32_t)v;
+}
+// decimal text of seed + i (what a separate reference run of replicate i would print in its "Arguments:" line)
+template <class Sink> SGP_HD void put_seed(Sink& out, const SeedSpec& s, const char* blob, unsigned long long i) {
+    const unsigned long long P19 = 10000000000000000000ull;
+    if (!s.wide) {
+        __int128 sv = (__int128)((((unsigned __int128)s.hi << 64) | (unsigned __int128)s.lo) + (unsigned __int128)i);
+        if (sv >= -(__int128)0x7fffffffffffffffLL && sv <= (__int128)0x7fffffffffffffffLL) { put_i64(out, (long long)sv); return; }
+        if (sv < 0) { out.put('-'); sv = -sv; }
+        const unsigned __int128 m = (unsigned __int128)sv;
+        if (m < (unsigned __int128)P19) { put_u64(out, (unsigned long long)m); return; }
+        const unsigned __int128 top = m / P19; const unsigned long long low = (unsigned long long)(m - top * P19);
+        put_u64(out, (unsigned long long)top);       // < 2^121 / 10^19 < 2^64
+        out.put((char)('0' + (int)(low / 1000000000000000000ull))); const unsigned long long r = low % 1000000000000000000ull;
+        put_u32_digits(out, (uint32_t)(r / 1000000000ull), 9); put_u32_digits(out, (uint32_t)(r % 1000000000ull), 9);
+        return;
+    }
+    int c; unsigned long long low;
+    if (!s.negative) { c = i >= P19 - s.dec_lo19 ? 1 : 0; low = c ? i - (P19 - s.dec_lo19) : s.dec_lo19 + i; }
+    else { c = i > s.dec_lo19 ? 1 : 0; low = c ? s.dec_lo19 + (P19 - i) : s.dec_lo19 - i; out.put('-'); }
+    for (int k = 0; k < s.hs_len[c]; ++k) out.put(blob[s.hs_off[c] + k]);
+    out.put((char)('0' + (int)(low / 1000000000000000000ull))); const unsigned long long r = low % 1000000000000000000ull;
+    put_u32_digits(out, (uint32_t)(r / 1000000000ull), 9); put_u32_digits(out, (uint32_t)(r % 1000000000ull), 9);
+}
+SGP_HD int seed_dec_len(const SeedSpec& s, const char* blob, unsigned long long i) { CountSink c; put_seed(c, s, blob, i); return (int)c.n; }
+
 // ---- MT19937 (Java / uncommons flavour) ------------------------------------------------------------------------------------
 // seed16: the 16 big-endian bytes PRNG.get16bytes produced, as 4 big-endian words.
 struct MtStream {

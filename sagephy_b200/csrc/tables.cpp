@@ -1,4 +1,6 @@
 #include "hostfmt.hpp"
+#include "engine.hpp"
+#include "rng.cuh"
 #include "d2s_tables.inc"
 
 namespace sgp {
@@ -17,5 +19,21 @@ namespace { struct StrSink { std::string s; void put(char c) { s.push_back(c); }
 
 std::string jdouble(double v) { StrSink k; put_double(k, host_math_tables(), v); return k.s; }
 double host_round_sig(double v, int n) { return round_sig(host_math_tables(), v, n); }
+
+void host_philox_probe(int variant, const uint32_t* ctr, const uint32_t* key, long long n, uint32_t* out) {
+    for (long long i = 0; i < n; ++i) {
+        const uint32_t* c = ctr + 4 * i; const uint32_t* k = key + 2 * i;
+        const U4 r = variant == 0 ? philox4x32_10(c[0], c[1], c[2], c[3], k[0], k[1])
+                                  : philox4x32_10_rk(c[0], c[1], c[2], c[3], philox_keys((uint64_t)k[0] | ((uint64_t)k[1] << 32)));
+        out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+    }
+}
+
+void host_seed_probe(const SeedHost& h, unsigned long long i, uint32_t key[4], std::string& text) {
+    std::string blob; SeedSpec s{}; s.lo = h.lo; s.hi = h.hi; s.wide = h.wide ? 1 : 0; s.negative = h.negative ? 1 : 0; s.dec_lo19 = h.dec_lo19;
+    for (int k = 0; k < 2; ++k) { s.hs_off[k] = (int)blob.size(); s.hs_len[k] = (int)h.hs[k].size(); blob += h.hs[k]; }
+    seed_words(s, i, key);
+    StrSink k; put_seed(k, s, blob.c_str(), i); text = k.s;
+}
 
 }  // namespace sgp

@@ -95,3 +95,41 @@ def oracle_mt_doubles(seed, n):
     out = np.empty(n, dtype=np.float64)
     oracle().oracle_mt_doubles(str(seed).encode(), n, out.ctypes.data)
     return out
+
+
+# ---- process-pool front ends (the oracle is single-threaded; the GPU boxes have 16+ host cores) -------------------------------------
+def _run_worker(job):
+    app, args = job
+    return oracle_run(app, args)
+
+
+def _batch_worker(job):
+    app, args, first, n = job
+    return oracle_batch(app, args, first, n)[1]
+
+
+def pool_size(procs=None):
+    return max(1, min(procs or (os.cpu_count() or 1), 32))
+
+
+def oracle_run_many(jobs, procs=None):
+    """jobs: [(app, args), ...] -> list of oracle_run results, computed on a process pool."""
+    from concurrent.futures import ProcessPoolExecutor
+    jobs = list(jobs)
+    if len(jobs) <= 1 or pool_size(procs) == 1:
+        return [_run_worker(j) for j in jobs]
+    with ProcessPoolExecutor(pool_size(procs)) as ex:
+        return list(ex.map(_run_worker, jobs, chunksize=max(1, len(jobs) // (4 * pool_size(procs)))))
+
+
+def oracle_batch_parallel(app, args, first, n, procs=None):
+    """oracle_batch over [first, first + n) split across a process pool. Returns stats[n, 26]."""
+    from concurrent.futures import ProcessPoolExecutor
+    p = pool_size(procs)
+    if p == 1 or n < 4 * p:
+        return oracle_batch(app, args, first, n)[1]
+    chunks = 4 * p
+    edges = [first + (n * k) // chunks for k in range(chunks + 1)]
+    with ProcessPoolExecutor(p) as ex:
+        parts = list(ex.map(_batch_worker, [(app, list(args), edges[k], edges[k + 1] - edges[k]) for k in range(chunks) if edges[k + 1] > edges[k]]))
+    return np.concatenate(parts, axis=0)

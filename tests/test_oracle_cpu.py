@@ -18,21 +18,83 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
 # ---- RNG -----------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("seed", [0, 1, 12345, 2 ** 31, 2 ** 63 - 1, (1 << 70) + 5, -1, -129, -(1 << 40)])
-def test_mt_seeding_matches_numpy_init_by_array(seed):
-    # PRNG.get16bytes + MersenneTwisterRNG2 ctor == MT19937 init_by_array over 4 big-endian words
+def java_seed_key(seed: int) -> np.ndarray:
+    """BigInteger(seed).toByteArray() -> PRNG.get16bytes -> 4 big-endian words, with Python's own big integers."""
     nbytes = max(1, (seed.bit_length() + 8) // 8) if seed >= 0 else max(1, ((-seed - 1).bit_length() + 8) // 8)
     raw = seed.to_bytes(nbytes, "big", signed=True)
     # BigInteger.toByteArray is minimal: strip redundant sign bytes
     while len(raw) > 1 and ((raw[0] == 0 and raw[1] < 0x80) or (raw[0] == 0xFF and raw[1] >= 0x80)):
         raw = raw[1:]
     sixteen = (b"\0" * 16 + raw)[-16:]
-    key = np.frombuffer(sixteen, dtype=">u4").astype(np.uint32)
+    return np.frombuffer(sixteen, dtype=">u4").astype(np.uint32)
+
+
+BIG_SEEDS = [0, 1, 12345, 2 ** 31, 2 ** 63 - 1, 2 ** 63, 2 ** 64 - 1, (1 << 70) + 5, -1, -129, -(1 << 40), -(1 << 63), -(1 << 63) - 1,
+             2 ** 119 - 1, 2 ** 119, 2 ** 120 + 2 ** 64 - 1, 2 ** 120 + 2 ** 64, 2 ** 127 - 1, 2 ** 127, 2 ** 128 + 77, -(2 ** 119), -(2 ** 119) - 1,
+             -(2 ** 120) - 2 ** 64, -(2 ** 127), -(2 ** 127) - 1, 10 ** 50 + 12345, -(10 ** 50), 10 ** 80 - 1, 10 ** 38 - 1,
+             123456789012345678901234567890123456789999999999999999999, -(10 ** 60 + 5)]
+
+
+@pytest.mark.parametrize("seed", BIG_SEEDS)
+def test_mt_seeding_matches_numpy_init_by_array(seed):
+    # PRNG.get16bytes + MersenneTwisterRNG2 ctor == MT19937 init_by_array over 4 big-endian words (SURVEY A.1)
+    key = java_seed_key(seed)
     bg = np.random.MT19937()
     bg._legacy_seeding(key)
     want = bg.random_raw(2000).astype(np.uint32)
     got = oracle_mt_words(seed, 2000)
     assert (want == got).all()
+
+
+@pytest.mark.parametrize("seed", BIG_SEEDS)
+def test_library_seed_arithmetic_matches_big_integers(seed):
+    # product host/device seed code (rng.cuh seed_words / put_seed, compiled for the host) against Python's arbitrary-precision
+    # integers: replicate i of a batch is the reference run with -s (seed + i) (math/PRNG.java:29-37,58-60)
+    import sagephy_b200 as sg
+    for i in (0, 1, 7, 255, 256, 10 ** 6, 2 ** 40 + 3, 9 * 10 ** 18, 2 ** 63 - 1):
+        key, text = sg.seed_probe(seed, i)
+        assert text == str(seed + i), (seed, i)
+        assert key == java_seed_key(seed + i).tolist(), (seed, i)
+    key, text = sg.seed_probe("+" + str(abs(seed)), 0)
+    assert text == str(abs(seed))
+    for bad in ("", "-", "12x", "1.5", " 7"):
+        with pytest.raises(sg.SagephyError):
+            sg.seed_probe(bad, 0)
+
+
+def test_oracle_seed_offset_is_big_integer_addition():
+    # the oracle's batch entry point adds the replicate index in decimal-string arithmetic; check it through the MT stream
+    for seed in (10 ** 50 - 3, -(10 ** 30) + 2, -5, 2 ** 64 - 2):
+        for i in (0, 3, 5, 7):
+            assert (oracle_mt_words(seed + i, 8) == oracle_mt_words(str(seed + i), 8)).all()
+    a = oracle_run("HostTreeGen", ["-s", str(10 ** 40 + 2), "-min", "2", "-max", "9", "1.0", "2.0", "0.3", "x"])
+    _, st = oracle_batch("HostTreeGen", ["-s", str(10 ** 40), "-min", "2", "-max", "9", "1.0", "2.0", "0.3", "x"], 2, 1)
+    assert int(st[0, 0]) == a["attempts"]
+
+
+def test_philox4x32_10_random123_known_answers():
+    # Random123 kat_vectors (philox4x32, 10 rounds) through the host build of the library's generator, both key-schedule forms,
+    # and against an independent big-integer restatement of the published round function
+    import sagephy_b200 as sg
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+
+    def ref(c, k):
+        c = list(c); k = list(k)
+        for _ in range(10):
+            p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+            c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xffffffff, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xffffffff]
+            k = [(k[0] + 0x9E3779B9) & 0xffffffff, (k[1] + 0xBB67AE85) & 0xffffffff]
+        return c
+    for c, k, want in kat:
+        assert ref(c, k) == list(want)
+        for variant in (0, 1):
+            assert sg.philox_host([c], [k], variant)[0].tolist() == list(want)
+    rng = np.random.default_rng(0)
+    ctr = rng.integers(0, 2 ** 32, (200, 4), dtype=np.uint64); key = rng.integers(0, 2 ** 32, (200, 2), dtype=np.uint64)
+    got = sg.philox_host(ctr.astype(np.uint32), key.astype(np.uint32), 1)
+    assert got.tolist() == [ref([int(x) for x in c], [int(x) for x in k]) for c, k in zip(ctr, key)]
 
 
 def test_java_next_double_layout():
