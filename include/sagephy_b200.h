@@ -96,6 +96,7 @@ typedef struct {
 typedef struct {
     double find_ms, build_ms, label_ms, emit_size_ms, emit_write_ms, d2h_ms, total_ms;   /* CUDA-event times of the last run */
     int64_t kernel_launches;
+    int64_t h2d_bytes;          /* host->device bytes of the run: host-tree tables, constant strings, tree templates */
 } sgp_timings;
 
 sgp_status sgp_context_create(int device, sgp_context** out);

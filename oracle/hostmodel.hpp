@@ -18,6 +18,10 @@
 
 namespace oracle {
 
+// test hook: how often Epoch.sampleArc found no eligible recipient (returned -5) since the counter was last reset
+inline long& no_recipient_hits() { static thread_local long n = 0; return n; }
+
+
 struct TopologyException : std::runtime_error { using std::runtime_error::runtime_error; };
 
 // ---- non-negative arbitrary-precision decimal (the subset of BigDecimal the path uses) --------------------------------
@@ -236,7 +240,7 @@ public:
             throw std::invalid_argument("IllegalArgumentException: Cannot exclude arc from sampling (it's the only one!): " + std::to_string(excludeArc));
         if (bias != "none") {
             CumMap dist = set_distance(ep, excludeArc, eventTime, bias, rate, emptyArcs, hostArc, include);
-            if (dist.empty()) return -5;
+            if (dist.empty()) { ++no_recipient_hits(); return -5; }
             Dec total = dist.last_key();
             Dec rnd = Dec::mul(total, Dec::from_double(prng.nextDouble()));
             arc = dist.higher(rnd);
@@ -247,7 +251,7 @@ public:
                 if (x != excludeArc && (!emptyArcs || std::find(emptyArcs->begin(), emptyArcs->end(), x) == emptyArcs->end()) &&
                     (include ? (arcHost == hostArc) : (arcHost != hostArc))) same.push_back(x);
             }
-            if (same.empty()) return -5;
+            if (same.empty()) { ++no_recipient_hits(); return -5; }
             arc = same[prng.nextInt((int)same.size())];
             // the reference's re-draw loop never iterates: Arrays.asList(int[]).indexOf(Integer) == -1 != fromArc (Epoch.java:279-291)
             (void)fromArcIdx;

@@ -8,7 +8,7 @@
 using namespace oracle;
 
 namespace {
-struct Handle { Outputs o; RepStats st; };
+struct Handle { Outputs o; RepStats st; long no_recipient = 0; };
 
 void dispatch(const std::vector<std::string>& argv, Outputs& o, RepStats* st) {
     if (argv.empty()) { o.out += "Usage: <HostTreeGen|GuestTreeGen|DomainTreeGen|BranchRelaxer> [options] <args>\n"; return; }
@@ -35,7 +35,9 @@ extern "C" {
 void* oracle_run(int argc, const char** argv) {
     auto* h = new Handle();
     std::vector<std::string> a(argv, argv + argc);
+    no_recipient_hits() = 0;
     dispatch(a, h->o, &h->st);
+    h->no_recipient = no_recipient_hits();
     return h;
 }
 int oracle_n_files(void* h) { return (int)((Handle*)h)->o.files.size(); }
@@ -46,6 +48,7 @@ const char* oracle_stdout(void* h) { return ((Handle*)h)->o.out.c_str(); }
 const char* oracle_stderr(void* h) { return ((Handle*)h)->o.err.c_str(); }
 int oracle_attempts(void* h) { return ((Handle*)h)->st.attempts; }
 int oracle_status(void* h) { return ((Handle*)h)->st.status; }
+long long oracle_no_recipient(void* h) { return ((Handle*)h)->no_recipient; }
 void oracle_free(void* h) { delete (Handle*)h; }
 
 // Batch: replicate i runs with seed+i. Per-replicate stats are written as 32 int64/doubles-in-slots rows.

@@ -51,7 +51,7 @@ class SummaryStruct(C.Structure):
 
 class TimingsStruct(C.Structure):
     _fields_ = [("find_ms", C.c_double), ("build_ms", C.c_double), ("label_ms", C.c_double), ("emit_size_ms", C.c_double),
-                ("emit_write_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double), ("kernel_launches", C.c_int64)]
+                ("emit_write_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double), ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64)]
 
 
 _lib = None

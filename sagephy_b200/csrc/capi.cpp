@@ -170,7 +170,7 @@ void sgp_batch_timings(const sgp_batch* b, sgp_timings* out) {
     if (!b || !out) return;
     const Timings& t = b->b.timings;
     out->find_ms = t.find_ms; out->build_ms = t.build_ms; out->label_ms = t.label_ms; out->emit_size_ms = t.emit_size_ms; out->emit_write_ms = t.emit_write_ms;
-    out->d2h_ms = t.d2h_ms; out->total_ms = t.total_ms; out->kernel_launches = t.launches;
+    out->d2h_ms = t.d2h_ms; out->total_ms = t.total_ms; out->kernel_launches = t.launches; out->h2d_bytes = t.h2d_bytes;
 }
 
 sgp_status sgp_batch_write_files(sgp_batch* b) {

@@ -26,13 +26,14 @@ namespace {
 // Device buffers come from the CUDA stream-ordered pool (release threshold = unlimited, see Context::Context), so
 // steady-state batches reuse memory instead of paying cudaMalloc/cudaFree per phase.
 thread_local cudaStream_t g_alloc_stream = nullptr;
+thread_local unsigned long long g_h2d_bytes = 0;      // host->device bytes of the current run (tables, constant strings, templates)
 template <class T> struct DevBuf {
     T* p = nullptr; size_t n = 0;
     DevBuf() {}
     DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { if (p) cudaFreeAsync(p, g_alloc_stream); }
     void alloc(size_t count) { if (p) { cudaFreeAsync(p, g_alloc_stream); p = nullptr; } n = count; if (count) CK(cudaMallocAsync(&p, count * sizeof(T), g_alloc_stream)); }
-    void upload(const std::vector<T>& v) { alloc(v.size()); if (!v.empty()) { CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, g_alloc_stream)); CK(cudaStreamSynchronize(g_alloc_stream)); } }
+    void upload(const std::vector<T>& v) { alloc(v.size()); if (!v.empty()) { CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, g_alloc_stream)); CK(cudaStreamSynchronize(g_alloc_stream)); g_h2d_bytes += v.size() * sizeof(T); } }
     T* release() { T* q = p; p = nullptr; n = 0; return q; }
 };
 
@@ -331,6 +332,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     out.n = n; out.device = device; out.app = cfg.app; out.quiet = cfg.quiet; out.out_prefix = cfg.out_prefix;
     Timings tm; EventTimer total(st), ph(st);
     total.start();
+    g_h2d_bytes = 0;
 
     SimParams P{};
     P.lambda = cfg.P.lambda; P.mu = cfg.P.mu; P.tau = cfg.P.tau; P.theta = cfg.P.theta; P.rho = cfg.P.rho; P.bias_rate = cfg.P.bias_rate;
@@ -618,7 +620,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     static const char* host_sfx[8] = {".unpruned.tree", ".pruned.tree", ".unpruned.info", ".pruned.info", ".unpruned.guest2host", ".pruned.guest2host", ".unpruned.leafmap", ".pruned.leafmap"};
     for (int s = 0; s < 8; ++s) out.suffix[s] = (mask & (1u << s)) ? host_sfx[s] : "";
     out.stream_mask = mask;
-    tm.total_ms = total.stop();
+    tm.total_ms = total.stop(); tm.h2d_bytes = (long long)g_h2d_bytes;
     out.timings = tm;
     if (!opts.keep_on_device) {
         EventTimer d2h(st); d2h.start();
@@ -647,6 +649,7 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
     const bool replay = opts.rng_mode == 1;
     out.stream = (void*)st; out.n = n; out.device = device; out.app = 3; out.quiet = !cfg.has_outfile; out.out_prefix = cfg.outfile;
     Timings tm; EventTimer total(st), ph(st); total.start();
+    g_h2d_bytes = 0;
 
     // tree templates: flattened host templates, or (chained stage) ingested on the device from a generator batch
     const bool chained = src != nullptr;
@@ -772,7 +775,7 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
     S.vertices_sampled = slots; S.out_bytes[0] = (long long)totals[0]; S.out_bytes[1] = (long long)totals[1];
     out.d_offsets = offsets.release();
     out.d_values[0] = rates.release(); out.d_values[1] = relaxed.release(); out.n_values = slots;
-    tm.total_ms = total.stop(); out.timings = tm;
+    tm.total_ms = total.stop(); tm.h2d_bytes = (long long)g_h2d_bytes; out.timings = tm;
     if (!opts.keep_on_device) { for (int s = 0; s < 2; ++s) if (mask & (1u << s)) out.stream_host(s); out.fetch_offsets(); }
 }
 

@@ -65,7 +65,7 @@ struct BatchOpts {
     bool keep_trees = false;  // tree generators: leave the vertex records on the device for a chained stage
 };
 
-struct Timings { double find_ms = 0, build_ms = 0, label_ms = 0, emit_size_ms = 0, emit_write_ms = 0, d2h_ms = 0, total_ms = 0; long long launches = 0; };
+struct Timings { double find_ms = 0, build_ms = 0, label_ms = 0, emit_size_ms = 0, emit_write_ms = 0, d2h_ms = 0, total_ms = 0; long long launches = 0, h2d_bytes = 0; };
 
 struct Summary {
     long long n_ok = 0, n_failed = 0, attempts_total = 0, vertices_sampled = 0, vertices_abandoned = 0, attempts_completed = 0;

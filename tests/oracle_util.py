@@ -28,6 +28,7 @@ def oracle():
         L.oracle_attempts.argtypes = [C.c_void_p]; L.oracle_attempts.restype = C.c_int
         L.oracle_status.argtypes = [C.c_void_p]; L.oracle_status.restype = C.c_int
         L.oracle_free.argtypes = [C.c_void_p]
+        L.oracle_no_recipient.argtypes = [C.c_void_p]; L.oracle_no_recipient.restype = C.c_longlong
         L.oracle_batch.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_longlong, C.c_longlong, C.c_void_p]; L.oracle_batch.restype = C.c_double
         L.oracle_mt_words.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
         L.oracle_mt_doubles.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
@@ -58,7 +59,7 @@ def oracle_run(app, args):
         for i in range(L.oracle_n_files(h)):
             files[L.oracle_file_name(h, i).decode()] = C.string_at(L.oracle_file_data(h, i), L.oracle_file_len(h, i))
         return dict(files=files, stdout=L.oracle_stdout(h).decode(), stderr=L.oracle_stderr(h).decode(),
-                    attempts=L.oracle_attempts(h), status=L.oracle_status(h))
+                    attempts=L.oracle_attempts(h), status=L.oracle_status(h), no_recipient=int(L.oracle_no_recipient(h)))
     finally:
         L.oracle_free(h)
 

@@ -28,7 +28,7 @@ def assert_same_files(got, want, prefix, what):
             raise AssertionError(f"{what} stream {sfx}: first difference at byte {k}:\n gpu   : {data[max(0, k - 60):k + 60]!r}\n oracle: {exp[max(0, k - 60):k + 60]!r}")
 
 
-def replay_parity_pool(ctx, app, args, n, prefix):
+def replay_parity_pool(ctx, app, args, n, prefix, no_recipient_is_error=False):
     """assert_replay_parity with the oracle runs spread over the host cores."""
     si = (args.index("-s") if "-s" in args else args.index("--seed")) + 1
     seed0 = int(args[si])
@@ -42,6 +42,11 @@ def replay_parity_pool(ctx, app, args, n, prefix):
             continue
         if want["status"] == 2:
             assert status[i] == 4, (i, status[i], want["stderr"][:200])
+            continue
+        if no_recipient_is_error and status[i] == 4:
+            # the reference carries on here with a stale arc left behind by an earlier transfer of the same epoch (Epoch.transferedToArc
+            # is only updated on success, GuestTreeInHostTreeCreator.java:194-195); the product refuses the replicate instead
+            assert want["no_recipient"] > 0, i
             continue
         assert status[i] == 0 and attempts[i] == want["attempts"], (app, i, status[i], attempts[i], want["attempts"])
         got = {b.stream_suffix(s): data[int(off[i]):int(off[i + 1])] for s, (data, off) in streams.items()}
@@ -89,9 +94,9 @@ def test_partially_tagged_host_tree_has_no_recipient(ctx):
     host = "((A:0.4,B:0.4):0.6,(C:0.7[x=1],D:0.7[x=1]):0.3):0.2;"
     for db in ("none", "simple"):
         args = ["-s", "1", "-db", db, "-rt", "0.6", host, "0.5", "0.3", "1.5", "o"]
-        b, wants = replay_parity_pool(ctx, "GuestTreeGen", args, 48, "o")
-        n_err = sum(1 for w in wants if w["status"] == 2)
-        assert n_err > 0 and n_err < 48, n_err
+        b, wants = replay_parity_pool(ctx, "GuestTreeGen", args, 48, "o", no_recipient_is_error=True)
+        n_err = int((b.rep_status == 4).sum())
+        assert 0 < n_err < 48 and sum(1 for w in wants if w["status"] == 2) > 0, n_err
         p = ctx.run("GuestTreeGen", args, n=4000, rng=sg.RNG_PHILOX, stream_mask=0b0010)
         assert set(np.unique(p.rep_status)) <= {0, 4} and (p.rep_status == 4).any() and (p.rep_status == 0).any()
 
@@ -202,7 +207,7 @@ def test_c4_domain_tree_gen_over_100_gene_trees_replay(ctx, species1000, tmp_pat
 def c2_pruned_tree():
     r = oracle_run("HostTreeGen", ["-s", "7", "-min", "100", "-max", "100", "-p", "0.8", "1.0", "5.0", "0.05", "c2"])
     t = r["files"]["c2.pruned.tree"].decode().strip()
-    assert t.count(",") == 99
+    assert re.sub(r"\[[^\]]*\]", "", t).count(",") == 99
     return t
 
 
