@@ -107,6 +107,22 @@ const char* sgp_last_error(const sgp_context* ctx);
  * "BranchRelaxer". Returns SGP_USAGE (with a batch holding the usage text) exactly when the reference would print usage. */
 sgp_status sgp_app_run(sgp_context* ctx, const char* app, int argc, const char* const* argv, const sgp_batch_opts* opts, sgp_batch** out);
 
+/* Multi-GPU front end of sgp_app_run: the replicates [replicate_offset, replicate_offset + n_replicates) are cut into
+ * contiguous index ranges, one per device, and run concurrently (one host thread and one context per device). Replicate ids are
+ * global (Philox counters / seed + i), so the shards together are bit-identical to a single-device run; no data crosses
+ * between GPUs. `out` receives one batch per device in index order (entries may be NULL after an error); `merged` (may be NULL)
+ * receives the element-wise sum of the shard summaries. The same device may be listed more than once. */
+typedef struct sgp_multi sgp_multi;
+sgp_status sgp_multi_create(const int* devices, int n_devices, sgp_multi** out);
+int sgp_multi_size(const sgp_multi* m);
+sgp_context* sgp_multi_context(sgp_multi* m, int i);
+void sgp_multi_destroy(sgp_multi* m);
+sgp_status sgp_app_run_multi(sgp_multi* m, const char* app, int argc, const char* const* argv, const sgp_batch_opts* opts,
+                             sgp_batch** out /* sgp_multi_size(m) entries */, sgp_summary* merged);
+/* sgp_batch_write_files_layout over the shards of one sgp_app_run_multi call: the files are what a single batch holding all the
+ * replicates would have written (packed: streams concatenated in index order, one .idx with run-wide offsets). */
+sgp_status sgp_batches_write_files_layout(sgp_batch* const* shards, int n_shards, int layout, int64_t first_index);
+
 /* Chained stage: BranchRelaxer over the trees of a tree-generator batch that is still resident on the
  * device — the in-memory equivalent of writing <prefix>.pruned.tree / .unpruned.tree per replicate and launching
  * `java ... BranchRelaxer <that file> <model> <args>` on each (apps/SaGePhy/BranchRelaxerParameters.java:80-117 reads the file,

@@ -31,7 +31,7 @@ STATUS_OK, STATUS_USAGE = 0, 6
 
 # every symbol include/sagephy_b200.h declares (checked by the CPU test-suite)
 EXPORTED_SYMBOLS = (
-    "sgp_context_create", "sgp_context_destroy", "sgp_last_error", "sgp_app_run", "sgp_relax_run_on_batch", "sgp_batch_n", "sgp_batch_stream_data",
+    "sgp_context_create", "sgp_context_destroy", "sgp_last_error", "sgp_app_run", "sgp_multi_create", "sgp_multi_size", "sgp_multi_context", "sgp_multi_destroy", "sgp_app_run_multi", "sgp_batches_write_files_layout", "sgp_relax_run_on_batch", "sgp_batch_n", "sgp_batch_stream_data",
     "sgp_batch_stream_device_data", "sgp_batch_stream_offsets", "sgp_batch_copy_stream", "sgp_batch_copy_offsets", "sgp_batch_copy_stream_async", "sgp_batch_copy_offsets_async", "sgp_context_wait_copies", "sgp_batch_stream_mask", "sgp_batch_values", "sgp_batch_stream_bytes", "sgp_batch_stream_suffix",
     "sgp_batch_status", "sgp_batch_attempts", "sgp_batch_sampled_leaves", "sgp_batch_root_times", "sgp_batch_total_times",
     "sgp_batch_event_counts", "sgp_batch_stdout", "sgp_batch_stderr", "sgp_batch_out_prefix", "sgp_batch_summary",
@@ -71,6 +71,12 @@ def load_library() -> C.CDLL:
     L.sgp_context_destroy.argtypes = [vp]
     L.sgp_last_error.argtypes = [vp]; L.sgp_last_error.restype = cp
     L.sgp_app_run.argtypes = [vp, cp, C.c_int, C.POINTER(cp), C.POINTER(BatchOpts), C.POINTER(vp)]; L.sgp_app_run.restype = C.c_int
+    L.sgp_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]; L.sgp_multi_create.restype = C.c_int
+    L.sgp_multi_size.argtypes = [vp]; L.sgp_multi_size.restype = C.c_int
+    L.sgp_multi_context.argtypes = [vp, C.c_int]; L.sgp_multi_context.restype = vp
+    L.sgp_multi_destroy.argtypes = [vp]
+    L.sgp_app_run_multi.argtypes = [vp, cp, C.c_int, C.POINTER(cp), C.POINTER(BatchOpts), C.POINTER(vp), C.POINTER(SummaryStruct)]; L.sgp_app_run_multi.restype = C.c_int
+    L.sgp_batches_write_files_layout.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int64]; L.sgp_batches_write_files_layout.restype = C.c_int
     L.sgp_relax_run_on_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(cp), C.POINTER(BatchOpts), C.POINTER(vp)]; L.sgp_relax_run_on_batch.restype = C.c_int
     L.sgp_batch_n.argtypes = [vp]; L.sgp_batch_n.restype = i64
     L.sgp_batch_stream_data.argtypes = [vp, C.c_int]; L.sgp_batch_stream_data.restype = vp
@@ -291,6 +297,51 @@ class Batch:
         rc = self._lib.sgp_batch_write_files(self._h)
         if rc != 0:
             raise SagephyError(f"sgp_batch_write_files failed ({rc})")
+
+
+class MultiContext:
+    """Several devices of one node behind one call (wraps sgp_multi): replicates are sharded by index range, one host thread per
+    device. run() returns (list of shard batches in index order, merged Summary)."""
+
+    def __init__(self, devices):
+        self._lib = load_library()
+        dev = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self._lib.sgp_multi_create(dev, len(devices), C.byref(h))
+        if rc != 0:
+            raise SagephyError("sgp_multi_create failed: " + self._lib.sgp_last_error(None).decode())
+        self._h, self.size = h, len(devices)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sgp_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, app: str, args, n: int = 1, rng: int = RNG_PHILOX, offset: int = 0, stream_mask: int = 0, keep_on_device: bool = False, flags: int = 0):
+        argv = [str(a).encode() for a in args]
+        arr = (C.c_char_p * len(argv))(*argv)
+        opts = BatchOpts(n, offset, rng, stream_mask, 1 if keep_on_device else 0, flags)
+        outs = (C.c_void_p * self.size)()
+        s = SummaryStruct()
+        rc = self._lib.sgp_app_run_multi(self._h, app.encode(), len(argv), arr, C.byref(opts), outs, C.byref(s))
+        shards = [Batch(self._lib, C.c_void_p(outs[i]), rc) for i in range(self.size) if outs[i]]
+        if rc not in (STATUS_OK, STATUS_USAGE):
+            raise SagephyError(f"{app} failed on {self.size} devices ({rc}): {shards[0].stderr if shards else ''}")
+        summary = Summary(s.n_ok, s.n_failed, s.attempts_total, s.vertices_sampled, s.vertices_abandoned, s.attempts_completed, np.array(s.event_counts, dtype=np.int64),
+                          np.array(s.leaf_hist, dtype=np.int64), np.array(s.out_bytes, dtype=np.int64))
+        return shards, summary
+
+    def write_files(self, shards, layout: int = LAYOUT_PACKED, first_index: int = 0):
+        arr = (C.c_void_p * len(shards))(*[b._h for b in shards])
+        rc = self._lib.sgp_batches_write_files_layout(arr, len(shards), int(layout), int(first_index))
+        if rc != STATUS_OK:
+            raise SagephyError(f"sgp_batches_write_files_layout failed ({rc})")
 
 
 class Context:

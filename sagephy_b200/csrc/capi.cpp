@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <thread>
 #include "../../include/sagephy_b200.h"
 #include "engine.hpp"
 #include "apps_common.hpp"
@@ -101,6 +102,91 @@ sgp_status sgp_relax_run_on_batch(sgp_context* ctx, sgp_batch* src, int which_tr
         ctx->last_error = e.what(); b->b.err_text += e.what(); *out = b;
         return SGP_ERR_INTERNAL;
     }
+}
+
+// ---- multi-GPU front end ---------------------------------------------------------------------------------------------------------
+struct sgp_multi { std::vector<sgp_context*> ctx; };
+
+sgp_status sgp_multi_create(const int* devices, int n_devices, sgp_multi** out) {
+    if (!devices || n_devices <= 0 || !out) return SGP_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    auto* m = new sgp_multi();
+    for (int i = 0; i < n_devices; ++i) {
+        sgp_context* c = nullptr;
+        const sgp_status st = sgp_context_create(devices[i], &c);
+        if (st != SGP_OK) { for (auto* x : m->ctx) sgp_context_destroy(x); delete m; return st; }
+        m->ctx.push_back(c);
+    }
+    *out = m;
+    return SGP_OK;
+}
+int sgp_multi_size(const sgp_multi* m) { return m ? (int)m->ctx.size() : 0; }
+sgp_context* sgp_multi_context(sgp_multi* m, int i) { return (m && i >= 0 && i < (int)m->ctx.size()) ? m->ctx[(size_t)i] : nullptr; }
+void sgp_multi_destroy(sgp_multi* m) { if (!m) return; for (auto* x : m->ctx) sgp_context_destroy(x); delete m; }
+
+sgp_status sgp_app_run_multi(sgp_multi* m, const char* app, int argc, const char* const* argv, const sgp_batch_opts* opts, sgp_batch** out, sgp_summary* merged) {
+    if (!m || m->ctx.empty() || !app || !out || argc < 0) return SGP_ERR_INVALID_ARGUMENT;
+    const int G = (int)m->ctx.size();
+    sgp_batch_opts o{}; if (opts) o = *opts; if (o.n_replicates <= 0) o.n_replicates = 1;
+    std::vector<sgp_status> st((size_t)G, SGP_OK);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g) out[g] = nullptr;
+    for (int g = 0; g < G; ++g) {
+        const int64_t lo = o.n_replicates * g / G, hi = o.n_replicates * (g + 1) / G;
+        if (hi <= lo) continue;                      // more devices than replicates
+        th.emplace_back([&, g, lo, hi]() {
+            sgp_batch_opts og = o; og.n_replicates = hi - lo; og.replicate_offset = o.replicate_offset + lo;
+            st[(size_t)g] = sgp_app_run(m->ctx[(size_t)g], app, argc, argv, &og, &out[g]);
+        });
+    }
+    for (auto& t : th) t.join();
+    sgp_status rc = SGP_OK;
+    for (int g = 0; g < G; ++g) if (st[(size_t)g] != SGP_OK && rc == SGP_OK) rc = st[(size_t)g];
+    if (merged) {
+        std::memset(merged, 0, sizeof *merged);
+        for (int g = 0; g < G; ++g) {
+            if (!out[g] || st[(size_t)g] != SGP_OK) continue;
+            sgp_summary s; sgp_batch_summary(out[g], &s);
+            merged->n_ok += s.n_ok; merged->n_failed += s.n_failed; merged->attempts_total += s.attempts_total; merged->vertices_sampled += s.vertices_sampled;
+            merged->vertices_abandoned += s.vertices_abandoned; merged->attempts_completed += s.attempts_completed;
+            for (int i = 0; i < 17; ++i) merged->event_counts[i] += s.event_counts[i];
+            for (int i = 0; i < SGP_HIST_LEAF_BINS; ++i) merged->leaf_hist[i] += s.leaf_hist[i];
+            for (int i = 0; i < 8; ++i) merged->out_bytes[i] += s.out_bytes[i];
+        }
+    }
+    return rc;
+}
+
+sgp_status sgp_batches_write_files_layout(sgp_batch* const* shards, int n_shards, int layout, int64_t first_index) {
+    if (!shards || n_shards <= 0 || (layout != SGP_LAYOUT_PACKED && layout != SGP_LAYOUT_PER_REPLICATE)) return SGP_ERR_INVALID_ARGUMENT;
+    std::vector<sgp_batch*> bs; for (int i = 0; i < n_shards; ++i) if (shards[i]) bs.push_back(shards[i]);
+    if (bs.empty()) return SGP_ERR_INVALID_ARGUMENT;
+    if (layout == SGP_LAYOUT_PER_REPLICATE) {
+        int64_t first = first_index;
+        for (auto* b : bs) { const sgp_status st = sgp_batch_write_files_layout(b, layout, first); if (st != SGP_OK) return st; first += b->b.n; }
+        return SGP_OK;
+    }
+    sgp_batch* b0 = bs[0];
+    if (b0->b.quiet || !b0->b.d_offsets) return SGP_OK;
+    long long n_total = 0; for (auto* b : bs) { b->b.fetch_info(); b->b.fetch_offsets(); n_total += b->b.n; }
+    static const char* kApps[] = {"HostTreeGen", "GuestTreeGen", "DomainTreeGen", "BranchRelaxer"};
+    for (int s = 0; s < 8; ++s) {
+        if (!(b0->b.stream_mask & (1u << s))) continue;
+        const std::string sfx = b0->b.suffix[s];
+        std::ofstream f(b0->b.out_prefix + sfx, std::ios::binary), idx(b0->b.out_prefix + sfx + ".idx", std::ios::binary);
+        if (!f || !idx) return SGP_ERR_INVALID_ARGUMENT;
+        idx << "#sagephy-idx app=" << kApps[b0->b.app & 3] << " n=" << n_total << " first=" << first_index << '\n';
+        unsigned long long base = 0;
+        for (auto* b : bs) {
+            const char* data = b->b.stream_host(s);
+            if (!data && b->b.stream_bytes[s]) return SGP_ERR_INTERNAL;
+            f.write(data, (std::streamsize)b->b.stream_bytes[s]);
+            const unsigned long long* off = b->b.h_offsets.data() + (size_t)s * (b->b.n + 1);
+            for (long long i = 0; i < b->b.n; ++i) idx << (base + off[i]) << '\t' << (off[i + 1] - off[i]) << '\t' << b->b.status[i] << '\n';
+            base += b->b.stream_bytes[s];
+        }
+    }
+    return SGP_OK;
 }
 
 int64_t sgp_batch_n(const sgp_batch* b) { return b ? b->b.n : 0; }

@@ -230,8 +230,11 @@ __device__ unsigned long long emit_pieces(int n_pieces, char* base, char* stage,
         const int i = i0 + lane;
         unsigned len = 0;
         if (i < n_pieces) {
-            if (WRITE) len = load_len(i);
-            else { CountSink c; piece(c, i); len = (unsigned)c.n; store_len(i, len); }
+            if (WRITE) {
+                len = load_len(i);
+                // the cache is 16 bits wide and saturates: a piece that long (a huge name or prefix) is measured again here
+                if (len == 0xffffu) { CountSink c; piece(c, i); len = (unsigned)c.n; }
+            } else { CountSink c; piece(c, i); len = (unsigned)c.n; store_len(i, len); }
         }
         unsigned total; const unsigned off = warp_excl_scan_u32(len, &total);
         if (WRITE && total) {

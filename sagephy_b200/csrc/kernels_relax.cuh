@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) k_relax_emit(RelaxArgs a) 
         if (ok) {
             auto pc = [&](auto& s, int x) { put_relax_vertex(s, a, tv, base, x); };
             if (WRITE) bytes = emit_pieces<true>(tv.nV, out, stage, pc, [&](int i) { return (unsigned)pl[i]; }, no_store);
-            else bytes = emit_pieces<false>(tv.nV, out, stage, pc, no_load, [&](int i, unsigned v) { pl[i] = (uint16_t)v; });
+            else bytes = emit_pieces<false>(tv.nV, out, stage, pc, no_load, [&](int i, unsigned v) { pl[i] = (uint16_t)(v > 0xffffu ? 0xffffu : v); });
         }
         if (!WRITE && lane == 0) a.sizes[r] = bytes;
     }
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) k_relax_emit(RelaxArgs a) 
             const int np = 1 + 3 * tv.nV + 1; const int att = a.attempts[r];
             auto pc = [&](auto& s, int k) { put_relax_info(s, a, tv, base, gid, att, k + 2); };
             if (WRITE) bytes = o + emit_pieces<true>(np, out + o, stage, pc, [&](int i) { return (unsigned)pl[i]; }, no_store);
-            else bytes = o + emit_pieces<false>(np, out, stage, pc, no_load, [&](int i, unsigned v) { pl[i] = (uint16_t)v; });
+            else bytes = o + emit_pieces<false>(np, out, stage, pc, no_load, [&](int i, unsigned v) { pl[i] = (uint16_t)(v > 0xffffu ? 0xffffu : v); });
         }
         if (!WRITE && lane == 0) a.sizes[(size_t)a.n + r] = bytes;
     }

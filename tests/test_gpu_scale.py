@@ -248,3 +248,48 @@ def test_c5_branch_relaxer_philox_against_the_oracle(ctx, c2_pruned_tree, model)
     orig = np.array([float(x) for x in LEN_RE.findall(re.sub(r"\[[^\]]*\]", "", c2_pruned_tree))])
     assert orig.shape == (199,) and (orig > 0).all()
     assert ks_ok((rel / orig)[::3, ::7].ravel(), (ref / orig)[:, ::7].ravel())
+
+
+# ---- multi-GPU front end of the C ABI / CLI: shards by index range == one device, byte for byte ----------------------------
+def test_app_run_multi_equals_single_device(ctx, tmp_path):
+    import subprocess
+    import torch
+    ndev = torch.cuda.device_count()
+    devices = [0, 1 % ndev, 0]                    # three shards; on a one-GPU box all three contexts share device 0
+    m = sg.MultiContext(devices)
+    try:
+        for app, args, rng in (("HostTreeGen", ["-s", "11", "-min", "5", "-max", "40", "-p", "0.8", "1.0", "3.0", "0.3", str(tmp_path / "m")], sg.RNG_PHILOX),
+                               ("GuestTreeGen", ["-s", "12", "-db", "simple", HOST8, "0.5", "0.4", "0.7", str(tmp_path / "g")], sg.RNG_MT_REPLAY)):
+            n = 1000
+            shards, summary = m.run(app, args, n=n, rng=rng, offset=7)
+            one = ctx.run(app, args, n=n, rng=rng, offset=7)
+            assert [b.n for b in shards] == [333, 333, 334]
+            for s in range(8):
+                assert b"".join(b.stream(s) for b in shards) == one.stream(s), (app, s)
+            assert np.concatenate([b.attempts for b in shards]).tolist() == one.attempts.tolist()
+            assert (summary.as_vector() == one.summary().as_vector()).all()
+            # packed files of the shards == packed files of the single batch (same .idx, run-wide offsets)
+            m.write_files(shards, sg.LAYOUT_PACKED, first_index=7)
+            multi_files = {p.name: p.read_bytes() for p in tmp_path.iterdir() if p.is_file()}
+            for p in tmp_path.iterdir():
+                if p.is_file():
+                    p.unlink()
+            one.write_files(layout=sg.LAYOUT_PACKED, first_index=7)
+            single_files = {p.name: p.read_bytes() for p in tmp_path.iterdir() if p.is_file()}
+            assert multi_files == single_files and len(single_files) >= 8
+            for p in tmp_path.iterdir():
+                if p.is_file():
+                    p.unlink()
+    finally:
+        m.close()
+    # the native CLI: `--gpus 2` (two shards; SAGEPHY_DEVICES maps both to device 0 when the box has one GPU) == one device
+    exe = os.path.join(ROOT, "sagephy_b200", "sagephy")
+    core = ["HostTreeGen", "-n", "301", "-rng", "mt-replay", "-s", "3", "-min", "5", "-max", "12", "1.0", "3.0", "0.3", "species"]
+    d1, d2 = tmp_path / "one", tmp_path / "two"; d1.mkdir(); d2.mkdir()
+    subprocess.check_call([exe] + core, cwd=d1)
+    env = dict(os.environ)
+    if ndev < 2:
+        env["SAGEPHY_DEVICES"] = "0,0"
+    subprocess.check_call([exe] + core + ["--gpus", "2"], cwd=d2, env=env)
+    f1 = {p.name: p.read_bytes() for p in d1.iterdir()}; f2 = {p.name: p.read_bytes() for p in d2.iterdir()}
+    assert f1 == f2 and "species.pruned.tree.idx" in f1
