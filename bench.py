@@ -118,7 +118,8 @@ def cpu_reference(app, args, n_trees, procs):
     from concurrent.futures import ProcessPoolExecutor
     per = max(1, n_trees // procs)
     t0 = time.perf_counter()
-    with ProcessPoolExecutor(procs) as ex:
+    import multiprocessing
+    with ProcessPoolExecutor(procs, mp_context=multiprocessing.get_context("spawn")) as ex:
         res = list(ex.map(_cpu_worker, [(app, args, i * per, per) for i in range(procs)]))
     wall = time.perf_counter() - t0
     ok = sum(r[0] for r in res)
@@ -145,7 +146,8 @@ def run_reference_arm(args):
     for _ in range(args.steps):
         from concurrent.futures import ProcessPoolExecutor
         per = max(1, per_step // procs)
-        with ProcessPoolExecutor(procs) as ex:
+        import multiprocessing
+        with ProcessPoolExecutor(procs, mp_context=multiprocessing.get_context("spawn")) as ex:
             res = list(ex.map(_cpu_worker, [("HostTreeGen", C2_ARGS, i * per, per) for i in range(procs)]))
         ok += sum(r[0] for r in res); t_sum += max(r[1] for r in res)
     value = ok / t_sum

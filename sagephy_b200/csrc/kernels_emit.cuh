@@ -252,6 +252,75 @@ __device__ unsigned long long emit_pieces(int n_pieces, char* base, char* stage,
     return running;
 }
 
+// .info streams: one THREAD per (replicate, file). A file is ~10-30 short lines, so "lane per line" left most of a warp idle and
+// cost ~8 000 warp instructions per replicate; here the 32 lanes of a warp format 32 files in lock step (same line number at the
+// same time) into private shared-memory slots, and the warp then flushes the slots one after the other with aligned 16-byte
+// stores. Files that do not fit a slot (an "Arguments:" line that embeds a whole Newick host tree) take the cooperative path:
+// header text copied by the whole warp straight from the constant blob, lines written by the owning lane.
+constexpr int kInfoSlot = 1024;
+template <bool PRUNED, class Sink> __device__ __forceinline__ void put_info_file(Sink& s, const EmitArgs& a, const RepInfo& inf, long long gid, int first_line) {
+    const int L = info_lines(a, PRUNED);
+    for (int ln = first_line; ln < L; ++ln) put_info_line<PRUNED>(s, a, inf, gid, ln);
+}
+template <bool WRITE>
+__global__ void __launch_bounds__(32) k_emit_info(EmitArgs a) {
+    __shared__ __align__(16) char s_slot[32][kInfoSlot];
+    const int lane = threadIdx.x;
+    const long long item = (long long)blockIdx.x * 32 + lane;
+    const long long r = item >> 1; const bool pr = (item & 1) != 0;
+    const int st = pr ? ST_PRUNED_INFO : ST_UNPRUNED_INFO;
+    const bool active = r < a.n && (a.stream_mask & (1u << st));
+    const long long gid = a.rep_base + (active ? r : 0);
+    const RepInfo& inf = a.info[active ? r : 0];
+    const bool ok = active && inf.status == REP_OK;
+    const bool note = active && !ok && pr && inf.status == REP_MAX_ATTEMPTS;      // the reference writes only the failure note
+    // total length (closed form for the long constant parts, the formatting code with a counting sink for the rest)
+    unsigned long long total = 0;
+    if (ok) { CountSink c; if (pr) put_info_file<true>(c, a, inf, gid, 0); else put_info_file<false>(c, a, inf, gid, 0); total = (unsigned long long)c.n; }
+    else if (note) total = 65;
+    if (!WRITE) { if (active) a.sizes[(size_t)st * a.n + r] = total; return; }
+    char* dst = active ? a.out[st] + a.offsets[(size_t)st * (a.n + 1) + r] : nullptr;
+    const int mis = (int)(reinterpret_cast<unsigned long long>(dst) & 15ull);
+    const bool staged = total > 0 && total + 16 <= (unsigned long long)kInfoSlot;
+    if (staged) {
+        SmemSink m{(uint32_t)__cvta_generic_to_shared(&s_slot[lane][0]) + (uint32_t)mis};
+        if (note) put_lit(m, "Failed to produce valid pruned tree within max allowed attempts.\n");
+        else if (pr) put_info_file<true>(m, a, inf, gid, 0); else put_info_file<false>(m, a, inf, gid, 0);
+    }
+    __syncwarp();
+    unsigned todo = __ballot_sync(0xffffffffu, staged);
+    while (todo) {
+        const int l = __ffs(todo) - 1; todo &= todo - 1;
+        char* d = reinterpret_cast<char*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst), l));
+        const unsigned len = (unsigned)__shfl_sync(0xffffffffu, (unsigned)total, l);
+        const int m = __shfl_sync(0xffffffffu, mis, l);
+        flush_stage(&s_slot[l][0], m, d, len);
+    }
+    // oversize files, one after the other
+    unsigned big = __ballot_sync(0xffffffffu, total > 0 && !staged);
+    while (big) {
+        const int l = __ffs(big) - 1; big &= big - 1;
+        char* d = reinterpret_cast<char*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst), l));
+        const long long g = __shfl_sync(0xffffffffu, gid, l);
+        const char* h0 = a.app == 0 ? "# HOSTTREEGEN\nArguments:\t" : a.app == 1 ? "# GUESTTREEGEN\nArguments:\t" : "# DOMAINTREEGEN\nArguments:\t";
+        const int h0len = a.app == 0 ? 25 : a.app == 1 ? 26 : 27;
+        for (int i = lane; i < h0len; i += 32) d[i] = h0[i];
+        if (a.args_pre_off16[0] >= 0) {
+            char* q = d + h0len; const int m = (int)(reinterpret_cast<unsigned long long>(q) & 15ull);
+            flush_stage(a.blob + a.args_pre_off16[m] - m, m, q, (unsigned)a.args_pre_len);       // source congruent to destination mod 16
+        } else for (int i = lane; i < a.args_pre_len; i += 32) d[h0len + i] = a.blob[a.args_pre_off + i];
+        unsigned long long o = (unsigned long long)h0len + a.args_pre_len;
+        if (a.seed_mode) {
+            const int seedlen = seed_dec_len(a.sseed, a.blob, (unsigned long long)g);
+            if (lane == 0) { MemSink ms{d + o}; put_seed(ms, a.sseed, a.blob, (unsigned long long)g); }
+            for (int i = lane; i < a.args_post_len; i += 32) d[o + seedlen + i] = a.blob[a.args_post_off + i];
+            o += (unsigned long long)seedlen + a.args_post_len;
+        }
+        if (lane == 0) d[o] = '\n';
+        if (lane == l) { MemSink ms{d + o + 1}; if (pr) put_info_file<true>(ms, a, inf, gid, 2); else put_info_file<false>(ms, a, inf, gid, 2); }
+    }
+}
+
 template <bool WRITE, int STREAM>
 __global__ void __launch_bounds__(kEmitWarps * 32, WRITE ? 8 : 10) k_emit(EmitArgs a) {
     __shared__ __align__(16) char s_stage[kEmitWarps][kStageBytes];

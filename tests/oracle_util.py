@@ -109,6 +109,12 @@ def _batch_worker(job):
     return oracle_batch(app, args, first, n)[1]
 
 
+def _mp_context():
+    # "spawn": the parent usually holds a CUDA context and worker threads by now; fork()ing such a process is not safe
+    import multiprocessing
+    return multiprocessing.get_context("spawn")
+
+
 def pool_size(procs=None):
     return max(1, min(procs or (os.cpu_count() or 1), 32))
 
@@ -119,7 +125,7 @@ def oracle_run_many(jobs, procs=None):
     jobs = list(jobs)
     if len(jobs) <= 1 or pool_size(procs) == 1:
         return [_run_worker(j) for j in jobs]
-    with ProcessPoolExecutor(pool_size(procs)) as ex:
+    with ProcessPoolExecutor(pool_size(procs), mp_context=_mp_context()) as ex:
         return list(ex.map(_run_worker, jobs, chunksize=max(1, len(jobs) // (4 * pool_size(procs)))))
 
 
@@ -131,6 +137,6 @@ def oracle_batch_parallel(app, args, first, n, procs=None):
         return oracle_batch(app, args, first, n)[1]
     chunks = 4 * p
     edges = [first + (n * k) // chunks for k in range(chunks + 1)]
-    with ProcessPoolExecutor(p) as ex:
+    with ProcessPoolExecutor(p, mp_context=_mp_context()) as ex:
         parts = list(ex.map(_batch_worker, [(app, list(args), edges[k], edges[k + 1] - edges[k]) for k in range(chunks) if edges[k + 1] > edges[k]]))
     return np.concatenate(parts, axis=0)
