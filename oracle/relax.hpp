@@ -129,14 +129,14 @@ inline double chi2_quantile(double p, double k) {     // math/ChiSquared.java:23
 }
 
 struct RateModelO {
-    enum Kind { CONSTANT, EXPONENTIAL, GAMMA, LOGNORMAL, NORMAL, UNIFORM, SAMPLES, ACTK98, ACRY07, ACABY02, ACLBPL07 } kind = CONSTANT;
+    enum Kind { CONSTANT, EXPONENTIAL, GAMMA, LOGNORMAL, NORMAL, UNIFORM, SAMPLES, ACTK98, ACRY07, ACABY02, ACLBPL07, IIDRK11 } kind = CONSTANT;
     double a = 0, b = 0, c = 0, d = 0, sigma = 0; std::vector<double> samples; std::string file;
     std::string name() const {
         static const char* n[] = {"ConstantRates", "IIDExponentialRates", "IIDGammaRates", "IIDLogNormalRates", "IIDNormalRates", "IIDUniformRates", "IIDSamplesFromFileRates",
-                                  "ThorneKishino98Rates", "RannalaYang07Rates", "ArisBrosouYang02Rates", "LepageBryantPhillipeLartillot07Rates"};
+                                  "ThorneKishino98Rates", "RannalaYang07Rates", "ArisBrosouYang02Rates", "LepageBryantPhillipeLartillot07Rates", "IIDRasmussenKellis11Rates"};
         return n[kind];
     }
-    bool strict_tree() const { return kind == ACTK98 || kind == ACRY07; }      // lengthsMustBeUltrametric()
+    bool strict_tree() const { return kind == ACTK98 || kind == ACRY07 || kind == IIDRK11; }      // lengthsMustBeUltrametric()
     // new LogNormalDistribution(mu, sigma2).sampleValue(prng)  (math/LogNormalDistribution.java:39-48,196-205)
     static double lognormal(double mu, double sigma2, JavaMT& prng) {
         if (sigma2 <= 0.0) throw std::invalid_argument("IllegalArgumentException: Cannot have non-positive sigma^2 for log-normal distribution.");
@@ -247,8 +247,172 @@ inline std::vector<std::pair<std::string, std::string>> RateModelO::params() con
         case ACRY07: return hashmap_order({{"start rate", D(a)}, {"sigma2", D(b)}}, 2);
         case ACABY02: return hashmap_order({{"start rate", D(a)}}, 1);
         case ACLBPL07: return hashmap_order({{"start rate", D(a)}, {"mu", D(b)}, {"theta", D(c)}, {"sigma", D(d)}}, 2);
+        case IIDRK11: return {};       // getModelParameters returns an empty map (IIDRasmussenKellis11RateModel.java:104-108)
     }
     return {};
+}
+
+// ---- IIDRK11: host-specific gamma rates (apps/SaGePhy/IIDRasmussenKellis11RateModel.java:60-180) --------------------------------------
+// Everything the constructor derives from the two trees and the leaf map: RBTree arrays (topology/RBTree.java:56-85), times from
+// branch lengths (io/PrIMENewickTree.java:733-779 with io/PrIMENewickTreeVerifier.java:237-270: scanning the BFS list backwards, the
+// first child to report sets its parent's time), PARAMS=(k,theta) per host vertex (io/PrIMENewickTree.java:74,382-387), the
+// most-parsimonious reconciliation sigma (topology/MPRMap.java:60-86,147-156 on the naive LCA of topology/RBTree.java:243-258).
+struct RK11Tree {
+    int n = 0, root = -1;
+    std::vector<int> parent, left, right; std::vector<double> vt, at; std::vector<std::optional<std::string>> names;
+    std::vector<std::optional<std::pair<double, double>>> params;
+    void build(const NTree& t) {
+        auto bfs = t.vertices_bfs(); n = (int)bfs.size(); root = t.root->number;
+        parent.assign(n, -1); left.assign(n, -1); right.assign(n, -1); names.resize(n); params.resize(n);
+        for (NVertex* v : bfs) if (!v->children.empty() && v->children.size() != 2) throw TopologyException("Cannot create RBTree from non-bifurcating NewickTree.");
+        bool any_bl = false;
+        at.assign(n, std::nan("")); vt.assign(n, std::nan(""));
+        for (NVertex* v : bfs) {
+            const int i = v->number;
+            if (v->parent) parent[i] = v->parent->number;
+            if (!v->children.empty()) { left[i] = v->children[0]->number; right[i] = v->children[1]->number; }
+            names[i] = v->name;
+            if (v->bl) { at[i] = *v->bl; any_bl = true; }
+            if (v->meta) {
+                // PARAMS="?(\([0-9+-.eE ]+[,0-9+-.eE ]+\))"? -> "[k,theta]" -> doubles
+                const std::string& m = *v->meta; size_t pos = m.find("PARAMS=");
+                if (pos != std::string::npos) {
+                    size_t k = pos + 7; if (k < m.size() && m[k] == '"') ++k;
+                    if (k < m.size() && m[k] == '(') {
+                        size_t e = m.find(')', k);
+                        if (e != std::string::npos) {
+                            std::string body; for (size_t q = k + 1; q < e; ++q) if (m[q] != ' ') body.push_back(m[q]);
+                            size_t c = body.find(',');
+                            if (c != std::string::npos) params[i] = std::make_pair(parse_double(body.substr(0, c)), parse_double(body.substr(c + 1)));
+                        }
+                    }
+                }
+            }
+        }
+        if (!any_bl) throw NewickIOException("Cannot create time map; times missing in tree.");
+        for (int i = n - 1; i > 0; --i) {
+            NVertex* v = bfs[i]; const int x = v->number;
+            if (v->is_leaf()) vt[x] = 0.0;
+            if (!std::isnan(vt[x])) { const int a = v->parent->number; if (std::isnan(vt[a])) vt[a] = vt[x] + at[x]; }
+        }
+        if (n == 1) vt[0] = 0.0;
+    }
+    bool has_params() const { for (auto& p : params) if (p) return true; return false; }
+    int lca(int x, int y) const {
+        std::vector<int> visited;
+        for (;;) {
+            if (x != -1) { if (std::find(visited.begin(), visited.end(), x) != visited.end()) return x; visited.push_back(x); x = parent[x]; }
+            if (y != -1) { if (std::find(visited.begin(), visited.end(), y) != visited.end()) return y; visited.push_back(y); y = parent[y]; }
+        }
+    }
+};
+struct RK11Model {
+    RK11Tree host, guest; std::vector<int> sigma; double scale = 1.0;
+    void init(const NTree& g, const NTree& h, const std::vector<std::pair<std::string, std::string>>& gs, double scaleFact) {
+        try {
+            host.build(h); guest.build(g); scale = scaleFact;
+            // LinkedHashMap semantics of GuestHostMap.add: a repeated guest leaf keeps its position and takes the last host leaf
+            std::vector<std::pair<std::string, std::string>> map;
+            for (auto& e : gs) { bool found = false; for (auto& m : map) if (m.first == e.first) { m.second = e.second; found = true; break; } if (!found) map.push_back(e); }
+            sigma.assign(guest.n, 0);
+            int n_leaves = 0;
+            for (int l = 0; l < guest.n; ++l) {
+                if (guest.left[l] != -1) continue;
+                ++n_leaves;
+                const std::string gname = guest.names[l] ? *guest.names[l] : std::string("null");
+                const std::string* hn = nullptr; for (auto& m : map) if (m.first == gname) hn = &m.second;
+                if (!hn) throw std::invalid_argument("IllegalArgumentException: Cannot find guest leaf " + gname + " in guest-to-host leaf map.");
+                int hv = -1; for (int v = 0; v < host.n; ++v) if (host.names[v] && *host.names[v] == *hn) hv = v;       // HashMap.put: the last vertex with that name wins
+                if (hv < 0) throw std::invalid_argument("IllegalArgumentException: Cannot find host leaf " + *hn + " corresponding to guest leaf " + gname + ".");
+                sigma[l] = hv;
+            }
+            if (n_leaves != (int)map.size()) throw std::invalid_argument("IllegalArgumentException: Mismatch in the number of guest tree leaves and guest-to-host map items: " + std::to_string(n_leaves) + " vs. " + std::to_string(map.size()) + ".");
+            compute_sigma(guest.root);
+            if (!host.has_params()) throw std::runtime_error("NullPointerException");        // getVertexParamsMap returns null
+            if (std::isnan(host.at[host.root])) host.at[host.root] = 0.0;
+            if (!host.params[host.root]) host.params[host.root] = std::make_pair(1000.0, 0.001);
+            if (std::isnan(guest.at[guest.root])) guest.at[guest.root] = 0.0;
+        } catch (std::exception& e) {
+            throw std::invalid_argument(std::string("IllegalArgumentException: Invalid input to rate model: ") + e.what());
+        }
+        const int x = guest.root, y = host.root;
+        if (std::fabs(guest.vt[x] + guest.at[x] - host.vt[y] - host.at[y]) > 1e-4) throw std::invalid_argument("IllegalArgumentException: Invalid guest and host trees: Time scales do not agree.");
+    }
+    int compute_sigma(int x) {
+        if (guest.left[x] == -1) return sigma[x];
+        const int l = compute_sigma(guest.left[x]), r = compute_sigma(guest.right[x]);
+        return sigma[x] = host.lca(l, r);
+    }
+    int enclosing_arc(int x) const {
+        int lo = sigma[x]; const double xt = guest.vt[x];
+        for (;;) {
+            if (lo == host.root) return lo;
+            const int lop = host.parent[lo];
+            if (host.vt[lop] >= xt) return lo;
+            lo = lop;
+        }
+    }
+    void rates(JavaMT& prng, std::vector<double>& out) const {       // getRates :110-157
+        std::vector<double> ws, rs;
+        for (int x = 0; x < guest.n; ++x) {
+            const int lo = enclosing_arc(x);
+            const int up = guest.parent[x] == -1 ? host.root : enclosing_arc(guest.parent[x]);
+            ws.clear(); rs.clear();
+            const double l = guest.at[x];
+            int h = lo;
+            for (;;) {
+                if (!host.params[h]) throw std::runtime_error("NullPointerException");
+                const double k = host.params[h]->first, theta = host.params[h]->second;
+                if (k <= 0.0 || theta <= 0.0) throw std::invalid_argument("IllegalArgumentException: Cannot have non-positive shape or scale for gamma distribution.");
+                ws.push_back(host.at[h] / l);
+                rs.push_back(chi2_quantile(prng.nextDouble(), 2 * k) * theta / 2);
+                if (h == up) break;
+                h = host.parent[h];
+                if (h < 0) throw std::out_of_range("ArrayIndexOutOfBoundsException: -1");
+            }
+            if (ws.size() == 1) ws[0] = 1.0;
+            else {
+                double dt = guest.vt[x] - host.vt[lo];
+                ws[0] = std::max(0.0, ws[0] - dt / l);
+                if (guest.parent[x] != -1) { dt = guest.vt[guest.parent[x]] - host.vt[up]; ws.back() = std::max(0.0, dt / l); }
+            }
+            double r = 0.0;
+            for (size_t i = 0; i < ws.size(); ++i) r += ws[i] * rs[i];
+            r *= scale;
+            out[x] = r;
+        }
+    }
+};
+// io/GuestHostMapReader.java:44-56: one "guest host" pair per line, split on blanks and tabs, reading stops at the first empty line
+inline std::vector<std::pair<std::string, std::string>> read_guest_host_map(const std::string& path) {
+    std::ifstream f(path); if (!f) throw std::invalid_argument("FileNotFoundException: " + path + " (No such file or directory)");
+    std::vector<std::pair<std::string, std::string>> out; std::string line;
+    while (std::getline(f, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        std::string ln = trim_java(line);
+        if (ln.empty()) break;
+        std::vector<std::string> parts; size_t i = 0;
+        while (i < ln.size()) { size_t j = i; while (j < ln.size() && ln[j] != ' ' && ln[j] != '\t') ++j; parts.push_back(ln.substr(i, j - i)); i = j; while (i < ln.size() && (ln[i] == ' ' || ln[i] == '\t')) ++i; }
+        if (parts.size() < 2) throw std::out_of_range("ArrayIndexOutOfBoundsException: 1");
+        out.push_back({parts[0], parts[1]});
+    }
+    return out;
+}
+
+// PrIMENewickTreeVerifier.runStandardTestSuite (io/PrIMENewickTreeVerifier.java:37-46) as far as plain Newick input can
+// trip it: leaf names present and unique (:79-94), branch lengths on every vertex but the root (:101-103,143-152)
+inline void strict_newick_checks(const NTree& t) {
+    auto bfs = t.vertices_bfs(); const int n = (int)bfs.size();
+    bool any_name = false, any_bl = false; for (NVertex* v : bfs) { any_name |= (bool)v->name; any_bl |= (bool)v->bl; }
+    if (any_name) {
+        std::set<std::string> seen;
+        for (NVertex* v : bfs) {
+            if (!v->is_leaf()) continue;
+            if (!v->name) throw NewickIOException("Missing name on Newick vertex " + std::to_string(v->number) + ".");
+            if (!seen.insert(*v->name).second) throw NewickIOException("Duplicate vertex name '" + *v->name + "' found in vertex " + std::to_string(v->number) + ".");
+        }
+    }
+    if (any_bl) for (int i = 0; i < n; ++i) for (NVertex* v : bfs) if (v->number == i && !v->bl && v != t.root) throw NewickIOException("Missing branch length on Newick vertex " + std::to_string(i) + ".");
 }
 
 inline const std::vector<OptSpec>& relax_specs() {
@@ -297,23 +461,19 @@ inline void run_branch_relaxer(const std::vector<std::string>& args, Outputs& o,
         else if (ieq(model, "ACLBPL07")) {
             m.kind = RateModelO::ACLBPL07; m.a = parse_double(arg(2)); m.b = parse_double(arg(3)); m.c = parse_double(arg(4)); m.d = parse_double(arg(5));
             if (2 * m.c * m.b < m.d * m.d) throw std::invalid_argument("IllegalArgumentException: Invalid parameters for CIR process: 0 rate may be achieved.");
-        } else throw std::invalid_argument("oracle: rate model outside the accelerated path (IIDRK11 needs a host tree and a guest-to-host map): " + model);
+        } else if (ieq(model, "IIDRK11")) m.kind = RateModelO::IIDRK11;        // BranchRelaxerParameters.java:108-113, built below once the tree is read
+        else throw std::invalid_argument("IllegalArgumentException: Invalid rate model identifier: " + model);
         std::unique_ptr<NTree> t = file_exists(arg(0)) ? nw_read_tree(read_file(arg(0))) : nw_read_tree(arg(0));
-        auto bfs = t->vertices_bfs(); int n = (int)bfs.size();
-        if (m.strict_tree()) {
-            // PrIMENewickTreeVerifier.runStandardTestSuite (io/PrIMENewickTreeVerifier.java:37-46) as far as plain Newick input can
-            // trip it: leaf names present and unique (:79-94), branch lengths on every vertex but the root (:101-103,143-152)
-            bool any_name = false, any_bl = false; for (NVertex* v : bfs) { any_name |= (bool)v->name; any_bl |= (bool)v->bl; }
-            if (any_name) {
-                std::set<std::string> seen;
-                for (NVertex* v : bfs) {
-                    if (!v->is_leaf()) continue;
-                    if (!v->name) throw NewickIOException("Missing name on Newick vertex " + std::to_string(v->number) + ".");
-                    if (!seen.insert(*v->name).second) throw NewickIOException("Duplicate vertex name '" + *v->name + "' found in vertex " + std::to_string(v->number) + ".");
-                }
-            }
-            if (any_bl) for (int i = 0; i < n; ++i) for (NVertex* v : bfs) if (v->number == i && !v->bl && v != t->root) throw NewickIOException("Missing branch length on Newick vertex " + std::to_string(i) + ".");
+        RK11Model rk; std::unique_ptr<NTree> rk_host;
+        if (m.kind == RateModelO::IIDRK11) {
+            strict_newick_checks(*t);
+            rk_host = file_exists(arg(2)) ? nw_read_tree(read_file(arg(2))) : nw_read_tree(arg(2));
+            strict_newick_checks(*rk_host);
+            auto gs = read_guest_host_map(arg(3));
+            rk.init(*t, *rk_host, gs, parse_double(arg(4)));
         }
+        auto bfs = t->vertices_bfs(); int n = (int)bfs.size();
+        if (m.strict_tree()) strict_newick_checks(*t);
         for (NVertex* v : bfs) if (v->children.size() == 1) throw TopologyException("Cannot create RTree from collapsable NewickTree.");
         for (NVertex* v : bfs) if (v->is_leaf() && !v->name) throw std::runtime_error("NullPointerException: Missing leaf name in vertex " + std::to_string(v->number) + ".");
         std::vector<double> orig(n, std::nan("")); bool has = false;
@@ -329,7 +489,8 @@ inline void run_branch_relaxer(const std::vector<std::string>& args, Outputs& o,
         for (;;) {
             if (attempts > maxAttempts) { o.err += "Failed to create valid rates within max allowed attempts.\n"; if (st) { st->status = 1; st->attempts = attempts; } return; }
             if (m.kind == RateModelO::SAMPLES) { /* the reference re-reads the file on every call; same values */ }
-            if (m.kind >= RateModelO::ACTK98) m.rates_autocorrelated(topo, parent, orig, prng, rates);
+            if (m.kind == RateModelO::IIDRK11) rk.rates(prng, rates);
+            else if (m.kind >= RateModelO::ACTK98) m.rates_autocorrelated(topo, parent, orig, prng, rates);
             else for (int x = 0; x < n; ++x) rates[x] = m.sample(prng);
             ++attempts;
             bool ok = true;

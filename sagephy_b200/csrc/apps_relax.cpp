@@ -69,6 +69,117 @@ RelaxTreeTemplate make_template(const FlatTree& t, bool keep_interior, bool stri
     }
     return r;
 }
+
+// ---- IIDRK11 --------------------------------------------------------------------------------------------------------------------
+// What the constructor of apps/SaGePhy/IIDRasmussenKellis11RateModel.java:60-101 derives from its inputs, plus the part of getRates
+// (:110-157) that does not depend on the random draws: which host arcs the branch above every guest vertex passes over, lowest
+// first, and the weight of each. Times come from branch lengths only (io/PrIMENewickTree.java:733-779 with the rule of
+// io/PrIMENewickTreeVerifier.java:237-270); VT= / AT= / TT= tags are not modelled.
+struct RkTree {
+    int n = 0, root = -1; std::vector<int> parent, left, right; std::vector<double> vt, at; std::vector<double> k, theta; std::vector<uint8_t> has_params;
+    void build(const FlatTree& t) {
+        n = t.n; root = t.root; parent = t.parent; left.assign(n, -1); right.assign(n, -1);
+        for (int v = 0; v < n; ++v) {
+            if (t.n_children[v] != 0 && t.n_children[v] != 2) throw SgpError("Cannot create RBTree from non-bifurcating NewickTree.");
+            if (t.n_children[v] == 2) { left[v] = t.first_child[v]; right[v] = t.next_sibling[left[v]]; }
+        }
+        at.assign(n, std::nan("")); vt.assign(n, std::nan("")); bool any = false;
+        for (int v = 0; v < n; ++v) if (t.has_bl[v]) { at[v] = t.bl[v]; any = true; }
+        if (!any) throw SgpError("Cannot create time map; times missing in tree.");
+        for (int i = n - 1; i > 0; --i) {
+            const int v = t.bfs[i];
+            if (t.n_children[v] == 0) vt[v] = 0.0;
+            if (!std::isnan(vt[v])) { const int a = parent[v]; if (std::isnan(vt[a])) vt[a] = vt[v] + at[v]; }
+        }
+        if (n == 1) vt[0] = 0.0;
+        k.assign(n, std::nan("")); theta.assign(n, std::nan("")); has_params.assign(n, 0);
+        for (int v = 0; v < n; ++v) {         // PARAMS="?(k,theta)"? (io/PrIMENewickTree.java:74,382-387)
+            if (!t.has_meta[v]) continue;
+            const std::string& m = t.meta[v]; size_t pos = m.find("PARAMS=");
+            if (pos == std::string::npos) continue;
+            size_t q = pos + 7; if (q < m.size() && m[q] == '"') ++q;
+            if (q >= m.size() || m[q] != '(') continue;
+            const size_t e = m.find(')', q); if (e == std::string::npos) continue;
+            std::string body; for (size_t j = q + 1; j < e; ++j) if (m[j] != ' ') body.push_back(m[j]);
+            const size_t c = body.find(','); if (c == std::string::npos) continue;
+            k[v] = to_double(body.substr(0, c)); theta[v] = to_double(body.substr(c + 1)); has_params[v] = 1;
+        }
+    }
+    int lca(int x, int y) const {            // topology/RBTree.java:243-258
+        std::vector<int> seen;
+        for (;;) {
+            if (x != -1) { for (int s : seen) if (s == x) return x; seen.push_back(x); x = parent[x]; }
+            if (y != -1) { for (int s : seen) if (s == y) return y; seen.push_back(y); y = parent[y]; }
+        }
+    }
+};
+
+void build_rk11(const FlatTree& gt, const FlatTree& ht, const std::string& map_path, double scale, RelaxConfig& cfg) {
+    RkTree G, H; std::vector<int> sigma;
+    try {
+        H.build(ht); G.build(gt);
+        // io/GuestHostMapReader.java:44-56 into the LinkedHashMap of topology/GuestHostMap.java:25-34
+        std::ifstream f(map_path); if (!f) throw SgpError("FileNotFoundException: " + map_path + " (No such file or directory)");
+        std::vector<std::pair<std::string, std::string>> map; std::string line;
+        while (std::getline(f, line)) {
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            const std::string ln = java_trim(line);
+            if (ln.empty()) break;
+            std::vector<std::string> parts; size_t i = 0;
+            while (i < ln.size()) { size_t j = i; while (j < ln.size() && ln[j] != ' ' && ln[j] != '\t') ++j; parts.push_back(ln.substr(i, j - i)); i = j; while (i < ln.size() && (ln[i] == ' ' || ln[i] == '\t')) ++i; }
+            if (parts.size() < 2) throw SgpError("ArrayIndexOutOfBoundsException: 1");
+            bool found = false; for (auto& m : map) if (m.first == parts[0]) { m.second = parts[1]; found = true; break; }
+            if (!found) map.emplace_back(parts[0], parts[1]);
+        }
+        // topology/MPRMap.java:60-86: leaves from the map, the rest by the LCA of the children's host vertices
+        sigma.assign(G.n, 0); int n_leaves = 0;
+        for (int l = 0; l < G.n; ++l) {
+            if (G.left[l] != -1) continue;
+            ++n_leaves;
+            const std::string gname = gt.has_name[l] ? gt.name[l] : std::string("null");
+            const std::string* hn = nullptr; for (auto& m : map) if (m.first == gname) hn = &m.second;
+            if (!hn) throw SgpError("Cannot find guest leaf " + gname + " in guest-to-host leaf map.");
+            int hv = -1; for (int v = 0; v < H.n; ++v) if (ht.has_name[v] && ht.name[v] == *hn) hv = v;
+            if (hv < 0) throw SgpError("Cannot find host leaf " + *hn + " corresponding to guest leaf " + gname + ".");
+            sigma[l] = hv;
+        }
+        if (n_leaves != (int)map.size()) throw SgpError("Mismatch in the number of guest tree leaves and guest-to-host map items: " + std::to_string(n_leaves) + " vs. " + std::to_string(map.size()) + ".");
+        for (int i = G.n - 1; i >= 0; --i) { const int x = gt.bfs[i]; if (G.left[x] != -1) sigma[x] = H.lca(sigma[G.left[x]], sigma[G.right[x]]); }      // children before parents
+        bool any_params = false; for (int v = 0; v < H.n; ++v) any_params |= H.has_params[v] != 0;
+        if (!any_params) throw SgpError("NullPointerException");
+        if (std::isnan(H.at[H.root])) H.at[H.root] = 0.0;
+        if (!H.has_params[H.root]) { H.k[H.root] = 1000.0; H.theta[H.root] = 0.001; H.has_params[H.root] = 1; }
+        if (std::isnan(G.at[G.root])) G.at[G.root] = 0.0;
+    } catch (SgpError& e) {
+        throw SgpError(std::string("Invalid input to rate model: ") + e.what());
+    }
+    if (std::fabs(G.vt[G.root] + G.at[G.root] - H.vt[H.root] - H.at[H.root]) > 1e-4) throw SgpError("Invalid guest and host trees: Time scales do not agree.");
+    auto enclosing = [&](int x) {
+        int lo = sigma[x]; const double xt = G.vt[x];
+        for (;;) { if (lo == H.root) return lo; const int lop = H.parent[lo]; if (H.vt[lop] >= xt) return lo; lo = lop; }
+    };
+    cfg.pa = scale; cfg.rk_off.assign(1, 0);
+    for (int x = 0; x < G.n; ++x) {
+        const int lo = enclosing(x), up = G.parent[x] == -1 ? H.root : enclosing(G.parent[x]);
+        const double l = G.at[x];
+        const size_t first = cfg.rk_w.size();
+        for (int h = lo;; h = H.parent[h]) {
+            if (h < 0) throw SgpError("Invalid guest and host trees: a guest branch leaves the host tree (ArrayIndexOutOfBoundsException in the reference)");
+            cfg.rk_k.push_back(H.has_params[h] ? H.k[h] : std::nan("")); cfg.rk_theta.push_back(H.has_params[h] ? H.theta[h] : std::nan(""));
+            cfg.rk_w.push_back(H.at[h] / l);
+            if (h == up) break;
+        }
+        const size_t cnt = cfg.rk_w.size() - first;
+        if (cnt > 255) throw SgpError("IIDRK11: a guest branch spans more than 255 host arcs (not supported)");
+        if (cnt == 1) cfg.rk_w[first] = 1.0;
+        else {
+            double dt = G.vt[x] - H.vt[lo];
+            cfg.rk_w[first] = std::max(0.0, cfg.rk_w[first] - dt / l);
+            if (G.parent[x] != -1) { dt = G.vt[G.parent[x]] - H.vt[up]; cfg.rk_w.back() = std::max(0.0, dt / l); }
+        }
+        cfg.rk_off.push_back((int32_t)cfg.rk_w.size());
+    }
+}
 }  // namespace
 
 void parse_relax_app(const std::vector<std::string>& args, bool multi_tree_input, RelaxConfig& cfg, AppResult& res, bool trees_from_batch) {
@@ -79,7 +190,8 @@ void parse_relax_app(const std::vector<std::string>& args, bool multi_tree_input
         res.out_text = "Usage:\n    java -jar sagephy-X.Y.Z.jar BranchRelaxer [options] <tree> <model> <arg1> <arg2> <...>\n"
                        "Supported models (accelerated): Constant <rate>, IIDGamma <k> <theta>, IIDLogNormal <mu> <sigma2>, IIDNormal <mu> <sigma2>,\n"
                        "    IIDUniform <a> <b>, IIDExponential <lambda>, IIDSamplesFromFile <filename>,\n"
-                       "    ACTK98 <start rate> <v>, ACRY07 <start rate> <sigma2>, ACABY02 <start rate>, ACLBPL07 <start rate> <mu> <theta> <sigma>\n\n";
+                       "    ACTK98 <start rate> <v>, ACRY07 <start rate> <sigma2>, ACABY02 <start rate>, ACLBPL07 <start rate> <mu> <theta> <sigma>,\n"
+                       "    IIDRK11 <host tree> <guest-to-host map> <scale factor>\n\n";
         return;
     }
     auto arg = [&](size_t i) -> const std::string& {
@@ -130,18 +242,24 @@ void parse_relax_app(const std::vector<std::string>& args, bool multi_tree_input
         if (2 * cfg.pc * cfg.pb < cfg.pd * cfg.pd) throw SgpError("Invalid parameters for CIR process: 0 rate may be achieved.");
         cfg.model_name = "LepageBryantPhillipeLartillot07Rates";
         kv = {{"start rate", jdouble(cfg.pa)}, {"mu", jdouble(cfg.pb)}, {"theta", jdouble(cfg.pc)}, {"sigma", jdouble(cfg.pd)}};
-    } else {
-        res.status = 4;
-        res.err_text = "rate model outside the accelerated path (IIDRK11 needs a host tree and a guest-to-host map; not in the scope table yet): " + model + "\n";
-        return;
-    }
+    } else if (same_nocase(model, "IIDRK11")) {         // apps/SaGePhy/IIDRasmussenKellis11RateModel.java; tables built below from the trees
+        cfg.model = 11; cfg.model_name = "IIDRasmussenKellis11Rates"; strict = true; hcap = 2;
+        (void)arg(2); (void)arg(3); (void)to_double(arg(4));
+        if (trees_from_batch || multi_tree_input) throw SgpError("IIDRK11 relaxes one guest tree against one host tree: chained and multi-tree input are not supported");
+    } else throw SgpError("Invalid rate model identifier: " + model);
     cfg.params = java_hashmap_order(kv, hcap);
     cfg.min_rate = to_double(p.str("-min", "1e-64")); cfg.max_rate = to_double(p.str("-max", "1e64")); cfg.max_attempts = to_int(p.str("-a", "10000"));
     cfg.do_meta = p.on("-x"); cfg.keep_interior = p.on("-innms");
     cfg.has_outfile = p.on("-o"); if (cfg.has_outfile) cfg.outfile = java_trim(p.str("-o", ""));
     if (trees_from_batch) { (void)arg(0); return; }      // chained stage: the trees are already on the device
     const std::string text = exists(arg(0)) ? slurp(arg(0)) : arg(0);
-    if (!multi_tree_input) cfg.trees.push_back(make_template(parse_newick(text), cfg.keep_interior, strict));
+    if (cfg.model == 11) {
+        const FlatTree gt = parse_newick(text);
+        cfg.trees.push_back(make_template(gt, cfg.keep_interior, true));
+        const FlatTree ht = parse_newick(exists(arg(2)) ? slurp(arg(2)) : arg(2));
+        (void)make_template(ht, false, true);          // the host tree is read with the same strict checks (BranchRelaxerParameters.java:109-110)
+        build_rk11(gt, ht, arg(3), to_double(arg(4)), cfg);
+    } else if (!multi_tree_input) cfg.trees.push_back(make_template(parse_newick(text), cfg.keep_interior, strict));
     else {
         size_t b = 0;
         while (b < text.size()) {

@@ -713,6 +713,12 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
         add(tail, a.model_tail_off, a.model_tail_len);
     }
     DevBuf<double> d_samples, rates, relaxed; d_samples.upload(cfg.samples);
+    DevBuf<int32_t> d_rk_off; DevBuf<double> d_rk_k, d_rk_theta, d_rk_w;
+    if (cfg.model == RM_RK11) {
+        if (chained || T != 1) throw SgpError("IIDRK11 relaxes one guest tree against one host tree: chained and multi-tree input are not supported");
+        d_rk_off.upload(cfg.rk_off); d_rk_k.upload(cfg.rk_k); d_rk_theta.upload(cfg.rk_theta); d_rk_w.upload(cfg.rk_w);
+        a.rk_off = d_rk_off.p; a.rk_k = d_rk_k.p; a.rk_theta = d_rk_theta.p; a.rk_w = d_rk_w.p;
+    }
     if (!chained) { d_views.upload(views); d_orig.upload(orig); d_chain.upload(chain); d_flags.upload(flags); d_name.upload(name_off); if (autocorr) { d_topo.upload(topo); d_parent.upload(parent); } }
     else {
         a.syn_names = 1; a.syn_number = d_num.p; a.syn_sigma = d_sig.p; a.syn_append_sigma = src->name_append_sigma ? 1 : 0;

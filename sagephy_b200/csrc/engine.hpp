@@ -54,6 +54,9 @@ struct RelaxConfig {
     bool has_seed = false; SeedHost seed;
     std::vector<std::string> args; int seed_arg_index = -1;
     std::string model_name; std::vector<std::pair<std::string, std::string>> params;   // in java.util.HashMap iteration order
+    // IIDRK11 (apps/SaGePhy/IIDRasmussenKellis11RateModel.java): guest vertex x draws one Gamma(k, theta) rate per host arc its branch
+    // passes over, segments rk_off[x] .. rk_off[x+1] in draw order with their (deterministic) weights; rate = pa * sum w * draw
+    std::vector<int32_t> rk_off; std::vector<double> rk_k, rk_theta, rk_w;
 };
 
 struct BatchOpts {

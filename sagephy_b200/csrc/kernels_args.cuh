@@ -124,7 +124,8 @@ namespace sgp {
 
 // ---- BranchRelaxer ------------------------------------------------------------------------------------------------------------
 enum RelaxModel : int { RM_CONSTANT = 0, RM_EXPONENTIAL = 1, RM_GAMMA = 2, RM_LOGNORMAL = 3, RM_NORMAL = 4, RM_UNIFORM = 5, RM_SAMPLES = 6,
-                        RM_ACTK98 = 7, RM_ACRY07 = 8, RM_ACABY02 = 9, RM_ACLBPL07 = 10 };      // autocorrelated: parent -> child along the tree
+                        RM_ACTK98 = 7, RM_ACRY07 = 8, RM_ACABY02 = 9, RM_ACLBPL07 = 10,      // autocorrelated: parent -> child along the tree
+                        RM_RK11 = 11 };                                                     // host-specific gamma rates (single input tree)
 
 // One input tree ("template"): vertex ids are the reference's post-order numbers, so id order == Newick emission order.
 struct RelaxTreeView {
@@ -140,6 +141,7 @@ struct RelaxArgs {
     const int32_t* parent;             // per template vertex: parent id (-1: root)
     double min_rate, max_rate; int max_attempts;
     const double* samples; int n_samples;
+    const int32_t* rk_off; const double* rk_k; const double* rk_theta; const double* rk_w;    // IIDRK11 segments per vertex of the (single) template
     int n_trees; long long sum_v;      // replicate r relaxes template r % n_trees; its vertex slot base is (r / n_trees) * sum_v + v0
     const RelaxTreeView* trees;
     const double* orig;                // per template vertex: original length (NaN: absent)

@@ -155,6 +155,25 @@ __device__ inline void ac_rates(const RelaxArgs& a, const RelaxTreeView& tv, lon
     }
 }
 
+// IIDRK11 (apps/SaGePhy/IIDRasmussenKellis11RateModel.java:110-157): per guest vertex one Gamma(k, theta) draw per host arc the
+// branch passes over (lowest arc first), combined with the precomputed weights and the scale factor (a.pa).
+template <bool REPLAY>
+__device__ inline void rk11_rates(const RelaxArgs& a, const RelaxTreeView& tv, long long base, MtStream& mt, unsigned long long gid, uint32_t attempt, int* err) {
+    double* rates = a.rates + base;
+    for (int x = 0; x < tv.nV && !*err; ++x) {
+        double r = 0.0;
+        for (int s = a.rk_off[x]; s < a.rk_off[x + 1]; ++s) {
+            const double k = a.rk_k[s], theta = a.rk_theta[s];
+            if (!(k > 0.0) || !(theta > 0.0)) { *err = 1; break; }       // GammaDistribution constructor throws / PARAMS missing (NullPointerException)
+            const double u = ac_uniform<REPLAY>(a, mt, gid, attempt, x, (uint32_t)(s - a.rk_off[x]));
+            const double draw = XDIV(XMUL(jchi2_quantile(u, XMUL(2.0, k), err), theta), 2.0);
+            if (*err) break;
+            r = XADD(r, XMUL(a.rk_w[s], draw));
+        }
+        rates[x] = XMUL(r, a.pa);
+    }
+}
+
 __device__ __forceinline__ long long relax_slot(const RelaxArgs& a, long long r, const RelaxTreeView** tv) {
     const long long t = r % a.n_trees; *tv = &a.trees[t];
     return (r / a.n_trees) * a.sum_v + a.trees[t].v0;
@@ -177,7 +196,8 @@ __global__ void __launch_bounds__(128) k_relax_rates(RelaxArgs a, int first_atte
         if (attempts > a.max_attempts) { status = REP_MAX_ATTEMPTS; break; }
         bool ok = true; int err = 0;
         if (a.model >= RM_ACTK98) {
-            ac_rates<REPLAY>(a, *tv, base, mt, gc, gid, (uint32_t)attempts, &err);
+            if (a.model == RM_RK11) rk11_rates<REPLAY>(a, *tv, base, mt, gid, (uint32_t)attempts, &err);
+            else ac_rates<REPLAY>(a, *tv, base, mt, gc, gid, (uint32_t)attempts, &err);
             if (!err) for (int x = 0; x < nV; ++x) { const double rate = a.rates[base + x]; if (x != tv->ignore && (rate < a.min_rate || rate > a.max_rate)) ok = false; }
         } else
         for (int x = 0; x < nV; ++x) {
