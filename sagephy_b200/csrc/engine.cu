@@ -730,7 +730,7 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
     DevBuf<int32_t> attempts, status; attempts.alloc((size_t)n); status.alloc((size_t)n);
     CK(cudaMemsetAsync(attempts.p, 0, (size_t)n * sizeof(int32_t), st)); CK(cudaMemsetAsync(status.p, 0, (size_t)n * sizeof(int32_t), st));
     DevBuf<uint32_t> mt_state; if (replay) mt_state.alloc((size_t)((n + 127) / 128 * 128 / 32 + 1) * 624 * 32);
-    a.n = n; a.rep_base = opts.offset; a.seed = cfg.seed.philox_key; a.model = cfg.model; a.pa = cfg.pa; a.pb = cfg.pb; a.pc = cfg.pc; a.pd = cfg.pd; a.sigma = cfg.sigma; a.topo = d_topo.p; a.parent = d_parent.p;
+    a.n = n; a.rep_base = opts.offset; a.seed = cfg.seed.philox_key; a.model = cfg.model; a.pa = cfg.pa; a.pb = cfg.pb; a.pc = cfg.pc; a.pd = cfg.pd; a.sigma = cfg.sigma; a.gamma_lng = jln_gamma(0.5 * (2.0 * cfg.pa)); a.ln2 = jlog(2.0); a.topo = d_topo.p; a.parent = d_parent.p;
     a.min_rate = cfg.min_rate; a.max_rate = cfg.max_rate; a.max_attempts = cfg.max_attempts; a.samples = d_samples.p; a.n_samples = (int)cfg.samples.size();
     a.n_trees = T; a.sum_v = sum_v; a.trees = d_views.p; a.orig = d_orig.p; a.chain = d_chain.p; a.vflags = d_flags.p; a.name_off = d_name.p; a.blob = d_blob.p;
     a.T = impl->T; a.rates = rates.p; a.relaxed = relaxed.p; a.attempts = attempts.p; a.status = status.p; a.mt_state = mt_state.p;

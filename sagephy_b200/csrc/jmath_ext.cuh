@@ -199,10 +199,12 @@ SGP_HD double jln_gamma(double xx) {
     for (int j = 0; j < 14; ++j) { y = XADD(y, 1.0); ser = XADD(ser, XDIV(LANCZOS[j], y)); }
     return XADD(tmp, jlog(XDIV(XMUL(SQRT_2_PI, ser), x)));
 }
-SGP_HD double jinc_gamma_ratio(double x, double k) {
+// g = jln_gamma(k): the reference recomputes it on every call (math/Gamma.java:135); callers that evaluate many quantiles of one
+// distribution pass the value they computed once — same function, same bits.
+SGP_HD double jinc_gamma_ratio(double x, double k, double g) {
     if (x == 0.0) return 0.0;
     const double accuracy = 1.0e-8, overflow = 1.0e30, xbig = 1.0E6, alimit = 1000.0;
-    double g_in = 0.0; const double g = jln_gamma(k);
+    double g_in = 0.0;
     const double factor = jexp(XSUB(XSUB(XMUL(k, jlog(x)), x), g));
     if (k > alimit) {
         const double pn1 = XMUL(XMUL(3.0, jsqrt(k)), XSUB(XADD(jpow(XDIV(x, k), 1.0 / 3.0), XDIV(1.0, XMUL(9.0, k))), 1.0));
@@ -232,10 +234,11 @@ SGP_HD double jinc_gamma_ratio(double x, double k) {
     return XDIV(XMUL(g_in, factor), k);
 }
 // ChiSquared.quantile; *err = 1 when the reference would throw (p outside [2e-6, 0.999998])
-SGP_HD double jchi2_quantile(double p, double k, int* err) {
+// G = jln_gamma(0.5 * k) and AA = jlog(2.0) (= 0x3FE62E42FEFA39EF), both constants of the distribution
+SGP_HD double jchi2_quantile_pre(double p, double k, double G, double AA, int* err) {
     if (p < 2e-6 || p > 0.999998 || k <= 0.0) { *err = 1; return dbl_nan(); }
-    const double E = 0.5e-6, AA = jlog(2.0);
-    const double XX = XMUL(0.5, k), C = XSUB(XX, 1.0), G = jln_gamma(XX);
+    const double E = 0.5e-6;
+    const double XX = XMUL(0.5, k), C = XSUB(XX, 1.0);
     double ch;
     if (k < XMUL(-1.24, jlog(p))) {
         ch = jpow(XMUL(XMUL(p, XX), jexp(XADD(G, XMUL(XX, AA)))), XDIV(1.0, XX));
@@ -256,7 +259,7 @@ SGP_HD double jchi2_quantile(double p, double k, int* err) {
     double Q;
     do {
         Q = ch;
-        const double P1 = XMUL(0.5, ch), P2 = XSUB(p, jinc_gamma_ratio(P1, XX));
+        const double P1 = XMUL(0.5, ch), P2 = XSUB(p, jinc_gamma_ratio(P1, XX, G));
         const double T = XMUL(P2, jexp(XSUB(XADD(XADD(XMUL(XX, AA), G), P1), XMUL(C, jlog(ch)))));
         const double B = XDIV(T, ch), A = XSUB(XMUL(0.5, T), XMUL(B, C));
         const double S1 = XDIV(XADD(210.0, XMUL(A, XADD(140.0, XMUL(A, XADD(105.0, XMUL(A, XADD(84.0, XMUL(A, XADD(70.0, XMUL(60.0, A)))))))))), 420.0);
@@ -269,6 +272,10 @@ SGP_HD double jchi2_quantile(double p, double k, int* err) {
         ch = XADD(ch, XMUL(T, XSUB(XADD(1.0, XMUL(XMUL(0.5, T), S1)), XMUL(XMUL(B, C), inner))));
     } while (fabs(XSUB(XDIV(Q, ch), 1.0)) > E);
     return ch;
+}
+SGP_HD double jchi2_quantile(double p, double k, int* err) {
+    if (p < 2e-6 || p > 0.999998 || k <= 0.0) { *err = 1; return dbl_nan(); }
+    return jchi2_quantile_pre(p, k, jln_gamma(XMUL(0.5, k)), jlog(2.0), err);
 }
 
 }  // namespace sgp

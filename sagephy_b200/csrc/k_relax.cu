@@ -1,5 +1,6 @@
 #include "kernels_relax.cuh"
 #include "launch.hpp"
+#include <algorithm>
 namespace sgp {
 void launch_relax_rates(bool replay, const RelaxArgs& a, int first_attempt, int only_flagged, cudaStream_t st) {
     const int blocks = (int)((a.n + 127) / 128);
@@ -10,7 +11,9 @@ void launch_relax_apply(const RelaxArgs& a, long long total_slots, cudaStream_t 
     k_relax_finish_apply<<<(unsigned)((a.n + 255) / 256), 256, 0, st>>>(a);
 }
 void launch_relax_apply_per_rep(const RelaxArgs& a, cudaStream_t st) {
-    k_relax_apply_per_rep<<<(unsigned)a.n, 256, 0, st>>>(a);
+    int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long blocks = std::max<long long>(1, std::min<long long>((a.n + 7) / 8, (long long)sms * 8));
+    k_relax_apply_per_rep<<<(unsigned)blocks, 256, 0, st>>>(a);
     k_relax_finish_apply<<<(unsigned)((a.n + 255) / 256), 256, 0, st>>>(a);
 }
 void launch_ingest_count(const IngestArgs& g, cudaStream_t st) { k_ingest_count<<<(unsigned)((g.n_src + 256) / 256), 256, 0, st>>>(g); }

@@ -137,6 +137,7 @@ struct RelaxArgs {
     long long n; long long rep_base; unsigned long long seed;
     int model; double pa, pb, sigma;   // model parameters (a, b, sqrt(variance))
     double pc, pd;                     // ACLBPL07: theta, sigma (pa = start rate, pb = mu)
+    double gamma_lng, ln2;             // IIDGamma: jln_gamma(k) and jlog(2.0), constants of every quantile evaluation of the run
     const int32_t* topo;               // per template vertex slot: vertex ids in RTree.getTopologicalOrdering() order (BFS from the root)
     const int32_t* parent;             // per template vertex: parent id (-1: root)
     double min_rate, max_rate; int max_attempts;

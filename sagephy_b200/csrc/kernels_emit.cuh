@@ -254,19 +254,21 @@ __device__ unsigned long long emit_pieces(int n_pieces, char* base, char* stage,
 
 // .info streams: one THREAD per (replicate, file). A file is ~10-30 short lines, so "lane per line" left most of a warp idle and
 // cost ~8 000 warp instructions per replicate; here the 32 lanes of a warp format 32 files in lock step (same line number at the
-// same time) into private shared-memory slots, and the warp then flushes the slots one after the other with aligned 16-byte
-// stores. Files that do not fit a slot (an "Arguments:" line that embeds a whole Newick host tree) take the cooperative path:
-// header text copied by the whole warp straight from the constant blob, lines written by the owning lane.
-constexpr int kInfoSlot = 1024;
+// same time) into a shared-memory stage that the lanes share by a prefix sum of their file sizes (as many lanes per round as
+// fit), and the warp then flushes the files one after the other with aligned 16-byte stores. A long "Arguments:" line (it may
+// embed a whole Newick host tree) is not staged: the whole warp copies it straight from the constant blob, file by file.
+constexpr int kInfoWarps = 4;
+constexpr int kInfoStage = 12 * 1024;          // bytes of stage per warp
 template <bool PRUNED, class Sink> __device__ __forceinline__ void put_info_file(Sink& s, const EmitArgs& a, const RepInfo& inf, long long gid, int first_line) {
     const int L = info_lines(a, PRUNED);
     for (int ln = first_line; ln < L; ++ln) put_info_line<PRUNED>(s, a, inf, gid, ln);
 }
 template <bool WRITE>
-__global__ void __launch_bounds__(32) k_emit_info(EmitArgs a) {
-    __shared__ __align__(16) char s_slot[32][kInfoSlot];
-    const int lane = threadIdx.x;
-    const long long item = (long long)blockIdx.x * 32 + lane;
+__global__ void __launch_bounds__(kInfoWarps * 32) k_emit_info(EmitArgs a) {
+    __shared__ __align__(16) char s_stage[kInfoWarps][kInfoStage];
+    const int lane = threadIdx.x & 31;
+    char* stage = s_stage[threadIdx.x >> 5];
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long r = item >> 1; const bool pr = (item & 1) != 0;
     const int st = pr ? ST_PRUNED_INFO : ST_UNPRUNED_INFO;
     const bool active = r < a.n && (a.stream_mask & (1u << st));
@@ -274,50 +276,81 @@ __global__ void __launch_bounds__(32) k_emit_info(EmitArgs a) {
     const RepInfo& inf = a.info[active ? r : 0];
     const bool ok = active && inf.status == REP_OK;
     const bool note = active && !ok && pr && inf.status == REP_MAX_ATTEMPTS;      // the reference writes only the failure note
-    // total length (closed form for the long constant parts, the formatting code with a counting sink for the rest)
-    unsigned long long total = 0;
-    if (ok) { CountSink c; if (pr) put_info_file<true>(c, a, inf, gid, 0); else put_info_file<false>(c, a, inf, gid, 0); total = (unsigned long long)c.n; }
-    else if (note) total = 65;
+    // header = lines 0-1 ("# APP" and "Arguments: [...]"): closed-form length; copied by the whole warp when it is long
+    const bool long_head = a.args_pre_len > 192;
+    const int h0len = a.app == 0 ? 25 : a.app == 1 ? 26 : 27;
+    const int seedlen = (ok && a.seed_mode) ? seed_dec_len(a.sseed, a.blob, (unsigned long long)gid) : 0;
+    const unsigned head = ok ? (unsigned)(h0len + a.args_pre_len + (a.seed_mode ? seedlen + a.args_post_len : 0) + 1) : 0u;
+    unsigned body = 0;             // what this lane formats itself
+    if (ok) { CountSink c; if (pr) put_info_file<true>(c, a, inf, gid, long_head ? 2 : 0); else put_info_file<false>(c, a, inf, gid, long_head ? 2 : 0); body = (unsigned)c.n; }
+    else if (note) body = 65;
+    const unsigned long long total = (unsigned long long)body + (long_head ? head : 0u);
     if (!WRITE) { if (active) a.sizes[(size_t)st * a.n + r] = total; return; }
     char* dst = active ? a.out[st] + a.offsets[(size_t)st * (a.n + 1) + r] : nullptr;
-    const int mis = (int)(reinterpret_cast<unsigned long long>(dst) & 15ull);
-    const bool staged = total > 0 && total + 16 <= (unsigned long long)kInfoSlot;
-    if (staged) {
-        SmemSink m{(uint32_t)__cvta_generic_to_shared(&s_slot[lane][0]) + (uint32_t)mis};
-        if (note) put_lit(m, "Failed to produce valid pruned tree within max allowed attempts.\n");
-        else if (pr) put_info_file<true>(m, a, inf, gid, 0); else put_info_file<false>(m, a, inf, gid, 0);
-    }
-    __syncwarp();
-    unsigned todo = __ballot_sync(0xffffffffu, staged);
-    while (todo) {
-        const int l = __ffs(todo) - 1; todo &= todo - 1;
-        char* d = reinterpret_cast<char*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst), l));
-        const unsigned len = (unsigned)__shfl_sync(0xffffffffu, (unsigned)total, l);
-        const int m = __shfl_sync(0xffffffffu, mis, l);
-        flush_stage(&s_slot[l][0], m, d, len);
-    }
-    // oversize files, one after the other
-    unsigned big = __ballot_sync(0xffffffffu, total > 0 && !staged);
-    while (big) {
-        const int l = __ffs(big) - 1; big &= big - 1;
-        char* d = reinterpret_cast<char*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst), l));
-        const long long g = __shfl_sync(0xffffffffu, gid, l);
-        const char* h0 = a.app == 0 ? "# HOSTTREEGEN\nArguments:\t" : a.app == 1 ? "# GUESTTREEGEN\nArguments:\t" : "# DOMAINTREEGEN\nArguments:\t";
-        const int h0len = a.app == 0 ? 25 : a.app == 1 ? 26 : 27;
-        for (int i = lane; i < h0len; i += 32) d[i] = h0[i];
-        if (a.args_pre_off16[0] >= 0) {
-            char* q = d + h0len; const int m = (int)(reinterpret_cast<unsigned long long>(q) & 15ull);
-            flush_stage(a.blob + a.args_pre_off16[m] - m, m, q, (unsigned)a.args_pre_len);       // source congruent to destination mod 16
-        } else for (int i = lane; i < a.args_pre_len; i += 32) d[h0len + i] = a.blob[a.args_pre_off + i];
-        unsigned long long o = (unsigned long long)h0len + a.args_pre_len;
-        if (a.seed_mode) {
-            const int seedlen = seed_dec_len(a.sseed, a.blob, (unsigned long long)g);
-            if (lane == 0) { MemSink ms{d + o}; put_seed(ms, a.sseed, a.blob, (unsigned long long)g); }
-            for (int i = lane; i < a.args_post_len; i += 32) d[o + seedlen + i] = a.blob[a.args_post_off + i];
-            o += (unsigned long long)seedlen + a.args_post_len;
+    if (long_head) {
+        unsigned todo = __ballot_sync(0xffffffffu, ok);
+        while (todo) {
+            const int l = __ffs(todo) - 1; todo &= todo - 1;
+            char* d = reinterpret_cast<char*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst), l));
+            const long long g = __shfl_sync(0xffffffffu, gid, l);
+            const char* h0 = a.app == 0 ? "# HOSTTREEGEN\nArguments:\t" : a.app == 1 ? "# GUESTTREEGEN\nArguments:\t" : "# DOMAINTREEGEN\nArguments:\t";
+            for (int i = lane; i < h0len; i += 32) d[i] = h0[i];
+            if (a.args_pre_off16[0] >= 0) {
+                char* q = d + h0len; const int m = (int)(reinterpret_cast<unsigned long long>(q) & 15ull);
+                flush_stage(a.blob + a.args_pre_off16[m] - m, m, q, (unsigned)a.args_pre_len);       // source congruent to destination mod 16
+            } else for (int i = lane; i < a.args_pre_len; i += 32) d[h0len + i] = a.blob[a.args_pre_off + i];
+            unsigned long long o = (unsigned long long)h0len + a.args_pre_len;
+            if (a.seed_mode) {
+                const int sl = __shfl_sync(0xffffffffu, seedlen, l);
+                if (lane == 0) { MemSink ms{d + o}; put_seed(ms, a.sseed, a.blob, (unsigned long long)g); }
+                for (int i = lane; i < a.args_post_len; i += 32) d[o + sl + i] = a.blob[a.args_post_off + i];
+                o += (unsigned long long)sl + a.args_post_len;
+            }
+            if (lane == 0) d[o] = '\n';
         }
-        if (lane == 0) d[o] = '\n';
-        if (lane == l) { MemSink ms{d + o + 1}; if (pr) put_info_file<true>(ms, a, inf, gid, 2); else put_info_file<false>(ms, a, inf, gid, 2); }
+        if (ok) dst += head;
+    }
+    // bodies: rounds of as many lanes as fit the stage; slot of a lane = [off, off + mis + body), congruent to its destination mod 16
+    const int mis = (int)(reinterpret_cast<unsigned long long>(dst) & 15ull);
+    const unsigned need = body ? ((body + (unsigned)mis + 15u) & ~15u) + 16u : 0u;
+    bool pending = body > 0;
+    for (;;) {
+        const unsigned want = __ballot_sync(0xffffffffu, pending);
+        if (!want) break;
+        // inclusive prefix sum of the slot sizes of the pending lanes
+        unsigned x = pending ? need : 0u;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        const bool fits = pending && x <= (unsigned)kInfoStage;
+        const unsigned now = __ballot_sync(0xffffffffu, fits);
+        if (!now) {
+            // the first pending file alone exceeds the stage: its owner writes it directly (byte stores)
+            const int l = __ffs(want) - 1;
+            if (lane == l) {
+                MemSink ms{dst};
+                if (note) put_lit(ms, "Failed to produce valid pruned tree within max allowed attempts.\n");
+                else if (pr) put_info_file<true>(ms, a, inf, gid, long_head ? 2 : 0); else put_info_file<false>(ms, a, inf, gid, long_head ? 2 : 0);
+                pending = false;
+            }
+            continue;
+        }
+        const unsigned off = x - need;
+        if (fits) {
+            SmemSink m{(uint32_t)__cvta_generic_to_shared(stage) + off + (uint32_t)mis};
+            if (note) put_lit(m, "Failed to produce valid pruned tree within max allowed attempts.\n");
+            else if (pr) put_info_file<true>(m, a, inf, gid, long_head ? 2 : 0); else put_info_file<false>(m, a, inf, gid, long_head ? 2 : 0);
+        }
+        __syncwarp();
+        unsigned todo = now;
+        while (todo) {
+            const int l = __ffs(todo) - 1; todo &= todo - 1;
+            char* d = reinterpret_cast<char*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst), l));
+            const unsigned len = __shfl_sync(0xffffffffu, body, l);
+            const unsigned so = __shfl_sync(0xffffffffu, off, l);
+            const int m = __shfl_sync(0xffffffffu, mis, l);
+            flush_stage(stage + so, m, d, len);
+        }
+        __syncwarp();
+        if (fits) pending = false;
     }
 }
 

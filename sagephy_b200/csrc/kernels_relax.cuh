@@ -36,7 +36,7 @@ __device__ inline double mt_next_gaussian(MtStream& mt, GaussCache& gc) {
 __device__ inline double rate_from_uniform(const RelaxArgs& a, double u, int* err) {
     switch (a.model) {
         case RM_EXPONENTIAL: return XDIV(-jlog(XSUB(1.0, u)), a.pa);
-        case RM_GAMMA: return XDIV(XMUL(jchi2_quantile(u, XMUL(2.0, a.pa), err), a.pb), 2.0);
+        case RM_GAMMA: return XDIV(XMUL(jchi2_quantile_pre(u, XMUL(2.0, a.pa), a.gamma_lng, a.ln2, err), a.pb), 2.0);
         case RM_LOGNORMAL: return jexp(XADD(XMUL(jnormal_quantile(u), a.sigma), a.pa));
         default: return a.pa;
     }
@@ -213,7 +213,10 @@ __global__ void __launch_bounds__(128) k_relax_rates(RelaxArgs a, int first_atte
     if (status == REP_OK) for (int x = 0; x < nV; ++x) a.relaxed[base + x] = XMUL(a.orig[tv->v0 + x], a.rates[base + x]);
 }
 
-// Philox fast path, attempt 0, one thread per (replicate, vertex).
+// Philox fast path, attempt 0, one thread per (replicate, vertex). A draw on which the reference would throw ends the run whatever
+// the other rates are (BranchRelaxer.java:137-140), so its mark must win over "rate outside [min, max]": kApplyError > REP_PENDING
+// under atomicMax; k_relax_finish_apply turns it into REP_MODEL_ERROR.
+constexpr int kApplyError = 7;
 __global__ void __launch_bounds__(256) k_relax_apply(RelaxArgs a, long long total_slots) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= total_slots) return;
@@ -229,22 +232,30 @@ __global__ void __launch_bounds__(256) k_relax_apply(RelaxArgs a, long long tota
     const double rate = draw_rate<false>(a, mt, gc, (unsigned long long)(a.rep_base + r), 0u, x, &err);
     a.rates[g] = rate;
     a.relaxed[g] = XMUL(a.orig[tv.v0 + x], rate);
-    if (err) atomicMax(&a.status[r], (int)REP_MODEL_ERROR);
+    if (err) atomicMax(&a.status[r], kApplyError);
     else if (x != tv.ignore && (rate < a.min_rate || rate > a.max_rate)) atomicMax(&a.status[r], (int)REP_PENDING);
 }
-// Same work with one block per replicate: used when every replicate has its own tree (chained stage), where the slot -> tree
-// search of k_relax_apply would be a 20-step binary search per vertex.
+// Same work with one WARP per replicate (grid-stride over replicates): used when every replicate has its own tree (chained
+// stage), where the slot -> tree search of k_relax_apply would be a 20-step binary search per vertex. Lanes take the vertices of the
+// tree 32 at a time: coalesced 8-byte reads of the original lengths, coalesced writes of rates and relaxed lengths.
 __global__ void __launch_bounds__(256) k_relax_apply_per_rep(RelaxArgs a) {
-    const long long r = blockIdx.x;
-    const RelaxTreeView* tvp; const long long base = relax_slot(a, r, &tvp);
-    const RelaxTreeView tv = *tvp;
-    for (int x = threadIdx.x; x < tv.nV; x += blockDim.x) {
-        MtStream mt; GaussCache gc{false, 0.0}; int err = 0;
-        const double rate = draw_rate<false>(a, mt, gc, (unsigned long long)(a.rep_base + r), 0u, x, &err);
-        a.rates[base + x] = rate;
-        a.relaxed[base + x] = XMUL(a.orig[tv.v0 + x], rate);
-        if (err) atomicMax(&a.status[r], (int)REP_MODEL_ERROR);
-        else if (x != tv.ignore && (rate < a.min_rate || rate > a.max_rate)) atomicMax(&a.status[r], (int)REP_PENDING);
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp0; r < a.n; r += n_warps) {
+        const RelaxTreeView* tvp; const long long base = relax_slot(a, r, &tvp);
+        const RelaxTreeView tv = *tvp;
+        const unsigned long long gid = (unsigned long long)(a.rep_base + r);
+        int flag = 0;
+        for (int x = lane; x < tv.nV; x += 32) {
+            MtStream mt; GaussCache gc{false, 0.0}; int err = 0;
+            const double rate = draw_rate<false>(a, mt, gc, gid, 0u, x, &err);
+            a.rates[base + x] = rate;
+            a.relaxed[base + x] = XMUL(a.orig[tv.v0 + x], rate);
+            if (err) flag = kApplyError;
+            else if (x != tv.ignore && (rate < a.min_rate || rate > a.max_rate) && flag < (int)REP_PENDING) flag = (int)REP_PENDING;
+        }
+        flag = __reduce_max_sync(0xffffffffu, flag);
+        if (lane == 0 && flag) atomicMax(&a.status[r], flag);
     }
 }
 __global__ void k_relax_finish_apply(RelaxArgs a) {
@@ -252,6 +263,7 @@ __global__ void k_relax_finish_apply(RelaxArgs a) {
     if (r >= a.n) return;
     if (a.trees[r % a.n_trees].nV == 0) { a.status[r] = REP_MODEL_ERROR; a.attempts[r] = 0; return; }
     if (a.status[r] == 0) { a.status[r] = REP_OK; a.attempts[r] = 1; }       // status was zero-initialised == "no violation seen"
+    else if (a.status[r] == kApplyError) { a.status[r] = REP_MODEL_ERROR; a.attempts[r] = 1; }
 }
 
 // ---- chained stage: generator trees -> templates ---------------------------------------------------------------------------

@@ -293,3 +293,59 @@ def test_app_run_multi_equals_single_device(ctx, tmp_path):
     subprocess.check_call([exe] + core + ["--gpus", "2"], cwd=d2, env=env)
     f1 = {p.name: p.read_bytes() for p in d1.iterdir()}; f2 = {p.name: p.read_bytes() for p in d2.iterdir()}
     assert f1 == f2 and "species.pruned.tree.idx" in f1
+
+
+# ---- IIDRK11 ------------------------------------------------------------------------------------------------------
+RK_HOST = "((A:0.4[PARAMS=(2.0,0.5)],B:0.4[PARAMS=(3.0,0.4)]):0.6[PARAMS=(1.5,0.7)],(C:0.7[PARAMS=(2.5,0.3)],(D:0.2[PARAMS=(4,0.25)],E:0.2[PARAMS=(2,0.6)]):0.5[PARAMS=(1.0,1.0)]):0.3[PARAMS=(2.0,0.5)]);"
+RK_HOST_PLAIN = "((A:0.4,B:0.4):0.6,(C:0.7,(D:0.2,E:0.2):0.5):0.3):0.2;"
+
+
+def test_iidrk11_replay_and_distribution(ctx, tmp_path):
+    # guest trees without transfers from the oracle's GuestTreeGen on the same species tree, their .leafmap as the guest-to-host map
+    # (apps/SaGePhy/IIDRasmussenKellis11RateModel.java; BranchRelaxerParameters.java:108-113)
+    n_checked = 0
+    for gs in range(1, 9):
+        g = oracle_run("GuestTreeGen", ["-s", str(gs), "-db", "none", "-min", "3", RK_HOST_PLAIN, "0.5", "0.3", "0.0", "g"])["files"]
+        gt = tmp_path / f"g{gs}.tree"; gt.write_bytes(g["g.pruned.tree"]); gm = tmp_path / f"g{gs}.map"; gm.write_bytes(g["g.pruned.leafmap"])
+        for extra in ([], ["-x", "-innms"]):
+            args = ["-s", "40"] + extra + ["-o", "rk.tree", str(gt), "IIDRK11", RK_HOST, str(gm), "1.5"]
+            n = 12
+            b = ctx.run("BranchRelaxer", args, n=n, rng=sg.RNG_MT_REPLAY)
+            for i in range(n):
+                want = oracle_run("BranchRelaxer", with_seed(args, 40 + i))
+                if want["status"] == 2:
+                    assert b.rep_status[i] == 4
+                    continue
+                assert b.rep_status[i] == 0 and b.attempts[i] == want["attempts"], (gs, i, b.rep_status[i])
+                assert b.files(i)[""] == want["files"]["rk.tree"] and b.files(i)[".info"] == want["files"]["rk.tree.info"], (gs, extra, i)
+                n_checked += 1
+    assert n_checked > 150
+    # retries: a tight rate window
+    args = ["-s", "7", "-min", "0.3", "-max", "3.0", "-a", "40", "-o", "rk.tree", str(tmp_path / "g1.tree"), "IIDRK11", RK_HOST, str(tmp_path / "g1.map"), "1.0"]
+    b = ctx.run("BranchRelaxer", args, n=24, rng=sg.RNG_MT_REPLAY)
+    for i in range(24):
+        want = oracle_run("BranchRelaxer", with_seed(args, 7 + i))
+        if want["status"] == 1:
+            assert b.rep_status[i] == 1
+        elif want["status"] == 0:
+            assert b.rep_status[i] == 0 and b.attempts[i] == want["attempts"] and b.files(i)[""] == want["files"]["rk.tree"]
+    # constructor errors of the reference refuse the run
+    (tmp_path / "short.map").write_text("G0_3 C\n")
+    for bad in (["-s", "1", str(tmp_path / "g1.tree"), "IIDRK11", RK_HOST, str(tmp_path / "short.map"), "1.0"],
+                ["-s", "1", str(tmp_path / "g1.tree"), "IIDRK11", RK_HOST_PLAIN, str(tmp_path / "g1.map"), "1.0"]):
+        assert oracle_run("BranchRelaxer", bad)["status"] == 2
+        with pytest.raises(sg.SagephyError):
+            ctx.run("BranchRelaxer", bad, n=2, rng=sg.RNG_MT_REPLAY)
+    # throughput mode: same conditional distributions as the MT oracle
+    args = ["-s", "99", str(tmp_path / "g2.tree"), "IIDRK11", RK_HOST, str(tmp_path / "g2.map"), "1.5"]
+    n = 20000
+    p = ctx.run("BranchRelaxer", args, n=n, rng=sg.RNG_PHILOX)
+    ok = p.rep_status == 0
+    assert ok.mean() > 0.99 and set(np.unique(p.rep_status)) <= {0, 4}
+    wants = oracle_run_many([("BranchRelaxer", with_seed(args, 99 + i)) for i in range(3000)])
+    ref = np.array([[float(x) for x in LEN_RE.findall(w["stdout"])] for w in wants if w["status"] == 0 and w["stdout"]])
+    nv = ref.shape[1]
+    rel = p.values(1).reshape(n, nv)[ok]
+    for x in range(0, nv, max(1, nv // 5)):
+        if ref[:, x].std() > 0:
+            assert ks_ok(rel[:, x], ref[:, x]), x

@@ -466,3 +466,51 @@ def test_host_tables_of_the_product_without_a_gpu():
     # ... and is refused when the stem is taken from the tree (DomainTreeGen's gene trees) and is missing there
     rc = f(b"((a:1,b:1):1,c:2);", C.c_double(float("nan")), C.byref(nv_o), C.byref(ne_o), *([None] * 5), C.c_int32(0), None, None, None, C.c_int32(0), None, C.c_int32(0), None, C.c_int64(0), err, C.c_int32(256))
     assert rc == 3 and b"top time" in err.value
+
+
+# ---- IIDRK11: closed forms of the host-specific gamma rates ------------------------------------------------------
+RK_HOST = "((A:0.4[PARAMS=(2.0,0.5)],B:0.4[PARAMS=(3.0,0.4)]):0.6[PARAMS=(1.5,0.7)],(C:0.7[PARAMS=(2.5,0.3)],(D:0.2[PARAMS=(4,0.25)],E:0.2[PARAMS=(2,0.6)]):0.5[PARAMS=(1.0,1.0)]):0.3[PARAMS=(2.0,0.5)]);"
+
+
+def test_iidrk11_oracle_closed_forms(tmp_path):
+    # a guest tree that IS the host tree (one gene per species, guest vertices at the host vertices' times): the branch above guest
+    # vertex x passes over exactly the host arc above sigma(x), so rate(x) ~ scale * Gamma(k, theta) of that arc
+    # (apps/SaGePhy/IIDRasmussenKellis11RateModel.java:110-157); the root arc without PARAMS defaults to Gamma(1000, 0.001) (:77-79)
+    guest = "((a:0.4,b:0.4):0.6,(c:0.7,(d:0.2,e:0.2):0.5):0.3);"
+    m = tmp_path / "map.txt"; m.write_text("a A\nb\tB\nc C\nd  D\ne E\n\nignored line\n")
+    scale = 1.5
+    par = [(2.0, 0.5), (3.0, 0.4), (1.5, 0.7), (2.5, 0.3), (4, 0.25), (2, 0.6), (1.0, 1.0), (2.0, 0.5), (1000, 0.001)]   # vertex ids = post-order
+    n = 3000
+    rates = np.empty((n, 9))
+    for i in range(n):
+        r = oracle_run("BranchRelaxer", ["-s", str(100 + i), "-o", "x", guest, "IIDRK11", RK_HOST, str(m), str(scale)])
+        if r["status"] == 2:        # a uniform outside [2e-6, 0.999998] aborts the reference run (math/ChiSquared.java:24)
+            rates[i] = np.nan; continue
+        line = [l for l in r["files"]["x.info"].decode().split("\n") if l.startswith("Rates:")][0]
+        rates[i] = [float(v) for v in line.split("[")[1].rstrip("]").split(", ")]
+        assert "Model:\tIIDRasmussenKellis11Rates\nModel parameters:\n" in r["files"]["x.info"].decode()
+    rates = rates[~np.isnan(rates[:, 0])]
+    assert len(rates) > 0.99 * n
+    for x, (k, th) in enumerate(par):
+        want = scale * k * th
+        assert abs(rates[:, x].mean() - want) < 5 * scale * math.sqrt(k) * th / math.sqrt(len(rates)), (x, rates[:, x].mean(), want)
+    # a guest branch that passes over two host arcs mixes their rates with the time shares as weights: guest "x" (mapped to D) joins
+    # "y" (mapped to E) at time 0.2 -> sigma = their parent; the branch above that duplication-free vertex runs from 0.2 to the guest
+    # root at 1.0 and passes over the host arcs above (D,E) [0.2, 0.7] and above its parent [0.7, 1.0]
+    guest2 = "((x:0.2,y:0.2):0.8,c:1.0);"
+    m2 = tmp_path / "map2.txt"; m2.write_text("x D\ny E\nc C\n")
+    got = []
+    for i in range(2000):
+        r = oracle_run("BranchRelaxer", ["-s", str(i), "-o", "x", guest2, "IIDRK11", RK_HOST, str(m2), "1.0"])
+        if r["status"] == 0:
+            line = [l for l in r["files"]["x.info"].decode().split("\n") if l.startswith("Rates:")][0]
+            got.append([float(v) for v in line.split("[")[1].rstrip("]").split(", ")])
+    got = np.array(got)
+    want = (0.5 / 0.8) * 1.0 * 1.0 + (0.3 / 0.8) * 2.0 * 0.5
+    assert abs(got[:, 2].mean() - want) < 0.06, (got[:, 2].mean(), want)
+    # constructor errors of the reference: leaf missing from the map, unknown host leaf, no PARAMS anywhere, time scales that disagree
+    for bad_map, host, gtree in (("a A\nb B\nc C\nd D\n", RK_HOST, guest), ("a A\nb B\nc C\nd D\ne Z\n", RK_HOST, guest),
+                                 ("a A\nb B\nc C\nd D\ne E\n", "((A:0.4,B:0.4):0.6,(C:0.7,(D:0.2,E:0.2):0.5):0.3);", guest),
+                                 ("a A\nb B\nc C\nd D\ne E\n", RK_HOST, "((a:0.4,b:0.4):0.7,(c:0.8,(d:0.2,e:0.2):0.6):0.3);")):
+        mm = tmp_path / "bad.txt"; mm.write_text(bad_map)
+        assert oracle_run("BranchRelaxer", ["-s", "1", gtree, "IIDRK11", host, str(mm), "1.0"])["status"] == 2
