@@ -79,6 +79,10 @@ typedef struct {
 /* Tree generators only: keep the vertex records of the accepted trees on the device so that the batch can feed
  * sgp_relax_run_on_batch without a host round trip (costs ~100 bytes of HBM per vertex until the batch is freed). */
 #define SGP_FLAG_KEEP_TREES 2
+/* Tree generators only: do not pipeline sub-batches (large HostTreeGen batches in Philox mode otherwise run the sampler of sub-batch
+ * k+1 on a second stream next to build / label / emit of sub-batch k). Same bytes either way; the per-phase times of sgp_timings are
+ * only clean (no overlap) with this flag. */
+#define SGP_FLAG_SERIAL 4
 
 /* summary counters of a batch (merged across GPUs with an allreduce(sum) by the caller) */
 #define SGP_HIST_LEAF_BINS 1025
@@ -97,6 +101,7 @@ typedef struct {
     double find_ms, build_ms, label_ms, emit_size_ms, emit_write_ms, d2h_ms, total_ms;   /* CUDA-event times of the last run */
     int64_t kernel_launches;
     int64_t h2d_bytes;          /* host->device bytes of the run: host-tree tables, constant strings, tree templates */
+    int64_t sub_batches;        /* > 1: pipelined run, phase times overlap (find on one stream, the rest on another) */
 } sgp_timings;
 
 sgp_status sgp_context_create(int device, sgp_context** out);

@@ -25,6 +25,7 @@ EVENT_NAMES = ("SPECIATION", "CODIVERGENCE", "LEAF", "UNSAMPLED_LEAF", "DUPLICAT
 RNG_PHILOX, RNG_MT_REPLAY = 0, 1
 FLAG_MULTI_TREE_INPUT = 1
 FLAG_KEEP_TREES = 2
+FLAG_SERIAL = 4
 LAYOUT_PACKED, LAYOUT_PER_REPLICATE = 0, 1
 STREAM_UNPRUNED_TREE, STREAM_PRUNED_TREE = 0, 1
 STATUS_OK, STATUS_USAGE = 0, 6
@@ -51,7 +52,7 @@ class SummaryStruct(C.Structure):
 
 class TimingsStruct(C.Structure):
     _fields_ = [("find_ms", C.c_double), ("build_ms", C.c_double), ("label_ms", C.c_double), ("emit_size_ms", C.c_double),
-                ("emit_write_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double), ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64)]
+                ("emit_write_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double), ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("sub_batches", C.c_int64)]
 
 
 _lib = None

@@ -59,7 +59,7 @@ sgp_status sgp_app_run(sgp_context* ctx, const char* app, int argc, const char* 
         if (o.rng_mode == SGP_RNG_MT_REPLAY && !cfg.has_seed) {
             // the reference would seed from /dev/random; replay of an unknown seed is meaningless but harmless
         }
-        BatchOpts bo; bo.n = o.n_replicates; bo.offset = o.replicate_offset; bo.rng_mode = o.rng_mode; bo.stream_mask = o.stream_mask; bo.keep_on_device = o.keep_on_device != 0; bo.keep_trees = (o.flags & SGP_FLAG_KEEP_TREES) != 0;
+        BatchOpts bo; bo.n = o.n_replicates; bo.offset = o.replicate_offset; bo.rng_mode = o.rng_mode; bo.stream_mask = o.stream_mask; bo.keep_on_device = o.keep_on_device != 0; bo.keep_trees = (o.flags & SGP_FLAG_KEEP_TREES) != 0; bo.serial = (o.flags & SGP_FLAG_SERIAL) != 0;
         ctx->ctx->run_treegen(cfg, bo, b->b);
         *out = b;
         return SGP_OK;
@@ -256,7 +256,7 @@ void sgp_batch_timings(const sgp_batch* b, sgp_timings* out) {
     if (!b || !out) return;
     const Timings& t = b->b.timings;
     out->find_ms = t.find_ms; out->build_ms = t.build_ms; out->label_ms = t.label_ms; out->emit_size_ms = t.emit_size_ms; out->emit_write_ms = t.emit_write_ms;
-    out->d2h_ms = t.d2h_ms; out->total_ms = t.total_ms; out->kernel_launches = t.launches; out->h2d_bytes = t.h2d_bytes;
+    out->d2h_ms = t.d2h_ms; out->total_ms = t.total_ms; out->kernel_launches = t.launches; out->h2d_bytes = t.h2d_bytes; out->sub_batches = t.sub_batches;
 }
 
 sgp_status sgp_batch_write_files(sgp_batch* b) {

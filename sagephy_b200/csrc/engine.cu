@@ -151,6 +151,33 @@ __global__ void k_peak_mixed(uint32_t* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ b0 ^ b1 ^ b2 ^ b3;
 }
 
+// Pipelined runs (see run_treegen): replicates per sub-batch, head room of the output buffers that are sized from the first
+// sub-batch, and the mailbox regions of the two streams.
+constexpr long long kSubBatch = 131072;
+constexpr double kOutputMargin = 1.03;
+constexpr size_t kMailFind = 16384, kMailEmit = 16384 + 512;
+
+// offsets[s][i] = carry[s] + sum of sizes[s][0..i) for i in [0, m], one block per stream; carry[s] is advanced to offsets[s][m], which
+// is where the next sub-batch of the run continues (slices of the [stream][stride] arrays of the whole run).
+__global__ void __launch_bounds__(1024) k_scan_streams(const unsigned long long* sizes, unsigned long long* offsets, long long stride, long long m, unsigned long long* carry) {
+    typedef cub::BlockScan<unsigned long long, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    const int s = blockIdx.x;
+    const unsigned long long* in = sizes + (size_t)s * stride; unsigned long long* outp = offsets + (size_t)s * stride;
+    unsigned long long running = carry[s];
+    for (long long base = 0; base < m; base += 1024 * 4) {
+        unsigned long long v[4];
+        const long long i0 = base + (long long)threadIdx.x * 4;
+        for (int q = 0; q < 4; ++q) v[q] = i0 + q < m ? in[i0 + q] : 0ull;
+        unsigned long long block_total;
+        Scan(tmp).ExclusiveSum(v, v, block_total);
+        for (int q = 0; q < 4; ++q) if (i0 + q < m) outp[i0 + q] = running + v[q];
+        running += block_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { outp[m] = running; carry[s] = running; }
+}
+
 struct EventTimer {
     cudaEvent_t a, b; cudaStream_t s;
     explicit EventTimer(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); }
@@ -163,6 +190,7 @@ struct EventTimer {
 
 struct Context::Impl {
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;        // second compute stream of pipelined runs (build / label / emit of sub-batch k under find of k+1)
     cudaStream_t copy = nullptr;
     // Small device->host results (counts, totals, the summary block) travel through a mapped pinned mailbox written by a
     // kernel, not through cudaMemcpy: a DMA copy would queue behind a caller's bulk copies that are still in flight on the
@@ -173,7 +201,7 @@ struct Context::Impl {
     // pool's free blocks costs hundreds of milliseconds of unmap / map).
     void* scratch_buf[8] = {nullptr}; size_t scratch_bytes[8] = {0};
     void* scratch(int slot, size_t bytes);
-    void post(size_t off, const void* dsrc, size_t bytes);
+    void post(size_t off, const void* dsrc, size_t bytes, cudaStream_t on = nullptr);
     template <class T> T take(size_t off) const { T v; memcpy(&v, mailbox + off, sizeof(T)); return v; }
     DevBuf<unsigned long long> g_table; DevBuf<double> p10;
     MathTables T{};
@@ -183,9 +211,9 @@ struct Context::Impl {
 __global__ void k_post_words(uint32_t* dst, const uint32_t* src, int words) {
     for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
 }
-void Context::Impl::post(size_t off, const void* dsrc, size_t bytes) {
+void Context::Impl::post(size_t off, const void* dsrc, size_t bytes, cudaStream_t on) {
     if (off + bytes > kMailboxBytes || (bytes & 3) || (off & 3)) throw SgpError("internal: mailbox overflow");
-    k_post_words<<<1, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(mailbox + off), static_cast<const uint32_t*>(dsrc), (int)(bytes / 4));
+    k_post_words<<<1, 256, 0, on ? on : stream>>>(reinterpret_cast<uint32_t*>(mailbox + off), static_cast<const uint32_t*>(dsrc), (int)(bytes / 4));
 }
 
 void* Context::Impl::scratch(int slot, size_t bytes) {
@@ -203,6 +231,7 @@ Context::Context(int dev) : device(dev), impl(new Impl()) {
     if (dev < 0 || dev >= count) throw SgpError("invalid CUDA device index " + std::to_string(dev));
     CK(cudaSetDevice(dev));
     CK(cudaStreamCreate(&impl->stream));
+    CK(cudaStreamCreateWithFlags(&impl->stream2, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&impl->copy, cudaStreamNonBlocking));
     CK(cudaHostAlloc((void**)&impl->mailbox, Impl::kMailboxBytes, cudaHostAllocMapped | cudaHostAllocPortable));
     g_alloc_stream = impl->stream;
@@ -219,6 +248,7 @@ Context::~Context() {
         cudaSetDevice(device); g_alloc_stream = impl->stream;
         impl->g_table.alloc(0); impl->p10.alloc(0);       // release pool memory before the stream goes away
         cudaStreamSynchronize(impl->stream); cudaStreamDestroy(impl->stream); impl->stream = nullptr; g_alloc_stream = nullptr;
+        if (impl->stream2) { cudaStreamSynchronize(impl->stream2); cudaStreamDestroy(impl->stream2); impl->stream2 = nullptr; }
         if (impl->copy) { cudaStreamSynchronize(impl->copy); cudaStreamDestroy(impl->copy); impl->copy = nullptr; }
         if (impl->mailbox) { cudaFreeHost(impl->mailbox); impl->mailbox = nullptr; }
         for (int i = 0; i < 8; ++i) if (impl->scratch_buf[i]) { cudaFree(impl->scratch_buf[i]); impl->scratch_buf[i] = nullptr; }
@@ -340,7 +370,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     const bool replay = opts.rng_mode == 1;
     out.stream = (void*)st;
     out.n = n; out.device = device; out.app = cfg.app; out.quiet = cfg.quiet; out.out_prefix = cfg.out_prefix;
-    Timings tm; EventTimer total(st), ph(st);
+    Timings tm; EventTimer total(st);
     total.start();
     g_h2d_bytes = 0;
 
@@ -385,142 +415,118 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     DevBuf<int32_t> d_sizes; { std::vector<int32_t> s(cfg.sizes.begin(), cfg.sizes.end()); d_sizes.upload(s); }
     DevBuf<RepInfo> info; info.alloc((size_t)n);
     CK(cudaMemsetAsync(info.p, 0, (size_t)n * sizeof(RepInfo), st));
-    DevBuf<unsigned long long> counter; counter.alloc(1);
-
     const bool fast_bd = !domain && !replay && cfg.P.tau == 0.0 && !cfg.P.do_gene_birth && cfg.host.nV <= 3;
     const bool per_leaf = !(cfg.P.minper <= 0 && cfg.P.maxper >= cfg.P.max_leaves);
     const int sm = impl->sm_count;
 
-    // ---- K1 find -----------------------------------------------------------------------------------------------------------
-    ph.start();
+    // ---- sub-batches ----------------------------------------------------------------------------------------------------------
+    // A run is cut into sub-batches of replicates. With one sub-batch everything runs on the context's stream in the order find ->
+    // build -> label -> emit. With several (HostTreeGen in Philox mode: the find kernel is issue-bound, build / label / emit are
+    // latency-bound) the find kernel of sub-batch k+1 runs on stream A while sub-batch k is built, labelled and emitted on stream B:
+    // the two share the SMs (the find kernel then keeps 3 instead of 4 blocks per SM resident). Stream offsets carry over from one
+    // sub-batch to the next, so the output is the same contiguous, index-ordered byte stream either way.
+    const bool no_pipe_env = getenv("SGP_NO_PIPELINE") != nullptr;
+    long long sub_n = n;
+    if (fast_bd && !opts.keep_trees && !opts.serial && !no_pipe_env && n >= 2 * kSubBatch) sub_n = kSubBatch;
+    const int K = (int)((n + sub_n - 1) / sub_n);
+    const bool piped = K > 1;
+    cudaStream_t stA = st, stB = piped ? impl->stream2 : st;
+    struct Sub {
+        long long r0 = 0, n = 0, total_nodes = 0, aux_stride = 1; int max_pool = 0;
+        DevBuf<unsigned long long> counter; DevBuf<long long> pool, node_off; DevBuf<int> max_pool_d;
+        DevBuf<Node> nodes; DevBuf<int32_t> aux; DevBuf<uint16_t> plen; DevBuf<unsigned long long> dig_f; DevBuf<int16_t> dig_e;
+        cudaEvent_t ev_found = nullptr;
+        ~Sub() { if (ev_found) cudaEventDestroy(ev_found); }
+    };
+    std::vector<std::unique_ptr<Sub>> subs;
+    for (int k = 0; k < K; ++k) { subs.emplace_back(new Sub()); subs.back()->r0 = (long long)k * sub_n; subs.back()->n = std::min<long long>(sub_n, n - (long long)k * sub_n); CK(cudaEventCreateWithFlags(&subs.back()->ev_found, cudaEventDisableTiming)); }
+    // phase times: events recorded around every phase of every sub-batch, read once at the end (no host sync inside the pipeline)
+    struct Span { cudaEvent_t a = nullptr, b = nullptr; double* sink = nullptr; };
+    std::vector<Span> spans;
+    auto span_begin = [&](double* sink, cudaStream_t s) { Span sp; sp.sink = sink; cudaEventCreate(&sp.a); cudaEventCreate(&sp.b); cudaEventRecord(sp.a, s); spans.push_back(sp); return spans.size() - 1; };
+    auto span_end = [&](size_t id, cudaStream_t s) { cudaEventRecord(spans[id].b, s); };
+    struct SpanGuard { std::vector<Span>& v; ~SpanGuard() { for (auto& sp : v) { if (sp.a) cudaEventDestroy(sp.a); if (sp.b) cudaEventDestroy(sp.b); } } } span_guard{spans};
+    // whatever happens, no buffer may be released while the second stream still works on it
+    struct StreamFence { cudaStream_t a, b; ~StreamFence() { if (a != b) { cudaStreamSynchronize(b); } } } fence{stA, stB};
+
     DevBuf<uint32_t> mt_state; DevBuf<int32_t> marks, leafcnt;
-    int max_workers = 0;
-    if (fast_bd) {
-        BdArgs a{}; a.P = P; a.H = make_tiny(cfg.host); a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.keys = philox_keys(seed); a.info = info.p;
-        a.work_counter = counter.p; a.sizes = d_sizes.p;
-        CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
-        int blocks = sm * 4; long long need = (n * 32 + 255) / 256; if (need < blocks) blocks = (int)need;
-        launch_bd_find(a, blocks, st); ++tm.launches;
-        CK(cudaGetLastError());
-    } else {
-        // node capacity of a worker's scratch pool: typical trees fit; the rare larger ones are re-run with 8x the capacity
-        int ref_leaves = cfg.host.nLeaves; for (const HostModel& g : cfg.genes) ref_leaves = std::max(ref_leaves, g.nLeaves);
-        int cap = 1024; while (cap < 6 * ref_leaves && cap < (1 << 16)) cap *= 2;
-        const int mark_n = domain ? max_gene_nv : cfg.host.nV, cnt_n = domain ? max_gene_nv : std::max(1, cfg.host.nLeaves);
-        long long workers = std::min<long long>((long long)sm * 1024, (n + 127) / 128 * 128);
-        DevBuf<long long> redo, keep; DevBuf<unsigned long long> redo_count;
-        const long long* rep_ids = nullptr; long long todo = n;
-        for (int round = 0;; ++round) {
-            // bound scratch to ~24 GiB
-            while ((double)workers * cap * (sizeof(Node) + 8.0) > 24.0 * (1ull << 30) && workers > 128) workers /= 2;
-            workers = std::max<long long>(128, workers / 128 * 128);
-            max_workers = std::max<long long>(max_workers, workers);
-            Node* s_nodes = (Node*)impl->scratch(0, (size_t)workers * cap * sizeof(Node));
-            int32_t* s_queue = (int32_t*)impl->scratch(1, (size_t)workers * cap * sizeof(int32_t)), *s_pend = (int32_t*)impl->scratch(2, (size_t)workers * cap * sizeof(int32_t));
-            // spare pools of 8x the size (~0.8 GB): trees that outgrow a worker's pool are redone at once inside this launch
-            DevBuf<int> b_next;
-            const int big_cap = (int)std::min<long long>((long long)cap * 8, 1 << 24);
-            const int big_count = (int)std::max<long long>(0, std::min<long long>(1024, (long long)((800ull << 20) / ((unsigned long long)big_cap * (sizeof(Node) + 8)))));
-            Node* b_nodes = nullptr; int32_t* b_queue = nullptr, *b_pend = nullptr;
-            if (big_count > 0) {
-                b_nodes = (Node*)impl->scratch(3, (size_t)big_count * big_cap * sizeof(Node));
-                b_queue = (int32_t*)impl->scratch(4, (size_t)big_count * big_cap * sizeof(int32_t)); b_pend = (int32_t*)impl->scratch(5, (size_t)big_count * big_cap * sizeof(int32_t));
-            }
-            b_next.alloc(1); CK(cudaMemsetAsync(b_next.p, 0, sizeof(int), st));
-            marks.alloc((size_t)workers * mark_n); leafcnt.alloc((size_t)workers * cnt_n);
-            if (domain) scratch_used.alloc((size_t)workers * cfg.genes.size());
-            if (replay) mt_state.alloc((size_t)(workers / 32 + 1) * 624 * 32);
-            FindArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = todo; a.rep_ids = rep_ids; a.rep_base = opts.offset; a.seed = seed; a.sseed = sseed; a.info = info.p;
-            a.work_counter = counter.p; a.scratch_nodes = s_nodes; a.scratch_queue = s_queue; a.scratch_pend = s_pend; a.cap = cap;
-            a.scratch_marks = marks.p; a.scratch_leafcnt = leafcnt.p; a.mt_state = mt_state.p; a.sizes = d_sizes.p; a.per_leaf_check = per_leaf;
-            a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
-            a.scratch_used = scratch_used.p; a.ev_base = d_ev_base.p; a.ev_off = d_ev_off.p; a.ev_list = d_ev_list.p;
-            a.big_nodes = b_nodes; a.big_queue = b_queue; a.big_pend = b_pend; a.big_cap = big_cap; a.big_count = big_count; a.big_next = b_next.p;
-            CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
-            int blocks = (int)(workers / 128);
-            launch_find_general(replay, domain, a, blocks, st);
-            ++tm.launches;
+    size_t scan_tmp_bytes = 0; cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp_bytes, (long long*)nullptr, (long long*)nullptr, (int)(sub_n + 1), stA);
+    DevBuf<char> scan_tmp; scan_tmp.alloc(scan_tmp_bytes);
+
+    // ---- K1 find (stream A) -------------------------------------------------------------------------------------------------
+    auto enqueue_find = [&](Sub& S, int k) {
+        const size_t sp = span_begin(&tm.find_ms, stA);
+        S.counter.alloc(1); CK(cudaMemsetAsync(S.counter.p, 0, sizeof(unsigned long long), stA));
+        if (fast_bd) {
+            BdArgs a{}; a.P = P; a.H = make_tiny(cfg.host); a.T = impl->T; a.n = S.n; a.rep_base = opts.offset + S.r0; a.seed = seed; a.keys = philox_keys(seed); a.info = info.p + S.r0;
+            a.work_counter = S.counter.p; a.sizes = d_sizes.p;
+            int blocks = sm * 4; long long need = (S.n * 32 + 255) / 256; if (need < blocks) blocks = (int)need;
+            launch_bd_find(a, blocks, piped ? 3 : 4, stA); ++tm.launches;
             CK(cudaGetLastError());
-            // replicates that ran out of node capacity are re-run with a larger pool
-            redo.alloc((size_t)n); redo_count.alloc(1);
-            CK(cudaMemsetAsync(redo_count.p, 0, sizeof(unsigned long long), st));
-            k_collect_status<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(info.p, n, REP_NODE_OVERFLOW, redo.p, redo_count.p); ++tm.launches;
-            impl->post(0, redo_count.p, sizeof(unsigned long long));
-            CK(cudaStreamSynchronize(st));
-            const unsigned long long cnt = impl->take<unsigned long long>(0);
-            if (cnt == 0 || cap >= (1 << 24) || round > 8) break;
-            keep.alloc((size_t)cnt);
-            CK(cudaMemcpyAsync(keep.p, redo.p, cnt * sizeof(long long), cudaMemcpyDeviceToDevice, st));
-            CK(cudaStreamSynchronize(st));
-            rep_ids = keep.p; todo = (long long)cnt; cap *= 8; workers = std::min<long long>(workers, (todo + 127) / 128 * 128);
+        } else {
+            // node capacity of a worker's scratch pool: typical trees fit; the rare larger ones are re-run with 8x the capacity
+            int ref_leaves = cfg.host.nLeaves; for (const HostModel& g : cfg.genes) ref_leaves = std::max(ref_leaves, g.nLeaves);
+            int cap = 1024; while (cap < 6 * ref_leaves && cap < (1 << 16)) cap *= 2;
+            const int mark_n = domain ? max_gene_nv : cfg.host.nV, cnt_n = domain ? max_gene_nv : std::max(1, cfg.host.nLeaves);
+            long long workers = std::min<long long>((long long)sm * 1024, (n + 127) / 128 * 128);
+            DevBuf<long long> redo, keep; DevBuf<unsigned long long> redo_count;
+            const long long* rep_ids = nullptr; long long todo = n;
+            for (int round = 0;; ++round) {
+                // bound scratch to ~24 GiB
+                while ((double)workers * cap * (sizeof(Node) + 8.0) > 24.0 * (1ull << 30) && workers > 128) workers /= 2;
+                workers = std::max<long long>(128, workers / 128 * 128);
+                Node* s_nodes = (Node*)impl->scratch(0, (size_t)workers * cap * sizeof(Node));
+                int32_t* s_queue = (int32_t*)impl->scratch(1, (size_t)workers * cap * sizeof(int32_t)), *s_pend = (int32_t*)impl->scratch(2, (size_t)workers * cap * sizeof(int32_t));
+                // spare pools of 8x the size (~0.8 GB): trees that outgrow a worker's pool are redone at once inside this launch
+                DevBuf<int> b_next;
+                const int big_cap = (int)std::min<long long>((long long)cap * 8, 1 << 24);
+                const int big_count = (int)std::max<long long>(0, std::min<long long>(1024, (long long)((800ull << 20) / ((unsigned long long)big_cap * (sizeof(Node) + 8)))));
+                Node* b_nodes = nullptr; int32_t* b_queue = nullptr, *b_pend = nullptr;
+                if (big_count > 0) {
+                    b_nodes = (Node*)impl->scratch(3, (size_t)big_count * big_cap * sizeof(Node));
+                    b_queue = (int32_t*)impl->scratch(4, (size_t)big_count * big_cap * sizeof(int32_t)); b_pend = (int32_t*)impl->scratch(5, (size_t)big_count * big_cap * sizeof(int32_t));
+                }
+                b_next.alloc(1); CK(cudaMemsetAsync(b_next.p, 0, sizeof(int), stA));
+                marks.alloc((size_t)workers * mark_n); leafcnt.alloc((size_t)workers * cnt_n);
+                if (domain) scratch_used.alloc((size_t)workers * cfg.genes.size());
+                if (replay) mt_state.alloc((size_t)(workers / 32 + 1) * 624 * 32);
+                FindArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = todo; a.rep_ids = rep_ids; a.rep_base = opts.offset; a.seed = seed; a.sseed = sseed; a.info = info.p;
+                a.work_counter = S.counter.p; a.scratch_nodes = s_nodes; a.scratch_queue = s_queue; a.scratch_pend = s_pend; a.cap = cap;
+                a.scratch_marks = marks.p; a.scratch_leafcnt = leafcnt.p; a.mt_state = mt_state.p; a.sizes = d_sizes.p; a.per_leaf_check = per_leaf;
+                a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
+                a.scratch_used = scratch_used.p; a.ev_base = d_ev_base.p; a.ev_off = d_ev_off.p; a.ev_list = d_ev_list.p;
+                a.big_nodes = b_nodes; a.big_queue = b_queue; a.big_pend = b_pend; a.big_cap = big_cap; a.big_count = big_count; a.big_next = b_next.p;
+                CK(cudaMemsetAsync(S.counter.p, 0, sizeof(unsigned long long), stA));
+                int blocks = (int)(workers / 128);
+                launch_find_general(replay, domain, a, blocks, stA);
+                ++tm.launches;
+                CK(cudaGetLastError());
+                // replicates that ran out of node capacity are re-run with a larger pool
+                redo.alloc((size_t)n); redo_count.alloc(1);
+                CK(cudaMemsetAsync(redo_count.p, 0, sizeof(unsigned long long), stA));
+                k_collect_status<<<(unsigned)((n + 255) / 256), 256, 0, stA>>>(info.p, n, REP_NODE_OVERFLOW, redo.p, redo_count.p); ++tm.launches;
+                impl->post(0, redo_count.p, sizeof(unsigned long long), stA);
+                CK(cudaStreamSynchronize(stA));
+                const unsigned long long cnt = impl->take<unsigned long long>(0);
+                if (cnt == 0 || cap >= (1 << 24) || round > 8) break;
+                keep.alloc((size_t)cnt);
+                CK(cudaMemcpyAsync(keep.p, redo.p, cnt * sizeof(long long), cudaMemcpyDeviceToDevice, stA));
+                CK(cudaStreamSynchronize(stA));
+                rep_ids = keep.p; todo = (long long)cnt; cap *= 8; workers = std::min<long long>(workers, (todo + 127) / 128 * 128);
+            }
         }
-    }
-    tm.find_ms = ph.stop();
+        span_end(sp, stA);
+        // node offsets of the sub-batch: exclusive scan of the accepted attempts' pool sizes
+        S.pool.alloc((size_t)S.n + 1); S.node_off.alloc((size_t)S.n + 1); S.max_pool_d.alloc(1);
+        CK(cudaMemsetAsync(S.pool.p, 0, ((size_t)S.n + 1) * sizeof(long long), stA));
+        CK(cudaMemsetAsync(S.max_pool_d.p, 0, sizeof(int), stA));
+        k_extract_pool<<<(unsigned)((S.n + 255) / 256), 256, 0, stA>>>(info.p + S.r0, S.n, S.pool.p, S.max_pool_d.p); ++tm.launches;
+        size_t tb = scan_tmp_bytes;
+        cub::DeviceScan::ExclusiveSum(scan_tmp.p, tb, S.pool.p, S.node_off.p, (int)(S.n + 1), stA); ++tm.launches;
+        impl->post(kMailFind + (size_t)(k & 15) * 16, S.node_off.p + S.n, sizeof(long long), stA); impl->post(kMailFind + (size_t)(k & 15) * 16 + 8, S.max_pool_d.p, sizeof(int), stA);
+        CK(cudaEventRecord(S.ev_found, stA));
+    };
 
-    // ---- node offsets ------------------------------------------------------------------------------------------------------
-    DevBuf<long long> pool, node_off; pool.alloc((size_t)n + 1); node_off.alloc((size_t)n + 1);
-    CK(cudaMemsetAsync(pool.p, 0, ((size_t)n + 1) * sizeof(long long), st));
-    DevBuf<int> max_pool_d; max_pool_d.alloc(1);
-    CK(cudaMemsetAsync(max_pool_d.p, 0, sizeof(int), st));
-    k_extract_pool<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(info.p, n, pool.p, max_pool_d.p); ++tm.launches;
-    {
-        size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, pool.p, node_off.p, (int)(n + 1), st);
-        DevBuf<char> tmp; tmp.alloc(tb);
-        cub::DeviceScan::ExclusiveSum(tmp.p, tb, pool.p, node_off.p, (int)(n + 1), st); ++tm.launches;
-        impl->post(0, node_off.p + n, sizeof(long long)); impl->post(8, max_pool_d.p, sizeof(int));
-        CK(cudaStreamSynchronize(st));
-    }
-    const long long total_nodes = impl->take<long long>(0);
-    const int max_pool = impl->take<int>(8);
-    DevBuf<Node> nodes; DevBuf<int32_t> aux;
-    const long long aux_stride = std::max<long long>(total_nodes, 1);
-    nodes.alloc((size_t)std::max<long long>(total_nodes, 1)); aux.alloc((size_t)aux_stride * 4);
-
-    // ---- K1 build ------------------------------------------------------------------------------------------------------------
-    ph.start();
-    if (fast_bd) {
-        BdArgs a{}; a.P = P; a.H = make_tiny(cfg.host); a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.keys = philox_keys(seed); a.info = info.p;
-        a.node_off = node_off.p; a.nodes = nodes.p;
-        launch_bd_build(a, (int)((n + 255) / 256), st); ++tm.launches;
-    } else {
-        const long long threads = std::max<long long>(128, std::min<long long>((long long)sm * 1024, (n + 127) / 128 * 128));
-        marks.alloc((size_t)threads * (domain ? max_gene_nv : cfg.host.nV));
-        if (domain) scratch_used.alloc((size_t)threads * cfg.genes.size());
-        if (replay) mt_state.alloc((size_t)(threads / 32 + 1) * 624 * 32);
-        CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
-        BuildArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.sseed = sseed; a.info = info.p; a.node_off = node_off.p; a.work_counter = counter.p;
-        a.nodes = nodes.p; a.aux = aux.p; a.aux_stride = aux_stride; a.scratch_marks = marks.p; a.scratch_leafcnt = nullptr; a.mt_state = mt_state.p;
-        a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
-        a.scratch_used = scratch_used.p; a.ev_base = d_ev_base.p; a.ev_off = d_ev_off.p; a.ev_list = d_ev_list.p;
-        // a lane builds its tree alone, so the largest trees set the kernel's tail: start them first
-        DevBuf<long long> order, n_sel; DevBuf<char> ptmp;
-        if (n >= 4096) {
-            order.alloc((size_t)n); n_sel.alloc(1);
-            cub::CountingInputIterator<long long> ids(0);
-            PoolAbove big{pool.p, 4 * (total_nodes / n) + 64};
-            size_t pb = 0; cub::DevicePartition::If(nullptr, pb, ids, order.p, n_sel.p, (int)n, big, st);
-            ptmp.alloc(pb);
-            cub::DevicePartition::If(ptmp.p, pb, ids, order.p, n_sel.p, (int)n, big, st); ++tm.launches;
-            a.order = order.p; a.n_big = n_sel.p;
-        }
-        launch_build_general(replay, domain, a, (int)(threads / 128), st);
-        ++tm.launches;
-    }
-    CK(cudaGetLastError());
-    tm.build_ms = ph.stop();
-
-    // ---- K3 label / prune ----------------------------------------------------------------------------------------------------
-    ph.start();
-    {
-        LabelArgs a{}; a.n = n; a.info = info.p; a.node_off = node_off.p; a.nodes = nodes.p; a.aux = aux.p; a.aux_stride = aux_stride; a.T = impl->T;
-        a.host_root_time = cfg.host.vtime[cfg.host.root]; a.has_stem_override = cfg.has_stem_override; a.stem_override = cfg.stem_override;
-        a.pool = pool.p;
-        tm.launches += launch_label_prune(a, max_pool, impl->sm_count, st);
-        CK(cudaGetLastError());
-    }
-    tm.label_ms = ph.stop();
-
-    // ---- K4 emit ---------------------------------------------------------------------------------------------------------------
     unsigned mask = opts.stream_mask;
     if (mask == 0) {
         if (cfg.quiet) mask = 1u << ST_PRUNED_TREE;
@@ -572,65 +578,161 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     for (const HostModel& gm : cfg.genes) { gene_epb.push_back((int32_t)(gene_ept.size() / 3)); for (int q = 0; q < gm.nE; ++q) { gene_ept.push_back(gm.ep_lo[q]); gene_ept.push_back(gm.ep_mid[q]); gene_ept.push_back(gm.ep_up[q]); } }
     DevBuf<double> d_gene_ept; d_gene_ept.upload(gene_ept); DevBuf<int32_t> d_gene_epb; d_gene_epb.upload(gene_epb);
     DevBuf<int32_t> d_gname, d_leafname, d_leaf_base, d_g2h_gene; d_gname.upload(gname); d_leafname.upload(leafname); d_leaf_base.upload(leaf_base); d_g2h_gene.upload(g2h_gene);
-    DevBuf<unsigned long long> sizes, offsets; sizes.alloc((size_t)ST_COUNT * (n + 1)); offsets.alloc((size_t)ST_COUNT * (n + 1));
-    CK(cudaMemsetAsync(sizes.p, 0, (size_t)ST_COUNT * (n + 1) * sizeof(unsigned long long), st));
-    e.n = n; e.rep_base = opts.offset; e.info = info.p; e.node_off = node_off.p; e.nodes = nodes.p; e.aux = aux.p; e.aux_stride = aux_stride; e.T = impl->T;
+    // sizes / offsets of all replicates, [stream][n + 1]; a sub-batch fills its slice, offsets carry over
+    const long long stride = n + 1;
+    DevBuf<unsigned long long> sizes, offsets, carry; sizes.alloc((size_t)ST_COUNT * stride); offsets.alloc((size_t)ST_COUNT * stride); carry.alloc(ST_COUNT);
+    CK(cudaMemsetAsync(sizes.p, 0, (size_t)ST_COUNT * stride * sizeof(unsigned long long), stA));
+    CK(cudaMemsetAsync(offsets.p, 0, (size_t)ST_COUNT * stride * sizeof(unsigned long long), stA));
+    CK(cudaMemsetAsync(carry.p, 0, ST_COUNT * sizeof(unsigned long long), stA));
+    DevBuf<int> overflow; overflow.alloc(1); CK(cudaMemsetAsync(overflow.p, 0, sizeof(int), stA));
+    e.rep_base = opts.offset; e.T = impl->T;
     e.app = cfg.app; e.exclude_meta = cfg.exclude_meta; e.append_sigma = cfg.append_sigma; e.is_species = cfg.is_species; e.stream_mask = mask;
     e.prefix_len = (int)std::min<size_t>(cfg.vertex_prefix.size(), sizeof(e.prefix)); memcpy(e.prefix, cfg.vertex_prefix.data(), e.prefix_len);
     if (cfg.vertex_prefix.size() > sizeof(e.prefix)) throw SgpError("vertex prefix longer than 24 bytes is not supported");
     e.blob = d_blob.p; e.gname_off = d_gname.p; e.leafname_off = d_leafname.p; e.ep_times = hd.ep_times.p;
     e.leaf_base = d_leaf_base.p; e.g2h_gene_off = d_g2h_gene.p; e.gene_ep_times = d_gene_ept.p; e.gene_ep_base = d_gene_epb.p;
-    // sizes are laid out [stream][n+1] so that one scan per stream yields offsets with the total in the last slot
-    DevBuf<unsigned long long> sizes_n; sizes_n.alloc((size_t)ST_COUNT * n);
-    CK(cudaMemsetAsync(sizes_n.p, 0, (size_t)ST_COUNT * n * sizeof(unsigned long long), st));
-    DevBuf<uint16_t> plen; DevBuf<unsigned long long> dig_f; DevBuf<int16_t> dig_e;
-    plen.alloc((size_t)ST_COUNT * aux_stride); dig_f.alloc((size_t)2 * aux_stride); dig_e.alloc((size_t)2 * aux_stride);
-    e.plen = plen.p; e.dig_f = dig_f.p; e.dig_e = dig_e.p;
-    e.sizes = sizes_n.p; e.offsets = offsets.p;
-    const unsigned emit_blocks = (unsigned)((n * 32 + 127) / 128);
-    ph.start();
-    tm.launches += launch_emit(false, e, emit_blocks, st);
-    CK(cudaGetLastError());
-    {
-        size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, sizes.p, offsets.p, (int)(n + 1), st);
-        DevBuf<char> tmp; tmp.alloc(tb);
-        for (int s = 0; s < ST_COUNT; ++s) {
-            CK(cudaMemcpyAsync(sizes.p + (size_t)s * (n + 1), sizes_n.p + (size_t)s * n, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
-            cub::DeviceScan::ExclusiveSum(tmp.p, tb, sizes.p + (size_t)s * (n + 1), offsets.p + (size_t)s * (n + 1), (int)(n + 1), st); ++tm.launches;
+    e.stride = stride; e.overflow = overflow.p;
+    cudaEvent_t ev_setup = nullptr; CK(cudaEventCreateWithFlags(&ev_setup, cudaEventDisableTiming));
+    struct EvGuard { cudaEvent_t& e; ~EvGuard() { if (e) cudaEventDestroy(e); } } ev_guard{ev_setup};
+    CK(cudaEventRecord(ev_setup, stA));
+    if (piped) CK(cudaStreamWaitEvent(stB, ev_setup, 0));
+    unsigned long long totals[ST_COUNT] = {0}, out_cap[ST_COUNT] = {0};
+
+    // ---- build -> label -> emit of one sub-batch (stream B) ---------------------------------------------------------------------
+    auto emit_args_for = [&](Sub& S) {
+        EmitArgs a = e; a.n = S.n; a.rep_base = opts.offset + S.r0; a.info = info.p + S.r0; a.node_off = S.node_off.p; a.nodes = S.nodes.p; a.aux = S.aux.p; a.aux_stride = S.aux_stride;
+        a.plen = S.plen.p; a.dig_f = S.dig_f.p; a.dig_e = S.dig_e.p; a.sizes = sizes.p + S.r0; a.offsets = offsets.p + S.r0;
+        for (int q = 0; q < ST_COUNT; ++q) { a.out[q] = out.d_stream[q]; a.cap[q] = out_cap[q]; }
+        return a;
+    };
+    auto post_process = [&](Sub& S, int k) {
+        CK(cudaEventSynchronize(S.ev_found));
+        S.total_nodes = impl->take<long long>(kMailFind + (size_t)(k & 15) * 16); S.max_pool = impl->take<int>(kMailFind + (size_t)(k & 15) * 16 + 8);
+        if (piped) CK(cudaStreamWaitEvent(stB, S.ev_found, 0));
+        g_alloc_stream = stB;
+        S.aux_stride = std::max<long long>(S.total_nodes, 1);
+        S.nodes.alloc((size_t)S.aux_stride); S.aux.alloc((size_t)S.aux_stride * 4);
+        S.plen.alloc((size_t)ST_COUNT * S.aux_stride); S.dig_f.alloc((size_t)2 * S.aux_stride); S.dig_e.alloc((size_t)2 * S.aux_stride);
+        g_alloc_stream = stA;
+        size_t sp = span_begin(&tm.build_ms, stB);
+        if (fast_bd) {
+            BdArgs a{}; a.P = P; a.H = make_tiny(cfg.host); a.T = impl->T; a.n = S.n; a.rep_base = opts.offset + S.r0; a.seed = seed; a.keys = philox_keys(seed); a.info = info.p + S.r0;
+            a.node_off = S.node_off.p; a.nodes = S.nodes.p;
+            launch_bd_build(a, (int)((S.n + 255) / 256), stB); ++tm.launches;
+        } else {
+            const long long threads = std::max<long long>(128, std::min<long long>((long long)sm * 1024, (n + 127) / 128 * 128));
+            marks.alloc((size_t)threads * (domain ? max_gene_nv : cfg.host.nV));
+            if (domain) scratch_used.alloc((size_t)threads * cfg.genes.size());
+            if (replay) mt_state.alloc((size_t)(threads / 32 + 1) * 624 * 32);
+            CK(cudaMemsetAsync(S.counter.p, 0, sizeof(unsigned long long), stB));
+            BuildArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.sseed = sseed; a.info = info.p; a.node_off = S.node_off.p; a.work_counter = S.counter.p;
+            a.nodes = S.nodes.p; a.aux = S.aux.p; a.aux_stride = S.aux_stride; a.scratch_marks = marks.p; a.scratch_leafcnt = nullptr; a.mt_state = mt_state.p;
+            a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
+            a.scratch_used = scratch_used.p; a.ev_base = d_ev_base.p; a.ev_off = d_ev_off.p; a.ev_list = d_ev_list.p;
+            // a lane builds its tree alone, so the largest trees set the kernel's tail: start them first
+            DevBuf<long long> order, n_sel; DevBuf<char> ptmp;
+            if (n >= 4096) {
+                order.alloc((size_t)n); n_sel.alloc(1);
+                cub::CountingInputIterator<long long> ids(0);
+                PoolAbove big{S.pool.p, 4 * (S.total_nodes / n) + 64};
+                size_t pb = 0; cub::DevicePartition::If(nullptr, pb, ids, order.p, n_sel.p, (int)n, big, stB);
+                ptmp.alloc(pb);
+                cub::DevicePartition::If(ptmp.p, pb, ids, order.p, n_sel.p, (int)n, big, stB); ++tm.launches;
+                a.order = order.p; a.n_big = n_sel.p;
+            }
+            launch_build_general(replay, domain, a, (int)(threads / 128), stB);
+            ++tm.launches;
         }
-        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        span_end(sp, stB);
+        sp = span_begin(&tm.label_ms, stB);
+        {
+            LabelArgs a{}; a.n = S.n; a.info = info.p + S.r0; a.node_off = S.node_off.p; a.nodes = S.nodes.p; a.aux = S.aux.p; a.aux_stride = S.aux_stride; a.T = impl->T;
+            a.host_root_time = cfg.host.vtime[cfg.host.root]; a.has_stem_override = cfg.has_stem_override; a.stem_override = cfg.stem_override;
+            a.pool = S.pool.p;
+            tm.launches += launch_label_prune(a, S.max_pool, impl->sm_count, stB);
+            CK(cudaGetLastError());
+        }
+        span_end(sp, stB);
+        sp = span_begin(&tm.emit_size_ms, stB);
+        const unsigned emit_blocks = (unsigned)((S.n * 32 + 127) / 128);
+        EmitArgs ea = emit_args_for(S);
+        tm.launches += launch_emit(false, ea, emit_blocks, stB);
+        CK(cudaGetLastError());
+        k_scan_streams<<<ST_COUNT, 1024, 0, stB>>>(sizes.p + S.r0, offsets.p + S.r0, stride, S.n, carry.p); ++tm.launches;
+        span_end(sp, stB);
+        if (k == 0) {
+            // output buffers: exact for a single sub-batch, otherwise sized from the first sub-batch's bytes per replicate with a margin
+            // (a later sub-batch that does not fit raises `overflow`; the run is then repeated unpipelined with exact sizes)
+            impl->post(kMailEmit, carry.p, ST_COUNT * sizeof(unsigned long long), stB);
+            CK(cudaStreamSynchronize(stB));
+            g_alloc_stream = stB;
+            for (int q = 0; q < ST_COUNT; ++q) {
+                const unsigned long long first = impl->take<unsigned long long>(kMailEmit + (size_t)q * 8);
+                unsigned long long cap = first;
+                if (piped) {
+                    const char* me = getenv("SGP_OUTPUT_MARGIN");        // test hook: a margin below 1 forces the fallback
+                    const double margin = me ? atof(me) : kOutputMargin;
+                    const double per = (double)first / (double)S.n; cap = (unsigned long long)(per * (double)n * margin) + (me ? 0ull : (1ull << 20));
+                }
+                out_cap[q] = std::max<unsigned long long>(cap, 1);
+                CK(cudaMallocAsync(&out.d_stream[q], out_cap[q], stB));
+            }
+            g_alloc_stream = stA;
+            ea = emit_args_for(S);
+        }
+        sp = span_begin(&tm.emit_write_ms, stB);
+        tm.launches += launch_emit(true, ea, emit_blocks, stB);
+        CK(cudaGetLastError());
+        span_end(sp, stB);
+        if (piped) {        // the vertex records of this sub-batch are not needed any more: hand them back in stream order
+            g_alloc_stream = stB;
+            S.nodes.alloc(0); S.aux.alloc(0); S.plen.alloc(0); S.dig_f.alloc(0); S.dig_e.alloc(0);
+            g_alloc_stream = stA;
+        }
+    };
+
+    struct StreamFence2 { cudaStream_t a, b; ~StreamFence2() { if (a != b) cudaStreamSynchronize(b); } } fence_last{stA, stB};      // destroyed first: before any buffer above
+    enqueue_find(*subs[0], 0);
+    for (int k = 0; k < K; ++k) {
+        if (k + 1 < K) enqueue_find(*subs[(size_t)k + 1], k + 1);       // stream A always has the next find queued before the host waits
+        post_process(*subs[(size_t)k], k);
     }
-    tm.emit_size_ms = ph.stop();
-    unsigned long long totals[ST_COUNT];
-    for (int s = 0; s < ST_COUNT; ++s) impl->post((size_t)s * 8, offsets.p + (size_t)s * (n + 1) + n, sizeof(unsigned long long));
-    CK(cudaStreamSynchronize(st));
-    for (int s = 0; s < ST_COUNT; ++s) totals[s] = impl->take<unsigned long long>((size_t)s * 8);
-    for (int s = 0; s < ST_COUNT; ++s) { out.stream_bytes[s] = totals[s]; CK(cudaMallocAsync(&out.d_stream[s], std::max<unsigned long long>(totals[s], 1), st)); e.out[s] = out.d_stream[s]; }
-    ph.start();
-    tm.launches += launch_emit(true, e, emit_blocks, st);
-    CK(cudaGetLastError());
-    tm.emit_write_ms = ph.stop();
+    impl->post(kMailEmit, carry.p, ST_COUNT * sizeof(unsigned long long), stB); impl->post(kMailEmit + 64, overflow.p, sizeof(int), stB);
+    CK(cudaStreamSynchronize(stB)); CK(cudaStreamSynchronize(stA));
+    for (int q = 0; q < ST_COUNT; ++q) { totals[q] = impl->take<unsigned long long>(kMailEmit + (size_t)q * 8); out.stream_bytes[q] = totals[q]; }
+    if (impl->take<int>(kMailEmit + 64) != 0) {
+        // a stream outgrew its estimated buffer: start over without the pipeline (exact sizes)
+        for (int q = 0; q < ST_COUNT; ++q) { if (out.d_stream[q]) { cudaFree(out.d_stream[q]); out.d_stream[q] = nullptr; } out.stream_bytes[q] = 0; }
+        subs.clear();
+        BatchOpts o2 = opts; o2.serial = true;
+        run_treegen(cfg, o2, out);
+        return;
+    }
+    for (auto& sp : spans) { float ms = 0; if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) *sp.sink += ms; }
 
     // ---- summary ---------------------------------------------------------------------------------------------------------------
     {
         DevBuf<DevSummary> ds; ds.alloc(1); CK(cudaMemsetAsync(ds.p, 0, sizeof(DevSummary), st));
         k_summary<<<(unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)impl->sm_count * 4)), 256, 0, st>>>(info.p, n, ds.p); ++tm.launches;
-        impl->post(0, ds.p, sizeof(DevSummary)); CK(cudaStreamSynchronize(st));
+        impl->post(0, ds.p, sizeof(DevSummary), st); CK(cudaStreamSynchronize(st));
         const DevSummary hs = impl->take<DevSummary>(0);
         Summary& S = out.summary; S.n_ok = (long long)hs.n_ok; S.n_failed = (long long)hs.n_failed; S.attempts_total = (long long)hs.attempts_total; S.vertices_sampled = (long long)hs.vertices; S.vertices_abandoned = (long long)hs.vertices_abandoned; S.attempts_completed = (long long)hs.attempts_completed;
         for (int i = 0; i < 17; ++i) S.event_counts[i] = (long long)hs.ev[i];
         for (int i = 0; i < 1025; ++i) S.leaf_hist[i] = (long long)hs.leaf_hist[i];
         for (int s = 0; s < ST_COUNT; ++s) S.out_bytes[s] = (long long)totals[s];
     }
-    out.d_offsets = offsets.release(); out.d_info = info.release();
+    out.d_offsets = offsets.release(); out.d_info = info.release(); out.offsets_stride = stride;
     if (opts.keep_trees) {
-        out.d_nodes = nodes.release(); out.d_aux = aux.release(); out.d_node_off = node_off.release(); out.aux_stride = aux_stride;
+        Sub& S = *subs[0];
+        out.d_nodes = S.nodes.release(); out.d_aux = S.aux.release(); out.d_node_off = S.node_off.release(); out.aux_stride = S.aux_stride;
         out.name_prefix = cfg.vertex_prefix; out.name_append_sigma = cfg.append_sigma;
     }
     static const char* host_sfx[8] = {".unpruned.tree", ".pruned.tree", ".unpruned.info", ".pruned.info", ".unpruned.guest2host", ".pruned.guest2host", ".unpruned.leafmap", ".pruned.leafmap"};
     for (int s = 0; s < 8; ++s) out.suffix[s] = (mask & (1u << s)) ? host_sfx[s] : "";
     out.stream_mask = mask;
     tm.total_ms = total.stop(); tm.h2d_bytes = (long long)g_h2d_bytes;
+    tm.sub_batches = K;
     out.timings = tm;
     if (!opts.keep_on_device) {
         EventTimer d2h(st); d2h.start();

@@ -66,9 +66,10 @@ struct BatchOpts {
     bool keep_on_device = false;
     bool multi_tree_input = false;
     bool keep_trees = false;  // tree generators: leave the vertex records on the device for a chained stage
+    bool serial = false;      // no sub-batch pipeline (clean per-phase timings; also the fallback when an output estimate was too small)
 };
 
-struct Timings { double find_ms = 0, build_ms = 0, label_ms = 0, emit_size_ms = 0, emit_write_ms = 0, d2h_ms = 0, total_ms = 0; long long launches = 0, h2d_bytes = 0; };
+struct Timings { double find_ms = 0, build_ms = 0, label_ms = 0, emit_size_ms = 0, emit_write_ms = 0, d2h_ms = 0, total_ms = 0; long long launches = 0, h2d_bytes = 0; int sub_batches = 1; };
 
 struct Summary {
     long long n_ok = 0, n_failed = 0, attempts_total = 0, vertices_sampled = 0, vertices_abandoned = 0, attempts_completed = 0;
@@ -92,6 +93,7 @@ public:
     // device
     char* d_stream[8] = {nullptr}; unsigned long long stream_bytes[8] = {0};
     unsigned long long* d_offsets = nullptr;      // [8][n+1]
+    long long offsets_stride = 0;
     void* d_info = nullptr;                       // RepInfo[n]
     // kept only with BatchOpts::keep_trees: vertex records, order arrays (4 x aux_stride), first record of each replicate
     void* d_nodes = nullptr; int32_t* d_aux = nullptr; long long* d_node_off = nullptr; long long aux_stride = 0;

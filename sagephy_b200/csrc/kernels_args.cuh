@@ -113,9 +113,14 @@ struct EmitArgs {
     uint16_t* plen;                // [ST_COUNT][aux_stride] cached piece lengths (size pass -> write pass)
     unsigned long long* dig_f;     // [2][aux_stride] cached shortest-decimal digits of branch lengths (unpruned, pruned)
     int16_t* dig_e;                // [2][aux_stride] ... and their decimal exponents
-    unsigned long long* sizes;     // [ST_COUNT][n]  (size pass output)
-    const unsigned long long* offsets;   // [ST_COUNT][n+1] (write pass input)
+    // sizes / offsets are laid out [ST_COUNT][stride] over ALL replicates of the run; a launch covers the `n` replicates that
+    // start at the position these pointers already point to (sub-batches of a pipelined run)
+    long long stride;
+    unsigned long long* sizes;     // size pass output: sizes[st * stride + r]
+    const unsigned long long* offsets;   // write pass input: offsets[st * stride + r], end of the replicate at [.. + r + 1]
     char* out[ST_COUNT];
+    unsigned long long cap[ST_COUNT];    // bytes allocated per stream: a replicate that would end beyond it is not written ...
+    int* overflow;                       // ... and raises this flag (the engine then grows the buffers and writes again)
 };
 
 }  // namespace sgp

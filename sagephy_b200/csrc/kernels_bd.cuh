@@ -105,22 +105,42 @@ __global__ void __launch_bounds__(kBdFindThreads) k_bd_find(BdArgs a) {
 }
 
 // Single-arc specialisation (HostTreeGen without -bi; requires vtime[0] == 0): no arc bookkeeping, and the vertex step is
-// branch-free. The lineage stack keeps its top element in a register: st[d] is the start time of parked lineage d (1-based,
-// st[0] is a dummy so that the refill load never needs a guard), `tos` mirrors st[depth]. A duplication stores the sibling and
+// branch-free. The lineage stack keeps its top element in a register: slot d is the start time of parked lineage d (1-based,
+// slot 0 is a dummy so that the refill load never needs a guard), `tos` mirrors slot `depth`. A duplication stores the sibling and
 // continues with one child; every other event continues with `tos` and issues the refill load one whole vertex step before its
 // value can be needed. Lanes of a warp take different events every trip, so selects instead of branches halve the issue count.
-__global__ void __launch_bounds__(kBdFindThreads, 4) k_bd_find_single(BdArgs a) {
-    __shared__ double2 s_logtab[128];
-    load_log_table(s_logtab);
+//
+// The first kBdSmemStack slots of every lane's stack live in SHARED memory, laid out [slot][thread]: lanes sit at different
+// depths, so a per-thread local-memory array made every stack access touch up to 32 different L1 lines (32 wavefronts per
+// instruction), while [slot][thread] hits 32 different banks whatever the depths are (2 wavefronts for 8-byte words). The C2
+// workload is below depth 16 in 99.997 % of its vertex steps; deeper lineages spill to a local-memory tail.
+constexpr int kBdSmemStack = 16;
+constexpr int kBdLogCopies = 4;         // replicated log table (see log_unit)
+__device__ __forceinline__ int lds_volatile(uint32_t addr) { int v; asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ int atoms_add(uint32_t addr, int v) { int o; asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(o) : "r"(addr), "r"(v) : "memory"); return o; }
+__device__ __forceinline__ void atoms_min(uint32_t addr, int v) { asm volatile("red.shared.min.s32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+// Variants (template parameters; the engine picks one, SGP_FIND_VARIANT overrides it for A/B measurements):
+//   SMEM_STACK  first kBdSmemStack stack slots in shared memory [slot][thread] instead of a per-thread local array
+//   LOGCOPIES   replication factor of the log table
+//   PTXCTL      control words through ld.volatile.shared / atom.shared with addresses computed once
+template <bool SMEM_STACK, int LOGCOPIES, bool PTXCTL, int MINBLOCKS>
+__global__ void __launch_bounds__(kBdFindThreads, MINBLOCKS) k_bd_find_single(BdArgs a) {
+    __shared__ double2 s_logtab[128 * LOGCOPIES];
+    load_log_table_rep<LOGCOPIES>(s_logtab);
     __shared__ int s_next[kBdFindThreads / 32];
     __shared__ int s_best[kBdFindThreads / 32];
-    double st[kBdStack + 1];
+    __shared__ double s_st[SMEM_STACK ? kBdSmemStack + 1 : 1][SMEM_STACK ? kBdFindThreads : 1];
+    double st_hi[SMEM_STACK ? kBdStack - kBdSmemStack : kBdStack + 1];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const BdConsts C = bd_consts(a.P);
     const double tip = a.H.tip;
     const int min_leaves = a.P.min_leaves, max_leaves = a.P.max_leaves, max_attempts = a.P.max_attempts;
+    // 32-bit shared-window addresses computed once (generic pointers make the compiler rebuild the window base at every use)
+    const uint32_t a_next = (uint32_t)__cvta_generic_to_shared(&s_next[wib]), a_best = (uint32_t)__cvta_generic_to_shared(&s_best[wib]);
     volatile int* v_best = &s_best[wib];
-    st[0] = 0.0;
+    auto best_now = [&]() { return PTXCTL ? lds_volatile(a_best) : *v_best; };
+    double* const my_st = &s_st[0][SMEM_STACK ? threadIdx.x : 0];          // slot d at my_st[d * kBdFindThreads]
+    if (SMEM_STACK) my_st[0] = 0.0; else st_hi[0] = 0.0;
     for (;;) {
         long long r = 0;
         if (lane == 0) r = (long long)atomicAdd(a.work_counter, 1ULL);
@@ -133,7 +153,8 @@ __global__ void __launch_bounds__(kBdFindThreads, 4) k_bd_find_single(BdArgs a) 
         if (lane == 0) { s_next[wib] = 0; s_best[wib] = 0x7fffffff; }
         __syncwarp();
         // lane state: 0 = needs an attempt, 1 = running attempt my_a, 2 = idle (nothing left to claim)
-        int state = 0, my_a = -1, depth = 0; uint32_t vidx = 0; int sampled = 0; bool overflow = false, cut_short = false;
+        int state = 0, my_a = -1, depth = 0; uint32_t vidx = 0; int sampled = 0; bool cut_short = false;
+        int ovf_a = 0x7fffffff;          // smallest attempt index that outgrew the stack (it counts as rejected: the replicate is refused if it would have won)
         double cur = 0.0, tos = 0.0;
         int acc_a = 0x7fffffff, acc_n = 0, acc_sampled = 0;
         unsigned long long v_completed = 0, v_abandoned = 0; int n_completed = 0;
@@ -142,41 +163,56 @@ __global__ void __launch_bounds__(kBdFindThreads, 4) k_bd_find_single(BdArgs a) 
         // point below (no warp vote per vertex step).
         for (;;) {
             if (state == 0) {
-                const int na = atomicAdd(&s_next[wib], 1);
-                if (na > *v_best || na > max_attempts) break;
+                const int na = PTXCTL ? atoms_add(a_next, 1) : atomicAdd(&s_next[wib], 1);
+                if (na > best_now() || na > max_attempts) break;
                 my_a = na; state = 1; cur = tip; tos = 0.0; depth = 0; vidx = 0; sampled = 0;
                 w_next = philox4x32_10_rk(0u, (uint32_t)my_a, rep_lo, rep_hi, a.keys);
             }
-            if (my_a > *v_best) { cut_short = true; break; }      // a smaller index was accepted meanwhile
+            if (my_a > best_now()) { cut_short = true; break; }      // a smaller index was accepted meanwhile
             const U4 w = w_next;
             ++vidx;
             w_next = philox4x32_10_rk(vidx, (uint32_t)my_a, rep_lo, rep_hi, a.keys);   // next vertex's block: independent of this vertex's math
-            const BdVertex v = bd_vertex_single(C, cur, w, s_logtab);
+            const BdVertex v = bd_vertex_single<LOGCOPIES>(C, cur, w, s_logtab, lane & (LOGCOPIES - 1));
             const bool dup = v.event == EV_DUPLICATION;
             sampled += v.event == EV_LEAF ? 1 : 0;
             const bool ovf = dup && depth >= kBdStack;
-            if (dup && !ovf) st[depth + 1] = v.et;
             const int nd = dup ? depth + 1 : depth - 1;
-            const double refill = st[nd > 0 ? (nd <= kBdStack ? nd : 0) : 0];
+            double refill;
+            if constexpr (SMEM_STACK) {
+                const bool deep = nd > kBdSmemStack;                 // rare: the slot lives in the local-memory tail
+                if (dup && !ovf && !deep) my_st[nd * kBdFindThreads] = v.et;
+                refill = my_st[(deep || nd < 0 ? 0 : nd) * kBdFindThreads];
+                if (deep) {
+                    const int k = (nd <= kBdStack ? nd : kBdStack) - kBdSmemStack - 1;
+                    if (dup && !ovf) st_hi[k] = v.et;
+                    refill = st_hi[k];
+                }
+            } else {
+                if (dup && !ovf) st_hi[depth + 1] = v.et;
+                refill = st_hi[nd > 0 ? (nd <= kBdStack ? nd : 0) : 0];
+            }
             cur = dup ? v.et : tos;
             tos = dup ? v.et : refill;
             depth = nd;
             if (nd < 0 || sampled > max_leaves || ovf) {       // ran to completion, or can no longer be accepted
-                state = 0; overflow |= ovf;
+                state = 0;
+                if (ovf && my_a < ovf_a) ovf_a = my_a;
                 v_completed += vidx; ++n_completed;
                 const bool ok = !ovf && sampled >= min_leaves && sampled <= max_leaves && (exact == -1 || sampled == exact);
-                if (ok) { atomicMin(&s_best[wib], my_a); acc_a = my_a; acc_n = (int)vidx; acc_sampled = sampled; }
+                if (ok) { if (PTXCTL) atoms_min(a_best, my_a); else atomicMin(&s_best[wib], my_a); acc_a = my_a; acc_n = (int)vidx; acc_sampled = sampled; }
             }
         }
         if (cut_short) v_abandoned += vidx;
         __syncwarp();
-        const int best = *v_best;
+        const int best = best_now();
         for (int o = 16; o > 0; o >>= 1) {
             v_completed += __shfl_xor_sync(0xffffffffu, v_completed, o); v_abandoned += __shfl_xor_sync(0xffffffffu, v_abandoned, o);
             n_completed += __shfl_xor_sync(0xffffffffu, n_completed, o);
         }
-        const bool any_overflow = __any_sync(0xffffffffu, overflow);
-        if (best != 0x7fffffff) {
+        // An attempt deeper than the stack is treated as rejected. If its index is below the accepted one, the sequential retry
+        // loop of the reference might have accepted IT: refuse the replicate instead of returning a biased tree.
+        const int first_ovf = __reduce_min_sync(0xffffffffu, ovf_a);
+        if (best != 0x7fffffff && first_ovf > best) {
             if (acc_a == best) {
                 RepInfo inf; memset(&inf, 0, sizeof(inf));
                 inf.status = REP_OK; inf.exact = exact; inf.root = -1; inf.p_root = -1; inf.acc_attempt = (uint32_t)best; inf.n_pool = acc_n;
@@ -186,7 +222,7 @@ __global__ void __launch_bounds__(kBdFindThreads, 4) k_bd_find_single(BdArgs a) 
             }
         } else if (lane == 0) {
             RepInfo inf; memset(&inf, 0, sizeof(inf));
-            inf.status = any_overflow ? REP_STACK_OVERFLOW : REP_MAX_ATTEMPTS; inf.exact = exact; inf.root = -1; inf.p_root = -1;
+            inf.status = first_ovf != 0x7fffffff ? REP_STACK_OVERFLOW : REP_MAX_ATTEMPTS; inf.exact = exact; inf.root = -1; inf.p_root = -1;
             inf.attempts = max_attempts + 1; inf.vertices_sampled = v_completed; inf.vertices_abandoned = v_abandoned; inf.attempts_completed = n_completed;
             a.info[r] = inf;
         }

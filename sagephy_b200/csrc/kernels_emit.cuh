@@ -285,10 +285,12 @@ __global__ void __launch_bounds__(kInfoWarps * 32) k_emit_info(EmitArgs a) {
     if (ok) { CountSink c; if (pr) put_info_file<true>(c, a, inf, gid, long_head ? 2 : 0); else put_info_file<false>(c, a, inf, gid, long_head ? 2 : 0); body = (unsigned)c.n; }
     else if (note) body = 65;
     const unsigned long long total = (unsigned long long)body + (long_head ? head : 0u);
-    if (!WRITE) { if (active) a.sizes[(size_t)st * a.n + r] = total; return; }
-    char* dst = active ? a.out[st] + a.offsets[(size_t)st * (a.n + 1) + r] : nullptr;
+    if (!WRITE) { if (active) a.sizes[(size_t)st * a.stride + r] = total; return; }
+    const bool room = active && a.offsets[(size_t)st * a.stride + r + 1] <= a.cap[st];
+    if (active && !room) { *a.overflow = 1; body = 0; }
+    char* dst = room ? a.out[st] + a.offsets[(size_t)st * a.stride + r] : nullptr;
     if (long_head) {
-        unsigned todo = __ballot_sync(0xffffffffu, ok);
+        unsigned todo = __ballot_sync(0xffffffffu, ok && room);
         while (todo) {
             const int l = __ffs(todo) - 1; todo &= todo - 1;
             char* d = reinterpret_cast<char*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst), l));
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(kInfoWarps * 32) k_emit_info(EmitArgs a) {
             }
             if (lane == 0) d[o] = '\n';
         }
-        if (ok) dst += head;
+        if (ok && room) dst += head;
     }
     // bodies: rounds of as many lanes as fit the stage; slot of a lane = [off, off + mis + body), congruent to its destination mod 16
     const int mis = (int)(reinterpret_cast<unsigned long long>(dst) & 15ull);
@@ -372,7 +374,8 @@ __global__ void __launch_bounds__(kEmitWarps * 32, WRITE ? 8 : 10) k_emit(EmitAr
     auto no_store = [](int, unsigned) {};
     {
         constexpr int st = STREAM;
-        char* base = WRITE ? a.out[st] + a.offsets[(size_t)st * (a.n + 1) + r] : nullptr;
+        if (WRITE && a.offsets[(size_t)st * a.stride + r + 1] > a.cap[st]) { if (lane == 0) *a.overflow = 1; return; }
+        char* base = WRITE ? a.out[st] + a.offsets[(size_t)st * a.stride + r] : nullptr;
         uint16_t* plen = a.plen + (size_t)st * a.aux_stride + off;       // cached piece lengths of this stream
         auto ld = [&](int i) { return (unsigned)plen[i]; };
         auto sd = [&](int i, unsigned v) { plen[i] = (uint16_t)(v > 0xffffu ? 0xffffu : v); };
@@ -472,7 +475,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, WRITE ? 8 : 10) k_emit(EmitAr
                 else bytes = emit_pieces<false>(np, nullptr, stage, pc, no_load, sd);
             }
         }
-        if (!WRITE && lane == 0) a.sizes[(size_t)st * a.n + r] = bytes;
+        if (!WRITE && lane == 0) a.sizes[(size_t)st * a.stride + r] = bytes;
     }
 }
 

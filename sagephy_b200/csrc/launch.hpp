@@ -6,7 +6,7 @@
 namespace sgp {
 void launch_find_general(bool replay, bool domain, const FindArgs& a, int blocks, cudaStream_t st);
 void launch_build_general(bool replay, bool domain, const BuildArgs& a, int blocks, cudaStream_t st);
-void launch_bd_find(const BdArgs& a, int blocks, cudaStream_t st);
+void launch_bd_find(const BdArgs& a, int blocks, int blocks_per_sm, cudaStream_t st);      // blocks is sized for 4 per SM; fewer resident blocks leave room for a concurrent stream
 void launch_bd_build(const BdArgs& a, int blocks, cudaStream_t st);
 int launch_label_prune(LabelArgs a, int max_pool, int sm_count, cudaStream_t st);          // returns the number of kernels launched
 int launch_emit(bool write, const EmitArgs& a, unsigned blocks, cudaStream_t st);   // returns the number of kernels launched

@@ -349,3 +349,28 @@ def test_iidrk11_replay_and_distribution(ctx, tmp_path):
     for x in range(0, nv, max(1, nv // 5)):
         if ref[:, x].std() > 0:
             assert ks_ok(rel[:, x], ref[:, x]), x
+
+
+# ---- sub-batch pipeline (find of sub-batch k+1 on a second stream next to build / label / emit of k) ------------------------------------
+def test_pipelined_run_equals_serial_run(ctx, monkeypatch):
+    args = ["-s", "77", "-min", "6", "-max", "14", "-p", "0.8", "1.0", "2.5", "0.3", "x"]
+    n = 300000                                   # three sub-batches of 131072
+    piped = ctx.run("HostTreeGen", args, n=n, rng=sg.RNG_PHILOX, offset=5)
+    assert piped.timings()["sub_batches"] == 3
+    serial = ctx.run("HostTreeGen", args, n=n, rng=sg.RNG_PHILOX, offset=5, flags=sg.FLAG_SERIAL)
+    assert serial.timings()["sub_batches"] == 1
+    assert (piped.rep_status == 0).all()
+    for s in range(4):
+        assert piped.stream_bytes(s) == serial.stream_bytes(s) and piped.stream_bytes(s) > 0
+        assert (piped.offsets(s) == serial.offsets(s)).all()
+        assert piped.stream(s) == serial.stream(s), s
+    assert (piped.summary().as_vector() == serial.summary().as_vector()).all()
+    assert (piped.attempts == serial.attempts).all()
+    piped.free()
+    # an output estimate that turns out too small (forced here) falls back to the unpipelined path: same bytes again
+    monkeypatch.setenv("SGP_OUTPUT_MARGIN", "0.6")
+    again = ctx.run("HostTreeGen", args, n=n, rng=sg.RNG_PHILOX, offset=5)
+    monkeypatch.delenv("SGP_OUTPUT_MARGIN")
+    assert again.timings()["sub_batches"] == 1
+    for s in range(4):
+        assert again.stream(s) == serial.stream(s), s
