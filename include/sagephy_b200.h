@@ -79,10 +79,14 @@ typedef struct {
 /* Tree generators only: keep the vertex records of the accepted trees on the device so that the batch can feed
  * sgp_relax_run_on_batch without a host round trip (costs ~100 bytes of HBM per vertex until the batch is freed). */
 #define SGP_FLAG_KEEP_TREES 2
-/* Tree generators only: do not pipeline sub-batches (large HostTreeGen batches in Philox mode otherwise run the sampler of sub-batch
- * k+1 on a second stream next to build / label / emit of sub-batch k). Same bytes either way; the per-phase times of sgp_timings are
- * only clean (no overlap) with this flag. */
+/* Tree generators only: one sub-batch, all phases in order on one stream. This is the default since the pipelined mode measured
+ * slower on a B200 (see SGP_FLAG_PIPELINE); the flag is kept so that callers which set it keep working. */
 #define SGP_FLAG_SERIAL 4
+/* Tree generators only (large HostTreeGen batches in Philox mode): run the sampler of sub-batch k+1 on a second stream next to
+ * build / label / emit of sub-batch k. Same bytes as the serial run; the per-phase times of sgp_timings then overlap. Opt-in:
+ * on a B200 the persistent sampler and the latency-bound kernels slow each other down more than the overlap gains
+ * (10^6 C2 replicates: 481 ms pipelined against 401 ms serial). */
+#define SGP_FLAG_PIPELINE 8
 
 /* summary counters of a batch (merged across GPUs with an allreduce(sum) by the caller) */
 #define SGP_HIST_LEAF_BINS 1025

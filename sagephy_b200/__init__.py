@@ -26,6 +26,7 @@ RNG_PHILOX, RNG_MT_REPLAY = 0, 1
 FLAG_MULTI_TREE_INPUT = 1
 FLAG_KEEP_TREES = 2
 FLAG_SERIAL = 4
+FLAG_PIPELINE = 8
 LAYOUT_PACKED, LAYOUT_PER_REPLICATE = 0, 1
 STREAM_UNPRUNED_TREE, STREAM_PRUNED_TREE = 0, 1
 STATUS_OK, STATUS_USAGE = 0, 6

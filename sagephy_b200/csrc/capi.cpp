@@ -59,7 +59,7 @@ sgp_status sgp_app_run(sgp_context* ctx, const char* app, int argc, const char* 
         if (o.rng_mode == SGP_RNG_MT_REPLAY && !cfg.has_seed) {
             // the reference would seed from /dev/random; replay of an unknown seed is meaningless but harmless
         }
-        BatchOpts bo; bo.n = o.n_replicates; bo.offset = o.replicate_offset; bo.rng_mode = o.rng_mode; bo.stream_mask = o.stream_mask; bo.keep_on_device = o.keep_on_device != 0; bo.keep_trees = (o.flags & SGP_FLAG_KEEP_TREES) != 0; bo.serial = (o.flags & SGP_FLAG_SERIAL) != 0;
+        BatchOpts bo; bo.n = o.n_replicates; bo.offset = o.replicate_offset; bo.rng_mode = o.rng_mode; bo.stream_mask = o.stream_mask; bo.keep_on_device = o.keep_on_device != 0; bo.keep_trees = (o.flags & SGP_FLAG_KEEP_TREES) != 0; bo.serial = (o.flags & SGP_FLAG_SERIAL) != 0; bo.pipeline = (o.flags & SGP_FLAG_PIPELINE) != 0;
         ctx->ctx->run_treegen(cfg, bo, b->b);
         *out = b;
         return SGP_OK;

@@ -38,6 +38,37 @@ struct __align__(16) Node {
 };
 static_assert(sizeof(Node) == 80, "Node layout");
 
+// ---- emission records -------------------------------------------------------------------------------------------------------------
+// The label kernel, which holds a whole tree in shared memory, leaves one compact record per output PIECE in the order the piece is
+// written, so that the write kernels read their input sequentially (coalesced, each byte once) instead of gathering 80-byte vertex
+// records through an order array once per stream and pass. A record carries everything the piece prints, the shortest-decimal
+// digits of its floating-point field (computed once) and the piece's length in bytes.
+constexpr int kNoDigits = 0x7fff;      // TreeRec::e / RowRec::e: f holds the raw bits of the double (0.0, NaN, infinities, negatives)
+enum TreeRecFlags : uint8_t { TR_LEAF = 1, TR_COMMA = 2, TR_ROOT = 4, TR_J_SHIFT = 3 /* bits 3-4: second DISCPT index */ };
+// One Newick piece ['(' x chain | ')'] name ':' length [tag] [','] [tree tag ';' '\n'], post-order of its view.
+struct __align__(16) TreeRec {
+    uint64_t f;            // branch length = f x 10^e (shortest decimal), or raw bits if e == kNoDigits
+    int32_t number, sigma, epoch;
+    int16_t e, chain;
+    uint8_t event, flags;
+    uint16_t len;          // bytes of the piece (0xffff: longer, measured again by the writer)
+    int16_t gtree, pad;
+};
+static_assert(sizeof(TreeRec) == 32, "TreeRec layout");
+// Transfer vertices only (GuestTreeGen / DomainTreeGen): same index as the TreeRec, touched for transfer events alone.
+struct __align__(16) TreeRecX { int32_t from_arc, to_arc; int16_t from_g, to_g; int32_t pad; };
+static_assert(sizeof(TreeRecX) == 16, "TreeRecX layout");
+enum RowRecFlags : uint8_t { RR_LEAFMAP = 1 };
+// One .guest2host row (and the .leafmap row of the same vertex, if it has one), breadth-first order of its view.
+struct __align__(16) RowRec {
+    uint64_t f;            // vertex time = f x 10^e, or raw bits if e == kNoDigits
+    int32_t number, sigma, epoch;
+    int16_t e, gtree;
+    uint8_t event, flags;
+    uint16_t len_g2h, len_lm, pad;
+};
+static_assert(sizeof(RowRec) == 32, "RowRec layout");
+
 // Per-replicate record produced by find/build/label and consumed by emit + the summary histograms.
 struct RepInfo {
     int32_t status;          // sgp_rep_status
@@ -49,7 +80,7 @@ struct RepInfo {
     int32_t n_u, n_p;        // vertices in the unpruned / pruned tree
     int32_t sampled_leaves;
     int32_t exact;           // -sizes draw (-1: none)
-    int32_t pad;
+    int16_t root_gtree_u, root_gtree_p;   // host tree index of the root vertex of the unpruned / pruned view (.guest2host header, DomainTreeGen)
     double total_u, beneath_u, total_p, beneath_p;
     double p_root_time;      // time of the pruned tree's root (0 if the pruned tree is empty)
     int32_t cnt_u[EV_COUNT];

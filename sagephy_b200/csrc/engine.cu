@@ -420,21 +420,23 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     const int sm = impl->sm_count;
 
     // ---- sub-batches ----------------------------------------------------------------------------------------------------------
-    // A run is cut into sub-batches of replicates. With one sub-batch everything runs on the context's stream in the order find ->
+    // A run can be cut into sub-batches of replicates. With one sub-batch (the default) everything runs on the context's stream in the order find ->
     // build -> label -> emit. With several (HostTreeGen in Philox mode: the find kernel is issue-bound, build / label / emit are
     // latency-bound) the find kernel of sub-batch k+1 runs on stream A while sub-batch k is built, labelled and emitted on stream B:
     // the two share the SMs (the find kernel then keeps 3 instead of 4 blocks per SM resident). Stream offsets carry over from one
     // sub-batch to the next, so the output is the same contiguous, index-ordered byte stream either way.
-    const bool no_pipe_env = getenv("SGP_NO_PIPELINE") != nullptr;
+    // Opt-in (SGP_FLAG_PIPELINE or SGP_PIPELINE=1): measured on a B200 the two streams slow each other down (481 ms against 401 ms
+    // per 10^6 C2 replicates), so the default is one sub-batch.
+    const bool want_pipe = opts.pipeline || getenv("SGP_PIPELINE") != nullptr;
     long long sub_n = n;
-    if (fast_bd && !opts.keep_trees && !opts.serial && !no_pipe_env && n >= 2 * kSubBatch) sub_n = kSubBatch;
+    if (fast_bd && want_pipe && !opts.keep_trees && !opts.serial && n >= 2 * kSubBatch) sub_n = kSubBatch;
     const int K = (int)((n + sub_n - 1) / sub_n);
     const bool piped = K > 1;
     cudaStream_t stA = st, stB = piped ? impl->stream2 : st;
     struct Sub {
         long long r0 = 0, n = 0, total_nodes = 0, aux_stride = 1; int max_pool = 0;
         DevBuf<unsigned long long> counter; DevBuf<long long> pool, node_off; DevBuf<int> max_pool_d;
-        DevBuf<Node> nodes; DevBuf<int32_t> aux; DevBuf<uint16_t> plen; DevBuf<unsigned long long> dig_f; DevBuf<int16_t> dig_e;
+        DevBuf<Node> nodes; DevBuf<int32_t> aux; DevBuf<TreeRec> trec; DevBuf<TreeRecX> trecx; DevBuf<RowRec> rows;
         cudaEvent_t ev_found = nullptr;
         ~Sub() { if (ev_found) cudaEventDestroy(ev_found); }
     };
@@ -601,7 +603,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     // ---- build -> label -> emit of one sub-batch (stream B) ---------------------------------------------------------------------
     auto emit_args_for = [&](Sub& S) {
         EmitArgs a = e; a.n = S.n; a.rep_base = opts.offset + S.r0; a.info = info.p + S.r0; a.node_off = S.node_off.p; a.nodes = S.nodes.p; a.aux = S.aux.p; a.aux_stride = S.aux_stride;
-        a.plen = S.plen.p; a.dig_f = S.dig_f.p; a.dig_e = S.dig_e.p; a.sizes = sizes.p + S.r0; a.offsets = offsets.p + S.r0;
+        a.trec = S.trec.p; a.trecx = S.trecx.p; a.rows = S.rows.p; a.sizes = sizes.p + S.r0; a.offsets = offsets.p + S.r0;
         for (int q = 0; q < ST_COUNT; ++q) { a.out[q] = out.d_stream[q]; a.cap[q] = out_cap[q]; }
         return a;
     };
@@ -611,8 +613,13 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         if (piped) CK(cudaStreamWaitEvent(stB, S.ev_found, 0));
         g_alloc_stream = stB;
         S.aux_stride = std::max<long long>(S.total_nodes, 1);
-        S.nodes.alloc((size_t)S.aux_stride); S.aux.alloc((size_t)S.aux_stride * 4);
-        S.plen.alloc((size_t)ST_COUNT * S.aux_stride); S.dig_f.alloc((size_t)2 * S.aux_stride); S.dig_e.alloc((size_t)2 * S.aux_stride);
+        // the order arrays and the labelled vertex records are only kept for chained stages and for trees too large for the
+        // shared-memory label kernel; everything else leaves the label kernel as emission records
+        const bool keep_nodes = opts.keep_trees || S.max_pool > label_warp_max_pool();
+        const bool want_rows = (mask & 0xF0u) != 0, want_trees = (mask & 0x3u) != 0;
+        S.nodes.alloc((size_t)S.aux_stride); if (keep_nodes || !fast_bd) S.aux.alloc((size_t)S.aux_stride * 4);      // (the general build kernel uses them as scratch)
+        if (want_trees) { S.trec.alloc((size_t)2 * S.aux_stride); if (cfg.app != 0) S.trecx.alloc((size_t)2 * S.aux_stride); }
+        if (want_rows) S.rows.alloc((size_t)2 * S.aux_stride);
         g_alloc_stream = stA;
         size_t sp = span_begin(&tm.build_ms, stB);
         if (fast_bd) {
@@ -650,14 +657,14 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             LabelArgs a{}; a.n = S.n; a.info = info.p + S.r0; a.node_off = S.node_off.p; a.nodes = S.nodes.p; a.aux = S.aux.p; a.aux_stride = S.aux_stride; a.T = impl->T;
             a.host_root_time = cfg.host.vtime[cfg.host.root]; a.has_stem_override = cfg.has_stem_override; a.stem_override = cfg.stem_override;
             a.pool = S.pool.p;
+            a.write_nodes = keep_nodes ? 1 : 0; a.E = emit_args_for(S);
             tm.launches += launch_label_prune(a, S.max_pool, impl->sm_count, stB);
             CK(cudaGetLastError());
         }
         span_end(sp, stB);
         sp = span_begin(&tm.emit_size_ms, stB);
-        const unsigned emit_blocks = (unsigned)((S.n * 32 + 127) / 128);
         EmitArgs ea = emit_args_for(S);
-        tm.launches += launch_emit(false, ea, emit_blocks, stB);
+        tm.launches += launch_emit_sizes(ea, stB);
         CK(cudaGetLastError());
         k_scan_streams<<<ST_COUNT, 1024, 0, stB>>>(sizes.p + S.r0, offsets.p + S.r0, stride, S.n, carry.p); ++tm.launches;
         span_end(sp, stB);
@@ -682,12 +689,12 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             ea = emit_args_for(S);
         }
         sp = span_begin(&tm.emit_write_ms, stB);
-        tm.launches += launch_emit(true, ea, emit_blocks, stB);
+        tm.launches += launch_emit_write(ea, stB);
         CK(cudaGetLastError());
         span_end(sp, stB);
         if (piped) {        // the vertex records of this sub-batch are not needed any more: hand them back in stream order
             g_alloc_stream = stB;
-            S.nodes.alloc(0); S.aux.alloc(0); S.plen.alloc(0); S.dig_f.alloc(0); S.dig_e.alloc(0);
+            S.nodes.alloc(0); S.aux.alloc(0); S.trec.alloc(0); S.trecx.alloc(0); S.rows.alloc(0);
             g_alloc_stream = stA;
         }
     };

@@ -66,7 +66,8 @@ struct BatchOpts {
     bool keep_on_device = false;
     bool multi_tree_input = false;
     bool keep_trees = false;  // tree generators: leave the vertex records on the device for a chained stage
-    bool serial = false;      // no sub-batch pipeline (clean per-phase timings; also the fallback when an output estimate was too small)
+    bool serial = false;      // never pipeline (also the fallback when an output estimate of a pipelined run was too small)
+    bool pipeline = false;    // opt-in: sampler of sub-batch k+1 on a second stream next to build / label / emit of sub-batch k
 };
 
 struct Timings { double find_ms = 0, build_ms = 0, label_ms = 0, emit_size_ms = 0, emit_write_ms = 0, d2h_ms = 0, total_ms = 0; long long launches = 0, h2d_bytes = 0; int sub_batches = 1; };

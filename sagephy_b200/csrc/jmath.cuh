@@ -282,16 +282,18 @@ SGP_HD void d2s_decimal(const MathTables& T, double v, uint64_t* f_out, int* e_o
     *f_out = f; *e_out = e;
 }
 
+SGP_HD int dec_len_u32(uint32_t v) {
+    return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
+}
+// (comparisons only: a division of a 64-bit value by a constant costs a dozen instructions on the device)
 SGP_HD int dec_len_u64(uint64_t f) {
-    int n = 1;
-    if (f >= 10000000000000000ull) { n += 16; f /= 10000000000000000ull; }
-    if (f >= 100000000ull) { n += 8; f /= 100000000ull; }
-    if (f >= 10000ull) { n += 4; f /= 10000ull; }
-    if (f >= 100ull) { n += 2; f /= 100ull; }
-    if (f >= 10ull) { n += 1; }
+    if (f <= 0xffffffffull) return dec_len_u32((uint32_t)f);
+    int n = 10;
+    uint64_t p = 10000000000ull;
+    while (n < 20 && f >= p) { ++n; p *= 10; }
     return n;
 }
-SGP_HD int dec_len_i32(int v) { int n = 0; uint32_t u; if (v < 0) { n = 1; u = (uint32_t)(-(int64_t)v); } else u = (uint32_t)v; return n + dec_len_u64(u); }
+SGP_HD int dec_len_i32(int v) { int n = 0; uint32_t u; if (v < 0) { n = 1; u = (uint32_t)(-(int64_t)v); } else u = (uint32_t)v; return n + dec_len_u32(u); }
 
 // Byte sinks: the same formatting code runs in the "size" pass (CountSink) and the "write" pass (MemSink).
 struct CountSink {
@@ -334,9 +336,6 @@ template <class Sink, int N> SGP_HD void put_lit(Sink& s, const char (&z)[N]) {
 #pragma unroll
     for (int i = 0; i < N - 1; ++i) s.put(z[i]);
 }
-SGP_HD int dec_len_u32(uint32_t v) {
-    return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
-}
 // n decimal digits of v (v < 10^n, n <= 10), most significant first, 32-bit arithmetic only
 template <class Sink> SGP_HD void put_u32_digits(Sink& s, uint32_t v, int n) {
     if (Sink::kRandomAccess) {
@@ -353,60 +352,64 @@ template <class Sink> SGP_HD void put_u32(Sink& s, uint32_t v) {
     if (Sink::kCounts) { s.skip(n); return; }
     put_u32_digits(s, v, n);
 }
+// values beyond 32 bits are rare (wide seeds): out of line, so that the common path stays small
+template <class Sink> SGP_HD_NOINL void put_u64_wide(Sink& s, uint64_t v) {
+    char tmp[20]; int n = 0;
+    while (v) { const uint64_t q = v / 10; tmp[n++] = (char)('0' + (int)(v - q * 10)); v = q; }
+    while (n) s.put(tmp[--n]);
+}
 template <class Sink> SGP_HD void put_u64(Sink& s, uint64_t v) {
-    if (v <= 0xffffffffull) { put_u32(s, (uint32_t)v); return; }
-    const int n = dec_len_u64(v);
-    if (Sink::kCounts) { s.skip(n); return; }
-    const uint64_t hi = v / 1000000000ull; const uint32_t lo = (uint32_t)(v - hi * 1000000000ull);
-    put_u64(s, hi); put_u32_digits(s, lo, 9);
+    if (v <= 0xffffffffull) put_u32(s, (uint32_t)v); else put_u64_wide(s, v);
+}
+template <class Sink> SGP_HD void put_i32(Sink& s, int v) {
+    if (v < 0) { s.put('-'); put_u32(s, (uint32_t)(-(int64_t)v)); } else put_u32(s, (uint32_t)v);
 }
 template <class Sink> SGP_HD void put_i64(Sink& s, long long v) {
+    if (v >= 0 && v <= 0xffffffffll) { put_u32(s, (uint32_t)v); return; }
     if (v < 0) { s.put('-'); put_u64(s, (uint64_t)(-(v + 1)) + 1ull); } else put_u64(s, (uint64_t)v);
 }
-// digits of f (n digits in total), positions [from, to) counted from the most significant digit
-template <class Sink> SGP_HD void put_digits(Sink& s, uint64_t f, int n, int from, int to) {
-    if (Sink::kCounts) { s.skip(to - from); return; }
-    // split into <= 9-digit limbs so that the digit loop runs in 32-bit arithmetic
-    const uint64_t hi = f / 1000000000ull; uint32_t l0 = (uint32_t)(f - hi * 1000000000ull);
-    uint32_t l1 = (uint32_t)(hi % 1000000000ull);
-    if (Sink::kRandomAccess) {
-        // digit at position pos (0 = most significant) goes to d[pos - from] when from <= pos < to
-        auto d = s.reserve(to - from);
-        int pos = n - 1;
-        for (int i = 0; i < 9 && pos >= from; ++i, --pos) { uint32_t q = l0 / 10u; if (pos < to) d[pos - from] = (char)('0' + (l0 - q * 10u)); l0 = q; }
-        if (n > 9) { pos = n - 10; for (int i = 0; i < 9 && pos >= from; ++i, --pos) { uint32_t q = l1 / 10u; if (pos < to) d[pos - from] = (char)('0' + (l1 - q * 10u)); l1 = q; } }
-        return;
-    }
-    char tmp[20];
-    int pos = n - 1;
-    for (int i = 0; i < 9 && pos >= 0; ++i, --pos) { uint32_t q = l0 / 10u; tmp[pos] = (char)('0' + (l0 - q * 10u)); l0 = q; }
-    for (int i = 0; i < 9 && pos >= 0; ++i, --pos) { uint32_t q = l1 / 10u; tmp[pos] = (char)('0' + (l1 - q * 10u)); l1 = q; }
-    for (; pos >= 0; --pos) tmp[pos] = '0';
-    for (int i = from; i < to; ++i) s.put(tmp[i]);
-}
 
-// Layout part of java.lang.Double.toString for a finite v > 0 whose shortest decimal is f x 10^e.
+// Layout part of java.lang.Double.toString for a finite v > 0 whose shortest decimal is f x 10^e (f < 10^18): plain notation
+// for 1e-3 <= v < 1e7, computerized scientific notation otherwise. One pass over the digits: digit i (0 = most significant)
+// lands at window position lead + i + (i >= split), everything else ('0', '.', padding zeros, exponent) is placed around them.
 template <class Sink> SGP_HD void put_double_digits(Sink& s, double v, uint64_t f, int e) {
-    const int n = dec_len_u64(f);
+    const uint64_t hi64 = f / 1000000000ull;
+    uint32_t l0 = (uint32_t)(f - hi64 * 1000000000ull);                  // low 9 digits
+    uint32_t l1 = hi64 < 1000000000ull ? (uint32_t)hi64 : (uint32_t)(hi64 % 1000000000ull);
+    const int n = hi64 ? 9 + dec_len_u32(l1) : dec_len_u32(l0);
     const int pe = n + e;          // v = 0.DIGITS x 10^pe
-    if (v >= 1e-3 && v < 1e7) {
-        if (pe <= 0) {
-            s.put('0'); s.put('.');
-            for (int i = 0; i < -pe; ++i) s.put('0');
-            put_digits(s, f, n, 0, n);
-        } else if (pe >= n) {
-            put_digits(s, f, n, 0, n);
-            for (int i = n; i < pe; ++i) s.put('0');
-            s.put('.'); s.put('0');
-        } else {
-            put_digits(s, f, n, 0, pe); s.put('.'); put_digits(s, f, n, pe, n);
-        }
+    const bool plain = v >= 1e-3 && v < 1e7;
+    int lead, split, total, exp10 = 0;
+    if (plain) {
+        if (pe <= 0) { lead = 2 - pe; split = 99; total = lead + n; }        // 0.000DIGITS
+        else if (pe >= n) { lead = 0; split = 99; total = pe + 2; }          // DIGITS000.0
+        else { lead = 0; split = pe; total = n + 1; }                        // DIG.ITS
     } else {
-        put_digits(s, f, n, 0, 1); s.put('.');
-        if (n == 1) s.put('0'); else put_digits(s, f, n, 1, n);
-        s.put('E');
-        put_i64(s, (long long)(pe - 1));
+        exp10 = pe - 1;
+        lead = 0; split = 1; total = (n == 1 ? 3 : n + 1) + 1 + dec_len_i32(exp10);      // D.IGITSE-x
     }
+    if (Sink::kCounts) { s.skip(total); return; }
+    auto put_all = [&](auto& w) {
+        int pos = n - 1;
+        for (int i = 0; i < 9 && pos >= 0; ++i, --pos) { const uint32_t q = l0 / 10u; w[lead + pos + (pos >= split ? 1 : 0)] = (char)('0' + (l0 - q * 10u)); l0 = q; }
+        for (; pos >= 0; --pos) { const uint32_t q = l1 / 10u; w[lead + pos + (pos >= split ? 1 : 0)] = (char)('0' + (l1 - q * 10u)); l1 = q; }
+        if (plain) {
+            if (pe <= 0) { w[0] = '0'; w[1] = '.'; for (int z = 2; z < lead; ++z) w[z] = '0'; }
+            else if (pe >= n) { for (int z = n; z < pe; ++z) w[z] = '0'; w[pe] = '.'; w[pe + 1] = '0'; }
+            else w[pe] = '.';
+        } else {
+            w[1] = '.';
+            int p = n + 1;
+            if (n == 1) { w[2] = '0'; p = 3; }
+            w[p++] = 'E';
+            uint32_t u = (uint32_t)exp10;
+            if (exp10 < 0) { w[p++] = '-'; u = (uint32_t)(-exp10); }
+            const int m = dec_len_u32(u);
+            for (int i = m - 1; i >= 0; --i) { const uint32_t q = u / 10u; w[p + i] = (char)('0' + (u - q * 10u)); u = q; }
+        }
+    };
+    if (Sink::kRandomAccess) { auto w = s.reserve(total); put_all(w); }
+    else { char tmp[32]; char* w = tmp; put_all(w); for (int i = 0; i < total; ++i) s.put(tmp[i]); }
 }
 
 // java.lang.Double.toString

@@ -1,18 +1,30 @@
 #include "kernels_emit.cuh"
 #include "launch.hpp"
+#include <cstdlib>
 namespace sgp {
-template <bool W, int S> static void launch_one(const EmitArgs& a, unsigned blocks, cudaStream_t st) { k_emit<W, S><<<blocks, kEmitWarps * 32, 0, st>>>(a); }
-template <bool W> static int launch_all(const EmitArgs& a, unsigned blocks, cudaStream_t st) {
+// size pass: finishes the records the label kernel left (tree and row streams) and measures the .info files
+int launch_emit_sizes(const EmitArgs& a, cudaStream_t st) {
     int n = 0;
-    if (a.stream_mask & (1u << 0)) { launch_one<W, 0>(a, blocks, st); ++n; }
-    if (a.stream_mask & (1u << 1)) { launch_one<W, 1>(a, blocks, st); ++n; }
-    // both .info files in one launch: a thread per (replicate, file)
-    if (a.stream_mask & 0xCu) { k_emit_info<W><<<(unsigned)((2 * a.n + kInfoWarps * 32 - 1) / (kInfoWarps * 32)), kInfoWarps * 32, 0, st>>>(a); ++n; }
-    if (a.stream_mask & (1u << 4)) { launch_one<W, 4>(a, blocks, st); ++n; }
-    if (a.stream_mask & (1u << 5)) { launch_one<W, 5>(a, blocks, st); ++n; }
-    if (a.stream_mask & (1u << 6)) { launch_one<W, 6>(a, blocks, st); ++n; }
-    if (a.stream_mask & (1u << 7)) { launch_one<W, 7>(a, blocks, st); ++n; }
+    if (a.stream_mask & 0xF3u) { k_finish_records<0><<<(unsigned)((a.n * 32 + 255) / 256), 256, 0, st>>>(a); ++n; }
+    if (a.stream_mask & 0xCu) { k_emit_info<false><<<(unsigned)((2 * a.n + kInfoWarps * 32 - 1) / (kInfoWarps * 32)), kInfoWarps * 32, 0, st>>>(a); ++n; }
     return n;
 }
-int launch_emit(bool write, const EmitArgs& a, unsigned blocks, cudaStream_t st) { return write ? launch_all<true>(a, blocks, st) : launch_all<false>(a, blocks, st); }
+template <bool BULK> static int launch_write(const EmitArgs& a, cudaStream_t st) {
+    const unsigned blocks = (unsigned)((a.n * 32 + kEmitWarps * 32 - 1) / (kEmitWarps * 32)), threads = kEmitWarps * 32;
+    int n = 0;
+    if (a.stream_mask & (1u << ST_UNPRUNED_TREE)) { k_write_tree<0, BULK><<<blocks, threads, 0, st>>>(a); ++n; }
+    if (a.stream_mask & (1u << ST_PRUNED_TREE)) { k_write_tree<1, BULK><<<blocks, threads, 0, st>>>(a); ++n; }
+    // both .info files in one launch: a thread per (replicate, file)
+    if (a.stream_mask & 0xCu) { k_emit_info<true><<<(unsigned)((2 * a.n + kInfoWarps * 32 - 1) / (kInfoWarps * 32)), kInfoWarps * 32, 0, st>>>(a); ++n; }
+    if (a.stream_mask & (1u << ST_UNPRUNED_G2H)) { k_write_rows<0, 0, BULK><<<blocks, threads, 0, st>>>(a); ++n; }
+    if (a.stream_mask & (1u << ST_PRUNED_G2H)) { k_write_rows<0, 1, BULK><<<blocks, threads, 0, st>>>(a); ++n; }
+    if (a.stream_mask & (1u << ST_UNPRUNED_LEAFMAP)) { k_write_rows<1, 0, BULK><<<blocks, threads, 0, st>>>(a); ++n; }
+    if (a.stream_mask & (1u << ST_PRUNED_LEAFMAP)) { k_write_rows<1, 1, BULK><<<blocks, threads, 0, st>>>(a); ++n; }
+    return n;
+}
+int launch_emit_write(const EmitArgs& a, cudaStream_t st) {
+    // SGP_EMIT_FLUSH=lsu: plain 16-byte stores instead of the bulk (TMA) copy, for A/B measurements
+    static const bool lsu = [] { const char* e = std::getenv("SGP_EMIT_FLUSH"); return e && e[0] == 'l'; }();
+    return lsu ? launch_write<false>(a, st) : launch_write<true>(a, st);
+}
 }  // namespace sgp

@@ -17,7 +17,8 @@ int launch_label_prune(LabelArgs a, int max_pool, int sm_count, cudaStream_t st)
     for (int cap : caps) {
         if (thread_only) break;
         a.min_pool = lo; a.cap = cap;
-        const size_t smem = (size_t)cap * kLabelBytesPerNode + kLabelExtraBytes;
+        const size_t smem = label_smem_bytes(cap);
+        if (smem + 2048 > (size_t)kMaxSmem) break;
         const int per_sm = (int)std::min<size_t>(32, (size_t)kMaxSmem / (smem + 1536));     // + static shared memory and the per-block reservation
         const long long want = (a.n + 31) / 32;
         const int blocks = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count * per_sm));
@@ -25,7 +26,12 @@ int launch_label_prune(LabelArgs a, int max_pool, int sm_count, cudaStream_t st)
         lo = cap;
         if (cap >= max_pool) break;
     }
-    if (max_pool > lo) { a.cap = lo; k_label_prune<<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(a); ++launches; }
+    if (max_pool > lo) {
+        if (!a.aux || !a.write_nodes) throw SgpError("internal: oversized trees need the order arrays");
+        a.cap = lo; k_label_prune<<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(a); ++launches;
+        k_records_from_nodes<<<(unsigned)((a.n * 32 + 127) / 128), 128, 0, st>>>(a); ++launches;
+    }
     return launches;
 }
+int label_warp_max_pool() { return getenv("SGP_LABEL_THREAD_KERNEL") ? 0 : 2340; }
 }  // namespace sgp

@@ -72,19 +72,6 @@ struct BdArgs {
     const long long* node_off; Node* nodes;
 };
 
-struct LabelArgs {
-    long long n;
-    RepInfo* info;
-    const long long* node_off;
-    Node* nodes;
-    int32_t* aux; long long aux_stride;     // ordU, ordP, bfsU, bfsP
-    MathTables T;
-    double host_root_time;                  // hostTree.getVertexTime(root)
-    int has_stem_override; double stem_override;    // HostTreeGen -stem (HostTreeGen.java:74-79)
-    const long long* pool;                  // vertices per replicate (0: failed)
-    int min_pool, cap;                      // warp kernel: size class (min_pool, cap]; thread kernel: trees above cap
-};
-
 enum Stream : int { ST_UNPRUNED_TREE = 0, ST_PRUNED_TREE = 1, ST_UNPRUNED_INFO = 2, ST_PRUNED_INFO = 3,
                     ST_UNPRUNED_G2H = 4, ST_PRUNED_G2H = 5, ST_UNPRUNED_LEAFMAP = 6, ST_PRUNED_LEAFMAP = 7, ST_COUNT = 8 };
 
@@ -110,9 +97,10 @@ struct EmitArgs {
     const int32_t* g2h_gene_off;
     const double* ep_times;        // 3 doubles per epoch [lo, mid, up] (DISCPT index)
     const double* gene_ep_times; const int32_t* gene_ep_base;     // DomainTreeGen: epochs of gene tree g start at gene_ep_base[g]
-    uint16_t* plen;                // [ST_COUNT][aux_stride] cached piece lengths (size pass -> write pass)
-    unsigned long long* dig_f;     // [2][aux_stride] cached shortest-decimal digits of branch lengths (unpruned, pruned)
-    int16_t* dig_e;                // [2][aux_stride] ... and their decimal exponents
+    // emission records written by the label kernel (device_types.cuh), [2 views][aux_stride], replicate r at node_off[r]
+    TreeRec* trec;                 // Newick pieces, post-order of the view
+    TreeRecX* trecx;               // transfer endpoints, same index (GuestTreeGen / DomainTreeGen; nullptr for HostTreeGen)
+    RowRec* rows;                  // .guest2host / .leafmap rows, breadth-first order of the view (nullptr if neither stream is wanted)
     // sizes / offsets are laid out [ST_COUNT][stride] over ALL replicates of the run; a launch covers the `n` replicates that
     // start at the position these pointers already point to (sub-batches of a pipelined run)
     long long stride;
@@ -121,6 +109,21 @@ struct EmitArgs {
     char* out[ST_COUNT];
     unsigned long long cap[ST_COUNT];    // bytes allocated per stream: a replicate that would end beyond it is not written ...
     int* overflow;                       // ... and raises this flag (the engine then grows the buffers and writes again)
+};
+
+struct LabelArgs {
+    long long n;
+    RepInfo* info;
+    const long long* node_off;
+    Node* nodes;
+    int32_t* aux; long long aux_stride;     // ordU, ordP, bfsU, bfsP (nullptr: not kept)
+    MathTables T;
+    double host_root_time;                  // hostTree.getVertexTime(root)
+    int has_stem_override; double stem_override;    // HostTreeGen -stem (HostTreeGen.java:74-79)
+    const long long* pool;                  // vertices per replicate (0: failed)
+    int min_pool, cap;                      // warp kernel: size class (min_pool, cap]; thread kernel: trees above cap
+    int write_nodes;                        // write the labelled vertex records and the order arrays back (chained stages, oversized trees)
+    EmitArgs E;                             // formats and the record arrays the kernel fills in
 };
 
 }  // namespace sgp

@@ -1,94 +1,24 @@
-// K4: text emission. One warp per replicate; every output file ("stream") of a replicate is a concatenation of
-// independent pieces whose byte offsets are an exclusive prefix sum of their lengths:
+// K4: text emission. Every output file ("stream") of a replicate is a concatenation of independent pieces whose byte
+// offsets are an exclusive prefix sum of their lengths:
 //   *.tree       one piece per vertex in post-order:  ['(' x run | ')'] name ':' length [tag] [','] [tree tag ';' '\n']
 //   *.info       one piece per line
 //   *.guest2host constant header + one row per vertex in breadth-first order
 //   *.leafmap    one row per leaf in breadth-first order
-// Size pass  (k_emit<false>): piece lengths through a CountSink; lengths (u16) and the shortest decimal digits of every
-//            branch length (Schubfach result f x 10^e) are cached per piece so that nothing is formatted twice.
-// Write pass (k_emit<true>):  32 pieces at a time: cached lengths -> warp exclusive scan -> each lane formats its piece
-//            once into a shared-memory staging buffer laid out congruent (mod 16) to the destination -> the warp flushes
-//            the buffer with aligned 16-byte coalesced stores.
+// Sizes:  the label kernel (kernels_label.cuh) leaves one emission record per piece, in the order the piece is written, with
+//         the piece's length and the shortest-decimal digits of its floating-point field, and the size of every tree / row stream
+//         of the replicate; k_emit_info<false> adds the sizes of the .info files.
+// Write:  k_write_tree / k_write_rows, one warp per replicate, 32 pieces per trip: the lanes load 32 consecutive records
+//         (coalesced, the next trip's records are in flight while this trip is formatted) -> warp exclusive scan of the lengths ->
+//         each lane formats its piece once into a shared-memory stage laid out congruent (mod 16) to the destination -> the
+//         stage leaves as one bulk shared->global copy (cp.async.bulk, TMA) plus byte stores for the unaligned head and tail,
+//         double-buffered so that the next trip is formatted while the copy drains.
 //
-// Formats follow NewickVertex.toString (io/NewickVertex.java:412-435), NewickTree.toString (io/NewickTree.java:457-465),
-// GuestVertex.setMeta (apps/SaGePhy/GuestVertex.java:183-425), HostTreeGen.getInfo (apps/SaGePhy/HostTreeGen.java:99-110,124-174),
-// GuestTreeInHostTreeCreator.getInfo/getLeafMap/getSigma (:431-559) and the file writers in GuestTreeGen.java:66-101.
+// Formats: emit_format.cuh; HostTreeGen.getInfo (apps/SaGePhy/HostTreeGen.java:99-110,124-174),
+// GuestTreeInHostTreeCreator.getInfo (:431-511) and the file writers in GuestTreeGen.java:66-101.
 #pragma once
-#include "kernels_args.cuh"
+#include "emit_format.cuh"
 
 namespace sgp {
-
-
-
-template <class Sink> __device__ __forceinline__ void put_blob(Sink& s, const char* b, int off, int len) { for (int i = 0; i < len; ++i) s.put(b[off + i]); }
-__device__ __forceinline__ void put_blob(CountSink& s, const char*, int, int len) { s.n += len; }
-
-template <class Sink> __device__ void put_name(Sink& s, const EmitArgs& a, const Node& x) {
-    for (int i = 0; i < a.prefix_len; ++i) s.put(a.prefix[i]);
-    put_i64(s, x.number);
-    if (a.append_sigma) { s.put('_'); put_i64(s, x.sigma); }
-}
-
-template <class Sink> __device__ void put_discpt(Sink& s, const EmitArgs& a, const Node& x) {
-    const double* t = a.app == 2 ? a.gene_ep_times + 3 * (size_t)(a.gene_ep_base[x.gtree] + x.epoch) : a.ep_times + 3 * (size_t)x.epoch;
-    int j = 0; while (j < 3) { if (t[j] >= x.abstime) break; ++j; }
-    put_lit(s, "DISCPT=("); put_i64(s, x.epoch); s.put(','); put_i64(s, j); s.put(')');
-}
-
-template <class Sink> __device__ void put_meta(Sink& s, const EmitArgs& a, const Node& x) {
-    put_lit(s, "[ID="); put_i64(s, x.number);
-    if (!a.is_species) {
-        put_lit(s, " HOST="); put_i64(s, x.sigma); put_lit(s, " GUEST=");
-        put_blob(s, a.blob, a.gname_off[2 * x.gtree], a.gname_off[2 * x.gtree + 1]);
-    }
-    switch (x.event) {
-        case EV_DUPLICATION: if (a.is_species) put_lit(s, " VERTEXTYPE=Speciation "); else put_lit(s, " VERTEXTYPE=Duplication "); put_discpt(s, a, x); break;
-        case EV_LOSS: put_lit(s, " VERTEXTYPE=Loss"); break;
-        case EV_REPLACING_LOSS: put_lit(s, " VERTEXTYPE=Replacing Loss"); break;
-        case EV_SPECIATION: put_lit(s, " VERTEXTYPE=Speciation "); put_discpt(s, a, x); break;
-        case EV_CODIVERGENCE: put_lit(s, " VERTEXTYPE=Co-divergence "); put_discpt(s, a, x); break;
-        case EV_LEAF: put_lit(s, " VERTEXTYPE=Leaf"); break;
-        case EV_UNSAMPLED_LEAF: put_lit(s, " VERTEXTYPE=UnsampledLeaf"); break;
-        default: {
-            const bool additive = x.event == EV_ADDITIVE_TRANSFER || (x.event >= EV_AT_GG_SS && x.event <= EV_AT_DG_DS);
-            if (additive) put_lit(s, " VERTEXTYPE=Additive Transfer"); else put_lit(s, " VERTEXTYPE=Replacing Transfer");
-            if (x.event >= EV_AT_GG_SS) {
-                const int k = (x.event - EV_AT_GG_SS) & 3;
-                if (k & 2) put_lit(s, " Intergene"); else put_lit(s, " Intragene"); if (k & 1) put_lit(s, " Interspecies"); else put_lit(s, " Intraspecies");
-            }
-            put_lit(s, " FROMTOLINEAGE=("); put_i64(s, x.from_arc); s.put(','); put_i64(s, x.to_arc);
-            if (x.event >= EV_AT_GG_SS) {
-                s.put(';');
-                if (x.from_g >= 0) put_blob(s, a.blob, a.gname_off[2 * x.from_g], a.gname_off[2 * x.from_g + 1]); else put_lit(s, "null");
-                s.put(',');
-                if (x.to_g >= 0) put_blob(s, a.blob, a.gname_off[2 * x.to_g], a.gname_off[2 * x.to_g + 1]); else put_lit(s, "null");
-            }
-            put_lit(s, ") "); put_discpt(s, a, x);
-        }
-    }
-    s.put(']');
-}
-
-// piece k (post-order rank) of a tree stream; (f, e) = cached shortest decimal of the branch length (e == kNoDigits: none)
-constexpr int kNoDigits = 0x7fff;
-template <bool PRUNED, class Sink> __device__ void put_tree_piece(Sink& s, const EmitArgs& a, const Node* N, const int32_t* ord, int k, int root,
-                                                                  unsigned long long f, int e) {
-    const int vi = ord[k];
-    const Node& x = N[vi];
-    const bool leaf = PRUNED ? x.p_left < 0 : x.left < 0;
-    if (leaf) { const int c = PRUNED ? x.chain_p : x.chain_u; for (int i = 0; i < c; ++i) s.put('('); }
-    else s.put(')');
-    put_name(s, a, x);
-    s.put(':');
-    const double bl = PRUNED ? x.p_bl : x.bl;
-    if (e != kNoDigits) put_double_digits(s, bl, f, e); else put_double(s, a.T, bl);
-    if (!a.exclude_meta) put_meta(s, a, x);
-    if (x.flags & (PRUNED ? NF_LEFT_P : NF_LEFT_U)) s.put(',');
-    if (vi == root) {
-        if (!a.exclude_meta) { if (PRUNED) put_lit(s, "[NAME=PrunedTree]"); else put_lit(s, "[NAME=UnprunedTree]"); }
-        s.put(';'); s.put('\n');
-    }
-}
 
 template <class Sink> __device__ void put_kv_int(Sink& s, const char* k, long long v) { put_str(s, k); put_i64(s, v); s.put('\n'); }
 template <class Sink> __device__ void put_kv_dbl(Sink& s, const EmitArgs& a, const char* k, double v) { put_str(s, k); put_double(s, a.T, v); s.put('\n'); }
@@ -165,37 +95,6 @@ template <bool PRUNED, class Sink> __device__ void put_info_line(Sink& s, const 
     s.put('\n');
 }
 
-__device__ __forceinline__ const char* event_enum_name(int e) {
-    switch (e) {
-        case EV_SPECIATION: return "SPECIATION"; case EV_CODIVERGENCE: return "CODIVERGENCE"; case EV_LEAF: return "LEAF";
-        case EV_UNSAMPLED_LEAF: return "UNSAMPLED_LEAF"; case EV_DUPLICATION: return "DUPLICATION"; case EV_LOSS: return "LOSS";
-        case EV_REPLACING_LOSS: return "REPLACING_LOSS"; case EV_ADDITIVE_TRANSFER: return "ADDITIVE_TRANSFER";
-        case EV_REPLACING_TRANSFER: return "REPLACING_TRANSFER";
-        case EV_AT_GG_SS: return "ADDITIVE_TRANSFER_INTRAGENE_INTRASPECIES"; case EV_AT_GG_DS: return "ADDITIVE_TRANSFER_INTRAGENE_INTERSPECIES";
-        case EV_AT_DG_SS: return "ADDITIVE_TRANSFER_INTERGENE_INTRASPECIES"; case EV_AT_DG_DS: return "ADDITIVE_TRANSFER_INTERGENE_INTERSPECIES";
-        case EV_RT_GG_SS: return "REPLACING_TRANSFER_INTRAGENE_INTRASPECIES"; case EV_RT_GG_DS: return "REPLACING_TRANSFER_INTRAGENE_INTERSPECIES";
-        case EV_RT_DG_SS: return "REPLACING_TRANSFER_INTERGENE_INTRASPECIES"; default: return "REPLACING_TRANSFER_INTERGENE_INTERSPECIES";
-    }
-}
-
-// guest2host row k (BFS rank)
-template <class Sink> __device__ void put_g2h_row(Sink& s, const EmitArgs& a, const Node* N, const int32_t* bfs, int k) {
-    const Node& x = N[bfs[k]];
-    put_name(s, a, x); s.put('\t'); put_i64(s, x.number); s.put('\t'); put_str(s, event_enum_name(x.event)); s.put('\t');
-    put_double(s, a.T, x.abstime); s.put('\t'); put_i64(s, x.sigma); s.put('\t'); put_i64(s, x.epoch); s.put('\n');
-}
-// leafmap row k (BFS rank); empty for interior vertices
-template <bool PRUNED, class Sink> __device__ void put_leafmap_row(Sink& s, const EmitArgs& a, const Node* N, const int32_t* bfs, int k) {
-    const Node& x = N[bfs[k]];
-    const bool leaf = PRUNED ? x.p_left < 0 : x.left < 0;
-    if (!leaf || !(x.event == EV_LEAF || x.event == EV_UNSAMPLED_LEAF)) return;
-    put_name(s, a, x); s.put('\t');
-    const int li = (a.app == 2 ? a.leaf_base[x.gtree] : 0) + x.sigma;
-    put_blob(s, a.blob, a.leafname_off[2 * li], a.leafname_off[2 * li + 1]);
-    if (a.app == 2) { s.put('\t'); put_blob(s, a.blob, a.gname_off[2 * x.gtree], a.gname_off[2 * x.gtree + 1]); }    // DomainTreeInHostTreeCreator.getLeafMap :1266
-    s.put('\n');
-}
-
 __device__ __forceinline__ unsigned warp_excl_scan_u32(unsigned v, unsigned* total) {
     unsigned x = v; const int lane = threadIdx.x & 31;
     for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
@@ -204,7 +103,7 @@ __device__ __forceinline__ unsigned warp_excl_scan_u32(unsigned v, unsigned* tot
 }
 
 constexpr int kEmitWarps = 4;               // warps per block
-constexpr int kStageBytes = 5120;           // shared staging per warp (32 pieces; longer groups fall back to direct stores)
+constexpr int kStageBytes = 4096;           // one staging buffer (32 pieces; longer groups fall back to direct stores); two per warp
 
 // Flushes `total` staged bytes (stage[mis .. mis+total), mis = dst & 15) to dst with aligned 16-byte stores.
 __device__ __forceinline__ void flush_stage(const char* stage, int mis, char* dst, unsigned total) {
@@ -219,7 +118,7 @@ __device__ __forceinline__ void flush_stage(const char* stage, int mis, char* ds
     if (done + lane < total) dst[done + lane] = stage[mis + done + lane];
 }
 
-// Pieces 0..n_pieces-1 of one stream of one replicate.
+// Pieces 0..n_pieces-1 of one stream of one replicate, lengths cached by the caller (BranchRelaxer emitter, kernels_relax.cuh).
 //   SIZE pass : len(i) computed with a CountSink by `piece(CountSink&, i, true)`, stored through store_len(i, len).
 //   WRITE pass: len(i) read through load_len(i); bytes produced by `piece(MemSink&, i, false)`.
 template <bool WRITE, class F, class LL, class SL>
@@ -356,127 +255,189 @@ __global__ void __launch_bounds__(kInfoWarps * 32) k_emit_info(EmitArgs a) {
     }
 }
 
-template <bool WRITE, int STREAM>
-__global__ void __launch_bounds__(kEmitWarps * 32, WRITE ? 8 : 10) k_emit(EmitArgs a) {
-    __shared__ __align__(16) char s_stage[kEmitWarps][kStageBytes];
+
+// ---- record-driven write kernels ---------------------------------------------------------------------------------------------------
+// Bulk asynchronous copy shared -> global (TMA, cp.async.bulk): both addresses 16-byte aligned, size a multiple of 16. The
+// issuing thread owns the bulk group; "wait_group.read N" returns when all but the N most recent groups have finished READING
+// shared memory, i.e. when their stage buffers may be overwritten.
+__device__ __forceinline__ void bulk_store(char* dst, uint32_t src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Flushes `total` staged bytes (stage[mis .. mis+total), mis = dst & 15): the 16-byte aligned body as one bulk copy issued by lane
+// 0, the unaligned head and tail (< 16 bytes each) as byte stores. Every lane that wrote the stage calls this (proxy fence).
+template <bool BULK> __device__ __forceinline__ void flush_stage_async(const char* stage, int mis, char* dst, unsigned total) {
+    if (!BULK) { flush_stage(stage, mis, dst, total); return; }
+    const int lane = threadIdx.x & 31;
+    fence_async_smem();
+    __syncwarp();
+    unsigned head = (16u - (unsigned)mis) & 15u; if (head > total) head = total;
+    const unsigned body = (total - head) & ~15u;
+    if (lane == 0 && body) bulk_store(dst + head, (uint32_t)__cvta_generic_to_shared(stage + mis + head), body);
+    if ((unsigned)lane < head) dst[lane] = stage[mis + lane];
+    const unsigned done = head + body;
+    if (done + lane < total) dst[done + lane] = stage[mis + done + lane];
+}
+
+// Pieces [0, n) of one stream of one replicate, from their records. `piece(sink, rec, i)` prints piece i, `len_of(rec)` is its
+// cached length. Returns the bytes written. `trip` counts the stage buffers this warp has used (double buffering across calls).
+template <bool BULK, class Rec, class F, class L>
+__device__ __forceinline__ unsigned long long emit_records(int n, const Rec* recs, char* base, char* stage2, unsigned& trip, F&& piece, L&& len_of) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long running = 0;
+    Rec cur; { const uint4 z = make_uint4(0, 0, 0, 0); uint4* c4 = reinterpret_cast<uint4*>(&cur); c4[0] = z; c4[1] = z; }
+    if (lane < n) { const uint4* s4 = reinterpret_cast<const uint4*>(recs + lane); uint4* c4 = reinterpret_cast<uint4*>(&cur); c4[0] = s4[0]; c4[1] = s4[1]; }
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        Rec nxt = cur;
+        if (i + 32 < n) { const uint4* s4 = reinterpret_cast<const uint4*>(recs + i + 32); uint4* c4 = reinterpret_cast<uint4*>(&nxt); c4[0] = s4[0]; c4[1] = s4[1]; }
+        unsigned len = 0;
+        if (i < n) {
+            len = len_of(cur);
+            if (len == 0xffffu) { CountSink c; piece(c, cur, i); len = (unsigned)c.n; }       // saturated cache: a huge name or prefix
+        }
+        unsigned total; const unsigned off = warp_excl_scan_u32(len, &total);
+        if (total) {
+            char* dst = base + running;
+            const int mis = (int)(reinterpret_cast<unsigned long long>(dst) & 15ull);
+            if (total + 16 <= (unsigned)kStageBytes) {
+                char* stage = stage2 + (trip & 1u) * kStageBytes;
+                if (BULK && trip >= 2) { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }       // the copy that last read this buffer is done
+                if (len) { SmemSink m{(uint32_t)__cvta_generic_to_shared(stage) + (uint32_t)mis + off}; piece(m, cur, i); }
+                if (!BULK) __syncwarp();
+                flush_stage_async<BULK>(stage, mis, dst, total);
+                if (!BULK) __syncwarp();
+                ++trip;
+            } else if (len) { MemSink m{dst + off}; piece(m, cur, i); }
+        }
+        running += total;
+        cur = nxt;
+    }
+    return running;
+}
+
+// Finishes the raw records the label kernels left (digits of the floating-point field, length of the piece) and sums the sizes of
+// the tree and row streams of every replicate: warp per replicate, records read and written back in place, coalesced.
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void load_rec32(void* dst, const void* src) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src); uint4* d4 = reinterpret_cast<uint4*>(dst);
+    d4[0] = s4[0]; d4[1] = s4[1];
+}
+template <int INSTANCE> __global__ void __launch_bounds__(256) k_finish_records(EmitArgs a) {      // (template: the header is included by two translation units)
     const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= a.n) return;
-    char* stage = s_stage[threadIdx.x >> 5];
     const RepInfo& inf = a.info[r];
-    const long long gid = a.rep_base + r;
-    const bool ok = inf.status == REP_OK;
-    const long long off = ok ? a.node_off[r] : 0;
-    const Node* N = a.nodes + off;
-    const int32_t* ordU = a.aux + off; const int32_t* ordP = a.aux + a.aux_stride + off;
-    const int32_t* bfsU = a.aux + 2 * a.aux_stride + off; const int32_t* bfsP = a.aux + 3 * a.aux_stride + off;
-    auto no_load = [](int) { return 0u; };
-    auto no_store = [](int, unsigned) {};
-    {
-        constexpr int st = STREAM;
-        if (WRITE && a.offsets[(size_t)st * a.stride + r + 1] > a.cap[st]) { if (lane == 0) *a.overflow = 1; return; }
-        char* base = WRITE ? a.out[st] + a.offsets[(size_t)st * a.stride + r] : nullptr;
-        uint16_t* plen = a.plen + (size_t)st * a.aux_stride + off;       // cached piece lengths of this stream
-        auto ld = [&](int i) { return (unsigned)plen[i]; };
-        auto sd = [&](int i, unsigned v) { plen[i] = (uint16_t)(v > 0xffffu ? 0xffffu : v); };
-        unsigned long long bytes = 0;
-        if (!ok) {
-            // failed replicate: the reference writes only the failure note (to <prefix>.info / <prefix>.pruned.info)
-            if (st == ST_PRUNED_INFO && inf.status == REP_MAX_ATTEMPTS) {
-                auto pc = [&](auto& s, int) { put_lit(s, "Failed to produce valid pruned tree within max allowed attempts.\n"); };
-                if (WRITE) bytes = emit_pieces<true>(1, base, stage, pc, [](int) { return 65u; }, no_store);
-                else bytes = emit_pieces<false>(1, base, stage, pc, no_load, no_store);
+    if (inf.status != REP_OK) return;
+    const long long off = a.node_off[r];
+    const unsigned mask = a.stream_mask;
+    const int up = inf.n_u, nu = inf.p_root >= 0 ? inf.n_p : 0;
+    unsigned long long* sz = a.sizes + r;
+#pragma unroll
+    for (int view = 0; view < 2; ++view) {
+        const int n = view ? nu : up;
+        if (mask & (1u << (view ? ST_PRUNED_TREE : ST_UNPRUNED_TREE))) {
+            TreeRec* recs = a.trec + (size_t)view * a.aux_stride + off;
+            const TreeRecX* recx = a.trecx ? a.trecx + (size_t)view * a.aux_stride + off : nullptr;
+            long long sum = 0;
+            for (int k = lane; k < n; k += 32) {
+                TreeRec t; load_rec32(&t, recs + k);
+                sum += view ? finish_tree_rec<true>(a, t, recx + k) : finish_tree_rec<false>(a, t, recx + k);
+                load_rec32(recs + k, &t);
             }
-        } else {
-            if constexpr (st == ST_UNPRUNED_TREE || st == ST_PRUNED_TREE) {
-                constexpr bool pr = st == ST_PRUNED_TREE;
-                if (pr && inf.p_root < 0) {
-                    auto pc = [&](auto& s, int) { if (a.exclude_meta) put_lit(s, ";\n"); else put_str(s, a.app == 0 ? "[NAME=PrunedTree];" : "[NAME=PrunedTree];\n"); };
-                    const unsigned l = a.exclude_meta ? 2u : (a.app == 0 ? 18u : 19u);
-                    if (WRITE) bytes = emit_pieces<true>(1, base, stage, pc, [l](int) { return l; }, no_store);
-                    else bytes = emit_pieces<false>(1, base, stage, pc, no_load, no_store);
-                } else {
-                unsigned long long* df = a.dig_f + (size_t)(pr ? 1 : 0) * a.aux_stride + off;
-                int16_t* de = a.dig_e + (size_t)(pr ? 1 : 0) * a.aux_stride + off;
-                const int32_t* ord = pr ? ordP : ordU; const int np = pr ? inf.n_p : inf.n_u; const int root = pr ? inf.p_root : inf.root;
-                if (WRITE) {
-                    auto pc = [&](auto& s, int k) { if (pr) put_tree_piece<true>(s, a, N, ord, k, root, df[k], (int)de[k]); else put_tree_piece<false>(s, a, N, ord, k, root, df[k], (int)de[k]); };
-                    bytes = emit_pieces<true>(np, base, stage, pc, ld, no_store);
-                } else {
-                    auto pc = [&](auto& s, int k) {
-                        const Node& x = N[ord[k]]; const double bl = pr ? x.p_bl : x.bl;
-                        uint64_t f = 0; int e = kNoDigits;
-                        if (bl > 0.0 && bl < dbl_inf()) d2s_decimal(a.T, bl, &f, &e);
-                        df[k] = (unsigned long long)f; de[k] = (int16_t)e;
-                        if (pr) put_tree_piece<true>(s, a, N, ord, k, root, f, e); else put_tree_piece<false>(s, a, N, ord, k, root, f, e);
-                    };
-                    bytes = emit_pieces<false>(np, base, stage, pc, no_load, sd);
-                }
-                }
+            sum = warp_sum_ll(sum);
+            // an empty pruned tree still prints NewickTree.toString of a null root
+            if (view && inf.p_root < 0) sum = a.exclude_meta ? 2 : (a.app == 0 ? 18 : 19);
+            if (lane == 0) sz[(size_t)(view ? ST_PRUNED_TREE : ST_UNPRUNED_TREE) * a.stride] = (unsigned long long)sum;
+        }
+        const bool wg = mask & (1u << (view ? ST_PRUNED_G2H : ST_UNPRUNED_G2H)), wl = mask & (1u << (view ? ST_PRUNED_LEAFMAP : ST_UNPRUNED_LEAFMAP));
+        if ((wg || wl) && a.rows) {
+            RowRec* recs = a.rows + (size_t)view * a.aux_stride + off;
+            long long sg = 0, sl = 0;
+            for (int k = lane; k < n; k += 32) {
+                RowRec t; load_rec32(&t, recs + k);
+                long long lg, ll; finish_row_rec(a, t, wg, wl, &lg, &ll); sg += lg; sl += ll;
+                load_rec32(recs + k, &t);
             }
-            if constexpr (st == ST_UNPRUNED_INFO || st == ST_PRUNED_INFO) {
-                constexpr bool pr = st == ST_PRUNED_INFO;
-                // lines 0-1 ("# APP" and "Arguments: [...]", which may embed a whole Newick host tree): warp-cooperative copy
-                const char* h0 = a.app == 0 ? "# HOSTTREEGEN\nArguments:\t" : a.app == 1 ? "# GUESTTREEGEN\nArguments:\t" : "# DOMAINTREEGEN\nArguments:\t";
-                const int h0len = a.app == 0 ? 25 : a.app == 1 ? 26 : 27;
-                const int seedlen = a.seed_mode ? seed_dec_len(a.sseed, a.blob, (unsigned long long)gid) : 0;
-                unsigned long long o = 0;
-                if (WRITE) {
-                    for (int i = lane; i < h0len; i += 32) base[i] = h0[i];
-                    if (a.args_pre_off16[0] >= 0) {
-                        // long argument text (a host tree given as a Newick string): aligned 16-byte copies from the copy of the
-                        // text whose blob offset is congruent to the destination mod 16
-                        char* dst = base + h0len;
-                        const int mis = (int)(reinterpret_cast<unsigned long long>(dst) & 15ull);
-                        flush_stage(a.blob + a.args_pre_off16[mis] - mis, mis, dst, (unsigned)a.args_pre_len);
-                    } else for (int i = lane; i < a.args_pre_len; i += 32) base[h0len + i] = a.blob[a.args_pre_off + i];
-                }
-                o = (unsigned long long)h0len + a.args_pre_len;
-                if (a.seed_mode) {
-                    if (WRITE) {
-                        if (lane == 0) { MemSink m{base + o}; put_seed(m, a.sseed, a.blob, (unsigned long long)gid); }
-                        for (int i = lane; i < a.args_post_len; i += 32) base[o + seedlen + i] = a.blob[a.args_post_off + i];
-                    }
-                    o += (unsigned long long)seedlen + a.args_post_len;
-                }
-                if (WRITE && lane == 0) base[o] = '\n';
-                o += 1;
-                auto pc = [&](auto& s, int ln) { if (pr) put_info_line<true>(s, a, inf, gid, ln + 2); else put_info_line<false>(s, a, inf, gid, ln + 2); };
-                // the remaining lines are cheap: their lengths are recomputed in the write pass instead of being cached
-                auto ld_info = [&](int ln) { CountSink c; if (pr) put_info_line<true>(c, a, inf, gid, ln + 2); else put_info_line<false>(c, a, inf, gid, ln + 2); return (unsigned)c.n; };
-                if (WRITE) bytes = o + emit_pieces<true>(info_lines(a, pr) - 2, base + o, stage, pc, ld_info, no_store);
-                else bytes = o + emit_pieces<false>(info_lines(a, pr) - 2, base, stage, pc, no_load, no_store);
-            }
-            if constexpr (st == ST_UNPRUNED_G2H || st == ST_PRUNED_G2H) {
-                constexpr bool pr = st == ST_PRUNED_G2H;
-                int head_len = a.g2h_head_len;
-                if (a.app == 2) {
-                    // DomainTreeGen prints the gene tree of the ROOT vertex as "Host tree" (getSigma :1279)
-                    const int rg = N[pr ? (inf.p_root >= 0 ? inf.p_root : inf.root) : inf.root].gtree;
-                    head_len = a.g2h_gene_off[2 * rg + 1];
-                    if (WRITE) for (int i = lane; i < head_len; i += 32) base[i] = a.blob[a.g2h_gene_off[2 * rg] + i];
-                } else if (WRITE) {
-                    const int mis = (int)(reinterpret_cast<unsigned long long>(base) & 15ull);
-                    flush_stage(a.blob + a.g2h_head_off16[mis] - mis, mis, base, (unsigned)a.g2h_head_len);      // source congruent to destination mod 16
-                }
-                bytes = (unsigned long long)head_len;
-                const int np = pr ? (inf.p_root >= 0 ? inf.n_p : 0) : inf.n_u;
-                const int32_t* bfs = pr ? bfsP : bfsU;
-                auto pc = [&](auto& s, int k) { put_g2h_row(s, a, N, bfs, k); };
-                if (WRITE) bytes += emit_pieces<true>(np, base + head_len, stage, pc, ld, no_store);
-                else bytes += emit_pieces<false>(np, nullptr, stage, pc, no_load, sd);
-            }
-            if constexpr (st == ST_UNPRUNED_LEAFMAP || st == ST_PRUNED_LEAFMAP) {
-                constexpr bool pr = st == ST_PRUNED_LEAFMAP;
-                const int np = pr ? (inf.p_root >= 0 ? inf.n_p : 0) : inf.n_u;
-                const int32_t* bfs = pr ? bfsP : bfsU;
-                auto pc = [&](auto& s, int k) { if (pr) put_leafmap_row<true>(s, a, N, bfs, k); else put_leafmap_row<false>(s, a, N, bfs, k); };
-                if (WRITE) bytes = emit_pieces<true>(np, base, stage, pc, ld, no_store);
-                else bytes = emit_pieces<false>(np, nullptr, stage, pc, no_load, sd);
+            sg = warp_sum_ll(sg); sl = warp_sum_ll(sl);
+            if (lane == 0) {
+                // DomainTreeGen prints the gene tree of the ROOT vertex as "Host tree" (getSigma :1279)
+                if (wg) sz[(size_t)(view ? ST_PRUNED_G2H : ST_UNPRUNED_G2H) * a.stride] = (unsigned long long)(sg + (a.app == 2 ? a.g2h_gene_off[2 * (view ? inf.root_gtree_p : inf.root_gtree_u) + 1] : a.g2h_head_len));
+                if (wl) sz[(size_t)(view ? ST_PRUNED_LEAFMAP : ST_UNPRUNED_LEAFMAP) * a.stride] = (unsigned long long)sl;
             }
         }
-        if (!WRITE && lane == 0) a.sizes[(size_t)st * a.stride + r] = bytes;
     }
+}
+
+// One Newick stream (VIEW 0: unpruned, 1: pruned): warp per replicate.
+template <int VIEW, bool BULK>
+__global__ void __launch_bounds__(kEmitWarps * 32) k_write_tree(EmitArgs a) {
+    __shared__ __align__(128) char s_stage[kEmitWarps][2 * kStageBytes];
+    const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= a.n) return;
+    constexpr int st = VIEW ? ST_PRUNED_TREE : ST_UNPRUNED_TREE;
+    const RepInfo& inf = a.info[r];
+    if (inf.status != REP_OK) return;
+    if (a.offsets[(size_t)st * a.stride + r + 1] > a.cap[st]) { if (lane == 0) *a.overflow = 1; return; }
+    char* base = a.out[st] + a.offsets[(size_t)st * a.stride + r];
+    char* stage2 = s_stage[threadIdx.x >> 5];
+    if (VIEW == 1 && inf.p_root < 0) {
+        // empty pruned tree: NewickTree.toString of a null root
+        if (lane == 0) { MemSink m{base}; if (a.exclude_meta) put_lit(m, ";\n"); else if (a.app == 0) put_lit(m, "[NAME=PrunedTree];"); else put_lit(m, "[NAME=PrunedTree];\n"); }
+        return;
+    }
+    const long long off = a.node_off[r];
+    const TreeRec* recs = a.trec + (size_t)VIEW * a.aux_stride + off;
+    const TreeRecX* recx = a.trecx ? a.trecx + (size_t)VIEW * a.aux_stride + off : nullptr;
+    unsigned trip = 0;
+    emit_records<BULK>(VIEW ? inf.n_p : inf.n_u, recs, base, stage2, trip,
+                       [&](auto& s, const TreeRec& t, int i) { put_tree_piece<VIEW == 1>(s, a, t, recx + i); },
+                       [](const TreeRec& t) { return (unsigned)t.len; });
+    if (BULK && lane == 0) bulk_wait_read<0>();         // shared memory must outlive the copies that read it
+}
+
+// One row stream (KIND 0: .guest2host, 1: .leafmap; VIEW 0: unpruned, 1: pruned): warp per replicate.
+template <int KIND, int VIEW, bool BULK>
+__global__ void __launch_bounds__(kEmitWarps * 32) k_write_rows(EmitArgs a) {
+    __shared__ __align__(128) char s_stage[kEmitWarps][2 * kStageBytes];
+    const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= a.n) return;
+    constexpr int st = KIND == 0 ? (VIEW ? ST_PRUNED_G2H : ST_UNPRUNED_G2H) : (VIEW ? ST_PRUNED_LEAFMAP : ST_UNPRUNED_LEAFMAP);
+    const RepInfo& inf = a.info[r];
+    if (inf.status != REP_OK) return;
+    if (a.offsets[(size_t)st * a.stride + r + 1] > a.cap[st]) { if (lane == 0) *a.overflow = 1; return; }
+    char* base = a.out[st] + a.offsets[(size_t)st * a.stride + r];
+    char* stage2 = s_stage[threadIdx.x >> 5];
+    const long long off = a.node_off[r];
+    const RowRec* recs = a.rows + (size_t)VIEW * a.aux_stride + off;
+    const int np = VIEW ? (inf.p_root >= 0 ? inf.n_p : 0) : inf.n_u;
+    unsigned trip = 0;
+    if (KIND == 0) {
+        int head_len = a.g2h_head_len;
+        if (a.app == 2) {
+            // DomainTreeGen prints the gene tree of the ROOT vertex as "Host tree" (getSigma :1279)
+            const int rg = VIEW ? inf.root_gtree_p : inf.root_gtree_u;
+            head_len = a.g2h_gene_off[2 * rg + 1];
+            for (int i = lane; i < head_len; i += 32) base[i] = a.blob[a.g2h_gene_off[2 * rg] + i];
+        } else {
+            const int mis = (int)(reinterpret_cast<unsigned long long>(base) & 15ull);
+            flush_stage(a.blob + a.g2h_head_off16[mis] - mis, mis, base, (unsigned)a.g2h_head_len);      // source congruent to destination mod 16
+        }
+        emit_records<BULK>(np, recs, base + head_len, stage2, trip,
+                           [&](auto& s, const RowRec& t, int) { put_g2h_row(s, a, t); }, [](const RowRec& t) { return (unsigned)t.len_g2h; });
+    } else {
+        emit_records<BULK>(np, recs, base, stage2, trip,
+                           [&](auto& s, const RowRec& t, int) { if (t.flags & RR_LEAFMAP) put_leafmap_row(s, a, t); }, [](const RowRec& t) { return (unsigned)t.len_lm; });
+    }
+    if (BULK && lane == 0) bulk_wait_read<0>();
 }
 
 }  // namespace sgp

@@ -14,7 +14,7 @@
 //   k_label_prune      — one thread per tree straight on global memory with the reference's serial traversals, for trees that
 //                        do not fit the shared-memory stage.
 #pragma once
-#include "kernels_args.cuh"
+#include "emit_format.cuh"
 
 namespace sgp {
 
@@ -91,6 +91,40 @@ __device__ __forceinline__ void label_bfs(Node* N, I* q, int start, bool pruned,
 // Shared-memory bytes per vertex of the warp kernel: the record + nine int16 work arrays.
 constexpr int kLabelBytesPerNode = (int)sizeof(Node) + 9 * (int)sizeof(int16_t);
 constexpr int kLabelExtraBytes = 16;
+__host__ __device__ inline size_t label_smem_bytes(int cap) { return (size_t)cap * kLabelBytesPerNode + kLabelExtraBytes; }
+
+__device__ __forceinline__ void store_rec32(void* dst, const void* src) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src); uint4* d4 = reinterpret_cast<uint4*>(dst);
+    d4[0] = s4[0]; d4[1] = s4[1];
+}
+
+// Raw emission records of one labelled tree (fields only: the floating-point value as its bits, no digits, no length);
+// executed by a whole warp. N = vertex records (shared or global memory), ordU / ordP / bfsU / bfsP = the four orders (int16 in
+// shared memory, int32 in global memory). k_finish_records (kernels_emit.cuh) turns the values into digits, measures every
+// piece and sums the stream sizes at full occupancy - inside the label kernel, which holds one warp per tree and few trees per SM,
+// that arithmetic took 60 ms per 10^6 C2 trees against 9 ms on its own.
+template <class I>
+__device__ __forceinline__ void make_records(const EmitArgs& E, long long goff, const Node* N, const I* ordU, const I* ordP, const I* bfsU, const I* bfsP,
+                                             int up, int nu, int root, int p_root) {
+    const int lane = threadIdx.x & 31;
+    const unsigned mask = E.stream_mask;
+    if (mask & (1u << ST_UNPRUNED_TREE)) {
+        TreeRec* out = E.trec + goff; TreeRecX* outx = E.trecx ? E.trecx + goff : nullptr;
+        for (int k = lane; k < up; k += 32) { const int v = ordU[k]; const TreeRec t = raw_tree_rec<false>(E, N[v], v == root, outx ? outx + k : nullptr); store_rec32(out + k, &t); }
+    }
+    if ((mask & (1u << ST_PRUNED_TREE)) && p_root >= 0) {
+        TreeRec* out = E.trec + E.aux_stride + goff; TreeRecX* outx = E.trecx ? E.trecx + E.aux_stride + goff : nullptr;
+        for (int k = lane; k < nu; k += 32) { const int v = ordP[k]; const TreeRec t = raw_tree_rec<true>(E, N[v], v == p_root, outx ? outx + k : nullptr); store_rec32(out + k, &t); }
+    }
+    if (E.rows && (mask & ((1u << ST_UNPRUNED_G2H) | (1u << ST_UNPRUNED_LEAFMAP)))) {
+        RowRec* out = E.rows + goff;
+        for (int k = lane; k < up; k += 32) { const RowRec rr = raw_row_rec<false>(N[bfsU[k]]); store_rec32(out + k, &rr); }
+    }
+    if (E.rows && (mask & ((1u << ST_PRUNED_G2H) | (1u << ST_PRUNED_LEAFMAP))) && p_root >= 0) {
+        RowRec* out = E.rows + E.aux_stride + goff;
+        for (int k = lane; k < nu; k += 32) { const RowRec rr = raw_row_rec<true>(N[bfsP[k]]); store_rec32(out + k, &rr); }
+    }
+}
 
 // One warp per tree, all lanes busy. The serial recursions of the reference are restated as level-synchronous sweeps over the
 // breadth-first order (a tree of ~270 vertices has ~30 levels, so a sweep is ~35 warp steps instead of ~270 dependent ones):
@@ -253,16 +287,20 @@ __global__ void __launch_bounds__(32) k_label_prune_warp(LabelArgs a) {
         }
         __syncwarp();
         {
-            uint4* dst = reinterpret_cast<uint4*>(a.nodes + goff); const uint4* src = reinterpret_cast<const uint4*>(sN);
-            const int nq = n_pool * (int)(sizeof(Node) / 16);
-            for (int i = lane; i < nq; i += 32) dst[i] = src[i];
-            int32_t* gOrdU = a.aux + goff; int32_t* gOrdP = a.aux + a.aux_stride + goff;
-            int32_t* gBfsU = a.aux + 2 * a.aux_stride + goff; int32_t* gBfsP = a.aux + 3 * a.aux_stride + goff;
-            for (int k = lane; k < up; k += 32) { gOrdU[k] = ordU[k]; gBfsU[k] = bfsU[k]; }
-            for (int k = lane; k < nu; k += 32) { gOrdP[k] = ordP[k]; gBfsP[k] = bfsP[k]; }
+            if (a.write_nodes) {
+                uint4* dst = reinterpret_cast<uint4*>(a.nodes + goff); const uint4* src = reinterpret_cast<const uint4*>(sN);
+                const int nq = n_pool * (int)(sizeof(Node) / 16);
+                for (int i = lane; i < nq; i += 32) dst[i] = src[i];
+                int32_t* gOrdU = a.aux + goff; int32_t* gOrdP = a.aux + a.aux_stride + goff;
+                int32_t* gBfsU = a.aux + 2 * a.aux_stride + goff; int32_t* gBfsP = a.aux + 3 * a.aux_stride + goff;
+                for (int k = lane; k < up; k += 32) { gOrdU[k] = ordU[k]; gBfsU[k] = bfsU[k]; }
+                for (int k = lane; k < nu; k += 32) { gOrdP[k] = ordP[k]; gBfsP[k] = bfsP[k]; }
+            }
+            make_records<int16_t>(a.E, goff, sN, ordU, ordP, bfsU, bfsP, up, nu, root, p_root);
             if (lane < EV_COUNT) { inf.cnt_u[lane] = s_cnt[0][lane]; inf.cnt_p[lane] = s_cnt[1][lane]; }
             if (lane == 0) {
                 inf.p_root = p_root; inf.n_u = up; inf.n_p = nu; inf.p_root_time = p_root >= 0 ? sN[p_root].abstime : 0.0;
+                inf.root_gtree_u = sN[root].gtree; inf.root_gtree_p = sN[p_root >= 0 ? p_root : root].gtree;
                 inf.total_u = s_sum[0][0]; inf.beneath_u = s_sum[0][1]; inf.total_p = s_sum[1][0]; inf.beneath_p = s_sum[1][1];
             }
         }
@@ -287,6 +325,7 @@ __global__ void __launch_bounds__(128) k_label_prune(LabelArgs a) {
     for (int k = 0; k < up; ++k) { Node& x = N[ordU[k]]; if (x.number < -1) x.number = nu + (-2 - x.number); }
     if (a.has_stem_override) { N[root].bl = a.stem_override; if (p_root >= 0) N[p_root].p_bl = a.stem_override; }
     inf.p_root = p_root; inf.n_u = up; inf.n_p = nu; inf.p_root_time = p_root >= 0 ? N[p_root].abstime : 0.0;
+    inf.root_gtree_u = N[root].gtree; inf.root_gtree_p = N[p_root >= 0 ? p_root : root].gtree;
     for (int e = 0; e < EV_COUNT; ++e) { inf.cnt_u[e] = 0; inf.cnt_p[e] = 0; }
     double tot, ben;
     label_bfs<int32_t>(N, bfsU, root, false, a.host_root_time, inf.cnt_u, tot, ben);
@@ -294,6 +333,17 @@ __global__ void __launch_bounds__(128) k_label_prune(LabelArgs a) {
     label_bfs<int32_t>(N, bfsP, p_root, true, a.host_root_time, inf.cnt_p, tot, ben);
     inf.total_p = tot; inf.beneath_p = ben;
     for (int k = 0; k < up; ++k) { Node& x = N[ordU[k]]; x.flags |= x.pad0; x.pad0 = 0; }
+}
+
+// Emission records of the trees the thread kernel labelled (warp per tree, vertex records and orders in global memory).
+__global__ void __launch_bounds__(128) k_records_from_nodes(LabelArgs a) {
+    const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= a.n) return;
+    const RepInfo& inf = a.info[r];
+    if (inf.status != REP_OK || inf.n_pool <= a.cap) return;
+    const long long off = a.node_off[r];
+    make_records<int32_t>(a.E, off, a.nodes + off, a.aux + off, a.aux + a.aux_stride + off, a.aux + 2 * a.aux_stride + off, a.aux + 3 * a.aux_stride + off,
+                          inf.n_u, inf.n_p, inf.root, inf.p_root);
 }
 
 }  // namespace sgp

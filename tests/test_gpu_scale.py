@@ -355,9 +355,9 @@ def test_iidrk11_replay_and_distribution(ctx, tmp_path):
 def test_pipelined_run_equals_serial_run(ctx, monkeypatch):
     args = ["-s", "77", "-min", "6", "-max", "14", "-p", "0.8", "1.0", "2.5", "0.3", "x"]
     n = 300000                                   # three sub-batches of 131072
-    piped = ctx.run("HostTreeGen", args, n=n, rng=sg.RNG_PHILOX, offset=5)
+    piped = ctx.run("HostTreeGen", args, n=n, rng=sg.RNG_PHILOX, offset=5, flags=sg.FLAG_PIPELINE)
     assert piped.timings()["sub_batches"] == 3
-    serial = ctx.run("HostTreeGen", args, n=n, rng=sg.RNG_PHILOX, offset=5, flags=sg.FLAG_SERIAL)
+    serial = ctx.run("HostTreeGen", args, n=n, rng=sg.RNG_PHILOX, offset=5)
     assert serial.timings()["sub_batches"] == 1
     assert (piped.rep_status == 0).all()
     for s in range(4):
@@ -369,7 +369,7 @@ def test_pipelined_run_equals_serial_run(ctx, monkeypatch):
     piped.free()
     # an output estimate that turns out too small (forced here) falls back to the unpipelined path: same bytes again
     monkeypatch.setenv("SGP_OUTPUT_MARGIN", "0.6")
-    again = ctx.run("HostTreeGen", args, n=n, rng=sg.RNG_PHILOX, offset=5)
+    again = ctx.run("HostTreeGen", args, n=n, rng=sg.RNG_PHILOX, offset=5, flags=sg.FLAG_PIPELINE)
     monkeypatch.delenv("SGP_OUTPUT_MARGIN")
     assert again.timings()["sub_batches"] == 1
     for s in range(4):
