@@ -51,8 +51,11 @@ struct __align__(16) TreeRec {
     int32_t number, sigma, epoch;
     int16_t e, chain;
     uint8_t event, flags;
-    uint16_t len;          // bytes of the piece (0xffff: longer, measured again by the writer)
-    int16_t gtree, pad;
+    int16_t gtree;
+    union {
+        struct { uint16_t len; int16_t pad; };     // finished: bytes of the piece (0xffff: longer, measured again by the writer)
+        int32_t link;      // raw pruned-view record: index of the same vertex's record in the unpruned view if both print the same length (-1: none)
+    };
 };
 static_assert(sizeof(TreeRec) == 32, "TreeRec layout");
 // Transfer vertices only (GuestTreeGen / DomainTreeGen): same index as the TreeRec, touched for transfer events alone.
@@ -65,7 +68,11 @@ struct __align__(16) RowRec {
     int32_t number, sigma, epoch;
     int16_t e, gtree;
     uint8_t event, flags;
-    uint16_t len_g2h, len_lm, pad;
+    uint16_t len_g2h;
+    union {
+        struct { uint16_t len_lm, pad; };
+        int32_t link;      // raw pruned-view record: index of the same vertex's row in the unpruned view (-1: none)
+    };
 };
 static_assert(sizeof(RowRec) == 32, "RowRec layout");
 

@@ -20,11 +20,12 @@ template <class Sink> __device__ __forceinline__ void put_name(Sink& s, const Em
 }
 
 // f x 10^e as java.lang.Double.toString lays it out; e == kNoDigits: f holds the bits of a value without digits (0.0, NaN, ...)
-template <class Sink> __device__ __forceinline__ void put_decimal(Sink& s, const MathTables& T, uint64_t f, int e) {
+// nd: number of digits of f (kept in the record: the finish kernel counts them once)
+template <class Sink> __device__ __forceinline__ void put_decimal(Sink& s, const MathTables& T, uint64_t f, int e, int nd) {
     if (e == kNoDigits) { put_double(s, T, __longlong_as_double((long long)f)); return; }
     // the layout depends on 1e-3 <= v < 1e7 only; v = 0.DIGITS x 10^pe, so that is -2 <= pe <= 7
-    const int pe = dec_len_u64(f) + e;
-    put_double_digits(s, (pe >= -2 && pe <= 7) ? 1.0 : 1e-9, f, e);
+    const int pe = nd + e;
+    put_double_digits(s, (pe >= -2 && pe <= 7) ? 1.0 : 1e-9, f, e, nd);
 }
 __device__ __forceinline__ void decimal_of(const MathTables& T, double v, uint64_t* f, int* e) {
     if (v > 0.0 && v < dbl_inf()) d2s_decimal(T, v, f, e);
@@ -41,25 +42,30 @@ __device__ __forceinline__ int discpt_index(const EmitArgs& a, int gtree, int ep
     return j;
 }
 
+__device__ __forceinline__ bool is_transfer_event(int ev) { return ev >= EV_ADDITIVE_TRANSFER; }
+
+// Lanes print different vertex types in the same trip, so everything that is common to several types (the key, the DISCPT tag)
+// is outside the switch: a branch of a switch runs once per type present in the warp.
 template <class Sink> __device__ void put_meta(Sink& s, const EmitArgs& a, const TreeRec& t, const TreeRecX* xp) {
     put_lit(s, "[ID="); put_i32(s, t.number);
     if (!a.is_species) {
         put_lit(s, " HOST="); put_i32(s, t.sigma); put_lit(s, " GUEST=");
         put_blob(s, a.blob, a.gname_off[2 * t.gtree], a.gname_off[2 * t.gtree + 1]);
     }
-    const int j = (t.flags >> TR_J_SHIFT) & 3;
+    put_lit(s, " VERTEXTYPE=");
+    bool discpt = false;
     switch (t.event) {
-        case EV_DUPLICATION: if (a.is_species) put_lit(s, " VERTEXTYPE=Speciation "); else put_lit(s, " VERTEXTYPE=Duplication "); put_discpt(s, t.epoch, j); break;
-        case EV_LOSS: put_lit(s, " VERTEXTYPE=Loss"); break;
-        case EV_REPLACING_LOSS: put_lit(s, " VERTEXTYPE=Replacing Loss"); break;
-        case EV_SPECIATION: put_lit(s, " VERTEXTYPE=Speciation "); put_discpt(s, t.epoch, j); break;
-        case EV_CODIVERGENCE: put_lit(s, " VERTEXTYPE=Co-divergence "); put_discpt(s, t.epoch, j); break;
-        case EV_LEAF: put_lit(s, " VERTEXTYPE=Leaf"); break;
-        case EV_UNSAMPLED_LEAF: put_lit(s, " VERTEXTYPE=UnsampledLeaf"); break;
+        case EV_DUPLICATION: if (a.is_species) put_lit(s, "Speciation"); else put_lit(s, "Duplication"); discpt = true; break;
+        case EV_LOSS: put_lit(s, "Loss"); break;
+        case EV_REPLACING_LOSS: put_lit(s, "Replacing Loss"); break;
+        case EV_SPECIATION: put_lit(s, "Speciation"); discpt = true; break;
+        case EV_CODIVERGENCE: put_lit(s, "Co-divergence"); discpt = true; break;
+        case EV_LEAF: put_lit(s, "Leaf"); break;
+        case EV_UNSAMPLED_LEAF: put_lit(s, "UnsampledLeaf"); break;
         default: {
             const TreeRecX x = *xp;
             const bool additive = t.event == EV_ADDITIVE_TRANSFER || (t.event >= EV_AT_GG_SS && t.event <= EV_AT_DG_DS);
-            if (additive) put_lit(s, " VERTEXTYPE=Additive Transfer"); else put_lit(s, " VERTEXTYPE=Replacing Transfer");
+            if (additive) put_lit(s, "Additive Transfer"); else put_lit(s, "Replacing Transfer");
             if (t.event >= EV_AT_GG_SS) {
                 const int k = (t.event - EV_AT_GG_SS) & 3;
                 if (k & 2) put_lit(s, " Intergene"); else put_lit(s, " Intragene"); if (k & 1) put_lit(s, " Interspecies"); else put_lit(s, " Intraspecies");
@@ -71,13 +77,13 @@ template <class Sink> __device__ void put_meta(Sink& s, const EmitArgs& a, const
                 s.put(',');
                 if (x.to_g >= 0) put_blob(s, a.blob, a.gname_off[2 * x.to_g], a.gname_off[2 * x.to_g + 1]); else put_lit(s, "null");
             }
-            put_lit(s, ") "); put_discpt(s, t.epoch, j);
+            s.put(')'); discpt = true;
         }
     }
+    if (discpt) { put_lit(s, " DISCPT=("); put_i32(s, t.epoch); s.put(','); s.put((char)('0' + ((t.flags >> TR_J_SHIFT) & 3))); s.put(')'); }
     s.put(']');
 }
 
-__device__ __forceinline__ bool is_transfer_event(int ev) { return ev >= EV_ADDITIVE_TRANSFER; }
 
 // one Newick piece
 template <bool PRUNED, class Sink> __device__ void put_tree_piece(Sink& s, const EmitArgs& a, const TreeRec& t, const TreeRecX* xp) {
@@ -85,7 +91,7 @@ template <bool PRUNED, class Sink> __device__ void put_tree_piece(Sink& s, const
     else s.put(')');
     put_name(s, a, t.number, t.sigma);
     s.put(':');
-    put_decimal(s, a.T, t.f, t.e);
+    put_decimal(s, a.T, t.f, t.e, t.pad);
     if (!a.exclude_meta) put_meta(s, a, t, xp);
     if (t.flags & TR_COMMA) s.put(',');
     if (t.flags & TR_ROOT) {
@@ -120,7 +126,7 @@ __device__ __forceinline__ void put_event_enum(CountSink& s, int e) { s.n += eve
 // .guest2host row: name, id, type, time (unrounded), host vertex / arc, host epoch
 template <class Sink> __device__ void put_g2h_row(Sink& s, const EmitArgs& a, const RowRec& r) {
     put_name(s, a, r.number, r.sigma); s.put('\t'); put_i32(s, r.number); s.put('\t'); put_event_enum(s, r.event); s.put('\t');
-    put_decimal(s, a.T, r.f, r.e); s.put('\t'); put_i32(s, r.sigma); s.put('\t'); put_i32(s, r.epoch); s.put('\n');
+    put_decimal(s, a.T, r.f, r.e, r.pad); s.put('\t'); put_i32(s, r.sigma); s.put('\t'); put_i32(s, r.epoch); s.put('\n');
 }
 // .leafmap row of a leaf of the view (RR_LEAFMAP): name, host leaf name [, gene tree name]
 template <class Sink> __device__ void put_leafmap_row(Sink& s, const EmitArgs& a, const RowRec& r) {
@@ -136,10 +142,11 @@ __device__ __forceinline__ uint16_t clamp_len(long long n) { return (uint16_t)(n
 // ---- records from a vertex ---------------------------------------------------------------------------------------------------------
 // Raw record (label kernels): every field the piece prints, the floating-point value as its bits with e = kRawValue.
 constexpr int kRawValue = 0x7ffe;
-template <bool PRUNED> __device__ __forceinline__ TreeRec raw_tree_rec(const EmitArgs& a, const Node& x, bool is_root, TreeRecX* xout) {
+template <bool PRUNED> __device__ __forceinline__ TreeRec raw_tree_rec(const EmitArgs& a, const Node& x, bool is_root, TreeRecX* xout, int link) {
     TreeRec t;
-    t.f = (uint64_t)__double_as_longlong(PRUNED ? x.p_bl : x.bl); t.e = (int16_t)kRawValue; t.len = 0;
-    t.number = x.number; t.sigma = x.sigma; t.epoch = x.epoch; t.event = x.event; t.gtree = x.gtree; t.pad = 0;
+    t.f = (uint64_t)__double_as_longlong(PRUNED ? x.p_bl : x.bl); t.e = (int16_t)kRawValue;
+    t.link = (PRUNED && __double_as_longlong(x.p_bl) == __double_as_longlong(x.bl)) ? link : -1;
+    t.number = x.number; t.sigma = x.sigma; t.epoch = x.epoch; t.event = x.event; t.gtree = x.gtree;
     const bool leaf = PRUNED ? x.p_left < 0 : x.left < 0;
     t.chain = leaf ? (PRUNED ? x.chain_p : x.chain_u) : (int16_t)0;
     uint8_t fl = leaf ? TR_LEAF : 0;
@@ -151,27 +158,40 @@ template <bool PRUNED> __device__ __forceinline__ TreeRec raw_tree_rec(const Emi
     if (is_transfer_event(x.event) && xout) { TreeRecX xr; xr.from_arc = x.from_arc; xr.to_arc = x.to_arc; xr.from_g = x.from_g; xr.to_g = x.to_g; xr.pad = 0; *xout = xr; }
     return t;
 }
-template <bool PRUNED> __device__ __forceinline__ RowRec raw_row_rec(const Node& x) {
+template <bool PRUNED> __device__ __forceinline__ RowRec raw_row_rec(const Node& x, int link) {
     RowRec r;
-    r.f = (uint64_t)__double_as_longlong(x.abstime); r.e = (int16_t)kRawValue; r.len_g2h = 0; r.len_lm = 0; r.pad = 0;
+    r.f = (uint64_t)__double_as_longlong(x.abstime); r.e = (int16_t)kRawValue; r.len_g2h = 0; r.link = PRUNED ? link : -1;
     r.number = x.number; r.sigma = x.sigma; r.epoch = x.epoch; r.gtree = x.gtree; r.event = x.event;
     const bool leaf = PRUNED ? x.p_left < 0 : x.left < 0;
     r.flags = (leaf && (x.event == EV_LEAF || x.event == EV_UNSAMPLED_LEAF)) ? RR_LEAFMAP : 0;
     return r;
 }
 // Finished record (k_finish_records): digits of the value, length of the piece. Returns the unclamped length.
-template <bool PRUNED> __device__ __forceinline__ long long finish_tree_rec(const EmitArgs& a, TreeRec& t, const TreeRecX* xp) {
-    uint64_t f; int e; decimal_of(a.T, __longlong_as_double((long long)t.f), &f, &e);
-    t.f = f; t.e = (int16_t)e;
+// `twin`: finished unpruned-view records of the replicate; a linked pruned-view record takes its digits from there.
+template <bool PRUNED> __device__ __forceinline__ long long finish_tree_rec(const EmitArgs& a, TreeRec& t, const TreeRecX* xp, const TreeRec* twin) {
+    const int link = t.link;
+    int nd;
+    if (PRUNED && twin && link >= 0) { t.f = twin[link].f; t.e = twin[link].e; nd = twin[link].pad; }
+    else { uint64_t f; int e; decimal_of(a.T, __longlong_as_double((long long)t.f), &f, &e); t.f = f; t.e = (int16_t)e; nd = e == kNoDigits ? 0 : dec_len_u64(f); }
+    t.pad = (int16_t)nd;            // (pad shares its word with link: from here on the record is finished)
     CountSink c; put_tree_piece<PRUNED>(c, a, t, xp);
     t.len = clamp_len(c.n);
     return c.n;
 }
-__device__ __forceinline__ void finish_row_rec(const EmitArgs& a, RowRec& r, bool need_g2h, bool need_lm, long long* len_g2h, long long* len_lm) {
+// A linked pruned-view row is the unpruned-view row of the same vertex (same text); only the leaf-map flag is its own.
+__device__ __forceinline__ void finish_row_rec(const EmitArgs& a, RowRec& r, bool need_g2h, bool need_lm, const RowRec* twin, bool twin_has_g2h, long long* len_g2h, long long* len_lm) {
     long long lg = 0, ll = 0;
-    if (need_g2h) { uint64_t f; int e; decimal_of(a.T, __longlong_as_double((long long)r.f), &f, &e); r.f = f; r.e = (int16_t)e; CountSink c; put_g2h_row(c, a, r); lg = c.n; }
+    const int link = r.link;
+    int nd = 0;
+    if (need_g2h) {
+        if (twin && twin_has_g2h && link >= 0) { r.f = twin[link].f; r.e = twin[link].e; nd = twin[link].pad; r.pad = (uint16_t)nd; lg = twin[link].len_g2h; if (lg == 0xffff) { CountSink c; put_g2h_row(c, a, r); lg = c.n; } }
+        else {
+            uint64_t f; int e; decimal_of(a.T, __longlong_as_double((long long)r.f), &f, &e); r.f = f; r.e = (int16_t)e; nd = e == kNoDigits ? 0 : dec_len_u64(f);
+            r.pad = (uint16_t)nd; CountSink c; put_g2h_row(c, a, r); lg = c.n;
+        }
+    }
     if (need_lm && (r.flags & RR_LEAFMAP)) { CountSink c; put_leafmap_row(c, a, r); ll = c.n; }
-    r.len_g2h = clamp_len(lg); r.len_lm = clamp_len(ll); *len_g2h = lg; *len_lm = ll;
+    r.len_g2h = clamp_len(lg); r.len_lm = clamp_len(ll); r.pad = (uint16_t)nd; *len_g2h = lg; *len_lm = ll;
 }
 
 }  // namespace sgp

@@ -273,25 +273,43 @@ SGP_HD void d2s_decimal(const MathTables& T, double v, uint64_t* f_out, int* e_o
             e = k + dk;
         }
     }
-    // strip trailing zeros
-    while (f >= 10) {
-        uint64_t qd = f / 10;
-        if (qd * 10 != f) break;
-        f = qd; ++e;
+    // strip trailing zeros (32-bit limbs: branch lengths rounded to 8 significant digits end in nine zeros, and a 64-bit division
+    // per stripped digit made this loop the most expensive part of the conversion on the device)
+    {
+        const uint64_t hi = f / 1000000000ull; uint32_t lo = (uint32_t)(f - hi * 1000000000ull);
+        if (hi == 0 || lo == 0) {
+            uint64_t rest = 0;
+            if (hi != 0) { rest = hi; e += 9; }          // f = hi x 10^9
+            else rest = lo;
+            if (rest <= 0xffffffffull) {
+                uint32_t x = (uint32_t)rest;
+                while (x >= 10u) { const uint32_t q = x / 10u; if (q * 10u != x) break; x = q; ++e; }
+                f = x;
+            } else {
+                f = rest;
+                while (f >= 10) { const uint64_t qd = f / 10; if (qd * 10 != f) break; f = qd; ++e; }
+            }
+        } else {
+            int k = 0; uint32_t p10 = 1;
+            while (true) { const uint32_t q = lo / 10u; if (q * 10u != lo) break; lo = q; ++k; p10 *= 10u; }
+            if (k) { f = hi * (uint64_t)(1000000000u / p10) + lo; e += k; }
+        }
     }
     *f_out = f; *e_out = e;
 }
 
+// Branch-free sums of comparisons: lanes of a warp print numbers of different lengths, and a comparison chain that compiles to
+// branches was 18 % of the instructions of the write kernels.
 SGP_HD int dec_len_u32(uint32_t v) {
-    return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
+    int n = 1 + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u);
+    if (v >= 100000u) n += (v >= 100000u) + (v >= 1000000u) + (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);
+    return n;
 }
-// (comparisons only: a division of a 64-bit value by a constant costs a dozen instructions on the device)
 SGP_HD int dec_len_u64(uint64_t f) {
     if (f <= 0xffffffffull) return dec_len_u32((uint32_t)f);
-    int n = 10;
-    uint64_t p = 10000000000ull;
-    while (n < 20 && f >= p) { ++n; p *= 10; }
-    return n;
+    const uint64_t hi = f / 1000000000ull;          // < 2^35
+    if (hi <= 0xffffffffull) return 9 + dec_len_u32((uint32_t)hi);
+    return 19 + (f >= 10000000000000000000ull);
 }
 SGP_HD int dec_len_i32(int v) { int n = 0; uint32_t u; if (v < 0) { n = 1; u = (uint32_t)(-(int64_t)v); } else u = (uint32_t)v; return n + dec_len_u32(u); }
 
@@ -372,13 +390,19 @@ template <class Sink> SGP_HD void put_i64(Sink& s, long long v) {
 // Layout part of java.lang.Double.toString for a finite v > 0 whose shortest decimal is f x 10^e (f < 10^18): plain notation
 // for 1e-3 <= v < 1e7, computerized scientific notation otherwise. One pass over the digits: digit i (0 = most significant)
 // lands at window position lead + i + (i >= split), everything else ('0', '.', padding zeros, exponent) is placed around them.
-template <class Sink> SGP_HD void put_double_digits(Sink& s, double v, uint64_t f, int e) {
+// n_hint > 0: the number of digits of f, if the caller knows it (then the size pass does no 64-bit arithmetic at all).
+template <class Sink> SGP_HD void put_double_digits(Sink& s, double v, uint64_t f, int e, int n_hint = 0) {
+    const bool plain = v >= 1e-3 && v < 1e7;
+    if (Sink::kCounts && n_hint > 0) {
+        const int n = n_hint, pe = n + e;
+        s.skip(plain ? (pe <= 0 ? 2 - pe + n : pe >= n ? pe + 2 : n + 1) : (n == 1 ? 3 : n + 1) + 1 + dec_len_i32(pe - 1));
+        return;
+    }
     const uint64_t hi64 = f / 1000000000ull;
     uint32_t l0 = (uint32_t)(f - hi64 * 1000000000ull);                  // low 9 digits
     uint32_t l1 = hi64 < 1000000000ull ? (uint32_t)hi64 : (uint32_t)(hi64 % 1000000000ull);
-    const int n = hi64 ? 9 + dec_len_u32(l1) : dec_len_u32(l0);
+    const int n = n_hint > 0 ? n_hint : (hi64 ? 9 + dec_len_u32(l1) : dec_len_u32(l0));
     const int pe = n + e;          // v = 0.DIGITS x 10^pe
-    const bool plain = v >= 1e-3 && v < 1e7;
     int lead, split, total, exp10 = 0;
     if (plain) {
         if (pe <= 0) { lead = 2 - pe; split = 99; total = lead + n; }        // 0.000DIGITS
@@ -394,7 +418,7 @@ template <class Sink> SGP_HD void put_double_digits(Sink& s, double v, uint64_t 
         for (int i = 0; i < 9 && pos >= 0; ++i, --pos) { const uint32_t q = l0 / 10u; w[lead + pos + (pos >= split ? 1 : 0)] = (char)('0' + (l0 - q * 10u)); l0 = q; }
         for (; pos >= 0; --pos) { const uint32_t q = l1 / 10u; w[lead + pos + (pos >= split ? 1 : 0)] = (char)('0' + (l1 - q * 10u)); l1 = q; }
         if (plain) {
-            if (pe <= 0) { w[0] = '0'; w[1] = '.'; for (int z = 2; z < lead; ++z) w[z] = '0'; }
+            if (pe <= 0) { w[0] = '0'; w[1] = '.'; if (lead > 2) w[2] = '0'; if (lead > 3) w[3] = '0'; for (int z = 4; z < lead; ++z) w[z] = '0'; }     // (1e-3 <= v: lead <= 4)
             else if (pe >= n) { for (int z = n; z < pe; ++z) w[z] = '0'; w[pe] = '.'; w[pe + 1] = '0'; }
             else w[pe] = '.';
         } else {

@@ -345,10 +345,11 @@ template <int INSTANCE> __global__ void __launch_bounds__(256) k_finish_records(
         if (mask & (1u << (view ? ST_PRUNED_TREE : ST_UNPRUNED_TREE))) {
             TreeRec* recs = a.trec + (size_t)view * a.aux_stride + off;
             const TreeRecX* recx = a.trecx ? a.trecx + (size_t)view * a.aux_stride + off : nullptr;
+            const TreeRec* twin = (view && (mask & (1u << ST_UNPRUNED_TREE))) ? a.trec + off : nullptr;       // finished in the previous round of this loop
             long long sum = 0;
             for (int k = lane; k < n; k += 32) {
                 TreeRec t; load_rec32(&t, recs + k);
-                sum += view ? finish_tree_rec<true>(a, t, recx + k) : finish_tree_rec<false>(a, t, recx + k);
+                sum += view ? finish_tree_rec<true>(a, t, recx + k, twin) : finish_tree_rec<false>(a, t, recx + k, nullptr);
                 load_rec32(recs + k, &t);
             }
             sum = warp_sum_ll(sum);
@@ -359,10 +360,12 @@ template <int INSTANCE> __global__ void __launch_bounds__(256) k_finish_records(
         const bool wg = mask & (1u << (view ? ST_PRUNED_G2H : ST_UNPRUNED_G2H)), wl = mask & (1u << (view ? ST_PRUNED_LEAFMAP : ST_UNPRUNED_LEAFMAP));
         if ((wg || wl) && a.rows) {
             RowRec* recs = a.rows + (size_t)view * a.aux_stride + off;
+            const bool twin_rows = view && (mask & ((1u << ST_UNPRUNED_G2H) | (1u << ST_UNPRUNED_LEAFMAP)));
+            const RowRec* twin = twin_rows ? a.rows + off : nullptr;
             long long sg = 0, sl = 0;
             for (int k = lane; k < n; k += 32) {
                 RowRec t; load_rec32(&t, recs + k);
-                long long lg, ll; finish_row_rec(a, t, wg, wl, &lg, &ll); sg += lg; sl += ll;
+                long long lg, ll; finish_row_rec(a, t, wg, wl, twin, (mask & (1u << ST_UNPRUNED_G2H)) != 0, &lg, &ll); sg += lg; sl += ll;
                 load_rec32(recs + k, &t);
             }
             sg = warp_sum_ll(sg); sl = warp_sum_ll(sl);
@@ -372,6 +375,7 @@ template <int INSTANCE> __global__ void __launch_bounds__(256) k_finish_records(
                 if (wl) sz[(size_t)(view ? ST_PRUNED_LEAFMAP : ST_UNPRUNED_LEAFMAP) * a.stride] = (unsigned long long)sl;
             }
         }
+        __syncwarp();          // the pruned view reads what other lanes finished in the unpruned view
     }
 }
 

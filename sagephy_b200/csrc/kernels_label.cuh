@@ -103,26 +103,36 @@ __device__ __forceinline__ void store_rec32(void* dst, const void* src) {
 // shared memory, int32 in global memory). k_finish_records (kernels_emit.cuh) turns the values into digits, measures every
 // piece and sums the stream sizes at full occupancy - inside the label kernel, which holds one warp per tree and few trees per SM,
 // that arithmetic took 60 ms per 10^6 C2 trees against 9 ms on its own.
+// rankU / rankB (optional, shared-memory kernel): per-vertex scratch that receives the vertex's position in the unpruned post-order /
+// breadth-first order, so that a pruned-view record can point at its unpruned twin (same digits, computed once).
 template <class I>
 __device__ __forceinline__ void make_records(const EmitArgs& E, long long goff, const Node* N, const I* ordU, const I* ordP, const I* bfsU, const I* bfsP,
-                                             int up, int nu, int root, int p_root) {
+                                             int up, int nu, int root, int p_root, I* rankU, I* rankB) {
     const int lane = threadIdx.x & 31;
     const unsigned mask = E.stream_mask;
-    if (mask & (1u << ST_UNPRUNED_TREE)) {
+    const bool tu = mask & (1u << ST_UNPRUNED_TREE), tp = (mask & (1u << ST_PRUNED_TREE)) && p_root >= 0;
+    const bool ru = E.rows && (mask & ((1u << ST_UNPRUNED_G2H) | (1u << ST_UNPRUNED_LEAFMAP))), rp = E.rows && (mask & ((1u << ST_PRUNED_G2H) | (1u << ST_PRUNED_LEAFMAP))) && p_root >= 0;
+    if (tu) {
         TreeRec* out = E.trec + goff; TreeRecX* outx = E.trecx ? E.trecx + goff : nullptr;
-        for (int k = lane; k < up; k += 32) { const int v = ordU[k]; const TreeRec t = raw_tree_rec<false>(E, N[v], v == root, outx ? outx + k : nullptr); store_rec32(out + k, &t); }
+        for (int k = lane; k < up; k += 32) {
+            const int v = ordU[k]; const TreeRec t = raw_tree_rec<false>(E, N[v], v == root, outx ? outx + k : nullptr, -1); store_rec32(out + k, &t);
+            if (rankU && tp) rankU[v] = (I)k;
+        }
     }
-    if ((mask & (1u << ST_PRUNED_TREE)) && p_root >= 0) {
-        TreeRec* out = E.trec + E.aux_stride + goff; TreeRecX* outx = E.trecx ? E.trecx + E.aux_stride + goff : nullptr;
-        for (int k = lane; k < nu; k += 32) { const int v = ordP[k]; const TreeRec t = raw_tree_rec<true>(E, N[v], v == p_root, outx ? outx + k : nullptr); store_rec32(out + k, &t); }
-    }
-    if (E.rows && (mask & ((1u << ST_UNPRUNED_G2H) | (1u << ST_UNPRUNED_LEAFMAP)))) {
+    if (ru) {
         RowRec* out = E.rows + goff;
-        for (int k = lane; k < up; k += 32) { const RowRec rr = raw_row_rec<false>(N[bfsU[k]]); store_rec32(out + k, &rr); }
+        for (int k = lane; k < up; k += 32) { const int v = bfsU[k]; const RowRec rr = raw_row_rec<false>(N[v], -1); store_rec32(out + k, &rr); if (rankB && rp) rankB[v] = (I)k; }
     }
-    if (E.rows && (mask & ((1u << ST_PRUNED_G2H) | (1u << ST_PRUNED_LEAFMAP))) && p_root >= 0) {
+    __syncwarp();
+    if (tp) {
+        TreeRec* out = E.trec + E.aux_stride + goff; TreeRecX* outx = E.trecx ? E.trecx + E.aux_stride + goff : nullptr;
+        for (int k = lane; k < nu; k += 32) {
+            const int v = ordP[k]; const TreeRec t = raw_tree_rec<true>(E, N[v], v == p_root, outx ? outx + k : nullptr, (rankU && tu) ? (int)rankU[v] : -1); store_rec32(out + k, &t);
+        }
+    }
+    if (rp) {
         RowRec* out = E.rows + E.aux_stride + goff;
-        for (int k = lane; k < nu; k += 32) { const RowRec rr = raw_row_rec<true>(N[bfsP[k]]); store_rec32(out + k, &rr); }
+        for (int k = lane; k < nu; k += 32) { const int v = bfsP[k]; const RowRec rr = raw_row_rec<true>(N[v], (rankB && ru) ? (int)rankB[v] : -1); store_rec32(out + k, &rr); }
     }
 }
 
@@ -296,7 +306,7 @@ __global__ void __launch_bounds__(32) k_label_prune_warp(LabelArgs a) {
                 for (int k = lane; k < up; k += 32) { gOrdU[k] = ordU[k]; gBfsU[k] = bfsU[k]; }
                 for (int k = lane; k < nu; k += 32) { gOrdP[k] = ordP[k]; gBfsP[k] = bfsP[k]; }
             }
-            make_records<int16_t>(a.E, goff, sN, ordU, ordP, bfsU, bfsP, up, nu, root, p_root);
+            make_records<int16_t>(a.E, goff, sN, ordU, ordP, bfsU, bfsP, up, nu, root, p_root, off, offS);      // (off / offS: dead work arrays)
             if (lane < EV_COUNT) { inf.cnt_u[lane] = s_cnt[0][lane]; inf.cnt_p[lane] = s_cnt[1][lane]; }
             if (lane == 0) {
                 inf.p_root = p_root; inf.n_u = up; inf.n_p = nu; inf.p_root_time = p_root >= 0 ? sN[p_root].abstime : 0.0;
@@ -343,7 +353,7 @@ __global__ void __launch_bounds__(128) k_records_from_nodes(LabelArgs a) {
     if (inf.status != REP_OK || inf.n_pool <= a.cap) return;
     const long long off = a.node_off[r];
     make_records<int32_t>(a.E, off, a.nodes + off, a.aux + off, a.aux + a.aux_stride + off, a.aux + 2 * a.aux_stride + off, a.aux + 3 * a.aux_stride + off,
-                          inf.n_u, inf.n_p, inf.root, inf.p_root);
+                          inf.n_u, inf.n_p, inf.root, inf.p_root, nullptr, nullptr);
 }
 
 }  // namespace sgp
