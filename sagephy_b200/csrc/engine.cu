@@ -436,7 +436,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     struct Sub {
         long long r0 = 0, n = 0, total_nodes = 0, aux_stride = 1; int max_pool = 0;
         DevBuf<unsigned long long> counter; DevBuf<long long> pool, node_off; DevBuf<int> max_pool_d;
-        DevBuf<Node> nodes; DevBuf<int32_t> aux; DevBuf<TreeRec> trec; DevBuf<TreeRecX> trecx; DevBuf<RowRec> rows;
+        DevBuf<Node> nodes; DevBuf<int32_t> aux; DevBuf<double> terms; DevBuf<TreeRec> trec; DevBuf<TreeRecX> trecx; DevBuf<RowRec> rows;
         cudaEvent_t ev_found = nullptr;
         ~Sub() { if (ev_found) cudaEventDestroy(ev_found); }
     };
@@ -620,6 +620,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         S.nodes.alloc((size_t)S.aux_stride); if (keep_nodes || !fast_bd) S.aux.alloc((size_t)S.aux_stride * 4);      // (the general build kernel uses them as scratch)
         if (want_trees) { S.trec.alloc((size_t)2 * S.aux_stride); if (cfg.app != 0) S.trecx.alloc((size_t)2 * S.aux_stride); }
         if (want_rows) S.rows.alloc((size_t)2 * S.aux_stride);
+        S.terms.alloc((size_t)(cfg.app == 0 ? 2 : 4) * S.aux_stride);
         g_alloc_stream = stA;
         size_t sp = span_begin(&tm.build_ms, stB);
         if (fast_bd) {
@@ -657,7 +658,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             LabelArgs a{}; a.n = S.n; a.info = info.p + S.r0; a.node_off = S.node_off.p; a.nodes = S.nodes.p; a.aux = S.aux.p; a.aux_stride = S.aux_stride; a.T = impl->T;
             a.host_root_time = cfg.host.vtime[cfg.host.root]; a.has_stem_override = cfg.has_stem_override; a.stem_override = cfg.stem_override;
             a.pool = S.pool.p;
-            a.write_nodes = keep_nodes ? 1 : 0; a.E = emit_args_for(S);
+            a.write_nodes = keep_nodes ? 1 : 0; a.E = emit_args_for(S); a.terms = S.terms.p; a.want_beneath = cfg.app == 0 ? 0 : 1;
             tm.launches += launch_label_prune(a, S.max_pool, impl->sm_count, stB);
             CK(cudaGetLastError());
         }
@@ -694,7 +695,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         span_end(sp, stB);
         if (piped) {        // the vertex records of this sub-batch are not needed any more: hand them back in stream order
             g_alloc_stream = stB;
-            S.nodes.alloc(0); S.aux.alloc(0); S.trec.alloc(0); S.trecx.alloc(0); S.rows.alloc(0);
+            S.nodes.alloc(0); S.aux.alloc(0); S.terms.alloc(0); S.trec.alloc(0); S.trecx.alloc(0); S.rows.alloc(0);
             g_alloc_stream = stA;
         }
     };

@@ -26,6 +26,7 @@ int launch_label_prune(LabelArgs a, int max_pool, int sm_count, cudaStream_t st)
         lo = cap;
         if (cap >= max_pool) break;
     }
+    if (lo > 0) { LabelArgs b = a; b.cap = lo; k_info_sums<<<(unsigned)((4 * a.n + 127) / 128), 128, 0, st>>>(b); ++launches; }
     if (max_pool > lo) {
         if (!a.aux || !a.write_nodes) throw SgpError("internal: oversized trees need the order arrays");
         a.cap = lo; k_label_prune<<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(a); ++launches;

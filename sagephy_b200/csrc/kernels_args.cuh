@@ -122,6 +122,7 @@ struct LabelArgs {
     int has_stem_override; double stem_override;    // HostTreeGen -stem (HostTreeGen.java:74-79)
     const long long* pool;                  // vertices per replicate (0: failed)
     int min_pool, cap;                      // warp kernel: size class (min_pool, cap]; thread kernel: trees above cap
+    double* terms; int want_beneath;        // [4][aux_stride] terms of the getInfo sums in breadth-first order: total U, total P, beneath-stem U, P (the last two if want_beneath)
     int write_nodes;                        // write the labelled vertex records and the order arrays back (chained stages, oversized trees)
     EmitArgs E;                             // formats and the record arrays the kernel fills in
 };

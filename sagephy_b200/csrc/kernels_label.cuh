@@ -93,6 +93,23 @@ constexpr int kLabelBytesPerNode = (int)sizeof(Node) + 9 * (int)sizeof(int16_t);
 constexpr int kLabelExtraBytes = 16;
 __host__ __device__ inline size_t label_smem_bytes(int cap) { return (size_t)cap * kLabelBytesPerNode + kLabelExtraBytes; }
 
+// ---- bulk asynchronous copy global -> shared (TMA) with an mbarrier that counts the bytes as they land ----------------------------
+__device__ __forceinline__ void mbar_init(uint32_t mbar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* src, uint32_t bytes) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory"); }
+
 __device__ __forceinline__ void store_rec32(void* dst, const void* src) {
     const uint4* s4 = reinterpret_cast<const uint4*>(src); uint4* d4 = reinterpret_cast<uint4*>(dst);
     d4[0] = s4[0]; d4[1] = s4[1];
@@ -148,7 +165,7 @@ __device__ __forceinline__ void make_records(const EmitArgs& E, long long goff, 
 __global__ void __launch_bounds__(32) k_label_prune_warp(LabelArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int32_t s_cnt[2][EV_COUNT];
-    __shared__ double s_sum[2][2];
+    __shared__ __align__(8) unsigned long long s_mbar;
     const int cap = a.cap;
     Node* sN = reinterpret_cast<Node*>(smem);
     int16_t* bfsU = reinterpret_cast<int16_t*>(smem + (size_t)cap * sizeof(Node));
@@ -156,25 +173,41 @@ __global__ void __launch_bounds__(32) k_label_prune_warp(LabelArgs a) {
     int16_t *sz = bfsP + cap, *ns = sz + cap, *off = ns + cap, *offS = off + cap, *lvl = offS + cap;     // lvl: cap + 2 entries
     const int lane = threadIdx.x;
     const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar), sN_addr = (uint32_t)__cvta_generic_to_shared(sN);
+    if (lane == 0) mbar_init(mbar, 1);
+    __syncwarp();
+    uint32_t phase = 0;
     // every trip looks at 32 consecutive replicates and works through those of this launch's size class
     for (long long base = (long long)blockIdx.x * 32; base < a.n; base += (long long)gridDim.x * 32) {
-      int np_lane = 0;
-      if (base + lane < a.n) np_lane = (int)a.pool[base + lane];          // 0 for failed replicates
+      int np_lane = 0; long long goff_lane = 0;
+      if (base + lane < a.n) { np_lane = (int)a.pool[base + lane]; goff_lane = a.node_off[base + lane]; }         // 0 for failed replicates
       unsigned todo = __ballot_sync(0xffffffffu, np_lane > a.min_pool && np_lane <= a.cap);
       while (todo) {
         const int b = __ffs(todo) - 1; todo &= todo - 1;
         const long long r = base + b;
         const int n_pool = __shfl_sync(0xffffffffu, np_lane, b);
         RepInfo& inf = a.info[r];
-        const long long goff = a.node_off[r];
-        const int root = inf.root;
+        const long long goff = __shfl_sync(0xffffffffu, goff_lane, b);
         {
-            const uint4* src = reinterpret_cast<const uint4*>(a.nodes + goff); uint4* dst = reinterpret_cast<uint4*>(sN);
-            const int nq = n_pool * (int)(sizeof(Node) / 16);
-            for (int i = lane; i < nq; i += 32) dst[i] = src[i];
+            // The tree's records arrive as ONE bulk copy (TMA) instead of a loop of 16-byte loads per lane; the next tree of this
+            // group is pulled into L2 meanwhile. Shared memory was last touched through the generic proxy: fence, then copy.
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t bytes = (uint32_t)n_pool * (uint32_t)sizeof(Node);
+                mbar_expect_tx(mbar, bytes);
+                bulk_load(sN_addr, a.nodes + goff, bytes, mbar);
+            }
+            if (todo) {
+                const int nb = __ffs(todo) - 1;
+                const long long ngoff = __shfl_sync(0xffffffffu, goff_lane, nb); const int nnp = __shfl_sync(0xffffffffu, np_lane, nb);
+                if (lane == 0) prefetch_l2_bulk(a.nodes + ngoff, (uint32_t)nnp * (uint32_t)sizeof(Node));
+            }
             for (int i = lane; i < 2 * EV_COUNT; i += 32) (&s_cnt[0][0])[i] = 0;
-            if (lane == 0) { bfsU[0] = (int16_t)root; lvl[0] = 0; off[root] = 0; offS[root] = 0; }
         }
+        const int root = inf.root;
+        if (lane == 0) { bfsU[0] = (int16_t)root; lvl[0] = 0; off[root] = 0; offS[root] = 0; }
+        mbar_wait(mbar, phase); phase ^= 1u;
         __syncwarp();
         // ---- 1. breadth-first order, levels
         int D = 0, up;
@@ -282,20 +315,21 @@ __global__ void __launch_bounds__(32) k_label_prune_warp(LabelArgs a) {
             }
         }
         __syncwarp();
-        // ---- 5. getInfo sums in breadth-first order (GuestTreeInHostTreeCreator.java:431-511)
-        if (lane < 2) {
-            const bool pruned = lane == 1;
-            const int16_t* q = pruned ? bfsP : bfsU; const int cnt = pruned ? nu : up;
-            double tot = 0.0, ben = 0.0;
-            for (int k = 0; k < cnt; ++k) {
-                const Node& x = sN[q[k]];
-                const double len = pruned ? x.p_bl : x.bl;
-                tot = XADD(tot, len);
-                ben = XADD(ben, fmax(fmin(XSUB(a.host_root_time, x.abstime), len), 0.0));
+        // ---- 5. the terms of the getInfo sums in breadth-first order (GuestTreeInHostTreeCreator.java:431-511). The sums themselves are
+        // order-dependent floating-point additions, i.e. serial: k_info_sums adds them up with a thread per sum and full occupancy
+        // (here they kept one or two lanes of the warp busy for 44 % of the kernel's instructions).
+        {
+            double* tU = a.terms + goff; double* tP = a.terms + a.aux_stride + goff;
+            double* bU = a.terms + 2 * a.aux_stride + goff; double* bP = a.terms + 3 * a.aux_stride + goff;
+            for (int k = lane; k < up; k += 32) {
+                const Node& x = sN[bfsU[k]]; tU[k] = x.bl;
+                if (a.want_beneath) bU[k] = fmax(fmin(XSUB(a.host_root_time, x.abstime), x.bl), 0.0);
             }
-            s_sum[lane][0] = tot; s_sum[lane][1] = ben;
+            for (int k = lane; k < nu; k += 32) {
+                const Node& x = sN[bfsP[k]]; tP[k] = x.p_bl;
+                if (a.want_beneath) bP[k] = fmax(fmin(XSUB(a.host_root_time, x.abstime), x.p_bl), 0.0);
+            }
         }
-        __syncwarp();
         {
             if (a.write_nodes) {
                 uint4* dst = reinterpret_cast<uint4*>(a.nodes + goff); const uint4* src = reinterpret_cast<const uint4*>(sN);
@@ -311,7 +345,6 @@ __global__ void __launch_bounds__(32) k_label_prune_warp(LabelArgs a) {
             if (lane == 0) {
                 inf.p_root = p_root; inf.n_u = up; inf.n_p = nu; inf.p_root_time = p_root >= 0 ? sN[p_root].abstime : 0.0;
                 inf.root_gtree_u = sN[root].gtree; inf.root_gtree_p = sN[p_root >= 0 ? p_root : root].gtree;
-                inf.total_u = s_sum[0][0]; inf.beneath_u = s_sum[0][1]; inf.total_p = s_sum[1][0]; inf.beneath_p = s_sum[1][1];
             }
         }
         __syncwarp();
@@ -343,6 +376,21 @@ __global__ void __launch_bounds__(128) k_label_prune(LabelArgs a) {
     label_bfs<int32_t>(N, bfsP, p_root, true, a.host_root_time, inf.cnt_p, tot, ben);
     inf.total_p = tot; inf.beneath_p = ben;
     for (int k = 0; k < up; ++k) { Node& x = N[ordU[k]]; x.flags |= x.pad0; x.pad0 = 0; }
+}
+
+// The getInfo sums of the trees the warp kernel labelled: one thread per (replicate, sum), terms read in breadth-first order.
+__global__ void __launch_bounds__(128) k_info_sums(LabelArgs a) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = t >> 2; const int which = (int)(t & 3);
+    if (r >= a.n) return;
+    RepInfo& inf = a.info[r];
+    if (inf.status != REP_OK || inf.n_pool > a.cap) return;          // (larger trees: k_label_prune has summed them itself)
+    if (which >= 2 && !a.want_beneath) { if (which == 2) inf.beneath_u = 0.0; else inf.beneath_p = 0.0; return; }
+    const double* term = a.terms + (size_t)which * a.aux_stride + a.node_off[r];
+    const int cnt = (which & 1) ? (inf.p_root >= 0 ? inf.n_p : 0) : inf.n_u;
+    double sum = 0.0;
+    for (int k = 0; k < cnt; ++k) sum = XADD(sum, term[k]);
+    if (which == 0) inf.total_u = sum; else if (which == 1) inf.total_p = sum; else if (which == 2) inf.beneath_u = sum; else inf.beneath_p = sum;
 }
 
 // Emission records of the trees the thread kernel labelled (warp per tree, vertex records and orders in global memory).
