@@ -15,7 +15,8 @@ enum Ev : uint8_t {
 };
 enum Prn : uint8_t { PR_UNPRUNABLE = 0, PR_PRUNABLE = 1, PR_COLLAPSABLE = 2, PR_UNKNOWN = 3 };
 
-enum NodeFlags : uint8_t { NF_LEFT_U = 1, NF_LEFT_P = 2, NF_IN_PRUNED = 4 };
+enum NodeFlags : uint8_t { NF_LEFT_U = 1, NF_LEFT_P = 2, NF_IN_PRUNED = 4,
+                           NF_RIGHT_CHILD = 8 /* set by the birth-death build kernel: the label kernels enter the vertex as its parent's right child */ };
 
 // One guest-tree vertex. 80 bytes, 16-byte aligned (five 16-byte vector accesses).
 struct __align__(16) Node {

@@ -14,5 +14,5 @@ void launch_bd_find(const BdArgs& a, int blocks, int blocks_per_sm, cudaStream_t
         case 3: k_bd_find_single<false, 1, false, 4><<<scaled(blocks_per_sm), kBdFindThreads, 0, st>>>(a); break;
     }
 }
-void launch_bd_build(const BdArgs& a, int blocks, cudaStream_t st) { k_bd_build<<<blocks, 256, 0, st>>>(a); }
+void launch_bd_build(const BdArgs& a, int blocks, cudaStream_t st) { k_bd_build<<<blocks, kBdBuildThreads, 0, st>>>(a); }
 }  // namespace sgp

@@ -230,55 +230,77 @@ __global__ void __launch_bounds__(kBdFindThreads, MINBLOCKS) k_bd_find_single(Bd
     }
 }
 
-// Build pass: regenerates the accepted attempt depth-first straight into the arena (no scratch).
-__global__ void __launch_bounds__(256) k_bd_build(BdArgs a) {
+// Build pass: regenerates the accepted attempt depth-first straight into the arena (no scratch). Thread per replicate; the 32
+// records a warp produces per step pass through shared memory so that they leave as 16-byte stores in which five consecutive
+// lanes cover one record (whole sectors) - a lane storing its own 80-byte record made every store instruction touch 32 sectors
+// (the kernel sat on lg_throttle). A right child is not linked into its parent here: that 4-byte write to a record stored
+// hundreds of steps earlier came back from DRAM as a read-modify-write (29 KB written + 8 KB read per 16 KB tree); the record
+// carries NF_RIGHT_CHILD instead and the label kernels, which hold the tree in shared memory, enter the link.
+constexpr int kBdBuildThreads = 256;
+__global__ void __launch_bounds__(kBdBuildThreads) k_bd_build(BdArgs a) {
     __shared__ double2 s_logtab[128];
+    __shared__ __align__(16) Node s_node[kBdBuildThreads / 32][32];
+    __shared__ Node* s_dst[kBdBuildThreads / 32][32];
     load_log_table(s_logtab);
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.n) return;
-    RepInfo& inf = a.info[r];
-    if (inf.status != REP_OK) return;
-    Node* N = a.nodes + a.node_off[r];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    bool active = r < a.n && a.info[r < a.n ? r : 0].status == REP_OK;
+    RepInfo* inf = active ? &a.info[r] : nullptr;
+    Node* N = active ? a.nodes + a.node_off[r] : nullptr;
     const unsigned long long gid = (unsigned long long)(a.rep_base + r);
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32), rep_lo = (uint32_t)gid, rep_hi = (uint32_t)(gid >> 32);
+    const uint32_t acc = active ? inf->acc_attempt : 0u;
     const BdConsts C = bd_consts(a.P);
     double st_time[kBdStack]; int8_t st_arc[kBdStack]; int32_t st_par[kBdStack];   // parent index; bit 31 set = right child
     int sp = 0; uint32_t vidx = 0;
-    st_time[0] = a.H.tip; st_arc[0] = (int8_t)a.H.root; st_par[0] = -1; sp = 1;
-    while (sp > 0) {
-        --sp;
-        const double start = st_time[sp]; const int X = st_arc[sp]; const int32_t pw = st_par[sp];
-        const U4 w = philox4x32_10(vidx, inf.acc_attempt, rep_lo, rep_hi, k0, k1);
-        const BdVertex v = a.H.nV == 1 ? bd_vertex_single(C, start, w, s_logtab) : bd_vertex(C, a.H, X, start, w, s_logtab);
-        const int me = (int)vidx++;
-        const bool internal = v.event == EV_DUPLICATION || v.event == EV_SPECIATION;
-        // the record is assembled in registers and leaves as five 16-byte stores (field-wise stores saturate the load/store unit:
-        // every one of them touches 32 different sectors per warp)
-        Node nd;
-        nd.abstime = v.et;
-        nd.bl = v.boundary ? round_sig(a.T, start - v.et, 8) : v.bt;       // GuestTreeInHostTreeCreator.java:385 vs :378
-        if (me == 0 && nd.bl <= 1.0e-32) nd.bl = 0.0;
-        nd.sigma = X; nd.left = internal ? me + 1 : -1; nd.right = -1; nd.from_arc = -1; nd.to_arc = -1; nd.number = -1;       // depth-first: the left child is the next vertex
-        nd.p_bl = 0.0; nd.p_left = -1; nd.p_right = -1; nd.event = v.event; nd.prun = PR_UNKNOWN; nd.flags = 0; nd.pad0 = 0; nd.gtree = 0;
-        nd.from_g = -1; nd.to_g = -1; nd.chain_u = 0; nd.chain_p = 0; nd.pad1 = 0;
-        int ep = a.H.v2e[X];
-        if (!v.boundary) { while (a.H.ep_up[ep] < v.et) ++ep; }
-        nd.epoch = ep;
-        nd.parent = pw == -1 ? -1 : (pw & 0x7fffffff);
-        {
-            const uint4* src = reinterpret_cast<const uint4*>(&nd); uint4* dst = reinterpret_cast<uint4*>(&N[me]);
+    if (active) { st_time[0] = a.H.tip; st_arc[0] = (int8_t)a.H.root; st_par[0] = -1; sp = 1; }
+    while (__any_sync(0xffffffffu, sp > 0)) {
+        Node* dst = nullptr;
+        if (sp > 0) {
+            --sp;
+            const double start = st_time[sp]; const int X = st_arc[sp]; const int32_t pw = st_par[sp];
+            const U4 w = philox4x32_10(vidx, acc, rep_lo, rep_hi, k0, k1);
+            const BdVertex v = a.H.nV == 1 ? bd_vertex_single(C, start, w, s_logtab) : bd_vertex(C, a.H, X, start, w, s_logtab);
+            const int me = (int)vidx++;
+            const bool internal = v.event == EV_DUPLICATION || v.event == EV_SPECIATION;
+            Node nd;
+            nd.abstime = v.et;
+            nd.bl = v.boundary ? round_sig(a.T, start - v.et, 8) : v.bt;       // GuestTreeInHostTreeCreator.java:385 vs :378
+            if (me == 0 && nd.bl <= 1.0e-32) nd.bl = 0.0;
+            nd.sigma = X; nd.left = internal ? me + 1 : -1; nd.right = -1; nd.from_arc = -1; nd.to_arc = -1; nd.number = -1;       // depth-first: the left child is the next vertex
+            nd.p_bl = 0.0; nd.p_left = -1; nd.p_right = -1; nd.event = v.event; nd.prun = PR_UNKNOWN; nd.flags = (pw != -1 && pw < 0) ? NF_RIGHT_CHILD : 0; nd.pad0 = 0; nd.gtree = 0;
+            nd.from_g = -1; nd.to_g = -1; nd.chain_u = 0; nd.chain_p = 0; nd.pad1 = 0;
+            int ep = a.H.v2e[X];
+            if (!v.boundary) { while (a.H.ep_up[ep] < v.et) ++ep; }
+            nd.epoch = ep;
+            nd.parent = pw == -1 ? -1 : (pw & 0x7fffffff);
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(&nd); uint4* stg = reinterpret_cast<uint4*>(&s_node[wib][lane]);
 #pragma unroll
-            for (int q = 0; q < (int)(sizeof(Node) / 16); ++q) dst[q] = src[q];
+                for (int q = 0; q < (int)(sizeof(Node) / 16); ++q) stg[q] = src[q];
+            }
+            dst = &N[me];
+            if (internal) {
+                const bool dup = v.event == EV_DUPLICATION;
+                st_time[sp] = v.et; st_arc[sp] = (int8_t)(dup ? X : a.H.right[X]); st_par[sp] = (int32_t)(0x80000000u | (uint32_t)me);
+                st_time[sp + 1] = v.et; st_arc[sp + 1] = (int8_t)(dup ? X : a.H.left[X]); st_par[sp + 1] = me; sp += 2;
+            }
         }
-        if (pw != -1 && pw < 0) N[pw & 0x7fffffff].right = me;             // right children are linked when they are created
-        if (internal) {
-            const bool dup = v.event == EV_DUPLICATION;
-            st_time[sp] = v.et; st_arc[sp] = (int8_t)(dup ? X : a.H.right[X]); st_par[sp] = (int32_t)(0x80000000u | (uint32_t)me);
-            st_time[sp + 1] = v.et; st_arc[sp + 1] = (int8_t)(dup ? X : a.H.left[X]); st_par[sp + 1] = me; sp += 2;
+        s_dst[wib][lane] = dst;
+        __syncwarp();
+        // 32 records x 5 quarters = 160 16-byte items, item i = quarter i % 5 of the record of lane i / 5
+#pragma unroll
+        for (int j = 0; j < (int)(sizeof(Node) / 16); ++j) {
+            const int item = lane + 32 * j, slot = item / 5, q = item - slot * 5;
+            Node* d = s_dst[wib][slot];
+            if (d) reinterpret_cast<uint4*>(d)[q] = reinterpret_cast<const uint4*>(&s_node[wib][slot])[q];
         }
+        __syncwarp();
     }
-    inf.root = 0;
-    if ((int)vidx != inf.n_pool) inf.status = REP_MODEL_ERROR;
+    if (active) {
+        inf->root = 0;
+        if ((int)vidx != inf->n_pool) inf->status = REP_MODEL_ERROR;
+    }
 }
 
 }  // namespace sgp
