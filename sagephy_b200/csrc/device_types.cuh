@@ -16,7 +16,8 @@ enum Ev : uint8_t {
 enum Prn : uint8_t { PR_UNPRUNABLE = 0, PR_PRUNABLE = 1, PR_COLLAPSABLE = 2, PR_UNKNOWN = 3 };
 
 enum NodeFlags : uint8_t { NF_LEFT_U = 1, NF_LEFT_P = 2, NF_IN_PRUNED = 4,
-                           NF_RIGHT_CHILD = 8 /* set by the birth-death build kernel: the label kernels enter the vertex as its parent's right child */ };
+                           NF_RIGHT_CHILD = 8 /* set by the birth-death build kernel: the label kernels enter the vertex as its parent's right child */,
+                           NF_DETACHED = 16 /* general engine, find pass: the vertex hangs below a replaced lineage (not part of the final tree) */ };
 
 // One guest-tree vertex. 80 bytes, 16-byte aligned (five 16-byte vector accesses).
 struct __align__(16) Node {
@@ -103,6 +104,7 @@ enum RepStatus : int32_t { REP_OK = 0, REP_MAX_ATTEMPTS = 1, REP_NODE_OVERFLOW =
 // Read-only host-tree tables in device memory.
 struct DevHost {
     int32_t nV, nE, root, nLeaves, max_arcs, has_lca;
+    int32_t ep_sorted;       // the upper epoch times increase with the epoch number (always, unless the host tree's times are inconsistent)
     const int32_t *parent, *left, *right, *host_tag, *v2e, *ep_off, *ep_arcs, *leaf_rank;
     const double *vtime, *ep_lo, *ep_mid, *ep_up, *lca_time;
 };

@@ -50,6 +50,7 @@ struct HostOnDevice {
         std::vector<double> et(3 * (size_t)h.nE); for (int e = 0; e < h.nE; ++e) { et[3 * e] = h.ep_lo[e]; et[3 * e + 1] = h.ep_mid[e]; et[3 * e + 2] = h.ep_up[e]; }
         ep_times.upload(et);
         view.nV = h.nV; view.nE = h.nE; view.root = h.root; view.nLeaves = h.nLeaves; view.max_arcs = h.max_arcs; view.has_lca = !h.lca_time.empty();
+        view.ep_sorted = 1; for (int e = 1; e < h.nE; ++e) if (!(h.ep_up[e] >= h.ep_up[e - 1])) view.ep_sorted = 0;
         view.parent = parent.p; view.left = left.p; view.right = right.p; view.host_tag = host_tag.p; view.v2e = v2e.p; view.ep_off = ep_off.p;
         view.ep_arcs = ep_arcs.p; view.leaf_rank = leaf_rank.p; view.vtime = vtime.p; view.ep_lo = ep_lo.p; view.ep_mid = ep_mid.p; view.ep_up = ep_up.p;
         view.lca_time = lca_time.p;

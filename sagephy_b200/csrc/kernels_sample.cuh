@@ -22,9 +22,9 @@ template <bool DOMAIN, class RNG, class ARGS>
 __device__ __forceinline__ void engine_resolve(EngineState<DOMAIN>& S, RNG& rng, const ARGS& a, const DomainEnv& E, SimWork& W) {
     if constexpr (DOMAIN) coop_resolve_domain(S, rng, a.P, E, W); else coop_resolve_transfers(S, rng, a.P, a.H, W);
 }
-template <bool DOMAIN, class RNG, class ARGS>
+template <bool DOMAIN, bool COUNT, class RNG, class ARGS>
 __device__ __forceinline__ int engine_step(EngineState<DOMAIN>& S, RNG& rng, const ARGS& a, const DomainEnv& E, SimWork& W) {
-    if constexpr (DOMAIN) return domain_step(S, rng, a.P, E, a.T, W); else return sim_step(S, rng, a.P, a.H, a.T, W);
+    if constexpr (DOMAIN) return domain_step(S, rng, a.P, E, a.T, W); else return sim_step<COUNT>(S, rng, a.P, a.H, a.T, W);
 }
 
 template <bool REPLAY, bool DOMAIN>
@@ -63,6 +63,18 @@ __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
                 attempts = 0; verts = 0; have = true; S.stage = -1;
             }
         }
+        if constexpr (!DOMAIN) {
+            // the per-host-leaf tallies of an attempt start at zero: cleared by the whole warp for every lane that starts one
+            if (a.per_leaf_check) {
+                unsigned starting = __ballot_sync(0xffffffffu, have && S.stage < 0 && attempts <= a.P.max_attempts);
+                while (starting) {
+                    const int l = __ffs(starting) - 1; starting &= starting - 1;
+                    int32_t* cnt = reinterpret_cast<int32_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(W.leaf_cnt), l));
+                    for (int i = threadIdx.x & 31; i < a.H.nLeaves; i += 32) cnt[i] = 0;
+                }
+                __syncwarp();
+            }
+        }
         if (have && S.stage < 0) {          // start the next attempt of this replicate (GuestTreeMachina.java:81-98)
             if (attempts > a.P.max_attempts) { inf.status = REP_MAX_ATTEMPTS; inf.attempts = attempts; inf.vertices_sampled = verts; a.info[r] = inf; have = false; }
             else if (REPLAY) { pos = mt.position(); engine_begin<DOMAIN>(S, mt, a, E); }
@@ -71,7 +83,7 @@ __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
         if (!__ballot_sync(0xffffffffu, have || !exhausted)) break;
         if (REPLAY) engine_resolve<DOMAIN>(S, mt, a, E, W); else engine_resolve<DOMAIN>(S, ph, a, E, W);
         if (have && S.stage >= 0) {
-            const int st = REPLAY ? engine_step<DOMAIN>(S, mt, a, E, W) : engine_step<DOMAIN>(S, ph, a, E, W);
+            const int st = REPLAY ? engine_step<DOMAIN, true>(S, mt, a, E, W) : engine_step<DOMAIN, true>(S, ph, a, E, W);
             if (st >= 0) {
                 verts += (uint64_t)S.n;
                 const int n = S.n, root = S.root;
@@ -86,9 +98,9 @@ __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
                     } else { inf.status = st; inf.attempts = attempts; inf.vertices_sampled = verts; a.info[r] = inf; have = false; }
                 } else {
                     ++attempts;
-                    int sampled = 0;
-                    const bool ok = DOMAIN ? attempt_ok_domain(a.P, a.H, E, W, root, inf.exact, a.max_gene_nv, a.per_leaf_check != 0, a.all_genes != 0, &sampled)
-                                           : attempt_ok(a.P, a.H, W, root, inf.exact, &sampled);
+                    int sampled = 0; bool ok;
+                    if constexpr (DOMAIN) ok = attempt_ok_domain(a.P, a.H, E, W, root, inf.exact, a.max_gene_nv, a.per_leaf_check != 0, a.all_genes != 0, &sampled);
+                    else { ok = attempt_ok_counted(a.P, S, W, inf.exact); sampled = S.sampled; }
                     if (ok) {
                         inf.status = REP_OK; inf.n_pool = n; inf.sampled_leaves = sampled;
                         if (REPLAY) { inf.acc_attempt = (uint32_t)pos; inf.acc_hi = (uint32_t)(pos >> 32); } else { inf.acc_attempt = (uint32_t)(attempts - 1); inf.acc_hi = 0; }
@@ -150,7 +162,7 @@ __global__ void __launch_bounds__(128) k_build_general(BuildArgs a) {
         if (!__ballot_sync(0xffffffffu, have || !exhausted)) break;
         if (REPLAY) engine_resolve<DOMAIN>(S, mt, a, E, W); else engine_resolve<DOMAIN>(S, ph, a, E, W);
         if (have) {
-            const int rc = REPLAY ? engine_step<DOMAIN>(S, mt, a, E, W) : engine_step<DOMAIN>(S, ph, a, E, W);
+            const int rc = REPLAY ? engine_step<DOMAIN, false>(S, mt, a, E, W) : engine_step<DOMAIN, false>(S, ph, a, E, W);
             if (rc >= 0) {
                 RepInfo& inf = a.info[r];
                 if (rc != REP_OK || S.n != inf.n_pool) inf.status = REP_MODEL_ERROR; else inf.root = S.root;

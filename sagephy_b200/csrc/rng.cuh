@@ -97,6 +97,9 @@ struct PhiloxStream {
         return val;
     }
     SGP_HD void begin_attempt(uint32_t a) { attempt = a; block = 0; have = 0; }
+    // drops the unread words of the current block: the next draw starts a fresh block. The general engine does this before every
+    // vertex, so that all lanes of a warp refill at the same point of the step instead of wherever their earlier draws left them.
+    SGP_HD void align() { have = 0; }
     SGP_HD uint64_t position() const { return 0; }
 };
 
@@ -166,6 +169,7 @@ struct MtStream {
     int idx;
     uint64_t drawn;    // words drawn so far (lets the build pass fast-forward to the accepted attempt)
     SGP_HD uint32_t& at(int i) { return mt[(size_t)i * stride]; }
+    SGP_HD void align() {}      // (replay: the stream is the reference's, word for word)
 
     SGP_HD_NOINL void seed(const uint32_t key[4]) {
         at(0) = 19650218u;
