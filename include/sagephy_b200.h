@@ -143,6 +143,20 @@ sgp_status sgp_batches_write_files_layout(sgp_batch* const* shards, int n_shards
 sgp_status sgp_relax_run_on_batch(sgp_context* ctx, sgp_batch* src, int which_tree, int argc, const char* const* argv,
                                   const sgp_batch_opts* opts, sgp_batch** out);
 
+/* Chained stage: DomainTreeGen over a forest of gene trees that are the pruned trees [first_tree,
+ * first_tree + n_trees) of a GuestTreeGen batch still resident on the device - the in-memory equivalent of writing those
+ * <prefix>_<i>.pruned.tree files into a directory and launching `java ... DomainTreeGen <species tree> <that directory> ...`
+ * (apps/SaGePhy/DomainTreeGenParameters.java:136-151 reads every file of the directory, io/NewickTreeReader.java:158-296 numbers the
+ * vertices in post-order and captures HOST=, io/PrIMENewickTreeVerifier.java:237-270 turns lengths into vertex times, one
+ * RBTreeEpochDiscretiser per gene tree: apps/SaGePhy/DomainTreeInHostTreeCreator.java:122-130). The vertex ids, lengths, names and
+ * HOST tags are read from the kept vertex records by the ingest kernels (~25 bytes per vertex cross PCIe; no Newick text is written
+ * or parsed); the epoch tables of the forest are then built like those of any host tree. Gene tree i is named
+ * "<out prefix of src>_<name_first_index + i>.pruned.tree" (the file SGP_LAYOUT_PER_REPLICATE writes for it) and the forest is
+ * ordered by name, as a directory listing is. argv is DomainTreeGen's own argv; its <guest tree directory> positional is only
+ * echoed in the "Arguments:" line. `src` must come from sgp_app_run("GuestTreeGen" | "HostTreeGen", ...) with SGP_FLAG_KEEP_TREES. */
+sgp_status sgp_domain_run_on_batch(sgp_context* ctx, sgp_batch* src, int64_t first_tree, int64_t n_trees, int64_t name_first_index,
+                                   int argc, const char* const* argv, const sgp_batch_opts* opts, sgp_batch** out);
+
 /* Batch accessors. Stream s is the concatenation over replicates, replicate i occupying bytes [offsets[i], offsets[i+1]). */
 int64_t sgp_batch_n(const sgp_batch* b);
 const char* sgp_batch_stream_data(sgp_batch* b, int stream);             /* host pointer (pinned), copies from HBM on first use */

@@ -33,7 +33,7 @@ STATUS_OK, STATUS_USAGE = 0, 6
 
 # every symbol include/sagephy_b200.h declares (checked by the CPU test-suite)
 EXPORTED_SYMBOLS = (
-    "sgp_context_create", "sgp_context_destroy", "sgp_last_error", "sgp_app_run", "sgp_multi_create", "sgp_multi_size", "sgp_multi_context", "sgp_multi_destroy", "sgp_app_run_multi", "sgp_batches_write_files_layout", "sgp_relax_run_on_batch", "sgp_batch_n", "sgp_batch_stream_data",
+    "sgp_context_create", "sgp_context_destroy", "sgp_last_error", "sgp_app_run", "sgp_multi_create", "sgp_multi_size", "sgp_multi_context", "sgp_multi_destroy", "sgp_app_run_multi", "sgp_batches_write_files_layout", "sgp_relax_run_on_batch", "sgp_domain_run_on_batch", "sgp_batch_n", "sgp_batch_stream_data",
     "sgp_batch_stream_device_data", "sgp_batch_stream_offsets", "sgp_batch_copy_stream", "sgp_batch_copy_offsets", "sgp_batch_copy_stream_async", "sgp_batch_copy_offsets_async", "sgp_context_wait_copies", "sgp_batch_stream_mask", "sgp_batch_values", "sgp_batch_stream_bytes", "sgp_batch_stream_suffix",
     "sgp_batch_status", "sgp_batch_attempts", "sgp_batch_sampled_leaves", "sgp_batch_root_times", "sgp_batch_total_times",
     "sgp_batch_event_counts", "sgp_batch_stdout", "sgp_batch_stderr", "sgp_batch_out_prefix", "sgp_batch_summary",
@@ -80,6 +80,7 @@ def load_library() -> C.CDLL:
     L.sgp_app_run_multi.argtypes = [vp, cp, C.c_int, C.POINTER(cp), C.POINTER(BatchOpts), C.POINTER(vp), C.POINTER(SummaryStruct)]; L.sgp_app_run_multi.restype = C.c_int
     L.sgp_batches_write_files_layout.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int64]; L.sgp_batches_write_files_layout.restype = C.c_int
     L.sgp_relax_run_on_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(cp), C.POINTER(BatchOpts), C.POINTER(vp)]; L.sgp_relax_run_on_batch.restype = C.c_int
+    L.sgp_domain_run_on_batch.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(cp), C.POINTER(BatchOpts), C.POINTER(vp)]; L.sgp_domain_run_on_batch.restype = C.c_int
     L.sgp_batch_n.argtypes = [vp]; L.sgp_batch_n.restype = i64
     L.sgp_batch_stream_data.argtypes = [vp, C.c_int]; L.sgp_batch_stream_data.restype = vp
     L.sgp_batch_stream_device_data.argtypes = [vp, C.c_int]; L.sgp_batch_stream_device_data.restype = vp
@@ -393,6 +394,20 @@ class Context:
         b = Batch(self._lib, h, rc)
         if check and rc not in (STATUS_OK, STATUS_USAGE):
             raise SagephyError(f"chained BranchRelaxer failed ({rc}): {self._lib.sgp_last_error(self._h).decode()} {b.stderr if h else ''}")
+        return b
+
+    def domain_on_batch(self, src: "Batch", args, first: int = 0, count: int = 0, name_first_index: int = 0, n: int = 1, rng: int = RNG_PHILOX, offset: int = 0,
+                        stream_mask: int = 0, keep_on_device: bool = False, check: bool = True) -> "Batch":
+        """Chained stage: ``DomainTreeGen args...`` over the pruned trees [first, first + count) of a generator batch made with
+        FLAG_KEEP_TREES as the gene-tree forest (no Newick text is written or parsed). count = 0: all trees of the batch."""
+        argv = [str(a).encode() for a in args]
+        arr = (C.c_char_p * len(argv))(*argv)
+        opts = BatchOpts(n, offset, rng, stream_mask, 1 if keep_on_device else 0, 0)
+        h = C.c_void_p()
+        rc = self._lib.sgp_domain_run_on_batch(self._h, src._h, first, count or src.n, name_first_index, len(argv), arr, C.byref(opts), C.byref(h))
+        b = Batch(self._lib, h, rc)
+        if check and rc not in (STATUS_OK, STATUS_USAGE):
+            raise SagephyError(f"chained DomainTreeGen failed ({rc}): {self._lib.sgp_last_error(self._h).decode()} {b.stderr if h else ''}")
         return b
 
     def wait_copies(self):

@@ -56,7 +56,7 @@ void common_window(const Parsed& p, TreeGenConfig& cfg) {
 
 }  // namespace
 
-void parse_treegen_app(const std::string& app, const std::vector<std::string>& args, TreeGenConfig& cfg, AppResult& res) {
+void parse_treegen_app(const std::string& app, const std::vector<std::string>& args, TreeGenConfig& cfg, AppResult& res, const std::vector<std::pair<std::string, FlatTree>>* forest) {
     cfg.args = args;
     if (app == "HostTreeGen") {
         Parsed p = scan(args, kHostOpts, (int)(sizeof kHostOpts / sizeof kHostOpts[0]));
@@ -148,10 +148,19 @@ void parse_treegen_app(const std::string& app, const std::vector<std::string>& a
         if (exists(sp)) { std::string nm = file_name(sp); cfg.host.build(parse_newick(slurp(sp)), &nm, &stem, false); }
         else cfg.host.build(parse_newick(sp), nullptr, &stem, false);
         // gene trees: every file of the directory, in sorted file-name order (the reference's File.listFiles() order is OS-dependent)
+        if (forest) {
+            // chained stage: the forest is already in memory (sorted by name like a directory listing would be)
+            if (forest->empty()) throw SgpError("no gene trees in the source batch");
+            std::vector<size_t> idx(forest->size()); for (size_t i = 0; i < idx.size(); ++i) idx[i] = i;
+            std::sort(idx.begin(), idx.end(), [&](size_t x, size_t y) { return (*forest)[x].first < (*forest)[y].first; });
+            cfg.genes.resize(forest->size());
+            for (size_t i = 0; i < idx.size(); ++i) { const auto& g = (*forest)[idx[i]]; cfg.genes[i].build(g.second, &g.first, nullptr, cfg.P.bias != 0 && cfg.P.tau > 0); }
+        } else {
         std::vector<std::string> files = list_dir(p.positional[1]);
         if (files.empty()) throw SgpError("no gene trees in directory " + p.positional[1]);
         cfg.genes.resize(files.size());
         for (size_t i = 0; i < files.size(); ++i) { std::string nm = file_name(files[i]); cfg.genes[i].build(parse_newick(slurp(files[i])), &nm, nullptr, cfg.P.bias != 0 && cfg.P.tau > 0); }
+        }
         cfg.out_prefix = cfg.quiet ? std::string() : java_trim(p.positional[5]);
         return;
     }

@@ -104,6 +104,37 @@ sgp_status sgp_relax_run_on_batch(sgp_context* ctx, sgp_batch* src, int which_tr
     }
 }
 
+sgp_status sgp_domain_run_on_batch(sgp_context* ctx, sgp_batch* src, int64_t first_tree, int64_t n_trees, int64_t name_first_index, int argc, const char* const* argv, const sgp_batch_opts* opts, sgp_batch** out) {
+    if (!ctx || !src || !out || argc < 0) return SGP_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (src->owner != ctx || !src->b.d_nodes) { ctx->last_error = "source batch holds no trees on this context (run the generator with SGP_FLAG_KEEP_TREES)"; return SGP_ERR_INVALID_ARGUMENT; }
+    sgp_batch_opts o{}; if (opts) o = *opts; if (o.n_replicates <= 0) o.n_replicates = 1;
+    std::vector<std::string> args; for (int i = 0; i < argc; ++i) args.emplace_back(argv[i] ? argv[i] : "");
+    auto* b = new sgp_batch(); b->owner = ctx;
+    try {
+        std::vector<FlatTree> trees = ctx->ctx->ingest_trees(src->b, first_tree, n_trees, true);
+        // gene tree i carries the name SGP_LAYOUT_PER_REPLICATE gives its file (the GUEST= value and the forest order follow from it)
+        std::vector<std::pair<std::string, FlatTree>> forest;
+        const std::string base = cli::file_name(src->b.out_prefix);
+        for (size_t i = 0; i < trees.size(); ++i) forest.emplace_back(base + "_" + std::to_string(name_first_index + (int64_t)i) + ".pruned.tree", std::move(trees[i]));
+        TreeGenConfig cfg; AppResult res;
+        parse_treegen_app("DomainTreeGen", args, cfg, res, &forest);
+        b->b.out_text = res.out_text; b->b.err_text = res.err_text;
+        if (res.status == 6) { *out = b; return SGP_USAGE; }
+        if (res.status != 0) { ctx->last_error = res.err_text; *out = b; return (sgp_status)res.status; }
+        BatchOpts bo; bo.n = o.n_replicates; bo.offset = o.replicate_offset; bo.rng_mode = o.rng_mode; bo.stream_mask = o.stream_mask; bo.keep_on_device = o.keep_on_device != 0; bo.keep_trees = (o.flags & SGP_FLAG_KEEP_TREES) != 0;
+        ctx->ctx->run_treegen(cfg, bo, b->b);
+        *out = b;
+        return SGP_OK;
+    } catch (SgpError& e) {
+        ctx->last_error = e.what(); b->b.err_text += std::string(e.what()) + "\n"; *out = b;
+        return std::string(e.what()).find("CUDA") != std::string::npos ? SGP_ERR_NO_DEVICE : SGP_ERR_INVALID_ARGUMENT;
+    } catch (std::exception& e) {
+        ctx->last_error = e.what(); b->b.err_text += e.what(); *out = b;
+        return SGP_ERR_INTERNAL;
+    }
+}
+
 // ---- multi-GPU front end ---------------------------------------------------------------------------------------------------------
 struct sgp_multi { std::vector<sgp_context*> ctx; };
 

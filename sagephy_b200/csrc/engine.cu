@@ -735,7 +735,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     if (opts.keep_trees) {
         Sub& S = *subs[0];
         out.d_nodes = S.nodes.release(); out.d_aux = S.aux.release(); out.d_node_off = S.node_off.release(); out.aux_stride = S.aux_stride;
-        out.name_prefix = cfg.vertex_prefix; out.name_append_sigma = cfg.append_sigma;
+        out.name_prefix = cfg.vertex_prefix; out.name_append_sigma = cfg.append_sigma; out.name_exclude_meta = cfg.exclude_meta;
     }
     static const char* host_sfx[8] = {".unpruned.tree", ".pruned.tree", ".unpruned.info", ".pruned.info", ".unpruned.guest2host", ".pruned.guest2host", ".unpruned.leafmap", ".pruned.leafmap"};
     for (int s = 0; s < 8; ++s) out.suffix[s] = (mask & (1u << s)) ? host_sfx[s] : "";
@@ -749,6 +749,68 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         out.fetch_offsets();
         out.timings.d2h_ms = d2h.stop();
     }
+}
+
+// ---- chained stage: trees of a generator batch as parsed input trees ---------------------------------------------------------------
+// What io/NewickTreeReader.java:158-296 + io/NewickVertex.java:367-375 would make of the batch's <prefix>.pruned.tree files: vertex ids
+// in post-order, lengths, names, the HOST= value of every vertex (0 without tags, -10 with tags that carry no HOST=). The device
+// part (k_ingest_count / k_ingest_fill, the kernels of the chained BranchRelaxer) reads the kept vertex records and order arrays and
+// leaves ~25 bytes per vertex, which is all that crosses PCIe: no Newick text is written or parsed.
+std::vector<FlatTree> Context::ingest_trees(const Batch& src, long long first, long long count, bool pruned) {
+    CK(cudaSetDevice(device));
+    cudaStream_t st = impl->stream; g_alloc_stream = st;
+    if (!src.d_nodes || !src.d_info || !src.d_aux || src.device != device) throw SgpError("source batch holds no trees on this device (run the generator with SGP_FLAG_KEEP_TREES)");
+    if (first < 0 || count <= 0 || first + count > src.n) throw SgpError("tree range outside the source batch");
+    if (count > (1 << 24)) throw SgpError("too many trees for one forest");
+    const int T = (int)count;
+    IngestArgs g{}; g.n_src = count; g.info = (const RepInfo*)src.d_info + first; g.node_off = src.d_node_off + first; g.nodes = (const Node*)src.d_nodes;
+    g.aux = src.d_aux; g.aux_stride = src.aux_stride; g.pruned = pruned ? 1 : 0; g.keep_interior = 1;
+    DevBuf<long long> nv, v0; nv.alloc((size_t)T + 1); v0.alloc((size_t)T + 1);
+    g.nv = nv.p; launch_ingest_count(g, st);
+    size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, nv.p, v0.p, T + 1, st);
+    DevBuf<char> tmp; tmp.alloc(tb);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, nv.p, v0.p, T + 1, st);
+    std::vector<long long> h_v0((size_t)T + 1);
+    CK(cudaMemcpyAsync(h_v0.data(), v0.p, ((size_t)T + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+    const size_t cnt = (size_t)std::max<long long>(h_v0[(size_t)T], 1);
+    DevBuf<RelaxTreeView> views; DevBuf<double> orig; DevBuf<int16_t> chain; DevBuf<uint8_t> flags; DevBuf<int32_t> num, sig, topo, parent, post_id;
+    views.alloc((size_t)T); orig.alloc(cnt); chain.alloc(cnt); flags.alloc(cnt); num.alloc(cnt); sig.alloc(cnt); topo.alloc(cnt); parent.alloc(cnt);
+    post_id.alloc((size_t)std::max<long long>(src.aux_stride, 1));
+    g.v0 = v0.p; g.views = views.p; g.orig = orig.p; g.chain = chain.p; g.vflags = flags.p; g.number = num.p; g.sigma = sig.p; g.topo = topo.p; g.parent = parent.p; g.post_id = post_id.p;
+    launch_ingest_fill(g, st);
+    CK(cudaGetLastError());
+    std::vector<double> h_bl(cnt); std::vector<uint8_t> h_fl(cnt); std::vector<int32_t> h_num(cnt), h_sig(cnt), h_par(cnt);
+    CK(cudaMemcpyAsync(h_bl.data(), orig.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(h_fl.data(), flags.p, cnt, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_num.data(), num.p, cnt * 4, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(h_sig.data(), sig.p, cnt * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_par.data(), parent.p, cnt * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<FlatTree> out((size_t)T);
+    for (int t = 0; t < T; ++t) {
+        const long long b = h_v0[(size_t)t]; const int n = (int)(h_v0[(size_t)t + 1] - b);
+        if (n == 0) throw SgpError("source replicate " + std::to_string(first + t) + " has no " + (pruned ? "pruned" : "unpruned") + " tree");
+        FlatTree& f = out[(size_t)t];
+        f.n = n; f.root = n - 1;          // the root is last in post-order
+        f.parent.assign(n, -1); f.first_child.assign(n, -1); f.next_sibling.assign(n, -1); f.n_children.assign(n, 0);
+        f.name.resize(n); f.has_name.assign(n, 1); f.bl.assign(n, 0.0); f.has_bl.assign(n, 1); f.meta.resize(n); f.has_meta.assign(n, src.name_exclude_meta ? 0 : 1);
+        f.host_tag.assign(n, 0);
+        for (int x = 0; x < n; ++x) {
+            const size_t k = (size_t)(b + x);
+            f.parent[x] = x == n - 1 ? -1 : h_par[k];
+            f.bl[x] = h_bl[k];
+            f.name[x] = src.name_prefix + std::to_string(h_num[k]) + (src.name_append_sigma ? "_" + std::to_string(h_sig[k]) : std::string());
+            // HOST= capture of io/NewickTreeReader.java:215-225: the tag's value; 0 for a vertex without any tag; -10 for tags without HOST= (species trees)
+            f.host_tag[x] = src.name_exclude_meta ? 0 : (src.app == 0 ? -10 : h_sig[k]);
+        }
+        for (int x = 0; x < n - 1; ++x) {          // children in id order: the left child of a vertex precedes the right one in post-order
+            const int p = f.parent[x];
+            if (p < 0 || p >= n) throw SgpError("internal: bad parent link in an ingested tree");
+            if (f.first_child[p] < 0) f.first_child[p] = x; else { int c = f.first_child[p]; while (f.next_sibling[c] >= 0) c = f.next_sibling[c]; f.next_sibling[c] = x; }
+            ++f.n_children[p];
+        }
+        f.bfs.push_back(f.root);
+        for (size_t i = 0; i < f.bfs.size(); ++i) for (int x = f.first_child[f.bfs[i]]; x >= 0; x = f.next_sibling[x]) f.bfs.push_back(x);
+    }
+    return out;
 }
 
 // ---- BranchRelaxer -----------------------------------------------------------------------------------------------------------

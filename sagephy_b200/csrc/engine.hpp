@@ -98,7 +98,7 @@ public:
     void* d_info = nullptr;                       // RepInfo[n]
     // kept only with BatchOpts::keep_trees: vertex records, order arrays (4 x aux_stride), first record of each replicate
     void* d_nodes = nullptr; int32_t* d_aux = nullptr; long long* d_node_off = nullptr; long long aux_stride = 0;
-    std::string name_prefix; bool name_append_sigma = false;
+    std::string name_prefix; bool name_append_sigma = false, name_exclude_meta = false;
     unsigned stream_mask = 0;
     double* d_values[2] = {nullptr, nullptr}; long long n_values = 0;   // BranchRelaxer: rates, relaxed lengths (flat, replicate-major)
     std::vector<double> h_values[2];
@@ -129,6 +129,9 @@ public:
     void run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch& out);
     // src != nullptr: chained run over the trees of a tree-generator batch (pruned or unpruned view), cfg.trees is ignored
     void run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& out, const Batch* src = nullptr, bool src_pruned = true);
+    // Chained stage: the trees [first, first + count) of a generator batch kept with keep_trees, as parsed Newick trees would look
+    // (post-order ids, lengths, names, HOST tags) - read from the vertex records on the device, never printed or parsed.
+    std::vector<FlatTree> ingest_trees(const Batch& src, long long first, long long count, bool pruned);
     void* copy_stream();          // second CUDA stream for device->host copies that overlap the next batch's kernels
     void wait_copies();
     void probe_d2s(const double* v, long long n, char* out);
@@ -145,7 +148,8 @@ void host_philox_probe(int variant, const uint32_t* ctr, const uint32_t* key, lo
 
 // apps.cpp: reference CLI grammar -> configs
 struct AppResult { int status = 0; std::string out_text, err_text; };   // status: 0 run, 6 usage, other = error code
-void parse_treegen_app(const std::string& app, const std::vector<std::string>& args, TreeGenConfig& cfg, AppResult& res);
+// forest != nullptr (DomainTreeGen, chained stage): gene trees and their names come from memory, the <guest tree directory> positional is only echoed
+void parse_treegen_app(const std::string& app, const std::vector<std::string>& args, TreeGenConfig& cfg, AppResult& res, const std::vector<std::pair<std::string, FlatTree>>* forest = nullptr);
 void parse_relax_app(const std::vector<std::string>& args, bool multi_tree_input, RelaxConfig& cfg, AppResult& res, bool trees_from_batch = false);
 
 }  // namespace sgp

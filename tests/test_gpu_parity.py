@@ -577,3 +577,36 @@ def test_domain_tree_gen_philox_matches_oracle_distributions(ctx, gene_dir):
     for e in (1, 4, 5, 6, 9, 10, 11, 12, 13, 14, 15, 16):
         assert chi2_two_sample_ok(ev[:, e].astype(float), st[:, 9 + e]), e
     assert chi2_two_sample_ok(b.attempts.astype(float), st[:, 0])
+
+
+# ---- chained stage: GuestTreeGen batch -> DomainTreeGen without files -----------------------------------------------------------------
+@pytest.mark.parametrize("src_opts", [[], ["-nox"]], ids=["tagged", "nox"])
+def test_chained_domain_tree_gen_equals_the_run_on_the_emitted_files(ctx, tmp_path, src_opts):
+    """DomainTreeGen over the pruned trees of a resident GuestTreeGen batch (sgp_domain_run_on_batch: vertex records read on the
+    device, no Newick text) == DomainTreeGen over a directory holding those trees as the files SGP_LAYOUT_PER_REPLICATE writes,
+    which in turn == the CPU oracle on that directory (replay mode, byte for byte)."""
+    n_genes = 12                                  # two-digit indices: the forest order is the sorted file-name order, not the index order
+    gargs = ["-s", "40", "-db", "none"] + src_opts + [HOST8, "0.4", "0.2", "0.2", str(tmp_path / "gt")]
+    src = ctx.run("GuestTreeGen", gargs, n=n_genes, rng=sg.RNG_MT_REPLAY, flags=sg.FLAG_KEEP_TREES)
+    assert (src.rep_status == 0).all()
+    d = tmp_path / "genes"; d.mkdir()
+    for i in range(n_genes):
+        (d / f"gt_{100 + i}.pruned.tree").write_bytes(src.replicate(sg.STREAM_PRUNED_TREE, i))
+    for opts in (["-s", "3", "-ig", "0.6"], ["-s", "4", "-db", "simple", "-rt", "1.0", "-all", "-a", "200"]):
+        args = opts + [HOST8, str(d), "0.4", "0.3", "0.9", "o"]
+        files = ctx.run("DomainTreeGen", args, n=6, rng=sg.RNG_MT_REPLAY)
+        chained = ctx.domain_on_batch(src, args, name_first_index=100, n=6, rng=sg.RNG_MT_REPLAY)
+        assert (chained.rep_status == files.rep_status).all()
+        for s in range(8):
+            assert bytes(chained.stream(s)) == bytes(files.stream(s)), (opts, s)
+        # and the file-based run is the oracle's (replicate 0)
+        want = oracle_run("DomainTreeGen", args)
+        if want["status"] == 0:
+            got = files.files(0)
+            for sfx, data in got.items():
+                assert data == want["files"]["o" + sfx], sfx
+        files.free(); chained.free()
+    # a sub-range of the batch as the forest
+    part = ctx.domain_on_batch(src, ["-s", "5", HOST8, "x", "0.4", "0.3", "0.5", "o"], first=2, count=5, name_first_index=2, n=3, rng=sg.RNG_MT_REPLAY)
+    assert (part.rep_status == 0).all() and part.stream_bytes(sg.STREAM_PRUNED_TREE) > 0
+    part.free(); src.free()
