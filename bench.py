@@ -330,8 +330,9 @@ def extra_workloads(h, peaks, K, W):
                 "roofline": {"bound": "issue", "kernel": "k_find_general + k_build_general", "achieved": (sampled + verts) / (fb_ms * 1e-3) * 1e-9, "peak": peak_gv, "unit": "Gvertex/s",
                              "frac": (sampled + verts) / (fb_ms * 1e-3) * 1e-9 / peak_gv, "traffic": None,
                              "note": "peak = issue-rate model of the birth-death vertex (a DTL vertex does at least that work); achieved = vertices created by find + build / their time"},
-                "roofline_emit": {"bound": "hbm", "kernel": "k_emit<write>", "achieved": (out_bytes + verts * 96) / (ew_ms * 1e-3) * 1e-9 / 1.0, "peak": hbm * world, "peak_source": hbm_src, "unit": "GB/s",
-                                  "frac": (out_bytes + verts * 96) / (ew_ms * 1e-3) * 1e-9 / (hbm * world), "traffic": None}}
+                "roofline_emit": {"bound": "hbm", "kernel": "k_write_tree + k_write_rows + k_emit_info<write>", "achieved": (out_bytes + verts * 128) / (ew_ms * 1e-3) * 1e-9 / 1.0, "peak": hbm * world, "peak_source": hbm_src, "unit": "GB/s",
+                                  "frac": (out_bytes + verts * 128) / (ew_ms * 1e-3) * 1e-9 / (hbm * world), "traffic": None,
+                                  "note": "algorithmic bytes = text written once + 32-byte emission records read once (Newick piece and .guest2host/.leafmap row per vertex and view)"}}
         if h.rank == 0 and world == 1 and cpu_n:
             v, s = cpu_single(app, argv, cpu_n)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": s}
@@ -360,6 +361,16 @@ def extra_workloads(h, peaks, K, W):
     gt.free()
     general("C4_domain_100_genes", "DomainTreeGen", ["-s", "9", "-ig", "0.5", "-is", "0.5", "-max", "100000", "-maxper", "100000", host1000, gd, "0.3", "0.3", "0.3", "d"],
             h.args.c4_domain_replicates, 256, 2, 2, "C4: DomainTreeGen -ig 0.5 -is 0.5 0.3 0.3 0.3 over 100 gene trees (GuestTreeGen -db none 0.2 0.2 0.1) of the 1000-leaf species tree")
+
+    # the same forest handed over on the device (sgp_domain_run_on_batch): ingest kernels + K0 tables + the run, no gene-tree files
+    gk = h.ctx.run("GuestTreeGen", ["-s", "77", "-db", "none", host1000, "0.2", "0.2", "0.1", os.path.join(tmp, "gene")], n=100, rng=sg.RNG_PHILOX, stream_mask=0b0010, flags=sg.FLAG_KEEP_TREES, keep_on_device=True)
+    dargs = ["-s", "9", "-ig", "0.5", "-is", "0.5", "-max", "100000", "-maxper", "100000", host1000, "chained", "0.3", "0.3", "0.3", "d"]
+    h.torch.cuda.synchronize(); t0 = time.perf_counter()
+    cb = h.ctx.domain_on_batch(gk, dargs, n=h.args.c4_domain_replicates, rng=sg.RNG_PHILOX, offset=h.rank * h.args.c4_domain_replicates, keep_on_device=True)
+    h.torch.cuda.synchronize(); chained_s = time.perf_counter() - t0
+    out["C4_domain_100_genes"]["chained"] = {"seconds_per_step": chained_s, "value": int(cb.summary().n_ok) / chained_s, "unit": UNIT,
+                                             "note": "forest = 100 pruned trees of a resident GuestTreeGen batch (sgp_domain_run_on_batch); includes ingest and the host-side epoch tables"}
+    cb.free(); gk.free()
 
     # ---- C5: BranchRelaxer over 199-vertex trees, chained on the device behind the generator (10 draws per C2 tree)
     n_src = h.args.c5_source_trees; draws = 10; n_rel = n_src * draws
@@ -478,7 +489,7 @@ def main():
         alg_inst = ALG_FP64_INST_PER_VERTEX + ALG_IMAD_INST_PER_VERTEX + ALG_ALU_INST_PER_VERTEX
         peak_plain = issue_slots * 32.0 / alg_inst * 1e-9 * world
         out_bytes = float(np.sum(total.out_bytes))
-        emit_alg_bytes = out_bytes + float(total.event_counts.sum()) * (80 + 16)      # node records + order arrays read once, text written once
+        emit_alg_bytes = out_bytes + 2.0 * float(total.event_counts.sum()) * 32      # text written once + one 32-byte emission record per Newick piece (two views) read once
         emit_gbs = emit_alg_bytes / (emitw_ms * 1e-3) * 1e-9
         cpu_val, cpu_sample = None, "measured at N = 1 only"
         if world == 1:
@@ -504,7 +515,7 @@ def main():
                          "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, scaled per replicate)", "traffic_source": traffic["source"] if traffic else None,
                          "alg_inst_per_vertex": {"fp64": ALG_FP64_INST_PER_VERTEX, "imad_wide": ALG_IMAD_INST_PER_VERTEX, "alu": ALG_ALU_INST_PER_VERTEX},
                          "measured_issue_peaks_ginst_per_s": dict(peaks, alu_derived_ginst_per_s=r_alu), "share_of_step": find_ms / dev_ms},
-            "roofline_emit": {"bound": "hbm", "kernel": "k_emit<write>", "achieved": emit_gbs, "peak": hbm * world, "peak_source": hbm_src, "unit": "GB/s",
+            "roofline_emit": {"bound": "hbm", "kernel": "k_write_tree<unpruned> + k_write_tree<pruned> + k_emit_info<write>", "achieved": emit_gbs, "peak": hbm * world, "peak_source": hbm_src, "unit": "GB/s",
                               "frac": emit_gbs / (hbm * world), "traffic": tr_emit["dram_bytes_per_replicate"] * n if tr_emit else None, "algorithmic_bytes": emit_alg_bytes / K / world,
                               "traffic_unit": "bytes per step over the write launches (ncu, scaled per replicate)", "traffic_source": traffic["source"] if traffic else None,
                               "share_of_step": emitw_ms / dev_ms},

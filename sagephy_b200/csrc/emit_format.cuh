@@ -87,8 +87,11 @@ template <class Sink> __device__ void put_meta(Sink& s, const EmitArgs& a, const
 
 // one Newick piece
 template <bool PRUNED, class Sink> __device__ void put_tree_piece(Sink& s, const EmitArgs& a, const TreeRec& t, const TreeRecX* xp) {
-    if (t.flags & TR_LEAF) { for (int i = 0; i < t.chain; ++i) s.put('('); }
-    else s.put(')');
+    {   // '(' x chain before a leaf, ')' before an interior vertex: one loop for both (no branch for the compiler to duplicate the rest into)
+        const bool leaf = (t.flags & TR_LEAF) != 0;
+        const int c = leaf ? t.chain : 1; const char ch = leaf ? '(' : ')';
+        for (int i = 0; i < c; ++i) s.put(ch);
+    }
     put_name(s, a, t.number, t.sigma);
     s.put(':');
     put_decimal(s, a.T, t.f, t.e, t.pad);

@@ -103,7 +103,7 @@ __device__ __forceinline__ unsigned warp_excl_scan_u32(unsigned v, unsigned* tot
 }
 
 constexpr int kEmitWarps = 4;               // warps per block
-constexpr int kStageBytes = 4096;           // one staging buffer (32 pieces; longer groups fall back to direct stores); two per warp
+constexpr int kStageBytes = 3072;           // one staging buffer (32 pieces; longer groups fall back to direct stores); two per warp
 
 // Flushes `total` staged bytes (stage[mis .. mis+total), mis = dst & 15) to dst with aligned 16-byte stores.
 __device__ __forceinline__ void flush_stage(const char* stage, int mis, char* dst, unsigned total) {
@@ -334,10 +334,11 @@ template <int INSTANCE> __global__ void __launch_bounds__(256) k_finish_records(
     const int lane = threadIdx.x & 31;
     if (r >= a.n) return;
     const RepInfo& inf = a.info[r];
-    if (inf.status != REP_OK) return;
+    const int status = inf.status, n_u = inf.n_u, n_p = inf.n_p, p_root_ = inf.p_root;       // (independent loads first, see k_write_tree)
     const long long off = a.node_off[r];
+    if (status != REP_OK) return;
     const unsigned mask = a.stream_mask;
-    const int up = inf.n_u, nu = inf.p_root >= 0 ? inf.n_p : 0;
+    const int up = n_u, nu = p_root_ >= 0 ? n_p : 0;
     unsigned long long* sz = a.sizes + r;
 #pragma unroll
     for (int view = 0; view < 2; ++view) {
@@ -379,29 +380,33 @@ template <int INSTANCE> __global__ void __launch_bounds__(256) k_finish_records(
     }
 }
 
-// One Newick stream (VIEW 0: unpruned, 1: pruned): warp per replicate.
+// One Newick stream (VIEW 0: unpruned, 1: pruned): warp per replicate. Everything the warp needs to find its records (status and
+// vertex counts, stream offsets, first record) is loaded up front in ONE round trip: as a chain of dependent loads behind early
+// returns it cost four round trips per replicate, as long as formatting the replicate's seven trips.
 template <int VIEW, bool BULK>
-__global__ void __launch_bounds__(kEmitWarps * 32) k_write_tree(EmitArgs a) {
+__global__ void __launch_bounds__(kEmitWarps * 32, 8) k_write_tree(EmitArgs a) {
     __shared__ __align__(128) char s_stage[kEmitWarps][2 * kStageBytes];
     const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= a.n) return;
     constexpr int st = VIEW ? ST_PRUNED_TREE : ST_UNPRUNED_TREE;
     const RepInfo& inf = a.info[r];
-    if (inf.status != REP_OK) return;
-    if (a.offsets[(size_t)st * a.stride + r + 1] > a.cap[st]) { if (lane == 0) *a.overflow = 1; return; }
-    char* base = a.out[st] + a.offsets[(size_t)st * a.stride + r];
+    const int status = inf.status, n_rec = VIEW ? inf.n_p : inf.n_u, p_root = inf.p_root;
+    const unsigned long long o0 = a.offsets[(size_t)st * a.stride + r], o1 = a.offsets[(size_t)st * a.stride + r + 1];
+    const long long off = a.node_off[r];
+    if (status != REP_OK) return;
+    if (o1 > a.cap[st]) { if (lane == 0) *a.overflow = 1; return; }
+    char* base = a.out[st] + o0;
     char* stage2 = s_stage[threadIdx.x >> 5];
-    if (VIEW == 1 && inf.p_root < 0) {
+    if (VIEW == 1 && p_root < 0) {
         // empty pruned tree: NewickTree.toString of a null root
         if (lane == 0) { MemSink m{base}; if (a.exclude_meta) put_lit(m, ";\n"); else if (a.app == 0) put_lit(m, "[NAME=PrunedTree];"); else put_lit(m, "[NAME=PrunedTree];\n"); }
         return;
     }
-    const long long off = a.node_off[r];
     const TreeRec* recs = a.trec + (size_t)VIEW * a.aux_stride + off;
     const TreeRecX* recx = a.trecx ? a.trecx + (size_t)VIEW * a.aux_stride + off : nullptr;
     unsigned trip = 0;
-    emit_records<BULK>(VIEW ? inf.n_p : inf.n_u, recs, base, stage2, trip,
+    emit_records<BULK>(n_rec, recs, base, stage2, trip,
                        [&](auto& s, const TreeRec& t, int i) { put_tree_piece<VIEW == 1>(s, a, t, recx + i); },
                        [](const TreeRec& t) { return (unsigned)t.len; });
     if (BULK && lane == 0) bulk_wait_read<0>();         // shared memory must outlive the copies that read it
@@ -409,20 +414,23 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_write_tree(EmitArgs a) {
 
 // One row stream (KIND 0: .guest2host, 1: .leafmap; VIEW 0: unpruned, 1: pruned): warp per replicate.
 template <int KIND, int VIEW, bool BULK>
-__global__ void __launch_bounds__(kEmitWarps * 32) k_write_rows(EmitArgs a) {
+__global__ void __launch_bounds__(kEmitWarps * 32, 8) k_write_rows(EmitArgs a) {
     __shared__ __align__(128) char s_stage[kEmitWarps][2 * kStageBytes];
     const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= a.n) return;
     constexpr int st = KIND == 0 ? (VIEW ? ST_PRUNED_G2H : ST_UNPRUNED_G2H) : (VIEW ? ST_PRUNED_LEAFMAP : ST_UNPRUNED_LEAFMAP);
     const RepInfo& inf = a.info[r];
-    if (inf.status != REP_OK) return;
-    if (a.offsets[(size_t)st * a.stride + r + 1] > a.cap[st]) { if (lane == 0) *a.overflow = 1; return; }
-    char* base = a.out[st] + a.offsets[(size_t)st * a.stride + r];
-    char* stage2 = s_stage[threadIdx.x >> 5];
+    // (independent loads first, see k_write_tree)
+    const int status = inf.status, n_view = VIEW ? inf.n_p : inf.n_u, p_root = inf.p_root;
+    const unsigned long long o0 = a.offsets[(size_t)st * a.stride + r], o1 = a.offsets[(size_t)st * a.stride + r + 1];
     const long long off = a.node_off[r];
+    if (status != REP_OK) return;
+    if (o1 > a.cap[st]) { if (lane == 0) *a.overflow = 1; return; }
+    char* base = a.out[st] + o0;
+    char* stage2 = s_stage[threadIdx.x >> 5];
     const RowRec* recs = a.rows + (size_t)VIEW * a.aux_stride + off;
-    const int np = VIEW ? (inf.p_root >= 0 ? inf.n_p : 0) : inf.n_u;
+    const int np = VIEW ? (p_root >= 0 ? n_view : 0) : n_view;
     unsigned trip = 0;
     if (KIND == 0) {
         int head_len = a.g2h_head_len;
