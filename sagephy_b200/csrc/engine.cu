@@ -452,7 +452,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     // whatever happens, no buffer may be released while the second stream still works on it
     struct StreamFence { cudaStream_t a, b; ~StreamFence() { if (a != b) { cudaStreamSynchronize(b); } } } fence{stA, stB};
 
-    DevBuf<uint32_t> mt_state; DevBuf<int32_t> marks, leafcnt;
+    DevBuf<uint32_t> mt_state; DevBuf<int32_t> marks, leafcnt; DevBuf<unsigned long long> arc_head;
     size_t scan_tmp_bytes = 0; cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp_bytes, (long long*)nullptr, (long long*)nullptr, (int)(sub_n + 1), stA);
     DevBuf<char> scan_tmp; scan_tmp.alloc(scan_tmp_bytes);
 
@@ -491,11 +491,16 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
                 }
                 b_next.alloc(1); CK(cudaMemsetAsync(b_next.p, 0, sizeof(int), stA));
                 marks.alloc((size_t)workers * mark_n); leafcnt.alloc((size_t)workers * cnt_n);
+                // per-arc vertex lists of the victim search: GuestTreeGen on hosts where a guest tree is large enough for the pool scan to
+                // cost more than keeping the lists (1000-leaf host: find 140 -> 95 ms per 8192 trees; 100-leaf host: 29 -> 31 ms per 2*10^5),
+                // and not so large that the heads would take > 8 GB
+                const bool arc_lists = !domain && cfg.host.nV >= 512 && (double)workers * cfg.host.nV * 8.0 <= 8.0 * (1ull << 30);
+                if (arc_lists) { arc_head.alloc((size_t)workers * cfg.host.nV); CK(cudaMemsetAsync(arc_head.p, 0, (size_t)workers * cfg.host.nV * 8, stA)); } else arc_head.alloc(0);
                 if (domain) scratch_used.alloc((size_t)workers * cfg.genes.size());
                 if (replay) mt_state.alloc((size_t)(workers / 32 + 1) * 624 * 32);
                 FindArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = todo; a.rep_ids = rep_ids; a.rep_base = opts.offset; a.seed = seed; a.sseed = sseed; a.info = info.p;
                 a.work_counter = S.counter.p; a.scratch_nodes = s_nodes; a.scratch_queue = s_queue; a.scratch_pend = s_pend; a.cap = cap;
-                a.scratch_marks = marks.p; a.scratch_leafcnt = leafcnt.p; a.mt_state = mt_state.p; a.sizes = d_sizes.p; a.per_leaf_check = per_leaf;
+                a.scratch_marks = marks.p; a.scratch_leafcnt = leafcnt.p; a.scratch_arc_head = arc_head.p; a.mt_state = mt_state.p; a.sizes = d_sizes.p; a.per_leaf_check = per_leaf;
                 a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
                 a.scratch_used = scratch_used.p; a.ev_base = d_ev_base.p; a.ev_off = d_ev_off.p; a.ev_list = d_ev_list.p;
                 a.big_nodes = b_nodes; a.big_queue = b_queue; a.big_pend = b_pend; a.big_cap = big_cap; a.big_count = big_count; a.big_next = b_next.p;
@@ -631,11 +636,15 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         } else {
             const long long threads = std::max<long long>(128, std::min<long long>((long long)sm * 1024, (n + 127) / 128 * 128));
             marks.alloc((size_t)threads * (domain ? max_gene_nv : cfg.host.nV));
+            {
+                const bool arc_lists = !domain && cfg.host.nV >= 512 && (double)threads * cfg.host.nV * 8.0 <= 8.0 * (1ull << 30);
+                if (arc_lists) { arc_head.alloc((size_t)threads * cfg.host.nV); CK(cudaMemsetAsync(arc_head.p, 0, (size_t)threads * cfg.host.nV * 8, stB)); } else arc_head.alloc(0);
+            }
             if (domain) scratch_used.alloc((size_t)threads * cfg.genes.size());
             if (replay) mt_state.alloc((size_t)(threads / 32 + 1) * 624 * 32);
             CK(cudaMemsetAsync(S.counter.p, 0, sizeof(unsigned long long), stB));
             BuildArgs a{}; a.P = P; a.H = hd.view; a.T = impl->T; a.n = n; a.rep_base = opts.offset; a.seed = seed; a.sseed = sseed; a.info = info.p; a.node_off = S.node_off.p; a.work_counter = S.counter.p;
-            a.nodes = S.nodes.p; a.aux = S.aux.p; a.aux_stride = S.aux_stride; a.scratch_marks = marks.p; a.scratch_leafcnt = nullptr; a.mt_state = mt_state.p;
+            a.nodes = S.nodes.p; a.aux = S.aux.p; a.aux_stride = S.aux_stride; a.scratch_marks = marks.p; a.scratch_leafcnt = nullptr; a.scratch_arc_head = arc_head.p; a.mt_state = mt_state.p;
             a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
             a.scratch_used = scratch_used.p; a.ev_base = d_ev_base.p; a.ev_off = d_ev_off.p; a.ev_list = d_ev_list.p;
             // a lane builds its tree alone, so the largest trees set the kernel's tail: start them first

@@ -28,6 +28,7 @@ struct FindArgs {
     // scratch (general engine): per worker thread
     Node* scratch_nodes; int32_t* scratch_queue; int32_t* scratch_pend; int cap;
     int32_t* scratch_marks; int32_t* scratch_leafcnt;      // nV / nLeaves ints per worker
+    unsigned long long* scratch_arc_head;                  // nV entries per worker, zeroed (SimWork::arc_head); nullptr: none
     uint32_t* mt_state;          // 624 words per worker, warp-interleaved (replay mode)
     const int32_t* sizes;        // -sizes list
     int per_leaf_check;
@@ -53,6 +54,7 @@ struct BuildArgs {
     Node* nodes;                 // arena
     int32_t* aux; long long aux_stride;    // 4 int arrays of length total_nodes: aux + k*aux_stride
     int32_t* scratch_marks; int32_t* scratch_leafcnt;
+    unsigned long long* scratch_arc_head;
     uint32_t* mt_state;
     const DevHost* genes; int n_genes; int max_gene_nv; int all_genes; double inter_gene, inter_species;
     int32_t* scratch_used;

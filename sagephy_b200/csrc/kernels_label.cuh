@@ -210,7 +210,10 @@ __global__ void __launch_bounds__(32) k_label_prune_warp(LabelArgs a) {
         mbar_wait(mbar, phase); phase ^= 1u;
         __syncwarp();
         // right children the birth-death build kernel left unlinked (NF_RIGHT_CHILD)
-        for (int v = lane; v < n_pool; v += 32) { Node& x = sN[v]; if (x.flags & NF_RIGHT_CHILD) { sN[x.parent].right = v; x.flags &= (uint8_t)~NF_RIGHT_CHILD; } }
+        for (int v = lane; v < n_pool; v += 32) {
+            Node& x = sN[v]; if (x.flags & NF_RIGHT_CHILD) { sN[x.parent].right = v; x.flags &= (uint8_t)~NF_RIGHT_CHILD; }
+            x.p_left = -1; x.p_right = -1; x.flags &= (uint8_t)~NF_DETACHED;          // (the samplers use p_left as a per-arc list link)
+        }
         __syncwarp();
         // ---- 1. breadth-first order, levels
         int D = 0, up;
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(128) k_label_prune(LabelArgs a) {
     int32_t* ordU = a.aux + off; int32_t* ordP = a.aux + a.aux_stride + off;
     int32_t* bfsU = a.aux + 2 * a.aux_stride + off; int32_t* bfsP = a.aux + 3 * a.aux_stride + off;
     const int root = inf.root;
-    for (int v = 0; v < inf.n_pool; ++v) { Node& x = N[v]; if (x.flags & NF_RIGHT_CHILD) { N[x.parent].right = v; x.flags &= (uint8_t)~NF_RIGHT_CHILD; } }
+    for (int v = 0; v < inf.n_pool; ++v) { Node& x = N[v]; if (x.flags & NF_RIGHT_CHILD) { N[x.parent].right = v; x.flags &= (uint8_t)~NF_RIGHT_CHILD; } x.p_left = -1; x.p_right = -1; x.flags &= (uint8_t)~NF_DETACHED; }
     int nu = 0, up = 0;
     const int p_root = label_postorder<int32_t>(N, ordU, ordP, bfsP, root, a.T, nu, up);
     for (int k = 0; k < up; ++k) { Node& x = N[ordU[k]]; if (x.number < -1) x.number = nu + (-2 - x.number); }

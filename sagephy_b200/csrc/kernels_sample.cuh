@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
     W.marks = a.scratch_marks + (size_t)worker * mark_n;
     W.leaf_cnt = a.per_leaf_check ? a.scratch_leafcnt + (size_t)worker * cnt_n : nullptr;
     W.mark_gen = 0;
+    W.arc_head = (!DOMAIN && a.scratch_arc_head) ? a.scratch_arc_head + (size_t)worker * a.H.nV : nullptr; W.arc_gen = 0;
     for (int i = 0; i < mark_n; ++i) W.marks[i] = 0;
     DomainEnv E{a.genes, a.n_genes, a.inter_gene, a.inter_species, DOMAIN ? a.scratch_used + (size_t)worker * a.n_genes : nullptr, a.ev_base, a.ev_off, a.ev_list};
     MtStream mt; PhiloxStream ph;
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(128) k_build_general(BuildArgs a) {
     SimWork W; W.logtab = s_logtab; W.nodes = nullptr; W.cap = 0; W.queue = nullptr; W.pend = nullptr;
     const int mark_n = DOMAIN ? a.max_gene_nv : a.H.nV;
     W.marks = a.scratch_marks + (size_t)worker * mark_n; W.leaf_cnt = nullptr; W.mark_gen = 0;
+    W.arc_head = (!DOMAIN && a.scratch_arc_head) ? a.scratch_arc_head + (size_t)worker * a.H.nV : nullptr; W.arc_gen = 0;
     for (int i = 0; i < mark_n; ++i) W.marks[i] = 0;
     DomainEnv E{a.genes, a.n_genes, a.inter_gene, a.inter_species, DOMAIN ? a.scratch_used + (size_t)worker * a.n_genes : nullptr, a.ev_base, a.ev_off, a.ev_list};
     MtStream mt; PhiloxStream ph;
