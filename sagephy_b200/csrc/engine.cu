@@ -494,7 +494,8 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
                 // per-arc vertex lists of the victim search: GuestTreeGen on hosts where a guest tree is large enough for the pool scan to
                 // cost more than keeping the lists (1000-leaf host: find 140 -> 95 ms per 8192 trees; 100-leaf host: 29 -> 31 ms per 2*10^5),
                 // and not so large that the heads would take > 8 GB
-                const bool arc_lists = !domain && cfg.host.nV >= 512 && (double)workers * cfg.host.nV * 8.0 <= 8.0 * (1ull << 30);
+                const char* al_env = getenv("SGP_ARC_LISTS");         // test hook: 1 forces the lists on small hosts, 0 switches them off
+                const bool arc_lists = !domain && (al_env ? al_env[0] == '1' : cfg.host.nV >= 512) && (double)workers * cfg.host.nV * 8.0 <= 8.0 * (1ull << 30);
                 if (arc_lists) { arc_head.alloc((size_t)workers * cfg.host.nV); CK(cudaMemsetAsync(arc_head.p, 0, (size_t)workers * cfg.host.nV * 8, stA)); } else arc_head.alloc(0);
                 if (domain) scratch_used.alloc((size_t)workers * cfg.genes.size());
                 if (replay) mt_state.alloc((size_t)(workers / 32 + 1) * 624 * 32);
@@ -637,7 +638,8 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             const long long threads = std::max<long long>(128, std::min<long long>((long long)sm * 1024, (n + 127) / 128 * 128));
             marks.alloc((size_t)threads * (domain ? max_gene_nv : cfg.host.nV));
             {
-                const bool arc_lists = !domain && cfg.host.nV >= 512 && (double)threads * cfg.host.nV * 8.0 <= 8.0 * (1ull << 30);
+                const char* al_env = getenv("SGP_ARC_LISTS");
+                const bool arc_lists = !domain && (al_env ? al_env[0] == '1' : cfg.host.nV >= 512) && (double)threads * cfg.host.nV * 8.0 <= 8.0 * (1ull << 30);
                 if (arc_lists) { arc_head.alloc((size_t)threads * cfg.host.nV); CK(cudaMemsetAsync(arc_head.p, 0, (size_t)threads * cfg.host.nV * 8, stB)); } else arc_head.alloc(0);
             }
             if (domain) scratch_used.alloc((size_t)threads * cfg.genes.size());

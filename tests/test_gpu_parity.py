@@ -167,6 +167,15 @@ def test_guest_tree_gen_replay_is_byte_exact(ctx, args):
     assert_replay_parity(ctx, "GuestTreeGen", args, 24, "o")
 
 
+def test_guest_tree_gen_victim_search_through_arc_lists(ctx, monkeypatch):
+    """Large hosts find the lineage a replacing transfer replaces through per-arc vertex lists instead of a scan of the pool
+    (switched on by host size); forced on here, the replay output must still be the oracle's, byte for byte."""
+    monkeypatch.setenv("SGP_ARC_LISTS", "1")
+    for args in (["-s", "21", "-db", "none", "-rt", "1.0", HOST8, "0.5", "0.3", "0.9", "g"],
+                 ["-s", "22", "-db", "simple", "-rt", "0.7", HOST8, "0.6", "0.2", "1.2", "g"]):
+        assert_replay_parity(ctx, "GuestTreeGen", args, 24, "g").free()
+
+
 def test_guest_tree_gen_large_trees_rerun_with_bigger_pools(ctx):
     # trees beyond the first scratch-pool size (1024 vertices) are re-run with 8x the pool: same bytes as the oracle
     args = ["-s", "41", "-db", "none", "-max", "100000", "-maxper", "100000", HOST8, "5.0", "0.2", "0.3", "o"]
