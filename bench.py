@@ -519,6 +519,7 @@ def main():
                               "frac": emit_gbs / (hbm * world), "traffic": tr_emit["dram_bytes_per_replicate"] * n if tr_emit else None, "algorithmic_bytes": emit_alg_bytes / K / world,
                               "traffic_unit": "bytes per step over the write launches (ncu, scaled per replicate)", "traffic_source": traffic["source"] if traffic else None,
                               "share_of_step": emitw_ms / dev_ms},
+            "post_sampling_dram_bytes_per_replicate": ({k: (v["dram_bytes_per_replicate"]) for k, v in traffic["kernels"].items() if k != "find"} if traffic else None),
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port", "sample": cpu_sample},
             "clocks": clk,
             "workloads": workloads,

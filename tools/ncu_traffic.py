@@ -15,7 +15,7 @@ ki = hdr.index("Kernel Name"); ri = hdr.index("dram__bytes_read.sum"); wi = hdr.
 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 tscale = {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "nsecond": 1e-6, "second": 1e3, "s": 1e3}
 groups = {"find": ("k_bd_find",), "build": ("k_bd_build",), "label": ("k_label_prune", "k_info_sums"), "finish": ("k_finish_records",),
-          "emit_write": ("k_write_tree", "k_write_rows", "k_emit_info<(bool)1>", "k_emit_info<true>")}
+          "emit_write": ("k_write_tree", "k_write_rows", "k_emit_info<(bool)1>", "k_emit_info<true>", "k_emit_info<1>")}
 acc = {g: {"dram_bytes": 0.0, "ms": 0.0, "launches": 0} for g in groups}
 passes = {}
 for r in rows[2:]:
@@ -24,7 +24,14 @@ for r in rows[2:]:
     name = r[ki]
     for g, pats in groups.items():
         if any(p in name for p in pats):
-            b = float(r[ri].replace(",", "")) * scale[units[ri]] + float(r[wi].replace(",", "")) * scale[units[wi]]
+            def num(x):
+                try:
+                    v = float(x.replace(",", ""))
+                    return v if v == v else None
+                except ValueError:
+                    return None
+            rd, wr = num(r[ri]), num(r[wi])
+            b = (rd * scale[units[ri]] + wr * scale[units[wi]]) if rd is not None and wr is not None else float("nan")
             acc[g]["dram_bytes"] += b; acc[g]["ms"] += float(r[ti].replace(",", "")) * tscale[units[ti]]; acc[g]["launches"] += 1
             passes[g] = passes.get(g, 0) + (1 if any(p in name for p in pats[:1]) else 0)
 res = {"source": src, "replicates_profiled": n, "kernels": {}}
@@ -32,7 +39,7 @@ res = {"source": src, "replicates_profiled": n, "kernels": {}}
 n_pass = max(1, acc["build"]["launches"] or acc["find"]["launches"] or 1)
 for g, a in acc.items():
     if a["launches"]:
-        res["kernels"][g] = {"dram_bytes_per_replicate": a["dram_bytes"] / n_pass / n, "ms_per_replicate_under_ncu": a["ms"] / n_pass / n, "launches_per_pass": a["launches"] / n_pass}
+        res["kernels"][g] = {"dram_bytes_per_replicate": (a["dram_bytes"] / n_pass / n) if a["dram_bytes"] == a["dram_bytes"] else None, "ms_per_replicate_under_ncu": a["ms"] / n_pass / n, "launches_per_pass": a["launches"] / n_pass}
 res["passes_in_capture"] = n_pass
 json.dump(res, open(out, "w"), indent=1)
 print(json.dumps(res, indent=1))
