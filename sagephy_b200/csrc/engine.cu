@@ -191,6 +191,7 @@ struct EventTimer {
 
 struct Context::Impl {
     cudaStream_t stream = nullptr;
+    cudaStream_t side[2] = {nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};   // side streams of the write kernels
     cudaStream_t stream2 = nullptr;        // second compute stream of pipelined runs (build / label / emit of sub-batch k under find of k+1)
     cudaStream_t copy = nullptr;
     // Small device->host results (counts, totals, the summary block) travel through a mapped pinned mailbox written by a
@@ -233,6 +234,8 @@ Context::Context(int dev) : device(dev), impl(new Impl()) {
     CK(cudaSetDevice(dev));
     CK(cudaStreamCreate(&impl->stream));
     CK(cudaStreamCreateWithFlags(&impl->stream2, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) { CK(cudaStreamCreateWithFlags(&impl->side[k], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&impl->ev_join[k], cudaEventDisableTiming)); }
+    CK(cudaEventCreateWithFlags(&impl->ev_fork, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&impl->copy, cudaStreamNonBlocking));
     CK(cudaHostAlloc((void**)&impl->mailbox, Impl::kMailboxBytes, cudaHostAllocMapped | cudaHostAllocPortable));
     g_alloc_stream = impl->stream;
@@ -250,6 +253,8 @@ Context::~Context() {
         impl->g_table.alloc(0); impl->p10.alloc(0);       // release pool memory before the stream goes away
         cudaStreamSynchronize(impl->stream); cudaStreamDestroy(impl->stream); impl->stream = nullptr; g_alloc_stream = nullptr;
         if (impl->stream2) { cudaStreamSynchronize(impl->stream2); cudaStreamDestroy(impl->stream2); impl->stream2 = nullptr; }
+        for (int k = 0; k < 2; ++k) { if (impl->side[k]) { cudaStreamSynchronize(impl->side[k]); cudaStreamDestroy(impl->side[k]); impl->side[k] = nullptr; } if (impl->ev_join[k]) { cudaEventDestroy(impl->ev_join[k]); impl->ev_join[k] = nullptr; } }
+        if (impl->ev_fork) { cudaEventDestroy(impl->ev_fork); impl->ev_fork = nullptr; }
         if (impl->copy) { cudaStreamSynchronize(impl->copy); cudaStreamDestroy(impl->copy); impl->copy = nullptr; }
         if (impl->mailbox) { cudaFreeHost(impl->mailbox); impl->mailbox = nullptr; }
         for (int i = 0; i < 8; ++i) if (impl->scratch_buf[i]) { cudaFree(impl->scratch_buf[i]); impl->scratch_buf[i] = nullptr; }
@@ -702,7 +707,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             ea = emit_args_for(S);
         }
         sp = span_begin(&tm.emit_write_ms, stB);
-        tm.launches += launch_emit_write(ea, stB);
+        tm.launches += launch_emit_write(ea, stB, impl->side, 2, impl->ev_fork, impl->ev_join);
         CK(cudaGetLastError());
         span_end(sp, stB);
         if (piped) {        // the vertex records of this sub-batch are not needed any more: hand them back in stream order

@@ -11,7 +11,7 @@ void launch_bd_build(const BdArgs& a, int blocks, cudaStream_t st);
 int launch_label_prune(LabelArgs a, int max_pool, int sm_count, cudaStream_t st);          // returns the number of kernels launched
 int label_warp_max_pool();                                                                // largest tree the shared-memory label kernel takes
 int launch_emit_sizes(const EmitArgs& a, cudaStream_t st);                                // finishes the emission records and measures every stream; returns the number of kernels launched
-int launch_emit_write(const EmitArgs& a, cudaStream_t st);                                // returns the number of kernels launched
+int launch_emit_write(const EmitArgs& a, cudaStream_t st, cudaStream_t* side, int n_side, cudaEvent_t fork, cudaEvent_t* join);   // returns the number of kernels launched; side streams (optional) run the independent write kernels next to each other
 void launch_relax_rates(bool replay, const RelaxArgs& a, int first_attempt, int only_flagged, cudaStream_t st);
 void launch_relax_apply(const RelaxArgs& a, long long total_slots, cudaStream_t st);
 void launch_relax_apply_per_rep(const RelaxArgs& a, cudaStream_t st);
