@@ -256,7 +256,7 @@ uint64_t sgp_batch_stream_bytes(const sgp_batch* b, int s) { return (b && s >= 0
 const char* sgp_batch_stream_suffix(const sgp_batch* b, int s) { return (b && s >= 0 && s < 8) ? b->b.suffix[s] : ""; }
 const int32_t* sgp_batch_status(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_info(); return b->b.status.data(); }
 const int32_t* sgp_batch_attempts(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_info(); return b->b.attempts.data(); }
-const int32_t* sgp_batch_sampled_leaves(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_info(); return b->b.sampled.data(); }
+const int32_t* sgp_batch_sampled_leaves(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_info(); if (b->b.sampled.size() != (size_t)b->b.n) b->b.sampled.assign((size_t)b->b.n, 0); return b->b.sampled.data(); }
 const double* sgp_batch_root_times(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_stats(); return b->b.root_time.data(); }
 const double* sgp_batch_total_times(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_stats(); return b->b.total_time.data(); }
 const int32_t* sgp_batch_event_counts(sgp_batch* b) { if (!b) return nullptr; b->b.fetch_stats(); return b->b.events.data(); }

@@ -337,7 +337,9 @@ void Batch::fetch_info() {
     have_info = true;
 }
 void Batch::fetch_stats() {
-    if (have_stats || !d_info) return;
+    if (have_stats) return;
+    if (app == 3) { root_time.assign((size_t)n, 0.0); total_time.assign((size_t)n, 0.0); events.assign((size_t)n * 17, 0); have_stats = true; return; }     // BranchRelaxer: no tree statistics
+    if (!d_info) return;
     cudaSetDevice(device);
     root_time.assign(n, 0.0); total_time.resize(n); events.resize((size_t)n * 17);
     if (n > 0) {
@@ -969,12 +971,13 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
     out.stream_mask = mask & 3u;
     out.suffix[0] = ""; out.suffix[1] = ".info";
     // per-replicate scalars
-    out.status.resize((size_t)n); out.attempts.resize((size_t)n); out.sampled.assign((size_t)n, 0); out.root_time.assign((size_t)n, 0.0); out.total_time.assign((size_t)n, 0.0);
-    out.events.assign((size_t)n * 17, 0);
+    // (the per-replicate tree statistics of a relaxer batch are all zero: they are materialised only if somebody asks, see fetch_stats -
+    // zero-filling 200 MB of host vectors per 2*10^6 replicates took half of a chained step)
+    out.status.resize((size_t)n); out.attempts.resize((size_t)n); out.sampled.clear();
     CK(cudaMemcpyAsync(out.status.data(), status.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out.attempts.data(), attempts.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    out.have_info = true; out.have_stats = true;
+    out.have_info = true; out.have_stats = false;
     Summary& S = out.summary;
     for (long long i = 0; i < n; ++i) { if (out.status[i] == REP_OK) ++S.n_ok; else ++S.n_failed; S.attempts_total += out.attempts[i]; }
     S.vertices_sampled = slots; S.out_bytes[0] = (long long)totals[0]; S.out_bytes[1] = (long long)totals[1];
