@@ -947,7 +947,8 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
     CK(cudaMemsetAsync(sizes.p, 0, (size_t)2 * (n + 1) * sizeof(unsigned long long), st)); CK(cudaMemsetAsync(sizes_n.p, 0, (size_t)2 * n * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(offsets.p, 0, (size_t)8 * (n + 1) * sizeof(unsigned long long), st));
     DevBuf<uint16_t> plen_tree, plen_info; plen_tree.alloc((size_t)slots); plen_info.alloc((size_t)(3 * slots + 8 * n));
-    a.plen_tree = plen_tree.p; a.plen_info = plen_info.p; a.sizes = sizes_n.p; a.offsets = offsets.p;
+    DevBuf<unsigned long long> rdig_f; DevBuf<int16_t> rdig_e; rdig_f.alloc((size_t)slots); rdig_e.alloc((size_t)slots);
+    a.plen_tree = plen_tree.p; a.plen_info = plen_info.p; a.rdig_f = rdig_f.p; a.rdig_e = rdig_e.p; a.sizes = sizes_n.p; a.offsets = offsets.p;
     a.has_outfile = (mask & 2u) ? 1 : 0;
     unsigned long long totals[2] = {0, 0};
     if (mask & 3u) {

@@ -172,6 +172,7 @@ struct RelaxArgs {
     int args_pre_off, args_pre_len, args_post_off, args_post_len, seed_mode; SeedSpec sseed;
     int model_tail_off, model_tail_len;            // "Model:\t...\nModel parameters:\n..." (constant per run)
     uint16_t* plen_tree; uint16_t* plen_info;      // cached piece lengths: [vertex slots], [3 * vertex slots + 8 * n]
+    unsigned long long* rdig_f; int16_t* rdig_e;   // cached shortest-decimal digits of the relaxed lengths: [vertex slots]
     unsigned long long* sizes;                     // [2][n]
     const unsigned long long* offsets;             // [2][n+1]
     char* out[2];

@@ -313,7 +313,8 @@ __global__ void __launch_bounds__(256) k_ingest_fill(IngestArgs g) {
 }
 
 // ---- emission -------------------------------------------------------------------------------------------------------------------
-template <class Sink> __device__ void put_relax_vertex(Sink& s, const RelaxArgs& a, const RelaxTreeView& tv, long long base, int x) {
+// (f, e): shortest-decimal digits of the relaxed length, computed once by the size pass and cached (rdig_f / rdig_e)
+template <class Sink> __device__ void put_relax_vertex(Sink& s, const RelaxArgs& a, const RelaxTreeView& tv, long long base, int x, unsigned long long dig_f, int dig_e) {
     const long long t = tv.v0 + x; const uint8_t f = a.vflags[t];
     if (f & 1) { for (int i = 0; i < a.chain[t]; ++i) s.put('('); } else s.put(')');
     if (f & 4) {
@@ -324,7 +325,7 @@ template <class Sink> __device__ void put_relax_vertex(Sink& s, const RelaxArgs&
         } else put_blob(s, a.blob, a.name_off[2 * t], a.name_off[2 * t + 1]);
     }
     const double len = a.relaxed[base + x];
-    if (len == len) { s.put(':'); put_double(s, a.T, len); }
+    if (len == len) { s.put(':'); put_decimal(s, a.T, dig_f, dig_e, dig_e == kNoDigits ? 0 : dec_len_u64(dig_f)); }
     if (a.do_meta) {
         put_lit(s, "[ID="); put_i64(s, x); put_lit(s, " ORIGBL="); put_double(s, a.T, a.orig[t]); put_lit(s, " RATE="); put_double(s, a.T, a.rates[base + x]); s.put(']');
     }
@@ -370,9 +371,19 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) k_relax_emit(RelaxArgs a) 
         uint16_t* pl = a.plen_tree + base;
         unsigned long long bytes = 0;
         if (ok) {
-            auto pc = [&](auto& s, int x) { put_relax_vertex(s, a, tv, base, x); };
-            if (WRITE) bytes = emit_pieces<true>(tv.nV, out, stage, pc, [&](int i) { return (unsigned)pl[i]; }, no_store);
-            else bytes = emit_pieces<false>(tv.nV, out, stage, pc, no_load, [&](int i, unsigned v) { pl[i] = (uint16_t)(v > 0xffffu ? 0xffffu : v); });
+            unsigned long long* df = a.rdig_f + base; int16_t* de = a.rdig_e + base;
+            if (WRITE) {
+                auto pc = [&](auto& s, int x) { put_relax_vertex(s, a, tv, base, x, df[x], (int)de[x]); };
+                bytes = emit_pieces<true>(tv.nV, out, stage, pc, [&](int i) { return (unsigned)pl[i]; }, no_store);
+            } else {
+                auto pc = [&](auto& s, int x) {
+                    uint64_t f = 0; int e = kNoDigits; const double len = a.relaxed[base + x];
+                    if (len == len) decimal_of(a.T, len, &f, &e);
+                    df[x] = (unsigned long long)f; de[x] = (int16_t)e;
+                    put_relax_vertex(s, a, tv, base, x, (unsigned long long)f, e);
+                };
+                bytes = emit_pieces<false>(tv.nV, out, stage, pc, no_load, [&](int i, unsigned v) { pl[i] = (uint16_t)(v > 0xffffu ? 0xffffu : v); });
+            }
         }
         if (!WRITE && lane == 0) a.sizes[r] = bytes;
     }
