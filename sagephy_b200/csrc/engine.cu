@@ -6,6 +6,7 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <map>
 #include <cstdio>
 #include <cstring>
 #include "engine.hpp"
@@ -206,6 +207,9 @@ struct Context::Impl {
     void post(size_t off, const void* dsrc, size_t bytes, cudaStream_t on = nullptr);
     template <class T> T take(size_t off) const { T v; memcpy(&v, mailbox + off, sizeof(T)); return v; }
     DevBuf<unsigned long long> g_table; DevBuf<double> p10;
+    // vertices per replicate seen in earlier runs of the same configuration (app + arguments without the seed value): sizes the arena
+    // of the one-pass general engine without a pilot run
+    std::map<std::string, double> nodes_per_replicate;
     MathTables T{};
     int sm_count = 148;
 };
@@ -443,6 +447,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     cudaStream_t stA = st, stB = piped ? impl->stream2 : st;
     struct Sub {
         long long r0 = 0, n = 0, total_nodes = 0, aux_stride = 1; int max_pool = 0;
+        bool one_pass = false; unsigned long long arena_cap = 0; DevBuf<unsigned long long> cursor; std::string cfg_key;     // general engine, one-pass mode
         DevBuf<unsigned long long> counter; DevBuf<long long> pool, node_off; DevBuf<int> max_pool_d;
         DevBuf<Node> nodes; DevBuf<int32_t> aux; DevBuf<double> terms; DevBuf<TreeRec> trec; DevBuf<TreeRecX> trecx; DevBuf<RowRec> rows;
         cudaEvent_t ev_found = nullptr;
@@ -476,11 +481,12 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         } else {
             // node capacity of a worker's scratch pool: typical trees fit; the rare larger ones are re-run with 8x the capacity
             int ref_leaves = cfg.host.nLeaves; for (const HostModel& g : cfg.genes) ref_leaves = std::max(ref_leaves, g.nLeaves);
-            int cap = 1024; while (cap < 6 * ref_leaves && cap < (1 << 16)) cap *= 2;
+            int cap0 = 1024; while (cap0 < 6 * ref_leaves && cap0 < (1 << 16)) cap0 *= 2;
             const int mark_n = domain ? max_gene_nv : cfg.host.nV, cnt_n = domain ? max_gene_nv : std::max(1, cfg.host.nLeaves);
-            long long workers = std::min<long long>((long long)sm * 1024, (n + 127) / 128 * 128);
+            auto general_find = [&](long long n_run, Node* arena, unsigned long long arena_cap, unsigned long long* arena_cursor, long long* node_off_out) {
+            int cap = cap0; long long workers = std::min<long long>((long long)sm * 1024, (n_run + 127) / 128 * 128);
             DevBuf<long long> redo, keep; DevBuf<unsigned long long> redo_count;
-            const long long* rep_ids = nullptr; long long todo = n;
+            const long long* rep_ids = nullptr; long long todo = n_run;
             for (int round = 0;; ++round) {
                 // bound scratch to ~24 GiB
                 while ((double)workers * cap * (sizeof(Node) + 8.0) > 24.0 * (1ull << 30) && workers > 128) workers /= 2;
@@ -512,15 +518,16 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
                 a.genes = d_genes.p; a.n_genes = (int)cfg.genes.size(); a.max_gene_nv = max_gene_nv; a.all_genes = cfg.all_genes; a.inter_gene = cfg.inter_gene; a.inter_species = cfg.inter_species;
                 a.scratch_used = scratch_used.p; a.ev_base = d_ev_base.p; a.ev_off = d_ev_off.p; a.ev_list = d_ev_list.p;
                 a.big_nodes = b_nodes; a.big_queue = b_queue; a.big_pend = b_pend; a.big_cap = big_cap; a.big_count = big_count; a.big_next = b_next.p;
+                a.arena = arena; a.arena_cap = arena_cap; a.arena_cursor = arena_cursor; a.node_off_out = node_off_out;
                 CK(cudaMemsetAsync(S.counter.p, 0, sizeof(unsigned long long), stA));
                 int blocks = (int)(workers / 128);
                 launch_find_general(replay, domain, a, blocks, stA);
                 ++tm.launches;
                 CK(cudaGetLastError());
                 // replicates that ran out of node capacity are re-run with a larger pool
-                redo.alloc((size_t)n); redo_count.alloc(1);
+                redo.alloc((size_t)n_run); redo_count.alloc(1);
                 CK(cudaMemsetAsync(redo_count.p, 0, sizeof(unsigned long long), stA));
-                k_collect_status<<<(unsigned)((n + 255) / 256), 256, 0, stA>>>(info.p, n, REP_NODE_OVERFLOW, redo.p, redo_count.p); ++tm.launches;
+                k_collect_status<<<(unsigned)((n_run + 255) / 256), 256, 0, stA>>>(info.p, n_run, REP_NODE_OVERFLOW, redo.p, redo_count.p); ++tm.launches;
                 impl->post(0, redo_count.p, sizeof(unsigned long long), stA);
                 CK(cudaStreamSynchronize(stA));
                 const unsigned long long cnt = impl->take<unsigned long long>(0);
@@ -530,15 +537,63 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
                 CK(cudaStreamSynchronize(stA));
                 rep_ids = keep.p; todo = (long long)cnt; cap *= 8; workers = std::min<long long>(workers, (todo + 127) / 128 * 128);
             }
+            };      // general_find
+            // ---- one-pass mode (large batches): accepted trees are copied into a bump-allocated arena by the find kernel itself. The
+            // arena is sized from a pilot run over a few hundred replicates (their results are overwritten by the main run); if
+            // the estimate turns out too small the vertex records are regenerated by the build kernel as in the two-pass mode.
+            S.node_off.alloc((size_t)S.n + 1); CK(cudaMemsetAsync(S.node_off.p, 0, ((size_t)S.n + 1) * sizeof(long long), stA));
+            const bool want_one_pass = n >= 8192 && getenv("SGP_TWO_PASS") == nullptr;
+            std::string cfg_key = std::to_string(cfg.app) + (replay ? "r" : "p");
+            for (size_t i = 0; i < cfg.args.size(); ++i) if ((int)i != cfg.seed_arg_index) { cfg_key += '\x1f'; cfg_key += cfg.args[i]; }
+            S.cfg_key = cfg_key;
+            const auto known = impl->nodes_per_replicate.find(cfg_key);
+            if (want_one_pass && known != impl->nodes_per_replicate.end() && getenv("SGP_ARENA_MARGIN") == nullptr) {
+                // this configuration ran before on this context: no pilot (a pilot costs one full wave of the latency-bound kernel)
+                S.arena_cap = (unsigned long long)(known->second * (double)n * 1.25) + (1ull << 20);
+                g_alloc_stream = stB; S.nodes.alloc((size_t)S.arena_cap); g_alloc_stream = stA;
+                S.cursor.alloc(1); CK(cudaMemsetAsync(S.cursor.p, 0, sizeof(unsigned long long), stA));
+                general_find(n, S.nodes.p, S.arena_cap, S.cursor.p, S.node_off.p);
+                S.one_pass = true;
+            } else if (want_one_pass) {
+                const long long n_pilot = std::max<long long>(256, n / 64);
+                general_find(n_pilot, nullptr, 0, nullptr, nullptr);
+                DevBuf<long long> ppool, poff; DevBuf<int> pmax; ppool.alloc((size_t)n_pilot + 1); poff.alloc((size_t)n_pilot + 1); pmax.alloc(1);
+                CK(cudaMemsetAsync(ppool.p, 0, ((size_t)n_pilot + 1) * sizeof(long long), stA)); CK(cudaMemsetAsync(pmax.p, 0, sizeof(int), stA));
+                k_extract_pool<<<(unsigned)((n_pilot + 255) / 256), 256, 0, stA>>>(info.p, n_pilot, ppool.p, pmax.p); ++tm.launches;
+                size_t tb = scan_tmp_bytes;
+                cub::DeviceScan::ExclusiveSum(scan_tmp.p, tb, ppool.p, poff.p, (int)(n_pilot + 1), stA); ++tm.launches;
+                impl->post(0, poff.p + n_pilot, sizeof(long long), stA); impl->post(8, pmax.p, sizeof(int), stA);
+                CK(cudaStreamSynchronize(stA));
+                const long long pilot_nodes = impl->take<long long>(0); const int pilot_max = impl->take<int>(8);
+                const double per_rep = (double)pilot_nodes / (double)n_pilot;
+                const char* me = getenv("SGP_ARENA_MARGIN");            // test hook: a margin below 1 forces the two-pass fallback
+                const double margin = me ? atof(me) : 1.25;
+                S.arena_cap = (unsigned long long)(per_rep * (double)n * margin) + (me ? 0ull : (unsigned long long)pilot_max * 64ull + (1ull << 16));
+                CK(cudaMemsetAsync(info.p, 0, (size_t)n * sizeof(RepInfo), stA));
+                g_alloc_stream = stB; S.nodes.alloc((size_t)S.arena_cap); g_alloc_stream = stA;
+                S.cursor.alloc(1); CK(cudaMemsetAsync(S.cursor.p, 0, sizeof(unsigned long long), stA));
+                general_find(n, S.nodes.p, S.arena_cap, S.cursor.p, S.node_off.p);
+                S.one_pass = true;
+            } else general_find(n, nullptr, 0, nullptr, nullptr);
         }
         span_end(sp, stA);
         // node offsets of the sub-batch: exclusive scan of the accepted attempts' pool sizes
-        S.pool.alloc((size_t)S.n + 1); S.node_off.alloc((size_t)S.n + 1); S.max_pool_d.alloc(1);
+        S.pool.alloc((size_t)S.n + 1); if (!S.node_off.p) S.node_off.alloc((size_t)S.n + 1); S.max_pool_d.alloc(1);
         CK(cudaMemsetAsync(S.pool.p, 0, ((size_t)S.n + 1) * sizeof(long long), stA));
         CK(cudaMemsetAsync(S.max_pool_d.p, 0, sizeof(int), stA));
         k_extract_pool<<<(unsigned)((S.n + 255) / 256), 256, 0, stA>>>(info.p + S.r0, S.n, S.pool.p, S.max_pool_d.p); ++tm.launches;
-        size_t tb = scan_tmp_bytes;
-        cub::DeviceScan::ExclusiveSum(scan_tmp.p, tb, S.pool.p, S.node_off.p, (int)(S.n + 1), stA); ++tm.launches;
+        if (S.one_pass) {
+            // the arena is filled already; did every accepted tree fit?
+            impl->post(0, S.cursor.p, sizeof(unsigned long long), stA);
+            CK(cudaStreamSynchronize(stA));
+            const unsigned long long used = impl->take<unsigned long long>(0);
+            if (used > S.arena_cap) { S.one_pass = false; g_alloc_stream = stB; S.nodes.alloc(0); g_alloc_stream = stA; }       // too small: two-pass (the find results stand, only the copies are incomplete)
+            else CK(cudaMemcpyAsync(S.node_off.p + S.n, S.cursor.p, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stA));      // "total" slot
+        }
+        if (!S.one_pass) {
+            size_t tb = scan_tmp_bytes;
+            cub::DeviceScan::ExclusiveSum(scan_tmp.p, tb, S.pool.p, S.node_off.p, (int)(S.n + 1), stA); ++tm.launches;
+        }
         impl->post(kMailFind + (size_t)(k & 15) * 16, S.node_off.p + S.n, sizeof(long long), stA); impl->post(kMailFind + (size_t)(k & 15) * 16 + 8, S.max_pool_d.p, sizeof(int), stA);
         CK(cudaEventRecord(S.ev_found, stA));
     };
@@ -626,12 +681,17 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         S.total_nodes = impl->take<long long>(kMailFind + (size_t)(k & 15) * 16); S.max_pool = impl->take<int>(kMailFind + (size_t)(k & 15) * 16 + 8);
         if (piped) CK(cudaStreamWaitEvent(stB, S.ev_found, 0));
         g_alloc_stream = stB;
-        S.aux_stride = std::max<long long>(S.total_nodes, 1);
+        if (!fast_bd && !S.cfg_key.empty() && S.n > 0) {
+            double& seen = impl->nodes_per_replicate[S.cfg_key];
+            seen = std::max(seen, (double)S.total_nodes / (double)S.n);
+        }
+        S.aux_stride = S.one_pass ? (long long)S.arena_cap : std::max<long long>(S.total_nodes, 1);
         // the order arrays and the labelled vertex records are only kept for chained stages and for trees too large for the
         // shared-memory label kernel; everything else leaves the label kernel as emission records
         const bool keep_nodes = opts.keep_trees || S.max_pool > label_warp_max_pool();
         const bool want_rows = (mask & 0xF0u) != 0, want_trees = (mask & 0x3u) != 0;
-        S.nodes.alloc((size_t)S.aux_stride); if (keep_nodes || !fast_bd) S.aux.alloc((size_t)S.aux_stride * 4);      // (the general build kernel uses them as scratch)
+        if (!S.one_pass) S.nodes.alloc((size_t)S.aux_stride);
+        if (keep_nodes || (!fast_bd && !S.one_pass)) S.aux.alloc((size_t)S.aux_stride * 4);      // (the general build kernel uses them as scratch)
         if (want_trees) { S.trec.alloc((size_t)2 * S.aux_stride); if (cfg.app != 0) S.trecx.alloc((size_t)2 * S.aux_stride); }
         if (want_rows) S.rows.alloc((size_t)2 * S.aux_stride);
         S.terms.alloc((size_t)(cfg.app == 0 ? 2 : 4) * S.aux_stride);
@@ -641,7 +701,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             BdArgs a{}; a.P = P; a.H = make_tiny(cfg.host); a.T = impl->T; a.n = S.n; a.rep_base = opts.offset + S.r0; a.seed = seed; a.keys = philox_keys(seed); a.info = info.p + S.r0;
             a.node_off = S.node_off.p; a.nodes = S.nodes.p;
             launch_bd_build(a, (int)((S.n + 255) / 256), stB); ++tm.launches;
-        } else {
+        } else if (!S.one_pass) {
             const long long threads = std::max<long long>(128, std::min<long long>((long long)sm * 1024, (n + 127) / 128 * 128));
             marks.alloc((size_t)threads * (domain ? max_gene_nv : cfg.host.nV));
             {

@@ -39,6 +39,9 @@ struct FindArgs {
     // replicate at once instead of leaving it to a later, latency-bound launch
     Node* big_nodes; int32_t* big_queue; int32_t* big_pend; int big_cap, big_count; int* big_next;
     const int32_t* ev_base; const int32_t* ev_off; const int32_t* ev_list;    // inter-gene candidate index: vertices of gene g whose first epoch is e = ev_list[ev_off[ev_base[g] + e] .. ev_off[ev_base[g] + e + 1])
+    // one-pass mode: an accepted tree is copied from the lane's scratch pool into the arena by the whole warp (bump allocation;
+    // node_off_out[r] = its first record). arena == nullptr: the build kernel regenerates the accepted attempts instead.
+    Node* arena; unsigned long long arena_cap; unsigned long long* arena_cursor; long long* node_off_out;
 };
 
 struct BuildArgs {

@@ -47,7 +47,40 @@ __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
     EngineState<DOMAIN> S; S.stage = -1;
     bool have = false, exhausted = false, again = false, big = false;
     long long r = 0; RepInfo inf; int attempts = 0; uint64_t verts = 0, pos = 0;
+    bool copy_pending = false; long long copy_r = 0; int copy_n = 0;
     for (;;) {
+        if (a.arena) {
+            // One-pass mode: the trees accepted in the previous trip leave their lanes' scratch pools for the arena before the lanes
+            // start anything new. The whole warp copies (16 bytes per lane, contiguous on both sides) - regenerating the tree in a
+            // second kernel cost 40 % of the sampling time, a per-lane copy as much as that.
+            unsigned cp = __ballot_sync(0xffffffffu, copy_pending);
+            while (cp) {
+                const int l = __ffs(cp) - 1; cp &= cp - 1;
+                const int nn = __shfl_sync(0xffffffffu, copy_n, l);
+                const long long rr = __shfl_sync(0xffffffffu, copy_r, l);
+                const uint4* s4 = reinterpret_cast<const uint4*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(W.nodes), l));
+                unsigned long long off = 0;
+                if ((threadIdx.x & 31) == 0) off = atomicAdd(a.arena_cursor, (unsigned long long)nn);
+                off = __shfl_sync(0xffffffffu, off, 0);
+                if (off + (unsigned long long)nn <= a.arena_cap) {
+                    uint4* d4 = reinterpret_cast<uint4*>(a.arena + off);
+                    const int nq = nn * (int)(sizeof(Node) / 16);
+                    // eight loads in flight per lane (the source is cold: one load per trip made the copy latency-bound)
+                    int i = threadIdx.x & 31;
+                    for (; i + 7 * 32 < nq; i += 8 * 32) {
+                        uint4 v[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = s4[i + q * 32];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) d4[i + q * 32] = v[q];
+                    }
+                    for (; i < nq; i += 32) d4[i] = s4[i];
+                    if ((threadIdx.x & 31) == 0) a.node_off_out[rr] = (long long)off;
+                }       // else: the cursor ends beyond the capacity; the engine sees that and lets the build kernel regenerate every tree
+            }
+            copy_pending = false;
+            __syncwarp();
+        }
         if (!have && !exhausted) {
             long long slot = 0;
             if (!again) slot = (long long)atomicAdd(a.work_counter, 1ULL);
@@ -103,7 +136,8 @@ __global__ void __launch_bounds__(128) k_find_general(FindArgs a) {
                     if constexpr (DOMAIN) ok = attempt_ok_domain(a.P, a.H, E, W, root, inf.exact, a.max_gene_nv, a.per_leaf_check != 0, a.all_genes != 0, &sampled);
                     else { ok = attempt_ok_counted(a.P, S, W, inf.exact); sampled = S.sampled; }
                     if (ok) {
-                        inf.status = REP_OK; inf.n_pool = n; inf.sampled_leaves = sampled;
+                        inf.status = REP_OK; inf.n_pool = n; inf.sampled_leaves = sampled; inf.root = root;
+                        copy_pending = true; copy_r = r; copy_n = n;
                         if (REPLAY) { inf.acc_attempt = (uint32_t)pos; inf.acc_hi = (uint32_t)(pos >> 32); } else { inf.acc_attempt = (uint32_t)(attempts - 1); inf.acc_hi = 0; }
                         ++attempts;     // GuestTreeMachina.java:107
                         inf.attempts = attempts; inf.vertices_sampled = verts; a.info[r] = inf; have = false;

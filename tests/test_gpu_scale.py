@@ -374,3 +374,46 @@ def test_pipelined_run_equals_serial_run(ctx, monkeypatch):
     assert again.timings()["sub_batches"] == 1
     for s in range(4):
         assert again.stream(s) == serial.stream(s), s
+
+
+# ---- general engine, one-pass mode (accepted trees copied into a bump-allocated arena by the find kernel) --------------------------------
+def test_one_pass_general_engine_equals_two_pass(ctx, monkeypatch, tmp_path):
+    """Batches of >= 8192 replicates skip the build kernel: the find kernel's warps copy every accepted tree into an arena sized from a
+    pilot run. Same bytes as the two-pass mode (SGP_TWO_PASS), also when the arena estimate is too small (forced: the engine then
+    falls back to the build kernel), in both RNG modes; and replicates of the one-pass run are the oracle's, byte for byte."""
+    from oracle_util import oracle_run
+    n = 9000
+    cases = [("GuestTreeGen", ["-s", "61", "-db", "simple", HOST8, "0.5", "0.3", "0.8", "g"])]
+    d = tmp_path / "genes"; d.mkdir()
+    for i in range(1, 4):
+        f = oracle_run("GuestTreeGen", ["-s", str(i), "-db", "none", HOST8, "0.4", "0.2", "0.2", "g"])["files"]
+        (d / f"gene{i}.tree").write_bytes(f["g.pruned.tree"])
+    cases.append(("DomainTreeGen", ["-s", "62", "-ig", "0.6", HOST8, str(d), "0.4", "0.3", "0.7", "o"]))
+    for app, args in cases:
+        for rng in (sg.RNG_MT_REPLAY, sg.RNG_PHILOX):
+            one = ctx.run(app, args, n=n, rng=rng)
+            assert one.timings()["build_ms"] < 0.05                     # no build kernel ran
+            monkeypatch.setenv("SGP_TWO_PASS", "1")
+            two = ctx.run(app, args, n=n, rng=rng)
+            monkeypatch.delenv("SGP_TWO_PASS")
+            assert two.timings()["build_ms"] > 0.05
+            monkeypatch.setenv("SGP_ARENA_MARGIN", "0.4")
+            small = ctx.run(app, args, n=n, rng=rng)
+            monkeypatch.delenv("SGP_ARENA_MARGIN")
+            assert small.timings()["build_ms"] > 0.05                   # the arena was too small: rebuilt
+            assert (one.rep_status == two.rep_status).all() and (one.attempts == two.attempts).all()
+            for s in range(8):
+                assert one.stream_bytes(s) == two.stream_bytes(s) == small.stream_bytes(s)
+                assert bytes(one.stream(s)) == bytes(two.stream(s)), (app, rng, s)
+                assert bytes(small.stream(s)) == bytes(two.stream(s)), (app, rng, s)
+            if rng == sg.RNG_MT_REPLAY:
+                seed0 = int(args[1])
+                for i in (0, 1, n // 2, n - 1):
+                    a2 = list(args); a2[1] = str(seed0 + i)
+                    want = oracle_run(app, a2)
+                    if want["status"] != 0:
+                        continue
+                    prefix = args[-1]
+                    for sfx, data in one.files(i).items():
+                        assert data == want["files"][prefix + sfx], (app, i, sfx)
+            one.free(); two.free(); small.free()
