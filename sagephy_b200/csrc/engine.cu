@@ -688,7 +688,16 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         S.aux_stride = S.one_pass ? (long long)S.arena_cap : std::max<long long>(S.total_nodes, 1);
         // the order arrays and the labelled vertex records are only kept for chained stages and for trees too large for the
         // shared-memory label kernel; everything else leaves the label kernel as emission records
-        const bool keep_nodes = opts.keep_trees || S.max_pool > label_warp_max_pool();
+        // trees above the shared-memory label kernel's reach are labelled in place with global work arrays (bounded to ~2 GB);
+        // only if even that does not fit do they go to the thread-per-tree kernel, which needs the order arrays
+        int work_blocks = 0; long long work_stride = 0; int32_t* work = nullptr;
+        const bool thread_label = getenv("SGP_LABEL_THREAD_KERNEL") != nullptr;
+        if (S.max_pool > label_smem_max_pool() && !thread_label) {
+            work_stride = 9ll * (S.max_pool + 2) + 16;
+            work_blocks = (int)std::min<long long>((long long)sm * 8, (2ll << 30) / (work_stride * 4));
+            if (work_blocks >= 16) work = (int32_t*)impl->scratch(6, (size_t)work_blocks * work_stride * 4); else work_blocks = 0;
+        }
+        const bool keep_nodes = opts.keep_trees || (S.max_pool > label_smem_max_pool() && work_blocks == 0);
         const bool want_rows = (mask & 0xF0u) != 0, want_trees = (mask & 0x3u) != 0;
         if (!S.one_pass) S.nodes.alloc((size_t)S.aux_stride);
         if (keep_nodes || (!fast_bd && !S.one_pass)) S.aux.alloc((size_t)S.aux_stride * 4);      // (the general build kernel uses them as scratch)
@@ -737,7 +746,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             LabelArgs a{}; a.n = S.n; a.info = info.p + S.r0; a.node_off = S.node_off.p; a.nodes = S.nodes.p; a.aux = S.aux.p; a.aux_stride = S.aux_stride; a.T = impl->T;
             a.host_root_time = cfg.host.vtime[cfg.host.root]; a.has_stem_override = cfg.has_stem_override; a.stem_override = cfg.stem_override;
             a.pool = S.pool.p;
-            a.write_nodes = keep_nodes ? 1 : 0; a.E = emit_args_for(S); a.terms = S.terms.p; a.want_beneath = cfg.app == 0 ? 0 : 1;
+            a.write_nodes = keep_nodes ? 1 : 0; a.work = work; a.work_stride = work_stride; a.work_blocks = work_blocks; a.E = emit_args_for(S); a.terms = S.terms.p; a.want_beneath = cfg.app == 0 ? 0 : 1;
             tm.launches += launch_label_prune(a, S.max_pool, impl->sm_count, stB);
             CK(cudaGetLastError());
         }

@@ -14,8 +14,9 @@ int launch_label_prune(LabelArgs a, int max_pool, int sm_count, cudaStream_t st)
         throw SgpError("cannot opt in to large dynamic shared memory for the label kernel on this device");
     int launches = 0, lo = 0;
     const bool thread_only = getenv("SGP_LABEL_THREAD_KERNEL") != nullptr;      // test hook: exercise the fallback on small trees
+    const bool global_only = getenv("SGP_LABEL_GLOBAL_KERNEL") != nullptr;      // test hook: every tree through the in-place warp kernel
     for (int cap : caps) {
-        if (thread_only) break;
+        if (thread_only || global_only) break;
         a.min_pool = lo; a.cap = cap;
         const size_t smem = label_smem_bytes(cap);
         if (smem + 2048 > (size_t)kMaxSmem) break;
@@ -26,13 +27,20 @@ int launch_label_prune(LabelArgs a, int max_pool, int sm_count, cudaStream_t st)
         lo = cap;
         if (cap >= max_pool) break;
     }
-    if (lo > 0) { LabelArgs b = a; b.cap = lo; k_info_sums<<<(unsigned)((4 * a.n + 127) / 128), 128, 0, st>>>(b); ++launches; }
-    if (max_pool > lo) {
+    // trees above the largest shared-memory class: the warp algorithm in place, work arrays in the scratch the engine passed
+    int warp_max = lo;
+    if (max_pool > lo && !thread_only && a.work && a.work_blocks > 0 && a.work_stride >= 9ll * (max_pool + 2)) {
+        LabelArgs g = a; g.min_pool = lo; g.cap = max_pool;
+        k_label_prune_warp_global<<<a.work_blocks, 32, 0, st>>>(g); ++launches;
+        warp_max = max_pool;
+    }
+    if (warp_max > 0) { LabelArgs b = a; b.cap = warp_max; k_info_sums<<<(unsigned)((4 * a.n + 127) / 128), 128, 0, st>>>(b); ++launches; }
+    if (max_pool > warp_max) {
         if (!a.aux || !a.write_nodes) throw SgpError("internal: oversized trees need the order arrays");
-        a.cap = lo; k_label_prune<<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(a); ++launches;
+        a.cap = warp_max; k_label_prune<<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(a); ++launches;
         k_records_from_nodes<<<(unsigned)((a.n * 32 + 127) / 128), 128, 0, st>>>(a); ++launches;
     }
     return launches;
 }
-int label_warp_max_pool() { return getenv("SGP_LABEL_THREAD_KERNEL") ? 0 : 2340; }
+int label_smem_max_pool() { return (getenv("SGP_LABEL_THREAD_KERNEL") || getenv("SGP_LABEL_GLOBAL_KERNEL")) ? 0 : 2340; }
 }  // namespace sgp

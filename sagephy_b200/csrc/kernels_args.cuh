@@ -128,6 +128,7 @@ struct LabelArgs {
     const long long* pool;                  // vertices per replicate (0: failed)
     int min_pool, cap;                      // warp kernel: size class (min_pool, cap]; thread kernel: trees above cap
     double* terms; int want_beneath;        // [4][aux_stride] terms of the getInfo sums in breadth-first order: total U, total P, beneath-stem U, P (the last two if want_beneath)
+    int32_t* work; long long work_stride; int work_blocks;   // k_label_prune_warp_global: work_blocks blocks with work_stride >= 9 * (max_pool + 2) ints of scratch each
     int write_nodes;                        // write the labelled vertex records and the order arrays back (chained stages, oversized trees)
     EmitArgs E;                             // formats and the record arrays the kernel fills in
 };

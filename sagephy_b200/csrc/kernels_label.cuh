@@ -162,17 +162,180 @@ __device__ __forceinline__ void make_records(const EmitArgs& E, long long goff, 
 //      survivors only; vertex numbers (survivors first, PruningHelper.java:25-90) and both post-order arrays follow directly
 //   4. breadth-first order of the pruned view with its marks and counts
 //   5. the getInfo sums, which are order-dependent floating-point sums: lane 0 adds the unpruned, lane 1 the pruned tree
+// Labels, prunes and numbers ONE tree with a whole warp (steps 1-5 above) and leaves its emission records, getInfo terms and
+// RepInfo fields. sN = the tree's vertex records (shared memory, or in place in the arena for trees that do not fit), W = nine work
+// arrays of `cap` (+2) entries of index type I, s_cnt = two zero-initialisable event histograms of the warp.
+template <class I>
+__device__ __forceinline__ void label_tree_by_warp(const LabelArgs& a, RepInfo& inf, long long goff, int n_pool, Node* sN, I* W, int cap,
+                                                   int32_t (*s_cnt)[EV_COUNT], bool in_place) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    I* bfsU = W;
+    I *ordU = bfsU + cap, *ordP = ordU + cap, *bfsP = ordP + cap, *pr = bfsP /* dead before bfsP is written */;
+    I *sz = bfsP + cap, *ns = sz + cap, *off = ns + cap, *offS = off + cap, *lvl = offS + cap;     // lvl: cap + 2 entries
+    const int root = inf.root;
+    for (int i = lane; i < 2 * EV_COUNT; i += 32) (&s_cnt[0][0])[i] = 0;
+    if (lane == 0) { bfsU[0] = (I)root; lvl[0] = 0; off[root] = 0; offS[root] = 0; }
+    __syncwarp();
+    {
+        // right children the birth-death build kernel left unlinked (NF_RIGHT_CHILD)
+        for (int v = lane; v < n_pool; v += 32) {
+            Node& x = sN[v]; if (x.flags & NF_RIGHT_CHILD) { sN[x.parent].right = v; x.flags &= (uint8_t)~NF_RIGHT_CHILD; }
+            x.p_left = -1; x.p_right = -1; x.flags &= (uint8_t)~NF_DETACHED;          // (the samplers use p_left as a per-arc list link)
+        }
+        __syncwarp();
+        // ---- 1. breadth-first order, levels
+        int D = 0, up;
+        {
+            int lo = 0, hi = 1;
+            while (lo < hi) {
+                ++D; if (lane == 0) lvl[D] = (I)hi;
+                int t = hi;
+                for (int b0 = lo; b0 < hi; b0 += 32) {
+                    const int k = b0 + lane; int l = -1, rr = -1;
+                    if (k < hi) {
+                        Node& x = sN[bfsU[k]]; l = x.left; rr = x.right;
+                        if (l >= 0) { Node& L = sN[l]; L.flags |= NF_LEFT_U; L.chain_u = (I)(x.chain_u + 1); sN[rr].chain_u = 0; }
+                        atomicAdd(&s_cnt[0][x.event], 1);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, l >= 0);
+                    if (l >= 0) { const int pos = t + 2 * __popc(m & lt_mask); bfsU[pos] = (I)l; bfsU[pos + 1] = (I)rr; }
+                    t += 2 * __popc(m);
+                }
+                __syncwarp();
+                lo = hi; hi = t;
+            }
+            up = hi;
+        }
+        // ---- 2. bottom-up
+        for (int d = D - 1; d >= 0; --d) {
+            const int lo = lvl[d], hi = lvl[d + 1];
+            for (int k = lo + lane; k < hi; k += 32) {
+                const int v = bfsU[k]; Node& x = sN[v];
+                const int l = x.left;
+                uint8_t prun; int size = 1, surv = 0;
+                if (l < 0) {
+                    const bool leaf = x.event == EV_LEAF;
+                    prun = leaf ? PR_UNPRUNABLE : PR_PRUNABLE; surv = leaf ? 1 : 0;
+                    if (leaf) { pr[v] = (I)v; x.p_bl = x.bl; x.p_left = -1; x.p_right = -1; } else pr[v] = -1;
+                } else {
+                    const int rr = x.right;
+                    const uint8_t pl = sN[l].prun, pq = sN[rr].prun;
+                    size += sz[l] + sz[rr]; surv = ns[l] + ns[rr];
+                    if (pl == PR_PRUNABLE && pq == PR_PRUNABLE) { prun = PR_PRUNABLE; pr[v] = -1; }
+                    else if (pl == PR_PRUNABLE || pq == PR_PRUNABLE) { prun = PR_COLLAPSABLE; pr[v] = pr[pl == PR_PRUNABLE ? rr : l]; }
+                    else { prun = PR_UNPRUNABLE; ++surv; x.p_left = pr[l]; x.p_right = pr[rr]; x.p_bl = x.bl; pr[v] = (I)v; }
+                }
+                x.prun = prun; sz[v] = (I)size; ns[v] = (I)surv;
+            }
+            __syncwarp();
+        }
+        const int nu = ns[root], p_root = pr[root];
+        // ---- 2b. collapse chains: gather the survivors whose parent collapses (list in ordU, which step 3 rewrites), then fold
+        {
+            int n_chain = 0;
+            for (int b0 = 0; b0 < up; b0 += 32) {
+                const int k = b0 + lane; bool start = false; int v = -1;
+                if (k < up) { v = bfsU[k]; const Node& x = sN[v]; start = x.prun == PR_UNPRUNABLE && x.parent >= 0 && sN[x.parent].prun == PR_COLLAPSABLE; }
+                const unsigned m = __ballot_sync(0xffffffffu, start);
+                if (start) ordU[n_chain + __popc(m & lt_mask)] = (I)v;        // ordU is free until step 3
+                n_chain += __popc(m);
+            }
+            __syncwarp();
+            for (int k = lane; k < n_chain; k += 32) {
+                Node& c = sN[ordU[k]];
+                double len = c.p_bl; int p = c.parent;
+                while (p >= 0 && sN[p].prun == PR_COLLAPSABLE) { len = round_sig(a.T, XADD(len, sN[p].bl), 8); p = sN[p].parent; }
+                c.p_bl = len;
+            }
+            __syncwarp();
+        }
+        // ---- 3. top-down: post-order positions and vertex numbers
+        for (int d = 0; d < D; ++d) {
+            const int lo = lvl[d], hi = lvl[d + 1];
+            for (int k = lo + lane; k < hi; k += 32) {
+                const int v = bfsU[k]; Node& x = sN[v];
+                const int o = off[v], os = offS[v], size = sz[v], surv = ns[v];
+                const int post = o + size - 1;
+                ordU[post] = (I)v;
+                if (x.prun == PR_UNPRUNABLE) { const int ps = os + surv - 1; x.number = ps; ordP[ps] = (I)v; }
+                else x.number = nu + post - (os + surv);
+                const int l = x.left;
+                if (l >= 0) { const int rr = x.right; off[l] = (I)o; offS[l] = (I)os; off[rr] = (I)(o + sz[l]); offS[rr] = (I)(os + ns[l]); }
+            }
+            __syncwarp();
+        }
+        if (lane == 0 && a.has_stem_override) { sN[root].bl = a.stem_override; if (p_root >= 0) sN[p_root].p_bl = a.stem_override; }
+        // ---- 4. breadth-first order of the pruned view (pr is dead from here on)
+        if (p_root >= 0) {
+            if (lane == 0) bfsP[0] = (I)p_root;
+            __syncwarp();
+            int lo = 0, hi = 1;
+            while (lo < hi) {
+                int t = hi;
+                for (int b0 = lo; b0 < hi; b0 += 32) {
+                    const int k = b0 + lane; int l = -1, rr = -1;
+                    if (k < hi) {
+                        Node& x = sN[bfsP[k]]; l = x.p_left; rr = x.p_right;
+                        x.flags |= NF_IN_PRUNED;
+                        if (l >= 0) { Node& L = sN[l]; L.flags |= NF_LEFT_P; L.chain_p = (I)(x.chain_p + 1); sN[rr].chain_p = 0; }
+                        atomicAdd(&s_cnt[1][x.event], 1);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, l >= 0);
+                    if (l >= 0) { const int pos = t + 2 * __popc(m & lt_mask); bfsP[pos] = (I)l; bfsP[pos + 1] = (I)rr; }
+                    t += 2 * __popc(m);
+                }
+                __syncwarp();
+                lo = hi; hi = t;
+            }
+        }
+        __syncwarp();
+        // ---- 5. the terms of the getInfo sums in breadth-first order (GuestTreeInHostTreeCreator.java:431-511). The sums themselves are
+        // order-dependent floating-point additions, i.e. serial: k_info_sums adds them up with a thread per sum and full occupancy
+        // (here they kept one or two lanes of the warp busy for 44 % of the kernel's instructions).
+        {
+            double* tU = a.terms + goff; double* tP = a.terms + a.aux_stride + goff;
+            double* bU = a.terms + 2 * a.aux_stride + goff; double* bP = a.terms + 3 * a.aux_stride + goff;
+            for (int k = lane; k < up; k += 32) {
+                const Node& x = sN[bfsU[k]]; tU[k] = x.bl;
+                if (a.want_beneath) bU[k] = fmax(fmin(XSUB(a.host_root_time, x.abstime), x.bl), 0.0);
+            }
+            for (int k = lane; k < nu; k += 32) {
+                const Node& x = sN[bfsP[k]]; tP[k] = x.p_bl;
+                if (a.want_beneath) bP[k] = fmax(fmin(XSUB(a.host_root_time, x.abstime), x.p_bl), 0.0);
+            }
+        }
+        {
+            if (a.write_nodes && !in_place) {
+                uint4* dst = reinterpret_cast<uint4*>(a.nodes + goff); const uint4* src = reinterpret_cast<const uint4*>(sN);
+                const int nq = n_pool * (int)(sizeof(Node) / 16);
+                for (int i = lane; i < nq; i += 32) dst[i] = src[i];
+            }
+            if (a.write_nodes && a.aux) {
+                int32_t* gOrdU = a.aux + goff; int32_t* gOrdP = a.aux + a.aux_stride + goff;
+                int32_t* gBfsU = a.aux + 2 * a.aux_stride + goff; int32_t* gBfsP = a.aux + 3 * a.aux_stride + goff;
+                for (int k = lane; k < up; k += 32) { gOrdU[k] = ordU[k]; gBfsU[k] = bfsU[k]; }
+                for (int k = lane; k < nu; k += 32) { gOrdP[k] = ordP[k]; gBfsP[k] = bfsP[k]; }
+            }
+            make_records<I>(a.E, goff, sN, ordU, ordP, bfsU, bfsP, up, nu, root, p_root, off, offS);      // (off / offS: dead work arrays)
+            if (lane < EV_COUNT) { inf.cnt_u[lane] = s_cnt[0][lane]; inf.cnt_p[lane] = s_cnt[1][lane]; }
+            if (lane == 0) {
+                inf.p_root = p_root; inf.n_u = up; inf.n_p = nu; inf.p_root_time = p_root >= 0 ? sN[p_root].abstime : 0.0;
+                inf.root_gtree_u = sN[root].gtree; inf.root_gtree_p = sN[p_root >= 0 ? p_root : root].gtree;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(32) k_label_prune_warp(LabelArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int32_t s_cnt[2][EV_COUNT];
     __shared__ __align__(8) unsigned long long s_mbar;
     const int cap = a.cap;
     Node* sN = reinterpret_cast<Node*>(smem);
-    int16_t* bfsU = reinterpret_cast<int16_t*>(smem + (size_t)cap * sizeof(Node));
-    int16_t *ordU = bfsU + cap, *ordP = ordU + cap, *bfsP = ordP + cap, *pr = bfsP /* dead before bfsP is written */;
-    int16_t *sz = bfsP + cap, *ns = sz + cap, *off = ns + cap, *offS = off + cap, *lvl = offS + cap;     // lvl: cap + 2 entries
+    int16_t* work = reinterpret_cast<int16_t*>(smem + (size_t)cap * sizeof(Node));
     const int lane = threadIdx.x;
-    const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar), sN_addr = (uint32_t)__cvta_generic_to_shared(sN);
     if (lane == 0) mbar_init(mbar, 1);
     __syncwarp();
@@ -203,158 +366,26 @@ __global__ void __launch_bounds__(32) k_label_prune_warp(LabelArgs a) {
                 const long long ngoff = __shfl_sync(0xffffffffu, goff_lane, nb); const int nnp = __shfl_sync(0xffffffffu, np_lane, nb);
                 if (lane == 0) prefetch_l2_bulk(a.nodes + ngoff, (uint32_t)nnp * (uint32_t)sizeof(Node));
             }
-            for (int i = lane; i < 2 * EV_COUNT; i += 32) (&s_cnt[0][0])[i] = 0;
         }
-        const int root = inf.root;
-        if (lane == 0) { bfsU[0] = (int16_t)root; lvl[0] = 0; off[root] = 0; offS[root] = 0; }
         mbar_wait(mbar, phase); phase ^= 1u;
         __syncwarp();
-        // right children the birth-death build kernel left unlinked (NF_RIGHT_CHILD)
-        for (int v = lane; v < n_pool; v += 32) {
-            Node& x = sN[v]; if (x.flags & NF_RIGHT_CHILD) { sN[x.parent].right = v; x.flags &= (uint8_t)~NF_RIGHT_CHILD; }
-            x.p_left = -1; x.p_right = -1; x.flags &= (uint8_t)~NF_DETACHED;          // (the samplers use p_left as a per-arc list link)
-        }
-        __syncwarp();
-        // ---- 1. breadth-first order, levels
-        int D = 0, up;
-        {
-            int lo = 0, hi = 1;
-            while (lo < hi) {
-                ++D; if (lane == 0) lvl[D] = (int16_t)hi;
-                int t = hi;
-                for (int b0 = lo; b0 < hi; b0 += 32) {
-                    const int k = b0 + lane; int l = -1, rr = -1;
-                    if (k < hi) {
-                        Node& x = sN[bfsU[k]]; l = x.left; rr = x.right;
-                        if (l >= 0) { Node& L = sN[l]; L.flags |= NF_LEFT_U; L.chain_u = (int16_t)(x.chain_u + 1); sN[rr].chain_u = 0; }
-                        atomicAdd(&s_cnt[0][x.event], 1);
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, l >= 0);
-                    if (l >= 0) { const int pos = t + 2 * __popc(m & lt_mask); bfsU[pos] = (int16_t)l; bfsU[pos + 1] = (int16_t)rr; }
-                    t += 2 * __popc(m);
-                }
-                __syncwarp();
-                lo = hi; hi = t;
-            }
-            up = hi;
-        }
-        // ---- 2. bottom-up
-        for (int d = D - 1; d >= 0; --d) {
-            const int lo = lvl[d], hi = lvl[d + 1];
-            for (int k = lo + lane; k < hi; k += 32) {
-                const int v = bfsU[k]; Node& x = sN[v];
-                const int l = x.left;
-                uint8_t prun; int size = 1, surv = 0;
-                if (l < 0) {
-                    const bool leaf = x.event == EV_LEAF;
-                    prun = leaf ? PR_UNPRUNABLE : PR_PRUNABLE; surv = leaf ? 1 : 0;
-                    if (leaf) { pr[v] = (int16_t)v; x.p_bl = x.bl; x.p_left = -1; x.p_right = -1; } else pr[v] = -1;
-                } else {
-                    const int rr = x.right;
-                    const uint8_t pl = sN[l].prun, pq = sN[rr].prun;
-                    size += sz[l] + sz[rr]; surv = ns[l] + ns[rr];
-                    if (pl == PR_PRUNABLE && pq == PR_PRUNABLE) { prun = PR_PRUNABLE; pr[v] = -1; }
-                    else if (pl == PR_PRUNABLE || pq == PR_PRUNABLE) { prun = PR_COLLAPSABLE; pr[v] = pr[pl == PR_PRUNABLE ? rr : l]; }
-                    else { prun = PR_UNPRUNABLE; ++surv; x.p_left = pr[l]; x.p_right = pr[rr]; x.p_bl = x.bl; pr[v] = (int16_t)v; }
-                }
-                x.prun = prun; sz[v] = (int16_t)size; ns[v] = (int16_t)surv;
-            }
-            __syncwarp();
-        }
-        const int nu = ns[root], p_root = pr[root];
-        // ---- 2b. collapse chains: gather the survivors whose parent collapses (list in ordU, which step 3 rewrites), then fold
-        {
-            int n_chain = 0;
-            for (int b0 = 0; b0 < up; b0 += 32) {
-                const int k = b0 + lane; bool start = false; int v = -1;
-                if (k < up) { v = bfsU[k]; const Node& x = sN[v]; start = x.prun == PR_UNPRUNABLE && x.parent >= 0 && sN[x.parent].prun == PR_COLLAPSABLE; }
-                const unsigned m = __ballot_sync(0xffffffffu, start);
-                if (start) ordU[n_chain + __popc(m & lt_mask)] = (int16_t)v;        // ordU is free until step 3
-                n_chain += __popc(m);
-            }
-            __syncwarp();
-            for (int k = lane; k < n_chain; k += 32) {
-                Node& c = sN[ordU[k]];
-                double len = c.p_bl; int p = c.parent;
-                while (p >= 0 && sN[p].prun == PR_COLLAPSABLE) { len = round_sig(a.T, XADD(len, sN[p].bl), 8); p = sN[p].parent; }
-                c.p_bl = len;
-            }
-            __syncwarp();
-        }
-        // ---- 3. top-down: post-order positions and vertex numbers
-        for (int d = 0; d < D; ++d) {
-            const int lo = lvl[d], hi = lvl[d + 1];
-            for (int k = lo + lane; k < hi; k += 32) {
-                const int v = bfsU[k]; Node& x = sN[v];
-                const int o = off[v], os = offS[v], size = sz[v], surv = ns[v];
-                const int post = o + size - 1;
-                ordU[post] = (int16_t)v;
-                if (x.prun == PR_UNPRUNABLE) { const int ps = os + surv - 1; x.number = ps; ordP[ps] = (int16_t)v; }
-                else x.number = nu + post - (os + surv);
-                const int l = x.left;
-                if (l >= 0) { const int rr = x.right; off[l] = (int16_t)o; offS[l] = (int16_t)os; off[rr] = (int16_t)(o + sz[l]); offS[rr] = (int16_t)(os + ns[l]); }
-            }
-            __syncwarp();
-        }
-        if (lane == 0 && a.has_stem_override) { sN[root].bl = a.stem_override; if (p_root >= 0) sN[p_root].p_bl = a.stem_override; }
-        // ---- 4. breadth-first order of the pruned view (pr is dead from here on)
-        if (p_root >= 0) {
-            if (lane == 0) bfsP[0] = (int16_t)p_root;
-            __syncwarp();
-            int lo = 0, hi = 1;
-            while (lo < hi) {
-                int t = hi;
-                for (int b0 = lo; b0 < hi; b0 += 32) {
-                    const int k = b0 + lane; int l = -1, rr = -1;
-                    if (k < hi) {
-                        Node& x = sN[bfsP[k]]; l = x.p_left; rr = x.p_right;
-                        x.flags |= NF_IN_PRUNED;
-                        if (l >= 0) { Node& L = sN[l]; L.flags |= NF_LEFT_P; L.chain_p = (int16_t)(x.chain_p + 1); sN[rr].chain_p = 0; }
-                        atomicAdd(&s_cnt[1][x.event], 1);
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, l >= 0);
-                    if (l >= 0) { const int pos = t + 2 * __popc(m & lt_mask); bfsP[pos] = (int16_t)l; bfsP[pos + 1] = (int16_t)rr; }
-                    t += 2 * __popc(m);
-                }
-                __syncwarp();
-                lo = hi; hi = t;
-            }
-        }
-        __syncwarp();
-        // ---- 5. the terms of the getInfo sums in breadth-first order (GuestTreeInHostTreeCreator.java:431-511). The sums themselves are
-        // order-dependent floating-point additions, i.e. serial: k_info_sums adds them up with a thread per sum and full occupancy
-        // (here they kept one or two lanes of the warp busy for 44 % of the kernel's instructions).
-        {
-            double* tU = a.terms + goff; double* tP = a.terms + a.aux_stride + goff;
-            double* bU = a.terms + 2 * a.aux_stride + goff; double* bP = a.terms + 3 * a.aux_stride + goff;
-            for (int k = lane; k < up; k += 32) {
-                const Node& x = sN[bfsU[k]]; tU[k] = x.bl;
-                if (a.want_beneath) bU[k] = fmax(fmin(XSUB(a.host_root_time, x.abstime), x.bl), 0.0);
-            }
-            for (int k = lane; k < nu; k += 32) {
-                const Node& x = sN[bfsP[k]]; tP[k] = x.p_bl;
-                if (a.want_beneath) bP[k] = fmax(fmin(XSUB(a.host_root_time, x.abstime), x.p_bl), 0.0);
-            }
-        }
-        {
-            if (a.write_nodes) {
-                uint4* dst = reinterpret_cast<uint4*>(a.nodes + goff); const uint4* src = reinterpret_cast<const uint4*>(sN);
-                const int nq = n_pool * (int)(sizeof(Node) / 16);
-                for (int i = lane; i < nq; i += 32) dst[i] = src[i];
-                int32_t* gOrdU = a.aux + goff; int32_t* gOrdP = a.aux + a.aux_stride + goff;
-                int32_t* gBfsU = a.aux + 2 * a.aux_stride + goff; int32_t* gBfsP = a.aux + 3 * a.aux_stride + goff;
-                for (int k = lane; k < up; k += 32) { gOrdU[k] = ordU[k]; gBfsU[k] = bfsU[k]; }
-                for (int k = lane; k < nu; k += 32) { gOrdP[k] = ordP[k]; gBfsP[k] = bfsP[k]; }
-            }
-            make_records<int16_t>(a.E, goff, sN, ordU, ordP, bfsU, bfsP, up, nu, root, p_root, off, offS);      // (off / offS: dead work arrays)
-            if (lane < EV_COUNT) { inf.cnt_u[lane] = s_cnt[0][lane]; inf.cnt_p[lane] = s_cnt[1][lane]; }
-            if (lane == 0) {
-                inf.p_root = p_root; inf.n_u = up; inf.n_p = nu; inf.p_root_time = p_root >= 0 ? sN[p_root].abstime : 0.0;
-                inf.root_gtree_u = sN[root].gtree; inf.root_gtree_p = sN[p_root >= 0 ? p_root : root].gtree;
-            }
-        }
+        label_tree_by_warp<int16_t>(a, inf, goff, n_pool, sN, work, cap, s_cnt, false);
         __syncwarp();
       }
+    }
+}
+
+// Trees that do not fit the shared-memory stage (> 2 340 vertices; a guest tree on a 1000-leaf host has ~3 400): the same warp
+// algorithm on the records in place (the arena, L2-resident while a warp works on one tree) with 32-bit work arrays in a global scratch
+// of the block. The thread-per-tree kernel below, which these trees used to go to, took 64 ms per 8 192 such trees.
+__global__ void __launch_bounds__(32) k_label_prune_warp_global(LabelArgs a) {
+    __shared__ int32_t s_cnt[2][EV_COUNT];
+    int32_t* work = a.work + (size_t)blockIdx.x * a.work_stride;
+    for (long long r = blockIdx.x; r < a.n; r += gridDim.x) {
+        const int n_pool = (int)a.pool[r];
+        if (n_pool <= a.min_pool || n_pool > a.cap) continue;
+        label_tree_by_warp<int32_t>(a, a.info[r], a.node_off[r], n_pool, a.nodes + a.node_off[r], work, a.cap, s_cnt, true);
+        __syncwarp();
     }
 }
 

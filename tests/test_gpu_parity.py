@@ -213,6 +213,16 @@ def test_label_kernels_agree(ctx, monkeypatch):
     fast = ctx.run("HostTreeGen", args, n=2000, rng=sg.RNG_PHILOX)
     for st in range(4):
         assert bytes(slow.stream(st)) == bytes(fast.stream(st))
+    # trees beyond the shared-memory stage (> 2 340 vertices) are labelled in place by the same warp algorithm with global work arrays:
+    # SGP_LABEL_GLOBAL_KERNEL routes every tree through that kernel
+    monkeypatch.setenv("SGP_LABEL_GLOBAL_KERNEL", "1")
+    assert_replay_parity(ctx, "HostTreeGen", HOST_CASES[2], 24, "o")
+    assert_replay_parity(ctx, "GuestTreeGen", GUEST_CASES[4], 24, "o")
+    assert_replay_parity(ctx, "GuestTreeGen", GUEST_CASES[7], 24, "o")
+    inplace = ctx.run("HostTreeGen", args, n=2000, rng=sg.RNG_PHILOX)
+    monkeypatch.delenv("SGP_LABEL_GLOBAL_KERNEL")
+    for st in range(4):
+        assert bytes(inplace.stream(st)) == bytes(fast.stream(st))
 
 
 def test_output_layouts_match_separate_reference_runs(ctx, tmp_path):
