@@ -542,7 +542,9 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             // arena is sized from a pilot run over a few hundred replicates (their results are overwritten by the main run); if
             // the estimate turns out too small the vertex records are regenerated by the build kernel as in the two-pass mode.
             S.node_off.alloc((size_t)S.n + 1); CK(cudaMemsetAsync(S.node_off.p, 0, ((size_t)S.n + 1) * sizeof(long long), stA));
-            const bool want_one_pass = n >= 8192 && getenv("SGP_TWO_PASS") == nullptr;
+            // worth it when the arena can be sized without a pilot (this configuration ran before), or when the batch is large enough
+            // for a pilot over n / 64 replicates to be cheap next to it
+            const bool want_one_pass = getenv("SGP_TWO_PASS") == nullptr && (n >= 8192 || (n >= 256 && getenv("SGP_ARENA_MARGIN") == nullptr));
             std::string cfg_key = std::to_string(cfg.app) + (replay ? "r" : "p");
             for (size_t i = 0; i < cfg.args.size(); ++i) if ((int)i != cfg.seed_arg_index) { cfg_key += '\x1f'; cfg_key += cfg.args[i]; }
             S.cfg_key = cfg_key;
@@ -554,7 +556,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
                 S.cursor.alloc(1); CK(cudaMemsetAsync(S.cursor.p, 0, sizeof(unsigned long long), stA));
                 general_find(n, S.nodes.p, S.arena_cap, S.cursor.p, S.node_off.p);
                 S.one_pass = true;
-            } else if (want_one_pass) {
+            } else if (want_one_pass && n >= 8192) {
                 const long long n_pilot = std::max<long long>(256, n / 64);
                 general_find(n_pilot, nullptr, 0, nullptr, nullptr);
                 DevBuf<long long> ppool, poff; DevBuf<int> pmax; ppool.alloc((size_t)n_pilot + 1); poff.alloc((size_t)n_pilot + 1); pmax.alloc(1);

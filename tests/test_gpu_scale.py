@@ -417,3 +417,11 @@ def test_one_pass_general_engine_equals_two_pass(ctx, monkeypatch, tmp_path):
                     for sfx, data in one.files(i).items():
                         assert data == want["files"][prefix + sfx], (app, i, sfx)
             one.free(); two.free(); small.free()
+    # a small batch goes one-pass too once its configuration has run on the context (no pilot needed): same bytes as the first run
+    args = ["-s", "63", "-db", "none", HOST8, "0.5", "0.3", "0.8", "g"]
+    first = ctx.run("GuestTreeGen", args, n=300, rng=sg.RNG_MT_REPLAY)
+    again = ctx.run("GuestTreeGen", args, n=300, rng=sg.RNG_MT_REPLAY)
+    assert first.timings()["build_ms"] > 0.05 and again.timings()["build_ms"] < 0.05
+    for s in range(8):
+        assert bytes(first.stream(s)) == bytes(again.stream(s))
+    first.free(); again.free()
