@@ -395,6 +395,26 @@ def test_committed_bench_line_follows_the_contract():
     assert r["impl"] == "reference" and r["metric"] == d["metric"] and r["unit"] == d["unit"] and r["e2e"]["h2d_bytes_per_step"] == 0
 
 
+def test_round2_bench_line_carries_every_baseline_config():
+    # profiles/r02_bench.json: the line `python bench.py` printed on a B200 at the end of round 2
+    import json
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+              "e2e", "gpu_launches", "roofline", "roofline_emit", "cpu_baseline", "clocks", "workloads"):
+        assert k in d, k
+    assert d["config"]["workload"].startswith("C2") and d["warmup"] >= 3 and d["gpu_launches"] > 0
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9 and d["roofline"]["traffic"] is not None
+    assert {"link_gbs_alone", "link_gbs_concurrent_per_gpu_mean", "frac_of_link"} <= set(d["e2e"])
+    assert not (set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"})
+    want = {"C3_db_none", "C3_db_simple", "C4_guest_db_exponential", "C4_guest_db_simple", "C4_guest_db_none", "C4_domain_100_genes", "C5_lognormal", "C5_gamma"}
+    assert want <= set(d["workloads"])
+    for name in want:
+        w = d["workloads"][name]
+        assert w["value"] > 0 and w["e2e"]["value"] > 0 and w["e2e"]["d2h_bytes_per_step"] > 0, name
+        assert {"bound", "achieved", "peak", "frac"} <= set(w["roofline"]) and w["cpu_baseline"]["value"] > 0, name
+    assert "chained" in d["workloads"]["C4_domain_100_genes"]
+
+
 def test_launch_list_summary_tool():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "summarize_launches.py"), os.path.join(ROOT, "profiles", "r01_launches_bench_c2.csv")],
                          capture_output=True, text=True, check=True).stdout
@@ -514,3 +534,24 @@ def test_iidrk11_oracle_closed_forms(tmp_path):
                                  ("a A\nb B\nc C\nd D\ne E\n", RK_HOST, "((a:0.4,b:0.4):0.7,(c:0.8,(d:0.2,e:0.2):0.6):0.3);")):
         mm = tmp_path / "bad.txt"; mm.write_text(bad_map)
         assert oracle_run("BranchRelaxer", ["-s", "1", gtree, "IIDRK11", host, str(mm), "1.0"])["status"] == 2
+
+
+def test_quantile_restatements_against_scipy_within_the_algorithms_tolerances():
+    """Independent pin of the two quantile restatements BranchRelaxer's rates go through (the device versions are bit-identical to
+    the oracle's, tests/test_gpu_parity.py): Voutier's rational approximation of the normal quantile (math/Normal.java:48-86; the
+    paper states an absolute error below 1.16e-4 in the central region 0.025 <= p <= 0.975 and a relative error below 2.5e-5 in the
+    tails) and Best & Roberts' AS 91 chi-square quantile with AS 32 / Lanczos underneath (math/ChiSquared.java:23-84,
+    math/Gamma.java:127-204; about six significant figures)."""
+    from scipy import stats
+    from oracle_util import oracle
+    L = oracle()
+    p = np.concatenate([np.linspace(1e-6, 0.025, 400), np.linspace(0.025, 0.975, 2000), np.linspace(0.975, 1 - 1e-6, 400)])
+    got = np.array([L.oracle_normal_quantile(float(v)) for v in p]); want = stats.norm.ppf(p)
+    central = (p >= 0.025) & (p <= 0.975)
+    assert np.max(np.abs(got[central] - want[central])) < 1.2e-4          # measured: 1.16e-4, the published bound
+    assert np.max(np.abs(got[~central] / want[~central] - 1.0)) < 3e-5
+    assert abs(L.oracle_normal_quantile(0.5)) < 1.2e-4 and L.oracle_normal_quantile(0.3) < 0 < L.oracle_normal_quantile(0.7)
+    q = np.linspace(2e-6, 0.999998, 3000)     # ChiSquared.quantile throws outside [2e-6, 0.999998]
+    for k, theta in ((2.0, 0.5), (0.25, 2.0), (4.0, 1.0), (50.0, 0.1)):
+        got = np.array([L.oracle_gamma_quantile(float(v), k, theta) for v in q]); want = stats.gamma.ppf(q, a=k, scale=theta)
+        assert np.max(np.abs(got / want - 1.0)) < 1e-6, (k, theta, float(np.max(np.abs(got / want - 1.0))))      # measured: <= 2e-7
