@@ -684,6 +684,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         if (piped) CK(cudaStreamWaitEvent(stB, S.ev_found, 0));
         g_alloc_stream = stB;
         if (!fast_bd && !S.cfg_key.empty() && S.n > 0) {
+            if (impl->nodes_per_replicate.size() > 256) impl->nodes_per_replicate.clear();      // (a cache, not a history)
             double& seen = impl->nodes_per_replicate[S.cfg_key];
             seen = std::max(seen, (double)S.total_nodes / (double)S.n);
         }
