@@ -417,6 +417,23 @@ def test_one_pass_general_engine_equals_two_pass(ctx, monkeypatch, tmp_path):
                     for sfx, data in one.files(i).items():
                         assert data == want["files"][prefix + sfx], (app, i, sfx)
             one.free(); two.free(); small.free()
+    # chained stages read the arena a one-pass run leaves (acceptance order, arena-capacity stride): same relaxed trees and the same
+    # DomainTreeGen forest as from a two-pass source
+    gargs = ["-s", "64", "-db", "none", HOST8, "0.4", "0.2", "0.3", str(tmp_path / "gt")]
+    src1 = ctx.run("GuestTreeGen", gargs, n=n, rng=sg.RNG_PHILOX, flags=sg.FLAG_KEEP_TREES, keep_on_device=True)
+    monkeypatch.setenv("SGP_TWO_PASS", "1")
+    src2 = ctx.run("GuestTreeGen", gargs, n=n, rng=sg.RNG_PHILOX, flags=sg.FLAG_KEEP_TREES, keep_on_device=True)
+    monkeypatch.delenv("SGP_TWO_PASS")
+    assert src1.timings()["build_ms"] < 0.05 < src2.timings()["build_ms"]
+    rargs = ["-s", "9", "x", "IIDLogNormal", "0", "0.25"]
+    r1 = ctx.relax_on_batch(src1, rargs, which=sg.STREAM_PRUNED_TREE, rng=sg.RNG_PHILOX); r2 = ctx.relax_on_batch(src2, rargs, which=sg.STREAM_PRUNED_TREE, rng=sg.RNG_PHILOX)
+    assert (r1.rep_status == r2.rep_status).all() and bytes(r1.stream(0)) == bytes(r2.stream(0))
+    dargs = ["-s", "3", "-ig", "0.6", HOST8, "chained", "0.4", "0.3", "0.9", "o"]
+    d1 = ctx.domain_on_batch(src1, dargs, first=10, count=6, n=4, rng=sg.RNG_MT_REPLAY); d2 = ctx.domain_on_batch(src2, dargs, first=10, count=6, n=4, rng=sg.RNG_MT_REPLAY)
+    for s in range(8):
+        assert bytes(d1.stream(s)) == bytes(d2.stream(s)), s
+    for b in (r1, r2, d1, d2, src1, src2):
+        b.free()
     # a small batch goes one-pass too once its configuration has run on the context (no pilot needed): same bytes as the first run
     args = ["-s", "63", "-db", "none", HOST8, "0.5", "0.3", "0.8", "g"]
     first = ctx.run("GuestTreeGen", args, n=300, rng=sg.RNG_MT_REPLAY)
