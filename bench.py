@@ -340,7 +340,7 @@ def extra_workloads(h, peaks, K, W):
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "measured at N = 1 only"}
         out[name] = line
 
-    # ---- C3: 10^6-shaped GuestTreeGen batches on the 100-leaf species tree (bounded to 2*10^5 per step: 20 GB of text)
+    # ---- C3: GuestTreeGen batches on the 100-leaf species tree, 8*10^5 per step (81 GB of text; 10^6 would not leave room for the records next to it)
     for db in ("none", "simple"):
         general(f"C3_db_{db}", "GuestTreeGen", ["-s", "20260103", "-db", db, SPECIES100, "0.3", "0.3", "0.3", "bench"], h.args.c3_replicates, 16384, 6, 120,
                 f"C3: GuestTreeGen -db {db} 0.3 0.3 0.3 on the 100-leaf species tree (tests/golden/species100.pruned.tree), -rt 0.5, 8 output files/replicate")
@@ -420,7 +420,7 @@ def main():
     ap.add_argument("--e2e-replicates", type=int, default=131072)
     ap.add_argument("--cpu-sample", type=int, default=600, help="replicates timed on one host core for cpu_baseline")
     ap.add_argument("--workloads", default="all", help="'all' (C2 headline + C3/C4/C5 in `workloads`) or 'c2' (headline only)")
-    ap.add_argument("--c3-replicates", type=int, default=200_000)
+    ap.add_argument("--c3-replicates", type=int, default=800_000)
     ap.add_argument("--c4-replicates", type=int, default=8192)
     ap.add_argument("--c4-domain-replicates", type=int, default=1024)
     ap.add_argument("--c5-source-trees", type=int, default=200_000)
