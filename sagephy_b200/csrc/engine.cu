@@ -670,6 +670,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     CK(cudaEventRecord(ev_setup, stA));
     if (piped) CK(cudaStreamWaitEvent(stB, ev_setup, 0));
     unsigned long long totals[ST_COUNT] = {0}, out_cap[ST_COUNT] = {0};
+    double mean_piece = 0.0; e.stage_bytes = 3072;
 
     // ---- build -> label -> emit of one sub-batch (stream B) ---------------------------------------------------------------------
     auto emit_args_for = [&](Sub& S) {
@@ -776,7 +777,13 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
                 }
                 out_cap[q] = std::max<unsigned long long>(cap, 1);
                 CK(cudaMallocAsync(&out.d_stream[q], out_cap[q], stB));
+                // mean piece length of the Newick streams (a vertex is one piece; the rows of the other streams are shorter)
+                if (q == ST_UNPRUNED_TREE || q == ST_PRUNED_TREE) mean_piece = std::max(mean_piece, (double)first / (double)std::max<long long>(S.total_nodes, 1));
             }
+            // stage of the write kernels: room for 32 pieces of 1.2 x the mean length (3 KB for HostTreeGen's 57-byte pieces - small
+            // stages keep 8 blocks per SM resident -, 5 KB for the 100-byte pieces of GuestTreeGen on a 1000-leaf host); a trip that
+            // still does not fit is written with plain stores
+            e.stage_bytes = (int)std::min<long long>(6144, std::max<long long>(3072, ((long long)(mean_piece * 38.0) + 256 + 127) / 128 * 128));
             g_alloc_stream = stA;
             ea = emit_args_for(S);
         }

@@ -13,17 +13,18 @@ int launch_emit_sizes(const EmitArgs& a, cudaStream_t st) {
 // back into `st`), so that one kernel's tail (its last, partly filled wave of blocks) is covered by the next kernel's blocks.
 template <bool BULK> static int launch_write(const EmitArgs& a, cudaStream_t st, cudaStream_t* side, int n_side, cudaEvent_t fork, cudaEvent_t* join) {
     const unsigned blocks = (unsigned)((a.n * 32 + kEmitWarps * 32 - 1) / (kEmitWarps * 32)), threads = kEmitWarps * 32;
+    const size_t smem = (size_t)kEmitWarps * 2 * a.stage_bytes;
     int n = 0;
     if (n_side > 0) cudaEventRecord(fork, st);
     auto on = [&](int k) { if (n_side <= 0 || k == 0) return st; cudaStream_t s = side[(k - 1) % n_side]; cudaStreamWaitEvent(s, fork, 0); return s; };
-    if (a.stream_mask & (1u << ST_UNPRUNED_TREE)) { k_write_tree<0, BULK><<<blocks, threads, 0, on(0)>>>(a); ++n; }
-    if (a.stream_mask & (1u << ST_PRUNED_TREE)) { k_write_tree<1, BULK><<<blocks, threads, 0, on(1)>>>(a); ++n; }
+    if (a.stream_mask & (1u << ST_UNPRUNED_TREE)) { k_write_tree<0, BULK><<<blocks, threads, smem, on(0)>>>(a); ++n; }
+    if (a.stream_mask & (1u << ST_PRUNED_TREE)) { k_write_tree<1, BULK><<<blocks, threads, smem, on(1)>>>(a); ++n; }
     // both .info files in one launch: a thread per (replicate, file)
     if (a.stream_mask & 0xCu) { k_emit_info<true><<<(unsigned)((2 * a.n + kInfoWarps * 32 - 1) / (kInfoWarps * 32)), kInfoWarps * 32, 0, on(2)>>>(a); ++n; }
-    if (a.stream_mask & (1u << ST_UNPRUNED_G2H)) { k_write_rows<0, 0, BULK><<<blocks, threads, 0, on(1)>>>(a); ++n; }
-    if (a.stream_mask & (1u << ST_PRUNED_G2H)) { k_write_rows<0, 1, BULK><<<blocks, threads, 0, on(2)>>>(a); ++n; }
-    if (a.stream_mask & (1u << ST_UNPRUNED_LEAFMAP)) { k_write_rows<1, 0, BULK><<<blocks, threads, 0, on(1)>>>(a); ++n; }
-    if (a.stream_mask & (1u << ST_PRUNED_LEAFMAP)) { k_write_rows<1, 1, BULK><<<blocks, threads, 0, on(2)>>>(a); ++n; }
+    if (a.stream_mask & (1u << ST_UNPRUNED_G2H)) { k_write_rows<0, 0, BULK><<<blocks, threads, smem, on(1)>>>(a); ++n; }
+    if (a.stream_mask & (1u << ST_PRUNED_G2H)) { k_write_rows<0, 1, BULK><<<blocks, threads, smem, on(2)>>>(a); ++n; }
+    if (a.stream_mask & (1u << ST_UNPRUNED_LEAFMAP)) { k_write_rows<1, 0, BULK><<<blocks, threads, smem, on(1)>>>(a); ++n; }
+    if (a.stream_mask & (1u << ST_PRUNED_LEAFMAP)) { k_write_rows<1, 1, BULK><<<blocks, threads, smem, on(2)>>>(a); ++n; }
     for (int k = 0; k < n_side; ++k) { cudaEventRecord(join[k], side[k]); cudaStreamWaitEvent(st, join[k], 0); }
     return n;
 }

@@ -114,6 +114,7 @@ struct EmitArgs {
     char* out[ST_COUNT];
     unsigned long long cap[ST_COUNT];    // bytes allocated per stream: a replicate that would end beyond it is not written ...
     int* overflow;                       // ... and raises this flag (the engine then grows the buffers and writes again)
+    int stage_bytes;                     // write kernels: bytes of one shared-memory stage buffer (two per warp), a multiple of 128
 };
 
 struct LabelArgs {

@@ -285,7 +285,7 @@ template <bool BULK> __device__ __forceinline__ void flush_stage_async(const cha
 // Pieces [0, n) of one stream of one replicate, from their records. `piece(sink, rec, i)` prints piece i, `len_of(rec)` is its
 // cached length. Returns the bytes written. `trip` counts the stage buffers this warp has used (double buffering across calls).
 template <bool BULK, class Rec, class F, class L>
-__device__ __forceinline__ unsigned long long emit_records(int n, const Rec* recs, char* base, char* stage2, unsigned& trip, F&& piece, L&& len_of) {
+__device__ __forceinline__ unsigned long long emit_records(int n, const Rec* recs, char* base, char* stage2, unsigned stage_bytes, unsigned& trip, F&& piece, L&& len_of) {
     const int lane = threadIdx.x & 31;
     unsigned long long running = 0;
     Rec cur; { const uint4 z = make_uint4(0, 0, 0, 0); uint4* c4 = reinterpret_cast<uint4*>(&cur); c4[0] = z; c4[1] = z; }
@@ -303,8 +303,8 @@ __device__ __forceinline__ unsigned long long emit_records(int n, const Rec* rec
         if (total) {
             char* dst = base + running;
             const int mis = (int)(reinterpret_cast<unsigned long long>(dst) & 15ull);
-            if (total + 16 <= (unsigned)kStageBytes) {
-                char* stage = stage2 + (trip & 1u) * kStageBytes;
+            if (total + 16 <= stage_bytes) {
+                char* stage = stage2 + (trip & 1u) * stage_bytes;
                 if (BULK && trip >= 2) { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }       // the copy that last read this buffer is done
                 if (len) { SmemSink m{(uint32_t)__cvta_generic_to_shared(stage) + (uint32_t)mis + off}; piece(m, cur, i); }
                 if (!BULK) __syncwarp();
@@ -385,7 +385,7 @@ template <int INSTANCE> __global__ void __launch_bounds__(256) k_finish_records(
 // returns it cost four round trips per replicate, as long as formatting the replicate's seven trips.
 template <int VIEW, bool BULK>
 __global__ void __launch_bounds__(kEmitWarps * 32, 8) k_write_tree(EmitArgs a) {
-    __shared__ __align__(128) char s_stage[kEmitWarps][2 * kStageBytes];
+    extern __shared__ __align__(128) char s_stage_dyn[];          // two stage buffers of a.stage_bytes per warp (sized by the launcher from the batch's mean piece length)
     const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= a.n) return;
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 8) k_write_tree(EmitArgs a) {
     if (status != REP_OK) return;
     if (o1 > a.cap[st]) { if (lane == 0) *a.overflow = 1; return; }
     char* base = a.out[st] + o0;
-    char* stage2 = s_stage[threadIdx.x >> 5];
+    char* stage2 = s_stage_dyn + (size_t)(threadIdx.x >> 5) * 2 * a.stage_bytes;
     if (VIEW == 1 && p_root < 0) {
         // empty pruned tree: NewickTree.toString of a null root
         if (lane == 0) { MemSink m{base}; if (a.exclude_meta) put_lit(m, ";\n"); else if (a.app == 0) put_lit(m, "[NAME=PrunedTree];"); else put_lit(m, "[NAME=PrunedTree];\n"); }
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 8) k_write_tree(EmitArgs a) {
     const TreeRec* recs = a.trec + (size_t)VIEW * a.aux_stride + off;
     const TreeRecX* recx = a.trecx ? a.trecx + (size_t)VIEW * a.aux_stride + off : nullptr;
     unsigned trip = 0;
-    emit_records<BULK>(n_rec, recs, base, stage2, trip,
+    emit_records<BULK>(n_rec, recs, base, stage2, (unsigned)a.stage_bytes, trip,
                        [&](auto& s, const TreeRec& t, int i) { put_tree_piece<VIEW == 1>(s, a, t, recx + i); },
                        [](const TreeRec& t) { return (unsigned)t.len; });
     if (BULK && lane == 0) bulk_wait_read<0>();         // shared memory must outlive the copies that read it
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 8) k_write_tree(EmitArgs a) {
 // One row stream (KIND 0: .guest2host, 1: .leafmap; VIEW 0: unpruned, 1: pruned): warp per replicate.
 template <int KIND, int VIEW, bool BULK>
 __global__ void __launch_bounds__(kEmitWarps * 32, 8) k_write_rows(EmitArgs a) {
-    __shared__ __align__(128) char s_stage[kEmitWarps][2 * kStageBytes];
+    extern __shared__ __align__(128) char s_stage_dyn[];
     const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= a.n) return;
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 8) k_write_rows(EmitArgs a) {
     if (status != REP_OK) return;
     if (o1 > a.cap[st]) { if (lane == 0) *a.overflow = 1; return; }
     char* base = a.out[st] + o0;
-    char* stage2 = s_stage[threadIdx.x >> 5];
+    char* stage2 = s_stage_dyn + (size_t)(threadIdx.x >> 5) * 2 * a.stage_bytes;
     const RowRec* recs = a.rows + (size_t)VIEW * a.aux_stride + off;
     const int np = VIEW ? (p_root >= 0 ? n_view : 0) : n_view;
     unsigned trip = 0;
@@ -443,10 +443,10 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 8) k_write_rows(EmitArgs a) {
             const int mis = (int)(reinterpret_cast<unsigned long long>(base) & 15ull);
             flush_stage(a.blob + a.g2h_head_off16[mis] - mis, mis, base, (unsigned)a.g2h_head_len);      // source congruent to destination mod 16
         }
-        emit_records<BULK>(np, recs, base + head_len, stage2, trip,
+        emit_records<BULK>(np, recs, base + head_len, stage2, (unsigned)a.stage_bytes, trip,
                            [&](auto& s, const RowRec& t, int) { put_g2h_row(s, a, t); }, [](const RowRec& t) { return (unsigned)t.len_g2h; });
     } else {
-        emit_records<BULK>(np, recs, base, stage2, trip,
+        emit_records<BULK>(np, recs, base, stage2, (unsigned)a.stage_bytes, trip,
                            [&](auto& s, const RowRec& t, int) { if (t.flags & RR_LEAFMAP) put_leafmap_row(s, a, t); }, [](const RowRec& t) { return (unsigned)t.len_lm; });
     }
     if (BULK && lane == 0) bulk_wait_read<0>();
