@@ -40,7 +40,7 @@ typedef enum {
     SGP_ERR_NO_DEVICE = 1,      /* no usable CUDA device / CUDA runtime failure */
     SGP_ERR_INVALID_ARGUMENT = 2,
     SGP_ERR_PARSE = 3,          /* malformed Newick / number */
-    SGP_ERR_UNSUPPORTED = 4,    /* e.g. -hybrid host graphs (out of scope) */
+    SGP_ERR_UNSUPPORTED = 4,    /* an application name the reference does not have */
     SGP_ERR_INTERNAL = 5,
     SGP_USAGE = 6               /* wrong positional count or -h: usage text is in the batch's stdout */
 } sgp_status;
@@ -213,6 +213,12 @@ sgp_status sgp_probe_philox(sgp_context* ctx, int variant, const uint32_t* ctr /
 /* Issue-rate microbenchmarks (roofline denominators for the sampler), giga warp-instructions per second, whole chip:
  * independent DFMA chains, independent IMAD chains, and an IMAD + SHF + LOP3 mix (what Philox is made of). */
 sgp_status sgp_probe_issue_peaks(sgp_context* ctx, double* dfma_ginst, double* imad_ginst, double* mixed_int_ginst);
+/* Host-side argument handling of the three generators (no GPU needed): everything sgp_app_run does before the first kernel -
+ * the reference's option grammar, number parsing, host / gene tree reading and the checks of its constructors
+ * (apps/SaGePhy/{Host,Guest,Domain}TreeGen.java + *Parameters.java). Returns what sgp_app_run would return at that point
+ * (SGP_OK, SGP_USAGE or the error) and copies the text the run would leave on stderr into `err`. With -hybrid this is the whole
+ * run: the reference cannot create a guest vertex in that mode (GuestVertex.java:100), see csrc/hybrid_host.hpp. */
+sgp_status sgp_probe_parse_app(const char* app, int argc, const char* const* argv, char* err, int32_t err_cap);
 /* Host-side table preparation ("K0", no GPU needed): parses a Newick host tree as GuestTreeGen would (stem override as given,
  * NaN = keep the tree's own) and returns the tables the kernels consume, for CPU tests of the host logic.
  * Sizes: parent/left/right/v2e/vtime [nV], ep_lo/ep_up [nE], ep_off [nE+1], ep_arcs [ep_off[nE]], lca_time [nV*nV].

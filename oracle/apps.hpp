@@ -11,6 +11,7 @@
 #include <map>
 #include <sstream>
 #include "treegen.hpp"
+#include "hybrid.hpp"
 
 namespace oracle {
 
@@ -167,6 +168,23 @@ inline void run_host_tree_gen(const std::vector<std::string>& args, Outputs& o, 
     }
 }
 
+// getHostHybridGraphCreator (GuestTreeGenParameters.java:182-197, DomainTreeGenParameters.java:205-220) followed by
+// GuestTreeMachina.sampleGuestTree -> createUnprunedTree (GuestTreeInHybridGraphCreator.java:86-96): never returns, see hybrid.hpp.
+[[noreturn]] inline void run_hybrid_host(const ParsedArgs& p, size_t hostPos, size_t dupPos, size_t lossPos) {
+    const std::string& str = p.pos[hostPos];
+    double dup = parse_double(p.pos[dupPos]);
+    double loss = parse_double(p.pos[lossPos]);
+    const std::vector<std::string>& hybrid = p.opts.at("-hybrid");
+    const size_t h0 = hybrid.size() - 3;                        // JCommander keeps the values of the last occurrence
+    double timespan = parse_double(hybrid[h0]);
+    double dupfact = parse_double(hybrid[h0 + 1]);
+    double lossfact = parse_double(hybrid[h0 + 2]);
+    gml::GMLGraph host = gml::first_graph(gml::readGML(file_exists(str) ? read_file(str) : str));
+    double rho = parse_double(p.get("-p", "1.0"));
+    if (p.has("-stem")) (void)parse_double(p.get("-stem", ""));
+    hybrid_creator_and_first_vertex(host, dup, loss, dupfact, lossfact, timespan, rho);
+}
+
 // ---- GuestTreeGen -----------------------------------------------------------------------------------------------------------
 inline const std::vector<OptSpec>& guest_specs() {
     static const std::vector<OptSpec> s = {
@@ -188,7 +206,6 @@ inline void run_guest_tree_gen(const std::vector<std::string>& args, Outputs& o,
             o.out += "Usage:\n    java -jar sagephy-X.Y.Z.jar GuestTreeGen [options] <host tree> <dup rate> <loss rate> <trans rate> <out prefix>\n\n";
             return;
         }
-        if (p.has("-hybrid")) throw std::invalid_argument("oracle: -hybrid host graphs are out of scope (SURVEY.md §2 row 17)");
         std::vector<int> sizes; bool hasSizes = p.has("-sizes");
         if (hasSizes) sizes = read_leaf_sizes(p.get("-sizes", ""));
         bool excludeMeta = p.has("-nox");
@@ -196,6 +213,7 @@ inline void run_guest_tree_gen(const std::vector<std::string>& args, Outputs& o,
         Machina machina(p.get("-s", ""), parse_int(p.get("-min", "2")), parse_int(p.get("-max", "1000")), parse_int(p.get("-minper", "0")),
                         parse_int(p.get("-maxper", "10")), hasSizes ? &sizes : nullptr, parse_int(p.get("-a", "10000")), p.get("-vp", "G"),
                         excludeMeta, true, false);
+        if (p.has("-hybrid")) run_hybrid_host(p, 0, 1, 2);     // GuestTreeGen.java:42
         // getHostTreeCreator (GuestTreeGenParameters.java:127-136)
         std::unique_ptr<NTree> hostNewick; std::optional<std::string> treeName;
         if (file_exists(p.pos[0])) { hostNewick = nw_read_tree(read_file(p.pos[0])); treeName = base_name(p.pos[0]); }
@@ -273,13 +291,13 @@ inline void run_domain_tree_gen(const std::vector<std::string>& args, Outputs& o
             o.out += "Usage:\n    java -jar sagephy-X.Y.Z.jar DomainTreeGen [options] <host tree file or string> <guest tree directory> <dup rate> <loss rate> <trans rate> <out prefix>\n\n";
             return;
         }
-        if (p.has("-hybrid")) throw std::invalid_argument("oracle: -hybrid host graphs are out of scope (SURVEY.md §2 row 17)");
         std::vector<int> sizes; bool hasSizes = p.has("-sizes");
         if (hasSizes) sizes = read_leaf_sizes(p.get("-sizes", ""));
         bool excludeMeta = p.has("-nox");
         if (!p.has("-s")) throw std::invalid_argument("oracle: a seed (-s) is required (the reference would read /dev/random)");
         Machina machina(p.get("-s", ""), parse_int(p.get("-min", "2")), parse_int(p.get("-max", "1000")), parse_int(p.get("-minper", "0")),
                         parse_int(p.get("-maxper", "10")), hasSizes ? &sizes : nullptr, parse_int(p.get("-a", "10000")), p.get("-vp", "D"), excludeMeta, true, false);
+        if (p.has("-hybrid")) run_hybrid_host(p, 0, 2, 3);     // DomainTreeGen.java:42
         std::unique_ptr<NTree> spNewick; std::optional<std::string> spName;
         if (file_exists(p.pos[0])) { spNewick = nw_read_tree(read_file(p.pos[0])); spName = base_name(p.pos[0]); } else spNewick = nw_read_tree(p.pos[0]);
         std::optional<double> stem = p.has("-stem") ? parse_double(p.get("-stem", "")) : 0.0;

@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = (
     "sgp_batch_status", "sgp_batch_attempts", "sgp_batch_sampled_leaves", "sgp_batch_root_times", "sgp_batch_total_times",
     "sgp_batch_event_counts", "sgp_batch_stdout", "sgp_batch_stderr", "sgp_batch_out_prefix", "sgp_batch_summary",
     "sgp_batch_timings", "sgp_batch_write_files", "sgp_batch_write_files_layout", "sgp_batch_free", "sgp_probe_double_to_string", "sgp_probe_math",
-    "sgp_probe_mt", "sgp_probe_seed", "sgp_probe_philox", "sgp_probe_issue_peaks", "sgp_probe_host_model")
+    "sgp_probe_mt", "sgp_probe_seed", "sgp_probe_philox", "sgp_probe_issue_peaks", "sgp_probe_host_model", "sgp_probe_parse_app")
 
 
 class BatchOpts(C.Structure):
@@ -110,6 +110,7 @@ def load_library() -> C.CDLL:
     L.sgp_probe_seed.argtypes = [cp, i64, C.POINTER(C.c_uint32), C.c_char_p, C.c_int32]; L.sgp_probe_seed.restype = C.c_int
     L.sgp_probe_philox.argtypes = [vp, C.c_int, vp, vp, i64, vp]; L.sgp_probe_philox.restype = C.c_int
     L.sgp_probe_issue_peaks.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]; L.sgp_probe_issue_peaks.restype = C.c_int
+    L.sgp_probe_parse_app.argtypes = [cp, C.c_int, C.POINTER(C.c_char_p), C.c_char_p, C.c_int32]; L.sgp_probe_parse_app.restype = C.c_int
     _lib = L
     return L
 
@@ -141,6 +142,16 @@ def seed_probe(seed, replicate: int = 0):
     if rc != 0:
         raise SagephyError(f"sgp_probe_seed failed ({rc})")
     return [int(k) for k in key], buf.value.decode()
+
+
+def probe_parse_app(app, args):
+    """Host-side argument handling of HostTreeGen / GuestTreeGen / DomainTreeGen without a GPU (`sgp_probe_parse_app`): returns
+    (status, stderr text) as `sgp_app_run` would leave them before its first kernel. With `-hybrid` that is the whole run."""
+    L = load_library()
+    argv = (C.c_char_p * max(len(args), 1))(*[str(a).encode() for a in args])
+    buf = C.create_string_buffer(1 << 16)
+    rc = L.sgp_probe_parse_app(app.encode(), len(args), argv, buf, 1 << 16)
+    return rc, buf.value.decode()
 
 
 @dataclass

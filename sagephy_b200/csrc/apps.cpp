@@ -7,6 +7,7 @@
 #include <dirent.h>
 #include <algorithm>
 #include "apps_common.hpp"
+#include "hybrid_host.hpp"
 
 namespace sgp {
 
@@ -54,6 +55,20 @@ void common_window(const Parsed& p, TreeGenConfig& cfg) {
     else { cfg.has_seed = false; cfg.seed = random_seed(); cfg.seed_arg_index = -1; }
 }
 
+// getHostHybridGraphCreator (GuestTreeGenParameters.java:182-197, DomainTreeGenParameters.java:205-220): rates, the three -hybrid
+// values, then the GML graph (a file if one of that name exists, else the argument itself), then -p and -stem.
+[[noreturn]] void hybrid_host(const Parsed& p, int host_pos, int dup_pos, int loss_pos) {
+    const double dup = to_double(p.positional[dup_pos]), loss = to_double(p.positional[loss_pos]);
+    const std::vector<std::string>& h = p.val.at("-hybrid");
+    const double timespan = to_double(h[h.size() - 3]), dupfact = to_double(h[h.size() - 2]), lossfact = to_double(h[h.size() - 1]);
+    const std::string& arg = p.positional[host_pos];
+    const std::string text = exists(arg) ? slurp(arg) : arg;
+    hybrid::Graph g = hybrid::read_first_graph(text);
+    const double rho = to_double(p.str("-p", "1.0"));
+    if (p.on("-stem")) (void)to_double(p.str("-stem", "0"));
+    hybrid::create_and_sample(g, dup, loss, dupfact, lossfact, timespan, rho);
+}
+
 }  // namespace
 
 void parse_treegen_app(const std::string& app, const std::vector<std::string>& args, TreeGenConfig& cfg, AppResult& res, const std::vector<std::pair<std::string, FlatTree>>* forest) {
@@ -97,10 +112,10 @@ void parse_treegen_app(const std::string& app, const std::vector<std::string>& a
                            "    (sagephy_b200: same options plus the batch options of sgp_batch_opts / `sagephy -n <replicates> -rng <philox|mt-replay>`)\n\n";
             return;
         }
-        if (p.on("-hybrid")) { res.status = 4; res.err_text = "-hybrid host graphs are outside the accelerated path (SURVEY.md section 2, row 17)\n"; return; }
         cfg.app = 1;
         common_window(p, cfg);
         cfg.P.minper = to_int(p.str("-minper", "0")); cfg.P.maxper = to_int(p.str("-maxper", "10"));
+        if (p.on("-hybrid")) hybrid_host(p, 0, 1, 2);             // never returns: see hybrid_host.hpp
         cfg.P.lambda = to_double(p.positional[1]); cfg.P.mu = to_double(p.positional[2]); cfg.P.tau = to_double(p.positional[3]);
         if (cfg.P.lambda < 0 || cfg.P.mu < 0 || cfg.P.tau < 0) throw SgpError("Cannot have rate less than 0.");
         cfg.P.theta = to_double(p.str("-rt", "0.5"));
@@ -127,10 +142,10 @@ void parse_treegen_app(const std::string& app, const std::vector<std::string>& a
                            "    (sagephy_b200: same options plus the batch options of sgp_batch_opts / `sagephy -n <replicates> -rng <philox|mt-replay>`)\n\n";
             return;
         }
-        if (p.on("-hybrid")) { res.status = 4; res.err_text = "-hybrid host graphs are outside the accelerated path (SURVEY.md section 2, row 17)\n"; return; }
         cfg.app = 2;
         common_window(p, cfg);
         cfg.P.minper = to_int(p.str("-minper", "0")); cfg.P.maxper = to_int(p.str("-maxper", "10"));
+        if (p.on("-hybrid")) hybrid_host(p, 0, 2, 3);             // never returns: see hybrid_host.hpp
         cfg.P.lambda = to_double(p.positional[2]); cfg.P.mu = to_double(p.positional[3]); cfg.P.tau = to_double(p.positional[4]);
         cfg.P.theta = to_double(p.str("-rt", "0.5"));
         const std::string db = p.str("-db", "none");                 // DomainTreeGenParameters.java: default "none"

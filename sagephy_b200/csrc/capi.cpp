@@ -381,6 +381,24 @@ sgp_status sgp_probe_issue_peaks(sgp_context* ctx, double* dfma, double* imad, d
     try { ctx->ctx->probe_issue(dfma, imad, ddep); return SGP_OK; } catch (std::exception& e) { ctx->last_error = e.what(); return SGP_ERR_NO_DEVICE; }
 }
 
+sgp_status sgp_probe_parse_app(const char* app, int argc, const char* const* argv, char* err, int32_t err_cap) {
+    if (!app || argc < 0) return SGP_ERR_INVALID_ARGUMENT;
+    std::vector<std::string> args; for (int i = 0; i < argc; ++i) args.emplace_back(argv[i] ? argv[i] : "");
+    std::string text; sgp_status st = SGP_OK;
+    try {
+        TreeGenConfig cfg; AppResult res;
+        parse_treegen_app(app, args, cfg, res);
+        text = res.err_text;
+        st = res.status == 6 ? SGP_USAGE : (sgp_status)res.status;
+    } catch (SgpError& e) {
+        text = std::string(e.what()) + "\n\nUse option -h or --help to show usage.\n";
+        const std::string w = e.what();
+        st = (w.find("Newick") != std::string::npos || w.find("NumberFormat") != std::string::npos) ? SGP_ERR_PARSE : SGP_ERR_INVALID_ARGUMENT;
+    } catch (std::exception& e) { text = e.what(); st = SGP_ERR_INVALID_ARGUMENT; }
+    if (err && err_cap > 0) std::snprintf(err, (size_t)err_cap, "%s", text.c_str());
+    return st;
+}
+
 sgp_status sgp_probe_host_model(const char* newick, double stem, int32_t* n_vertices, int32_t* n_epochs,
                                 int32_t* parent, int32_t* left, int32_t* right, int32_t* v2e, double* vtime, int32_t cap_v,
                                 double* ep_lo, double* ep_up, int32_t* ep_off, int32_t cap_e, int32_t* ep_arcs, int32_t cap_arcs,

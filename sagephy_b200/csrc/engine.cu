@@ -698,7 +698,8 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         const bool thread_label = getenv("SGP_LABEL_THREAD_KERNEL") != nullptr;
         if (S.max_pool > label_smem_max_pool() && !thread_label) {
             work_stride = 9ll * (S.max_pool + 2) + 16;
-            work_blocks = (int)std::min<long long>((long long)sm * 8, (2ll << 30) / (work_stride * 4));
+            work_blocks = (int)std::min<long long>((long long)sm * 32, (2ll << 30) / (work_stride * 4));      // (latency-bound: 32 one-warp blocks per SM measured best)
+            if (const char* wb = getenv("SGP_LABEL_GLOBAL_BLOCKS")) work_blocks = std::max(16, atoi(wb));
             if (work_blocks >= 16) work = (int32_t*)impl->scratch(6, (size_t)work_blocks * work_stride * 4); else work_blocks = 0;
         }
         const bool keep_nodes = opts.keep_trees || (S.max_pool > label_smem_max_pool() && work_blocks == 0);

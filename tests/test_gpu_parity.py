@@ -295,6 +295,27 @@ def test_native_cli_writes_the_reference_files(tmp_path):
             assert strip(got) == strip(data), name
 
 
+def test_hybrid_host_graph_ends_like_the_reference(ctx, tmp_path):
+    # the reference validates the GML network and then dies on its first guest vertex (GuestVertex.java:100 gets the
+    # null GuestTreeInHybridGraphCreator.java:272 passes) - stack trace, exit 0, no files; so does the drop-in, for any -n
+    import subprocess
+    from test_hybrid_cpu import ALLO, BAD_GRAPHS, TAIL
+    (tmp_path / "net.gml").write_text(ALLO)
+    args = ["-s", "4", "-hybrid", "0.2", "2.0", "0.5", "net.gml", "0.3", "0.2", "0.0", "out"]
+    want = oracle_run("GuestTreeGen", ["-s", "4", "-hybrid", "0.2", "2.0", "0.5", str(tmp_path / "net.gml"), "0.3", "0.2", "0.0", "out"])
+    assert want["files"] == {} and want["stderr"] == "java.lang.NullPointerException" + TAIL
+    for n in (1, 1000):
+        b = ctx.run("GuestTreeGen", ["-s", "4", "-hybrid", "0.2", "2.0", "0.5", str(tmp_path / "net.gml"), "0.3", "0.2", "0.0", "out"], n=n, check=False)
+        assert b.status_code not in (sg.STATUS_OK, sg.STATUS_USAGE) and b.stderr == want["stderr"] and b.stdout == ""
+    bad = ["-s", "4", "-hybrid", "0.2", "2.0", "0.5", BAD_GRAPHS["not_connected"], "0.3", "0.2", "0.0", "out"]
+    assert ctx.run("GuestTreeGen", bad, n=5, check=False).stderr == oracle_run("GuestTreeGen", bad)["stderr"]
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sagephy_b200", "sagephy")
+    for extra in ([], ["-n", "100"], ["-n", "100", "--gpus", "2"]):
+        r = subprocess.run([exe, "GuestTreeGen"] + extra + args, cwd=tmp_path, capture_output=True, text=True, env=dict(os.environ, SAGEPHY_DEVICES="0,0"))
+        assert r.returncode == 0 and r.stdout == "" and r.stderr == want["stderr"], (extra, r)
+        assert sorted(p.name for p in tmp_path.iterdir()) == ["net.gml"]
+
+
 # ---- Philox throughput mode: distributions ---------------------------------------------------------------------------------------
 def ks_ok(a, b):
     return stats.ks_2samp(a, b).pvalue > 0.01

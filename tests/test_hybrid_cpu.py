@@ -1,0 +1,136 @@
+"""`-hybrid` host graphs. The reference reads a GML hybridisation network, validates it and then fails on
+its first guest vertex: GuestTreeInHybridGraphCreator.java:272 passes `null` for the guest tree and GuestVertex.java:100
+dereferences it. A drop-in therefore ends every such run like the reference does - the message of the first check that fails, or
+the NullPointerException for a valid network, then "Use option -h ...", no files. These tests compare the product's host-side
+argument path (`sgp_probe_parse_app`, no GPU) with the oracle's restatement (oracle/hybrid.hpp) on every branch of the checks."""
+import os
+
+import pytest
+
+import sagephy_b200 as sg
+from oracle_util import oracle_run
+
+TAIL = "\n\nUse option -h or --help to show usage.\n"
+
+# stem tip 0, speciation 1, hybrid donors 2 and 3, allopolyploid hybrid 4, leaves A, B, H
+ALLO = """# allopolyploid hybrid of two lineages
+graph [
+  directed 1
+  name "net"
+  node [ id 0 time 2.0 ]
+  node [ id 1 time 1.5 ]
+  node [ id 2 time 1.0 ]
+  node [ id 3 time 1.0 ]
+  node [ id 4 time 1.0 ]
+  node [ id 5 name "A" time 0 ]
+  node [ id 6 name "B" time 0.0 graphics [ x 1.0 y 2.0 ] ]
+  node [ id 7 name "H" time 0.0 ]
+  edge [ source 0 target 1 ]
+  edge [ source 1 target 2 ]
+  edge [ source 1 target 3 ]
+  edge [ source 2 target 4 ]
+  edge [ source 3 target 4 ]
+  edge [ source 2 target 5 ]
+  edge [ source 3 target 6 ]
+  edge [ source 4 target 7 ]
+]
+"""
+# stem tip 0, hybrid donor 1 (leaf X below it), autopolyploid hybrid 2 on a zero-length arc from 1, leaf Y below the hybrid
+AUTO = """graph [ directed 1
+  node [ id 0 time 3.0 ] node [ id 1 time 2.0 ] node [ id 2 time 2.0 ] node [ id 3 name "X" time 0.0 ] node [ id 4 name "Y" time 0.0 ]
+  edge [ source 0 target 1 ] edge [ source 1 target 2 ] edge [ source 1 target 3 ] edge [ source 2 target 4 ]
+]"""
+
+
+def swap(text, old, new):
+    assert old in text
+    return text.replace(old, new, 1)
+
+
+BAD_GRAPHS = {
+    "not_directed": swap(ALLO, "directed 1", "directed 0"),
+    "directed_missing": swap(ALLO, "  directed 1\n", ""),
+    "no_graph": "Creator \"x\" Version 1",
+    "vertex_lacks_id": swap(ALLO, "node [ id 2 time 1.0 ]", "node [ time 1.0 ]"),
+    "duplicate_id": swap(ALLO, "node [ id 2 time 1.0 ]", "node [ id 1 time 1.0 ]"),
+    "id_out_of_range": swap(ALLO, "node [ id 2 time 1.0 ]", "node [ id 12 time 1.0 ]"),
+    "no_time": swap(ALLO, "node [ id 2 time 1.0 ]", "node [ id 2 ]"),
+    "time_not_a_number": swap(ALLO, "node [ id 2 time 1.0 ]", "node [ id 2 time \"1.0\" ]"),
+    "arc_target_out_of_range": swap(ALLO, "edge [ source 4 target 7 ]", "edge [ source 4 target 9 ]"),
+    "arc_backwards_in_time": swap(ALLO, "edge [ source 2 target 5 ]", "edge [ source 5 target 2 ]"),
+    "self_loop": ALLO.replace("]\n]", "]\n  edge [ source 1 target 1 ]\n]"),
+    "edge_without_target": swap(ALLO, "edge [ source 4 target 7 ]", "edge [ id 3 source 4 ]"),
+    "not_connected": ALLO.replace("edge [ source 4 target 7 ]\n", "").replace("node [ id 7 name \"H\" time 0.0 ]", "node [ id 7 name \"H\" time 0.0 ]\n  node [ id 8 name \"Z\" time 0.0 ]\n  edge [ source 7 target 8 ]"),
+    "stem_tip_with_two_children": ALLO.replace("]\n]", "]\n  edge [ source 0 target 2 ]\n]"),
+    "leaf_on_zero_arc": swap(ALLO, "node [ id 7 name \"H\" time 0.0 ]", "node [ id 7 name \"H\" time 1.0 ]"),
+    "unary_vertex_between_long_arcs": swap(AUTO, "node [ id 2 time 2.0 ]", "node [ id 2 time 1.0 ]"),
+    "two_zero_children": swap(swap(ALLO, "node [ id 5 name \"A\" time 0 ]", "node [ id 5 name \"A\" time 1.0 ]"), "edge [ source 2 target 5 ]", "edge [ source 2 target 5 ]"),
+    "hybrid_with_a_long_parent_arc": swap(ALLO, "node [ id 3 time 1.0 ]", "node [ id 3 time 1.2 ]"),
+    "three_parents": ALLO.replace("]\n]", "]\n  edge [ source 1 target 4 ]\n]"),
+    "leaf_without_name": swap(ALLO, "node [ id 7 name \"H\" time 0.0 ]", "node [ id 7 time 0.0 ]"),
+    "leaf_with_empty_name": swap(ALLO, "name \"H\"", "name \"\""),
+    "syntax_missing_bracket": ALLO.rstrip()[:-1],
+    "syntax_trailing": ALLO + "]",
+    "syntax_bad_key": swap(ALLO, "name \"net\"", "9name \"net\""),
+    "syntax_bad_number": swap(ALLO, "time 1.5", "time 1.5.2"),
+    "syntax_open_string": swap(ALLO, "name \"H\"", "name \"H"),
+    "type_of_id": swap(ALLO, "node [ id 2 time 1.0 ]", "node [ id \"2\" time 1.0 ]"),
+    "type_of_source": swap(ALLO, "edge [ source 4 target 7 ]", "edge [ source 4.0 target 7 ]"),
+    "type_of_directed": swap(ALLO, "directed 1", "directed \"yes\""),
+    # lines are queued without their line breaks: "time 1.5" + "edge" reads as the number 1.5e
+    "token_runs_into_next_line": "graph [\ndirected 1\nnode [ id 0 time 1.5\nedge 1 ]\n]",
+}
+
+
+def both(app, args):
+    rc, text = sg.probe_parse_app(app, args)
+    want = oracle_run(app, args)
+    assert want["files"] == {} and want["stdout"] == ""
+    return rc, text, want["stderr"]
+
+
+@pytest.mark.parametrize("text", [ALLO, AUTO], ids=["allopolyploid", "autopolyploid"])
+@pytest.mark.parametrize("app", ["GuestTreeGen", "DomainTreeGen"])
+def test_valid_hybrid_network_ends_like_the_reference(tmp_path, app, text):
+    f = tmp_path / "net.gml"
+    f.write_text(text)
+    rates = ["0.3", "0.2", "0.0"]
+    for host in (str(f), text):                                   # a file, or the GML text itself as the argument
+        args = ["-s", "4", "-hybrid", "0.2", "2.0", "0.5", host] + (["genes"] if app == "DomainTreeGen" else []) + rates + [str(tmp_path / "out")]
+        rc, got, want = both(app, args)
+        assert rc != 0 and got == want == "java.lang.NullPointerException" + TAIL
+    assert sorted(os.listdir(tmp_path)) == ["net.gml"]
+
+
+@pytest.mark.parametrize("name", sorted(BAD_GRAPHS))
+def test_hybrid_network_checks_match_the_oracle(name):
+    args = ["-s", "4", "-hybrid", "0.2", "2.0", "0.5", BAD_GRAPHS[name], "0.3", "0.2", "0.0", "out"]
+    rc, got, want = both("GuestTreeGen", args)
+    assert rc != 0 and got == want, (name, got, want)
+    assert got.endswith(TAIL) and not got.startswith("java.lang.NullPointerException" + TAIL) or name == "directed_missing"
+
+
+@pytest.mark.parametrize("args,needle", [
+    (["-s", "4", "-hybrid", "0.2", "2.0", "x", ALLO, "0.3", "0.2", "0.0", "out"], "NumberFormatException"),
+    (["-s", "4", "-hybrid", "0.2", "2.0", "0.5", ALLO, "zz", "0.2", "0.0", "out"], "NumberFormatException"),
+    (["-s", "4", "-hybrid", "-0.2", "2.0", "0.5", ALLO, "0.3", "0.2", "0.0", "out"], "Cannot have rate or rate factor less than 0."),
+    (["-s", "4", "-hybrid", "0.2", "2.0", "0.5", ALLO, "-0.3", "0.2", "0.0", "out"], "Cannot have rate or rate factor less than 0."),
+    (["-s", "4", "-hybrid", "0.2", "2.0", "0.5", "-p", "1.5", ALLO, "0.3", "0.2", "0.0", "out"], "Cannot have leaf sampling probability outside [0,1]."),
+    (["-s", "4", "-hybrid", "0.2", "2.0", "0.5", "-p", "p", ALLO, "0.3", "0.2", "0.0", "out"], "NumberFormatException"),
+    (["-s", "4", "-hybrid", "0.2", "2.0", "0.5", "-stem", "s", ALLO, "0.3", "0.2", "0.0", "out"], "NumberFormatException"),
+    (["-s", "4", ALLO, "0.3", "0.2", "0.0", "out", "-hybrid", "0.2", "2.0"], "Expected a value after parameter -hybrid"),
+])
+def test_hybrid_argument_checks_match_the_oracle(args, needle):
+    rc, got, want = both("GuestTreeGen", args)
+    assert rc != 0 and needle in got and needle in want
+    assert got.endswith(TAIL) and want.endswith(TAIL)
+
+
+def test_parse_probe_accepts_ordinary_runs(tmp_path):
+    host = "((A:0.4,B:0.4):0.6,C:1.0):0.2;"
+    assert sg.probe_parse_app("GuestTreeGen", ["-s", "1", host, "0.3", "0.3", "0.1", "o"]) == (0, "")
+    assert sg.probe_parse_app("HostTreeGen", ["-s", "1", "1.0", "2.0", "0.3", "o"]) == (0, "")
+    rc, text = sg.probe_parse_app("HostTreeGen", ["1.0", "2.0"])
+    assert rc == sg.STATUS_USAGE and text == ""
+    rc, text = sg.probe_parse_app("GuestTreeGen", ["-s", "1", host, "-0.3", "0.3", "0.1", "o"])
+    assert rc != 0 and "Cannot have rate less than 0." in text
