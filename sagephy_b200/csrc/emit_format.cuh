@@ -13,16 +13,37 @@ namespace sgp {
 template <class Sink> __device__ __forceinline__ void put_blob(Sink& s, const char* b, int off, int len) { for (int i = 0; i < len; ++i) s.put(b[off + i]); }
 __device__ __forceinline__ void put_blob(CountSink& s, const char*, int, int len) { s.n += len; }
 
-template <class Sink> __device__ __forceinline__ void put_name(Sink& s, const EmitArgs& a, int number, int sigma) {
+// Decimal lengths kept in a finished record. A piece prints its vertex number twice (name, ID=), its host vertex twice (name,
+// HOST= or the row's column) and its epoch once; measuring each number at every use was 15 % of the instructions of the write
+// kernels and 24 % of the finish kernel. The finish kernel now measures each once and keeps the result in the record's `pad`
+// word: bits 0-4 digits of f, then 3 bits each for number, sigma and epoch (0 = not recorded: negative, or more than 7 digits).
+__device__ __forceinline__ int len_hint(int v) { return (v >= 0 && v < 10000000) ? dec_len_u32((uint32_t)v) : 0; }
+__device__ __forceinline__ int pack_pad(int nd, int number, int sigma, int epoch) { return nd | (len_hint(number) << 5) | (len_hint(sigma) << 8) | (len_hint(epoch) << 11); }
+__device__ __forceinline__ int pad_nd(int pad) { return pad & 31; }
+__device__ __forceinline__ int pad_num(int pad) { return (pad >> 5) & 7; }
+__device__ __forceinline__ int pad_sig(int pad) { return (pad >> 8) & 7; }
+__device__ __forceinline__ int pad_ep(int pad) { return (pad >> 11) & 7; }
+template <class Sink> __device__ __forceinline__ void put_i32_len(Sink& s, int v, int len) {
+    if (len == 0) { put_i32(s, v); return; }
+    if (Sink::kCounts) s.skip(len); else put_u32_digits(s, (uint32_t)v, len);
+}
+
+template <class Sink> __device__ __forceinline__ void put_name(Sink& s, const EmitArgs& a, int number, int sigma, int pad) {
     for (int i = 0; i < a.prefix_len; ++i) s.put(a.prefix[i]);
-    put_i32(s, number);
-    if (a.append_sigma) { s.put('_'); put_i32(s, sigma); }
+    put_i32_len(s, number, pad_num(pad));
+    if (a.append_sigma) { s.put('_'); put_i32_len(s, sigma, pad_sig(pad)); }
 }
 
 // f x 10^e as java.lang.Double.toString lays it out; e == kNoDigits: f holds the bits of a value without digits (0.0, NaN, ...)
 // nd: number of digits of f (kept in the record: the finish kernel counts them once)
+// values without digits (0.0 at the root, NaN, infinities, negatives): the general java.lang.Double.toString, out of line - it is
+// rare, and inlined it put a second copy of the whole shortest-decimal conversion into every instantiation of every piece
+template <class Sink> static __device__ __noinline__ void put_double_out_of_line(Sink& s, const unsigned long long* g, const double* p10, double v) {
+    MathTables T; T.g = g; T.p10 = p10;
+    put_double(s, T, v);
+}
 template <class Sink> __device__ __forceinline__ void put_decimal(Sink& s, const MathTables& T, uint64_t f, int e, int nd) {
-    if (e == kNoDigits) { put_double(s, T, __longlong_as_double((long long)f)); return; }
+    if (e == kNoDigits) { put_double_out_of_line(s, T.g, T.p10, __longlong_as_double((long long)f)); return; }
     // the layout depends on 1e-3 <= v < 1e7 only; v = 0.DIGITS x 10^pe, so that is -2 <= pe <= 7
     const int pe = nd + e;
     put_double_digits(s, (pe >= -2 && pe <= 7) ? 1.0 : 1e-9, f, e, nd);
@@ -30,6 +51,15 @@ template <class Sink> __device__ __forceinline__ void put_decimal(Sink& s, const
 __device__ __forceinline__ void decimal_of(const MathTables& T, double v, uint64_t* f, int* e) {
     if (v > 0.0 && v < dbl_inf()) d2s_decimal(T, v, f, e);
     else { *f = (uint64_t)__double_as_longlong(v); *e = kNoDigits; }
+}
+// The same as ONE out-of-line copy (the finish kernel converts at four places; inlined four times the conversion alone was
+// 100 KB of code against an instruction cache of 32 KB, and `no_instruction` was that kernel's largest stall). Returns
+// f; e and the digit count of f come back packed as (e & 0xffff) | nd << 16.
+static __device__ __noinline__ uint64_t decimal_of_packed(const unsigned long long* g, const double* p10, double v, int* e_nd) {
+    MathTables T; T.g = g; T.p10 = p10;
+    uint64_t f; int e; decimal_of(T, v, &f, &e);
+    *e_nd = (e & 0xffff) | ((e == kNoDigits ? 0 : dec_len_u64(f)) << 16);
+    return f;
 }
 
 template <class Sink> __device__ __forceinline__ void put_discpt(Sink& s, int epoch, int j) {
@@ -47,9 +77,9 @@ __device__ __forceinline__ bool is_transfer_event(int ev) { return ev >= EV_ADDI
 // Lanes print different vertex types in the same trip, so everything that is common to several types (the key, the DISCPT tag)
 // is outside the switch: a branch of a switch runs once per type present in the warp.
 template <class Sink> __device__ void put_meta(Sink& s, const EmitArgs& a, const TreeRec& t, const TreeRecX* xp) {
-    put_lit(s, "[ID="); put_i32(s, t.number);
+    put_lit(s, "[ID="); put_i32_len(s, t.number, pad_num(t.pad));
     if (!a.is_species) {
-        put_lit(s, " HOST="); put_i32(s, t.sigma); put_lit(s, " GUEST=");
+        put_lit(s, " HOST="); put_i32_len(s, t.sigma, pad_sig(t.pad)); put_lit(s, " GUEST=");
         put_blob(s, a.blob, a.gname_off[2 * t.gtree], a.gname_off[2 * t.gtree + 1]);
     }
     put_lit(s, " VERTEXTYPE=");
@@ -80,7 +110,7 @@ template <class Sink> __device__ void put_meta(Sink& s, const EmitArgs& a, const
             s.put(')'); discpt = true;
         }
     }
-    if (discpt) { put_lit(s, " DISCPT=("); put_i32(s, t.epoch); s.put(','); s.put((char)('0' + ((t.flags >> TR_J_SHIFT) & 3))); s.put(')'); }
+    if (discpt) { put_lit(s, " DISCPT=("); put_i32_len(s, t.epoch, pad_ep(t.pad)); s.put(','); s.put((char)('0' + ((t.flags >> TR_J_SHIFT) & 3))); s.put(')'); }
     s.put(']');
 }
 
@@ -92,9 +122,9 @@ template <bool PRUNED, class Sink> __device__ void put_tree_piece(Sink& s, const
         const int c = leaf ? t.chain : 1; const char ch = leaf ? '(' : ')';
         for (int i = 0; i < c; ++i) s.put(ch);
     }
-    put_name(s, a, t.number, t.sigma);
+    put_name(s, a, t.number, t.sigma, t.pad);
     s.put(':');
-    put_decimal(s, a.T, t.f, t.e, t.pad);
+    put_decimal(s, a.T, t.f, t.e, pad_nd(t.pad));
     if (!a.exclude_meta) put_meta(s, a, t, xp);
     if (t.flags & TR_COMMA) s.put(',');
     if (t.flags & TR_ROOT) {
@@ -128,12 +158,12 @@ __device__ __forceinline__ void put_event_enum(CountSink& s, int e) { s.n += eve
 
 // .guest2host row: name, id, type, time (unrounded), host vertex / arc, host epoch
 template <class Sink> __device__ void put_g2h_row(Sink& s, const EmitArgs& a, const RowRec& r) {
-    put_name(s, a, r.number, r.sigma); s.put('\t'); put_i32(s, r.number); s.put('\t'); put_event_enum(s, r.event); s.put('\t');
-    put_decimal(s, a.T, r.f, r.e, r.pad); s.put('\t'); put_i32(s, r.sigma); s.put('\t'); put_i32(s, r.epoch); s.put('\n');
+    put_name(s, a, r.number, r.sigma, r.pad); s.put('\t'); put_i32_len(s, r.number, pad_num(r.pad)); s.put('\t'); put_event_enum(s, r.event); s.put('\t');
+    put_decimal(s, a.T, r.f, r.e, pad_nd(r.pad)); s.put('\t'); put_i32_len(s, r.sigma, pad_sig(r.pad)); s.put('\t'); put_i32_len(s, r.epoch, pad_ep(r.pad)); s.put('\n');
 }
 // .leafmap row of a leaf of the view (RR_LEAFMAP): name, host leaf name [, gene tree name]
 template <class Sink> __device__ void put_leafmap_row(Sink& s, const EmitArgs& a, const RowRec& r) {
-    put_name(s, a, r.number, r.sigma); s.put('\t');
+    put_name(s, a, r.number, r.sigma, r.pad); s.put('\t');
     const int li = (a.app == 2 ? a.leaf_base[r.gtree] : 0) + r.sigma;
     put_blob(s, a.blob, a.leafname_off[2 * li], a.leafname_off[2 * li + 1]);
     if (a.app == 2) { s.put('\t'); put_blob(s, a.blob, a.gname_off[2 * r.gtree], a.gname_off[2 * r.gtree + 1]); }    // DomainTreeInHostTreeCreator.getLeafMap :1266
@@ -174,9 +204,9 @@ template <bool PRUNED> __device__ __forceinline__ RowRec raw_row_rec(const Node&
 template <bool PRUNED> __device__ __forceinline__ long long finish_tree_rec(const EmitArgs& a, TreeRec& t, const TreeRecX* xp, const TreeRec* twin) {
     const int link = t.link;
     int nd;
-    if (PRUNED && twin && link >= 0) { t.f = twin[link].f; t.e = twin[link].e; nd = twin[link].pad; }
-    else { uint64_t f; int e; decimal_of(a.T, __longlong_as_double((long long)t.f), &f, &e); t.f = f; t.e = (int16_t)e; nd = e == kNoDigits ? 0 : dec_len_u64(f); }
-    t.pad = (int16_t)nd;            // (pad shares its word with link: from here on the record is finished)
+    if (PRUNED && twin && link >= 0) { t.f = twin[link].f; t.e = twin[link].e; nd = pad_nd(twin[link].pad); }
+    else { int e_nd; t.f = decimal_of_packed(a.T.g, a.T.p10, __longlong_as_double((long long)t.f), &e_nd); t.e = (int16_t)(e_nd & 0xffff); nd = e_nd >> 16; }
+    t.pad = (int16_t)pack_pad(nd, t.number, t.sigma, t.epoch);            // (pad shares its word with link: from here on the record is finished)
     CountSink c; put_tree_piece<PRUNED>(c, a, t, xp);
     t.len = clamp_len(c.n);
     return c.n;
@@ -185,16 +215,18 @@ template <bool PRUNED> __device__ __forceinline__ long long finish_tree_rec(cons
 __device__ __forceinline__ void finish_row_rec(const EmitArgs& a, RowRec& r, bool need_g2h, bool need_lm, const RowRec* twin, bool twin_has_g2h, long long* len_g2h, long long* len_lm) {
     long long lg = 0, ll = 0;
     const int link = r.link;
-    int nd = 0;
+    int pad = 0;
     if (need_g2h) {
-        if (twin && twin_has_g2h && link >= 0) { r.f = twin[link].f; r.e = twin[link].e; nd = twin[link].pad; r.pad = (uint16_t)nd; lg = twin[link].len_g2h; if (lg == 0xffff) { CountSink c; put_g2h_row(c, a, r); lg = c.n; } }
+        // a linked row prints the same vertex (same number, host vertex, epoch and time) as its twin: the whole pad word carries over
+        if (twin && twin_has_g2h && link >= 0) { r.f = twin[link].f; r.e = twin[link].e; pad = twin[link].pad; r.pad = (uint16_t)pad; lg = twin[link].len_g2h; if (lg == 0xffff) { CountSink c; put_g2h_row(c, a, r); lg = c.n; } }
         else {
-            uint64_t f; int e; decimal_of(a.T, __longlong_as_double((long long)r.f), &f, &e); r.f = f; r.e = (int16_t)e; nd = e == kNoDigits ? 0 : dec_len_u64(f);
-            r.pad = (uint16_t)nd; CountSink c; put_g2h_row(c, a, r); lg = c.n;
+            int e_nd; r.f = decimal_of_packed(a.T.g, a.T.p10, __longlong_as_double((long long)r.f), &e_nd); r.e = (int16_t)(e_nd & 0xffff);
+            pad = pack_pad(e_nd >> 16, r.number, r.sigma, r.epoch);
+            r.pad = (uint16_t)pad; CountSink c; put_g2h_row(c, a, r); lg = c.n;
         }
-    }
+    } else { pad = pack_pad(0, r.number, r.sigma, r.epoch); r.pad = (uint16_t)pad; }
     if (need_lm && (r.flags & RR_LEAFMAP)) { CountSink c; put_leafmap_row(c, a, r); ll = c.n; }
-    r.len_g2h = clamp_len(lg); r.len_lm = clamp_len(ll); r.pad = (uint16_t)nd; *len_g2h = lg; *len_lm = ll;
+    r.len_g2h = clamp_len(lg); r.len_lm = clamp_len(ll); r.pad = (uint16_t)pad; *len_g2h = lg; *len_lm = ll;
 }
 
 }  // namespace sgp

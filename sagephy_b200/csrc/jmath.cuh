@@ -224,6 +224,25 @@ SGP_HD int d2s_flog10pow2(int e) { return (int)(((int64_t)e * 661971961083LL) >>
 SGP_HD int d2s_flog10_34pow2(int e) { return (int)(((int64_t)e * 661971961083LL + (-274743187321LL)) >> 41); }
 SGP_HD int d2s_flog2pow10(int e) { return (int)(((int64_t)e * 913124641741LL) >> 38); }
 
+// x (!= 0) without its trailing decimal zeros; *k = how many there were (<= 9). Four fixed steps, no loop.
+SGP_HD uint32_t strip_zeros_u32(uint32_t x, int* k_out) {
+    int k = 0; uint32_t q;
+    q = x / 100000000u; if (q * 100000000u == x) { x = q; k += 8; }
+    q = x / 10000u;     if (q * 10000u == x)     { x = q; k += 4; }
+    q = x / 100u;       if (q * 100u == x)       { x = q; k += 2; }
+    q = x / 10u;        if (q * 10u == x)        { x = q; k += 1; }
+    *k_out = k;
+    return x;
+}
+// 10^k for 0 <= k <= 9 as a product of selected factors (no table, no loop)
+SGP_HD uint32_t pow10_u32(int k) {
+    uint32_t p = (k & 1) ? 10u : 1u;
+    if (k & 2) p *= 100u;
+    if (k & 4) p *= 10000u;
+    if (k & 8) p *= 100000000u;
+    return p;
+}
+
 // Shortest decimal: v (finite, > 0) == f * 10^e with f free of trailing zeros. Mirrors the published Schubfach
 // procedure that Double.toString is specified by since JDK 19 (R. Giulietti, "The Schubfach way to render doubles").
 SGP_HD void d2s_decimal(const MathTables& T, double v, uint64_t* f_out, int* e_out) {
@@ -273,8 +292,9 @@ SGP_HD void d2s_decimal(const MathTables& T, double v, uint64_t* f_out, int* e_o
             e = k + dk;
         }
     }
-    // strip trailing zeros (32-bit limbs: branch lengths rounded to 8 significant digits end in nine zeros, and a 64-bit division
-    // per stripped digit made this loop the most expensive part of the conversion on the device)
+    // strip trailing zeros: 32-bit limbs (branch lengths rounded to 8 significant digits end in nine zeros, and a 64-bit division
+    // per stripped digit made this the most expensive part of the conversion on the device) and a fixed sequence of four
+    // divisibility tests (10^8, 10^4, 10^2, 10) instead of a loop per digit: lanes of a warp strip different numbers of zeros
     {
         const uint64_t hi = f / 1000000000ull; uint32_t lo = (uint32_t)(f - hi * 1000000000ull);
         if (hi == 0 || lo == 0) {
@@ -282,17 +302,14 @@ SGP_HD void d2s_decimal(const MathTables& T, double v, uint64_t* f_out, int* e_o
             if (hi != 0) { rest = hi; e += 9; }          // f = hi x 10^9
             else rest = lo;
             if (rest <= 0xffffffffull) {
-                uint32_t x = (uint32_t)rest;
-                while (x >= 10u) { const uint32_t q = x / 10u; if (q * 10u != x) break; x = q; ++e; }
-                f = x;
+                int k; f = strip_zeros_u32((uint32_t)rest, &k); e += k;
             } else {
                 f = rest;
                 while (f >= 10) { const uint64_t qd = f / 10; if (qd * 10 != f) break; f = qd; ++e; }
             }
         } else {
-            int k = 0; uint32_t p10 = 1;
-            while (true) { const uint32_t q = lo / 10u; if (q * 10u != lo) break; lo = q; ++k; p10 *= 10u; }
-            if (k) { f = hi * (uint64_t)(1000000000u / p10) + lo; e += k; }
+            int k; lo = strip_zeros_u32(lo, &k);
+            if (k) { f = hi * (uint64_t)pow10_u32(9 - k) + lo; e += k; }
         }
     }
     *f_out = f; *e_out = e;

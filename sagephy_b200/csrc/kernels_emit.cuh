@@ -340,8 +340,8 @@ template <int INSTANCE> __global__ void __launch_bounds__(256) k_finish_records(
     const unsigned mask = a.stream_mask;
     const int up = n_u, nu = p_root_ >= 0 ? n_p : 0;
     unsigned long long* sz = a.sizes + r;
-#pragma unroll
-    for (int view = 0; view < 2; ++view) {
+#pragma unroll 1
+    for (int view = 0; view < 2; ++view) {          // (not unrolled: the body is ~2 000 instructions and the instruction cache 32 KB)
         const int n = view ? nu : up;
         if (mask & (1u << (view ? ST_PRUNED_TREE : ST_UNPRUNED_TREE))) {
             TreeRec* recs = a.trec + (size_t)view * a.aux_stride + off;
