@@ -6,7 +6,9 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <chrono>
 #include <map>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include "engine.hpp"
@@ -27,13 +29,107 @@ namespace {
 // Device buffers come from the CUDA stream-ordered pool (release threshold = unlimited, see Context::Context), so
 // steady-state batches reuse memory instead of paying cudaMalloc/cudaFree per phase.
 thread_local cudaStream_t g_alloc_stream = nullptr;
+// SGP_TRACE=1: host time stamps between the phases of a run (where does the host wait?), printed to stderr at the end of the run
+struct HostMarks {
+    bool on = getenv("SGP_TRACE") != nullptr; std::vector<std::pair<const char*, double>> v;
+    void mark(const char* name) { if (on) v.emplace_back(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count()); }
+    void dump() { if (!on || v.empty()) return; std::string o = "sgp trace (host ms):"; for (size_t i = 1; i < v.size(); ++i) { char b[96]; snprintf(b, sizeof b, " %s %.2f", v[i].first, v[i].second - v[i - 1].second); o += b; } fprintf(stderr, "%s\n", o.c_str()); v.clear(); }
+};
+thread_local HostMarks g_marks;
 thread_local unsigned long long g_h2d_bytes = 0;      // host->device bytes of the current run (tables, constant strings, templates)
+// Size classes for large stream-ordered allocations. The sizes of a run's big buffers (vertex arena, records, output streams) differ
+// by a fraction of a percent from one batch to the next; the pool cannot serve a request from a free block that is a few KB too
+// small, so every batch made it map fresh memory - and that blocks the calling thread until ALL work in flight on the device has
+// drained, including a caller's device-to-host copies of the previous batch (measured: 3-100 ms per cudaMallocAsync inside the
+// end-to-end pipeline, none without the copies in flight). Rounded up to one of 64 classes per octave (< 1.6 % over-allocation)
+// consecutive batches ask for the same sizes and the pool hands the previous batch's blocks back.
+inline size_t pool_size_class(size_t bytes) {
+    if (bytes < (size_t)(1u << 20)) return bytes;
+    size_t g = 1; while ((g << 6) < bytes) g <<= 1;          // bytes / 128 < g <= bytes / 64
+    return (bytes + g - 1) / g * g;
+}
+// Large device buffers (vertex arena, records, output streams: everything from kBigBytes up) do not go through the stream-ordered
+// pool at all. The pool serves a request that fits none of its free blocks by re-mapping physical memory, and that waits for ALL
+// work in flight on the device - a caller's device-to-host copies of the previous batch included (see pool_size_class); which
+// requests fit depends on the history of the pool, and the stalls came and went with the order of the workloads. These buffers
+// are plain cudaMalloc blocks kept in a per-device free list instead: a request takes the smallest free block of at least its
+// size class (and at most 1.25 x), a free puts the block back - no driver call, no mapping, nothing to wait for. Reuse is safe in
+// stream order: a block handed back while work may still be using it carries an event recorded on the stream that used it, and a
+// taker on another stream (a second context on the same device) waits for that event first; blocks that were visible to the caller
+// (a batch's outputs, which it may still be copying) are only put back after the device has gone idle, as cudaFree would have
+// waited for. When the device runs out of memory every unused block (and the pool's reserve) goes back to the driver and the
+// request is retried.
+constexpr size_t kBigBytes = (size_t)32 << 20;
+struct BlockCache {
+    struct Block { void* p; size_t bytes; bool used; cudaEvent_t ev; cudaStream_t last; bool pending; };
+    std::mutex mu; std::vector<Block> blocks;
+    static BlockCache& of(int device) { static BlockCache caches[64]; return caches[device & 63]; }
+    void* take(size_t bytes, cudaStream_t on) {
+        const size_t want = pool_size_class(bytes);
+        {
+            std::lock_guard<std::mutex> g(mu);
+            Block* best = nullptr;
+            for (Block& b : blocks) if (!b.used && b.bytes >= want && b.bytes <= want + want / 4 && (!best || b.bytes < best->bytes)) best = &b;
+            if (best) {
+                best->used = true;
+                if (best->pending && best->last != on) cudaStreamWaitEvent(on, best->ev, 0);
+                best->pending = false;
+                return best->p;
+            }
+        }
+        void* q = nullptr;
+        const bool trace = getenv("SGP_TRACE") != nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
+        cudaError_t e = cudaMalloc(&q, want);
+        const bool oom = e == cudaErrorMemoryAllocation;
+        if (oom) { cudaGetLastError(); drop_unused(); e = cudaMalloc(&q, want); }
+        if (trace) fprintf(stderr, "sgp trace: new block of %zu MiB%s, %.2f ms\n", want >> 20, oom ? " after returning every unused block to the driver" : "", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        if (e != cudaSuccess) { cudaGetLastError(); throw SgpError(std::string("out of device memory (") + std::to_string(want >> 20) + " MiB requested): " + cudaGetErrorString(e)); }
+        std::lock_guard<std::mutex> g(mu);
+        blocks.push_back({q, want, true, nullptr, nullptr, false});
+        return q;
+    }
+    // true if p was one of ours. `idle`: the device is known to have finished with the block; otherwise work queued on `on` may still use it
+    bool give_back(void* p, cudaStream_t on, bool idle) {
+        std::lock_guard<std::mutex> g(mu);
+        for (Block& b : blocks) if (b.p == p) {
+            b.used = false; b.pending = false;
+            if (!idle) {
+                if (!b.ev) cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming);
+                if (b.ev && cudaEventRecord(b.ev, on) == cudaSuccess) { b.pending = true; b.last = on; } else { cudaGetLastError(); cudaDeviceSynchronize(); }
+            }
+            return true;
+        }
+        return false;
+    }
+    void drop_unused() {
+        cudaDeviceSynchronize();
+        {
+            std::lock_guard<std::mutex> g(mu);
+            for (size_t i = 0; i < blocks.size();) { if (!blocks[i].used) { cudaFree(blocks[i].p); if (blocks[i].ev) cudaEventDestroy(blocks[i].ev); blocks[i] = blocks.back(); blocks.pop_back(); } else ++i; }
+        }
+        cudaMemPool_t dflt; int dev = 0; cudaGetDevice(&dev);
+        if (cudaDeviceGetDefaultMemPool(&dflt, dev) == cudaSuccess) cudaMemPoolTrimTo(dflt, 0);
+    }
+};
+thread_local int g_device = 0;
+inline cudaError_t malloc_async_retry(void** p, size_t bytes, cudaStream_t on) {
+    cudaError_t e = cudaMallocAsync(p, bytes, on);
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); BlockCache::of(g_device).drop_unused(); e = cudaMallocAsync(p, bytes, on); }
+    return e;
+}
 template <class T> struct DevBuf {
     T* p = nullptr; size_t n = 0;
     DevBuf() {}
     DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { if (p) cudaFreeAsync(p, g_alloc_stream); }
-    void alloc(size_t count) { if (p) { cudaFreeAsync(p, g_alloc_stream); p = nullptr; } n = count; if (count) CK(cudaMallocAsync(&p, count * sizeof(T), g_alloc_stream)); }
+    ~DevBuf() { drop(); }
+    void drop() { if (p && !BlockCache::of(g_device).give_back(p, g_alloc_stream, false)) cudaFreeAsync(p, g_alloc_stream); p = nullptr; }
+    void alloc(size_t count) {
+        drop(); n = count;
+        if (!count) return;
+        if (count * sizeof(T) >= kBigBytes) p = (T*)BlockCache::of(g_device).take(count * sizeof(T), g_alloc_stream);
+        else CK(malloc_async_retry((void**)&p, count * sizeof(T), g_alloc_stream));
+    }
     void upload(const std::vector<T>& v) { alloc(v.size()); if (!v.empty()) { CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, g_alloc_stream)); CK(cudaStreamSynchronize(g_alloc_stream)); g_h2d_bytes += v.size() * sizeof(T); } }
     T* release() { T* q = p; p = nullptr; n = 0; return q; }
 };
@@ -204,6 +300,8 @@ struct Context::Impl {
     // pool's free blocks costs hundreds of milliseconds of unmap / map).
     void* scratch_buf[8] = {nullptr}; size_t scratch_bytes[8] = {0};
     void* scratch(int slot, size_t bytes);
+    // Output streams: block cache for the large ones (see BlockCache), the stream-ordered pool for the rest.
+    void alloc_output(char** p, size_t bytes, cudaStream_t on);
     void post(size_t off, const void* dsrc, size_t bytes, cudaStream_t on = nullptr);
     template <class T> T take(size_t off) const { T v; memcpy(&v, mailbox + off, sizeof(T)); return v; }
     DevBuf<unsigned long long> g_table; DevBuf<double> p10;
@@ -222,10 +320,18 @@ void Context::Impl::post(size_t off, const void* dsrc, size_t bytes, cudaStream_
     k_post_words<<<1, 256, 0, on ? on : stream>>>(reinterpret_cast<uint32_t*>(mailbox + off), static_cast<const uint32_t*>(dsrc), (int)(bytes / 4));
 }
 
+void Context::Impl::alloc_output(char** p, size_t bytes, cudaStream_t on) {
+    const size_t want = std::max<size_t>(bytes, 1);
+    if (want >= kBigBytes) *p = (char*)BlockCache::of(g_device).take(want, on);
+    else CK(malloc_async_retry((void**)p, want, on));
+}
+
 void* Context::Impl::scratch(int slot, size_t bytes) {
     if (bytes > scratch_bytes[slot]) {
         if (scratch_buf[slot]) { CK(cudaStreamSynchronize(stream)); CK(cudaFree(scratch_buf[slot])); scratch_buf[slot] = nullptr; scratch_bytes[slot] = 0; }
-        CK(cudaMalloc(&scratch_buf[slot], bytes)); scratch_bytes[slot] = bytes;
+        cudaError_t e = cudaMalloc(&scratch_buf[slot], bytes);
+        if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); BlockCache::of(g_device).drop_unused(); e = cudaMalloc(&scratch_buf[slot], bytes); }
+        CK(e); scratch_bytes[slot] = bytes;
     }
     return scratch_buf[slot];
 }
@@ -269,7 +375,13 @@ Batch::Batch() {}
 Batch::~Batch() {
     cudaSetDevice(device);
     // plain cudaFree: the owning context (and its stream) may already be gone when a batch is released
-    auto rel = [&](void* q) { if (q) cudaFree(q); };
+    // cached blocks go back to the per-device free list once the device is idle (the caller may have copies of them in flight)
+    bool synced = false;
+    auto rel = [&](void* q) {
+        if (!q) return;
+        if (!synced) { cudaDeviceSynchronize(); synced = true; }
+        if (!BlockCache::of(device).give_back(q, nullptr, true)) cudaFree(q);
+    };
     for (int s = 0; s < 8; ++s) { rel(d_stream[s]); if (h_stream[s]) cudaFreeHost(h_stream[s]); }
     rel(d_offsets); rel(d_info); rel(d_values[0]); rel(d_values[1]); rel(d_nodes); rel(d_aux); rel(d_node_off);
 }
@@ -376,7 +488,7 @@ static TinyHost make_tiny(const HostModel& h) {
 void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch& out) {
     CK(cudaSetDevice(device));
     cudaStream_t st = impl->stream;
-    g_alloc_stream = st;
+    g_alloc_stream = st; g_device = device;
     const long long n = opts.n;
     if (n <= 0) throw SgpError("replicate count must be positive");
     const bool replay = opts.rng_mode == 1;
@@ -400,7 +512,9 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     const unsigned long long seed = cfg.seed.philox_key;
     std::string seed_blob_dummy; const SeedSpec sseed = make_seed_spec(cfg.seed, seed_blob_dummy);      // MT keys need no blob
 
+    g_marks.mark("start");
     HostOnDevice hd; hd.upload(cfg.host);
+    g_marks.mark("host_upload");
     const bool domain = cfg.app == 2;
     std::vector<std::unique_ptr<HostOnDevice>> gene_dev; std::vector<DevHost> gene_views; int max_gene_nv = 1;
     for (const HostModel& g : cfg.genes) { gene_dev.emplace_back(new HostOnDevice()); gene_dev.back()->upload(g); gene_views.push_back(gene_dev.back()->view); max_gene_nv = std::max(max_gene_nv, g.nV); }
@@ -680,7 +794,9 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         return a;
     };
     auto post_process = [&](Sub& S, int k) {
+        g_marks.mark("enqueued_find");
         CK(cudaEventSynchronize(S.ev_found));
+        g_marks.mark("find_done");
         S.total_nodes = impl->take<long long>(kMailFind + (size_t)(k & 15) * 16); S.max_pool = impl->take<int>(kMailFind + (size_t)(k & 15) * 16 + 8);
         if (piped) CK(cudaStreamWaitEvent(stB, S.ev_found, 0));
         g_alloc_stream = stB;
@@ -756,6 +872,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             CK(cudaGetLastError());
         }
         span_end(sp, stB);
+        g_marks.mark("label_enqueued");
         sp = span_begin(&tm.emit_size_ms, stB);
         EmitArgs ea = emit_args_for(S);
         tm.launches += launch_emit_sizes(ea, stB);
@@ -766,7 +883,9 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             // output buffers: exact for a single sub-batch, otherwise sized from the first sub-batch's bytes per replicate with a margin
             // (a later sub-batch that does not fit raises `overflow`; the run is then repeated unpipelined with exact sizes)
             impl->post(kMailEmit, carry.p, ST_COUNT * sizeof(unsigned long long), stB);
+            g_marks.mark("sizes_enqueued");
             CK(cudaStreamSynchronize(stB));
+            g_marks.mark("sizes_done");
             g_alloc_stream = stB;
             for (int q = 0; q < ST_COUNT; ++q) {
                 const unsigned long long first = impl->take<unsigned long long>(kMailEmit + (size_t)q * 8);
@@ -777,7 +896,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
                     const double per = (double)first / (double)S.n; cap = (unsigned long long)(per * (double)n * margin) + (me ? 0ull : (1ull << 20));
                 }
                 out_cap[q] = std::max<unsigned long long>(cap, 1);
-                CK(cudaMallocAsync(&out.d_stream[q], out_cap[q], stB));
+                impl->alloc_output(&out.d_stream[q], out_cap[q], stB);
                 // mean piece length of the Newick streams (a vertex is one piece; the rows of the other streams are shorter)
                 if (q == ST_UNPRUNED_TREE || q == ST_PRUNED_TREE) mean_piece = std::max(mean_piece, (double)first / (double)std::max<long long>(S.total_nodes, 1));
             }
@@ -788,6 +907,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
             g_alloc_stream = stA;
             ea = emit_args_for(S);
         }
+        g_marks.mark("outputs_allocated");
         sp = span_begin(&tm.emit_write_ms, stB);
         tm.launches += launch_emit_write(ea, stB, impl->side, 2, impl->ev_fork, impl->ev_join);
         CK(cudaGetLastError());
@@ -806,11 +926,13 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         post_process(*subs[(size_t)k], k);
     }
     impl->post(kMailEmit, carry.p, ST_COUNT * sizeof(unsigned long long), stB); impl->post(kMailEmit + 64, overflow.p, sizeof(int), stB);
+    g_marks.mark("write_enqueued");
     CK(cudaStreamSynchronize(stB)); CK(cudaStreamSynchronize(stA));
+    g_marks.mark("write_done");
     for (int q = 0; q < ST_COUNT; ++q) { totals[q] = impl->take<unsigned long long>(kMailEmit + (size_t)q * 8); out.stream_bytes[q] = totals[q]; }
     if (impl->take<int>(kMailEmit + 64) != 0) {
         // a stream outgrew its estimated buffer: start over without the pipeline (exact sizes)
-        for (int q = 0; q < ST_COUNT; ++q) { if (out.d_stream[q]) { cudaFree(out.d_stream[q]); out.d_stream[q] = nullptr; } out.stream_bytes[q] = 0; }
+        for (int q = 0; q < ST_COUNT; ++q) { if (out.d_stream[q]) { if (!BlockCache::of(device).give_back(out.d_stream[q], stB, false)) cudaFree(out.d_stream[q]); out.d_stream[q] = nullptr; } out.stream_bytes[q] = 0; }
         subs.clear();
         BatchOpts o2 = opts; o2.serial = true;
         run_treegen(cfg, o2, out);
@@ -823,6 +945,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
         DevBuf<DevSummary> ds; ds.alloc(1); CK(cudaMemsetAsync(ds.p, 0, sizeof(DevSummary), st));
         k_summary<<<(unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)impl->sm_count * 4)), 256, 0, st>>>(info.p, n, ds.p); ++tm.launches;
         impl->post(0, ds.p, sizeof(DevSummary), st); CK(cudaStreamSynchronize(st));
+        g_marks.mark("summary_done");
         const DevSummary hs = impl->take<DevSummary>(0);
         Summary& S = out.summary; S.n_ok = (long long)hs.n_ok; S.n_failed = (long long)hs.n_failed; S.attempts_total = (long long)hs.attempts_total; S.vertices_sampled = (long long)hs.vertices; S.vertices_abandoned = (long long)hs.vertices_abandoned; S.attempts_completed = (long long)hs.attempts_completed;
         for (int i = 0; i < 17; ++i) S.event_counts[i] = (long long)hs.ev[i];
@@ -839,6 +962,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
     for (int s = 0; s < 8; ++s) out.suffix[s] = (mask & (1u << s)) ? host_sfx[s] : "";
     out.stream_mask = mask;
     tm.total_ms = total.stop(); tm.h2d_bytes = (long long)g_h2d_bytes;
+    g_marks.mark("end"); g_marks.dump();
     tm.sub_batches = K;
     out.timings = tm;
     if (!opts.keep_on_device) {
@@ -856,7 +980,7 @@ void Context::run_treegen(const TreeGenConfig& cfg, const BatchOpts& opts, Batch
 // leaves ~25 bytes per vertex, which is all that crosses PCIe: no Newick text is written or parsed.
 std::vector<FlatTree> Context::ingest_trees(const Batch& src, long long first, long long count, bool pruned) {
     CK(cudaSetDevice(device));
-    cudaStream_t st = impl->stream; g_alloc_stream = st;
+    cudaStream_t st = impl->stream; g_alloc_stream = st; g_device = device;
     if (!src.d_nodes || !src.d_info || !src.d_aux || src.device != device) throw SgpError("source batch holds no trees on this device (run the generator with SGP_FLAG_KEEP_TREES)");
     if (first < 0 || count <= 0 || first + count > src.n) throw SgpError("tree range outside the source batch");
     if (count > (1 << 24)) throw SgpError("too many trees for one forest");
@@ -924,7 +1048,7 @@ const double* Batch::values_host(int which) {
 
 void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& out, const Batch* src, bool src_pruned) {
     CK(cudaSetDevice(device));
-    cudaStream_t st = impl->stream; g_alloc_stream = st;
+    cudaStream_t st = impl->stream; g_alloc_stream = st; g_device = device;
     const long long n = opts.n;
     if (n <= 0) throw SgpError("replicate count must be positive");
     const bool replay = opts.rng_mode == 1;
@@ -1044,7 +1168,7 @@ void Context::run_relax(const RelaxConfig& cfg, const BatchOpts& opts, Batch& ou
         CK(cudaStreamSynchronize(st));
         for (int s = 0; s < 2; ++s) totals[s] = impl->take<unsigned long long>((size_t)s * 8);
         tm.emit_size_ms = ph.stop();
-        for (int s = 0; s < 2; ++s) { out.stream_bytes[s] = totals[s]; CK(cudaMallocAsync(&out.d_stream[s], std::max<unsigned long long>(totals[s], 1), st)); a.out[s] = out.d_stream[s]; }
+        for (int s = 0; s < 2; ++s) { out.stream_bytes[s] = totals[s]; impl->alloc_output(&out.d_stream[s], totals[s], st); a.out[s] = out.d_stream[s]; }
         ph.start();
         launch_relax_emit(true, a, st); ++tm.launches; CK(cudaGetLastError());
         tm.emit_write_ms = ph.stop();

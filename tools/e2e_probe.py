@@ -24,3 +24,25 @@ for rep in range(3):
     print("copy alone ms", dt * 1e3, "GB/s", tot / dt / 1e9)
 t = time.perf_counter(); st = b.rep_status; print("rep_status ms", (time.perf_counter() - t) * 1e3)
 t = time.perf_counter(); b.free(); print("free ms", (time.perf_counter() - t) * 1e3)
+
+# the pipelined loop of bench.py's e2e leg with host timers around every phase (where do the bubbles on the copy engine come from?)
+import collections
+ph = collections.defaultdict(float); prev = None; n_steps = 10
+torch.cuda.synchronize(); T0 = time.perf_counter()
+for i in range(n_steps):
+    t = time.perf_counter(); b = step(30 + i); ph["compute (blocking)"] += time.perf_counter() - t
+    for k, v in b.timings().items():
+        if k.endswith("_ms"): ph["dev " + k] += v * 1e-3
+    if prev is not None:
+        t = time.perf_counter(); ctx.wait_copies(); ph["wait_copies"] += time.perf_counter() - t
+        t = time.perf_counter(); prev.free(); ph["free"] += time.perf_counter() - t
+    t = time.perf_counter(); st = b.rep_status; ph["rep_status"] += time.perf_counter() - t
+    t = time.perf_counter(); tot = 0
+    for s in range(8):
+        if pinned[i & 1][s] is not None and b.stream_bytes(s):
+            tot += b.copy_stream_into_async(s, pinned[i & 1][s].data_ptr(), pinned[i & 1][s].numel()); b.copy_offsets_into_async(s, offs[i & 1][s].data_ptr())
+    ph["enqueue copies"] += time.perf_counter() - t
+    prev = b
+ctx.wait_copies(); prev.free()
+wall = time.perf_counter() - T0
+print("pipelined ms/chunk", wall / n_steps * 1e3, "GB/s", tot * n_steps / wall / 1e9, {k: round(v / n_steps * 1e3, 2) for k, v in ph.items()})
