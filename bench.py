@@ -157,7 +157,7 @@ def run_reference_arm(args):
                        "time = slowest worker's loop); the Java jar cannot run here (no JVM)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": f"{per_step} replicates per step x {args.steps} steps of the same workload"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit_line(line)
 
 
 # ---- GPU side ----------------------------------------------------------------------------------------------------------------------
@@ -359,7 +359,7 @@ def extra_workloads(h, peaks, K, W):
     open(host1000, "wb").write(hb.replicate(1, int(ok[0])))
     hb.free()
     for db in (["-db", "exponential", "-dbr", "1.0"], ["-db", "simple"], ["-db", "none"]):
-        general(f"C4_guest_db_{db[1]}", "GuestTreeGen", ["-s", "5"] + db + ["-max", "100000", "-maxper", "100000", host1000, "0.3", "0.3", "0.3", "g"], h.args.c4_replicates, 2048, 4, 2,
+        general(f"C4_guest_db_{db[1]}", "GuestTreeGen", ["-s", "5"] + db + ["-max", "100000", "-maxper", "100000", host1000, "0.3", "0.3", "0.3", "g"], h.args.c4_replicates, 4096, 4, 2,
                 f"C4: GuestTreeGen {' '.join(db)} 0.3 0.3 0.3 on a 1000-leaf species tree (HostTreeGen -min 1000 -max 1000 1.0 7.0 0.05)")
     gd = os.path.join(tmp, "genes"); os.makedirs(gd)
     gt = h.ctx.run("GuestTreeGen", ["-s", "77", "-db", "none", host1000, "0.2", "0.2", "0.1", "g"], n=100, rng=sg.RNG_PHILOX, stream_mask=0b0010)
@@ -418,7 +418,27 @@ def extra_workloads(h, peaks, K, W):
     return out
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version line to stdout when NCCL_DEBUG is
+    set in the environment), so file descriptor 1 is pointed at stderr for the life of the process and the line goes to a private
+    duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n"); out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -532,7 +552,7 @@ def main():
             "clocks": clk,
             "workloads": workloads,
         }
-        print(json.dumps(line))
+        emit_line(line)
     if world > 1:
         h.dist.destroy_process_group()
 
