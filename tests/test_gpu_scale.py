@@ -442,3 +442,37 @@ def test_one_pass_general_engine_equals_two_pass(ctx, monkeypatch, tmp_path):
     for s in range(8):
         assert bytes(first.stream(s)) == bytes(again.stream(s))
     first.free(); again.free()
+
+
+def test_pipelined_caller_gets_the_bytes_of_separate_runs(ctx):
+    # The end-to-end pattern of bench.py: chunk i's outputs are copied to pinned host memory on the copy stream while chunk i+1
+    # computes and chunk i-1's buffers have just gone back to the engine's free list (large buffers are recycled between runs,
+    # csrc/engine.cu BlockCache). Every chunk must arrive as the bytes of a separate, synchronous run of the same replicates.
+    import hashlib
+    import torch
+    args = ["-s", "20260101", "-min", "100", "-max", "100", "-p", "0.8", "-a", "10000", "1.0", "5.0", "0.05", "bench"]
+    n = 4000                                   # ~45 MB per Newick stream: above the recycling threshold
+    want = []
+    for i in range(4):
+        b = ctx.run("HostTreeGen", args, n=n, rng=sg.RNG_PHILOX, offset=i * n, keep_on_device=True)
+        want.append([hashlib.sha256(b.stream(s)).hexdigest() for s in range(4)])
+        assert b.stream_bytes(0) > 32 << 20
+        b.free()
+    cap = 64 << 20
+    pinned = [[torch.empty(cap, dtype=torch.uint8, pin_memory=True) for _ in range(4)] for _ in range(2)]
+    sizes = [[0] * 4 for _ in range(2)]
+    got = [None] * 4
+    prev = None
+    for i in range(4):
+        b = ctx.run("HostTreeGen", args, n=n, rng=sg.RNG_PHILOX, offset=i * n, keep_on_device=True)
+        if prev is not None:
+            ctx.wait_copies()
+            got[i - 1] = [hashlib.sha256(pinned[(i - 1) & 1][s][:sizes[(i - 1) & 1][s]].numpy().tobytes()).hexdigest() for s in range(4)]
+            prev.free()
+        for s in range(4):
+            sizes[i & 1][s] = b.copy_stream_into_async(s, pinned[i & 1][s].data_ptr(), cap)
+        prev = b
+    ctx.wait_copies()
+    got[3] = [hashlib.sha256(pinned[1][s][:sizes[1][s]].numpy().tobytes()).hexdigest() for s in range(4)]
+    prev.free()
+    assert got == want
