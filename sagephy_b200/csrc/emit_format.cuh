@@ -17,7 +17,7 @@ __device__ __forceinline__ void put_blob(CountSink& s, const char*, int, int len
 // HOST= or the row's column) and its epoch once; measuring each number at every use was 15 % of the instructions of the write
 // kernels and 24 % of the finish kernel. The finish kernel now measures each once and keeps the result in the record's `pad`
 // word: bits 0-4 digits of f, then 3 bits each for number, sigma and epoch (0 = not recorded: negative, or more than 7 digits).
-__device__ __forceinline__ int len_hint(int v) { return (v >= 0 && v < 10000000) ? dec_len_u32((uint32_t)v) : 0; }
+__device__ __forceinline__ int len_hint(int v) { return (v >= 0 && v < 10000000) ? dec_len_u32_compact((uint32_t)v) : 0; }
 __device__ __forceinline__ int pack_pad(int nd, int number, int sigma, int epoch) { return nd | (len_hint(number) << 5) | (len_hint(sigma) << 8) | (len_hint(epoch) << 11); }
 __device__ __forceinline__ int pad_nd(int pad) { return pad & 31; }
 __device__ __forceinline__ int pad_num(int pad) { return (pad >> 5) & 7; }
@@ -58,7 +58,7 @@ __device__ __forceinline__ void decimal_of(const MathTables& T, double v, uint64
 static __device__ __noinline__ uint64_t decimal_of_packed(const unsigned long long* g, const double* p10, double v, int* e_nd) {
     MathTables T; T.g = g; T.p10 = p10;
     uint64_t f; int e; decimal_of(T, v, &f, &e);
-    *e_nd = (e & 0xffff) | ((e == kNoDigits ? 0 : dec_len_u64(f)) << 16);
+    *e_nd = (e & 0xffff) | ((e == kNoDigits ? 0 : dec_len_u64_compact(f)) << 16);
     return f;
 }
 

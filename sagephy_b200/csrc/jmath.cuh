@@ -317,28 +317,38 @@ SGP_HD void d2s_decimal(const MathTables& T, double v, uint64_t* f_out, int* e_o
 
 // Branch-free sums of comparisons: lanes of a warp print numbers of different lengths, and a comparison chain that compiles to
 // branches was 18 % of the instructions of the write kernels.
-// On the device: bit length -> floor(log10) estimate (x 1233 / 4096) -> one comparison with a power of ten from constant memory.
-// The sum of nine comparisons this replaces compiled to ~50 instructions per call site, and with some forty call sites inlined into
-// the formatting code it was 46 % of the finish kernel's instructions (static count) - the reason that kernel did not fit the
-// instruction cache.
+SGP_HD int dec_len_u32(uint32_t v) {
+    int n = 1 + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u);
+    if (v >= 100000u) n += (v >= 100000u) + (v >= 1000000u) + (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);
+    return n;
+}
+// The same in a third of the code, for the size pass: bit length -> floor(log10) estimate (x 1233 / 4096) -> one comparison with a
+// power of ten from constant memory. The sum of comparisons above compiles to ~50 instructions per call site, and with some forty
+// call sites inlined into the counting instantiation of the formatting code it was 46 % of the finish kernel's instructions
+// (static count) - the reason that kernel did not fit the instruction cache. The write kernels keep the sum: there the table load
+// (lanes index it differently) cost more than the instructions it saved (+3 % on C3, +5 % on the relaxer's emitter).
 #if defined(__CUDACC__)
 static __constant__ uint32_t kPow10U32[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u};
 #endif
-SGP_HD int dec_len_u32(uint32_t v) {
+SGP_HD int dec_len_u32_compact(uint32_t v) {
 #if defined(__CUDA_ARCH__)
     const uint32_t w = v | 1u;                                   // same number of digits as v, and 1 for v == 0
     const int t = ((32 - __clz((int)w)) * 1233) >> 12;          // floor(log10(w)) or one more
     return t + (w >= kPow10U32[t] ? 1 : 0);
 #else
-    int n = 1 + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u);
-    if (v >= 100000u) n += (v >= 100000u) + (v >= 1000000u) + (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);
-    return n;
+    return dec_len_u32(v);
 #endif
 }
 SGP_HD int dec_len_u64(uint64_t f) {
     if (f <= 0xffffffffull) return dec_len_u32((uint32_t)f);
     const uint64_t hi = f / 1000000000ull;          // < 2^35
     if (hi <= 0xffffffffull) return 9 + dec_len_u32((uint32_t)hi);
+    return 19 + (f >= 10000000000000000000ull);
+}
+SGP_HD int dec_len_u64_compact(uint64_t f) {
+    if (f <= 0xffffffffull) return dec_len_u32_compact((uint32_t)f);
+    const uint64_t hi = f / 1000000000ull;          // < 2^35
+    if (hi <= 0xffffffffull) return 9 + dec_len_u32_compact((uint32_t)hi);
     return 19 + (f >= 10000000000000000000ull);
 }
 SGP_HD int dec_len_i32(int v) { int n = 0; uint32_t u; if (v < 0) { n = 1; u = (uint32_t)(-(int64_t)v); } else u = (uint32_t)v; return n + dec_len_u32(u); }
@@ -396,8 +406,8 @@ template <class Sink> SGP_HD void put_u32_digits(Sink& s, uint32_t v, int n) {
     for (int i = 0; i < n; ++i) s.put(tmp[i]);
 }
 template <class Sink> SGP_HD void put_u32(Sink& s, uint32_t v) {
+    if (Sink::kCounts) { s.skip(dec_len_u32_compact(v)); return; }
     const int n = dec_len_u32(v);
-    if (Sink::kCounts) { s.skip(n); return; }
     put_u32_digits(s, v, n);
 }
 // values beyond 32 bits are rare (wide seeds): out of line, so that the common path stays small
