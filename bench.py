@@ -372,7 +372,10 @@ def extra_workloads(h, peaks, K, W):
     # the same forest handed over on the device (sgp_domain_run_on_batch): ingest kernels + K0 tables + the run, no gene-tree files
     gk = h.ctx.run("GuestTreeGen", ["-s", "77", "-db", "none", host1000, "0.2", "0.2", "0.1", os.path.join(tmp, "gene")], n=100, rng=sg.RNG_PHILOX, stream_mask=0b0010, flags=sg.FLAG_KEEP_TREES, keep_on_device=True)
     dargs = ["-s", "9", "-ig", "0.5", "-is", "0.5", "-max", "100000", "-maxper", "100000", host1000, "chained", "0.3", "0.3", "0.3", "d"]
-    h.torch.cuda.synchronize(); t0 = time.perf_counter()
+    # one untimed run first, like every other workload: the first run of a configuration sizes its vertex arena with a pilot pass, which
+    # for this latency-bound workload costs as much as the run itself
+    h.ctx.domain_on_batch(gk, dargs, n=h.args.c4_domain_replicates, rng=sg.RNG_PHILOX, offset=(h.world + h.rank) * h.args.c4_domain_replicates, keep_on_device=True).free()
+    h.barrier(); h.torch.cuda.synchronize(); t0 = time.perf_counter()
     cb = h.ctx.domain_on_batch(gk, dargs, n=h.args.c4_domain_replicates, rng=sg.RNG_PHILOX, offset=h.rank * h.args.c4_domain_replicates, keep_on_device=True)
     h.torch.cuda.synchronize(); chained_s = time.perf_counter() - t0
     chained_max, = h.allmax([chained_s]); chained_ok, = h.allsum([int(cb.summary().n_ok)])

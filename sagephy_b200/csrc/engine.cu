@@ -368,6 +368,7 @@ Context::~Context() {
         if (impl->copy) { cudaStreamSynchronize(impl->copy); cudaStreamDestroy(impl->copy); impl->copy = nullptr; }
         if (impl->mailbox) { cudaFreeHost(impl->mailbox); impl->mailbox = nullptr; }
         for (int i = 0; i < 8; ++i) if (impl->scratch_buf[i]) { cudaFree(impl->scratch_buf[i]); impl->scratch_buf[i] = nullptr; }
+        BlockCache::of(device).drop_unused();      // recycled buffers nobody holds go back to the driver with the context (live batches keep theirs)
     }
 }
 
