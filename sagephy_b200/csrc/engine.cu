@@ -26,8 +26,8 @@ const unsigned long long* d2s_g_table(); int d2s_g_table_len(); const double* p1
 
 namespace {
 
-// Device buffers come from the CUDA stream-ordered pool (release threshold = unlimited, see Context::Context), so
-// steady-state batches reuse memory instead of paying cudaMalloc/cudaFree per phase.
+// Small device buffers come from the CUDA stream-ordered pool (release threshold = unlimited, see Context::Context), large ones from
+// a per-device free list of cudaMalloc blocks (BlockCache below): steady-state batches make no driver allocation call.
 thread_local cudaStream_t g_alloc_stream = nullptr;
 // SGP_TRACE=1: host time stamps between the phases of a run (where does the host wait?), printed to stderr at the end of the run
 struct HostMarks {
@@ -37,12 +37,9 @@ struct HostMarks {
 };
 thread_local HostMarks g_marks;
 thread_local unsigned long long g_h2d_bytes = 0;      // host->device bytes of the current run (tables, constant strings, templates)
-// Size classes for large stream-ordered allocations. The sizes of a run's big buffers (vertex arena, records, output streams) differ
-// by a fraction of a percent from one batch to the next; the pool cannot serve a request from a free block that is a few KB too
-// small, so every batch made it map fresh memory - and that blocks the calling thread until ALL work in flight on the device has
-// drained, including a caller's device-to-host copies of the previous batch (measured: 3-100 ms per cudaMallocAsync inside the
-// end-to-end pipeline, none without the copies in flight). Rounded up to one of 64 classes per octave (< 1.6 % over-allocation)
-// consecutive batches ask for the same sizes and the pool hands the previous batch's blocks back.
+// Size classes of the large buffers. The sizes of a run's vertex arena, records and output streams differ by a fraction of a percent
+// from one batch to the next; rounded up to one of 64 classes per octave (< 1.6 % over-allocation) consecutive batches ask for the
+// same sizes and find the previous batch's blocks in the free list.
 inline size_t pool_size_class(size_t bytes) {
     if (bytes < (size_t)(1u << 20)) return bytes;
     size_t g = 1; while ((g << 6) < bytes) g <<= 1;          // bytes / 128 < g <= bytes / 64
@@ -50,7 +47,8 @@ inline size_t pool_size_class(size_t bytes) {
 }
 // Large device buffers (vertex arena, records, output streams: everything from kBigBytes up) do not go through the stream-ordered
 // pool at all. The pool serves a request that fits none of its free blocks by re-mapping physical memory, and that waits for ALL
-// work in flight on the device - a caller's device-to-host copies of the previous batch included (see pool_size_class); which
+// work in flight on the device - a caller's device-to-host copies of the previous batch included (measured: 3-100 ms per
+// cudaMallocAsync inside the end-to-end pipeline, 0.01 ms without copies in flight); which
 // requests fit depends on the history of the pool, and the stalls came and went with the order of the workloads. These buffers
 // are plain cudaMalloc blocks kept in a per-device free list instead: a request takes the smallest free block of at least its
 // size class (and at most 1.25 x), a free puts the block back - no driver call, no mapping, nothing to wait for. Reuse is safe in
