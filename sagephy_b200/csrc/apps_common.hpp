@@ -31,12 +31,12 @@ inline Parsed scan(const std::vector<std::string>& args, const Opt* table, int n
         for (int k = 0; k < n_opts; ++k) if (tok == table[k].shortn || tok == table[k].longn) { o = &table[k]; break; }
         if (o) {
             if (o->arity == 0) { p.val[o->shortn].push_back("true"); continue; }
-            if (i + o->arity >= args.size()) throw SgpError("Expected a value after parameter " + tok);
+            if (i + o->arity >= args.size()) throw SgpError("ParameterException: Expected a value after parameter " + tok);
             for (int k = 0; k < o->arity; ++k) { p.val[o->shortn].push_back(args[++i]); p.val_index[o->shortn] = (int)i; }
             continue;
         }
         const bool looks_numeric = tok.size() > 1 && tok[0] == '-' && ((tok[1] >= '0' && tok[1] <= '9') || tok[1] == '.');
-        if (tok.size() > 1 && tok[0] == '-' && !looks_numeric) throw SgpError("Unknown option: " + tok);
+        if (tok.size() > 1 && tok[0] == '-' && !looks_numeric) throw SgpError("ParameterException: Unknown option: " + tok);
         p.positional.push_back(tok);
     }
     return p;

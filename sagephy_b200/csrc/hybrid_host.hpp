@@ -28,7 +28,7 @@ namespace hybrid {
 
 struct Node { bool has_id = false; int id = 0; bool has_name = false; std::string name; int time_kind = 0; double time = 0; };   // time_kind: 0 none, 1 number, 2 other
 struct Edge { bool has_id = false; int id = 0; bool has_src = false, has_dst = false; int src = 0, dst = 0; };
-struct Graph { bool seen = false; int directed = -1; std::vector<Node> nodes; std::vector<Edge> edges; };
+struct Graph { int directed = -1; std::vector<Node> nodes; std::vector<Edge> edges; };
 
 inline bool ieq(const std::string& a, const char* b) {
     size_t i = 0; for (; i < a.size() && b[i]; ++i) if (std::tolower((unsigned char)a[i]) != std::tolower((unsigned char)b[i])) return false;
@@ -39,7 +39,7 @@ inline bool jspace(int c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 28 &
 
 struct Scanner {
     std::string q; size_t at = 0;
-    Graph g; int n_graphs = 0;
+    std::vector<Graph> graphs;                               // every top-level "graph [...]" is built (GMLFactory.getGraphs), the first one is used
     std::string deferred;                                    // first error of the GMLGraph / GMLNode / GMLEdge constructors (they run after the whole text has been parsed)
     void defer(const std::string& why) { if (deferred.empty()) deferred = "uc.sgp.sagephy.io.GMLIOException: " + why; }
     int peek() const { return at < q.size() ? (unsigned char)q[at] : -1; }
@@ -47,7 +47,7 @@ struct Scanner {
         throw SgpError("uc.sgp.sagephy.io.GMLIOException: Error parsing GML file. First 100 remaining unparsed characters:\n" + q.substr(std::min(at, q.size()), 100) +
                        "\nCaused by: uc.sgp.sagephy.io.GMLIOException: " + why);
     }
-    // scope: 0 top level, 1 first graph, 2 node of it, 3 edge of it, 4 anything else (skipped, but still checked for syntax)
+    // scope: 0 top level, 1 a graph, 2 a node of it, 3 an edge of it, 4 anything else (skipped, but still checked for syntax)
     void list(int scope, Node* nd, Edge* ed) {
         for (;;) {
             while (jspace(peek())) ++at;
@@ -59,16 +59,16 @@ struct Scanner {
             if (peek() == '[') {
                 ++at;
                 int inner = 4; Node n; Edge e;
-                if (scope == 0 && ieq(key, "graph")) { inner = n_graphs++ == 0 ? 1 : 4; if (inner == 1) g.seen = true; }
+                if (scope == 0 && ieq(key, "graph")) { inner = 1; graphs.emplace_back(); }
                 else if (scope == 1 && ieq(key, "node")) inner = 2;
                 else if (scope == 1 && ieq(key, "edge")) inner = 3;
                 list(inner, &n, &e);
                 if (peek() != ']') fail("Error parsing GML file. Expected ].");
                 ++at;
-                if (inner == 2) g.nodes.push_back(n);
+                if (inner == 2) graphs.back().nodes.push_back(n);
                 if (inner == 3) {
                     if (!e.has_src || !e.has_dst) defer("Invalid GML edge with ID" + (e.has_id ? std::to_string(e.id) : std::string("null")) + ": source and target attributes are required.");
-                    else g.edges.push_back(e);
+                    else graphs.back().edges.push_back(e);
                 }
                 if (scope >= 1 && scope <= 3 && inner == 4) typed(scope, key, 'L', "", nd, ed);
                 continue;
@@ -97,14 +97,18 @@ struct Scanner {
     // the typed keys of GMLGraph / GMLNode / GMLEdge (first occurrence wins, a wrong type raises)
     void typed(int scope, const std::string& key, char kind, const std::string& v, Node* nd, Edge* ed) {
         auto want = [&](char k, const char* what, const char* type) { if (kind != k) defer(std::string("Invalid attribute for GML ") + what + ": expected " + type + "."); };
-        if (scope == 1) {
-            if (ieq(key, "id")) want('I', "ID", "integer");
+        if (scope == 0) {
+            if (ieq(key, "graph")) want('L', "graph", "list [...]");
+        } else if (scope == 1) {
+            if (ieq(key, "node")) want('L', "node", "list [...]");
+            else if (ieq(key, "edge")) want('L', "edge", "list [...]");
+            else if (ieq(key, "id")) want('I', "ID", "integer");
             else if (ieq(key, "name")) want('S', "name", "string");
             else if (ieq(key, "label")) want('S', "label", "string");
             else if (ieq(key, "comment")) want('S', "comment", "string");
             else if (ieq(key, "creator")) want('S', "Creator", "string");
             else if (ieq(key, "version")) want('I', "version", "integer");
-            else if (ieq(key, "directed")) { want('I', "directed", "integer"); if (g.directed < 0) g.directed = std::atoi(v.c_str()) != 0; }
+            else if (ieq(key, "directed")) { want('I', "directed", "integer"); Graph& g = graphs.back(); if (kind == 'I' && g.directed < 0) g.directed = std::atoi(v.c_str()) != 0; }
         } else if (scope == 2) {
             if (ieq(key, "id")) { want('I', "ID", "integer"); if (!nd->has_id) { nd->has_id = true; nd->id = std::atoi(v.c_str()); } }
             else if (ieq(key, "name")) { want('S', "name", "string"); if (!nd->has_name) { nd->has_name = true; nd->name = v; } }
@@ -152,8 +156,8 @@ inline Graph read_first_graph(const std::string& gml_text) {
     sc.list(0, nullptr, nullptr);
     if (sc.peek() >= 0) sc.fail("GML file has trailing characters after supposed end.");
     if (!sc.deferred.empty()) throw SgpError(sc.deferred);
-    if (!sc.g.seen) throw SgpError("java.lang.IndexOutOfBoundsException: Index 0 out of bounds for length 0");
-    return sc.g;
+    if (sc.graphs.empty()) throw SgpError("java.lang.IndexOutOfBoundsException: Index 0 out of bounds for length 0");
+    return sc.graphs.front();
 }
 
 // new GuestTreeInHybridGraphCreator(...) and the first createGuestVertex; never returns.

@@ -79,6 +79,10 @@ BAD_GRAPHS = {
     "type_of_directed": swap(ALLO, "directed 1", "directed \"yes\""),
     # lines are queued without their line breaks: "time 1.5" + "edge" reads as the number 1.5e
     "token_runs_into_next_line": "graph [\ndirected 1\nnode [ id 0 time 1.5\nedge 1 ]\n]",
+    "node_is_not_a_list": swap(ALLO, "node [ id 7 name \"H\" time 0.0 ]", "node \"H\""),
+    "graph_is_not_a_list": "graph 5 " + ALLO,
+    # GMLFactory.getGraphs builds every graph before the first one is used
+    "second_graph_is_broken": ALLO + "graph [ node [ id \"x\" ] ]",
 }
 
 
@@ -134,3 +138,31 @@ def test_parse_probe_accepts_ordinary_runs(tmp_path):
     assert rc == sg.STATUS_USAGE and text == ""
     rc, text = sg.probe_parse_app("GuestTreeGen", ["-s", "1", host, "-0.3", "0.3", "0.1", "o"])
     assert rc != 0 and "Cannot have rate less than 0." in text
+
+
+def test_mutated_networks_get_the_same_answer_from_product_and_oracle():
+    # two independent readers of the same grammar (a one-pass scanner in the product, a key-value tree like the Java in the oracle) on
+    # random edits of valid networks: deleted spans, inserted and substituted tokens
+    import random
+    rng = random.Random(20261020)
+    tokens = ['[', ']', '"', ' ', '\n', 'id', 'time', 'node', 'edge', 'source', 'target', 'directed', 'graph', 'name', '1', '0', '7', '1.5', '-', 'e', '.',
+              'label', 'graphics', '#', '2.0', '9', 'x']
+    checked = 0
+    while checked < 1500:
+        t = list(rng.choice([ALLO, AUTO]))
+        for _ in range(rng.choice([1, 1, 2, 3])):
+            k = rng.randrange(len(t)); op = rng.random()
+            if op < 0.35:
+                del t[k:k + rng.choice([1, 1, 2, 5, 12])]
+            elif op < 0.7:
+                t[k:k] = list(rng.choice(tokens))
+            else:
+                t[k:k + rng.choice([1, 3])] = list(rng.choice(tokens))
+        text = "".join(t)
+        if not text.strip():
+            continue
+        args = ["-s", "4", "-hybrid", "0.2", "2.0", "0.5", text, "0.3", "0.2", "0.0", "out"]
+        rc, got = sg.probe_parse_app("GuestTreeGen", args)
+        want = oracle_run("GuestTreeGen", args)
+        assert rc != 0 and got == want["stderr"] and want["files"] == {}, (text, got, want["stderr"])
+        checked += 1
