@@ -257,6 +257,10 @@ class Harness:
         self.barrier(); e_wall = time.perf_counter() - t0
         wall_max, = self.allmax([e_wall]); ok_sum, d2h_sum, h2d_sum = self.allsum([e_ok, d2h, h2d])
         del pinned, offs
+        try:          # give the pinned pages back to the OS: torch caches them, and eight ranks times every workload's buffers add up
+            torch._C._host_emptyCache()
+        except Exception:
+            pass
         return {"value": ok_sum / wall_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d_sum / e_steps / self.world), "d2h_bytes_per_step": int(d2h_sum / e_steps / self.world),
                 "replicates_per_gpu_per_step": ne, "steps": e_steps, "d2h_gbs_per_gpu": d2h_sum / self.world / wall_max * 1e-9}
 
