@@ -166,3 +166,81 @@ def test_mutated_networks_get_the_same_answer_from_product_and_oracle():
         want = oracle_run("GuestTreeGen", args)
         assert rc != 0 and got == want["stderr"] and want["files"] == {}, (text, got, want["stderr"])
         checked += 1
+
+
+def _gml_syntax_ok(text):
+    """Third, independent reader of the grammar of io/GMLReader.java:62-231 (Python, syntax only): does the text parse?"""
+    ws = set(" \t\n\x0b\x0c\r\x1c\x1d\x1e\x1f")
+    lines = text.strip(''.join(chr(c) for c in range(33))).split("\n")
+    kept = []
+    for ln in lines:
+        first = next((c for c in ln if c not in ws), None)
+        if first != "#":
+            kept.append(ln)
+    q = "".join(kept); n = len(q); pos = 0
+
+    def skip():
+        nonlocal pos
+        while pos < n and q[pos] in ws:
+            pos += 1
+
+    def plist():
+        nonlocal pos
+        while True:
+            skip()
+            if pos >= n or q[pos] == "]":
+                return True
+            if not (q[pos].isascii() and q[pos].isalpha()):
+                return False
+            pos += 1
+            while pos < n and q[pos].isascii() and q[pos].isalnum():
+                pos += 1
+            skip()
+            if pos < n and q[pos] == "[":
+                pos += 1
+                if not plist() or pos >= n or q[pos] != "]":
+                    return False
+                pos += 1
+            elif pos < n and q[pos] == '"':
+                end = q.find('"', pos + 1)
+                if end < 0:
+                    return False
+                pos = end + 1
+            else:
+                start = pos
+                while pos < n and q[pos] in "0123456789.Ee+-":
+                    pos += 1
+                tok = q[start:pos]
+                try:
+                    if "." in tok:
+                        float(tok)
+                        if tok.lower().lstrip("+-").startswith(("inf", "nan")):
+                            return False
+                    else:
+                        if not tok or not tok.lstrip("+-").isdigit() or len(tok) - len(tok.lstrip("+-")) > 1 or not -2 ** 31 <= int(tok) < 2 ** 31:
+                            return False
+                except ValueError:
+                    return False
+    return plist() and pos >= n
+
+
+def test_gml_syntax_verdict_agrees_with_an_independent_reader():
+    import random
+    rng = random.Random(7)
+    tokens = ['[', ']', '"', ' ', '\n', 'id', 'time', 'node', 'edge', 'graph', '1', '1.5', '-', 'e', '.', '#', 'x', '+', '2e3', '.5']
+    for k in range(1200):
+        t = list(rng.choice([ALLO, AUTO]))
+        for _ in range(rng.choice([1, 2, 3])):
+            i = rng.randrange(len(t)); op = rng.random()
+            if op < 0.4:
+                del t[i:i + rng.choice([1, 2, 7])]
+            else:
+                t[i:i] = list(rng.choice(tokens))
+        text = "".join(t)
+        if not text.strip():
+            continue
+        err = oracle_run("GuestTreeGen", ["-s", "4", "-hybrid", "0.2", "2.0", "0.5", text, "0.3", "0.2", "0.0", "out"])["stderr"]
+        if err.startswith("ParameterException"):          # the mutated text begins with '-' and is taken for an option
+            continue
+        syntax_error = err.startswith("uc.sgp.sagephy.io.GMLIOException: Error parsing GML file.")
+        assert syntax_error == (not _gml_syntax_ok(text)), (text, err[:200])
